@@ -1,0 +1,652 @@
+// C-ABI layer (include/asr_b200.h): argument checking, workspace carving and kernel orchestration.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/asr_b200.h"
+#include "kernels.h"
+
+using namespace asr;
+
+namespace {
+
+inline int conv_len(int n) { return (n - 3) / 2 + 1; }
+
+// Bump allocator over the caller's workspace (base == nullptr: size-only dry run).
+struct Bump {
+  uint8_t* base;
+  size_t off = 0;
+  explicit Bump(void* b) : base(static_cast<uint8_t*>(b)) {}
+  template <class T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct EncodeWs {
+  bf16 *y1, *z, *xn, *qkv, *att, *ff, *enc_bf16;
+  float* h;
+  void carve(Bump& b, const AsrConfig& c, int B, int T) {
+    const int F1 = conv_len(c.input_dim), T1 = conv_len(T), F2 = conv_len(F1), T2 = conv_len(T1);
+    const size_t M = size_t(B) * T2, D = c.embedding_dim;
+    y1 = b.take<bf16>(size_t(B) * T1 * F1 * 64);
+    z = b.take<bf16>(M * F2 * 64);
+    h = b.take<float>(M * D);
+    xn = b.take<bf16>(M * D);
+    qkv = b.take<bf16>(M * 3 * D);
+    att = b.take<bf16>(M * D);
+    ff = b.take<bf16>(M * c.ff_dim);
+    enc_bf16 = b.take<bf16>(M * D);
+  }
+};
+
+struct DecFwdWs {
+  bf16 *enc_bf16, *ckv, *xn, *qkv, *qc, *att, *ff;
+  float* h;
+  void carve(Bump& b, const AsrConfig& c, int B, int Tp, int L) {
+    const size_t M = size_t(B) * Tp, R = size_t(B) * L, D = c.embedding_dim;
+    enc_bf16 = b.take<bf16>(M * D);
+    ckv = b.take<bf16>(size_t(c.decoder_num_layers) * M * 2 * D);
+    h = b.take<float>(R * D);
+    xn = b.take<bf16>(R * D);
+    qkv = b.take<bf16>(R * 3 * D);
+    qc = b.take<bf16>(R * D);
+    att = b.take<bf16>(R * D);
+    ff = b.take<bf16>(R * c.ff_dim);
+  }
+};
+
+struct GreedyWs {
+  bf16 *enc_bf16, *ckv, *cache;
+  float *h, *qkv, *att, *qc, *ff, *logits;
+  int32_t *step, *finished;
+  void carve(Bump& b, const AsrConfig& c, int B, int Tp, int L) {
+    const size_t M = size_t(B) * Tp, D = c.embedding_dim;
+    const size_t vpad = (size_t(c.vocab_size) + 63) / 64 * 64;
+    enc_bf16 = b.take<bf16>(M * D);
+    ckv = b.take<bf16>(size_t(c.decoder_num_layers) * M * 2 * D);
+    cache = b.take<bf16>(size_t(c.decoder_num_layers) * B * L * 2 * D);
+    h = b.take<float>(size_t(B) * D);
+    qkv = b.take<float>(size_t(B) * 3 * D);
+    att = b.take<float>(size_t(B) * D);
+    qc = b.take<float>(size_t(B) * D);
+    ff = b.take<float>(size_t(B) * c.ff_dim);
+    logits = b.take<float>(size_t(B) * vpad);
+    step = b.take<int32_t>(1);
+    finished = b.take<int32_t>(B);
+  }
+};
+
+struct GraphKey {
+  void* ws = nullptr; const void* enc = nullptr; void* tokens = nullptr; void* n_tokens = nullptr;
+  void* step_logits = nullptr; const void* first = nullptr; int B = 0, Tp = 0, L = 0, stop = 0;
+  bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
+};
+
+__global__ void dec_init_kernel(int32_t* tokens, int ld_tok, int32_t* n_tokens, int32_t* finished, int32_t* step,
+                                int B, int L, int bos, const int32_t* first_tokens) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) *step = 0;
+  if (b < B) {
+    tokens[size_t(b) * ld_tok] = first_tokens ? first_tokens[b] : bos;
+    finished[b] = 0;
+    if (n_tokens) n_tokens[b] = L + 1;
+  }
+}
+
+}  // namespace
+
+struct AsrHandle {
+  AsrConfig cfg;
+  AsrWeights w;
+  std::vector<AsrEncoderLayerWeights> enc;
+  std::vector<AsrDecoderLayerWeights> dec;
+  bool loaded = false;
+  cudaGraphExec_t graph_exec = nullptr;
+  GraphKey graph_key;
+};
+
+namespace {
+
+int check_cfg(const AsrConfig& c) {
+  if (c.vocab_size <= 0 || c.input_dim < 7 || c.embedding_dim <= 0 || c.decoder_seq_len <= 0 ||
+      c.encoder_seq_len <= 0 || c.encoder_num_layers < 0 || c.decoder_num_layers < 0 || c.num_heads <= 0 ||
+      c.ff_dim <= 0)
+    return set_error(ASR_E_INVALID, "asr_create: non-positive dimension in config");
+  if (c.embedding_dim != 64 * c.num_heads)
+    return set_error(ASR_E_UNSUPPORTED, "unsupported config: head_dim = %d/%d, only head_dim 64 is implemented",
+                     c.embedding_dim, c.num_heads);
+  if (c.embedding_dim % 128 != 0 || c.embedding_dim > 1024)
+    return set_error(ASR_E_UNSUPPORTED, "unsupported config: embedding_dim %d must be a multiple of 128, <= 1024",
+                     c.embedding_dim);
+  if (c.ff_dim % 64 != 0) return set_error(ASR_E_UNSUPPORTED, "unsupported config: ff_dim %d %% 64 != 0", c.ff_dim);
+  return 0;
+}
+
+int gemm(const bf16* X, int ldx, const void* W, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
+  return launch_gemm_tc(X, ldx, static_cast<const bf16*>(W), K, M, N, K, ep, s);
+}
+
+// x (bf16, normalised) -> self attention block output added to the fp32 residual stream h (in place)
+int self_attention_block(const AsrConfig& c, const AsrMhaWeights& w, const bf16* xn, bf16* qkv, bf16* att, float* h,
+                         int B, int S, int causal, const uint8_t* valid, const int32_t* k_lens, cudaStream_t s) {
+  const int D = c.embedding_dim, M = B * S;
+  GemmEpilogue e1;
+  e1.bias = w.b_qkv; e1.out_bf16 = qkv; e1.ld_bf16 = 3 * D;
+  if (int rc = gemm(xn, D, w.w_qkv, M, 3 * D, D, e1, s)) return rc;
+  AttnParams a;
+  a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D;
+  a.ldq = a.ldk = a.ldv = 3 * D;
+  a.q_batch_stride = a.k_batch_stride = a.v_batch_stride = (long long)S * 3 * D;
+  a.out = att; a.ldo = D; a.o_batch_stride = (long long)S * D;
+  a.B = B; a.H = c.num_heads; a.Sq = S; a.Sk = S;
+  a.scale = 1.0f / sqrtf((float)D);
+  a.causal = causal; a.q_valid = valid; a.k_valid = valid; a.k_lens = k_lens;
+  if (int rc = launch_attention_tc(a, s)) return rc;
+  GemmEpilogue e2;
+  e2.bias = w.b_out; e2.residual = h; e2.ld_res = D; e2.out_f32 = h; e2.ld_f32 = D;
+  return gemm(att, D, w.w_out, M, D, D, e2, s);
+}
+
+int ffn_block(const AsrConfig& c, const AsrFfnWeights& w, const bf16* xn, bf16* ff, float* h, int M, cudaStream_t s) {
+  const int D = c.embedding_dim, FF = c.ff_dim;
+  GemmEpilogue e1;
+  e1.bias = w.b1; e1.relu = 1; e1.out_bf16 = ff; e1.ld_bf16 = FF;
+  if (int rc = gemm(xn, D, w.w1, M, FF, D, e1, s)) return rc;
+  GemmEpilogue e2;
+  e2.bias = w.b2; e2.residual = h; e2.ld_res = D; e2.out_f32 = h; e2.ld_f32 = D;
+  return gemm(ff, FF, w.w2, M, D, FF, e2, s);
+}
+
+// cross-attention K/V of every decoder layer, once per utterance: ckv[l] = enc * [Wk; Wv]^T + b  (bf16 [M, 2D])
+int cross_kv(const AsrHandle* h, const bf16* enc_bf16, bf16* ckv, int M, cudaStream_t s) {
+  const int D = h->cfg.embedding_dim;
+  for (int l = 0; l < h->cfg.decoder_num_layers; ++l) {
+    const AsrMhaWeights& w = h->dec[l].cross_attn;
+    GemmEpilogue e;
+    e.bias = w.b_qkv + D;
+    e.out_bf16 = ckv + size_t(l) * M * 2 * D;
+    e.ld_bf16 = 2 * D;
+    if (int rc = gemm(enc_bf16, D, static_cast<const bf16*>(w.w_qkv) + size_t(D) * D, M, 2 * D, D, e, s)) return rc;
+  }
+  return 0;
+}
+
+int greedy_step(const AsrHandle* h, const GreedyWs& ws, int B, int Tp, int L, int stop_at_eos, int32_t* tokens,
+                int32_t* n_tokens, float* step_logits, cudaStream_t s) {
+  const AsrConfig& c = h->cfg;
+  const int D = c.embedding_dim, FF = c.ff_dim, H = c.num_heads;
+  const float scale = 1.0f / sqrtf((float)D);
+  const size_t M = size_t(B) * Tp;
+  for (int l = 0; l < c.decoder_num_layers; ++l) {
+    const AsrDecoderLayerWeights& w = h->dec[l];
+    bf16* cache = ws.cache + size_t(l) * B * L * 2 * D;
+    const bf16* ckv = ws.ckv + size_t(l) * M * 2 * D;
+    {  // LN1 -> packed QKV; K/V rows appended to the cache (model.py:67-68, layers.py:16-18)
+      DecLinear p;
+      p.x = ws.h; p.ldx = D; p.ln_gamma = w.norm1.gamma; p.ln_beta = w.norm1.beta;
+      p.w = static_cast<const bf16*>(w.self_attn.w_qkv); p.bias = w.self_attn.b_qkv;
+      p.B = B; p.N = 3 * D; p.K = D; p.out = ws.qkv; p.ldo = 3 * D;
+      p.kv_cache = cache; p.kv_col0 = D; p.kv_rows = L; p.step = ws.step;
+      if (int rc = launch_dec_linear(p, s)) return rc;
+    }
+    {  // causal self attention over the cache rows 0..t
+      DecAttn a;
+      a.q = ws.qkv; a.ldq = 3 * D; a.k = cache; a.v = cache + D; a.ldkv = 2 * D;
+      a.kv_batch_stride = (long long)L * 2 * D; a.n_keys = L; a.step = ws.step;
+      a.out = ws.att; a.ldo = D; a.B = B; a.H = H; a.scale = scale;
+      if (int rc = launch_dec_attention(a, s)) return rc;
+    }
+    {  // out projection + residual
+      DecLinear p;
+      p.x = ws.att; p.ldx = D; p.w = static_cast<const bf16*>(w.self_attn.w_out); p.bias = w.self_attn.b_out;
+      p.B = B; p.N = D; p.K = D; p.out = ws.h; p.ldo = D; p.residual = ws.h; p.ld_res = D;
+      if (int rc = launch_dec_linear(p, s)) return rc;
+    }
+    {  // LN2 -> cross-attention query (model.py:70-71)
+      DecLinear p;
+      p.x = ws.h; p.ldx = D; p.ln_gamma = w.norm2.gamma; p.ln_beta = w.norm2.beta;
+      p.w = static_cast<const bf16*>(w.cross_attn.w_qkv); p.bias = w.cross_attn.b_qkv;
+      p.B = B; p.N = D; p.K = D; p.out = ws.qc; p.ldo = D;
+      if (int rc = launch_dec_linear(p, s)) return rc;
+    }
+    {  // unmasked cross attention over the precomputed encoder K/V
+      DecAttn a;
+      a.q = ws.qc; a.ldq = D; a.k = ckv; a.v = ckv + D; a.ldkv = 2 * D;
+      a.kv_batch_stride = (long long)Tp * 2 * D; a.n_keys = Tp; a.step = nullptr;
+      a.out = ws.att; a.ldo = D; a.B = B; a.H = H; a.scale = scale;
+      if (int rc = launch_dec_attention(a, s)) return rc;
+    }
+    {
+      DecLinear p;
+      p.x = ws.att; p.ldx = D; p.w = static_cast<const bf16*>(w.cross_attn.w_out); p.bias = w.cross_attn.b_out;
+      p.B = B; p.N = D; p.K = D; p.out = ws.h; p.ldo = D; p.residual = ws.h; p.ld_res = D;
+      if (int rc = launch_dec_linear(p, s)) return rc;
+    }
+    {  // LN3 -> FFN (model.py:73-74)
+      DecLinear p;
+      p.x = ws.h; p.ldx = D; p.ln_gamma = w.norm3.gamma; p.ln_beta = w.norm3.beta;
+      p.w = static_cast<const bf16*>(w.ffn.w1); p.bias = w.ffn.b1; p.relu = 1;
+      p.B = B; p.N = FF; p.K = D; p.out = ws.ff; p.ldo = FF;
+      if (int rc = launch_dec_linear(p, s)) return rc;
+    }
+    {
+      DecLinear p;
+      p.x = ws.ff; p.ldx = FF; p.w = static_cast<const bf16*>(w.ffn.w2); p.bias = w.ffn.b2;
+      p.B = B; p.N = D; p.K = FF; p.out = ws.h; p.ldo = D; p.residual = ws.h; p.ld_res = D;
+      if (int rc = launch_dec_linear(p, s)) return rc;
+    }
+  }
+  const int vpad = (c.vocab_size + 63) / 64 * 64;
+  {  // classifier WITHOUT the final LayerNorm (model.py:142)
+    DecLinear p;
+    p.x = ws.h; p.ldx = D; p.w = static_cast<const bf16*>(h->w.classifier_w);
+    p.B = B; p.N = c.vocab_size; p.K = D; p.out = ws.logits; p.ldo = vpad;
+    if (int rc = launch_dec_linear(p, s)) return rc;
+  }
+  DecSelect sel;
+  sel.logits = ws.logits; sel.ld = vpad; sel.V = c.vocab_size; sel.B = B;
+  sel.tokens = tokens; sel.ld_tok = L + 1; sel.n_tokens = n_tokens; sel.finished = ws.finished; sel.step = ws.step;
+  sel.step_logits = step_logits; sel.L = L; sel.eos = c.eos_token_id; sel.pad = c.pad_token_id;
+  sel.stop_at_eos = stop_at_eos;
+  return launch_dec_select_embed(sel, h->w.embedding, h->w.dec_pe, D, ws.h, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* asr_last_error(void) { return last_error(); }
+int asr_version(void) { return 1; }
+
+int asr_create(const AsrConfig* cfg, AsrHandle** out) {
+  if (!cfg || !out) return set_error(ASR_E_INVALID, "asr_create: null argument");
+  if (int rc = check_cfg(*cfg)) return rc;
+  AsrHandle* h = new (std::nothrow) AsrHandle();
+  if (!h) return set_error(ASR_E_INVALID, "asr_create: out of host memory");
+  h->cfg = *cfg;
+  *out = h;
+  return 0;
+}
+
+void asr_destroy(AsrHandle* h) {
+  if (!h) return;
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  delete h;
+}
+
+int asr_load_weights(AsrHandle* h, const AsrWeights* w) {
+  if (!h || !w) return set_error(ASR_E_INVALID, "asr_load_weights: null argument");
+  if ((h->cfg.encoder_num_layers && !w->enc_layers) || (h->cfg.decoder_num_layers && !w->dec_layers))
+    return set_error(ASR_E_INVALID, "asr_load_weights: missing layer tables");
+  h->w = *w;
+  h->enc.assign(w->enc_layers, w->enc_layers + h->cfg.encoder_num_layers);
+  h->dec.assign(w->dec_layers, w->dec_layers + h->cfg.decoder_num_layers);
+  h->w.enc_layers = h->enc.data();
+  h->w.dec_layers = h->dec.data();
+  h->loaded = true;
+  if (h->graph_exec) {
+    cudaGraphExecDestroy(h->graph_exec);
+    h->graph_exec = nullptr;
+  }
+  return 0;
+}
+
+int asr_workspace_bytes(const AsrHandle* h, int B, int T, int L, size_t* bytes) {
+  if (!h || !bytes || B < 0 || T < 7 || L <= 0) return set_error(ASR_E_INVALID, "asr_workspace_bytes: bad argument");
+  const int Tp = conv_len(conv_len(T));
+  size_t need = 0;
+  { Bump b(nullptr); EncodeWs w; w.carve(b, h->cfg, B, T); need = b.off > need ? b.off : need; }
+  { Bump b(nullptr); DecFwdWs w; w.carve(b, h->cfg, B, Tp, L); need = b.off > need ? b.off : need; }
+  { Bump b(nullptr); GreedyWs w; w.carve(b, h->cfg, B, Tp, L); need = b.off > need ? b.off : need; }
+  *bytes = need + 256;
+  return 0;
+}
+
+static int encoder_core(AsrHandle* h, const EncodeWs& w, int B, int T2, const int32_t* enc_lens, float* enc_out,
+                        cudaStream_t s) {
+  const AsrConfig& c = h->cfg;
+  const int F2 = conv_len(conv_len(c.input_dim));
+  const int D = c.embedding_dim, M = B * T2, Kin = 64 * F2;
+  {  // _lin_in + positional encoding (model.py:47)
+    GemmEpilogue e;
+    e.bias = h->w.lin_in_b; e.rowvec = h->w.enc_pe; e.rowvec_period = T2; e.ld_rowvec = D;
+    e.out_f32 = w.h; e.ld_f32 = D;
+    if (int rc = gemm(w.z, Kin, h->w.lin_in_w, M, D, Kin, e, s)) return rc;
+  }
+  for (int l = 0; l < c.encoder_num_layers; ++l) {
+    const AsrEncoderLayerWeights& lw = h->enc[l];
+    if (int rc = launch_layernorm(w.h, lw.norm1.gamma, lw.norm1.beta, M, D, 1e-5f, nullptr, w.xn, s)) return rc;
+    if (int rc = self_attention_block(c, lw.attn, w.xn, w.qkv, w.att, w.h, B, T2, 0, nullptr, enc_lens, s)) return rc;
+    if (int rc = launch_layernorm(w.h, lw.norm2.gamma, lw.norm2.beta, M, D, 1e-5f, nullptr, w.xn, s)) return rc;
+    if (int rc = ffn_block(c, lw.ffn, w.xn, w.ff, w.h, M, s)) return rc;
+  }
+  return launch_layernorm(w.h, h->w.enc_norm_out.gamma, h->w.enc_norm_out.beta, M, D, 1e-5f, enc_out, nullptr, s);
+}
+
+int asr_encode(AsrHandle* h, const float* spectrum, int B, int T, const int32_t* enc_lens, void* ws, size_t ws_bytes,
+               float* enc_out, asr_stream_t stream) {
+  if (!h || !h->loaded) return set_error(ASR_E_INVALID, "asr_encode: weights not loaded");
+  if (B == 0) return 0;
+  if (!spectrum || !enc_out || !ws || B < 0) return set_error(ASR_E_INVALID, "asr_encode: null argument");
+  const AsrConfig& c = h->cfg;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (T < 7) return set_error(ASR_E_INVALID, "asr_encode: T=%d too short for two stride-2 convs", T);
+  const int F1 = conv_len(c.input_dim), T1 = conv_len(T), T2 = conv_len(T1);
+  if (T2 > c.encoder_seq_len)
+    return set_error(ASR_E_INVALID, "asr_encode: %d encoder frames exceed encoder_seq_len %d (positional buffer)", T2,
+                     c.encoder_seq_len);
+  Bump bump(ws);
+  EncodeWs w;
+  w.carve(bump, c, B, T);
+  if (bump.off > ws_bytes) return set_error(ASR_E_WORKSPACE, "asr_encode: workspace %zu < %zu bytes", ws_bytes, bump.off);
+  if (int rc = launch_conv1(spectrum, h->w.conv1_w, h->w.conv1_b, B, c.input_dim, T, w.y1, s)) return rc;
+  if (int rc = launch_conv2(w.y1, static_cast<const bf16*>(h->w.conv2_wfrag), h->w.conv2_b, B, F1, T1, w.z, s)) return rc;
+  return encoder_core(h, w, B, T2, enc_lens, enc_out, s);
+}
+
+int asr_encoder_forward(AsrHandle* h, const void* z_bf16, int B, int Tp, const int32_t* enc_lens, void* ws,
+                        size_t ws_bytes, float* enc_out, asr_stream_t stream) {
+  if (!h || !h->loaded) return set_error(ASR_E_INVALID, "asr_encoder_forward: weights not loaded");
+  if (B == 0) return 0;
+  if (!z_bf16 || !enc_out || !ws || B < 0 || Tp <= 0) return set_error(ASR_E_INVALID, "asr_encoder_forward: bad argument");
+  const AsrConfig& c = h->cfg;
+  if (Tp > c.encoder_seq_len)
+    return set_error(ASR_E_INVALID, "asr_encoder_forward: %d frames exceed encoder_seq_len %d", Tp, c.encoder_seq_len);
+  Bump bump(ws);
+  EncodeWs w;
+  w.carve(bump, c, B, 4 * Tp + 3);   // smallest T with subsampled length Tp; same layout as asr_encode
+  if (bump.off > ws_bytes)
+    return set_error(ASR_E_WORKSPACE, "asr_encoder_forward: workspace %zu < %zu bytes", ws_bytes, bump.off);
+  w.z = const_cast<bf16*>(static_cast<const bf16*>(z_bf16));
+  return encoder_core(h, w, B, Tp, enc_lens, enc_out, static_cast<cudaStream_t>(stream));
+}
+
+int asr_decoder_forward(AsrHandle* h, const float* enc_out, int B, int Tp, const int32_t* text, const uint8_t* valid,
+                        int L, void* ws, size_t ws_bytes, float* logits, asr_stream_t stream) {
+  if (!h || !h->loaded) return set_error(ASR_E_INVALID, "asr_decoder_forward: weights not loaded");
+  if (B == 0 || L == 0) return 0;
+  if (!enc_out || !text || !logits || !ws || B < 0 || Tp <= 0 || L < 0)
+    return set_error(ASR_E_INVALID, "asr_decoder_forward: bad argument");
+  const AsrConfig& c = h->cfg;
+  if (L > c.decoder_seq_len)
+    return set_error(ASR_E_INVALID, "asr_decoder_forward: L=%d exceeds decoder_seq_len %d", L, c.decoder_seq_len);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Bump bump(ws);
+  DecFwdWs w;
+  w.carve(bump, c, B, Tp, L);
+  if (bump.off > ws_bytes)
+    return set_error(ASR_E_WORKSPACE, "asr_decoder_forward: workspace %zu < %zu bytes", ws_bytes, bump.off);
+  const int D = c.embedding_dim, M = B * Tp, R = B * L;
+  if (int rc = launch_f32_to_bf16(enc_out, w.enc_bf16, size_t(M) * D, s)) return rc;
+  if (int rc = cross_kv(h, w.enc_bf16, w.ckv, M, s)) return rc;
+  if (int rc = launch_embed_pe(text, L, h->w.embedding, h->w.dec_pe, B, L, D, c.vocab_size, w.h, s)) return rc;
+  for (int l = 0; l < c.decoder_num_layers; ++l) {
+    const AsrDecoderLayerWeights& lw = h->dec[l];
+    if (int rc = launch_layernorm(w.h, lw.norm1.gamma, lw.norm1.beta, R, D, 1e-5f, nullptr, w.xn, s)) return rc;
+    if (int rc = self_attention_block(c, lw.self_attn, w.xn, w.qkv, w.att, w.h, B, L, 1, valid, nullptr, s)) return rc;
+    if (int rc = launch_layernorm(w.h, lw.norm2.gamma, lw.norm2.beta, R, D, 1e-5f, nullptr, w.xn, s)) return rc;
+    {  // cross attention: q from the decoder stream, K/V precomputed from the encoder output; never masked
+      GemmEpilogue e1;
+      e1.bias = lw.cross_attn.b_qkv; e1.out_bf16 = w.qc; e1.ld_bf16 = D;
+      if (int rc = gemm(w.xn, D, lw.cross_attn.w_qkv, R, D, D, e1, s)) return rc;
+      const bf16* ckv = w.ckv + size_t(l) * M * 2 * D;
+      AttnParams a;
+      a.q = w.qc; a.ldq = D; a.q_batch_stride = (long long)L * D;
+      a.k = ckv; a.v = ckv + D; a.ldk = a.ldv = 2 * D;
+      a.k_batch_stride = a.v_batch_stride = (long long)Tp * 2 * D;
+      a.out = w.att; a.ldo = D; a.o_batch_stride = (long long)L * D;
+      a.B = B; a.H = c.num_heads; a.Sq = L; a.Sk = Tp; a.scale = 1.0f / sqrtf((float)D);
+      if (int rc = launch_attention_tc(a, s)) return rc;
+      GemmEpilogue e2;
+      e2.bias = lw.cross_attn.b_out; e2.residual = w.h; e2.ld_res = D; e2.out_f32 = w.h; e2.ld_f32 = D;
+      if (int rc = gemm(w.att, D, lw.cross_attn.w_out, R, D, D, e2, s)) return rc;
+    }
+    if (int rc = launch_layernorm(w.h, lw.norm3.gamma, lw.norm3.beta, R, D, 1e-5f, nullptr, w.xn, s)) return rc;
+    if (int rc = ffn_block(c, lw.ffn, w.xn, w.ff, w.h, R, s)) return rc;
+  }
+  if (int rc = launch_layernorm(w.h, h->w.dec_norm.gamma, h->w.dec_norm.beta, R, D, 1e-5f, nullptr, w.xn, s)) return rc;
+  GemmEpilogue e;
+  e.out_f32 = logits; e.ld_f32 = c.vocab_size; e.n_store = c.vocab_size;
+  return gemm(w.xn, D, h->w.classifier_w, R, c.vocab_size, D, e, s);
+}
+
+int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, int stop_at_eos,
+                      const int32_t* first_tokens, void* ws, size_t ws_bytes, int32_t* tokens, int32_t* n_tokens,
+                      float* step_logits, asr_stream_t stream) {
+  if (!h || !h->loaded) return set_error(ASR_E_INVALID, "asr_decode_greedy: weights not loaded");
+  if (B == 0) return 0;
+  if (!enc_out || !tokens || !ws || B < 0 || Tp <= 0 || L <= 0)
+    return set_error(ASR_E_INVALID, "asr_decode_greedy: bad argument");
+  const AsrConfig& c = h->cfg;
+  if (L > c.decoder_seq_len)
+    return set_error(ASR_E_INVALID, "asr_decode_greedy: L=%d exceeds decoder_seq_len %d", L, c.decoder_seq_len);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Bump bump(ws);
+  GreedyWs w;
+  w.carve(bump, c, B, Tp, L);
+  if (bump.off > ws_bytes)
+    return set_error(ASR_E_WORKSPACE, "asr_decode_greedy: workspace %zu < %zu bytes", ws_bytes, bump.off);
+  const int D = c.embedding_dim, M = B * Tp;
+
+  if (int rc = launch_f32_to_bf16(enc_out, w.enc_bf16, size_t(M) * D, s)) return rc;
+  if (int rc = cross_kv(h, w.enc_bf16, w.ckv, M, s)) return rc;
+  dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, n_tokens, w.finished, w.step, B, L, c.bos_token_id,
+                                               first_tokens);
+  ASR_CUDA_OK(cudaGetLastError());
+  if (int rc = launch_dec_embed(tokens, L + 1, w.step, h->w.embedding, h->w.dec_pe, B, D, c.vocab_size, w.h, s))
+    return rc;
+
+  const char* no_graph = std::getenv("ASR_B200_NO_GRAPH");
+  if (no_graph && no_graph[0] == '1') {
+    for (int t = 0; t < L; ++t)
+      if (int rc = greedy_step(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, s)) return rc;
+    return 0;
+  }
+  GraphKey key;
+  key.ws = ws; key.enc = enc_out; key.tokens = tokens; key.n_tokens = n_tokens; key.step_logits = step_logits;
+  key.first = first_tokens; key.B = B; key.Tp = Tp; key.L = L; key.stop = stop_at_eos;
+  int first = 0;
+  if (!h->graph_exec || !(h->graph_key == key)) {
+    if (h->graph_exec) {
+      cudaGraphExecDestroy(h->graph_exec);
+      h->graph_exec = nullptr;
+    }
+    // step 0 runs eagerly (also performs every one-time kernel attribute setup outside of capture)
+    if (int rc = greedy_step(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, s)) return rc;
+    first = 1;
+    if (L > 1) {
+      cudaGraph_t graph = nullptr;
+      ASR_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
+      int rc = greedy_step(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, s);
+      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      ASR_CUDA_OK(ce);
+      ce = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      ASR_CUDA_OK(ce);
+      h->graph_key = key;
+    }
+  }
+  for (int t = first; t < L; ++t) ASR_CUDA_OK(cudaGraphLaunch(h->graph_exec, s));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------- operators
+int asr_layernorm(const float* x, const float* gamma, const float* beta, int rows, int D, float* y_f32, void* y_bf16,
+                  asr_stream_t stream) {
+  if (rows == 0) return 0;
+  if (!x || !gamma || !beta || (!y_f32 && !y_bf16) || rows < 0) return set_error(ASR_E_INVALID, "asr_layernorm: bad argument");
+  return launch_layernorm(x, gamma, beta, rows, D, 1e-5f, y_f32, static_cast<bf16*>(y_bf16), static_cast<cudaStream_t>(stream));
+}
+
+int asr_f32_to_bf16(const float* x, void* y, size_t n, asr_stream_t stream) {
+  if (n && (!x || !y)) return set_error(ASR_E_INVALID, "asr_f32_to_bf16: null argument");
+  return launch_f32_to_bf16(x, static_cast<bf16*>(y), n, static_cast<cudaStream_t>(stream));
+}
+
+int asr_gemm_bf16(const void* x, const void* w, const float* bias, const float* residual, const float* pe,
+                  int pe_period, int M, int N, int K, int relu, float* y_f32, void* y_bf16, int impl,
+                  asr_stream_t stream) {
+  if (M == 0) return 0;
+  if (!x || !w || (!y_f32 && !y_bf16) || M < 0 || N <= 0 || K <= 0) return set_error(ASR_E_INVALID, "asr_gemm_bf16: bad argument");
+  GemmEpilogue e;
+  e.bias = bias; e.residual = residual; e.ld_res = N; e.rowvec = pe; e.rowvec_period = pe_period > 0 ? pe_period : 1;
+  e.ld_rowvec = N; e.out_f32 = y_f32; e.ld_f32 = N; e.out_bf16 = static_cast<bf16*>(y_bf16); e.ld_bf16 = N;
+  e.relu = relu; e.n_store = N;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (impl == 1) return launch_gemm_naive(static_cast<const bf16*>(x), K, static_cast<const bf16*>(w), K, M, N, K, e, s);
+  return launch_gemm_tc(static_cast<const bf16*>(x), K, static_cast<const bf16*>(w), K, M, N, K, e, s);
+}
+
+int asr_attention(const void* q, int ldq, long long q_bs, const void* k, int ldk, long long k_bs, const void* v,
+                  int ldv, long long v_bs, void* out, int ldo, long long o_bs, int B, int H, int Sq, int Sk,
+                  float scale, int causal, const int32_t* k_lens, const uint8_t* q_valid, const uint8_t* k_valid,
+                  const uint8_t* dense_mask, int mask_B, int impl, asr_stream_t stream) {
+  if (B == 0 || Sq == 0) return 0;
+  AttnParams a;
+  a.q = static_cast<const bf16*>(q); a.ldq = ldq; a.q_batch_stride = q_bs;
+  a.k = static_cast<const bf16*>(k); a.ldk = ldk; a.k_batch_stride = k_bs;
+  a.v = static_cast<const bf16*>(v); a.ldv = ldv; a.v_batch_stride = v_bs;
+  a.out = static_cast<bf16*>(out); a.ldo = ldo; a.o_batch_stride = o_bs;
+  a.B = B; a.H = H; a.Sq = Sq; a.Sk = Sk; a.scale = scale; a.causal = causal;
+  a.k_lens = k_lens; a.q_valid = q_valid; a.k_valid = k_valid; a.dense_mask = dense_mask; a.mask_B = mask_B;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return impl == 1 ? launch_attention_naive(a, s) : launch_attention_tc(a, s);
+}
+
+size_t asr_mha_workspace_bytes(int B, int Sq, int Sk, int D) {
+  const size_t rq = size_t(B) * Sq, rk = size_t(B) * Sk;
+  return (rq * D + rk * D + rq * 3 * D + rk * 2 * D + rq * D) * 2 + 8 * 256;
+}
+
+int asr_mha(const float* x, const float* src, const AsrMhaWeights* w, int B, int Sq, int Sk, int D, int H, int causal,
+            const uint8_t* q_valid, const uint8_t* k_valid, const uint8_t* dense_mask, int mask_B, void* ws,
+            size_t ws_bytes, float* out, asr_stream_t stream) {
+  if (B == 0 || Sq == 0) return 0;
+  if (!x || !w || !out || !ws || B < 0 || Sq < 0) return set_error(ASR_E_INVALID, "asr_mha: bad argument");
+  if (D != 64 * H || D % 128 != 0) return set_error(ASR_E_UNSUPPORTED, "asr_mha: only head_dim 64 and D %% 128 == 0 (D=%d, H=%d)", D, H);
+  if (!src) Sk = Sq;
+  if (Sk <= 0) return set_error(ASR_E_INVALID, "asr_mha: empty key sequence");
+  if (ws_bytes < asr_mha_workspace_bytes(B, Sq, Sk, D)) return set_error(ASR_E_WORKSPACE, "asr_mha: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int Rq = B * Sq, Rk = B * Sk;
+  Bump b(ws);
+  bf16* xb = b.take<bf16>(size_t(Rq) * D);
+  bf16* sb = b.take<bf16>(size_t(Rk) * D);
+  bf16* qkv = b.take<bf16>(size_t(Rq) * 3 * D);
+  bf16* kv = b.take<bf16>(size_t(Rk) * 2 * D);
+  bf16* att = b.take<bf16>(size_t(Rq) * D);
+  if (int rc = launch_f32_to_bf16(x, xb, size_t(Rq) * D, s)) return rc;
+  AttnParams a;
+  if (!src) {
+    GemmEpilogue e;
+    e.bias = w->b_qkv; e.out_bf16 = qkv; e.ld_bf16 = 3 * D;
+    if (int rc = launch_gemm_tc(xb, D, static_cast<const bf16*>(w->w_qkv), D, Rq, 3 * D, D, e, s)) return rc;
+    a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D;
+    a.ldq = a.ldk = a.ldv = 3 * D;
+    a.q_batch_stride = a.k_batch_stride = a.v_batch_stride = (long long)Sq * 3 * D;
+  } else {
+    if (int rc = launch_f32_to_bf16(src, sb, size_t(Rk) * D, s)) return rc;
+    GemmEpilogue e;
+    e.bias = w->b_qkv; e.out_bf16 = qkv; e.ld_bf16 = D;
+    if (int rc = launch_gemm_tc(xb, D, static_cast<const bf16*>(w->w_qkv), D, Rq, D, D, e, s)) return rc;
+    GemmEpilogue e2;
+    e2.bias = w->b_qkv + D; e2.out_bf16 = kv; e2.ld_bf16 = 2 * D;
+    if (int rc = launch_gemm_tc(sb, D, static_cast<const bf16*>(w->w_qkv) + size_t(D) * D, D, Rk, 2 * D, D, e2, s)) return rc;
+    a.q = qkv; a.ldq = D; a.q_batch_stride = (long long)Sq * D;
+    a.k = kv; a.v = kv + D; a.ldk = a.ldv = 2 * D;
+    a.k_batch_stride = a.v_batch_stride = (long long)Sk * 2 * D;
+  }
+  a.out = att; a.ldo = D; a.o_batch_stride = (long long)Sq * D;
+  a.B = B; a.H = H; a.Sq = Sq; a.Sk = Sk; a.scale = 1.0f / sqrtf((float)D); a.causal = causal;
+  a.q_valid = q_valid; a.k_valid = k_valid; a.dense_mask = dense_mask; a.mask_B = mask_B;
+  if (int rc = launch_attention_tc(a, s)) return rc;
+  GemmEpilogue e3;
+  e3.bias = w->b_out; e3.out_f32 = out; e3.ld_f32 = D;
+  return launch_gemm_tc(att, D, static_cast<const bf16*>(w->w_out), D, Rq, D, D, e3, s);
+}
+
+size_t asr_ffn_workspace_bytes(int rows, int D, int FF) { return (size_t(rows) * D + size_t(rows) * FF) * 2 + 4 * 256; }
+
+int asr_ffn(const float* x, const AsrFfnWeights* w, int rows, int D, int FF, void* ws, size_t ws_bytes, float* out,
+            asr_stream_t stream) {
+  if (rows == 0) return 0;
+  if (!x || !w || !out || !ws || rows < 0) return set_error(ASR_E_INVALID, "asr_ffn: bad argument");
+  if (D % 64 != 0 || FF % 64 != 0) return set_error(ASR_E_UNSUPPORTED, "asr_ffn: D and FF must be multiples of 64");
+  if (ws_bytes < asr_ffn_workspace_bytes(rows, D, FF)) return set_error(ASR_E_WORKSPACE, "asr_ffn: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Bump b(ws);
+  bf16* xb = b.take<bf16>(size_t(rows) * D);
+  bf16* ff = b.take<bf16>(size_t(rows) * FF);
+  if (int rc = launch_f32_to_bf16(x, xb, size_t(rows) * D, s)) return rc;
+  GemmEpilogue e1;
+  e1.bias = w->b1; e1.relu = 1; e1.out_bf16 = ff; e1.ld_bf16 = FF;
+  if (int rc = launch_gemm_tc(xb, D, static_cast<const bf16*>(w->w1), D, rows, FF, D, e1, s)) return rc;
+  GemmEpilogue e2;
+  e2.bias = w->b2; e2.out_f32 = out; e2.ld_f32 = D;
+  return launch_gemm_tc(ff, FF, static_cast<const bf16*>(w->w2), FF, rows, D, FF, e2, s);
+}
+
+size_t asr_conv_workspace_bytes(int B, int F, int T) {
+  return size_t(B) * conv_len(T) * conv_len(F) * 64 * 2 + 512;
+}
+
+int asr_conv_frontend(const float* spectrum, const float* conv1_w, const float* conv1_b, const void* conv2_wfrag,
+                      const float* conv2_b, int B, int F, int T, void* ws, size_t ws_bytes, void* z_bf16,
+                      asr_stream_t stream) {
+  if (B == 0) return 0;
+  if (!spectrum || !conv1_w || !conv1_b || !conv2_wfrag || !conv2_b || !ws || !z_bf16 || B < 0)
+    return set_error(ASR_E_INVALID, "asr_conv_frontend: bad argument");
+  if (conv_len(conv_len(F)) < 1 || conv_len(conv_len(T)) < 1) return set_error(ASR_E_INVALID, "asr_conv_frontend: input too small");
+  if (ws_bytes < asr_conv_workspace_bytes(B, F, T)) return set_error(ASR_E_WORKSPACE, "asr_conv_frontend: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Bump b(ws);
+  bf16* y1 = b.take<bf16>(size_t(B) * conv_len(T) * conv_len(F) * 64);
+  if (int rc = launch_conv1(spectrum, conv1_w, conv1_b, B, F, T, y1, s)) return rc;
+  return launch_conv2(y1, static_cast<const bf16*>(conv2_wfrag), conv2_b, B, conv_len(F), conv_len(T),
+                      static_cast<bf16*>(z_bf16), s);
+}
+
+int asr_embed_pe(const int32_t* tokens, const float* emb, const float* pe, int B, int L, int D, int vocab, float* out,
+                 asr_stream_t stream) {
+  if (B == 0 || L == 0) return 0;
+  if (!tokens || !emb || !pe || !out || D % 4 != 0) return set_error(ASR_E_INVALID, "asr_embed_pe: bad argument");
+  return launch_embed_pe(tokens, L, emb, pe, B, L, D, vocab, out, static_cast<cudaStream_t>(stream));
+}
+
+int asr_dec_linear(const float* x, const float* ln_gamma, const float* ln_beta, const void* w, const float* bias,
+                   const float* residual, int B, int N, int K, int relu, float* out, asr_stream_t stream) {
+  if (B == 0) return 0;
+  if (!x || !w || !out) return set_error(ASR_E_INVALID, "asr_dec_linear: null argument");
+  DecLinear p;
+  p.x = x; p.ldx = K; p.ln_gamma = ln_gamma; p.ln_beta = ln_beta; p.w = static_cast<const bf16*>(w); p.bias = bias;
+  p.B = B; p.N = N; p.K = K; p.relu = relu; p.out = out; p.ldo = N; p.residual = residual; p.ld_res = N;
+  return launch_dec_linear(p, static_cast<cudaStream_t>(stream));
+}
+
+int asr_dec_attention(const float* q, const void* k, const void* v, int ldkv, long long kv_bs, int n_keys, int B,
+                      int H, float scale, float* out, asr_stream_t stream) {
+  if (B == 0) return 0;
+  if (!q || !k || !v || !out || n_keys <= 0) return set_error(ASR_E_INVALID, "asr_dec_attention: bad argument");
+  DecAttn a;
+  a.q = q; a.ldq = H * 64; a.k = static_cast<const bf16*>(k); a.v = static_cast<const bf16*>(v); a.ldkv = ldkv;
+  a.kv_batch_stride = kv_bs; a.n_keys = n_keys; a.out = out; a.ldo = H * 64; a.B = B; a.H = H; a.scale = scale;
+  return launch_dec_attention(a, static_cast<cudaStream_t>(stream));
+}
+
+int asr_umma_probe(const void* a, const void* b, float* d, int N, int b_mn_major, asr_stream_t stream) {
+  if (!a || !b || !d) return set_error(ASR_E_INVALID, "asr_umma_probe: null argument");
+  return launch_umma_probe(static_cast<const bf16*>(a), static_cast<const bf16*>(b), d, N, b_mn_major,
+                           static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,348 @@
+// Fused multi-head attention core: softmax(mask(Q K^T * scale)) V, flash style, never materialising (B,S,S').
+//
+// Replaces reference layers.py:20-27 (bmm, masked_fill(-inf), softmax, nan_to_num, bmm) for all heads at once.
+// Quirks reproduced: scale is a runtime float (= emb_dim**-0.5, layers.py:20), fully masked rows give zeros
+// (nan_to_num, layers.py:25).
+//
+// sm_100a design, one CTA per (q-tile of 128 rows, head, utterance), dh = 64:
+//   warp 4 (one elected thread): TMA loads of the Q tile and a 2-deep K/V tile ring (SWIZZLE_128B), and all
+//                                tcgen05.mma issue: S = Q K^T (M128 N128 K64) and O_j = P V (M128 N64 K128,
+//                                V consumed in place as an MN-major B operand, P from shared memory).
+//   warps 0-3 (one query row per thread): tcgen05.ld S from TMEM, scale + mask + online softmax in fp32,
+//                                P -> bf16 into the swizzled smem A-operand tile, per-tile partial O_j read back
+//                                from TMEM and folded into fp32 register accumulators (no TMEM rescale needed).
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace asr {
+namespace {
+
+constexpr int BQ = 128;   // query rows per CTA
+constexpr int BKV = 128;  // keys per tile
+constexpr int DH = 64;
+constexpr int TILE_BYTES = BKV * DH * 2;  // 16 KB (Q, K and V tiles alike)
+constexpr int P_BYTES = BQ * BKV * 2;     // 32 KB
+constexpr size_t ATTN_SMEM = TILE_BYTES * 5 + P_BYTES + 128 + 1024;
+constexpr uint32_t TMEM_COLS = 256;       // S: [0,128), O_j: [128,192)
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct AttnDev {
+  bf16* out; int ldo; long long o_batch_stride;
+  int H, Sq, Sk;
+  float scale_log2;
+  int causal;
+  const int32_t* k_lens;
+  const uint8_t* q_valid;
+  const uint8_t* k_valid;
+  const uint8_t* dense_mask;
+  int mask_B;
+};
+
+__global__ void __launch_bounds__(160, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, AttnDev p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TILE_BYTES;          // 2 stages
+  uint8_t* sV = smem + 3 * TILE_BYTES;      // 2 stages
+  uint8_t* sP = smem + 5 * TILE_BYTES;      // two 64-key K blocks of 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_ready = bars + 6;
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+
+  int k_end = p.Sk;
+  if (p.k_lens) k_end = min(k_end, max(0, p.k_lens[b]));
+  if (p.causal) k_end = min(k_end, q0 + BQ);
+  const int nkv = (k_end + BKV - 1) / BKV;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(&kv_full[0], 1);
+    mbar_init(&kv_full[1], 1);
+    mbar_init(&kv_empty[0], 1);
+    mbar_init(&kv_empty[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + 128;
+
+  if (warp == 4) {
+    if (lane == 0 && nkv > 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      mbar_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(sQ, &tmQ, q_full, h * DH, q0, b);
+      for (int j = 0; j < 2 && j < nkv; ++j) {
+        mbar_expect_tx(&kv_full[j], 2 * TILE_BYTES);
+        tma_load_3d(sK + j * TILE_BYTES, &tmK, &kv_full[j], h * DH, j * BKV, b);
+        tma_load_3d(sV + j * TILE_BYTES, &tmV, &kv_full[j], h * DH, j * BKV, b);
+      }
+      constexpr uint32_t idesc_S = umma_idesc_bf16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_O = umma_idesc_bf16(BQ, DH, 0, 1);   // B = V tile, MN-major
+      const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j & 1;
+        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(sK + s * TILE_BYTES), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_bf16_ss(tmem_S, q_desc + uint64_t(k * 2), k_desc + uint64_t(k * 2), idesc_S, k != 0);
+        umma_commit(s_full);
+        if (j >= 1 && j + 1 < nkv) {   // refill the stage tile j-1 used, once P V_{j-1} has drained it
+          const int sp = (j - 1) & 1;
+          mbar_wait(&kv_empty[sp], ((j - 1) >> 1) & 1);
+          mbar_expect_tx(&kv_full[sp], 2 * TILE_BYTES);
+          tma_load_3d(sK + sp * TILE_BYTES, &tmK, &kv_full[sp], h * DH, (j + 1) * BKV, b);
+          tma_load_3d(sV + sp * TILE_BYTES, &tmV, &kv_full[sp], h * DH, (j + 1) * BKV, b);
+        }
+        mbar_wait(p_ready, j & 1);
+        tc_fence_after();
+        const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(sV + s * TILE_BYTES), 1024, 1024);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          const uint64_t p_desc = umma_smem_desc_sw128(smem_u32(sP + (k >> 2) * (BQ * 128)), 16, 1024) + uint64_t((k & 3) * 2);
+          umma_bf16_ss(tmem_O, p_desc, v_desc + uint64_t(k * (2048 >> 4)), idesc_O, k != 0);
+        }
+        umma_commit(o_full);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    // ---------------- softmax warps: thread <-> query row
+    const int r = warp * 32 + lane;
+    const int qi = q0 + r;
+    const uint32_t lane_addr = uint32_t(warp * 32) << 16;
+    bool row_masked = false;
+    if (p.q_valid && qi < p.Sq) row_masked = p.q_valid[size_t(b) * p.Sq + qi] == 0;
+    const uint8_t* kvalid = p.k_valid ? p.k_valid + size_t(b) * p.Sk : nullptr;
+    const uint8_t* dmask = nullptr;
+    if (p.dense_mask && qi < p.Sq)
+      dmask = p.dense_mask + (size_t(p.mask_B > 1 ? b : 0) * p.Sq + qi) * p.Sk;
+    int k_lim = p.Sk;
+    if (p.k_lens) k_lim = min(k_lim, max(0, p.k_lens[b]));
+    if (p.causal) k_lim = min(k_lim, qi + 1);
+    if (row_masked) k_lim = 0;
+
+    float m = -INFINITY, l = 0.f;
+    float o[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o[d] = 0.f;
+
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kbase = j * BKV;
+      // pass 1: row maximum of the masked, scaled scores
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t rr[32];
+        tmem_ld32(tmem_S + lane_addr + uint32_t(c * 32), rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int kj = kbase + c * 32 + i;
+          bool ok = kj < k_lim;
+          if (kvalid && ok) ok = kvalid[kj] != 0;
+          if (dmask && ok) ok = dmask[kj] == 0;
+          if (ok) mx = fmaxf(mx, __uint_as_float(rr[i]) * p.scale_log2);
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = (m_new == -INFINITY) ? 1.f : fast_exp2(m - m_new);
+      // fold in the pending partial O_{j-1} (relative to the old max), then rescale to the new max
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < DH / 32; ++c) {
+          uint32_t rr[32];
+          tmem_ld32(tmem_O + lane_addr + uint32_t(c * 32), rr);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(rr[i]);
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < DH; ++d) o[d] *= alpha;
+      // pass 2: probabilities -> bf16 P tile (swizzled K-major A operand), row sum in fp32
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < BKV / 32; ++c) {
+        uint32_t rr[32];
+        tmem_ld32(tmem_S + lane_addr + uint32_t(c * 32), rr);
+        tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float pv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int kj = kbase + c * 32 + i + u;
+            bool ok = kj < k_lim;
+            if (kvalid && ok) ok = kvalid[kj] != 0;
+            if (dmask && ok) ok = dmask[kj] == 0;
+            pv[u] = ok ? fast_exp2(__uint_as_float(rr[i + u]) * p.scale_log2 - m_new) : 0.f;
+          }
+          lsum += pv[0] + pv[1];
+          packed[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+        }
+        uint8_t* blk = sP + (c >> 1) * (BQ * 128) + r * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int chunk = (c & 1) * 4 + q4;
+          *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) =
+              make_uint4(packed[q4 * 4 + 0], packed[q4 * 4 + 1], packed[q4 * 4 + 2], packed[q4 * 4 + 3]);
+        }
+      }
+      l = l * alpha + lsum;
+      m = m_new;
+      fence_proxy_async();   // P writes (generic proxy) -> UMMA operand reads (async proxy)
+      tc_fence_before();     // order our TMEM loads before the MMAs that overwrite S / O_j
+      mbar_arrive(p_ready);
+    }
+    if (nkv > 0) {
+      mbar_wait(o_full, (nkv - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c) {
+        uint32_t rr[32];
+        tmem_ld32(tmem_O + lane_addr + uint32_t(c * 32), rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(rr[i]);
+      }
+    }
+    if (qi < p.Sq) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;   // fully masked row -> zeros (layers.py:25)
+      bf16* op = p.out + size_t(b) * p.o_batch_stride + size_t(qi) * p.ldo + h * DH;
+#pragma unroll
+      for (int d = 0; d < DH; d += 8) {
+        uint4 t;
+        t.x = pack_bf16x2(o[d + 0] * inv, o[d + 1] * inv);
+        t.y = pack_bf16x2(o[d + 2] * inv, o[d + 3] * inv);
+        t.z = pack_bf16x2(o[d + 4] * inv, o[d + 5] * inv);
+        t.w = pack_bf16x2(o[d + 6] * inv, o[d + 7] * inv);
+        *reinterpret_cast<uint4*>(op + d) = t;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------ naive cross-check (CUDA cores, one warp per row)
+__global__ void attn_naive_kernel(AttnParams p) {
+  const int qi = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int lane = threadIdx.x;
+  const bf16* q = p.q + size_t(b) * p.q_batch_stride + size_t(qi) * p.ldq + h * DH;
+  const float q0 = __bfloat162float(q[lane * 2]), q1 = __bfloat162float(q[lane * 2 + 1]);
+  bool row_masked = p.q_valid && p.q_valid[size_t(b) * p.Sq + qi] == 0;
+  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int kj = 0; kj < p.Sk; ++kj) {
+    bool ok = !row_masked;
+    if (p.k_lens && kj >= p.k_lens[b]) ok = false;
+    if (p.causal && kj > qi) ok = false;
+    if (p.k_valid && p.k_valid[size_t(b) * p.Sk + kj] == 0) ok = false;
+    if (p.dense_mask && p.dense_mask[(size_t(p.mask_B > 1 ? b : 0) * p.Sq + qi) * p.Sk + kj] != 0) ok = false;
+    if (!ok) continue;
+    const bf16* k = p.k + size_t(b) * p.k_batch_stride + size_t(kj) * p.ldk + h * DH;
+    const bf16* v = p.v + size_t(b) * p.v_batch_stride + size_t(kj) * p.ldv + h * DH;
+    float s = q0 * __bfloat162float(k[lane * 2]) + q1 * __bfloat162float(k[lane * 2 + 1]);
+    s = warp_sum(s) * p.scale;
+    const float m_new = fmaxf(m, s);
+    const float a = expf(m - m_new), pw = expf(s - m_new);
+    l = l * a + pw;
+    o0 = o0 * a + pw * __bfloat162float(v[lane * 2]);
+    o1 = o1 * a + pw * __bfloat162float(v[lane * 2 + 1]);
+    m = m_new;
+  }
+  const float inv = l > 0.f ? 1.f / l : 0.f;
+  bf16* op = p.out + size_t(b) * p.o_batch_stride + size_t(qi) * p.ldo + h * DH;
+  op[lane * 2] = __float2bfloat16(o0 * inv);
+  op[lane * 2 + 1] = __float2bfloat16(o1 * inv);
+}
+
+int check_params(const AttnParams& p) {
+  if (p.B <= 0 || p.H <= 0 || p.Sq <= 0 || p.Sk <= 0) return set_error(-2, "attention: empty problem");
+  if (!p.q || !p.k || !p.v || !p.out) return set_error(-2, "attention: null pointer");
+  return 0;
+}
+
+}  // namespace
+
+int launch_attention_tc(const AttnParams& p, cudaStream_t s) {
+  if (int rc = check_params(p)) return rc;
+  CUtensorMap tmQ, tmK, tmV;
+  const uint32_t box[3] = {DH, BQ, 1};
+  {
+    uint64_t dims[3] = {(uint64_t)p.H * DH, (uint64_t)p.Sq, (uint64_t)p.B};
+    uint64_t str[3] = {2, (uint64_t)p.ldq * 2, (uint64_t)p.q_batch_stride * 2};
+    if (int rc = make_tmap_bf16(&tmQ, p.q, 3, dims, str, box, nullptr)) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)p.H * DH, (uint64_t)p.Sk, (uint64_t)p.B};
+    uint64_t str[3] = {2, (uint64_t)p.ldk * 2, (uint64_t)p.k_batch_stride * 2};
+    if (int rc = make_tmap_bf16(&tmK, p.k, 3, dims, str, box, nullptr)) return rc;
+    str[1] = (uint64_t)p.ldv * 2;
+    str[2] = (uint64_t)p.v_batch_stride * 2;
+    if (int rc = make_tmap_bf16(&tmV, p.v, 3, dims, str, box, nullptr)) return rc;
+  }
+  AttnDev d;
+  d.out = p.out; d.ldo = p.ldo; d.o_batch_stride = p.o_batch_stride;
+  d.H = p.H; d.Sq = p.Sq; d.Sk = p.Sk;
+  d.scale_log2 = p.scale * 1.4426950408889634f;
+  d.causal = p.causal; d.k_lens = p.k_lens; d.q_valid = p.q_valid; d.k_valid = p.k_valid;
+  d.dense_mask = p.dense_mask; d.mask_B = p.mask_B;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATTN_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((p.Sq + BQ - 1) / BQ, p.H, p.B);
+  attn_tc_kernel<<<grid, 160, ATTN_SMEM, s>>>(tmQ, tmK, tmV, d);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_attention_naive(const AttnParams& p, cudaStream_t s) {
+  if (int rc = check_params(p)) return rc;
+  dim3 grid(p.Sq, p.H, p.B);
+  attn_naive_kernel<<<grid, 32, 0, s>>>(p);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace asr

@@ -1,0 +1,350 @@
+// Y[M,N] = X[M,K] * W[N,K]^T with fused bias / ReLU / positional-encoding / residual epilogue.
+//
+// Replaces every nn.Linear call site of the reference forward path (model.py:47,123; layers.py:16-18,40,54-57)
+// for the batched (encoder / teacher-forced decoder / cross-K/V) case.
+//
+// sm_100a design: one 128 x BN output tile per CTA.
+//   warp 4  : TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B, 64-wide K blocks, STAGES-deep mbarrier ring)
+//   warp 5  : UMMA issuer   (one elected thread, tcgen05.mma kind::f16, fp32 accumulators in TMEM)
+//   warps 0-3: epilogue     (tcgen05.ld 32 lanes x 32 columns per warp -> registers -> fused epilogue -> HBM)
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace asr {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+template <int BN, int STAGES>
+constexpr size_t gemm_smem_bytes() {
+  return size_t(STAGES) * (A_STAGE_BYTES + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+}
+
+__device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], int row, int col0,
+                                               int n_store) {
+  // 32 consecutive columns of one row, processed 4 at a time.
+  const bool res_vec = ep.residual && (ep.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
+  const bool f32_vec = ep.out_f32 && (ep.ld_f32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.out_f32) & 15) == 0);
+  const bool b16_vec = ep.out_bf16 && (ep.ld_bf16 % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 7) == 0);
+  const float* pe_row = ep.rowvec ? ep.rowvec + size_t(row % ep.rowvec_period) * ep.ld_rowvec : nullptr;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const int col = col0 + j;
+    if (col >= n_store) break;
+    float v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[j + i]);
+    const bool full = (col + 4 <= n_store);
+    if (ep.bias) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (full || col + i < n_store) v[i] += __ldg(ep.bias + col + i);
+    }
+    if (ep.relu) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (pe_row) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (full || col + i < n_store) v[i] += __ldg(pe_row + col + i);
+    }
+    if (ep.residual) {
+      const float* rp = ep.residual + size_t(row) * ep.ld_res + col;
+      if (full && res_vec) {
+        const float4 t = *reinterpret_cast<const float4*>(rp);
+        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (col + i < n_store) v[i] += rp[i];
+      }
+    }
+    if (ep.out_f32) {
+      float* op = ep.out_f32 + size_t(row) * ep.ld_f32 + col;
+      if (full && f32_vec) {
+        *reinterpret_cast<float4*>(op) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (col + i < n_store) op[i] = v[i];
+      }
+    }
+    if (ep.out_bf16) {
+      bf16* op = ep.out_bf16 + size_t(row) * ep.ld_bf16 + col;
+      if (full && b16_vec) {
+        uint2 t;
+        t.x = pack_bf16x2(v[0], v[1]);
+        t.y = pack_bf16x2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(op) = t;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (col + i < n_store) op[i] = __float2bfloat16(v[i]);
+      }
+    }
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
+               int M, int n_store, int K) {
+  constexpr int B_STAGE_BYTES = BN * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int nk = K / BK;
+
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
+        tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BK, m0);
+        tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(sA + s * A_STAGE_BYTES), 16, 1024);
+        const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + s * B_STAGE_BYTES), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k)   // +32 B per 16-element K step inside the 128 B swizzle row
+          umma_bf16_ss(tmem_base, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = m0 + warp * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(c * 32), r);
+      tmem_ld_wait();
+      if (row < M) epilogue_chunk(ep, r, row, n0 + c * 32, n_store);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, BN);
+}
+
+template <int BN, int STAGES>
+int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int n_store, int n_pad,
+               int K, cudaStream_t s) {
+  auto kern = gemm_tc_kernel<BN, STAGES>;
+  constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(n_pad / BN, (M + BM - 1) / BM);
+  kern<<<grid, 192, smem, s>>>(tmA, tmB, ep, M, n_store, K);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void gemm_naive_kernel(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N, int K,
+                                  GemmEpilogue ep) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (col >= N || row >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k)
+    acc = fmaf(__bfloat162float(X[size_t(row) * ldx + k]), __bfloat162float(W[size_t(col) * ldw + k]), acc);
+  if (ep.bias) acc += ep.bias[col];
+  if (ep.relu) acc = fmaxf(acc, 0.f);
+  if (ep.rowvec) acc += ep.rowvec[size_t(row % ep.rowvec_period) * ep.ld_rowvec + col];
+  if (ep.residual) acc += ep.residual[size_t(row) * ep.ld_res + col];
+  if (ep.out_f32) ep.out_f32[size_t(row) * ep.ld_f32 + col] = acc;
+  if (ep.out_bf16) ep.out_bf16[size_t(row) * ep.ld_bf16 + col] = __float2bfloat16(acc);
+}
+
+}  // namespace
+
+int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep_in,
+                   cudaStream_t s) {
+  if (M <= 0) return 0;
+  if (K % BK != 0 || K <= 0) return set_error(-2, "gemm: K=%d must be a positive multiple of 64", K);
+  const int n_pad = (N + 63) / 64 * 64;   // W must hold n_pad rows (zero rows past N)
+  GemmEpilogue ep = ep_in;
+  const int n_store = ep.n_store > 0 ? ep.n_store : N;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t str[2] = {2, (uint64_t)ldx * 2};
+    uint32_t box[2] = {BK, BM};
+    int rc = make_tmap_bf16(&tmA, X, 2, dims, str, box, nullptr);
+    if (rc) return rc;
+  }
+  // pick the N tile: largest of 256/128/64 dividing n_pad that still gives >= ~1 wave of CTAs when possible
+  const int mt = (M + BM - 1) / BM;
+  int bn = 64;
+  if (n_pad % 256 == 0 && mt * (n_pad / 256) >= 148) bn = 256;
+  else if (n_pad % 128 == 0 && mt * (n_pad / 128) >= 148) bn = 128;
+  else if (n_pad % 128 == 0 && mt * (n_pad / 64) > 4 * 148) bn = 128;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)n_pad};
+    uint64_t str[2] = {2, (uint64_t)ldw * 2};
+    uint32_t box[2] = {BK, (uint32_t)bn};
+    int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box, nullptr);
+    if (rc) return rc;
+  }
+  switch (bn) {
+    case 256: return launch_one<256, 4>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+    case 128: return launch_one<128, 4>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+    default: return launch_one<64, 4>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+  }
+}
+
+int launch_gemm_naive(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+                      cudaStream_t s) {
+  if (M <= 0) return 0;
+  const int n = ep.n_store > 0 ? ep.n_store : N;
+  dim3 grid((n + 127) / 128, M);
+  gemm_naive_kernel<<<grid, 128, 0, s>>>(X, ldx, W, ldw, M, n, K, ep);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// UMMA probe: D[128, N] = A[128, 64] * B, one CTA, one K block of 64.
+//   b_mn_major == 0: B given as [N, 64] (K contiguous)   -> D = A * B^T
+//   b_mn_major == 1: B given as [64 (k), N=64] (N contiguous, what a V tile looks like) -> D = A * B
+// Used by tests/test_ops_gpu.py to pin the descriptor encodings the GEMM and attention kernels rely on.
+namespace {
+__global__ void __launch_bounds__(128, 1)
+umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* D, int N,
+                  int b_mn_major) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                 // 16 KB
+  uint8_t* sB = smem + 16384;         // up to 16 KB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 32768);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) {
+    const uint32_t b_bytes = b_mn_major ? 64 * 128 : N * 128;
+    mbar_expect_tx(&bar[0], 16384 + b_bytes);
+    tma_load_2d(sA, &tmA, &bar[0], 0, 0);
+    tma_load_2d(sB, &tmB, &bar[0], 0, 0);
+    mbar_wait(&bar[0], 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc_bf16(128, N, 0, b_mn_major);
+    const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(sA), 16, 1024);
+    const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB), b_mn_major ? 1024 : 16, 1024);
+    for (int k = 0; k < 4; ++k) {
+      // K-major: +32 B per K step; MN-major: 16 K rows of 128 B = +2048 B per K step
+      const uint64_t b_adv = b_mn_major ? uint64_t(k * (2048 >> 4)) : uint64_t(k * 2);
+      umma_bf16_ss(tmem_base, a_desc + uint64_t(k * 2), b_desc + b_adv, idesc, k != 0);
+    }
+    umma_commit(&bar[1]);
+  }
+  __syncwarp();
+  mbar_wait(&bar[1], 0);
+  tc_fence_after();
+  for (int c = 0; c < N / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(c * 32), r);
+    tmem_ld_wait();
+    const int row = warp * 32 + lane;
+    for (int j = 0; j < 32; ++j) D[size_t(row) * N + c * 32 + j] = __uint_as_float(r[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+}  // namespace
+
+int launch_umma_probe(const bf16* A, const bf16* Bm, float* D, int N, int b_mn_major, cudaStream_t s) {
+  if (b_mn_major ? (N != 64) : (N % 32 != 0 || N < 32 || N > 128))
+    return set_error(-2, "umma_probe: unsupported N=%d for b_mn_major=%d", N, b_mn_major);
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {64, 128};
+    uint64_t str[2] = {2, 128};
+    uint32_t box[2] = {64, 128};
+    int rc = make_tmap_bf16(&tmA, A, 2, dims, str, box, nullptr);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {64, (uint64_t)(b_mn_major ? 64 : N)};
+    uint64_t str[2] = {2, 128};
+    uint32_t box[2] = {64, (uint32_t)(b_mn_major ? 64 : N)};
+    int rc = make_tmap_bf16(&tmB, Bm, 2, dims, str, box, nullptr);
+    if (rc) return rc;
+  }
+  const size_t smem = 32768 + 64 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  umma_probe_kernel<<<1, 128, smem, s>>>(tmA, tmB, D, N, b_mn_major);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace asr

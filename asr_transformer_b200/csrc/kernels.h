@@ -1,0 +1,134 @@
+// Internal launcher interface between the C-ABI layer (api.cu) and the sm_100a kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace asr {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (thread-local message, negative return codes; never throws / aborts)
+int set_error(int code, const char* fmt, ...);
+const char* last_error();
+#define ASR_CUDA_OK(expr)                                                                           \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return ::asr::set_error(-100, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ---- TMA tensor maps (driver entry point resolved at run time, no link-time libcuda dependency)
+// bf16 tensor, innermost dim contiguous. dims/strides innermost first; strides in BYTES for dims >= 1.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const uint32_t* elem_strides /*nullable*/);
+
+// ---- GEMM  Y[M,N] = X[M,K] * W[N,K]^T (+bias)(relu)(+rowvec)(+residual)  (tcgen05 / TMEM / TMA)
+struct GemmEpilogue {
+  const float* bias = nullptr;       // [N]
+  const float* residual = nullptr;   // fp32 [M, ld_res], added last
+  int ld_res = 0;
+  const float* rowvec = nullptr;     // fp32 [period, ld_rowvec] (positional encoding): + rowvec[row % period, col]
+  int rowvec_period = 1;
+  int ld_rowvec = 0;
+  float* out_f32 = nullptr;          // [M, ld_f32]
+  int ld_f32 = 0;
+  bf16* out_bf16 = nullptr;          // [M, ld_bf16]
+  int ld_bf16 = 0;
+  int relu = 0;
+  int n_store = 0;                   // columns >= n_store are not stored (0 => N)
+};
+// X: bf16 [M, K] (row stride ldx elements), W: bf16 [N_pad, K] (row stride ldw), K % 64 == 0, N_pad % 64 == 0.
+int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+                   cudaStream_t s);
+// Debug / cross-check: same contract, one thread per output element on CUDA cores.
+int launch_gemm_naive(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+                      cudaStream_t s);
+
+// ---- multi-head attention core (flash style, tcgen05).  dh = 64 only.
+struct AttnParams {
+  const bf16* q = nullptr;  int ldq = 0;  long long q_batch_stride = 0;   // element strides; head h at column h*64
+  const bf16* k = nullptr;  int ldk = 0;  long long k_batch_stride = 0;
+  const bf16* v = nullptr;  int ldv = 0;  long long v_batch_stride = 0;
+  bf16* out = nullptr;      int ldo = 0;  long long o_batch_stride = 0;   // [B, Sq, H*64]
+  int B = 0, H = 0, Sq = 0, Sk = 0;
+  float scale = 1.f;                   // emb_dim ** -0.5 (reference layers.py:20), NOT head_dim ** -0.5
+  int causal = 0;                      // mask key j > query i
+  const int32_t* k_lens = nullptr;     // [B]: keys >= k_lens[b] masked
+  const uint8_t* q_valid = nullptr;    // [B, Sq]: 0 => whole query row masked
+  const uint8_t* k_valid = nullptr;    // [B, Sk]: 0 => key masked
+  const uint8_t* dense_mask = nullptr; // [mask_B (1 or B), Sq, Sk]: nonzero => masked
+  int mask_B = 1;
+};
+int launch_attention_tc(const AttnParams& p, cudaStream_t s);
+int launch_attention_naive(const AttnParams& p, cudaStream_t s);
+
+// ---- UMMA probe (bring-up / regression check of descriptor encodings)
+int launch_umma_probe(const bf16* A, const bf16* Bm, float* D, int N, int b_mn_major, cudaStream_t s);
+
+// ---- elementwise / normalisation
+int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int D, float eps, float* y_f32,
+                     bf16* y_bf16, cudaStream_t s);
+int launch_embed_pe(const int32_t* tokens, int ld_tok, const float* emb, const float* pe, int B, int L, int D,
+                    int vocab, float* out, cudaStream_t s);
+int launch_f32_to_bf16(const float* x, bf16* y, size_t n, cudaStream_t s);
+
+// ---- conv front-end (reference model.py:168-171)
+// conv1: spectrum fp32 (B,1,F,T) -> y1 bf16 channels-last (B, T1, F1, 64)
+int launch_conv1(const float* spec, const float* w1 /*[9][64]*/, const float* b1, int B, int F, int T, bf16* y1,
+                 cudaStream_t s);
+// conv2: y1 -> z bf16 (B, T2, F2*64) with column order (f, c)
+int launch_conv2(const bf16* y1, const bf16* w2 /*[64 co][9][64 ci]*/, const float* b2, int B, int F1, int T1,
+                 bf16* z, cudaStream_t s);
+
+// ---- greedy decode step kernels
+struct DecLinear {
+  const float* x = nullptr;      // fp32 [B, K]
+  int ldx = 0;
+  const float* ln_gamma = nullptr, *ln_beta = nullptr;   // optional LayerNorm prologue over K (K == D)
+  const bf16* w = nullptr;       // bf16 [N_pad, K]
+  const float* bias = nullptr;   // [N] nullable
+  int B = 0, N = 0, K = 0;
+  int relu = 0;
+  float* out = nullptr;          // fp32 [B, ldo]; with residual: out = residual + acc + bias (may alias residual)
+  int ldo = 0;
+  const float* residual = nullptr;
+  int ld_res = 0;
+  // QKV-append mode: columns [kv_col0, N) are also written as bf16 into the cache row of step t
+  bf16* kv_cache = nullptr;      // [B, kv_rows, N - kv_col0]
+  int kv_col0 = 0, kv_rows = 0;
+  const int32_t* step = nullptr; // device step counter (row index into the cache)
+};
+int launch_dec_linear(const DecLinear& p, cudaStream_t s);
+
+struct DecAttn {
+  const float* q = nullptr; int ldq = 0;          // fp32 [B, ldq], head h at col h*64
+  const bf16* k = nullptr;  const bf16* v = nullptr;
+  int ldkv = 0; long long kv_batch_stride = 0;    // element strides
+  int n_keys = 0;                                 // used when step == nullptr
+  const int32_t* step = nullptr;                  // n_keys = *step + 1 (self attention over the cache)
+  float* out = nullptr; int ldo = 0;
+  int B = 0, H = 0;
+  float scale = 1.f;
+};
+int launch_dec_attention(const DecAttn& p, cudaStream_t s);
+
+struct DecSelect {
+  const float* logits = nullptr; int ld = 0; int V = 0; int B = 0;
+  int32_t* tokens = nullptr; int ld_tok = 0;      // tokens[b, step+1] = argmax
+  int32_t* n_tokens = nullptr;                    // first EOS position (count of tokens incl. BOS/EOS), nullable
+  int32_t* finished = nullptr;                    // [B]
+  int32_t* step = nullptr;                        // incremented by block 0 after use
+  float* step_logits = nullptr;                   // [B, L, V] nullable: copy of this step's logits
+  int L = 0;
+  int eos = 0, pad = 0, stop_at_eos = 0;
+};
+// argmax + EOS bookkeeping + embedding of the next token into h_next (single CTA; advances *step)
+int launch_dec_select_embed(const DecSelect& p, const float* emb, const float* pe, int D, float* h_next,
+                            cudaStream_t s);
+int launch_dec_embed(const int32_t* tokens, int ld_tok, const int32_t* step, const float* emb, const float* pe, int B,
+                     int D, int vocab, float* h, cudaStream_t s);
+
+}  // namespace asr

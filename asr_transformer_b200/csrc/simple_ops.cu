@@ -1,0 +1,268 @@
+// LayerNorm, embedding + positional encoding, dtype casts and the conv subsampling front-end.
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace asr {
+namespace {
+
+// ---------------------------------------------------------------- LayerNorm (nn.LayerNorm, eps 1e-5, affine)
+// One warp per row, 16-byte vectorised loads, fp32 statistics via warp shuffles; optional fp32 and bf16 outputs.
+constexpr int LN_MAX_CHUNKS = 8;   // D <= 1024
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 int rows, int D, float eps, float* __restrict__ y_f32, bf16* __restrict__ y_bf16) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + size_t(row) * D;
+  float4 v[LN_MAX_CHUNKS];
+  float sum = 0.f;
+  const int nch = D / 128;   // full 128-float chunks; D % 128 == 0 enforced by the launcher
+#pragma unroll
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    if (i < nch) {
+      v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+      sum += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+  }
+  const float mean = warp_sum(sum) / float(D);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    if (i < nch) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / float(D) + eps);
+#pragma unroll
+  for (int i = 0; i < LN_MAX_CHUNKS; ++i) {
+    if (i < nch) {
+      const int col = i * 128 + lane * 4;
+      const float4 g = *reinterpret_cast<const float4*>(gamma + col);
+      const float4 bt = *reinterpret_cast<const float4*>(beta + col);
+      float4 o;
+      o.x = (v[i].x - mean) * rstd * g.x + bt.x;
+      o.y = (v[i].y - mean) * rstd * g.y + bt.y;
+      o.z = (v[i].z - mean) * rstd * g.z + bt.z;
+      o.w = (v[i].w - mean) * rstd * g.w + bt.w;
+      if (y_f32) *reinterpret_cast<float4*>(y_f32 + size_t(row) * D + col) = o;
+      if (y_bf16) {
+        uint2 t;
+        t.x = pack_bf16x2(o.x, o.y);
+        t.y = pack_bf16x2(o.z, o.w);
+        *reinterpret_cast<uint2*>(y_bf16 + size_t(row) * D + col) = t;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- embedding + positional encoding
+// out[b, t, :] = E[tokens[b, t]] + pe[t]   (reference model.py:117)
+__global__ void embed_pe_kernel(const int32_t* tokens, int ld_tok, const float* emb, const float* pe, int L, int D,
+                                int vocab, float* out) {
+  const int t = blockIdx.x, b = blockIdx.y;
+  int tok = tokens[size_t(b) * ld_tok + t];
+  tok = min(max(tok, 0), vocab - 1);
+  const float* e = emb + size_t(tok) * D;
+  const float* pr = pe + size_t(t) * D;
+  float* o = out + (size_t(b) * L + t) * D;
+  for (int d = threadIdx.x * 4; d < D; d += blockDim.x * 4) {
+    const float4 a = *reinterpret_cast<const float4*>(e + d);
+    const float4 c = *reinterpret_cast<const float4*>(pr + d);
+    *reinterpret_cast<float4*>(o + d) = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+  }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, size_t n4) {
+  size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    uint2 t;
+    t.x = pack_bf16x2(v.x, v.y);
+    t.y = pack_bf16x2(v.z, v.w);
+    reinterpret_cast<uint2*>(y)[i] = t;
+  }
+}
+__global__ void f32_to_bf16_tail_kernel(const float* x, bf16* y, size_t start, size_t n) {
+  const size_t i = start + threadIdx.x;
+  if (i < n) y[i] = __float2bfloat16(x[i]);
+}
+
+// ---------------------------------------------------------------- conv1: Conv2d(1,64,3,stride 2) + ReLU
+// spectrum fp32 (B,1,F,T) -> y1 bf16 channels-last (B, T1, F1, 64).  C_in = 1, so this is CUDA-core work:
+// 8 threads per output pixel, each producing 8 channels and one 16-byte store (128 B per pixel, coalesced).
+__global__ void __launch_bounds__(256)
+conv1_kernel(const float* __restrict__ spec, const float* __restrict__ w1, const float* __restrict__ b1, int B, int F,
+             int T, int F1, int T1, bf16* __restrict__ y1) {
+  __shared__ float sw[9 * 64];
+  __shared__ float sb[64];
+  for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) sw[i] = w1[i];
+  if (threadIdx.x < 64) sb[threadIdx.x] = b1[threadIdx.x];
+  __syncthreads();
+  const size_t total = size_t(B) * T1 * F1;
+  const int cg = threadIdx.x & 7;
+  for (size_t pix = size_t(blockIdx.x) * 32 + (threadIdx.x >> 3); pix < total; pix += size_t(gridDim.x) * 32) {
+    const int f1 = int(pix % F1);
+    const int t1 = int((pix / F1) % T1);
+    const int b = int(pix / (size_t(F1) * T1));
+    const float* xp = spec + (size_t(b) * F + 2 * f1) * T + 2 * t1;
+    float in[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) in[kh * 3 + kw] = __ldg(xp + size_t(kh) * T + kw);
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = sb[cg * 8 + c];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = fmaf(in[tap], sw[tap * 64 + cg * 8 + c], acc[c]);
+    uint4 o;
+    o.x = pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
+    o.y = pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+    o.z = pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
+    o.w = pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+    *reinterpret_cast<uint4*>(y1 + pix * 64 + cg * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------- conv2: Conv2d(64,64,3,stride 2) + ReLU
+// Implicit GEMM on tensor cores: M = B*T2*F2 output pixels, N = 64, K = 9 taps * 64 channels.
+// Weights live in shared memory pre-arranged as mma fragments (host packs them, see packing.py), so each
+// B fragment is one conflict-free 8-byte LDS.  A fragments are 16-byte channel vectors read straight from
+// the channels-last y1.  Output z[pixel, co] with pixel = (b, t2, f2): i.e. (B, T2, F2*64), column order (f, c);
+// the matching column permutation of _lin_in.weight is done once at weight-pack time.
+constexpr int CONV2_KSTEPS = 36;   // 9 taps * 2 halves of 32 channels * 2 sub-steps of 16
+constexpr int CONV2_W_BYTES = CONV2_KSTEPS * 8 * 32 * 8;   // 73,728
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128)
+conv2_kernel(const bf16* __restrict__ y1, const uint2* __restrict__ wfrag, const float* __restrict__ b2, int B,
+             int F1, int T1, int F2, int T2, bf16* __restrict__ z) {
+  extern __shared__ uint2 sw[];   // [36][8][32] fragments
+  for (int i = threadIdx.x; i < CONV2_KSTEPS * 8 * 32; i += blockDim.x) sw[i] = wfrag[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const long long M = (long long)B * T2 * F2;
+  const long long ntiles = (M + 63) / 64;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long m_lo = tile * 64 + warp * 16 + g;
+    const long long m_hi = m_lo + 8;
+    const bf16* pa[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      long long m = i ? m_hi : m_lo;
+      if (m >= M) m = M - 1;   // clamp (stores are predicated)
+      const int f2 = int(m % F2);
+      const int t2 = int((m / F2) % T2);
+      const int b = int(m / ((long long)F2 * T2));
+      pa[i] = y1 + ((size_t(b) * T1 + 2 * t2) * F1 + 2 * f2) * 64 + c * 8;
+    }
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const int kh = tap / 3, kw = tap % 3;
+      const size_t toff = (size_t(kw) * F1 + kh) * 64;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint4 vlo = __ldg(reinterpret_cast<const uint4*>(pa[0] + toff + half * 32));
+        const uint4 vhi = __ldg(reinterpret_cast<const uint4*>(pa[1] + toff + half * 32));
+        const uint2* wk = sw + size_t((tap * 2 + half) * 2) * 8 * 32 + lane;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const uint2 w0 = wk[nt * 32];
+          const uint2 w1 = wk[8 * 32 + nt * 32];
+          mma_bf16_16816(acc[nt], vlo.x, vhi.x, vlo.y, vhi.y, w0.x, w0.y);
+          mma_bf16_16816(acc[nt], vlo.z, vhi.z, vlo.w, vhi.w, w1.x, w1.y);
+        }
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int co = nt * 8 + 2 * c;
+      const float bb0 = __ldg(b2 + co), bb1 = __ldg(b2 + co + 1);
+      if (m_lo < M)
+        *reinterpret_cast<uint32_t*>(z + size_t(m_lo) * 64 + co) =
+            pack_bf16x2(fmaxf(acc[nt][0] + bb0, 0.f), fmaxf(acc[nt][1] + bb1, 0.f));
+      if (m_hi < M)
+        *reinterpret_cast<uint32_t*>(z + size_t(m_hi) * 64 + co) =
+            pack_bf16x2(fmaxf(acc[nt][2] + bb0, 0.f), fmaxf(acc[nt][3] + bb1, 0.f));
+    }
+  }
+}
+
+}  // namespace
+
+int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int D, float eps, float* y_f32,
+                     bf16* y_bf16, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  if (D % 128 != 0 || D > 128 * LN_MAX_CHUNKS) return set_error(-2, "layernorm: D=%d must be a multiple of 128, <= 1024", D);
+  const int rows_per_block = 8;
+  layernorm_kernel<<<(rows + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, s>>>(x, gamma, beta, rows,
+                                                                                                  D, eps, y_f32, y_bf16);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_embed_pe(const int32_t* tokens, int ld_tok, const float* emb, const float* pe, int B, int L, int D,
+                    int vocab, float* out, cudaStream_t s) {
+  if (B <= 0 || L <= 0) return 0;
+  embed_pe_kernel<<<dim3(L, B), 64, 0, s>>>(tokens, ld_tok, emb, pe, L, D, vocab, out);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_f32_to_bf16(const float* x, bf16* y, size_t n, cudaStream_t s) {
+  if (n == 0) return 0;
+  const size_t n4 = n / 4;
+  if (n4) {
+    const int blocks = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+    f32_to_bf16_kernel<<<blocks, 256, 0, s>>>(x, y, n4);
+  }
+  if (n % 4) f32_to_bf16_tail_kernel<<<1, 4, 0, s>>>(x, y, n4 * 4, n);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_conv1(const float* spec, const float* w1, const float* b1, int B, int F, int T, bf16* y1, cudaStream_t s) {
+  const int F1 = (F - 3) / 2 + 1, T1 = (T - 3) / 2 + 1;
+  if (F1 <= 0 || T1 <= 0) return set_error(-2, "conv1: input %dx%d too small", F, T);
+  const size_t total = size_t(B) * T1 * F1;
+  const int blocks = (int)((total + 31) / 32 < 148 * 16 ? (total + 31) / 32 : 148 * 16);
+  conv1_kernel<<<blocks, 256, 0, s>>>(spec, w1, b1, B, F, T, F1, T1, y1);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_conv2(const bf16* y1, const bf16* w2frag, const float* b2, int B, int F1, int T1, bf16* z, cudaStream_t s) {
+  const int F2 = (F1 - 3) / 2 + 1, T2 = (T1 - 3) / 2 + 1;
+  if (F2 <= 0 || T2 <= 0) return set_error(-2, "conv2: input %dx%d too small", F1, T1);
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_W_BYTES));
+    attr_set = true;
+  }
+  const long long ntiles = ((long long)B * T2 * F2 + 63) / 64;
+  const int blocks = (int)(ntiles < 148 * 3 ? ntiles : 148 * 3);
+  conv2_kernel<<<blocks, 128, CONV2_W_BYTES, s>>>(y1, reinterpret_cast<const uint2*>(w2frag), b2, B, F1, T1, F2, T2, z);
+  ASR_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace asr

@@ -1,0 +1,270 @@
+"""Weight packing and the per-model engine that owns the C-ABI handle.
+
+Packing happens once per weight version:
+  * per-head ``_q/_k/_v`` Linear(D, 64) -> one bf16 ``[3D, D]`` matrix (rows: q heads | k heads | v heads),
+  * ``input_layer.0.weight`` -> fp32 ``[9 taps, 64]``; ``input_layer.2.weight`` -> bf16 mma-fragment order,
+  * ``encoder._lin_in.weight`` columns permuted from the reference's ``c*F'+f`` (model.py:43-45) to ``f*64+c``,
+    which is the order the conv kernel writes, so no transpose/contiguous pass exists at run time,
+  * ``decoder._classifier.weight`` zero-padded to a multiple of 64 rows.
+GEMM weights are stored as bf16 (lossless when the checkpoint is bf16-representable, as in the parity tests).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import lib as _l
+
+
+def conv_len(n: int) -> int:
+    return (n - 3) // 2 + 1
+
+
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def pack_mha(mha: nn.Module) -> dict:
+    """reference layers.py:10-12,35-36 -> packed [3D, D] / [3D] (+ out projection)."""
+    heads = list(mha._heads)
+    wq = torch.cat([h._q.weight for h in heads], 0)
+    wk = torch.cat([h._k.weight for h in heads], 0)
+    wv = torch.cat([h._v.weight for h in heads], 0)
+    bq = torch.cat([h._q.bias for h in heads], 0)
+    bk = torch.cat([h._k.bias for h in heads], 0)
+    bv = torch.cat([h._v.bias for h in heads], 0)
+    return {"w_qkv": _bf16(torch.cat([wq, wk, wv], 0)), "b_qkv": _f32(torch.cat([bq, bk, bv], 0)),
+            "w_out": _bf16(mha._out_linear.weight), "b_out": _f32(mha._out_linear.bias)}
+
+
+def pack_ffn(ff: nn.Module) -> dict:
+    return {"w1": _bf16(ff.squeeze.weight), "b1": _f32(ff.squeeze.bias),
+            "w2": _bf16(ff.unsqueeze.weight), "b2": _f32(ff.unsqueeze.bias)}
+
+
+def pack_norm(ln: nn.Module) -> dict:
+    return {"gamma": _f32(ln.weight), "beta": _f32(ln.bias)}
+
+
+def pack_conv1(w: torch.Tensor) -> torch.Tensor:
+    """(64,1,3,3) -> fp32 [tap = kh*3+kw][64]."""
+    return _f32(w.detach().reshape(64, 9).t())
+
+
+def pack_conv2_fragments(w: torch.Tensor) -> torch.Tensor:
+    """(co=64, ci=64, kh, kw) -> bf16 [36 k-steps][8 n-tiles][32 lanes][4] in mma.m16n8k16 B-fragment order.
+
+    k-step ks = (tap*2 + half)*2 + sub covers channels half*32 + c*8 + sub*4 + {0..3} for lane (g, c) = divmod(lane, 4)
+    and output channel co = nt*8 + g (see conv2_kernel in csrc/simple_ops.cu)."""
+    taps = w.detach().permute(2, 3, 0, 1).reshape(9, 64, 64)          # [tap, co, ci]
+    t = taps.reshape(9, 8, 8, 2, 4, 2, 4)                              # tap, nt, g, half, c, sub, j
+    t = t.permute(0, 3, 5, 1, 2, 4, 6)                                 # tap, half, sub, nt, g, c, j
+    return _bf16(t.reshape(36, 8, 32, 4))
+
+
+def pack_lin_in(w: torch.Tensor) -> torch.Tensor:
+    """(D, 64*F') columns c*F'+f -> f*64+c."""
+    D, K = w.shape
+    Fp = K // 64
+    return _bf16(w.detach().reshape(D, 64, Fp).permute(0, 2, 1).reshape(D, K))
+
+
+def pack_classifier(w: torch.Tensor) -> torch.Tensor:
+    V, D = w.shape
+    vpad = (V + 63) // 64 * 64
+    out = torch.zeros(vpad, D, dtype=torch.bfloat16, device=w.device)
+    out[:V] = w.detach().to(torch.bfloat16)
+    return out
+
+
+def _mha_struct(p: dict) -> _l.AsrMhaWeights:
+    return _l.AsrMhaWeights(p["w_qkv"].data_ptr(), p["b_qkv"].data_ptr(), p["w_out"].data_ptr(), p["b_out"].data_ptr())
+
+
+def _ffn_struct(p: dict) -> _l.AsrFfnWeights:
+    return _l.AsrFfnWeights(p["w1"].data_ptr(), p["b1"].data_ptr(), p["w2"].data_ptr(), p["b2"].data_ptr())
+
+
+def _norm_struct(p: dict) -> _l.AsrNormWeights:
+    return _l.AsrNormWeights(p["gamma"].data_ptr(), p["beta"].data_ptr())
+
+
+def weights_version(module: nn.Module) -> Tuple:
+    """Cheap fingerprint: any in-place update, .to(), load_state_dict or re-assignment changes it."""
+    ps = list(module.parameters()) + list(module.buffers())
+    return (len(ps), sum(p._version for p in ps), ps[0].data_ptr() if ps else 0, str(ps[0].device) if ps else "")
+
+
+class Engine:
+    """Owns an AsrHandle plus the packed device weights for (input_layer?, encoder?, decoder?)."""
+
+    def __init__(self):
+        self.handle = C.c_void_p()
+        self.keep: List = []
+        self.version = None
+        self.cfg: Optional[_l.AsrConfig] = None
+        self.device: Optional[torch.device] = None
+
+    # the handle is process-local: copies / pickles start empty and re-pack on first use
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
+
+    def __deepcopy__(self, memo):
+        return Engine()
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _l.load().asr_destroy(self.handle)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ build
+    def sync(self, owner: nn.Module, input_layer=None, encoder=None, decoder=None, bos: int = 1) -> "Engine":
+        ver = weights_version(owner)
+        if ver == self.version:
+            return self
+        dev = next(owner.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("asr_b200 has no CPU path: move the model to a CUDA device (model.cuda())")
+        L = _l.load()
+        keep: List = []
+        w = _l.AsrWeights()
+        cfg = _l.AsrConfig()
+        D = H = FF = None
+        if encoder is not None:
+            D = encoder._lin_in.out_features
+            Fp = encoder._lin_in.in_features // 64
+            cfg.input_dim = 4 * Fp + 3 if input_layer is None else getattr(owner, "_input_dim", 4 * Fp + 3)
+            cfg.encoder_seq_len = encoder._pe.pe.shape[1]
+            cfg.encoder_num_layers = len(encoder._layers)
+            lin_w, lin_b = pack_lin_in(encoder._lin_in.weight), _f32(encoder._lin_in.bias)
+            pe = _f32(encoder._pe.pe[0])
+            no = pack_norm(encoder._norm_out)
+            keep += [lin_w, lin_b, pe, no]
+            w.lin_in_w, w.lin_in_b, w.enc_pe = lin_w.data_ptr(), lin_b.data_ptr(), pe.data_ptr()
+            w.enc_norm_out = _norm_struct(no)
+            arr = (_l.AsrEncoderLayerWeights * max(1, len(encoder._layers)))()
+            for i, layer in enumerate(encoder._layers):
+                n1, a, n2, f = pack_norm(layer._norm1), pack_mha(layer._attention), pack_norm(layer._norm2), \
+                    pack_ffn(layer._feedforward)
+                keep += [n1, a, n2, f]
+                arr[i] = _l.AsrEncoderLayerWeights(_norm_struct(n1), _mha_struct(a), _norm_struct(n2), _ffn_struct(f))
+                H = len(layer._attention._heads)
+                FF = layer._feedforward.ff_dim
+            keep.append(arr)
+            w.enc_layers = arr
+        else:
+            cfg.input_dim, cfg.encoder_seq_len, cfg.encoder_num_layers = 83, 1, 0
+        if input_layer is not None:
+            c1w, c1b = pack_conv1(input_layer[0].weight), _f32(input_layer[0].bias)
+            c2w, c2b = pack_conv2_fragments(input_layer[2].weight), _f32(input_layer[2].bias)
+            keep += [c1w, c1b, c2w, c2b]
+            w.conv1_w, w.conv1_b, w.conv2_wfrag, w.conv2_b = c1w.data_ptr(), c1b.data_ptr(), c2w.data_ptr(), c2b.data_ptr()
+        if decoder is not None:
+            D = decoder._embedding.embedding_dim
+            cfg.vocab_size = decoder._embedding.num_embeddings
+            cfg.decoder_seq_len = decoder._pe.pe.shape[1]
+            cfg.decoder_num_layers = len(decoder._layers)
+            cfg.eos_token_id = int(decoder._eos_token_id)
+            pad = decoder._embedding.padding_idx
+            cfg.pad_token_id = int(pad) if pad is not None else 0
+            emb, pe = _f32(decoder._embedding.weight), _f32(decoder._pe.pe[0])
+            nl, cw = pack_norm(decoder._norm_layer), pack_classifier(decoder._classifier.weight)
+            keep += [emb, pe, nl, cw]
+            w.embedding, w.dec_pe, w.classifier_w = emb.data_ptr(), pe.data_ptr(), cw.data_ptr()
+            w.dec_norm = _norm_struct(nl)
+            arr = (_l.AsrDecoderLayerWeights * max(1, len(decoder._layers)))()
+            for i, layer in enumerate(decoder._layers):
+                n1, sa, n2 = pack_norm(layer._norm1), pack_mha(layer._mask_attention), pack_norm(layer._norm2)
+                ca, n3, f = pack_mha(layer._cross_attention), pack_norm(layer._norm3), pack_ffn(layer._feedforward)
+                keep += [n1, sa, n2, ca, n3, f]
+                arr[i] = _l.AsrDecoderLayerWeights(_norm_struct(n1), _mha_struct(sa), _norm_struct(n2),
+                                                   _mha_struct(ca), _norm_struct(n3), _ffn_struct(f))
+                H = len(layer._mask_attention._heads)
+                FF = layer._feedforward.ff_dim
+            keep.append(arr)
+            w.dec_layers = arr
+        else:
+            cfg.vocab_size, cfg.decoder_seq_len, cfg.decoder_num_layers = 1, 1, 0
+        if H is None:   # zero layers everywhere: derive from D
+            H, FF = D // 64, 64
+        cfg.embedding_dim, cfg.num_heads, cfg.ff_dim, cfg.bos_token_id = D, H, FF, bos
+        if self.handle:
+            L.asr_destroy(self.handle)
+            self.handle = C.c_void_p()
+        _l.check(L.asr_create(C.byref(cfg), C.byref(self.handle)), "asr_create")
+        _l.check(L.asr_load_weights(self.handle, C.byref(w)), "asr_load_weights")
+        self.keep, self.version, self.cfg, self.device = keep, ver, cfg, dev
+        return self
+
+    # ------------------------------------------------------------------ calls
+    def _ws(self, B: int, T: int, Ldec: int) -> torch.Tensor:
+        n = C.c_size_t()
+        _l.check(_l.load().asr_workspace_bytes(self.handle, B, max(T, 7), max(Ldec, 1), C.byref(n)), "workspace_bytes")
+        return _l.workspace(n.value, self.device, "model")
+
+    def encode(self, spectrum: torch.Tensor, enc_lens: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Transformer.input_layer + Encoder.forward: (B,1,F,T) fp32 -> (B,T',D) fp32."""
+        if spectrum.dim() != 4 or spectrum.shape[1] != 1 or spectrum.shape[2] != self.cfg.input_dim:
+            raise RuntimeError(f"expected spectrum (B,1,{self.cfg.input_dim},T), got {tuple(spectrum.shape)}")
+        spectrum = spectrum.to(torch.float32).contiguous()
+        B, _, _, T = spectrum.shape
+        Tp = conv_len(conv_len(T))
+        if out is None:
+            out = torch.empty(B, Tp, self.cfg.embedding_dim, dtype=torch.float32, device=spectrum.device)
+        ws = self._ws(B, T, self.cfg.decoder_seq_len)
+        lens = None if enc_lens is None else enc_lens.to(device=spectrum.device, dtype=torch.int32).contiguous()
+        _l.check(_l.load().asr_encode(self.handle, _l.ptr(spectrum), B, T, _l.ptr(lens), _l.ptr(ws), ws.numel(),
+                                      _l.ptr(out), _l.stream()), "asr_encode")
+        return out
+
+    def encoder_forward(self, z_bf16: torch.Tensor, enc_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B, Tp, _ = z_bf16.shape
+        out = torch.empty(B, Tp, self.cfg.embedding_dim, dtype=torch.float32, device=z_bf16.device)
+        ws = self._ws(B, 4 * Tp + 3, self.cfg.decoder_seq_len)
+        lens = None if enc_lens is None else enc_lens.to(device=z_bf16.device, dtype=torch.int32).contiguous()
+        _l.check(_l.load().asr_encoder_forward(self.handle, _l.ptr(z_bf16), B, Tp, _l.ptr(lens), _l.ptr(ws),
+                                               ws.numel(), _l.ptr(out), _l.stream()), "asr_encoder_forward")
+        return out
+
+    def decoder_forward(self, enc_out: torch.Tensor, text: torch.Tensor, valid: torch.Tensor) -> torch.Tensor:
+        B, Tp, _ = enc_out.shape
+        L = text.shape[1]
+        enc_out = enc_out.to(torch.float32).contiguous()
+        text = text.to(torch.int32).contiguous()
+        valid = valid.to(torch.uint8).contiguous()
+        logits = torch.empty(B, L, self.cfg.vocab_size, dtype=torch.float32, device=enc_out.device)
+        ws = self._ws(B, 4 * Tp + 3, L)
+        _l.check(_l.load().asr_decoder_forward(self.handle, _l.ptr(enc_out), B, Tp, _l.ptr(text), _l.ptr(valid), L,
+                                               _l.ptr(ws), ws.numel(), _l.ptr(logits), _l.stream()),
+                 "asr_decoder_forward")
+        return logits
+
+    def decode_greedy(self, enc_out: torch.Tensor, max_len: Optional[int] = None, stop_at_eos: bool = False,
+                      first_tokens: Optional[torch.Tensor] = None, want_logits: bool = False,
+                      tokens_out: Optional[torch.Tensor] = None, n_tokens_out: Optional[torch.Tensor] = None):
+        B, Tp, _ = enc_out.shape
+        L = int(max_len or self.cfg.decoder_seq_len)
+        enc_out = enc_out.to(torch.float32).contiguous()
+        dev = enc_out.device
+        tokens = tokens_out if tokens_out is not None else torch.empty(B, L + 1, dtype=torch.int32, device=dev)
+        n_tok = n_tokens_out if n_tokens_out is not None else torch.empty(B, dtype=torch.int32, device=dev)
+        step_logits = torch.empty(B, L, self.cfg.vocab_size, dtype=torch.float32, device=dev) if want_logits else None
+        first = None if first_tokens is None else first_tokens.to(device=dev, dtype=torch.int32).contiguous()
+        ws = self._ws(B, 4 * Tp + 3, L)
+        _l.check(_l.load().asr_decode_greedy(self.handle, _l.ptr(enc_out), B, Tp, L, int(bool(stop_at_eos)),
+                                             _l.ptr(first), _l.ptr(ws), ws.numel(), _l.ptr(tokens), _l.ptr(n_tok),
+                                             _l.ptr(step_logits), _l.stream()), "asr_decode_greedy")
+        return tokens, n_tok, step_logits

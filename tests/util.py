@@ -1,0 +1,53 @@
+"""Shared helpers for the parity tests."""
+import hashlib
+import os
+
+import torch
+
+from oracle import speech_transformer as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# stated tolerances: bf16 tensor-core operands, fp32 accumulate / epilogue / residual
+TOL_MAX = 3e-2     # max |delta| for enc_out and logits
+TOL_MEAN = 5e-3    # mean |delta|
+TOL_FP32 = 1e-5    # fp32-only kernels (LayerNorm, PE, embedding)
+TAU = 2e-2         # near-tie threshold on the fp32 reference top1-top2 margin
+
+
+def golden(name):
+    return torch.load(os.path.join(GOLDEN, name), map_location="cpu", weights_only=False)
+
+
+def state_checksum(sd) -> str:
+    h = hashlib.sha256()
+    for k in sorted(sd.keys()):
+        h.update(k.encode())
+        h.update(sd[k].detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+def build_model(cfg: O.Config, device="cpu"):
+    """Our drop-in Transformer with the reference's seed-0 default init, rounded to bf16-representable fp32."""
+    import asr_transformer_b200 as A
+    torch.manual_seed(0)
+    m = A.Transformer(**cfg.ctor_kwargs())
+    with torch.no_grad():
+        for p in m.parameters():
+            O.bf16_representable_(p)
+    m.eval()
+    return m.to(device)
+
+
+def cpu_state(m):
+    return {k: v.detach().cpu().float() if v.is_floating_point() else v.detach().cpu() for k, v in m.state_dict().items()}
+
+
+def assert_close(got, ref, tol_max=TOL_MAX, tol_mean=TOL_MEAN, what=""):
+    got, ref = got.detach().float().cpu(), ref.detach().float().cpu()
+    assert got.shape == ref.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    assert torch.isfinite(got).all(), f"{what}: non-finite values"
+    d = (got - ref).abs()
+    assert d.max().item() <= tol_max and d.mean().item() <= tol_mean, \
+        f"{what}: max|d|={d.max().item():.3e} (tol {tol_max}), mean|d|={d.mean().item():.3e} (tol {tol_mean})"
+    return d.max().item(), d.mean().item()
