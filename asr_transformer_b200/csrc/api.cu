@@ -88,6 +88,38 @@ struct GraphKey {
   bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
 };
 
+// Optional per-kernel-class timing of the decode step (asr_decode_profile): CUDA event pairs around every launch.
+enum DecClass { DC_QKV = 0, DC_SELF_ATTN, DC_OUT_PROJ, DC_CROSS_Q, DC_CROSS_ATTN, DC_FFN1, DC_FFN2, DC_CLASSIFIER,
+                DC_SELECT, DC_COUNT };
+struct StepProf {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> cls;
+  size_t used = 0;
+  cudaStream_t s = nullptr;
+  void mark(int c) {
+    if (used + 2 > ev.size()) {
+      ev.resize(used + 2);
+      cudaEventCreate(&ev[used]);
+      cudaEventCreate(&ev[used + 1]);
+    }
+    cls.push_back(c);
+    cudaEventRecord(ev[used], s);
+  }
+  void done() {
+    cudaEventRecord(ev[used + 1], s);
+    used += 2;
+  }
+  ~StepProf() {
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+};
+#define PROF(prof, c, call)            \
+  do {                                 \
+    if (prof) (prof)->mark(c);         \
+    if (int rc_ = (call)) return rc_;  \
+    if (prof) (prof)->done();          \
+  } while (0)
+
 __global__ void dec_init_kernel(int32_t* tokens, int ld_tok, int32_t* n_tokens, int32_t* finished, int32_t* step,
                                 int B, int L, int bos, const int32_t* first_tokens) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -109,6 +141,7 @@ struct AsrHandle {
   bool loaded = false;
   cudaGraphExec_t graph_exec = nullptr;
   GraphKey graph_key;
+  unsigned long long graph_kernels = 0;   // kernels per captured decode step
 };
 
 namespace {
@@ -178,7 +211,7 @@ int cross_kv(const AsrHandle* h, const bf16* enc_bf16, bf16* ckv, int M, cudaStr
 }
 
 int greedy_step(const AsrHandle* h, const GreedyWs& ws, int B, int Tp, int L, int stop_at_eos, int32_t* tokens,
-                int32_t* n_tokens, float* step_logits, cudaStream_t s) {
+                int32_t* n_tokens, float* step_logits, cudaStream_t s, StepProf* prof = nullptr) {
   const AsrConfig& c = h->cfg;
   const int D = c.embedding_dim, FF = c.ff_dim, H = c.num_heads;
   const float scale = 1.0f / sqrtf((float)D);
@@ -193,53 +226,53 @@ int greedy_step(const AsrHandle* h, const GreedyWs& ws, int B, int Tp, int L, in
       p.w = static_cast<const bf16*>(w.self_attn.w_qkv); p.bias = w.self_attn.b_qkv;
       p.B = B; p.N = 3 * D; p.K = D; p.out = ws.qkv; p.ldo = 3 * D;
       p.kv_cache = cache; p.kv_col0 = D; p.kv_rows = L; p.step = ws.step;
-      if (int rc = launch_dec_linear(p, s)) return rc;
+      PROF(prof, DC_QKV, launch_dec_linear(p, s));
     }
     {  // causal self attention over the cache rows 0..t
       DecAttn a;
       a.q = ws.qkv; a.ldq = 3 * D; a.k = cache; a.v = cache + D; a.ldkv = 2 * D;
       a.kv_batch_stride = (long long)L * 2 * D; a.n_keys = L; a.step = ws.step;
       a.out = ws.att; a.ldo = D; a.B = B; a.H = H; a.scale = scale;
-      if (int rc = launch_dec_attention(a, s)) return rc;
+      PROF(prof, DC_SELF_ATTN, launch_dec_attention(a, s));
     }
     {  // out projection + residual
       DecLinear p;
       p.x = ws.att; p.ldx = D; p.w = static_cast<const bf16*>(w.self_attn.w_out); p.bias = w.self_attn.b_out;
       p.B = B; p.N = D; p.K = D; p.out = ws.h; p.ldo = D; p.residual = ws.h; p.ld_res = D;
-      if (int rc = launch_dec_linear(p, s)) return rc;
+      PROF(prof, DC_OUT_PROJ, launch_dec_linear(p, s));
     }
     {  // LN2 -> cross-attention query (model.py:70-71)
       DecLinear p;
       p.x = ws.h; p.ldx = D; p.ln_gamma = w.norm2.gamma; p.ln_beta = w.norm2.beta;
       p.w = static_cast<const bf16*>(w.cross_attn.w_qkv); p.bias = w.cross_attn.b_qkv;
       p.B = B; p.N = D; p.K = D; p.out = ws.qc; p.ldo = D;
-      if (int rc = launch_dec_linear(p, s)) return rc;
+      PROF(prof, DC_CROSS_Q, launch_dec_linear(p, s));
     }
     {  // unmasked cross attention over the precomputed encoder K/V
       DecAttn a;
       a.q = ws.qc; a.ldq = D; a.k = ckv; a.v = ckv + D; a.ldkv = 2 * D;
       a.kv_batch_stride = (long long)Tp * 2 * D; a.n_keys = Tp; a.step = nullptr;
       a.out = ws.att; a.ldo = D; a.B = B; a.H = H; a.scale = scale;
-      if (int rc = launch_dec_attention(a, s)) return rc;
+      PROF(prof, DC_CROSS_ATTN, launch_dec_attention(a, s));
     }
     {
       DecLinear p;
       p.x = ws.att; p.ldx = D; p.w = static_cast<const bf16*>(w.cross_attn.w_out); p.bias = w.cross_attn.b_out;
       p.B = B; p.N = D; p.K = D; p.out = ws.h; p.ldo = D; p.residual = ws.h; p.ld_res = D;
-      if (int rc = launch_dec_linear(p, s)) return rc;
+      PROF(prof, DC_OUT_PROJ, launch_dec_linear(p, s));
     }
     {  // LN3 -> FFN (model.py:73-74)
       DecLinear p;
       p.x = ws.h; p.ldx = D; p.ln_gamma = w.norm3.gamma; p.ln_beta = w.norm3.beta;
       p.w = static_cast<const bf16*>(w.ffn.w1); p.bias = w.ffn.b1; p.relu = 1;
       p.B = B; p.N = FF; p.K = D; p.out = ws.ff; p.ldo = FF;
-      if (int rc = launch_dec_linear(p, s)) return rc;
+      PROF(prof, DC_FFN1, launch_dec_linear(p, s));
     }
     {
       DecLinear p;
       p.x = ws.ff; p.ldx = FF; p.w = static_cast<const bf16*>(w.ffn.w2); p.bias = w.ffn.b2;
       p.B = B; p.N = D; p.K = FF; p.out = ws.h; p.ldo = D; p.residual = ws.h; p.ld_res = D;
-      if (int rc = launch_dec_linear(p, s)) return rc;
+      PROF(prof, DC_FFN2, launch_dec_linear(p, s));
     }
   }
   const int vpad = (c.vocab_size + 63) / 64 * 64;
@@ -247,14 +280,15 @@ int greedy_step(const AsrHandle* h, const GreedyWs& ws, int B, int Tp, int L, in
     DecLinear p;
     p.x = ws.h; p.ldx = D; p.w = static_cast<const bf16*>(h->w.classifier_w);
     p.B = B; p.N = c.vocab_size; p.K = D; p.out = ws.logits; p.ldo = vpad;
-    if (int rc = launch_dec_linear(p, s)) return rc;
+    PROF(prof, DC_CLASSIFIER, launch_dec_linear(p, s));
   }
   DecSelect sel;
   sel.logits = ws.logits; sel.ld = vpad; sel.V = c.vocab_size; sel.B = B;
   sel.tokens = tokens; sel.ld_tok = L + 1; sel.n_tokens = n_tokens; sel.finished = ws.finished; sel.step = ws.step;
   sel.step_logits = step_logits; sel.L = L; sel.eos = c.eos_token_id; sel.pad = c.pad_token_id;
   sel.stop_at_eos = stop_at_eos;
-  return launch_dec_select_embed(sel, h->w.embedding, h->w.dec_pe, D, ws.h, s);
+  PROF(prof, DC_SELECT, launch_dec_select_embed(sel, h->w.embedding, h->w.dec_pe, D, ws.h, s));
+  return 0;
 }
 
 }  // namespace
@@ -439,6 +473,7 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
   dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, n_tokens, w.finished, w.step, B, L, c.bos_token_id,
                                                first_tokens);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
   if (int rc = launch_dec_embed(tokens, L + 1, w.step, h->w.embedding, h->w.dec_pe, B, D, c.vocab_size, w.h, s))
     return rc;
 
@@ -462,8 +497,11 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
     first = 1;
     if (L > 1) {
       cudaGraph_t graph = nullptr;
+      const unsigned long long before = g_kernel_launches;
       ASR_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
       int rc = greedy_step(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, s);
+      h->graph_kernels = g_kernel_launches - before;
+      g_kernel_launches = before;          // captured, not launched
       cudaError_t ce = cudaStreamEndCapture(s, &graph);
       if (rc) {
         if (graph) cudaGraphDestroy(graph);
@@ -477,8 +515,50 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
     }
   }
   for (int t = first; t < L; ++t) ASR_CUDA_OK(cudaGraphLaunch(h->graph_exec, s));
+  ASR_LAUNCHED(h->graph_kernels * (unsigned long long)(L - first));
   return 0;
 }
+
+// Same work as asr_decode_greedy, launched eagerly with a CUDA event pair around every kernel; synchronises the
+// stream at the end and returns the summed device time (ms) and launch count per kernel class (DecClass order).
+int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L, void* ws, size_t ws_bytes,
+                       int32_t* tokens, float* ms_per_class, int32_t* launches_per_class, asr_stream_t stream) {
+  if (!h || !h->loaded || !enc_out || !tokens || !ws || !ms_per_class || !launches_per_class || B <= 0 || L <= 0)
+    return set_error(ASR_E_INVALID, "asr_decode_profile: bad argument");
+  const AsrConfig& c = h->cfg;
+  if (L > c.decoder_seq_len) return set_error(ASR_E_INVALID, "asr_decode_profile: L exceeds decoder_seq_len");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Bump bump(ws);
+  GreedyWs w;
+  w.carve(bump, c, B, Tp, L);
+  if (bump.off > ws_bytes) return set_error(ASR_E_WORKSPACE, "asr_decode_profile: workspace too small");
+  const int D = c.embedding_dim, M = B * Tp;
+  if (int rc = launch_f32_to_bf16(enc_out, w.enc_bf16, size_t(M) * D, s)) return rc;
+  if (int rc = cross_kv(h, w.enc_bf16, w.ckv, M, s)) return rc;
+  dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, nullptr, w.finished, w.step, B, L, c.bos_token_id,
+                                               nullptr);
+  ASR_CUDA_OK(cudaGetLastError());
+  if (int rc = launch_dec_embed(tokens, L + 1, w.step, h->w.embedding, h->w.dec_pe, B, D, c.vocab_size, w.h, s))
+    return rc;
+  StepProf prof;
+  prof.s = s;
+  for (int t = 0; t < L; ++t)
+    if (int rc = greedy_step(h, w, B, Tp, L, 0, tokens, nullptr, nullptr, s, &prof)) return rc;
+  ASR_CUDA_OK(cudaStreamSynchronize(s));
+  for (int i = 0; i < DC_COUNT; ++i) {
+    ms_per_class[i] = 0.f;
+    launches_per_class[i] = 0;
+  }
+  for (size_t i = 0; i < prof.cls.size(); ++i) {
+    float ms = 0.f;
+    ASR_CUDA_OK(cudaEventElapsedTime(&ms, prof.ev[2 * i], prof.ev[2 * i + 1]));
+    ms_per_class[prof.cls[i]] += ms;
+    launches_per_class[prof.cls[i]] += 1;
+  }
+  return 0;
+}
+
+unsigned long long asr_launch_count(void) { return g_kernel_launches; }
 
 // ------------------------------------------------------------------------------------------- operators
 int asr_layernorm(const float* x, const float* gamma, const float* beta, int rows, int D, float* y_f32, void* y_bf16,

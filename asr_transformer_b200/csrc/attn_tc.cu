@@ -334,6 +334,7 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t s) {
   dim3 grid((p.Sq + BQ - 1) / BQ, p.H, p.B);
   attn_tc_kernel<<<grid, 160, ATTN_SMEM, s>>>(tmQ, tmK, tmV, d);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
   return 0;
 }
 
@@ -342,6 +343,7 @@ int launch_attention_naive(const AttnParams& p, cudaStream_t s) {
   dim3 grid(p.Sq, p.H, p.B);
   attn_naive_kernel<<<grid, 32, 0, s>>>(p);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
   return 0;
 }
 

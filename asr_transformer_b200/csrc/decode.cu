@@ -190,6 +190,7 @@ dec_attn_kernel(DecAttn p) {
   const bf16* kb = p.k + size_t(b) * p.kv_batch_stride + h * 64 + c8 * 8;
   const bf16* vb = p.v + size_t(b) * p.kv_batch_stride + h * 64 + c8 * 8;
 
+  const unsigned gmask = 0xFFu << (lane & 24);
   float mx = -INFINITY;
   for (int kj = grp; kj < n; kj += 16) {
     const uint4 kv = __ldg(reinterpret_cast<const uint4*>(kb + size_t(kj) * p.ldkv));
@@ -201,9 +202,9 @@ dec_attn_kernel(DecAttn p) {
       s = fmaf(q[2 * i], f.x, s);
       s = fmaf(q[2 * i + 1], f.y, s);
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(gmask, s, 1);   // reduce inside the 8-lane key group only: trip counts differ
+    s += __shfl_xor_sync(gmask, s, 2);   // between the four groups of a warp when n % 16 != 0
+    s += __shfl_xor_sync(gmask, s, 4);
     if (c8 == 0) s_sc[kj] = s;
     mx = fmaxf(mx, s);
   }
@@ -324,6 +325,7 @@ int launch_dec_linear(const DecLinear& p, cudaStream_t s) {
   dim3 grid(n_pad / 32, (p.B + DL_ROWS - 1) / DL_ROWS);
   dec_linear_kernel<<<grid, 128, 0, s>>>(p);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
   return 0;
 }
 
@@ -341,6 +343,7 @@ int launch_dec_attention(const DecAttn& p, cudaStream_t s) {
   }
   dec_attn_kernel<<<dim3(p.H, p.B), 128, smem, s>>>(p);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
   return 0;
 }
 
@@ -349,6 +352,7 @@ int launch_dec_embed(const int32_t* tokens, int ld_tok, const int32_t* step, con
   if (B <= 0) return 0;
   dec_embed_kernel<<<B, 64, 0, s>>>(tokens, ld_tok, step, emb, pe, D, vocab, h);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
   return 0;
 }
 
@@ -357,6 +361,7 @@ int launch_dec_select_embed(const DecSelect& p, const float* emb, const float* p
   if (p.B <= 0) return 0;
   dec_select_kernel<<<1, 1024, 0, s>>>(p, emb, pe, D, h_next);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
   return 0;
 }
 

@@ -189,6 +189,7 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogu
   dim3 grid(n_pad / BN, (M + BM - 1) / BM);
   kern<<<grid, 192, smem, s>>>(tmA, tmB, ep, M, n_store, K);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
   return 0;
 }
 
@@ -253,6 +254,7 @@ int launch_gemm_naive(const bf16* X, int ldx, const bf16* W, int ldw, int M, int
   dim3 grid((n + 127) / 128, M);
   gemm_naive_kernel<<<grid, 128, 0, s>>>(X, ldx, W, ldw, M, n, K, ep);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
   return 0;
 }
 
@@ -344,6 +346,7 @@ int launch_umma_probe(const bf16* A, const bf16* Bm, float* D, int N, int b_mn_m
   }
   umma_probe_kernel<<<1, 128, smem, s>>>(tmA, tmB, D, N, b_mn_major);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
   return 0;
 }
 

@@ -20,6 +20,10 @@ const char* last_error();
       return ::asr::set_error(-100, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
+// ---- launch accounting (bench.py reports the number of our kernels launched in the timed region)
+extern unsigned long long g_kernel_launches;
+#define ASR_LAUNCHED(n) (::asr::g_kernel_launches += (n))
+
 // ---- TMA tensor maps (driver entry point resolved at run time, no link-time libcuda dependency)
 // bf16 tensor, innermost dim contiguous. dims/strides innermost first; strides in BYTES for dims >= 1.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

@@ -217,6 +217,7 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, int 
   layernorm_kernel<<<(rows + rows_per_block - 1) / rows_per_block, rows_per_block * 32, 0, s>>>(x, gamma, beta, rows,
                                                                                                   D, eps, y_f32, y_bf16);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
   return 0;
 }
 
@@ -225,6 +226,7 @@ int launch_embed_pe(const int32_t* tokens, int ld_tok, const float* emb, const f
   if (B <= 0 || L <= 0) return 0;
   embed_pe_kernel<<<dim3(L, B), 64, 0, s>>>(tokens, ld_tok, emb, pe, L, D, vocab, out);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
   return 0;
 }
 
@@ -237,6 +239,7 @@ int launch_f32_to_bf16(const float* x, bf16* y, size_t n, cudaStream_t s) {
   }
   if (n % 4) f32_to_bf16_tail_kernel<<<1, 4, 0, s>>>(x, y, n4 * 4, n);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED((n4 ? 1 : 0) + (n % 4 ? 1 : 0));
   return 0;
 }
 
@@ -247,6 +250,7 @@ int launch_conv1(const float* spec, const float* w1, const float* b1, int B, int
   const int blocks = (int)((total + 31) / 32 < 148 * 16 ? (total + 31) / 32 : 148 * 16);
   conv1_kernel<<<blocks, 256, 0, s>>>(spec, w1, b1, B, F, T, F1, T1, y1);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
   return 0;
 }
 
@@ -262,6 +266,7 @@ int launch_conv2(const bf16* y1, const bf16* w2frag, const float* b2, int B, int
   const int blocks = (int)(ntiles < 148 * 3 ? ntiles : 148 * 3);
   conv2_kernel<<<blocks, 128, CONV2_W_BYTES, s>>>(y1, reinterpret_cast<const uint2*>(w2frag), b2, B, F1, T1, F2, T2, z);
   ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
   return 0;
 }
 

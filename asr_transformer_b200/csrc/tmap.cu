@@ -8,6 +8,7 @@
 namespace asr {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_kernel_launches = 0;
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;

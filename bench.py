@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Headline benchmark: utterances/sec for batched greedy ASR (10 s synthetic log-mel, L = 128 decode steps).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path (conv front-end -> encoder -> cross-K/V -> 128 greedy decode steps) over one
+batch of synthetic utterances.  Workload = BASELINE.json configs[1] (C2): repo-default Speech-Transformer, batch 64
+per GPU, bf16 tensor-core operands with fp32 accumulation.  Weak scaling: every GPU decodes its own 64 utterances,
+no collective on the compute path, one final all_gather of the token matrices.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed (CUDA events) with inputs resident in HBM; `e2e` goes through
+the public API with pinned HOST buffers, H2D of the spectrogram and D2H of the transcripts inside the timed region.
+`--impl reference` times the reference's own CPU algorithm (the oracle's literal restatement of model.py:125-151:
+per-utterance, no KV cache; the reference is pure Python and cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = "C2"
+METRIC = "utt/sec (10 s audio, greedy decode)"
+UNIT = "utt/s"
+DEC_CLASSES = ["dec_linear_qkv", "dec_attn_self", "dec_linear_out_proj", "dec_linear_cross_q", "dec_attn_cross",
+               "dec_linear_ffn1", "dec_linear_ffn2", "dec_linear_classifier", "dec_select_embed"]
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (default: the workload's batch)")
+    ap.add_argument("--workload", default=WORKLOAD)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_desc(cfg, batch, n_gpus):
+    return {
+        "workload": f"{cfg.name}: repo-default Speech-Transformer ({cfg.encoder_num_layers} enc / "
+                    f"{cfg.decoder_num_layers} dec, d_model {cfg.embedding_dim}, {cfg.num_heads} heads, FFN {cfg.ff_dim}, "
+                    f"vocab {cfg.vocab_size}), random init (seed 0, bf16-representable), synthetic structured log-mel "
+                    f"{cfg.input_dim}x{cfg.frames} (10 ms hop), greedy decode exactly {cfg.decoder_seq_len} steps",
+        "batch_per_gpu": batch, "global_batch": batch * n_gpus, "frames": cfg.frames,
+        "encoder_frames": cfg.encoder_seq_len, "decode_steps": cfg.decoder_seq_len,
+        "l2": "flushed between timed iterations (256 MiB device write, outside the event-timed spans)",
+        "parallelism": f"dp{n_gpus}: utterance sharding, one process per GPU, no collective on the compute path, "
+                       "final all_gather of token ids",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                for n, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def decode_class_bytes(cfg, B):
+    """Algorithmic HBM bytes per launch of each decode-step kernel class (bf16 weights and K/V caches, fp32
+    activations), averaged over the L steps (self-attention reads t+1 cache rows at step t)."""
+    D, FF, V, Tp, L = cfg.embedding_dim, cfg.ff_dim, cfg.vocab_size, cfg.encoder_seq_len, cfg.decoder_seq_len
+    f = 4
+    return {
+        "dec_linear_qkv": 3 * D * D * 2 + B * D * f + B * 3 * D * f + B * 2 * D * 2,
+        "dec_attn_self": B * (D * f + 2 * ((L + 1) / 2) * D * 2 + D * f),
+        "dec_linear_out_proj": D * D * 2 + 3 * B * D * f,
+        "dec_linear_cross_q": D * D * 2 + 2 * B * D * f,
+        "dec_attn_cross": B * (D * f + 2 * Tp * D * 2 + D * f),
+        "dec_linear_ffn1": D * FF * 2 + B * D * f + B * FF * f,
+        "dec_linear_ffn2": D * FF * 2 + B * FF * f + 2 * B * D * f,
+        "dec_linear_classifier": V * D * 2 + B * D * f + B * V * f,
+        "dec_select_embed": B * V * f + B * D * f,
+    }
+
+
+def run_reference(args, cfg):
+    """Reference arm: the reference's CPU algorithm (literal restatement, oracle/speech_transformer.py) on the host
+    cores.  One step = ONE utterance of the same workload (bounded sample; the reference costs O(L^2) per utterance)."""
+    from oracle import speech_transformer as O
+    from tests.util import build_model, cpu_state
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = build_model(cfg)
+    sd = cpu_state(model)
+    batch = args.batch or cfg.batch
+    spec = O.structured_spectrum(batch, cfg.frames, cfg.input_dim, seed=1)
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            b = i % batch
+            t0 = time.perf_counter()
+            O.evaluate_reference_style(sd, spec[b:b + 1], cfg)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = len(times) / total
+    sample = f"1 utterance per step ({cfg.frames} frames, {cfg.decoder_seq_len} decode steps), {len(times)} timed steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_desc(cfg, batch, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    args = parse()
+    from oracle import speech_transformer as O      # workload registry + synthetic inputs + CPU baseline only
+    cfg = O.CONFIGS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    from tests.util import build_model, cpu_state
+    from asr_transformer_b200 import lib as L
+    from asr_transformer_b200.parallel import gather_tokens
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    batch = args.batch or cfg.batch
+    model = build_model(cfg, dev)
+    lib = L.load()
+    # every rank decodes its own utterances (different seed per rank): weak scaling
+    spec_host = O.structured_spectrum(batch, cfg.frames, cfg.input_dim, seed=1 + rank).pin_memory()
+    spec_dev = spec_host.to(dev)
+    tokens = torch.empty(batch, cfg.decoder_seq_len + 1, dtype=torch.int32, device=dev)
+    n_tok = torch.empty(batch, dtype=torch.int32, device=dev)
+    enc = torch.empty(batch, cfg.encoder_seq_len, cfg.embedding_dim, dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    eng = model._eng()
+
+    def step_device():
+        eng.encode(spec_dev, out=enc)
+        eng.decode_greedy(enc, tokens_out=tokens, n_tokens_out=n_tok)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+
+    # ------------------------------------------------------------------ device-timed throughput (inputs in HBM)
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = lib.asr_launch_count()
+    sampler.start()
+    barrier()
+    for s, e in ev:
+        flush.fill_(1)                      # evict L2 (126 MB) between timed iterations
+        s.record()
+        step_device()
+        e.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = lib.asr_launch_count() - launches0
+    ms = [s.elapsed_time(e) for s, e in ev]
+    total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * batch * args.steps / (total_ms / 1e3)
+
+    # ------------------------------------------------------------------ end to end through the public API
+    def step_e2e():
+        x = spec_host.to(dev, non_blocking=True)
+        t, n = model.greedy_decode(x)
+        if dist is not None:
+            t, n = gather_tokens(t, n)
+        return t.cpu(), n.cpu()
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out_tokens, _ = step_e2e()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * batch * args.steps / float(e2e_s.item())
+    h2d = spec_host.numel() * 4
+    d2h = out_tokens.numel() * 4 + out_tokens.shape[0] * 4
+
+    result = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": workload_desc(cfg, batch, world), "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+    }
+
+    if rank == 0:
+        # -------------------------------------------------------------- roofline of the dominant kernel
+        ws = eng._ws(batch, 4 * cfg.encoder_seq_len + 3, cfg.decoder_seq_len)
+        ms_cls = (C.c_float * 9)()
+        n_cls = (C.c_int32 * 9)()
+        for _ in range(2):     # second pass is the measured one (first warms caches / clocks)
+            L.check(lib.asr_decode_profile(eng.handle, L.ptr(enc), batch, cfg.encoder_seq_len, cfg.decoder_seq_len,
+                                           L.ptr(ws), ws.numel(), L.ptr(tokens), ms_cls, n_cls, L.stream()),
+                    "asr_decode_profile")
+        hbm_peak, tf_peak, peak_src = measured_peaks()
+        bytes_cls = decode_class_bytes(cfg, batch)
+        prof = {}
+        tot = sum(ms_cls)
+        for i, name in enumerate(DEC_CLASSES):
+            if n_cls[i]:
+                avg_us = 1e3 * ms_cls[i] / n_cls[i]
+                prof[name] = {"launches": int(n_cls[i]), "avg_us": round(avg_us, 3), "share": round(ms_cls[i] / tot, 4),
+                              "alg_bytes_per_launch": int(bytes_cls[name]),
+                              "gbs": round(bytes_cls[name] / (avg_us * 1e-6) / 1e9, 1)}
+        top = max(prof, key=lambda k: prof[k]["share"])
+        result["roofline"] = {"kernel": top, "bound": "hbm", "achieved": prof[top]["gbs"], "peak": hbm_peak,
+                              "unit": "GB/s", "frac": round(prof[top]["gbs"] / hbm_peak, 4), "traffic": None,
+                              "peak_source": peak_src,
+                              "note": "per-launch CUDA-event time of every decode-step kernel (eager replay of the "
+                                      "timed workload in this process); see profiles/ for the ncu launch list"}
+        result["decode_kernel_profile"] = prof
+        step_bytes = sum(bytes_cls[k] * (prof[k]["launches"] / cfg.decoder_seq_len) for k in prof)
+        result["decode_step"] = {"alg_bytes": int(step_bytes),
+                                 "roofline_ms_per_decode": round(cfg.decoder_seq_len * step_bytes / (hbm_peak * 1e9) * 1e3, 3)}
+
+        # -------------------------------------------------------------- CPU baseline (reference algorithm, host cores)
+        if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            sd = cpu_state(model)
+            n_cpu = 2
+            with torch.no_grad():
+                import dataclasses
+                O.evaluate_reference_style(sd, spec_host[:1].contiguous(), dataclasses.replace(cfg, decoder_seq_len=4))  # warm-up
+                t0 = time.perf_counter()
+                O.evaluate_reference_style(sd, spec_host[:n_cpu].contiguous(), cfg)
+                dt = time.perf_counter() - t0
+            result["cpu_baseline"] = {
+                "value": n_cpu / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                "sample": f"{n_cpu} utterances of the same workload through the oracle's literal restatement of the "
+                          f"reference greedy loop (model.py:125-151: per utterance, no KV cache), {dt:.1f} s"}
+        print(json.dumps(result))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -121,6 +121,14 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
                       const int32_t* first_tokens /* [B] nullable: defaults to bos_token_id */, void* ws,
                       size_t ws_bytes, int32_t* tokens, int32_t* n_tokens, float* step_logits, asr_stream_t stream);
 
+/* Profiling aid for bench.py: the same decode launched eagerly with a CUDA-event pair around every kernel.
+ * Synchronises `stream` before returning.  ms_per_class / launches_per_class: 9 entries in the order
+ * {qkv linear, self attention, out projections, cross q linear, cross attention, ffn1, ffn2, classifier, select}. */
+int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L, void* ws, size_t ws_bytes,
+                       int32_t* tokens, float* ms_per_class, int32_t* launches_per_class, asr_stream_t stream);
+/* Number of kernels this library has launched in the calling process (graph replays counted per kernel). */
+unsigned long long asr_launch_count(void);
+
 /* ---- operator-level entry points (sub-module drop-ins and parity tests) --------------------------------- */
 /* nn.LayerNorm call sites (model.py:20,23,52,67,70,73,122). y_f32 / y_bf16 nullable. */
 int asr_layernorm(const float* x, const float* gamma, const float* beta, int rows, int D, float* y_f32, void* y_bf16,

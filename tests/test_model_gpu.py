@@ -1,0 +1,174 @@
+"""Model-level parity on the GPU through the drop-in modules / C-ABI:
+golden fixtures produced by the unmodified reference (T0, C1) and the CPU oracle at BASELINE sizes (C2 ...)."""
+import os
+
+import pytest
+import torch
+
+from oracle import speech_transformer as O
+from tests.util import TAU, TOL_FP32, assert_close, build_model, cpu_state, golden, state_checksum
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def t0():
+    cfg = O.CONFIGS["T0"]
+    fx = golden("model_T0.pt")
+    m = build_model(cfg, DEV)
+    assert state_checksum(cpu_state(m)) == fx["state_checksum"]
+    spec = O.structured_spectrum(cfg.batch, cfg.frames, cfg.input_dim, seed=1).to(DEV)
+    return cfg, fx, m, spec
+
+
+def test_frontend_and_encoder_T0(t0):
+    cfg, fx, m, spec = t0
+    conv = m.input_layer(spec)
+    assert_close(conv, fx["conv_out"], 6e-2, 4e-3, "input_layer")
+    enc = m.encode(spec)
+    assert_close(enc, fx["enc_out"], what="enc_out")
+    # Encoder.forward drop-in on reference-layout conv features
+    assert_close(m.encoder(fx["conv_out"].to(DEV)), fx["enc_out"], what="Encoder.forward")
+
+
+def test_forward_logits_T0(t0):
+    cfg, fx, m, spec = t0
+    logits = m(spec, fx["text"].to(DEV), fx["mask"].to(DEV))
+    assert logits.dtype == torch.float32 and logits.shape == fx["forward_logits"].shape
+    assert_close(logits, fx["forward_logits"], what="Transformer.forward logits")
+    # Decoder.forward drop-in on the reference's encoder output
+    out = m.decoder(fx["text"].to(DEV), fx["mask"].to(DEV), fx["enc_out"].to(DEV))
+    assert_close(out, fx["forward_logits"], what="Decoder.forward logits")
+
+
+def check_tokens(ref_tokens, ref_logits, got_tokens, min_frac=0.99):
+    r = O.compare_tokens(ref_tokens, ref_logits, got_tokens, TAU)
+    assert not r["hard"], f"token divergence not explained by an argmax near-tie: {r['hard']}"
+    frac = r["identical"] / r["utterances"]
+    return r, frac
+
+
+def test_greedy_tokens_T0(t0):
+    cfg, fx, m, spec = t0
+    tokens, n_tok, logits = m.greedy_decode(spec, return_logits=True)
+    torch.cuda.synchronize()
+    assert tokens.shape == (cfg.batch, cfg.decoder_seq_len + 1) and tokens.dtype == torch.int32
+    r, frac = check_tokens(fx["tokens"], fx["step_logits"], tokens)
+    assert frac == 1.0, r
+    assert_close(logits, fx["step_logits"], what="step logits (no final LayerNorm)")
+
+
+def test_evaluate_contract_T0(t0):
+    cfg, fx, m, spec = t0
+    bos = torch.full((cfg.batch, 1), cfg.bos_token_id, dtype=torch.int32, device=DEV)
+    last, probs = m.evaluate(spec, bos)
+    assert last.dtype == torch.int64 and tuple(last.shape) == (1, cfg.decoder_seq_len + 1)
+    assert torch.equal(last.cpu(), fx["evaluate_tokens_last"])
+    assert [tuple(p.shape) for p in probs] == fx["evaluate_probs_shapes"]
+    got = torch.tensor([float(p.double().sum()) for p in probs])
+    assert torch.allclose(got, fx["evaluate_probs_sum"], rtol=2e-3, atol=0.5)
+    # Decoder.evaluate drop-in
+    last2, probs2 = m.decoder.evaluate(bos, fx["enc_out"].to(DEV))
+    assert torch.equal(last2.cpu(), fx["evaluate_tokens_last"]) and len(probs2) == len(probs)
+
+
+def test_stop_at_eos_and_lengths(t0):
+    cfg, fx, m, spec = t0
+    ref = fx["tokens"]
+    tokens, n_tok = m.greedy_decode(spec, stop_at_eos=True)
+    tokens, n_tok = tokens.cpu().long(), n_tok.cpu()
+    for b in range(cfg.batch):
+        eos_pos = (ref[b, 1:] == cfg.eos_token_id).nonzero()
+        if eos_pos.numel():
+            n = int(eos_pos[0]) + 2
+            assert int(n_tok[b]) == n
+            assert torch.equal(tokens[b, :n], ref[b, :n]) and (tokens[b, n:] == cfg.pad_token_id).all()
+        else:
+            assert int(n_tok[b]) == cfg.decoder_seq_len + 1 and torch.equal(tokens[b], ref[b])
+    # shorter max_len is a prefix of the full decode
+    t8, _ = m.greedy_decode(spec, max_len=8)
+    assert torch.equal(t8.cpu().long(), ref[:, :9])
+
+
+def test_batch_invariance_T0(t0):
+    """Tokens of an utterance must not depend on the batch it is decoded in."""
+    cfg, fx, m, spec = t0
+    full, _ = m.greedy_decode(spec)
+    for b in range(cfg.batch):
+        one, _ = m.greedy_decode(spec[b:b + 1])
+        assert torch.equal(one[0], full[b])
+    rep = torch.cat([spec, spec, spec], 0)
+    t3, _ = m.greedy_decode(rep)
+    assert torch.equal(t3[:cfg.batch], full) and torch.equal(t3[2 * cfg.batch:], full)
+
+
+def test_empty_batch(t0):
+    cfg, fx, m, spec = t0
+    tokens, n_tok = m.greedy_decode(spec[:0])
+    assert tokens.shape == (0, cfg.decoder_seq_len + 1)
+
+
+def test_key_padding_truncation_equivalence(t0):
+    """Masks-on encoder (the 'next' row): a zero-padded utterance with lengths == the unpadded utterance."""
+    cfg, fx, m, spec = t0
+    T_short = 123
+    padded = spec.clone()
+    padded[1, :, :, T_short:] = 0
+    lengths = torch.tensor([cfg.frames, T_short, cfg.frames], device=DEV)
+    enc = m.encode(padded, lengths)
+    alone = m.encode(spec[1:2, :, :, :T_short].contiguous())
+    n = alone.shape[1]
+    assert_close(enc[1, :n], alone[0], 2e-2, 2e-3, "masked batch row == unpadded utterance")
+
+
+def test_reference_golden_C1():
+    """BASELINE config 1 (repo-default model, batch 8, 10 s, L=128) against the reference's own outputs."""
+    cfg = O.CONFIGS["C1"]
+    fx = golden("model_C1.pt")
+    m = build_model(cfg, DEV)
+    assert state_checksum(cpu_state(m)) == fx["state_checksum"]
+    spec = O.structured_spectrum(cfg.batch, cfg.frames, cfg.input_dim, seed=1).to(DEV)
+    enc = m.encode(spec)
+    assert_close(enc, fx["enc_out"], what="C1 enc_out")
+    logits = m(spec, fx["text"].to(DEV), fx["mask"].to(DEV))
+    assert_close(logits, fx["forward_logits"], what="C1 forward logits")
+    tokens, n_tok, step_logits = m.greedy_decode(spec, return_logits=True)
+    r, frac = check_tokens(fx["tokens"], fx["step_logits"], tokens)
+    print("C1 greedy:", r)
+    assert frac >= 0.99 or r["utterances"] - r["identical"] <= 1, r
+    ident = [b for b in range(cfg.batch) if torch.equal(tokens[b].cpu().long(), fx["tokens"][b])]
+    assert_close(step_logits[ident], fx["step_logits"][ident], what="C1 step logits")
+
+
+@pytest.mark.parametrize("name,batch", [("C2", 64), ("C5", 8)])
+def test_greedy_vs_oracle_baseline_sizes(name, batch):
+    """BASELINE sizes against the CPU oracle (KV-cached restatement, pinned to the reference by the goldens)."""
+    cfg = O.CONFIGS[name]
+    m = build_model(cfg, DEV)
+    sd = cpu_state(m)
+    spec = O.structured_spectrum(batch, cfg.frames, cfg.input_dim, seed=11)
+    torch.set_num_threads(os.cpu_count() or 1)
+    enc_ref = O.encode(sd, spec)
+    tok_ref, logits_ref = O.greedy_kv_cached(sd, enc_ref, cfg)
+    enc = m.encode(spec.to(DEV))
+    assert_close(enc, enc_ref, what=f"{name} enc_out")
+    tokens, _ = m.greedy_decode(spec.to(DEV))
+    r, frac = check_tokens(tok_ref, logits_ref, tokens)
+    print(f"{name} greedy:", {k: r[k] for k in ("utterances", "identical", "near_tie", "distinct_rows")})
+    assert r["distinct_rows"] >= 0.9 * batch
+    assert frac >= 0.95, r      # every divergence is already proven to be a near-tie by check_tokens
+
+
+def test_long_form_encoder_C4():
+    """30 s utterances: encoder sequence 749 stresses the flash-attention tiling (6 KV tiles)."""
+    cfg = O.CONFIGS["C4"]
+    m = build_model(cfg, DEV)
+    sd = cpu_state(m)
+    spec = O.structured_spectrum(2, cfg.frames, cfg.input_dim, seed=12)
+    enc_ref = O.encode(sd, spec)
+    assert_close(m.encode(spec.to(DEV)), enc_ref, what="C4 enc_out")
+    tok_ref, logits_ref = O.greedy_kv_cached(sd, enc_ref, cfg, max_len=48)
+    tokens, _ = m.greedy_decode(spec.to(DEV), max_len=48)
+    r, frac = check_tokens(tok_ref, logits_ref, tokens)
+    assert frac == 1.0 or not r["hard"]

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Bring-up on a GPU box: each group runs in its own process so one faulting kernel cannot poison the rest.
+# usage: tools/gpu_bringup.sh [groups...]   (default: all)
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
+run() { name=$1; shift; timeout 420 python -m pytest "$@" -q --tb=short -p no:cacheprovider --timeout 90 > gpurun_out/$name.log 2>&1; echo "$name exit $?"; tail -n 3 gpurun_out/$name.log; }
+groups=${@:-"probe ln gemm attn modules dec model smoke bench"}
+for g in $groups; do
+case $g in
+  probe) run probe tests/test_ops_gpu.py -m gpu -k "umma_probe" ;;
+  ln) run ln tests/test_ops_gpu.py -m gpu -k "layernorm or embed" ;;
+  gemm) run gemm tests/test_ops_gpu.py -m gpu -k "gemm" ;;
+  attn) run attn tests/test_ops_gpu.py -m gpu -k "attention and not dec_attention" ;;
+  modules) run modules tests/test_ops_gpu.py -m gpu -k "module or conv" ;;
+  dec) run dec tests/test_ops_gpu.py -m gpu -k "dec_" ;;
+  model) run model tests/test_model_gpu.py -m gpu ;;
+  smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -n 2 gpurun_out/smoke.log ;;
+  bench) timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -c 3000 gpurun_out/bench.log; tail -n 5 gpurun_out/bench.err ;;
+  benchref) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/benchref.log 2>&1; echo "benchref exit $?"; tail -c 1500 gpurun_out/benchref.log ;;
+esac
+done
