@@ -65,6 +65,7 @@ struct GreedyWs {
   bf16 *enc_bf16, *ckv, *cache;
   float *h, *qkv, *att, *qc, *ff, *logits;
   int32_t *step, *finished;
+  unsigned* barrier;   // [2]: grid barrier counter, finished-utterance counter
   void carve(Bump& b, const AsrConfig& c, int B, int Tp, int L) {
     const size_t M = size_t(B) * Tp, D = c.embedding_dim;
     const size_t vpad = (size_t(c.vocab_size) + 63) / 64 * 64;
@@ -79,6 +80,7 @@ struct GreedyWs {
     logits = b.take<float>(size_t(B) * vpad);
     step = b.take<int32_t>(1);
     finished = b.take<int32_t>(B);
+    barrier = b.take<unsigned>(2);
   }
 };
 
@@ -142,6 +144,7 @@ struct AsrHandle {
   cudaGraphExec_t graph_exec = nullptr;
   GraphKey graph_key;
   unsigned long long graph_kernels = 0;   // kernels per captured decode step
+  cudaStream_t capture_stream = nullptr;  // the caller's stream may be the legacy default stream, which cannot capture
 };
 
 namespace {
@@ -291,6 +294,36 @@ int greedy_step(const AsrHandle* h, const GreedyWs& ws, int B, int Tp, int L, in
   return 0;
 }
 
+static int build_persistent(const AsrHandle* h, const GreedyWs& w, int B, int Tp, int L, int stop_at_eos,
+                            int32_t* tokens, int32_t* n_tokens, float* step_logits, PersistentParams& pp) {
+  const AsrConfig& c = h->cfg;
+  const int D = c.embedding_dim;
+    std::memset(&pp, 0, sizeof(pp));
+  pp.B = B; pp.D = D; pp.H = c.num_heads; pp.FF = c.ff_dim; pp.V = c.vocab_size; pp.L = L; pp.Tp = Tp;
+  pp.nd = c.decoder_num_layers;
+  if (pp.nd > PERSIST_MAX_LAYERS) return set_error(ASR_E_UNSUPPORTED, "more than %d decoder layers", PERSIST_MAX_LAYERS);
+  for (int l = 0; l < pp.nd; ++l) {
+    const AsrDecoderLayerWeights& lw = h->dec[l];
+    PersistentLayer& pl = pp.layer[l];
+    pl.ln1_g = lw.norm1.gamma; pl.ln1_b = lw.norm1.beta;
+    pl.w_qkv = static_cast<const bf16*>(lw.self_attn.w_qkv); pl.b_qkv = lw.self_attn.b_qkv;
+    pl.w_o = static_cast<const bf16*>(lw.self_attn.w_out); pl.b_o = lw.self_attn.b_out;
+    pl.ln2_g = lw.norm2.gamma; pl.ln2_b = lw.norm2.beta;
+    pl.w_qc = static_cast<const bf16*>(lw.cross_attn.w_qkv); pl.b_qc = lw.cross_attn.b_qkv;
+    pl.w_oc = static_cast<const bf16*>(lw.cross_attn.w_out); pl.b_oc = lw.cross_attn.b_out;
+    pl.ln3_g = lw.norm3.gamma; pl.ln3_b = lw.norm3.beta;
+    pl.w1 = static_cast<const bf16*>(lw.ffn.w1); pl.b1 = lw.ffn.b1;
+    pl.w2 = static_cast<const bf16*>(lw.ffn.w2); pl.b2 = lw.ffn.b2;
+  }
+  pp.classifier = static_cast<const bf16*>(h->w.classifier_w); pp.emb = h->w.embedding; pp.pe = h->w.dec_pe;
+  pp.cache = w.cache; pp.ckv = w.ckv; pp.h = w.h; pp.qkv = w.qkv; pp.ff = w.ff;
+  pp.tokens = tokens; pp.n_tokens = n_tokens; pp.finished = w.finished; pp.step_logits = step_logits;
+  pp.barrier = w.barrier; pp.done_count = w.barrier + 1;
+  pp.eos = c.eos_token_id; pp.pad = c.pad_token_id; pp.stop_at_eos = stop_at_eos;
+  pp.scale = 1.0f / sqrtf((float)D);
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -311,6 +344,7 @@ int asr_create(const AsrConfig* cfg, AsrHandle** out) {
 void asr_destroy(AsrHandle* h) {
   if (!h) return;
   if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   delete h;
 }
 
@@ -477,8 +511,15 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
   if (int rc = launch_dec_embed(tokens, L + 1, w.step, h->w.embedding, h->w.dec_pe, B, D, c.vocab_size, w.h, s))
     return rc;
 
-  const char* no_graph = std::getenv("ASR_B200_NO_GRAPH");
-  if (no_graph && no_graph[0] == '1') {
+  // Launch mode: "persistent" (default: one cooperative kernel for all L steps), "graph" (one CUDA-graph replay of
+  // the 51-kernel step per token) or "eager" (same kernels, launched one by one; bring-up / profiling).
+  const char* mode = std::getenv("ASR_B200_DECODE");
+  if (!mode || !mode[0] || mode[0] == 'p') {
+    PersistentParams pp;
+    if (int rc = build_persistent(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, pp)) return rc;
+    return launch_dec_persistent(pp, s);
+  }
+  if (mode[0] == 'e') {
     for (int t = 0; t < L; ++t)
       if (int rc = greedy_step(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, s)) return rc;
     return 0;
@@ -498,11 +539,13 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
     if (L > 1) {
       cudaGraph_t graph = nullptr;
       const unsigned long long before = g_kernel_launches;
-      ASR_CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed));
-      int rc = greedy_step(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, s);
+      if (!h->capture_stream) ASR_CUDA_OK(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+      cudaStream_t cs = h->capture_stream;   // capture records, it does not execute: any capturable stream will do
+      ASR_CUDA_OK(cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed));
+      int rc = greedy_step(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, cs);
       h->graph_kernels = g_kernel_launches - before;
       g_kernel_launches = before;          // captured, not launched
-      cudaError_t ce = cudaStreamEndCapture(s, &graph);
+      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
       if (rc) {
         if (graph) cudaGraphDestroy(graph);
         return rc;
@@ -545,7 +588,7 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
   for (int t = 0; t < L; ++t)
     if (int rc = greedy_step(h, w, B, Tp, L, 0, tokens, nullptr, nullptr, s, &prof)) return rc;
   ASR_CUDA_OK(cudaStreamSynchronize(s));
-  for (int i = 0; i < DC_COUNT; ++i) {
+  for (int i = 0; i <= DC_COUNT; ++i) {
     ms_per_class[i] = 0.f;
     launches_per_class[i] = 0;
   }
@@ -554,6 +597,31 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
     ASR_CUDA_OK(cudaEventElapsedTime(&ms, prof.ev[2 * i], prof.ev[2 * i + 1]));
     ms_per_class[prof.cls[i]] += ms;
     launches_per_class[prof.cls[i]] += 1;
+  }
+  // slot DC_COUNT: the persistent cooperative kernel (all L steps in one launch), timed on its own
+  {
+    dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, nullptr, w.finished, w.step, B, L, c.bos_token_id,
+                                                 nullptr);
+    ASR_CUDA_OK(cudaGetLastError());
+    if (int rc = launch_dec_embed(tokens, L + 1, w.step, h->w.embedding, h->w.dec_pe, B, D, c.vocab_size, w.h, s))
+      return rc;
+    PersistentParams pp;
+    if (int rc = build_persistent(h, w, B, Tp, L, 0, tokens, nullptr, nullptr, pp)) return rc;
+    cudaEvent_t e0, e1;
+    ASR_CUDA_OK(cudaEventCreate(&e0));
+    ASR_CUDA_OK(cudaEventCreate(&e1));
+    ASR_CUDA_OK(cudaMemsetAsync(pp.barrier, 0, 2 * sizeof(unsigned), s));
+    ASR_CUDA_OK(cudaEventRecord(e0, s));
+    int rc = launch_dec_persistent(pp, s);
+    ASR_CUDA_OK(cudaEventRecord(e1, s));
+    ASR_CUDA_OK(cudaStreamSynchronize(s));
+    if (!rc) {
+      ASR_CUDA_OK(cudaEventElapsedTime(&ms_per_class[DC_COUNT], e0, e1));
+      launches_per_class[DC_COUNT] = 1;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
   }
   return 0;
 }

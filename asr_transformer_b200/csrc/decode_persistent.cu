@@ -1,0 +1,586 @@
+// Persistent cooperative greedy decoder: ONE launch runs all L decode steps of the whole utterance batch.
+//
+// Restates reference model.py:125-151 (Decoder.evaluate) with a device-resident KV cache; no host sync, no kernel
+// boundary per token.  One CTA per SM (cooperative launch), phases separated by grid-wide barriers:
+//
+//   per layer:  A  LN1 + packed QKV linear (grid-split over output columns, K/V rows appended to the cache)   | barrier
+//               B  utterance-local chain in ONE CTA per utterance: causal self attention -> out projection + residual
+//                  -> LN2 -> cross-attention query -> cross attention over the precomputed encoder K/V -> out
+//                  projection + residual  (no global traffic between the sub-steps, everything stays in smem)     | barrier
+//               C  LN3 + FFN squeeze + ReLU (grid-split)                                                          | barrier
+//               D  FFN unsqueeze + residual (grid-split)                                                          | barrier
+//   per step:   E  utterance-local: classifier (no final LayerNorm, model.py:142) -> argmax (lowest index wins)
+//                  -> EOS bookkeeping -> embedding + PE of the next token                                         | barrier
+//
+// Precision: Linear layers see fp32-accurate activations (bf16 hi + lo split, two tensor-core passes per weight
+// tile, fp32 accumulate); K/V caches bf16; attention scores / softmax / residual / LayerNorm fp32.
+// Data written by one CTA and read by another after a barrier is loaded with ld.global.cg (L2), never through L1.
+#include <cooperative_groups.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace asr {
+namespace {
+
+constexpr int NT = 256;              // threads per CTA
+constexpr int NW = NT / 32;
+constexpr int MROWS = 16;            // batch rows per grid-split work item (one m16 MMA tile)
+constexpr int PAD = 32;              // smem row padding (elements): row stride == 64 B mod 128 B -> conflict-free LDS.128
+
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+// Grid-wide barrier on a monotonically increasing counter (zeroed by the launcher). Bounded spin: a protocol bug
+// becomes a launch failure, never a hung GPU.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+  target += gridDim.x;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_u32(counter) < target) {
+      if (clock64() - t0 > 4000000000LL) __trap();
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// split fp32 -> bf16 hi + lo and store 4 consecutive elements
+__device__ __forceinline__ void store_hilo4(bf16* hi, bf16* lo, float4 v) {
+  const bf16 h0 = __float2bfloat16(v.x), h1 = __float2bfloat16(v.y), h2 = __float2bfloat16(v.z), h3 = __float2bfloat16(v.w);
+  uint2 a, b;
+  a.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  a.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+  b.x = pack_bf16x2(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
+  b.y = pack_bf16x2(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
+  *reinterpret_cast<uint2*>(hi) = a;
+  *reinterpret_cast<uint2*>(lo) = b;
+}
+
+struct Smem {
+  bf16* hi;        // [MROWS][kmax + PAD]
+  bf16* lo;
+  float* red;      // [NW tiles][8 K chunks][32 lanes][4] partial sums
+  float* vec;      // utterance-local fp32 vectors: h[D], x[D] (attention out / LN out), q[D], logits / scores ...
+  float* sc;       // [H][max(L, Tp)] attention scores
+  float* part;     // [NW][D] partial attention outputs
+  float* stat;     // small scratch
+};
+
+enum Epi { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_QKV = 2 };
+
+struct LinArgs {
+  const float* x; int ldx; int K;
+  const float* ln_g; const float* ln_b;     // nullable: LayerNorm prologue over K
+  const bf16* w; const float* bias; int N;  // W [N_pad][K] bf16
+  int relu; int epi;
+  float* out; int ldo;                      // EPI_RESIDUAL: out += (in place)
+  bf16* cache; int cache_rows; int cache_col0; int step;   // EPI_QKV
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// Grid-split linear: out[B, N] = epi( LN?(x)[B, K] * W^T + bias ).  CTA -> (16-row block, set of 8-column tiles);
+// the CTA's 8 warps are spread over (tile, K split); partial sums are reduced through smem.
+__device__ void linear_phase(const LinArgs& a, int B, const Smem& sm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+  const int MB = (B + MROWS - 1) / MROWS;
+  const int S = gridDim.x / MB;             // CTAs ("slots") per row block
+  if (S == 0 || (int)blockIdx.x >= MB * S) return;
+  const int mb = blockIdx.x % MB, slot = blockIdx.x / MB;
+  const int ntiles = (a.N + 7) / 8;
+  if (slot >= ntiles) return;
+  const int n_my = (ntiles - slot + S - 1) / S;        // tiles slot, slot+S, ...
+  const int ld = a.K + PAD;
+  const int row0 = mb * MROWS;
+
+  // ---- stage activations (optional LayerNorm) as bf16 hi/lo; one warp per row, 2 rows per warp
+  for (int r = warp; r < MROWS; r += NW) {
+    const int row = row0 + r;
+    bf16* hi = sm.hi + r * ld;
+    bf16* lo = sm.lo + r * ld;
+    if (row >= B) {
+      for (int k = lane * 4; k < a.K; k += 128) {
+        *reinterpret_cast<uint2*>(hi + k) = make_uint2(0, 0);
+        *reinterpret_cast<uint2*>(lo + k) = make_uint2(0, 0);
+      }
+      continue;
+    }
+    const float* xr = a.x + size_t(row) * a.ldx;
+    if (a.ln_g) {
+      float4 v[8];                           // K <= 1024
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i * 128 < a.K) {
+          v[i] = ldcg4(xr + i * 128 + lane * 4);
+          sum += v[i].x + v[i].y + v[i].z + v[i].w;
+        }
+      const float mean = warp_sum(sum) / float(a.K);
+      float sq = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i * 128 < a.K) {
+          const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+          sq += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+        }
+      const float rstd = 1.0f / sqrtf(warp_sum(sq) / float(a.K) + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (i * 128 < a.K) {
+          const int k = i * 128 + lane * 4;
+          const float4 gm = __ldg(reinterpret_cast<const float4*>(a.ln_g + k));
+          const float4 bt = __ldg(reinterpret_cast<const float4*>(a.ln_b + k));
+          float4 o;
+          o.x = (v[i].x - mean) * rstd * gm.x + bt.x;
+          o.y = (v[i].y - mean) * rstd * gm.y + bt.y;
+          o.z = (v[i].z - mean) * rstd * gm.z + bt.z;
+          o.w = (v[i].w - mean) * rstd * gm.w + bt.w;
+          store_hilo4(hi + k, lo + k, o);
+        }
+    } else {
+      for (int k = lane * 4; k < a.K; k += 128) store_hilo4(hi + k, lo + k, ldcg4(xr + k));
+    }
+  }
+  __syncthreads();
+
+  // ---- tensor-core passes.  K is cut into a FIXED number of chunks that depends on K only (never on the batch or
+  // the grid), every (tile, chunk) partial sum starts from zero and the chunks are added in index order, so the
+  // result of a row is bit-identical whatever batch it is decoded in (batch invariance).
+  int nch = 8;
+  while (nch > 1 && a.K % (32 * nch) != 0) nch >>= 1;
+  const int kc = a.K / nch;                                  // multiple of 32, <= 256 for K <= 2048
+  float4* red = reinterpret_cast<float4*>(sm.red);           // [NW tiles][8 chunks][32 lanes]
+  for (int base = 0; base < n_my; base += NW) {
+    const int nr = min(NW, n_my - base);
+    for (int q = warp; q < nr * nch; q += NW) {
+      const int ti = q / nch, ch = q % nch;
+      const int tile = slot + (base + ti) * S;
+      const int k0 = ch * kc;
+      const bf16* wrow = a.w + size_t(tile * 8 + g) * a.K + k0 + c * 8;
+      const bf16* ah = sm.hi + g * ld + k0 + c * 8;
+      const bf16* al = sm.lo + g * ld + k0 + c * 8;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int kb = 0; kb < kc; kb += 128) {                 // 4 x 16-byte weight loads in flight per lane
+        uint4 wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (kb + u * 32 < kc) wv[u] = __ldg(reinterpret_cast<const uint4*>(wrow + kb + u * 32));
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (kb + u * 32 < kc) {
+            const int k = kb + u * 32;
+            const uint4 h0 = *reinterpret_cast<const uint4*>(ah + k);
+            const uint4 h1 = *reinterpret_cast<const uint4*>(ah + 8 * ld + k);
+            const uint4 l0 = *reinterpret_cast<const uint4*>(al + k);
+            const uint4 l1 = *reinterpret_cast<const uint4*>(al + 8 * ld + k);
+            mma16816(acc, h0.x, h1.x, h0.y, h1.y, wv[u].x, wv[u].y);
+            mma16816(acc, h0.z, h1.z, h0.w, h1.w, wv[u].z, wv[u].w);
+            mma16816(acc, l0.x, l1.x, l0.y, l1.y, wv[u].x, wv[u].y);
+            mma16816(acc, l0.z, l1.z, l0.w, l1.w, wv[u].z, wv[u].w);
+          }
+      }
+      red[(ti * 8 + ch) * 32 + lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    }
+    __syncthreads();
+    if (warp < nr) {
+      const int tile = slot + (base + warp) * S;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int ch = 0; ch < nch; ++ch) {
+        const float4 t = red[(warp * 8 + ch) * 32 + lane];
+        acc[0] += t.x; acc[1] += t.y; acc[2] += t.z; acc[3] += t.w;
+      }
+      const int col = tile * 8 + 2 * c;
+      if (col < a.N) {
+        const bool two = col + 1 < a.N;
+        const float b0 = a.bias ? __ldg(a.bias + col) : 0.f;
+        const float b1 = (a.bias && two) ? __ldg(a.bias + col + 1) : 0.f;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int row = row0 + g + hh * 8;
+          if (row >= B) continue;
+          float v0 = acc[hh * 2] + b0, v1 = acc[hh * 2 + 1] + b1;
+          if (a.relu) {
+            v0 = fmaxf(v0, 0.f);
+            v1 = fmaxf(v1, 0.f);
+          }
+          float* op = a.out + size_t(row) * a.ldo + col;
+          if (a.epi == EPI_RESIDUAL) {
+            v0 += __ldcg(op);
+            if (two) v1 += __ldcg(op + 1);
+          }
+          op[0] = v0;
+          if (two) op[1] = v1;
+          if (a.epi == EPI_QKV && col >= a.cache_col0) {
+            const int w = a.N - a.cache_col0;
+            bf16* kp = a.cache + (size_t(row) * a.cache_rows + a.step) * w + (col - a.cache_col0);
+            kp[0] = __float2bfloat16(v0);
+            if (two) kp[1] = __float2bfloat16(v1);
+          }
+        }
+      }
+    }
+    if (base + NW < n_my) __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Utterance-local helpers (one CTA = one utterance, M = 1)
+
+// y[n] = W[n, :] . x + bias[n]  for n < N; x given as bf16 hi/lo rows in smem (row 0 of the staging buffers).
+// Warp w handles 8-column tiles w, w+8, ...; only MMA row 0 carries data.  Result written to y (smem, fp32).
+__device__ void matvec_cta(const bf16* xhi, const bf16* xlo, int K, const bf16* W, const float* bias, int N, float* y) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+  const int ntiles = (N + 7) / 8;
+  for (int tile = warp; tile < ntiles; tile += NW) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const bf16* wrow = W + size_t(tile * 8 + g) * K + c * 8;
+    for (int kb = 0; kb < K; kb += 128) {
+      uint4 wv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (kb + u * 32 < K) wv[u] = __ldg(reinterpret_cast<const uint4*>(wrow + kb + u * 32));
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (kb + u * 32 < K) {
+          const int k = kb + u * 32 + c * 8;
+          uint4 h0 = make_uint4(0, 0, 0, 0), l0 = make_uint4(0, 0, 0, 0);
+          if (g == 0) {
+            h0 = *reinterpret_cast<const uint4*>(xhi + k);
+            l0 = *reinterpret_cast<const uint4*>(xlo + k);
+          }
+          mma16816(acc, h0.x, 0u, h0.y, 0u, wv[u].x, wv[u].y);
+          mma16816(acc, h0.z, 0u, h0.w, 0u, wv[u].z, wv[u].w);
+          mma16816(acc, l0.x, 0u, l0.y, 0u, wv[u].x, wv[u].y);
+          mma16816(acc, l0.z, 0u, l0.w, 0u, wv[u].z, wv[u].w);
+        }
+    }
+    if (g == 0) {
+      const int col = tile * 8 + 2 * c;
+      if (col < N) y[col] = acc[0] + (bias ? __ldg(bias + col) : 0.f);
+      if (col + 1 < N) y[col + 1] = acc[1] + (bias ? __ldg(bias + col + 1) : 0.f);
+    }
+  }
+}
+
+// x (smem fp32 [D]) -> optional LayerNorm -> bf16 hi/lo row 0 of the staging buffers. Executed by warp 0.
+__device__ void stage_vec(const float* x, int D, const float* g, const float* b, bf16* hi, bf16* lo) {
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x >= 32) return;
+  float mean = 0.f, rstd = 1.f;
+  if (g) {
+    float sum = 0.f;
+    for (int k = lane; k < D; k += 32) sum += x[k];
+    mean = warp_sum(sum) / float(D);
+    float sq = 0.f;
+    for (int k = lane; k < D; k += 32) {
+      const float d = x[k] - mean;
+      sq += d * d;
+    }
+    rstd = 1.0f / sqrtf(warp_sum(sq) / float(D) + 1e-5f);
+  }
+  for (int k = lane * 4; k < D; k += 128) {
+    float4 v = *reinterpret_cast<const float4*>(x + k);
+    if (g) {
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(g + k));
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(b + k));
+      v.x = (v.x - mean) * rstd * gm.x + bt.x;
+      v.y = (v.y - mean) * rstd * gm.y + bt.y;
+      v.z = (v.z - mean) * rstd * gm.z + bt.z;
+      v.w = (v.w - mean) * rstd * gm.w + bt.w;
+    }
+    store_hilo4(hi + k, lo + k, v);
+  }
+}
+
+// Single-query attention for all H heads of one utterance. q: smem fp32 [H*64] (unscaled); K/V rows of 2 x H*64 bf16
+// (k at kbase, v at vbase, row stride ldkv elements); out: smem fp32 [H*64].
+// Warp w serves head w % H with key subset (w / H) of NW / H; 8 lanes per 128-byte key row, 4 keys per warp pass.
+template <bool COHERENT>
+__device__ void attention_cta(const float* q, const bf16* kbase, const bf16* vbase, int ldkv, int n, int H, float scale,
+                              const Smem& sm, int sc_ld, float* out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c8 = lane & 7, sub = lane >> 3;
+  const int wph = NW / H > 0 ? NW / H : 1;          // warps per head (H <= NW assumed by the launcher)
+  const int h = warp % H, part = warp / H;
+  const bool active = part < wph;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  float qv[8];
+  {
+    const float4 a = *reinterpret_cast<const float4*>(q + h * 64 + c8 * 8);
+    const float4 b = *reinterpret_cast<const float4*>(q + h * 64 + c8 * 8 + 4);
+    qv[0] = a.x * scale; qv[1] = a.y * scale; qv[2] = a.z * scale; qv[3] = a.w * scale;
+    qv[4] = b.x * scale; qv[5] = b.y * scale; qv[6] = b.z * scale; qv[7] = b.w * scale;
+  }
+  float* sc = sm.sc + h * sc_ld;
+  const int stride = wph * 4;
+  const bf16* kp = kbase + h * 64 + c8 * 8;
+  const bf16* vp = vbase + h * 64 + c8 * 8;
+  float mx = -INFINITY;
+  if (active) {
+    for (int kj = part * 4 + sub; kj < n; kj += stride) {
+      const uint4* ptr = reinterpret_cast<const uint4*>(kp + size_t(kj) * ldkv);
+      const uint4 kv = COHERENT ? __ldcg(ptr) : __ldg(ptr);
+      const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kv);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(k2[i]);
+        s = fmaf(qv[2 * i], f.x, s);
+        s = fmaf(qv[2 * i + 1], f.y, s);
+      }
+      s += __shfl_xor_sync(gmask, s, 1);
+      s += __shfl_xor_sync(gmask, s, 2);
+      s += __shfl_xor_sync(gmask, s, 4);
+      if (c8 == 0) sc[kj] = s;
+      mx = fmaxf(mx, s);
+    }
+  }
+  mx = warp_max(mx);
+  if (lane == 0) sm.stat[warp] = mx;
+  __syncthreads();
+  float hmx = -INFINITY;
+  for (int pI = 0; pI < wph; ++pI) hmx = fmaxf(hmx, sm.stat[pI * H + h]);
+  __syncthreads();
+  // probabilities (each warp of the head exponentiates its own keys again: it wrote them) + partial sums
+  float sum = 0.f;
+  float o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+  if (active) {
+    for (int kj = part * 4 + sub; kj < n; kj += stride) {
+      const float pw = __expf(sc[kj] - hmx);
+      if (c8 == 0) sum += pw;
+      const uint4* ptr = reinterpret_cast<const uint4*>(vp + size_t(kj) * ldkv);
+      const uint4 vv = COHERENT ? __ldcg(ptr) : __ldg(ptr);
+      const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(v2[i]);
+        o[2 * i] = fmaf(pw, f.x, o[2 * i]);
+        o[2 * i + 1] = fmaf(pw, f.y, o[2 * i + 1]);
+      }
+    }
+  }
+  // reduce the 4 key sub-groups of the warp (lanes with equal c8), then the warps of the head through smem
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
+    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) sm.stat[NW + warp] = sum;
+  if (sub == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm.part[warp * 64 + c8 * 8 + i] = o[i];
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < H * 64; d += NT) {
+    const int hh = d >> 6, dd = d & 63;
+    float t = 0.f, l = 0.f;
+    for (int pI = 0; pI < wph; ++pI) {
+      t += sm.part[(pI * H + hh) * 64 + dd];
+      l += sm.stat[NW + pI * H + hh];
+    }
+    out[d] = l > 0.f ? t / l : 0.f;
+  }
+  __syncthreads();
+}
+
+}  // namespace
+
+namespace {
+
+__global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_constant__ PersistentParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  Smem sm;
+  {
+    uint8_t* ptr = smem_raw;
+    const int ld = p.kmax + PAD;
+    sm.hi = reinterpret_cast<bf16*>(ptr); ptr += size_t(MROWS) * ld * 2;
+    sm.lo = reinterpret_cast<bf16*>(ptr); ptr += size_t(MROWS) * ld * 2;
+    sm.red = reinterpret_cast<float*>(ptr); ptr += NW * 8 * 32 * 16;
+    sm.vec = reinterpret_cast<float*>(ptr); ptr += size_t(4) * p.kmax * 4;
+    sm.part = reinterpret_cast<float*>(ptr); ptr += NW * 64 * 4;
+    sm.stat = reinterpret_cast<float*>(ptr); ptr += 64 * 4;
+    sm.sc = reinterpret_cast<float*>(ptr);
+  }
+  const int D = p.D, B = p.B;
+  unsigned target = 0;
+  float* v_h = sm.vec;                 // [D] residual row
+  float* v_x = sm.vec + p.kmax;        // [D] attention output / scratch
+  float* v_q = sm.vec + 2 * p.kmax;    // [D] query
+  float* v_l = sm.vec + 3 * p.kmax;    // logits (V <= kmax)
+
+  for (int t = 0; t < p.L; ++t) {
+    for (int l = 0; l < p.nd; ++l) {
+      const PersistentLayer& w = p.layer[l];
+      bf16* cache = p.cache + size_t(l) * B * p.L * 2 * D;
+      const bf16* ckv = p.ckv + size_t(l) * B * p.Tp * 2 * D;
+      {  // ---- A: LN1 + QKV, append K/V (model.py:67-68, layers.py:16-18)
+        LinArgs a;
+        a.x = p.h; a.ldx = D; a.K = D; a.ln_g = w.ln1_g; a.ln_b = w.ln1_b; a.w = w.w_qkv; a.bias = w.b_qkv;
+        a.N = 3 * D; a.relu = 0; a.epi = EPI_QKV; a.out = p.qkv; a.ldo = 3 * D;
+        a.cache = cache; a.cache_rows = p.L; a.cache_col0 = D; a.step = t;
+        linear_phase(a, B, sm);
+      }
+      grid_barrier(p.barrier, target);
+      // ---- B: utterance-local attention chain
+      for (int u = blockIdx.x; u < B; u += gridDim.x) {
+        for (int d = threadIdx.x * 4; d < D; d += NT * 4) {
+          *reinterpret_cast<float4*>(v_h + d) = ldcg4(p.h + size_t(u) * D + d);
+          *reinterpret_cast<float4*>(v_q + d) = ldcg4(p.qkv + size_t(u) * 3 * D + d);
+        }
+        __syncthreads();
+        const bf16* kc = cache + size_t(u) * p.L * 2 * D;
+        attention_cta<true>(v_q, kc, kc + D, 2 * D, t + 1, p.H, p.scale, sm, p.sc_ld, v_x);
+        stage_vec(v_x, D, nullptr, nullptr, sm.hi, sm.lo);
+        __syncthreads();
+        matvec_cta(sm.hi, sm.lo, D, w.w_o, w.b_o, D, v_x);             // out projection
+        __syncthreads();
+        for (int d = threadIdx.x; d < D; d += NT) v_h[d] += v_x[d];   // residual (model.py:68)
+        __syncthreads();
+        stage_vec(v_h, D, w.ln2_g, w.ln2_b, sm.hi, sm.lo);             // LN2 (model.py:70)
+        __syncthreads();
+        matvec_cta(sm.hi, sm.lo, D, w.w_qc, w.b_qc, D, v_q);           // cross-attention query
+        __syncthreads();
+        const bf16* ck = ckv + size_t(u) * p.Tp * 2 * D;
+        attention_cta<false>(v_q, ck, ck + D, 2 * D, p.Tp, p.H, p.scale, sm, p.sc_ld, v_x);
+        stage_vec(v_x, D, nullptr, nullptr, sm.hi, sm.lo);
+        __syncthreads();
+        matvec_cta(sm.hi, sm.lo, D, w.w_oc, w.b_oc, D, v_x);
+        __syncthreads();
+        for (int d = threadIdx.x; d < D; d += NT) p.h[size_t(u) * D + d] = v_h[d] + v_x[d];   // residual (model.py:71)
+        __syncthreads();
+      }
+      grid_barrier(p.barrier, target);
+      {  // ---- C: LN3 + FFN squeeze + ReLU (model.py:73-74, layers.py:54-55)
+        LinArgs a;
+        a.x = p.h; a.ldx = D; a.K = D; a.ln_g = w.ln3_g; a.ln_b = w.ln3_b; a.w = w.w1; a.bias = w.b1;
+        a.N = p.FF; a.relu = 1; a.epi = EPI_STORE; a.out = p.ff; a.ldo = p.FF;
+        a.cache = nullptr; a.cache_rows = 0; a.cache_col0 = 0; a.step = 0;
+        linear_phase(a, B, sm);
+      }
+      grid_barrier(p.barrier, target);
+      {  // ---- D: FFN unsqueeze + residual
+        LinArgs a;
+        a.x = p.ff; a.ldx = p.FF; a.K = p.FF; a.ln_g = nullptr; a.ln_b = nullptr; a.w = w.w2; a.bias = w.b2;
+        a.N = D; a.relu = 0; a.epi = EPI_RESIDUAL; a.out = p.h; a.ldo = D;
+        a.cache = nullptr; a.cache_rows = 0; a.cache_col0 = 0; a.step = 0;
+        linear_phase(a, B, sm);
+      }
+      grid_barrier(p.barrier, target);
+    }
+    // ---- E: classifier (no final LayerNorm, model.py:142) + argmax + EOS + next embedding
+    for (int u = blockIdx.x; u < B; u += gridDim.x) {
+      for (int d = threadIdx.x * 4; d < D; d += NT * 4)
+        *reinterpret_cast<float4*>(v_h + d) = ldcg4(p.h + size_t(u) * D + d);
+      __syncthreads();
+      stage_vec(v_h, D, nullptr, nullptr, sm.hi, sm.lo);
+      __syncthreads();
+      matvec_cta(sm.hi, sm.lo, D, p.classifier, nullptr, p.V, v_l);
+      __syncthreads();
+      if (p.step_logits)
+        for (int v = threadIdx.x; v < p.V; v += NT) p.step_logits[(size_t(u) * p.L + t) * p.V + v] = v_l[v];
+      if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int v = lane; v < p.V; v += 32)
+          if (v_l[v] > best) {
+            best = v_l[v];
+            bi = v;
+          }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob > best || (ob == best && oi < bi)) {
+            best = ob;
+            bi = oi;
+          }
+        }
+        if (bi == 0x7fffffff) bi = 0;
+        int tok = bi;
+        if (p.stop_at_eos) {
+          const int fin = p.finished[u];
+          if (fin) tok = p.pad;
+          else if (tok == p.eos && lane == 0) {
+            p.finished[u] = 1;
+            if (p.n_tokens) p.n_tokens[u] = t + 2;
+            atomicAdd(p.done_count, 1u);
+          }
+        }
+        if (lane == 0) {
+          p.tokens[size_t(u) * (p.L + 1) + t + 1] = tok;
+          sm.stat[32] = __int_as_float(tok);
+        }
+      }
+      __syncthreads();
+      if (t + 1 < p.L) {   // embedding + positional encoding of the next input token (model.py:137)
+        const int tok = __float_as_int(sm.stat[32]);
+        for (int d = threadIdx.x * 4; d < D; d += NT * 4) {
+          const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + size_t(tok) * D + d));
+          const float4 q = __ldg(reinterpret_cast<const float4*>(p.pe + size_t(t + 1) * D + d));
+          *reinterpret_cast<float4*>(p.h + size_t(u) * D + d) = make_float4(e.x + q.x, e.y + q.y, e.z + q.z, e.w + q.w);
+        }
+      }
+      __syncthreads();
+    }
+    grid_barrier(p.barrier, target);
+    if (p.stop_at_eos && ld_acquire_u32(p.done_count) >= (unsigned)B) break;   // uniform: read after the barrier
+  }
+}
+
+}  // namespace
+
+size_t persistent_smem_bytes(int D, int FF, int V, int L, int Tp, int H) {
+  int kmax = D > FF ? D : FF;
+  if (V > kmax) kmax = (V + 127) / 128 * 128;
+  const int sc_ld = ((L > Tp ? L : Tp) + 3) & ~3;
+  return size_t(2) * MROWS * (kmax + PAD) * 2 + NW * 8 * 32 * 16 + size_t(4) * kmax * 4 + NW * 64 * 4 + 64 * 4 +
+         size_t(H) * sc_ld * 4 + 16;
+}
+
+int launch_dec_persistent(PersistentParams& p, cudaStream_t s) {
+  if (p.nd > PERSIST_MAX_LAYERS) return set_error(-2, "persistent decoder: more than %d layers", PERSIST_MAX_LAYERS);
+  if (p.H > NW || NW % p.H != 0) return set_error(-2, "persistent decoder: num_heads %d must divide %d", p.H, NW);
+  if (p.D % 128 != 0 || p.D > 1024 || p.FF % 64 != 0 || p.FF > 2048)
+    return set_error(-2, "persistent decoder: unsupported D=%d / FF=%d", p.D, p.FF);
+  p.kmax = p.D > p.FF ? p.D : p.FF;
+  if (p.V > p.kmax) p.kmax = (p.V + 127) / 128 * 128;
+  p.sc_ld = ((p.L > p.Tp ? p.L : p.Tp) + 3) & ~3;
+  const size_t smem = persistent_smem_bytes(p.D, p.FF, p.V, p.L, p.Tp, p.H);
+  if (smem > 227 * 1024) return set_error(-2, "persistent decoder: needs %zu B of shared memory", smem);
+  static size_t configured = 0;
+  if (smem > configured) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(dec_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int dev = 0, sms = 0, per_sm = 0;
+  ASR_CUDA_OK(cudaGetDevice(&dev));
+  ASR_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  ASR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dec_persistent_kernel, NT, smem));
+  if (per_sm < 1) return set_error(-2, "persistent decoder: kernel does not fit on an SM");
+  ASR_CUDA_OK(cudaMemsetAsync(p.barrier, 0, 2 * sizeof(unsigned), s));   // barrier + done_count are adjacent
+  void* args[] = {&p};
+  ASR_CUDA_OK(cudaLaunchCooperativeKernel((void*)dec_persistent_kernel, dim3(sms), dim3(NT), args, smem, s));
+  ASR_LAUNCHED(1);
+  return 0;
+}
+
+}  // namespace asr

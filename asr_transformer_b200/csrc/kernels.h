@@ -135,4 +135,35 @@ int launch_dec_select_embed(const DecSelect& p, const float* emb, const float* p
 int launch_dec_embed(const int32_t* tokens, int ld_tok, const int32_t* step, const float* emb, const float* pe, int B,
                      int D, int vocab, float* h, cudaStream_t s);
 
+// ---- persistent cooperative greedy decoder (decode_persistent.cu): one launch for all L steps
+struct PersistentLayer {
+  const float *ln1_g, *ln1_b;
+  const bf16* w_qkv; const float* b_qkv;
+  const bf16* w_o; const float* b_o;
+  const float *ln2_g, *ln2_b;
+  const bf16* w_qc; const float* b_qc;
+  const bf16* w_oc; const float* b_oc;
+  const float *ln3_g, *ln3_b;
+  const bf16* w1; const float* b1;
+  const bf16* w2; const float* b2;
+};
+constexpr int PERSIST_MAX_LAYERS = 16;
+
+struct PersistentParams {
+  int B, D, H, FF, V, L, Tp, nd;
+  PersistentLayer layer[PERSIST_MAX_LAYERS];
+  const bf16* classifier; const float* emb; const float* pe;
+  bf16* cache;            // [nd][B][L][2D]
+  const bf16* ckv;        // [nd][B*Tp][2D]
+  float *h, *qkv, *ff;    // [B][D], [B][3D], [B][FF]
+  int32_t* tokens; int32_t* n_tokens; int32_t* finished; float* step_logits;
+  unsigned* barrier;      // zeroed before launch
+  unsigned* done_count;   // zeroed before launch (stop_at_eos early exit)
+  int eos, pad, stop_at_eos, kmax, sc_ld;
+  float scale;
+};
+
+size_t persistent_smem_bytes(int D, int FF, int V, int L, int Tp, int H);
+int launch_dec_persistent(PersistentParams& p, cudaStream_t s);
+
 }  // namespace asr

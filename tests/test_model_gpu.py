@@ -49,7 +49,10 @@ def check_tokens(ref_tokens, ref_logits, got_tokens, min_frac=0.99):
     return r, frac
 
 
-def test_greedy_tokens_T0(t0):
+@pytest.mark.parametrize("mode", ["persistent", "graph", "eager"])
+def test_greedy_tokens_T0(t0, mode, monkeypatch):
+    """All three launch modes of asr_decode_greedy (ASR_B200_DECODE) against the reference's tokens and logits."""
+    monkeypatch.setenv("ASR_B200_DECODE", mode)
     cfg, fx, m, spec = t0
     tokens, n_tok, logits = m.greedy_decode(spec, return_logits=True)
     torch.cuda.synchronize()
@@ -101,6 +104,21 @@ def test_batch_invariance_T0(t0):
     rep = torch.cat([spec, spec, spec], 0)
     t3, _ = m.greedy_decode(rep)
     assert torch.equal(t3[:cfg.batch], full) and torch.equal(t3[2 * cfg.batch:], full)
+
+
+def test_persistent_matches_per_kernel_step_C2(monkeypatch):
+    """The persistent cooperative kernel and the per-kernel (graph) step are two schedules of the same arithmetic."""
+    cfg = O.CONFIGS["C2"]
+    m = build_model(cfg, DEV)
+    spec = O.structured_spectrum(64, cfg.frames, cfg.input_dim, seed=21).to(DEV)
+    monkeypatch.setenv("ASR_B200_DECODE", "graph")
+    tg, _, lg = m.greedy_decode(spec, return_logits=True)
+    monkeypatch.setenv("ASR_B200_DECODE", "persistent")
+    tp, _, lp = m.greedy_decode(spec, return_logits=True)
+    r = O.compare_tokens(tg, lg.cpu(), tp, TAU)
+    assert not r["hard"] and r["identical"] >= 62, r
+    same = [b for b in range(64) if torch.equal(tg[b], tp[b])]
+    assert_close(lp[same], lg[same], 1e-3, 1e-4, "persistent vs graph step logits")
 
 
 def test_empty_batch(t0):

@@ -16,6 +16,7 @@ case $g in
   model) run model tests/test_model_gpu.py -m gpu ;;
   smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -n 2 gpurun_out/smoke.log ;;
   bench) timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -c 3000 gpurun_out/bench.log; tail -n 5 gpurun_out/bench.err ;;
+  benchgraph) timeout 600 python bench.py --steps 5 --warmup 3 --decode-mode graph --no-cpu-baseline > gpurun_out/benchgraph.log 2> gpurun_out/benchgraph.err; echo "benchgraph exit $?"; tail -c 3000 gpurun_out/benchgraph.log; tail -n 5 gpurun_out/benchgraph.err ;;
   benchref) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/benchref.log 2>&1; echo "benchref exit $?"; tail -c 1500 gpurun_out/benchref.log ;;
 esac
 done
