@@ -93,9 +93,55 @@ struct LinArgs {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
+// Tensor-core part of the grid-split linear.  LPU = 16-byte weight loads per (tile, K chunk) unit; 8 / LPU units are
+// kept in flight per warp so that 8 independent loads are outstanding before the first MMA.
+template <int LPU>
+__device__ __noinline__ void mma_units(const LinArgs& a, const Smem& sm, int nunits, int nch, int kc, int slot, int S,
+                                          int base, int ld) {
+  constexpr int UF = 8 / LPU;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+  float4* red = reinterpret_cast<float4*>(sm.red);
+  for (int j0 = 0; warp + j0 * NW < nunits; j0 += UF) {
+    uint4 wv[UF][LPU];
+#pragma unroll
+    for (int f = 0; f < UF; ++f) {
+      const int q = warp + (j0 + f) * NW;
+      if (q < nunits) {
+        const int ti = q / nch, ch = q % nch;
+        const int tile = slot + (base + ti) * S;
+        const bf16* wrow = a.w + size_t(tile * 8 + g) * a.K + ch * kc + c * 8;
+#pragma unroll
+        for (int u = 0; u < LPU; ++u) wv[f][u] = __ldg(reinterpret_cast<const uint4*>(wrow + u * 32));
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < UF; ++f) {
+      const int q = warp + (j0 + f) * NW;
+      if (q < nunits) {
+        const int ti = q / nch, ch = q % nch;
+        const bf16* ah = sm.hi + g * ld + ch * kc + c * 8;
+        const bf16* al = sm.lo + g * ld + ch * kc + c * 8;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int u = 0; u < LPU; ++u) {
+          const uint4 h0 = *reinterpret_cast<const uint4*>(ah + u * 32);
+          const uint4 h1 = *reinterpret_cast<const uint4*>(ah + 8 * ld + u * 32);
+          const uint4 l0 = *reinterpret_cast<const uint4*>(al + u * 32);
+          const uint4 l1 = *reinterpret_cast<const uint4*>(al + 8 * ld + u * 32);
+          mma16816(acc, h0.x, h1.x, h0.y, h1.y, wv[f][u].x, wv[f][u].y);
+          mma16816(acc, h0.z, h1.z, h0.w, h1.w, wv[f][u].z, wv[f][u].w);
+          mma16816(acc, l0.x, l1.x, l0.y, l1.y, wv[f][u].x, wv[f][u].y);
+          mma16816(acc, l0.z, l1.z, l0.w, l1.w, wv[f][u].z, wv[f][u].w);
+        }
+        red[(ti * 8 + ch) * 32 + lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      }
+    }
+  }
+}
+
 // Grid-split linear: out[B, N] = epi( LN?(x)[B, K] * W^T + bias ).  CTA -> (16-row block, set of 8-column tiles);
-// the CTA's 8 warps are spread over (tile, K split); partial sums are reduced through smem.
-__device__ void linear_phase(const LinArgs& a, int B, const Smem& sm) {
+// the CTA's 8 warps are spread over (tile, K chunk) units; partial sums are reduced through smem in a fixed order.
+__device__ __noinline__ void linear_phase(const LinArgs& a, int B, const Smem& sm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   const int MB = (B + MROWS - 1) / MROWS;
   const int S = gridDim.x / MB;             // CTAs ("slots") per row block
@@ -107,52 +153,60 @@ __device__ void linear_phase(const LinArgs& a, int B, const Smem& sm) {
   const int ld = a.K + PAD;
   const int row0 = mb * MROWS;
 
-  // ---- stage activations (optional LayerNorm) as bf16 hi/lo; one warp per row, 2 rows per warp
-  for (int r = warp; r < MROWS; r += NW) {
-    const int row = row0 + r;
-    bf16* hi = sm.hi + r * ld;
-    bf16* lo = sm.lo + r * ld;
-    if (row >= B) {
-      for (int k = lane * 4; k < a.K; k += 128) {
-        *reinterpret_cast<uint2*>(hi + k) = make_uint2(0, 0);
-        *reinterpret_cast<uint2*>(lo + k) = make_uint2(0, 0);
-      }
-      continue;
+  // ---- stage activations (optional LayerNorm) as bf16 hi/lo: warp w owns rows w and w + 8, both loaded up front
+  if (a.ln_g) {                              // K = D <= 512 on this path (launcher check)
+    float4 v[2][4];
+    float mean[2], rstd[2];
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = row0 + warp + rr * 8;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i * 128 < a.K)
+          v[rr][i] = row < B ? ldcg4(a.x + size_t(row) * a.ldx + i * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float* xr = a.x + size_t(row) * a.ldx;
-    if (a.ln_g) {
-      float4 v[8];                           // K <= 1024
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
       float sum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i * 128 < a.K) {
-          v[i] = ldcg4(xr + i * 128 + lane * 4);
-          sum += v[i].x + v[i].y + v[i].z + v[i].w;
-        }
-      const float mean = warp_sum(sum) / float(a.K);
+      for (int i = 0; i < 4; ++i)
+        if (i * 128 < a.K) sum += v[rr][i].x + v[rr][i].y + v[rr][i].z + v[rr][i].w;
+      mean[rr] = warp_sum(sum) / float(a.K);
       float sq = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 4; ++i)
         if (i * 128 < a.K) {
-          const float d0 = v[i].x - mean, d1 = v[i].y - mean, d2 = v[i].z - mean, d3 = v[i].w - mean;
+          const float d0 = v[rr][i].x - mean[rr], d1 = v[rr][i].y - mean[rr], d2 = v[rr][i].z - mean[rr],
+                      d3 = v[rr][i].w - mean[rr];
           sq += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
         }
-      const float rstd = 1.0f / sqrtf(warp_sum(sq) / float(a.K) + 1e-5f);
+      rstd[rr] = 1.0f / sqrtf(warp_sum(sq) / float(a.K) + 1e-5f);
+    }
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (i * 128 < a.K) {
-          const int k = i * 128 + lane * 4;
-          const float4 gm = __ldg(reinterpret_cast<const float4*>(a.ln_g + k));
-          const float4 bt = __ldg(reinterpret_cast<const float4*>(a.ln_b + k));
+    for (int i = 0; i < 4; ++i)
+      if (i * 128 < a.K) {
+        const int k = i * 128 + lane * 4;
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(a.ln_g + k));
+        const float4 bt = __ldg(reinterpret_cast<const float4*>(a.ln_b + k));
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
           float4 o;
-          o.x = (v[i].x - mean) * rstd * gm.x + bt.x;
-          o.y = (v[i].y - mean) * rstd * gm.y + bt.y;
-          o.z = (v[i].z - mean) * rstd * gm.z + bt.z;
-          o.w = (v[i].w - mean) * rstd * gm.w + bt.w;
-          store_hilo4(hi + k, lo + k, o);
+          o.x = (v[rr][i].x - mean[rr]) * rstd[rr] * gm.x + bt.x;
+          o.y = (v[rr][i].y - mean[rr]) * rstd[rr] * gm.y + bt.y;
+          o.z = (v[rr][i].z - mean[rr]) * rstd[rr] * gm.z + bt.z;
+          o.w = (v[rr][i].w - mean[rr]) * rstd[rr] * gm.w + bt.w;
+          const int r = warp + rr * 8;
+          store_hilo4(sm.hi + r * ld + k, sm.lo + r * ld + k, o);
         }
-    } else {
-      for (int k = lane * 4; k < a.K; k += 128) store_hilo4(hi + k, lo + k, ldcg4(xr + k));
+      }
+  } else {
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int r = warp + rr * 8, row = row0 + r;
+      const float* xr = a.x + size_t(row) * a.ldx;
+#pragma unroll 4
+      for (int k = lane * 4; k < a.K; k += 128)
+        store_hilo4(sm.hi + r * ld + k, sm.lo + r * ld + k, row < B ? ldcg4(xr + k) : make_float4(0.f, 0.f, 0.f, 0.f));
     }
   }
   __syncthreads();
@@ -166,35 +220,11 @@ __device__ void linear_phase(const LinArgs& a, int B, const Smem& sm) {
   float4* red = reinterpret_cast<float4*>(sm.red);           // [NW tiles][8 chunks][32 lanes]
   for (int base = 0; base < n_my; base += NW) {
     const int nr = min(NW, n_my - base);
-    for (int q = warp; q < nr * nch; q += NW) {
-      const int ti = q / nch, ch = q % nch;
-      const int tile = slot + (base + ti) * S;
-      const int k0 = ch * kc;
-      const bf16* wrow = a.w + size_t(tile * 8 + g) * a.K + k0 + c * 8;
-      const bf16* ah = sm.hi + g * ld + k0 + c * 8;
-      const bf16* al = sm.lo + g * ld + k0 + c * 8;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-      for (int kb = 0; kb < kc; kb += 128) {                 // 4 x 16-byte weight loads in flight per lane
-        uint4 wv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (kb + u * 32 < kc) wv[u] = __ldg(reinterpret_cast<const uint4*>(wrow + kb + u * 32));
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (kb + u * 32 < kc) {
-            const int k = kb + u * 32;
-            const uint4 h0 = *reinterpret_cast<const uint4*>(ah + k);
-            const uint4 h1 = *reinterpret_cast<const uint4*>(ah + 8 * ld + k);
-            const uint4 l0 = *reinterpret_cast<const uint4*>(al + k);
-            const uint4 l1 = *reinterpret_cast<const uint4*>(al + 8 * ld + k);
-            mma16816(acc, h0.x, h1.x, h0.y, h1.y, wv[u].x, wv[u].y);
-            mma16816(acc, h0.z, h1.z, h0.w, h1.w, wv[u].z, wv[u].w);
-            mma16816(acc, l0.x, l1.x, l0.y, l1.y, wv[u].x, wv[u].y);
-            mma16816(acc, l0.z, l1.z, l0.w, l1.w, wv[u].z, wv[u].w);
-          }
-      }
-      red[(ti * 8 + ch) * 32 + lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    switch (kc / 32) {
+      case 1: mma_units<1>(a, sm, nr * nch, nch, kc, slot, S, base, ld); break;
+      case 2: mma_units<2>(a, sm, nr * nch, nch, kc, slot, S, base, ld); break;
+      case 4: mma_units<4>(a, sm, nr * nch, nch, kc, slot, S, base, ld); break;
+      default: mma_units<8>(a, sm, nr * nch, nch, kc, slot, S, base, ld); break;
     }
     __syncthreads();
     if (warp < nr) {
@@ -243,19 +273,26 @@ __device__ void linear_phase(const LinArgs& a, int B, const Smem& sm) {
 
 // y[n] = W[n, :] . x + bias[n]  for n < N; x given as bf16 hi/lo rows in smem (row 0 of the staging buffers).
 // Warp w handles 8-column tiles w, w+8, ...; only MMA row 0 carries data.  Result written to y (smem, fp32).
-__device__ void matvec_cta(const bf16* xhi, const bf16* xlo, int K, const bf16* W, const float* bias, int N, float* y) {
+// The weight rows of TWO tiles (up to 16 x 16 B per lane) are requested before the first MMA.
+__device__ __noinline__ void matvec_cta(const bf16* xhi, const bf16* xlo, int K, const bf16* W, const float* bias, int N, float* y) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   const int ntiles = (N + 7) / 8;
-  for (int tile = warp; tile < ntiles; tile += NW) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const bf16* wrow = W + size_t(tile * 8 + g) * K + c * 8;
-    for (int kb = 0; kb < K; kb += 128) {
-      uint4 wv[4];
+  for (int tile0 = warp; tile0 < ntiles; tile0 += 2 * NW) {
+    const int tile1 = tile0 + NW;
+    const bool has1 = tile1 < ntiles;
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+    const bf16* w0 = W + size_t(tile0 * 8 + g) * K + c * 8;
+    const bf16* w1 = W + size_t((has1 ? tile1 : tile0) * 8 + g) * K + c * 8;
+    for (int kb = 0; kb < K; kb += 256) {
+      uint4 wa[8], wb[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (kb + u * 32 < K) wv[u] = __ldg(reinterpret_cast<const uint4*>(wrow + kb + u * 32));
+      for (int u = 0; u < 8; ++u)
+        if (kb + u * 32 < K) {
+          wa[u] = __ldg(reinterpret_cast<const uint4*>(w0 + kb + u * 32));
+          wb[u] = __ldg(reinterpret_cast<const uint4*>(w1 + kb + u * 32));
+        }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 8; ++u)
         if (kb + u * 32 < K) {
           const int k = kb + u * 32 + c * 8;
           uint4 h0 = make_uint4(0, 0, 0, 0), l0 = make_uint4(0, 0, 0, 0);
@@ -263,22 +300,31 @@ __device__ void matvec_cta(const bf16* xhi, const bf16* xlo, int K, const bf16* 
             h0 = *reinterpret_cast<const uint4*>(xhi + k);
             l0 = *reinterpret_cast<const uint4*>(xlo + k);
           }
-          mma16816(acc, h0.x, 0u, h0.y, 0u, wv[u].x, wv[u].y);
-          mma16816(acc, h0.z, 0u, h0.w, 0u, wv[u].z, wv[u].w);
-          mma16816(acc, l0.x, 0u, l0.y, 0u, wv[u].x, wv[u].y);
-          mma16816(acc, l0.z, 0u, l0.w, 0u, wv[u].z, wv[u].w);
+          mma16816(acc0, h0.x, 0u, h0.y, 0u, wa[u].x, wa[u].y);
+          mma16816(acc0, h0.z, 0u, h0.w, 0u, wa[u].z, wa[u].w);
+          mma16816(acc0, l0.x, 0u, l0.y, 0u, wa[u].x, wa[u].y);
+          mma16816(acc0, l0.z, 0u, l0.w, 0u, wa[u].z, wa[u].w);
+          mma16816(acc1, h0.x, 0u, h0.y, 0u, wb[u].x, wb[u].y);
+          mma16816(acc1, h0.z, 0u, h0.w, 0u, wb[u].z, wb[u].w);
+          mma16816(acc1, l0.x, 0u, l0.y, 0u, wb[u].x, wb[u].y);
+          mma16816(acc1, l0.z, 0u, l0.w, 0u, wb[u].z, wb[u].w);
         }
     }
     if (g == 0) {
-      const int col = tile * 8 + 2 * c;
-      if (col < N) y[col] = acc[0] + (bias ? __ldg(bias + col) : 0.f);
-      if (col + 1 < N) y[col + 1] = acc[1] + (bias ? __ldg(bias + col + 1) : 0.f);
+      int col = tile0 * 8 + 2 * c;
+      if (col < N) y[col] = acc0[0] + (bias ? __ldg(bias + col) : 0.f);
+      if (col + 1 < N) y[col + 1] = acc0[1] + (bias ? __ldg(bias + col + 1) : 0.f);
+      if (has1) {
+        col = tile1 * 8 + 2 * c;
+        if (col < N) y[col] = acc1[0] + (bias ? __ldg(bias + col) : 0.f);
+        if (col + 1 < N) y[col + 1] = acc1[1] + (bias ? __ldg(bias + col + 1) : 0.f);
+      }
     }
   }
 }
 
 // x (smem fp32 [D]) -> optional LayerNorm -> bf16 hi/lo row 0 of the staging buffers. Executed by warp 0.
-__device__ void stage_vec(const float* x, int D, const float* g, const float* b, bf16* hi, bf16* lo) {
+__device__ __noinline__ void stage_vec(const float* x, int D, const float* g, const float* b, bf16* hi, bf16* lo) {
   const int lane = threadIdx.x & 31;
   if (threadIdx.x >= 32) return;
   float mean = 0.f, rstd = 1.f;
@@ -309,94 +355,131 @@ __device__ void stage_vec(const float* x, int D, const float* g, const float* b,
 
 // Single-query attention for all H heads of one utterance. q: smem fp32 [H*64] (unscaled); K/V rows of 2 x H*64 bf16
 // (k at kbase, v at vbase, row stride ldkv elements); out: smem fp32 [H*64].
-// Warp w serves head w % H with key subset (w / H) of NW / H; 8 lanes per 128-byte key row, 4 keys per warp pass.
+// Warp w serves head w % H with key subset (w / H) of NW / H; 8 lanes per 128-byte key row, 4 key groups per warp.
+// Flash-style single pass: every group keeps a running (max, sum, 8-dim accumulator); 8 keys (K and V rows, 16 x 16 B
+// per lane) are requested before any of them is consumed, so the loop is bandwidth- not latency-bound.
+constexpr int AU = 8;   // keys in flight per group
+
 template <bool COHERENT>
-__device__ void attention_cta(const float* q, const bf16* kbase, const bf16* vbase, int ldkv, int n, int H, float scale,
-                              const Smem& sm, int sc_ld, float* out) {
+__device__ __forceinline__ uint4 ld_kv(const bf16* p) {
+  const uint4* ptr = reinterpret_cast<const uint4*>(p);
+  return COHERENT ? __ldcg(ptr) : __ldg(ptr);
+}
+
+template <bool COHERENT>
+__device__ __noinline__ void attention_cta(const float* q, const bf16* kbase, const bf16* vbase, int ldkv, int n, int H, float scale,
+                              const Smem& sm, float* out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c8 = lane & 7, sub = lane >> 3;
-  const int wph = NW / H > 0 ? NW / H : 1;          // warps per head (H <= NW assumed by the launcher)
+  const int wph = NW / H;                           // warps per head (launcher guarantees NW % H == 0)
   const int h = warp % H, part = warp / H;
-  const bool active = part < wph;
   const unsigned gmask = 0xFFu << (lane & 24);
+  const float kLog2e = 1.4426950408889634f;
   float qv[8];
   {
     const float4 a = *reinterpret_cast<const float4*>(q + h * 64 + c8 * 8);
     const float4 b = *reinterpret_cast<const float4*>(q + h * 64 + c8 * 8 + 4);
-    qv[0] = a.x * scale; qv[1] = a.y * scale; qv[2] = a.z * scale; qv[3] = a.w * scale;
-    qv[4] = b.x * scale; qv[5] = b.y * scale; qv[6] = b.z * scale; qv[7] = b.w * scale;
+    const float sc = scale * kLog2e;                // scores kept in log2 units: p = exp2(s - m)
+    qv[0] = a.x * sc; qv[1] = a.y * sc; qv[2] = a.z * sc; qv[3] = a.w * sc;
+    qv[4] = b.x * sc; qv[5] = b.y * sc; qv[6] = b.z * sc; qv[7] = b.w * sc;
   }
-  float* sc = sm.sc + h * sc_ld;
   const int stride = wph * 4;
   const bf16* kp = kbase + h * 64 + c8 * 8;
   const bf16* vp = vbase + h * 64 + c8 * 8;
-  float mx = -INFINITY;
-  if (active) {
-    for (int kj = part * 4 + sub; kj < n; kj += stride) {
-      const uint4* ptr = reinterpret_cast<const uint4*>(kp + size_t(kj) * ldkv);
-      const uint4 kv = COHERENT ? __ldcg(ptr) : __ldg(ptr);
-      const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kv);
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __bfloat1622float2(k2[i]);
-        s = fmaf(qv[2 * i], f.x, s);
-        s = fmaf(qv[2 * i + 1], f.y, s);
-      }
-      s += __shfl_xor_sync(gmask, s, 1);
-      s += __shfl_xor_sync(gmask, s, 2);
-      s += __shfl_xor_sync(gmask, s, 4);
-      if (c8 == 0) sc[kj] = s;
-      mx = fmaxf(mx, s);
-    }
-  }
-  mx = warp_max(mx);
-  if (lane == 0) sm.stat[warp] = mx;
-  __syncthreads();
-  float hmx = -INFINITY;
-  for (int pI = 0; pI < wph; ++pI) hmx = fmaxf(hmx, sm.stat[pI * H + h]);
-  __syncthreads();
-  // probabilities (each warp of the head exponentiates its own keys again: it wrote them) + partial sums
-  float sum = 0.f;
+  float m = -INFINITY, l = 0.f;
   float o[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = 0.f;
-  if (active) {
-    for (int kj = part * 4 + sub; kj < n; kj += stride) {
-      const float pw = __expf(sc[kj] - hmx);
-      if (c8 == 0) sum += pw;
-      const uint4* ptr = reinterpret_cast<const uint4*>(vp + size_t(kj) * ldkv);
-      const uint4 vv = COHERENT ? __ldcg(ptr) : __ldg(ptr);
-      const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vv);
+
+  for (int k0 = part * 4 + sub; k0 < n; k0 += stride * AU) {   // trip count is uniform inside an 8-lane group
+    uint4 kr[AU], vr[AU];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __bfloat1622float2(v2[i]);
-        o[2 * i] = fmaf(pw, f.x, o[2 * i]);
-        o[2 * i + 1] = fmaf(pw, f.y, o[2 * i + 1]);
+    for (int u = 0; u < AU; ++u) {
+      const int kj = k0 + u * stride;
+      if (kj < n) {
+        kr[u] = ld_kv<COHERENT>(kp + size_t(kj) * ldkv);
+        vr[u] = ld_kv<COHERENT>(vp + size_t(kj) * ldkv);
       }
     }
-  }
-  // reduce the 4 key sub-groups of the warp (lanes with equal c8), then the warps of the head through smem
+    float sc[AU];
+    float bm = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 8);
-    o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+    for (int u = 0; u < AU; ++u) {
+      const int kj = k0 + u * stride;
+      float sv = 0.f;
+      if (kj < n) {
+        const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr[u]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(k2[i]);
+          sv = fmaf(qv[2 * i], f.x, sv);
+          sv = fmaf(qv[2 * i + 1], f.y, sv);
+        }
+      }
+      sv += __shfl_xor_sync(gmask, sv, 1);
+      sv += __shfl_xor_sync(gmask, sv, 2);
+      sv += __shfl_xor_sync(gmask, sv, 4);
+      sc[u] = kj < n ? sv : -INFINITY;
+      bm = fmaxf(bm, sc[u]);
+    }
+    const float m_new = fmaxf(m, bm);               // finite: the batch holds at least one valid key
+    const float alpha = exp2f(m - m_new);           // m == -inf -> 0
+    l *= alpha;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] *= alpha;
+#pragma unroll
+    for (int u = 0; u < AU; ++u) {
+      const float pw = exp2f(sc[u] - m_new);        // masked tail: exp2(-inf) = 0
+      if (k0 + u * stride < n) {
+        l += pw;
+        const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vr[u]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __bfloat1622float2(v2[i]);
+          o[2 * i] = fmaf(pw, f.x, o[2 * i]);
+          o[2 * i + 1] = fmaf(pw, f.y, o[2 * i + 1]);
+        }
+      }
+    }
+    m = m_new;
   }
-  sum = warp_sum(sum);
-  if (lane == 0) sm.stat[NW + warp] = sum;
+  // merge the 4 key groups of the warp (lanes with equal c8), rescaling to the common maximum
+#pragma unroll
+  for (int off = 8; off <= 16; off <<= 1) {
+    const float mo = __shfl_xor_sync(0xffffffffu, m, off);
+    const float lo = __shfl_xor_sync(0xffffffffu, l, off);
+    const float mn = fmaxf(m, mo);
+    const float fa = (m == -INFINITY) ? 0.f : exp2f(m - mn);
+    const float fb = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
+    l = l * fa + lo * fb;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float oo = __shfl_xor_sync(0xffffffffu, o[i], off);
+      o[i] = o[i] * fa + oo * fb;
+    }
+    m = mn;
+  }
   if (sub == 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) sm.part[warp * 64 + c8 * 8 + i] = o[i];
+    if (c8 == 0) {
+      sm.stat[warp] = m;
+      sm.stat[NW + warp] = l;
+    }
   }
   __syncthreads();
-  for (int d = threadIdx.x; d < H * 64; d += NT) {
+  for (int d = threadIdx.x; d < H * 64; d += NT) {   // merge the warps of each head
     const int hh = d >> 6, dd = d & 63;
-    float t = 0.f, l = 0.f;
+    float mm = -INFINITY;
+    for (int pI = 0; pI < wph; ++pI) mm = fmaxf(mm, sm.stat[pI * H + hh]);
+    float t = 0.f, ls = 0.f;
     for (int pI = 0; pI < wph; ++pI) {
-      t += sm.part[(pI * H + hh) * 64 + dd];
-      l += sm.stat[NW + pI * H + hh];
+      const float mw = sm.stat[pI * H + hh];
+      const float f = (mw == -INFINITY) ? 0.f : exp2f(mw - mm);
+      t += sm.part[(pI * H + hh) * 64 + dd] * f;
+      ls += sm.stat[NW + pI * H + hh] * f;
     }
-    out[d] = l > 0.f ? t / l : 0.f;
+    out[d] = ls > 0.f ? t / ls : 0.f;
   }
   __syncthreads();
 }
@@ -447,7 +530,7 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
         }
         __syncthreads();
         const bf16* kc = cache + size_t(u) * p.L * 2 * D;
-        attention_cta<true>(v_q, kc, kc + D, 2 * D, t + 1, p.H, p.scale, sm, p.sc_ld, v_x);
+        attention_cta<true>(v_q, kc, kc + D, 2 * D, t + 1, p.H, p.scale, sm, v_x);
         stage_vec(v_x, D, nullptr, nullptr, sm.hi, sm.lo);
         __syncthreads();
         matvec_cta(sm.hi, sm.lo, D, w.w_o, w.b_o, D, v_x);             // out projection
@@ -459,7 +542,7 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
         matvec_cta(sm.hi, sm.lo, D, w.w_qc, w.b_qc, D, v_q);           // cross-attention query
         __syncthreads();
         const bf16* ck = ckv + size_t(u) * p.Tp * 2 * D;
-        attention_cta<false>(v_q, ck, ck + D, 2 * D, p.Tp, p.H, p.scale, sm, p.sc_ld, v_x);
+        attention_cta<false>(v_q, ck, ck + D, 2 * D, p.Tp, p.H, p.scale, sm, v_x);
         stage_vec(v_x, D, nullptr, nullptr, sm.hi, sm.lo);
         __syncthreads();
         matvec_cta(sm.hi, sm.lo, D, w.w_oc, w.b_oc, D, v_x);
@@ -559,7 +642,7 @@ size_t persistent_smem_bytes(int D, int FF, int V, int L, int Tp, int H) {
 int launch_dec_persistent(PersistentParams& p, cudaStream_t s) {
   if (p.nd > PERSIST_MAX_LAYERS) return set_error(-2, "persistent decoder: more than %d layers", PERSIST_MAX_LAYERS);
   if (p.H > NW || NW % p.H != 0) return set_error(-2, "persistent decoder: num_heads %d must divide %d", p.H, NW);
-  if (p.D % 128 != 0 || p.D > 1024 || p.FF % 64 != 0 || p.FF > 2048)
+  if (p.D % 128 != 0 || p.D > 512 || p.FF % 64 != 0 || p.FF > 2048)
     return set_error(-2, "persistent decoder: unsupported D=%d / FF=%d", p.D, p.FF);
   p.kmax = p.D > p.FF ? p.D : p.FF;
   if (p.V > p.kmax) p.kmax = (p.V + 127) / 128 * 128;
