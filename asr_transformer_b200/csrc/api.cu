@@ -565,7 +565,8 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
 // Same work as asr_decode_greedy, launched eagerly with a CUDA event pair around every kernel; synchronises the
 // stream at the end and returns the summed device time (ms) and launch count per kernel class (DecClass order).
 int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L, void* ws, size_t ws_bytes,
-                       int32_t* tokens, float* ms_per_class, int32_t* launches_per_class, asr_stream_t stream) {
+                       int32_t* tokens, float* ms_per_class, int32_t* launches_per_class, long long* phase_cycles,
+                       asr_stream_t stream) {
   if (!h || !h->loaded || !enc_out || !tokens || !ws || !ms_per_class || !launches_per_class || B <= 0 || L <= 0)
     return set_error(ASR_E_INVALID, "asr_decode_profile: bad argument");
   const AsrConfig& c = h->cfg;
@@ -607,6 +608,7 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
       return rc;
     PersistentParams pp;
     if (int rc = build_persistent(h, w, B, Tp, L, 0, tokens, nullptr, nullptr, pp)) return rc;
+    pp.timing = phase_cycles;   // device buffer [#SMs][10], nullable
     cudaEvent_t e0, e1;
     ASR_CUDA_OK(cudaEventCreate(&e0));
     ASR_CUDA_OK(cudaEventCreate(&e1));

@@ -499,11 +499,24 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
     sm.red = reinterpret_cast<float*>(ptr); ptr += NW * 8 * 32 * 16;
     sm.vec = reinterpret_cast<float*>(ptr); ptr += size_t(4) * p.kmax * 4;
     sm.part = reinterpret_cast<float*>(ptr); ptr += NW * 64 * 4;
-    sm.stat = reinterpret_cast<float*>(ptr); ptr += 64 * 4;
+    sm.stat = reinterpret_cast<float*>(ptr); ptr += 64 * 4;   // [0,2NW) softmax stats, [32] token, [40,60) phase timers
     sm.sc = reinterpret_cast<float*>(ptr);
   }
   const int D = p.D, B = p.B;
   unsigned target = 0;
+  // optional per-phase cycle accounting (asr_decode_profile): thread 0 of every CTA accumulates clock64 deltas
+  long long* tacc = reinterpret_cast<long long*>(sm.stat + 40);   // 10 counters in smem (8-byte aligned)
+  long long t_prev = 0;
+  if (p.timing && threadIdx.x == 0) {
+    for (int i = 0; i < 10; ++i) tacc[i] = 0;
+    t_prev = clock64();
+  }
+#define PHASE_DONE(idx)                                  \
+  if (p.timing && threadIdx.x == 0) {                    \
+    const long long now_ = clock64();                    \
+    tacc[idx] += now_ - t_prev;                          \
+    t_prev = now_;                                       \
+  }
   float* v_h = sm.vec;                 // [D] residual row
   float* v_x = sm.vec + p.kmax;        // [D] attention output / scratch
   float* v_q = sm.vec + 2 * p.kmax;    // [D] query
@@ -521,7 +534,9 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
         a.cache = cache; a.cache_rows = p.L; a.cache_col0 = D; a.step = t;
         linear_phase(a, B, sm);
       }
+      PHASE_DONE(0)
       grid_barrier(p.barrier, target);
+      PHASE_DONE(1)
       // ---- B: utterance-local attention chain
       for (int u = blockIdx.x; u < B; u += gridDim.x) {
         for (int d = threadIdx.x * 4; d < D; d += NT * 4) {
@@ -550,7 +565,9 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
         for (int d = threadIdx.x; d < D; d += NT) p.h[size_t(u) * D + d] = v_h[d] + v_x[d];   // residual (model.py:71)
         __syncthreads();
       }
+      PHASE_DONE(2)
       grid_barrier(p.barrier, target);
+      PHASE_DONE(3)
       {  // ---- C: LN3 + FFN squeeze + ReLU (model.py:73-74, layers.py:54-55)
         LinArgs a;
         a.x = p.h; a.ldx = D; a.K = D; a.ln_g = w.ln3_g; a.ln_b = w.ln3_b; a.w = w.w1; a.bias = w.b1;
@@ -558,7 +575,9 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
         a.cache = nullptr; a.cache_rows = 0; a.cache_col0 = 0; a.step = 0;
         linear_phase(a, B, sm);
       }
+      PHASE_DONE(4)
       grid_barrier(p.barrier, target);
+      PHASE_DONE(5)
       {  // ---- D: FFN unsqueeze + residual
         LinArgs a;
         a.x = p.ff; a.ldx = p.FF; a.K = p.FF; a.ln_g = nullptr; a.ln_b = nullptr; a.w = w.w2; a.bias = w.b2;
@@ -566,7 +585,9 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
         a.cache = nullptr; a.cache_rows = 0; a.cache_col0 = 0; a.step = 0;
         linear_phase(a, B, sm);
       }
+      PHASE_DONE(6)
       grid_barrier(p.barrier, target);
+      PHASE_DONE(7)
     }
     // ---- E: classifier (no final LayerNorm, model.py:142) + argmax + EOS + next embedding
     for (int u = blockIdx.x; u < B; u += gridDim.x) {
@@ -624,9 +645,14 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
       }
       __syncthreads();
     }
+    PHASE_DONE(8)
     grid_barrier(p.barrier, target);
+    PHASE_DONE(9)
     if (p.stop_at_eos && ld_acquire_u32(p.done_count) >= (unsigned)B) break;   // uniform: read after the barrier
   }
+  if (p.timing && threadIdx.x == 0)
+    for (int i = 0; i < 10; ++i) p.timing[size_t(blockIdx.x) * 10 + i] = tacc[i];
+#undef PHASE_DONE
 }
 
 }  // namespace

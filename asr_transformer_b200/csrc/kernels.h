@@ -159,6 +159,7 @@ struct PersistentParams {
   int32_t* tokens; int32_t* n_tokens; int32_t* finished; float* step_logits;
   unsigned* barrier;      // zeroed before launch
   unsigned* done_count;   // zeroed before launch (stop_at_eos early exit)
+  long long* timing;      // nullable: [gridDim][10] per-phase clock64 totals {A,bar,B,bar,C,bar,D,bar,E,bar}
   int eos, pad, stop_at_eos, kmax, sc_ld;
   float scale;
 };

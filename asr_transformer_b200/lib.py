@@ -68,7 +68,7 @@ _SIGNATURES = {
     "asr_decode_greedy": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     "asr_decode_profile": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p,
-                                   c_void_p, c_void_p]),
+                                   c_void_p, c_void_p, c_void_p]),
     "asr_launch_count": (C.c_ulonglong, []),
     "asr_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "asr_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -17,6 +17,9 @@ case $g in
   smoke) timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -n 2 gpurun_out/smoke.log ;;
   bench) timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -c 3000 gpurun_out/bench.log; tail -n 5 gpurun_out/bench.err ;;
   benchgraph) timeout 600 python bench.py --steps 5 --warmup 3 --decode-mode graph --no-cpu-baseline > gpurun_out/benchgraph.log 2> gpurun_out/benchgraph.err; echo "benchgraph exit $?"; tail -c 3000 gpurun_out/benchgraph.log; tail -n 5 gpurun_out/benchgraph.err ;;
+  ncu) CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-profile"
+       $CMD > gpurun_out/ncu_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1; echo "ncu list exit $?"
+       $CMD > gpurun_out/ncu_plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:dec_persistent -c 1 -o gpurun_out/prof_persistent $CMD > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"; ls -la gpurun_out/*.ncu-rep ;;
   benchref) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/benchref.log 2>&1; echo "benchref exit $?"; tail -c 1500 gpurun_out/benchref.log ;;
 esac
 done
