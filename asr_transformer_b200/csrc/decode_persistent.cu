@@ -93,47 +93,46 @@ struct LinArgs {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-// Tensor-core part of the grid-split linear.  LPU = 16-byte weight loads per (tile, K chunk) unit; 8 / LPU units are
-// kept in flight per warp so that 8 independent loads are outstanding before the first MMA.
-template <int LPU>
-__device__ __noinline__ void mma_units(const LinArgs& a, const Smem& sm, int nunits, int nch, int kc, int slot, int S,
+// Tensor-core part of the grid-split linear.  lpu = 16-byte weight loads per (tile, K chunk) unit (1, 2, 4 or 8);
+// 8 / lpu units are kept in flight per warp so that 8 independent loads are outstanding before the first MMA.
+__device__ __forceinline__ void mma_units(const LinArgs& a, const Smem& sm, int nunits, int nch, int kc, int slot, int S,
                                           int base, int ld) {
-  constexpr int UF = 8 / LPU;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+  const int lpu = kc >> 5;                       // power of two
+  const int lsh = 31 - __clz(lpu);
+  const int uf = 8 >> lsh;
   float4* red = reinterpret_cast<float4*>(sm.red);
-  for (int j0 = 0; warp + j0 * NW < nunits; j0 += UF) {
-    uint4 wv[UF][LPU];
+  for (int j0 = 0; warp + j0 * NW < nunits; j0 += uf) {
+    uint4 wv[8];
 #pragma unroll
-    for (int f = 0; f < UF; ++f) {
+    for (int j = 0; j < 8; ++j) {
+      const int f = j >> lsh, u = j & (lpu - 1);
       const int q = warp + (j0 + f) * NW;
       if (q < nunits) {
         const int ti = q / nch, ch = q % nch;
         const int tile = slot + (base + ti) * S;
-        const bf16* wrow = a.w + size_t(tile * 8 + g) * a.K + ch * kc + c * 8;
-#pragma unroll
-        for (int u = 0; u < LPU; ++u) wv[f][u] = __ldg(reinterpret_cast<const uint4*>(wrow + u * 32));
+        wv[j] = __ldg(reinterpret_cast<const uint4*>(a.w + size_t(tile * 8 + g) * a.K + ch * kc + c * 8 + u * 32));
       }
     }
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int f = 0; f < UF; ++f) {
+    for (int j = 0; j < 8; ++j) {
+      const int f = j >> lsh, u = j & (lpu - 1);
       const int q = warp + (j0 + f) * NW;
       if (q < nunits) {
         const int ti = q / nch, ch = q % nch;
-        const bf16* ah = sm.hi + g * ld + ch * kc + c * 8;
-        const bf16* al = sm.lo + g * ld + ch * kc + c * 8;
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int u = 0; u < LPU; ++u) {
-          const uint4 h0 = *reinterpret_cast<const uint4*>(ah + u * 32);
-          const uint4 h1 = *reinterpret_cast<const uint4*>(ah + 8 * ld + u * 32);
-          const uint4 l0 = *reinterpret_cast<const uint4*>(al + u * 32);
-          const uint4 l1 = *reinterpret_cast<const uint4*>(al + 8 * ld + u * 32);
-          mma16816(acc, h0.x, h1.x, h0.y, h1.y, wv[f][u].x, wv[f][u].y);
-          mma16816(acc, h0.z, h1.z, h0.w, h1.w, wv[f][u].z, wv[f][u].w);
-          mma16816(acc, l0.x, l1.x, l0.y, l1.y, wv[f][u].x, wv[f][u].y);
-          mma16816(acc, l0.z, l1.z, l0.w, l1.w, wv[f][u].z, wv[f][u].w);
-        }
-        red[(ti * 8 + ch) * 32 + lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (u == 0) acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+        const bf16* ah = sm.hi + g * ld + ch * kc + c * 8 + u * 32;
+        const bf16* al = sm.lo + g * ld + ch * kc + c * 8 + u * 32;
+        const uint4 h0 = *reinterpret_cast<const uint4*>(ah);
+        const uint4 h1 = *reinterpret_cast<const uint4*>(ah + 8 * ld);
+        const uint4 l0 = *reinterpret_cast<const uint4*>(al);
+        const uint4 l1 = *reinterpret_cast<const uint4*>(al + 8 * ld);
+        mma16816(acc, h0.x, h1.x, h0.y, h1.y, wv[j].x, wv[j].y);
+        mma16816(acc, h0.z, h1.z, h0.w, h1.w, wv[j].z, wv[j].w);
+        mma16816(acc, l0.x, l1.x, l0.y, l1.y, wv[j].x, wv[j].y);
+        mma16816(acc, l0.z, l1.z, l0.w, l1.w, wv[j].z, wv[j].w);
+        if (u == lpu - 1) red[(ti * 8 + ch) * 32 + lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
       }
     }
   }
@@ -141,7 +140,7 @@ __device__ __noinline__ void mma_units(const LinArgs& a, const Smem& sm, int nun
 
 // Grid-split linear: out[B, N] = epi( LN?(x)[B, K] * W^T + bias ).  CTA -> (16-row block, set of 8-column tiles);
 // the CTA's 8 warps are spread over (tile, K chunk) units; partial sums are reduced through smem in a fixed order.
-__device__ __noinline__ void linear_phase(const LinArgs& a, int B, const Smem& sm) {
+__device__ __forceinline__ void linear_phase(const LinArgs& a, int B, const Smem& sm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   const int MB = (B + MROWS - 1) / MROWS;
   const int S = gridDim.x / MB;             // CTAs ("slots") per row block
@@ -220,12 +219,7 @@ __device__ __noinline__ void linear_phase(const LinArgs& a, int B, const Smem& s
   float4* red = reinterpret_cast<float4*>(sm.red);           // [NW tiles][8 chunks][32 lanes]
   for (int base = 0; base < n_my; base += NW) {
     const int nr = min(NW, n_my - base);
-    switch (kc / 32) {
-      case 1: mma_units<1>(a, sm, nr * nch, nch, kc, slot, S, base, ld); break;
-      case 2: mma_units<2>(a, sm, nr * nch, nch, kc, slot, S, base, ld); break;
-      case 4: mma_units<4>(a, sm, nr * nch, nch, kc, slot, S, base, ld); break;
-      default: mma_units<8>(a, sm, nr * nch, nch, kc, slot, S, base, ld); break;
-    }
+    mma_units(a, sm, nr * nch, nch, kc, slot, S, base, ld);
     __syncthreads();
     if (warp < nr) {
       const int tile = slot + (base + warp) * S;
@@ -274,7 +268,7 @@ __device__ __noinline__ void linear_phase(const LinArgs& a, int B, const Smem& s
 // y[n] = W[n, :] . x + bias[n]  for n < N; x given as bf16 hi/lo rows in smem (row 0 of the staging buffers).
 // Warp w handles 8-column tiles w, w+8, ...; only MMA row 0 carries data.  Result written to y (smem, fp32).
 // The weight rows of TWO tiles (up to 16 x 16 B per lane) are requested before the first MMA.
-__device__ __noinline__ void matvec_cta(const bf16* xhi, const bf16* xlo, int K, const bf16* W, const float* bias, int N, float* y) {
+__device__ __forceinline__ void matvec_cta(const bf16* xhi, const bf16* xlo, int K, const bf16* W, const float* bias, int N, float* y) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   const int ntiles = (N + 7) / 8;
   for (int tile0 = warp; tile0 < ntiles; tile0 += 2 * NW) {
@@ -283,32 +277,31 @@ __device__ __noinline__ void matvec_cta(const bf16* xhi, const bf16* xlo, int K,
     float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
     const bf16* w0 = W + size_t(tile0 * 8 + g) * K + c * 8;
     const bf16* w1 = W + size_t((has1 ? tile1 : tile0) * 8 + g) * K + c * 8;
-    for (int kb = 0; kb < K; kb += 256) {
-      uint4 wa[8], wb[8];
+#pragma unroll 1
+    for (int kb = 0; kb < K; kb += 128) {
+      uint4 wa[4], wb[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (kb + u * 32 < K) {
-          wa[u] = __ldg(reinterpret_cast<const uint4*>(w0 + kb + u * 32));
-          wb[u] = __ldg(reinterpret_cast<const uint4*>(w1 + kb + u * 32));
-        }
+      for (int u = 0; u < 4; ++u) {
+        wa[u] = __ldg(reinterpret_cast<const uint4*>(w0 + kb + u * 32));
+        wb[u] = __ldg(reinterpret_cast<const uint4*>(w1 + kb + u * 32));
+      }
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        if (kb + u * 32 < K) {
-          const int k = kb + u * 32 + c * 8;
-          uint4 h0 = make_uint4(0, 0, 0, 0), l0 = make_uint4(0, 0, 0, 0);
-          if (g == 0) {
-            h0 = *reinterpret_cast<const uint4*>(xhi + k);
-            l0 = *reinterpret_cast<const uint4*>(xlo + k);
-          }
-          mma16816(acc0, h0.x, 0u, h0.y, 0u, wa[u].x, wa[u].y);
-          mma16816(acc0, h0.z, 0u, h0.w, 0u, wa[u].z, wa[u].w);
-          mma16816(acc0, l0.x, 0u, l0.y, 0u, wa[u].x, wa[u].y);
-          mma16816(acc0, l0.z, 0u, l0.w, 0u, wa[u].z, wa[u].w);
-          mma16816(acc1, h0.x, 0u, h0.y, 0u, wb[u].x, wb[u].y);
-          mma16816(acc1, h0.z, 0u, h0.w, 0u, wb[u].z, wb[u].w);
-          mma16816(acc1, l0.x, 0u, l0.y, 0u, wb[u].x, wb[u].y);
-          mma16816(acc1, l0.z, 0u, l0.w, 0u, wb[u].z, wb[u].w);
+      for (int u = 0; u < 4; ++u) {
+        const int k = kb + u * 32 + c * 8;
+        uint4 h0 = make_uint4(0, 0, 0, 0), l0 = make_uint4(0, 0, 0, 0);
+        if (g == 0) {
+          h0 = *reinterpret_cast<const uint4*>(xhi + k);
+          l0 = *reinterpret_cast<const uint4*>(xlo + k);
         }
+        mma16816(acc0, h0.x, 0u, h0.y, 0u, wa[u].x, wa[u].y);
+        mma16816(acc0, h0.z, 0u, h0.w, 0u, wa[u].z, wa[u].w);
+        mma16816(acc0, l0.x, 0u, l0.y, 0u, wa[u].x, wa[u].y);
+        mma16816(acc0, l0.z, 0u, l0.w, 0u, wa[u].z, wa[u].w);
+        mma16816(acc1, h0.x, 0u, h0.y, 0u, wb[u].x, wb[u].y);
+        mma16816(acc1, h0.z, 0u, h0.w, 0u, wb[u].z, wb[u].w);
+        mma16816(acc1, l0.x, 0u, l0.y, 0u, wb[u].x, wb[u].y);
+        mma16816(acc1, l0.z, 0u, l0.w, 0u, wb[u].z, wb[u].w);
+      }
     }
     if (g == 0) {
       int col = tile0 * 8 + 2 * c;
@@ -324,7 +317,7 @@ __device__ __noinline__ void matvec_cta(const bf16* xhi, const bf16* xlo, int K,
 }
 
 // x (smem fp32 [D]) -> optional LayerNorm -> bf16 hi/lo row 0 of the staging buffers. Executed by warp 0.
-__device__ __noinline__ void stage_vec(const float* x, int D, const float* g, const float* b, bf16* hi, bf16* lo) {
+__device__ __forceinline__ void stage_vec(const float* x, int D, const float* g, const float* b, bf16* hi, bf16* lo) {
   const int lane = threadIdx.x & 31;
   if (threadIdx.x >= 32) return;
   float mean = 0.f, rstd = 1.f;
@@ -367,7 +360,7 @@ __device__ __forceinline__ uint4 ld_kv(const bf16* p) {
 }
 
 template <bool COHERENT>
-__device__ __noinline__ void attention_cta(const float* q, const bf16* kbase, const bf16* vbase, int ldkv, int n, int H, float scale,
+__device__ __forceinline__ void attention_cta(const float* q, const bf16* kbase, const bf16* vbase, int ldkv, int n, int H, float scale,
                               const Smem& sm, float* out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c8 = lane & 7, sub = lane >> 3;
@@ -527,67 +520,59 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
       const PersistentLayer& w = p.layer[l];
       bf16* cache = p.cache + size_t(l) * B * p.L * 2 * D;
       const bf16* ckv = p.ckv + size_t(l) * B * p.Tp * 2 * D;
-      {  // ---- A: LN1 + QKV, append K/V (model.py:67-68, layers.py:16-18)
-        LinArgs a;
-        a.x = p.h; a.ldx = D; a.K = D; a.ln_g = w.ln1_g; a.ln_b = w.ln1_b; a.w = w.w_qkv; a.bias = w.b_qkv;
-        a.N = 3 * D; a.relu = 0; a.epi = EPI_QKV; a.out = p.qkv; a.ldo = 3 * D;
-        a.cache = cache; a.cache_rows = p.L; a.cache_col0 = D; a.step = t;
-        linear_phase(a, B, sm);
-      }
-      PHASE_DONE(0)
-      grid_barrier(p.barrier, target);
-      PHASE_DONE(1)
-      // ---- B: utterance-local attention chain
-      for (int u = blockIdx.x; u < B; u += gridDim.x) {
-        for (int d = threadIdx.x * 4; d < D; d += NT * 4) {
-          *reinterpret_cast<float4*>(v_h + d) = ldcg4(p.h + size_t(u) * D + d);
-          *reinterpret_cast<float4*>(v_q + d) = ldcg4(p.qkv + size_t(u) * 3 * D + d);
+      for (int ph = 0; ph < 4; ++ph) {
+        if (ph != 1) {
+          // ---- A: LN1 + QKV, append K/V (model.py:67-68, layers.py:16-18)
+          // ---- C: LN3 + FFN squeeze + ReLU (model.py:73-74, layers.py:54-55)
+          // ---- D: FFN unsqueeze + residual
+          LinArgs a;
+          a.x = ph == 3 ? p.ff : p.h;
+          a.ldx = a.K = ph == 3 ? p.FF : D;
+          a.ln_g = ph == 0 ? w.ln1_g : (ph == 2 ? w.ln3_g : nullptr);
+          a.ln_b = ph == 0 ? w.ln1_b : (ph == 2 ? w.ln3_b : nullptr);
+          a.w = ph == 0 ? w.w_qkv : (ph == 2 ? w.w1 : w.w2);
+          a.bias = ph == 0 ? w.b_qkv : (ph == 2 ? w.b1 : w.b2);
+          a.N = ph == 0 ? 3 * D : (ph == 2 ? p.FF : D);
+          a.relu = ph == 2;
+          a.epi = ph == 0 ? EPI_QKV : (ph == 2 ? EPI_STORE : EPI_RESIDUAL);
+          a.out = ph == 0 ? p.qkv : (ph == 2 ? p.ff : p.h);
+          a.ldo = a.N;
+          a.cache = cache; a.cache_rows = p.L; a.cache_col0 = D; a.step = t;
+          linear_phase(a, B, sm);
+        } else {
+        // ---- B: utterance-local attention chain
+        for (int u = blockIdx.x; u < B; u += gridDim.x) {
+          for (int d = threadIdx.x * 4; d < D; d += NT * 4) {
+            *reinterpret_cast<float4*>(v_h + d) = ldcg4(p.h + size_t(u) * D + d);
+            *reinterpret_cast<float4*>(v_q + d) = ldcg4(p.qkv + size_t(u) * 3 * D + d);
+          }
+          __syncthreads();
+          const bf16* kc = cache + size_t(u) * p.L * 2 * D;
+          attention_cta<true>(v_q, kc, kc + D, 2 * D, t + 1, p.H, p.scale, sm, v_x);
+          stage_vec(v_x, D, nullptr, nullptr, sm.hi, sm.lo);
+          __syncthreads();
+          matvec_cta(sm.hi, sm.lo, D, w.w_o, w.b_o, D, v_x);             // out projection
+          __syncthreads();
+          for (int d = threadIdx.x; d < D; d += NT) v_h[d] += v_x[d];   // residual (model.py:68)
+          __syncthreads();
+          stage_vec(v_h, D, w.ln2_g, w.ln2_b, sm.hi, sm.lo);             // LN2 (model.py:70)
+          __syncthreads();
+          matvec_cta(sm.hi, sm.lo, D, w.w_qc, w.b_qc, D, v_q);           // cross-attention query
+          __syncthreads();
+          const bf16* ck = ckv + size_t(u) * p.Tp * 2 * D;
+          attention_cta<false>(v_q, ck, ck + D, 2 * D, p.Tp, p.H, p.scale, sm, v_x);
+          stage_vec(v_x, D, nullptr, nullptr, sm.hi, sm.lo);
+          __syncthreads();
+          matvec_cta(sm.hi, sm.lo, D, w.w_oc, w.b_oc, D, v_x);
+          __syncthreads();
+          for (int d = threadIdx.x; d < D; d += NT) p.h[size_t(u) * D + d] = v_h[d] + v_x[d];   // residual (model.py:71)
+          __syncthreads();
         }
-        __syncthreads();
-        const bf16* kc = cache + size_t(u) * p.L * 2 * D;
-        attention_cta<true>(v_q, kc, kc + D, 2 * D, t + 1, p.H, p.scale, sm, v_x);
-        stage_vec(v_x, D, nullptr, nullptr, sm.hi, sm.lo);
-        __syncthreads();
-        matvec_cta(sm.hi, sm.lo, D, w.w_o, w.b_o, D, v_x);             // out projection
-        __syncthreads();
-        for (int d = threadIdx.x; d < D; d += NT) v_h[d] += v_x[d];   // residual (model.py:68)
-        __syncthreads();
-        stage_vec(v_h, D, w.ln2_g, w.ln2_b, sm.hi, sm.lo);             // LN2 (model.py:70)
-        __syncthreads();
-        matvec_cta(sm.hi, sm.lo, D, w.w_qc, w.b_qc, D, v_q);           // cross-attention query
-        __syncthreads();
-        const bf16* ck = ckv + size_t(u) * p.Tp * 2 * D;
-        attention_cta<false>(v_q, ck, ck + D, 2 * D, p.Tp, p.H, p.scale, sm, v_x);
-        stage_vec(v_x, D, nullptr, nullptr, sm.hi, sm.lo);
-        __syncthreads();
-        matvec_cta(sm.hi, sm.lo, D, w.w_oc, w.b_oc, D, v_x);
-        __syncthreads();
-        for (int d = threadIdx.x; d < D; d += NT) p.h[size_t(u) * D + d] = v_h[d] + v_x[d];   // residual (model.py:71)
-        __syncthreads();
+        }
+        PHASE_DONE(2 * ph)
+        grid_barrier(p.barrier, target);
+        PHASE_DONE(2 * ph + 1)
       }
-      PHASE_DONE(2)
-      grid_barrier(p.barrier, target);
-      PHASE_DONE(3)
-      {  // ---- C: LN3 + FFN squeeze + ReLU (model.py:73-74, layers.py:54-55)
-        LinArgs a;
-        a.x = p.h; a.ldx = D; a.K = D; a.ln_g = w.ln3_g; a.ln_b = w.ln3_b; a.w = w.w1; a.bias = w.b1;
-        a.N = p.FF; a.relu = 1; a.epi = EPI_STORE; a.out = p.ff; a.ldo = p.FF;
-        a.cache = nullptr; a.cache_rows = 0; a.cache_col0 = 0; a.step = 0;
-        linear_phase(a, B, sm);
-      }
-      PHASE_DONE(4)
-      grid_barrier(p.barrier, target);
-      PHASE_DONE(5)
-      {  // ---- D: FFN unsqueeze + residual
-        LinArgs a;
-        a.x = p.ff; a.ldx = p.FF; a.K = p.FF; a.ln_g = nullptr; a.ln_b = nullptr; a.w = w.w2; a.bias = w.b2;
-        a.N = D; a.relu = 0; a.epi = EPI_RESIDUAL; a.out = p.h; a.ldo = D;
-        a.cache = nullptr; a.cache_rows = 0; a.cache_col0 = 0; a.step = 0;
-        linear_phase(a, B, sm);
-      }
-      PHASE_DONE(6)
-      grid_barrier(p.barrier, target);
-      PHASE_DONE(7)
     }
     // ---- E: classifier (no final LayerNorm, model.py:142) + argmax + EOS + next embedding
     for (int u = blockIdx.x; u < B; u += gridDim.x) {
