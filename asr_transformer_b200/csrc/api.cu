@@ -514,7 +514,9 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
   // Launch mode: "persistent" (default: one cooperative kernel for all L steps), "graph" (one CUDA-graph replay of
   // the 51-kernel step per token) or "eager" (same kernels, launched one by one; bring-up / profiling).
   const char* mode = std::getenv("ASR_B200_DECODE");
-  if (!mode || !mode[0] || mode[0] == 'p') {
+  // configurations whose staging buffers do not fit the persistent kernel's shared memory use the graph path
+  const bool can_persist = persistent_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers);
+  if ((!mode || !mode[0] || mode[0] == 'p') && can_persist) {
     PersistentParams pp;
     if (int rc = build_persistent(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, pp)) return rc;
     return launch_dec_persistent(pp, s);
@@ -600,7 +602,7 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
     launches_per_class[prof.cls[i]] += 1;
   }
   // slot DC_COUNT: the persistent cooperative kernel (all L steps in one launch), timed on its own
-  {
+  if (persistent_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers)) {
     dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, nullptr, w.finished, w.step, B, L, c.bos_token_id,
                                                  nullptr);
     ASR_CUDA_OK(cudaGetLastError());

@@ -12,11 +12,16 @@
 //   per step:   E  utterance-local: classifier (no final LayerNorm, model.py:142) -> argmax (lowest index wins)
 //                  -> EOS bookkeeping -> embedding + PE of the next token                                         | barrier
 //
+// Memory system design (this path is bound by HBM/L2 traffic and latency, not by math):
+//   * the encoder K/V of an (utterance, layer) - the dominant stream, 1.53 MB per utterance-step at the default
+//     model - is pulled by TMA bulk copies (cp.async.bulk, L2 evict-first) into a 3-stage shared-memory ring; the
+//     first stages of the NEXT layer are requested as soon as the current layer's cross attention is done, so they
+//     land while the grid-split FFN / QKV phases run;
+//   * weights are read with an L2 evict-last policy so the 11 MB weight set stays L2-resident under that stream;
+//   * every loop keeps >= 8 independent 16-byte loads in flight per lane before the first use.
 // Precision: Linear layers see fp32-accurate activations (bf16 hi + lo split, two tensor-core passes per weight
 // tile, fp32 accumulate); K/V caches bf16; attention scores / softmax / residual / LayerNorm fp32.
 // Data written by one CTA and read by another after a barrier is loaded with ld.global.cg (L2), never through L1.
-#include <cooperative_groups.h>
-
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -27,6 +32,8 @@ constexpr int NT = 256;              // threads per CTA
 constexpr int NW = NT / 32;
 constexpr int MROWS = 16;            // batch rows per grid-split work item (one m16 MMA tile)
 constexpr int PAD = 32;              // smem row padding (elements): row stride == 64 B mod 128 B -> conflict-free LDS.128
+constexpr int RING = 3;              // cross-K/V ring stages
+constexpr int CHUNK_BYTES = 32768;   // bytes per ring stage (= 128 / H keys of all heads, K and V)
 
 __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
@@ -41,6 +48,32 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   return v;
 }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// read-only 16-byte weight load that asks L2 to keep the line (weights are re-read every step by every CTA)
+__device__ __forceinline__ uint4 ldg_keep(const bf16* p, uint64_t pol) {
+  uint4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+}
+// TMA 1-D bulk copy global -> shared, completion on an mbarrier, L2 evict-first (streamed once per step)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
 
 // Grid-wide barrier on a monotonically increasing counter (zeroed by the launcher). Bounded spin: a protocol bug
 // becomes a launch failure, never a hung GPU.
@@ -75,10 +108,11 @@ struct Smem {
   bf16* hi;        // [MROWS][kmax + PAD]
   bf16* lo;
   float* red;      // [NW tiles][8 K chunks][32 lanes][4] partial sums
-  float* vec;      // utterance-local fp32 vectors: h[D], x[D] (attention out / LN out), q[D], logits / scores ...
-  float* sc;       // [H][max(L, Tp)] attention scores
-  float* part;     // [NW][D] partial attention outputs
-  float* stat;     // small scratch
+  float* vec;      // utterance-local fp32 vectors: h[D], x[D] (attention out / LN out), q[D], logits[V]
+  float* part;     // [NW][64] partial attention outputs
+  float* stat;     // [0,2NW) softmax stats, [32] token, [40,60) phase timers
+  uint8_t* ring;   // [RING][CHUNK_BYTES] cross-K/V stages
+  uint64_t* full;  // [RING] mbarriers
 };
 
 enum Epi { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_QKV = 2 };
@@ -96,7 +130,7 @@ struct LinArgs {
 // Tensor-core part of the grid-split linear.  lpu = 16-byte weight loads per (tile, K chunk) unit (1, 2, 4 or 8);
 // 8 / lpu units are kept in flight per warp so that 8 independent loads are outstanding before the first MMA.
 __device__ __forceinline__ void mma_units(const LinArgs& a, const Smem& sm, int nunits, int nch, int kc, int slot, int S,
-                                          int base, int ld) {
+                                          int base, int ld, uint64_t pol_w) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   const int lpu = kc >> 5;                       // power of two
   const int lsh = 31 - __clz(lpu);
@@ -111,7 +145,7 @@ __device__ __forceinline__ void mma_units(const LinArgs& a, const Smem& sm, int 
       if (q < nunits) {
         const int ti = q / nch, ch = q % nch;
         const int tile = slot + (base + ti) * S;
-        wv[j] = __ldg(reinterpret_cast<const uint4*>(a.w + size_t(tile * 8 + g) * a.K + ch * kc + c * 8 + u * 32));
+        wv[j] = ldg_keep(a.w + size_t(tile * 8 + g) * a.K + ch * kc + c * 8 + u * 32, pol_w);
       }
     }
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -140,7 +174,7 @@ __device__ __forceinline__ void mma_units(const LinArgs& a, const Smem& sm, int 
 
 // Grid-split linear: out[B, N] = epi( LN?(x)[B, K] * W^T + bias ).  CTA -> (16-row block, set of 8-column tiles);
 // the CTA's 8 warps are spread over (tile, K chunk) units; partial sums are reduced through smem in a fixed order.
-__device__ __forceinline__ void linear_phase(const LinArgs& a, int B, const Smem& sm) {
+__device__ __forceinline__ void linear_phase(const LinArgs& a, int B, const Smem& sm, uint64_t pol_w) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   const int MB = (B + MROWS - 1) / MROWS;
   const int S = gridDim.x / MB;             // CTAs ("slots") per row block
@@ -219,7 +253,7 @@ __device__ __forceinline__ void linear_phase(const LinArgs& a, int B, const Smem
   float4* red = reinterpret_cast<float4*>(sm.red);           // [NW tiles][8 chunks][32 lanes]
   for (int base = 0; base < n_my; base += NW) {
     const int nr = min(NW, n_my - base);
-    mma_units(a, sm, nr * nch, nch, kc, slot, S, base, ld);
+    mma_units(a, sm, nr * nch, nch, kc, slot, S, base, ld, pol_w);
     __syncthreads();
     if (warp < nr) {
       const int tile = slot + (base + warp) * S;
@@ -267,8 +301,9 @@ __device__ __forceinline__ void linear_phase(const LinArgs& a, int B, const Smem
 
 // y[n] = W[n, :] . x + bias[n]  for n < N; x given as bf16 hi/lo rows in smem (row 0 of the staging buffers).
 // Warp w handles 8-column tiles w, w+8, ...; only MMA row 0 carries data.  Result written to y (smem, fp32).
-// The weight rows of TWO tiles (up to 16 x 16 B per lane) are requested before the first MMA.
-__device__ __forceinline__ void matvec_cta(const bf16* xhi, const bf16* xlo, int K, const bf16* W, const float* bias, int N, float* y) {
+// Two tiles x 128 K elements (8 x 16 B weight loads per lane) are requested before the first MMA.  K % 128 == 0.
+__device__ __forceinline__ void matvec_cta(const bf16* xhi, const bf16* xlo, int K, const bf16* W, const float* bias,
+                                           int N, float* y, uint64_t pol_w) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   const int ntiles = (N + 7) / 8;
   for (int tile0 = warp; tile0 < ntiles; tile0 += 2 * NW) {
@@ -282,8 +317,8 @@ __device__ __forceinline__ void matvec_cta(const bf16* xhi, const bf16* xlo, int
       uint4 wa[4], wb[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        wa[u] = __ldg(reinterpret_cast<const uint4*>(w0 + kb + u * 32));
-        wb[u] = __ldg(reinterpret_cast<const uint4*>(w1 + kb + u * 32));
+        wa[u] = ldg_keep(w0 + kb + u * 32, pol_w);
+        wb[u] = ldg_keep(w1 + kb + u * 32, pol_w);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -346,122 +381,152 @@ __device__ __forceinline__ void stage_vec(const float* x, int D, const float* g,
   }
 }
 
-// Single-query attention for all H heads of one utterance. q: smem fp32 [H*64] (unscaled); K/V rows of 2 x H*64 bf16
-// (k at kbase, v at vbase, row stride ldkv elements); out: smem fp32 [H*64].
-// Warp w serves head w % H with key subset (w / H) of NW / H; 8 lanes per 128-byte key row, 4 key groups per warp.
-// Flash-style single pass: every group keeps a running (max, sum, 8-dim accumulator); 8 keys (K and V rows, 16 x 16 B
-// per lane) are requested before any of them is consumed, so the loop is bandwidth- not latency-bound.
-constexpr int AU = 8;   // keys in flight per group
+// ---- single-query attention for all H heads of one utterance, flash style.
+// Warp w serves head w % H with key subset (w / H) of NW / H; 8 lanes per 128-byte head row, 4 key groups per warp.
+// Every group keeps a running (max, sum, 8-dim accumulator) in log2 units; groups and warps are merged at the end.
+struct AttnState {
+  float qv[8];
+  float m, l;
+  float o[8];
+};
 
-template <bool COHERENT>
-__device__ __forceinline__ uint4 ld_kv(const bf16* p) {
-  const uint4* ptr = reinterpret_cast<const uint4*>(p);
-  return COHERENT ? __ldcg(ptr) : __ldg(ptr);
+__device__ __forceinline__ void attn_begin(AttnState& st, const float* q, int H, float scale) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c8 = lane & 7;
+  const int h = warp % H;
+  const float4 a = *reinterpret_cast<const float4*>(q + h * 64 + c8 * 8);
+  const float4 b = *reinterpret_cast<const float4*>(q + h * 64 + c8 * 8 + 4);
+  const float sc = scale * 1.4426950408889634f;    // p = exp2(s - m)
+  st.qv[0] = a.x * sc; st.qv[1] = a.y * sc; st.qv[2] = a.z * sc; st.qv[3] = a.w * sc;
+  st.qv[4] = b.x * sc; st.qv[5] = b.y * sc; st.qv[6] = b.z * sc; st.qv[7] = b.w * sc;
+  st.m = -INFINITY;
+  st.l = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) st.o[i] = 0.f;
 }
 
-template <bool COHERENT>
-__device__ __forceinline__ void attention_cta(const float* q, const bf16* kbase, const bf16* vbase, int ldkv, int n, int H, float scale,
-                              const Smem& sm, float* out) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c8 = lane & 7, sub = lane >> 3;
-  const int wph = NW / H;                           // warps per head (launcher guarantees NW % H == 0)
-  const int h = warp % H, part = warp / H;
-  const unsigned gmask = 0xFFu << (lane & 24);
-  const float kLog2e = 1.4426950408889634f;
-  float qv[8];
-  {
-    const float4 a = *reinterpret_cast<const float4*>(q + h * 64 + c8 * 8);
-    const float4 b = *reinterpret_cast<const float4*>(q + h * 64 + c8 * 8 + 4);
-    const float sc = scale * kLog2e;                // scores kept in log2 units: p = exp2(s - m)
-    qv[0] = a.x * sc; qv[1] = a.y * sc; qv[2] = a.z * sc; qv[3] = a.w * sc;
-    qv[4] = b.x * sc; qv[5] = b.y * sc; qv[6] = b.z * sc; qv[7] = b.w * sc;
+// fold NB keys (rows already in registers) into the running state; valid[u] masks the tail
+template <int NB>
+__device__ __forceinline__ void attn_fold(AttnState& st, const uint4 (&kr)[NB], const uint4 (&vr)[NB],
+                                          const bool (&valid)[NB], unsigned gmask) {
+  float sc[NB];
+  float bm = -INFINITY;
+#pragma unroll
+  for (int u = 0; u < NB; ++u) {
+    float sv = 0.f;
+    if (valid[u]) {
+      const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr[u]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(k2[i]);
+        sv = fmaf(st.qv[2 * i], f.x, sv);
+        sv = fmaf(st.qv[2 * i + 1], f.y, sv);
+      }
+    }
+    sv += __shfl_xor_sync(gmask, sv, 1);
+    sv += __shfl_xor_sync(gmask, sv, 2);
+    sv += __shfl_xor_sync(gmask, sv, 4);
+    sc[u] = valid[u] ? sv : -INFINITY;
+    bm = fmaxf(bm, sc[u]);
   }
+  if (bm == -INFINITY) return;                    // no valid key in this batch (uniform inside the 8-lane group)
+  const float m_new = fmaxf(st.m, bm);
+  const float alpha = exp2f(st.m - m_new);        // st.m == -inf -> 0
+  st.l *= alpha;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) st.o[i] *= alpha;
+#pragma unroll
+  for (int u = 0; u < NB; ++u) {
+    if (valid[u]) {
+      const float pw = exp2f(sc[u] - m_new);
+      st.l += pw;
+      const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vr[u]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(v2[i]);
+        st.o[2 * i] = fmaf(pw, f.x, st.o[2 * i]);
+        st.o[2 * i + 1] = fmaf(pw, f.y, st.o[2 * i + 1]);
+      }
+    }
+  }
+  st.m = m_new;
+}
+
+// keys straight from global memory (self-attention cache, written by other CTAs before the barrier -> ld.global.cg)
+__device__ __forceinline__ void attn_global(AttnState& st, const bf16* kbase, const bf16* vbase, int ldkv, int n, int H) {
+  constexpr int AU = 8;                              // keys in flight per group: 16 x 16 B per lane
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c8 = lane & 7, sub = lane >> 3;
+  const int wph = NW / H, h = warp % H, part = warp / H;
+  const unsigned gmask = 0xFFu << (lane & 24);
   const int stride = wph * 4;
   const bf16* kp = kbase + h * 64 + c8 * 8;
   const bf16* vp = vbase + h * 64 + c8 * 8;
-  float m = -INFINITY, l = 0.f;
-  float o[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = 0.f;
-
   for (int k0 = part * 4 + sub; k0 < n; k0 += stride * AU) {   // trip count is uniform inside an 8-lane group
     uint4 kr[AU], vr[AU];
+    bool valid[AU];
 #pragma unroll
     for (int u = 0; u < AU; ++u) {
       const int kj = k0 + u * stride;
-      if (kj < n) {
-        kr[u] = ld_kv<COHERENT>(kp + size_t(kj) * ldkv);
-        vr[u] = ld_kv<COHERENT>(vp + size_t(kj) * ldkv);
+      valid[u] = kj < n;
+      if (valid[u]) {
+        kr[u] = __ldcg(reinterpret_cast<const uint4*>(kp + size_t(kj) * ldkv));
+        vr[u] = __ldcg(reinterpret_cast<const uint4*>(vp + size_t(kj) * ldkv));
       }
     }
-    float sc[AU];
-    float bm = -INFINITY;
-#pragma unroll
-    for (int u = 0; u < AU; ++u) {
-      const int kj = k0 + u * stride;
-      float sv = 0.f;
-      if (kj < n) {
-        const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr[u]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(k2[i]);
-          sv = fmaf(qv[2 * i], f.x, sv);
-          sv = fmaf(qv[2 * i + 1], f.y, sv);
-        }
-      }
-      sv += __shfl_xor_sync(gmask, sv, 1);
-      sv += __shfl_xor_sync(gmask, sv, 2);
-      sv += __shfl_xor_sync(gmask, sv, 4);
-      sc[u] = kj < n ? sv : -INFINITY;
-      bm = fmaxf(bm, sc[u]);
-    }
-    const float m_new = fmaxf(m, bm);               // finite: the batch holds at least one valid key
-    const float alpha = exp2f(m - m_new);           // m == -inf -> 0
-    l *= alpha;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] *= alpha;
-#pragma unroll
-    for (int u = 0; u < AU; ++u) {
-      const float pw = exp2f(sc[u] - m_new);        // masked tail: exp2(-inf) = 0
-      if (k0 + u * stride < n) {
-        l += pw;
-        const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vr[u]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __bfloat1622float2(v2[i]);
-          o[2 * i] = fmaf(pw, f.x, o[2 * i]);
-          o[2 * i + 1] = fmaf(pw, f.y, o[2 * i + 1]);
-        }
-      }
-    }
-    m = m_new;
+    attn_fold<AU>(st, kr, vr, valid, gmask);
   }
-  // merge the 4 key groups of the warp (lanes with equal c8), rescaling to the common maximum
+}
+
+// one ring stage: nk key rows of [K(H*64) | V(H*64)] bf16 in shared memory; each group owns 4 key slots per chunk
+__device__ __forceinline__ void attn_chunk(AttnState& st, const uint8_t* stage, int nk, int H) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c8 = lane & 7, sub = lane >> 3;
+  const int wph = NW / H, h = warp % H, part = warp / H;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  const int stride = wph * 4;
+  const int row_bytes = H * 256;                     // K and V of all heads
+  const uint8_t* base = stage + h * 128 + c8 * 16;
+  uint4 kr[4], vr[4];
+  bool valid[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int kl = part * 4 + sub + u * stride;
+    valid[u] = kl < nk;
+    if (valid[u]) {
+      kr[u] = *reinterpret_cast<const uint4*>(base + size_t(kl) * row_bytes);
+      vr[u] = *reinterpret_cast<const uint4*>(base + size_t(kl) * row_bytes + H * 128);
+    }
+  }
+  attn_fold<4>(st, kr, vr, valid, gmask);
+}
+
+// merge the key groups of each warp and the warps of each head; out: smem fp32 [H*64]
+__device__ __forceinline__ void attn_finish(AttnState& st, int H, const Smem& sm, float* out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c8 = lane & 7, sub = lane >> 3;
+  const int wph = NW / H;
 #pragma unroll
   for (int off = 8; off <= 16; off <<= 1) {
-    const float mo = __shfl_xor_sync(0xffffffffu, m, off);
-    const float lo = __shfl_xor_sync(0xffffffffu, l, off);
-    const float mn = fmaxf(m, mo);
-    const float fa = (m == -INFINITY) ? 0.f : exp2f(m - mn);
+    const float mo = __shfl_xor_sync(0xffffffffu, st.m, off);
+    const float lo = __shfl_xor_sync(0xffffffffu, st.l, off);
+    const float mn = fmaxf(st.m, mo);
+    const float fa = (st.m == -INFINITY) ? 0.f : exp2f(st.m - mn);
     const float fb = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
-    l = l * fa + lo * fb;
+    st.l = st.l * fa + lo * fb;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float oo = __shfl_xor_sync(0xffffffffu, o[i], off);
-      o[i] = o[i] * fa + oo * fb;
+      const float oo = __shfl_xor_sync(0xffffffffu, st.o[i], off);
+      st.o[i] = st.o[i] * fa + oo * fb;
     }
-    m = mn;
+    st.m = mn;
   }
   if (sub == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sm.part[warp * 64 + c8 * 8 + i] = o[i];
+    for (int i = 0; i < 8; ++i) sm.part[warp * 64 + c8 * 8 + i] = st.o[i];
     if (c8 == 0) {
-      sm.stat[warp] = m;
-      sm.stat[NW + warp] = l;
+      sm.stat[warp] = st.m;
+      sm.stat[NW + warp] = st.l;
     }
   }
   __syncthreads();
-  for (int d = threadIdx.x; d < H * 64; d += NT) {   // merge the warps of each head
+  for (int d = threadIdx.x; d < H * 64; d += NT) {
     const int hh = d >> 6, dd = d & 63;
     float mm = -INFINITY;
     for (int pI = 0; pI < wph; ++pI) mm = fmaxf(mm, sm.stat[pI * H + hh]);
@@ -472,33 +537,55 @@ __device__ __forceinline__ void attention_cta(const float* q, const bf16* kbase,
       t += sm.part[(pI * H + hh) * 64 + dd] * f;
       ls += sm.stat[NW + pI * H + hh] * f;
     }
-    out[d] = ls > 0.f ? t / ls : 0.f;
+    out[d] = ls > 0.f ? t / ls : 0.f;                // fully masked -> zeros (layers.py:25)
   }
   __syncthreads();
 }
 
-}  // namespace
-
-namespace {
+// request ring stages [c0, c1) of one (utterance, layer) encoder K/V block; thread 0 only
+__device__ __forceinline__ void ring_issue(const Smem& sm, const bf16* ck, int Tp, int H, int ck_keys, int c0, int c1,
+                                           uint64_t pol) {
+  const int row_bytes = H * 256;
+  for (int c = c0; c < c1; ++c) {
+    const int s = c % RING;
+    const int nk = min(ck_keys, Tp - c * ck_keys);
+    const uint32_t bytes = uint32_t(nk) * row_bytes;
+    mbar_expect_tx(&sm.full[s], bytes);
+    bulk_g2s(sm.ring + size_t(s) * CHUNK_BYTES, reinterpret_cast<const uint8_t*>(ck) + size_t(c) * ck_keys * row_bytes,
+             bytes, &sm.full[s], pol);
+  }
+}
 
 __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_constant__ PersistentParams p) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   Smem sm;
   {
-    uint8_t* ptr = smem_raw;
+    uint8_t* ptr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
     const int ld = p.kmax + PAD;
+    sm.ring = ptr; ptr += size_t(RING) * CHUNK_BYTES;
     sm.hi = reinterpret_cast<bf16*>(ptr); ptr += size_t(MROWS) * ld * 2;
     sm.lo = reinterpret_cast<bf16*>(ptr); ptr += size_t(MROWS) * ld * 2;
     sm.red = reinterpret_cast<float*>(ptr); ptr += NW * 8 * 32 * 16;
     sm.vec = reinterpret_cast<float*>(ptr); ptr += size_t(4) * p.kmax * 4;
     sm.part = reinterpret_cast<float*>(ptr); ptr += NW * 64 * 4;
-    sm.stat = reinterpret_cast<float*>(ptr); ptr += 64 * 4;   // [0,2NW) softmax stats, [32] token, [40,60) phase timers
-    sm.sc = reinterpret_cast<float*>(ptr);
+    sm.stat = reinterpret_cast<float*>(ptr); ptr += 64 * 4;
+    sm.full = reinterpret_cast<uint64_t*>(ptr);
   }
-  const int D = p.D, B = p.B;
+  const int D = p.D, B = p.B, H = p.H;
+  const uint64_t pol_w = l2_policy_evict_last();
+  const uint64_t pol_kv = l2_policy_evict_first();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RING; ++s) mbar_init(&sm.full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
   unsigned target = 0;
+  unsigned ring_parity = 0;            // bit s = parity of the next completion to wait for on stage s
+  int pre_u = -1, pre_l = -1;          // (utterance, layer) whose first ring stages have already been requested
+  const int ck_keys = CHUNK_BYTES / (H * 256);                 // keys per ring stage
+  const int nchunks = (p.Tp + ck_keys - 1) / ck_keys;
   // optional per-phase cycle accounting (asr_decode_profile): thread 0 of every CTA accumulates clock64 deltas
-  long long* tacc = reinterpret_cast<long long*>(sm.stat + 40);   // 10 counters in smem (8-byte aligned)
+  long long* tacc = reinterpret_cast<long long*>(sm.stat + 40);
   long long t_prev = 0;
   if (p.timing && threadIdx.x == 0) {
     for (int i = 0; i < 10; ++i) tacc[i] = 0;
@@ -514,6 +601,14 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
   float* v_x = sm.vec + p.kmax;        // [D] attention output / scratch
   float* v_q = sm.vec + 2 * p.kmax;    // [D] query
   float* v_l = sm.vec + 3 * p.kmax;    // logits (V <= kmax)
+
+  // the encoder K/V of this CTA's first utterance, layer 0, can be requested before anything else runs
+  if ((int)blockIdx.x < B) {
+    if (threadIdx.x == 0)
+      ring_issue(sm, p.ckv + size_t(blockIdx.x) * p.Tp * 2 * D, p.Tp, H, ck_keys, 0, min(RING, nchunks), pol_kv);
+    pre_u = blockIdx.x;
+    pre_l = 0;
+  }
 
   for (int t = 0; t < p.L; ++t) {
     for (int l = 0; l < p.nd; ++l) {
@@ -538,36 +633,71 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
           a.out = ph == 0 ? p.qkv : (ph == 2 ? p.ff : p.h);
           a.ldo = a.N;
           a.cache = cache; a.cache_rows = p.L; a.cache_col0 = D; a.step = t;
-          linear_phase(a, B, sm);
+          linear_phase(a, B, sm, pol_w);
         } else {
-        // ---- B: utterance-local attention chain
-        for (int u = blockIdx.x; u < B; u += gridDim.x) {
-          for (int d = threadIdx.x * 4; d < D; d += NT * 4) {
-            *reinterpret_cast<float4*>(v_h + d) = ldcg4(p.h + size_t(u) * D + d);
-            *reinterpret_cast<float4*>(v_q + d) = ldcg4(p.qkv + size_t(u) * 3 * D + d);
+          // ---- B: utterance-local attention chain
+          for (int u = blockIdx.x; u < B; u += gridDim.x) {
+            for (int d = threadIdx.x * 4; d < D; d += NT * 4) {
+              *reinterpret_cast<float4*>(v_h + d) = ldcg4(p.h + size_t(u) * D + d);
+              *reinterpret_cast<float4*>(v_q + d) = ldcg4(p.qkv + size_t(u) * 3 * D + d);
+            }
+            __syncthreads();
+            AttnState st;
+            const bf16* kc = cache + size_t(u) * p.L * 2 * D;
+            attn_begin(st, v_q, H, p.scale);
+            attn_global(st, kc, kc + D, 2 * D, t + 1, H);                  // causal self attention: keys 0..t
+            attn_finish(st, H, sm, v_x);
+            stage_vec(v_x, D, nullptr, nullptr, sm.hi, sm.lo);
+            __syncthreads();
+            matvec_cta(sm.hi, sm.lo, D, w.w_o, w.b_o, D, v_x, pol_w);     // out projection
+            __syncthreads();
+            for (int d = threadIdx.x; d < D; d += NT) v_h[d] += v_x[d];   // residual (model.py:68)
+            __syncthreads();
+            stage_vec(v_h, D, w.ln2_g, w.ln2_b, sm.hi, sm.lo);             // LN2 (model.py:70)
+            __syncthreads();
+            matvec_cta(sm.hi, sm.lo, D, w.w_qc, w.b_qc, D, v_q, pol_w);   // cross-attention query
+            __syncthreads();
+            // cross attention over the encoder K/V, streamed through the shared-memory ring (never masked)
+            const bf16* ck = ckv + size_t(u) * p.Tp * 2 * D;
+            if (!(pre_u == u && pre_l == l) && threadIdx.x == 0)
+              ring_issue(sm, ck, p.Tp, H, ck_keys, 0, min(RING, nchunks), pol_kv);
+            attn_begin(st, v_q, H, p.scale);
+            for (int c = 0; c < nchunks; ++c) {
+              const int s = c % RING;
+              mbar_wait(&sm.full[s], (ring_parity >> s) & 1u);
+              ring_parity ^= 1u << s;
+              attn_chunk(st, sm.ring + size_t(s) * CHUNK_BYTES, min(ck_keys, p.Tp - c * ck_keys), H);
+              __syncthreads();                                              // stage s drained by every warp
+              if (c + RING < nchunks && threadIdx.x == 0)
+                ring_issue(sm, ck, p.Tp, H, ck_keys, c + RING, c + RING + 1, pol_kv);
+            }
+            // request the first stages of the next (utterance, layer) this CTA will serve: they land while the
+            // grid-split phases run.  Static data (computed once per utterance), so no ordering hazard.
+            {
+              int nu = u + gridDim.x, nl = l;
+              if (nu >= B) {
+                nu = blockIdx.x;
+                nl = l + 1;
+                if (nl >= p.nd) nl = (t + 1 < p.L) ? 0 : -1;
+              }
+              if (nl >= 0) {
+                if (threadIdx.x == 0)
+                  ring_issue(sm, p.ckv + (size_t(nl) * B + nu) * p.Tp * 2 * D, p.Tp, H, ck_keys, 0, min(RING, nchunks),
+                             pol_kv);
+                pre_u = nu;
+                pre_l = nl;
+              } else {
+                pre_u = pre_l = -1;
+              }
+            }
+            attn_finish(st, H, sm, v_x);
+            stage_vec(v_x, D, nullptr, nullptr, sm.hi, sm.lo);
+            __syncthreads();
+            matvec_cta(sm.hi, sm.lo, D, w.w_oc, w.b_oc, D, v_x, pol_w);
+            __syncthreads();
+            for (int d = threadIdx.x; d < D; d += NT) p.h[size_t(u) * D + d] = v_h[d] + v_x[d];   // residual (model.py:71)
+            __syncthreads();
           }
-          __syncthreads();
-          const bf16* kc = cache + size_t(u) * p.L * 2 * D;
-          attention_cta<true>(v_q, kc, kc + D, 2 * D, t + 1, p.H, p.scale, sm, v_x);
-          stage_vec(v_x, D, nullptr, nullptr, sm.hi, sm.lo);
-          __syncthreads();
-          matvec_cta(sm.hi, sm.lo, D, w.w_o, w.b_o, D, v_x);             // out projection
-          __syncthreads();
-          for (int d = threadIdx.x; d < D; d += NT) v_h[d] += v_x[d];   // residual (model.py:68)
-          __syncthreads();
-          stage_vec(v_h, D, w.ln2_g, w.ln2_b, sm.hi, sm.lo);             // LN2 (model.py:70)
-          __syncthreads();
-          matvec_cta(sm.hi, sm.lo, D, w.w_qc, w.b_qc, D, v_q);           // cross-attention query
-          __syncthreads();
-          const bf16* ck = ckv + size_t(u) * p.Tp * 2 * D;
-          attention_cta<false>(v_q, ck, ck + D, 2 * D, p.Tp, p.H, p.scale, sm, v_x);
-          stage_vec(v_x, D, nullptr, nullptr, sm.hi, sm.lo);
-          __syncthreads();
-          matvec_cta(sm.hi, sm.lo, D, w.w_oc, w.b_oc, D, v_x);
-          __syncthreads();
-          for (int d = threadIdx.x; d < D; d += NT) p.h[size_t(u) * D + d] = v_h[d] + v_x[d];   // residual (model.py:71)
-          __syncthreads();
-        }
         }
         PHASE_DONE(2 * ph)
         grid_barrier(p.barrier, target);
@@ -581,7 +711,7 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
       __syncthreads();
       stage_vec(v_h, D, nullptr, nullptr, sm.hi, sm.lo);
       __syncthreads();
-      matvec_cta(sm.hi, sm.lo, D, p.classifier, nullptr, p.V, v_l);
+      matvec_cta(sm.hi, sm.lo, D, p.classifier, nullptr, p.V, v_l, pol_w);
       __syncthreads();
       if (p.step_logits)
         for (int v = threadIdx.x; v < p.V; v += NT) p.step_logits[(size_t(u) * p.L + t) * p.V + v] = v_l[v];
@@ -635,6 +765,10 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
     PHASE_DONE(9)
     if (p.stop_at_eos && ld_acquire_u32(p.done_count) >= (unsigned)B) break;   // uniform: read after the barrier
   }
+  // drain: a requested-but-unconsumed prefetch must land before the CTA (and its shared memory) goes away
+  if (pre_u >= 0) {
+    for (int c = 0; c < min(RING, nchunks); ++c) mbar_wait(&sm.full[c % RING], (ring_parity >> (c % RING)) & 1u);
+  }
   if (p.timing && threadIdx.x == 0)
     for (int i = 0; i < 10; ++i) p.timing[size_t(blockIdx.x) * 10 + i] = tacc[i];
 #undef PHASE_DONE
@@ -642,23 +776,26 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
 
 }  // namespace
 
-size_t persistent_smem_bytes(int D, int FF, int V, int L, int Tp, int H) {
+size_t persistent_smem_bytes(int D, int FF, int V) {
   int kmax = D > FF ? D : FF;
   if (V > kmax) kmax = (V + 127) / 128 * 128;
-  const int sc_ld = ((L > Tp ? L : Tp) + 3) & ~3;
-  return size_t(2) * MROWS * (kmax + PAD) * 2 + NW * 8 * 32 * 16 + size_t(4) * kmax * 4 + NW * 64 * 4 + 64 * 4 +
-         size_t(H) * sc_ld * 4 + 16;
+  return 128 + size_t(RING) * CHUNK_BYTES + size_t(2) * MROWS * (kmax + PAD) * 2 + NW * 8 * 32 * 16 +
+         size_t(4) * kmax * 4 + NW * 64 * 4 + 64 * 4 + RING * 8 + 16;
+}
+
+bool persistent_supported(int D, int FF, int V, int H, int nd) {
+  return nd <= PERSIST_MAX_LAYERS && (H == 2 || H == 4 || H == 8) && D == 64 * H && D % 128 == 0 && D <= 512 &&
+         FF % 64 == 0 && FF <= 2048 && persistent_smem_bytes(D, FF, V) <= 227 * 1024;
 }
 
 int launch_dec_persistent(PersistentParams& p, cudaStream_t s) {
   if (p.nd > PERSIST_MAX_LAYERS) return set_error(-2, "persistent decoder: more than %d layers", PERSIST_MAX_LAYERS);
-  if (p.H > NW || NW % p.H != 0) return set_error(-2, "persistent decoder: num_heads %d must divide %d", p.H, NW);
-  if (p.D % 128 != 0 || p.D > 512 || p.FF % 64 != 0 || p.FF > 2048)
+  if (p.H > NW || NW % p.H != 0 || p.H < 2) return set_error(-2, "persistent decoder: num_heads %d must be 2, 4 or 8", p.H);
+  if (p.D != 64 * p.H || p.D % 128 != 0 || p.D > 512 || p.FF % 64 != 0 || p.FF > 2048)
     return set_error(-2, "persistent decoder: unsupported D=%d / FF=%d", p.D, p.FF);
   p.kmax = p.D > p.FF ? p.D : p.FF;
   if (p.V > p.kmax) p.kmax = (p.V + 127) / 128 * 128;
-  p.sc_ld = ((p.L > p.Tp ? p.L : p.Tp) + 3) & ~3;
-  const size_t smem = persistent_smem_bytes(p.D, p.FF, p.V, p.L, p.Tp, p.H);
+  const size_t smem = persistent_smem_bytes(p.D, p.FF, p.V);
   if (smem > 227 * 1024) return set_error(-2, "persistent decoder: needs %zu B of shared memory", smem);
   static size_t configured = 0;
   if (smem > configured) {

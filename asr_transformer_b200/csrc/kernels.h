@@ -164,7 +164,8 @@ struct PersistentParams {
   float scale;
 };
 
-size_t persistent_smem_bytes(int D, int FF, int V, int L, int Tp, int H);
+size_t persistent_smem_bytes(int D, int FF, int V);
+bool persistent_supported(int D, int FF, int V, int H, int nd);
 int launch_dec_persistent(PersistentParams& p, cudaStream_t s);
 
 }  // namespace asr
