@@ -65,7 +65,7 @@ struct GreedyWs {
   bf16 *enc_bf16, *ckv, *cache;
   float *h, *qkv, *att, *qc, *ff, *logits;
   int32_t *step, *finished;
-  unsigned* barrier;   // [2]: grid barrier counter, finished-utterance counter
+  unsigned* barrier;   // [2][PERSIST_MAX_TEAMS][32]: per-team barrier counters, finished-utterance counters
   void carve(Bump& b, const AsrConfig& c, int B, int Tp, int L) {
     const size_t M = size_t(B) * Tp, D = c.embedding_dim;
     const size_t vpad = (size_t(c.vocab_size) + 63) / 64 * 64;
@@ -80,7 +80,7 @@ struct GreedyWs {
     logits = b.take<float>(size_t(B) * vpad);
     step = b.take<int32_t>(1);
     finished = b.take<int32_t>(B);
-    barrier = b.take<unsigned>(2);
+    barrier = b.take<unsigned>(2 * PERSIST_MAX_TEAMS * 32);
   }
 };
 
@@ -318,7 +318,15 @@ static int build_persistent(const AsrHandle* h, const GreedyWs& w, int B, int Tp
   pp.classifier = static_cast<const bf16*>(h->w.classifier_w); pp.emb = h->w.embedding; pp.pe = h->w.dec_pe;
   pp.cache = w.cache; pp.ckv = w.ckv; pp.h = w.h; pp.qkv = w.qkv; pp.ff = w.ff;
   pp.tokens = tokens; pp.n_tokens = n_tokens; pp.finished = w.finished; pp.step_logits = step_logits;
-  pp.barrier = w.barrier; pp.done_count = w.barrier + 1;
+  pp.barrier = w.barrier; pp.done_count = w.barrier + PERSIST_MAX_TEAMS * 32;
+  {  // teams: one m16 row block (16 utterances) per team unless overridden (ASR_B200_TEAMS)
+    const char* te = std::getenv("ASR_B200_TEAMS");
+    int teams = te && te[0] ? std::atoi(te) : (B + 15) / 16;
+    if (teams < 1) teams = 1;
+    if (teams > PERSIST_MAX_TEAMS) teams = PERSIST_MAX_TEAMS;
+    if (teams > B) teams = B;
+    pp.teams = teams;
+  }
   pp.eos = c.eos_token_id; pp.pad = c.pad_token_id; pp.stop_at_eos = stop_at_eos;
   pp.scale = 1.0f / sqrtf((float)D);
   return 0;
@@ -521,7 +529,7 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
     if (int rc = build_persistent(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, pp)) return rc;
     return launch_dec_persistent(pp, s);
   }
-  if (mode[0] == 'e') {
+  if (mode && mode[0] == 'e') {
     for (int t = 0; t < L; ++t)
       if (int rc = greedy_step(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, s)) return rc;
     return 0;
@@ -610,11 +618,10 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
       return rc;
     PersistentParams pp;
     if (int rc = build_persistent(h, w, B, Tp, L, 0, tokens, nullptr, nullptr, pp)) return rc;
-    pp.timing = phase_cycles;   // device buffer [#SMs][10], nullable
+    pp.timing = phase_cycles;   // device buffer [#SMs][16], nullable
     cudaEvent_t e0, e1;
     ASR_CUDA_OK(cudaEventCreate(&e0));
     ASR_CUDA_OK(cudaEventCreate(&e1));
-    ASR_CUDA_OK(cudaMemsetAsync(pp.barrier, 0, 2 * sizeof(unsigned), s));
     ASR_CUDA_OK(cudaEventRecord(e0, s));
     int rc = launch_dec_persistent(pp, s);
     ASR_CUDA_OK(cudaEventRecord(e1, s));

@@ -75,16 +75,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       : "memory");
 }
 
-// Grid-wide barrier on a monotonically increasing counter (zeroed by the launcher). Bounded spin: a protocol bug
-// becomes a launch failure, never a hung GPU.
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
-  target += gridDim.x;
+// Team-wide barrier on a monotonically increasing counter (zeroed by the launcher).  Polling uses relaxed gpu-scope
+// loads (served by L2, no L1 invalidation per poll); one fence on each side orders the data.  Bounded spin: a
+// protocol bug becomes a launch failure, never a hung GPU.
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target, int ncta) {
+  target += ncta;
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
     atomicAdd(counter, 1u);
     const long long t0 = clock64();
-    while (ld_acquire_u32(counter) < target) {
+    while (ld_relaxed_u32(counter) < target) {
       if (clock64() - t0 > 4000000000LL) __trap();
     }
     __threadfence();
@@ -110,7 +116,7 @@ struct Smem {
   float* red;      // [NW tiles][8 K chunks][32 lanes][4] partial sums
   float* vec;      // utterance-local fp32 vectors: h[D], x[D] (attention out / LN out), q[D], logits[V]
   float* part;     // [NW][64] partial attention outputs
-  float* stat;     // [0,2NW) softmax stats, [32] token, [40,60) phase timers
+  float* stat;     // [0,2NW) softmax stats, [32] token, [40,72) phase timers
   uint8_t* ring;   // [RING][CHUNK_BYTES] cross-K/V stages
   uint64_t* full;  // [RING] mbarriers
 };
@@ -174,12 +180,13 @@ __device__ __forceinline__ void mma_units(const LinArgs& a, const Smem& sm, int 
 
 // Grid-split linear: out[B, N] = epi( LN?(x)[B, K] * W^T + bias ).  CTA -> (16-row block, set of 8-column tiles);
 // the CTA's 8 warps are spread over (tile, K chunk) units; partial sums are reduced through smem in a fixed order.
-__device__ __forceinline__ void linear_phase(const LinArgs& a, int B, const Smem& sm, uint64_t pol_w) {
+__device__ __forceinline__ void linear_phase(const LinArgs& a, int B, const Smem& sm, uint64_t pol_w, int cta,
+                                             int ncta) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   const int MB = (B + MROWS - 1) / MROWS;
-  const int S = gridDim.x / MB;             // CTAs ("slots") per row block
-  if (S == 0 || (int)blockIdx.x >= MB * S) return;
-  const int mb = blockIdx.x % MB, slot = blockIdx.x / MB;
+  const int S = ncta / MB;                  // CTAs ("slots") per row block
+  if (S == 0 || cta >= MB * S) return;
+  const int mb = cta % MB, slot = cta / MB;
   const int ntiles = (a.N + 7) / 8;
   if (slot >= ntiles) return;
   const int n_my = (ntiles - slot + S - 1) / S;        // tiles slot, slot+S, ...
@@ -299,17 +306,30 @@ __device__ __forceinline__ void linear_phase(const LinArgs& a, int B, const Smem
 // ------------------------------------------------------------------------------------------------------------------
 // Utterance-local helpers (one CTA = one utterance, M = 1)
 
-// y[n] = W[n, :] . x + bias[n]  for n < N; x given as bf16 hi/lo rows in smem (row 0 of the staging buffers).
-// Warp w handles 8-column tiles w, w+8, ...; only MMA row 0 carries data.  Result written to y (smem, fp32).
-// Two tiles x 128 K elements (8 x 16 B weight loads per lane) are requested before the first MMA.  K % 128 == 0.
-__device__ __forceinline__ void matvec_cta(const bf16* xhi, const bf16* xlo, int K, const bf16* W, const float* bias,
-                                           int N, float* y, uint64_t pol_w) {
+// y[n] = W[n, :] . x + bias[n] for n < N; x: fp32 vector in smem (exact, no bf16 split needed on this path),
+// W bf16 [N_pad][K], K % 128 == 0.  CUDA-core FMAs: at M = 1 the tensor cores would be 1/16 used and their dependent
+// accumulate chain is the latency bottleneck.  Warp w handles 8-row tiles w, w+8, ...; lane (g, c) owns row g of the
+// tile and the K slices [kb + 8c, kb + 8c + 8): 16-byte weight loads, 8 independent FMA chains, 4-lane reduction.
+// Two tiles x 128 K elements (8 loads per lane) are requested before the first FMA.
+__device__ __forceinline__ void fma8(float (&acc)[8], const uint4 w, const float4 x0, const float4 x1) {
+  const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+  const float2 a = __bfloat1622float2(w2[0]), b = __bfloat1622float2(w2[1]), c = __bfloat1622float2(w2[2]),
+               d = __bfloat1622float2(w2[3]);
+  acc[0] = fmaf(a.x, x0.x, acc[0]); acc[1] = fmaf(a.y, x0.y, acc[1]);
+  acc[2] = fmaf(b.x, x0.z, acc[2]); acc[3] = fmaf(b.y, x0.w, acc[3]);
+  acc[4] = fmaf(c.x, x1.x, acc[4]); acc[5] = fmaf(c.y, x1.y, acc[5]);
+  acc[6] = fmaf(d.x, x1.z, acc[6]); acc[7] = fmaf(d.y, x1.w, acc[7]);
+}
+__device__ __forceinline__ void matvec_cta(const float* x, int K, const bf16* W, const float* bias, int N, float* y,
+                                           uint64_t pol_w) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
   const int ntiles = (N + 7) / 8;
   for (int tile0 = warp; tile0 < ntiles; tile0 += 2 * NW) {
     const int tile1 = tile0 + NW;
     const bool has1 = tile1 < ntiles;
-    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+    float a0[8], a1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a0[i] = a1[i] = 0.f;
     const bf16* w0 = W + size_t(tile0 * 8 + g) * K + c * 8;
     const bf16* w1 = W + size_t((has1 ? tile1 : tile0) * 8 + g) * K + c * 8;
 #pragma unroll 1
@@ -322,63 +342,41 @@ __device__ __forceinline__ void matvec_cta(const bf16* xhi, const bf16* xlo, int
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int k = kb + u * 32 + c * 8;
-        uint4 h0 = make_uint4(0, 0, 0, 0), l0 = make_uint4(0, 0, 0, 0);
-        if (g == 0) {
-          h0 = *reinterpret_cast<const uint4*>(xhi + k);
-          l0 = *reinterpret_cast<const uint4*>(xlo + k);
-        }
-        mma16816(acc0, h0.x, 0u, h0.y, 0u, wa[u].x, wa[u].y);
-        mma16816(acc0, h0.z, 0u, h0.w, 0u, wa[u].z, wa[u].w);
-        mma16816(acc0, l0.x, 0u, l0.y, 0u, wa[u].x, wa[u].y);
-        mma16816(acc0, l0.z, 0u, l0.w, 0u, wa[u].z, wa[u].w);
-        mma16816(acc1, h0.x, 0u, h0.y, 0u, wb[u].x, wb[u].y);
-        mma16816(acc1, h0.z, 0u, h0.w, 0u, wb[u].z, wb[u].w);
-        mma16816(acc1, l0.x, 0u, l0.y, 0u, wb[u].x, wb[u].y);
-        mma16816(acc1, l0.z, 0u, l0.w, 0u, wb[u].z, wb[u].w);
+        const float* xp = x + kb + u * 32 + c * 8;
+        const float4 x0 = *reinterpret_cast<const float4*>(xp);
+        const float4 x1 = *reinterpret_cast<const float4*>(xp + 4);
+        fma8(a0, wa[u], x0, x1);
+        fma8(a1, wb[u], x0, x1);
       }
     }
-    if (g == 0) {
-      int col = tile0 * 8 + 2 * c;
-      if (col < N) y[col] = acc0[0] + (bias ? __ldg(bias + col) : 0.f);
-      if (col + 1 < N) y[col + 1] = acc0[1] + (bias ? __ldg(bias + col + 1) : 0.f);
-      if (has1) {
-        col = tile1 * 8 + 2 * c;
-        if (col < N) y[col] = acc1[0] + (bias ? __ldg(bias + col) : 0.f);
-        if (col + 1 < N) y[col + 1] = acc1[1] + (bias ? __ldg(bias + col + 1) : 0.f);
-      }
+    float r0 = ((a0[0] + a0[1]) + (a0[2] + a0[3])) + ((a0[4] + a0[5]) + (a0[6] + a0[7]));
+    float r1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]));
+    r0 += __shfl_xor_sync(0xffffffffu, r0, 1);
+    r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+    if (c == 0) {
+      const int n0 = tile0 * 8 + g, n1 = tile1 * 8 + g;
+      if (n0 < N) y[n0] = r0 + (bias ? __ldg(bias + n0) : 0.f);
+      if (has1 && n1 < N) y[n1] = r1 + (bias ? __ldg(bias + n1) : 0.f);
     }
   }
 }
 
-// x (smem fp32 [D]) -> optional LayerNorm -> bf16 hi/lo row 0 of the staging buffers. Executed by warp 0.
-__device__ __forceinline__ void stage_vec(const float* x, int D, const float* g, const float* b, bf16* hi, bf16* lo) {
+// in-place LayerNorm of a smem fp32 vector (warp 0); other warps wait at the caller's __syncthreads
+__device__ __forceinline__ void ln_vec(float* x, int D, const float* g, const float* b) {
   const int lane = threadIdx.x & 31;
   if (threadIdx.x >= 32) return;
-  float mean = 0.f, rstd = 1.f;
-  if (g) {
-    float sum = 0.f;
-    for (int k = lane; k < D; k += 32) sum += x[k];
-    mean = warp_sum(sum) / float(D);
-    float sq = 0.f;
-    for (int k = lane; k < D; k += 32) {
-      const float d = x[k] - mean;
-      sq += d * d;
-    }
-    rstd = 1.0f / sqrtf(warp_sum(sq) / float(D) + 1e-5f);
+  float sum = 0.f;
+  for (int k = lane; k < D; k += 32) sum += x[k];
+  const float mean = warp_sum(sum) / float(D);
+  float sq = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float d = x[k] - mean;
+    sq += d * d;
   }
-  for (int k = lane * 4; k < D; k += 128) {
-    float4 v = *reinterpret_cast<const float4*>(x + k);
-    if (g) {
-      const float4 gm = __ldg(reinterpret_cast<const float4*>(g + k));
-      const float4 bt = __ldg(reinterpret_cast<const float4*>(b + k));
-      v.x = (v.x - mean) * rstd * gm.x + bt.x;
-      v.y = (v.y - mean) * rstd * gm.y + bt.y;
-      v.z = (v.z - mean) * rstd * gm.z + bt.z;
-      v.w = (v.w - mean) * rstd * gm.w + bt.w;
-    }
-    store_hilo4(hi + k, lo + k, v);
-  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / float(D) + 1e-5f);
+  for (int k = lane; k < D; k += 32) x[k] = (x[k] - mean) * rstd * __ldg(g + k) + __ldg(b + k);
 }
 
 // ---- single-query attention for all H heads of one utterance, flash style.
@@ -568,10 +566,18 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
     sm.red = reinterpret_cast<float*>(ptr); ptr += NW * 8 * 32 * 16;
     sm.vec = reinterpret_cast<float*>(ptr); ptr += size_t(4) * p.kmax * 4;
     sm.part = reinterpret_cast<float*>(ptr); ptr += NW * 64 * 4;
-    sm.stat = reinterpret_cast<float*>(ptr); ptr += 64 * 4;
+    sm.stat = reinterpret_cast<float*>(ptr); ptr += 80 * 4;
     sm.full = reinterpret_cast<uint64_t*>(ptr);
   }
-  const int D = p.D, B = p.B, H = p.H;
+  // Teams: the grid is cut into p.teams independent groups of CTAs; each decodes its own contiguous slice of the
+  // batch with its own barrier, so the (latency-bound) phase chains of different slices overlap on the machine.
+  const int ncta = gridDim.x / p.teams;
+  const int team = blockIdx.x / ncta, cta = blockIdx.x % ncta;
+  const int per_team = (p.B + p.teams - 1) / p.teams;
+  const int b0 = team * per_team;
+  const int B = min(per_team, p.B - b0);             // utterances of this team
+  if (team >= p.teams || B <= 0) return;
+  const int D = p.D, H = p.H;
   const uint64_t pol_w = l2_policy_evict_last();
   const uint64_t pol_kv = l2_policy_evict_first();
   if (threadIdx.x == 0) {
@@ -579,6 +585,15 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
     fence_barrier_init();
   }
   __syncthreads();
+  unsigned* bar_counter = p.barrier + team * 32;      // 128 B apart
+  unsigned* done_counter = p.done_count + team * 32;
+  float* g_h = p.h + size_t(b0) * D;
+  float* g_qkv = p.qkv + size_t(b0) * 3 * D;
+  float* g_ff = p.ff + size_t(b0) * p.FF;
+  int32_t* g_tokens = p.tokens + size_t(b0) * (p.L + 1);
+  int32_t* g_ntok = p.n_tokens ? p.n_tokens + b0 : nullptr;
+  int32_t* g_fin = p.finished + b0;
+  float* g_logits = p.step_logits ? p.step_logits + size_t(b0) * p.L * p.V : nullptr;
   unsigned target = 0;
   unsigned ring_parity = 0;            // bit s = parity of the next completion to wait for on stage s
   int pre_u = -1, pre_l = -1;          // (utterance, layer) whose first ring stages have already been requested
@@ -588,7 +603,7 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
   long long* tacc = reinterpret_cast<long long*>(sm.stat + 40);
   long long t_prev = 0;
   if (p.timing && threadIdx.x == 0) {
-    for (int i = 0; i < 10; ++i) tacc[i] = 0;
+    for (int i = 0; i < 16; ++i) tacc[i] = 0;
     t_prev = clock64();
   }
 #define PHASE_DONE(idx)                                  \
@@ -597,31 +612,40 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
     tacc[idx] += now_ - t_prev;                          \
     t_prev = now_;                                       \
   }
+  // sub-phases of B (slots 10..15) are measured with their own clock and do not disturb the phase clock
+  long long t_sub = 0;
+#define SUB_START() if (p.timing && threadIdx.x == 0) t_sub = clock64();
+#define SUB_DONE(idx)                                    \
+  if (p.timing && threadIdx.x == 0) {                    \
+    const long long now_ = clock64();                    \
+    tacc[idx] += now_ - t_sub;                           \
+    t_sub = now_;                                        \
+  }
   float* v_h = sm.vec;                 // [D] residual row
   float* v_x = sm.vec + p.kmax;        // [D] attention output / scratch
   float* v_q = sm.vec + 2 * p.kmax;    // [D] query
   float* v_l = sm.vec + 3 * p.kmax;    // logits (V <= kmax)
 
   // the encoder K/V of this CTA's first utterance, layer 0, can be requested before anything else runs
-  if ((int)blockIdx.x < B) {
+  if (cta < B) {
     if (threadIdx.x == 0)
-      ring_issue(sm, p.ckv + size_t(blockIdx.x) * p.Tp * 2 * D, p.Tp, H, ck_keys, 0, min(RING, nchunks), pol_kv);
-    pre_u = blockIdx.x;
+      ring_issue(sm, p.ckv + size_t(b0 + cta) * p.Tp * 2 * D, p.Tp, H, ck_keys, 0, min(RING, nchunks), pol_kv);
+    pre_u = cta;
     pre_l = 0;
   }
 
   for (int t = 0; t < p.L; ++t) {
     for (int l = 0; l < p.nd; ++l) {
       const PersistentLayer& w = p.layer[l];
-      bf16* cache = p.cache + size_t(l) * B * p.L * 2 * D;
-      const bf16* ckv = p.ckv + size_t(l) * B * p.Tp * 2 * D;
+      bf16* cache = p.cache + (size_t(l) * p.B + b0) * p.L * 2 * D;          // this team's slice of layer l
+      const bf16* ckv = p.ckv + (size_t(l) * p.B + b0) * p.Tp * 2 * D;
       for (int ph = 0; ph < 4; ++ph) {
         if (ph != 1) {
           // ---- A: LN1 + QKV, append K/V (model.py:67-68, layers.py:16-18)
           // ---- C: LN3 + FFN squeeze + ReLU (model.py:73-74, layers.py:54-55)
           // ---- D: FFN unsqueeze + residual
           LinArgs a;
-          a.x = ph == 3 ? p.ff : p.h;
+          a.x = ph == 3 ? g_ff : g_h;
           a.ldx = a.K = ph == 3 ? p.FF : D;
           a.ln_g = ph == 0 ? w.ln1_g : (ph == 2 ? w.ln3_g : nullptr);
           a.ln_b = ph == 0 ? w.ln1_b : (ph == 2 ? w.ln3_b : nullptr);
@@ -630,33 +654,40 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
           a.N = ph == 0 ? 3 * D : (ph == 2 ? p.FF : D);
           a.relu = ph == 2;
           a.epi = ph == 0 ? EPI_QKV : (ph == 2 ? EPI_STORE : EPI_RESIDUAL);
-          a.out = ph == 0 ? p.qkv : (ph == 2 ? p.ff : p.h);
+          a.out = ph == 0 ? g_qkv : (ph == 2 ? g_ff : g_h);
           a.ldo = a.N;
           a.cache = cache; a.cache_rows = p.L; a.cache_col0 = D; a.step = t;
-          linear_phase(a, B, sm, pol_w);
+          linear_phase(a, B, sm, pol_w, cta, ncta);
         } else {
           // ---- B: utterance-local attention chain
-          for (int u = blockIdx.x; u < B; u += gridDim.x) {
+          for (int u = cta; u < B; u += ncta) {
+            SUB_START()
             for (int d = threadIdx.x * 4; d < D; d += NT * 4) {
-              *reinterpret_cast<float4*>(v_h + d) = ldcg4(p.h + size_t(u) * D + d);
-              *reinterpret_cast<float4*>(v_q + d) = ldcg4(p.qkv + size_t(u) * 3 * D + d);
+              *reinterpret_cast<float4*>(v_h + d) = ldcg4(g_h + size_t(u) * D + d);
+              *reinterpret_cast<float4*>(v_q + d) = ldcg4(g_qkv + size_t(u) * 3 * D + d);
             }
             __syncthreads();
+            SUB_DONE(10)
             AttnState st;
             const bf16* kc = cache + size_t(u) * p.L * 2 * D;
             attn_begin(st, v_q, H, p.scale);
             attn_global(st, kc, kc + D, 2 * D, t + 1, H);                  // causal self attention: keys 0..t
             attn_finish(st, H, sm, v_x);
-            stage_vec(v_x, D, nullptr, nullptr, sm.hi, sm.lo);
+            SUB_DONE(11)
+            matvec_cta(v_x, D, w.w_o, w.b_o, D, v_q, pol_w);              // out projection (v_q reused as scratch)
             __syncthreads();
-            matvec_cta(sm.hi, sm.lo, D, w.w_o, w.b_o, D, v_x, pol_w);     // out projection
+            for (int d = threadIdx.x; d < D; d += NT) {                    // residual (model.py:68); keep h, LN a copy
+              const float hv = v_h[d] + v_q[d];
+              v_h[d] = hv;
+              v_x[d] = hv;
+            }
             __syncthreads();
-            for (int d = threadIdx.x; d < D; d += NT) v_h[d] += v_x[d];   // residual (model.py:68)
+            SUB_DONE(12)
+            ln_vec(v_x, D, w.ln2_g, w.ln2_b);                              // LN2 (model.py:70)
             __syncthreads();
-            stage_vec(v_h, D, w.ln2_g, w.ln2_b, sm.hi, sm.lo);             // LN2 (model.py:70)
+            matvec_cta(v_x, D, w.w_qc, w.b_qc, D, v_q, pol_w);            // cross-attention query
             __syncthreads();
-            matvec_cta(sm.hi, sm.lo, D, w.w_qc, w.b_qc, D, v_q, pol_w);   // cross-attention query
-            __syncthreads();
+            SUB_DONE(13)
             // cross attention over the encoder K/V, streamed through the shared-memory ring (never masked)
             const bf16* ck = ckv + size_t(u) * p.Tp * 2 * D;
             if (!(pre_u == u && pre_l == l) && threadIdx.x == 0)
@@ -674,15 +705,15 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
             // request the first stages of the next (utterance, layer) this CTA will serve: they land while the
             // grid-split phases run.  Static data (computed once per utterance), so no ordering hazard.
             {
-              int nu = u + gridDim.x, nl = l;
+              int nu = u + ncta, nl = l;
               if (nu >= B) {
-                nu = blockIdx.x;
+                nu = cta;
                 nl = l + 1;
                 if (nl >= p.nd) nl = (t + 1 < p.L) ? 0 : -1;
               }
               if (nl >= 0) {
                 if (threadIdx.x == 0)
-                  ring_issue(sm, p.ckv + (size_t(nl) * B + nu) * p.Tp * 2 * D, p.Tp, H, ck_keys, 0, min(RING, nchunks),
+                  ring_issue(sm, p.ckv + (size_t(nl) * p.B + b0 + nu) * p.Tp * 2 * D, p.Tp, H, ck_keys, 0, min(RING, nchunks),
                              pol_kv);
                 pre_u = nu;
                 pre_l = nl;
@@ -691,30 +722,28 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
               }
             }
             attn_finish(st, H, sm, v_x);
-            stage_vec(v_x, D, nullptr, nullptr, sm.hi, sm.lo);
+            SUB_DONE(14)
+            matvec_cta(v_x, D, w.w_oc, w.b_oc, D, v_q, pol_w);
             __syncthreads();
-            matvec_cta(sm.hi, sm.lo, D, w.w_oc, w.b_oc, D, v_x, pol_w);
+            for (int d = threadIdx.x; d < D; d += NT) g_h[size_t(u) * D + d] = v_h[d] + v_q[d];   // residual (model.py:71)
             __syncthreads();
-            for (int d = threadIdx.x; d < D; d += NT) p.h[size_t(u) * D + d] = v_h[d] + v_x[d];   // residual (model.py:71)
-            __syncthreads();
+            SUB_DONE(15)
           }
         }
         PHASE_DONE(2 * ph)
-        grid_barrier(p.barrier, target);
+        grid_barrier(bar_counter, target, ncta);
         PHASE_DONE(2 * ph + 1)
       }
     }
     // ---- E: classifier (no final LayerNorm, model.py:142) + argmax + EOS + next embedding
-    for (int u = blockIdx.x; u < B; u += gridDim.x) {
+    for (int u = cta; u < B; u += ncta) {
       for (int d = threadIdx.x * 4; d < D; d += NT * 4)
-        *reinterpret_cast<float4*>(v_h + d) = ldcg4(p.h + size_t(u) * D + d);
+        *reinterpret_cast<float4*>(v_h + d) = ldcg4(g_h + size_t(u) * D + d);
       __syncthreads();
-      stage_vec(v_h, D, nullptr, nullptr, sm.hi, sm.lo);
+      matvec_cta(v_h, D, p.classifier, nullptr, p.V, v_l, pol_w);
       __syncthreads();
-      matvec_cta(sm.hi, sm.lo, D, p.classifier, nullptr, p.V, v_l, pol_w);
-      __syncthreads();
-      if (p.step_logits)
-        for (int v = threadIdx.x; v < p.V; v += NT) p.step_logits[(size_t(u) * p.L + t) * p.V + v] = v_l[v];
+      if (g_logits)
+        for (int v = threadIdx.x; v < p.V; v += NT) g_logits[(size_t(u) * p.L + t) * p.V + v] = v_l[v];
       if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         float best = -INFINITY;
@@ -736,16 +765,16 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
         if (bi == 0x7fffffff) bi = 0;
         int tok = bi;
         if (p.stop_at_eos) {
-          const int fin = p.finished[u];
+          const int fin = g_fin[u];
           if (fin) tok = p.pad;
           else if (tok == p.eos && lane == 0) {
-            p.finished[u] = 1;
-            if (p.n_tokens) p.n_tokens[u] = t + 2;
-            atomicAdd(p.done_count, 1u);
+            g_fin[u] = 1;
+            if (g_ntok) g_ntok[u] = t + 2;
+            atomicAdd(done_counter, 1u);
           }
         }
         if (lane == 0) {
-          p.tokens[size_t(u) * (p.L + 1) + t + 1] = tok;
+          g_tokens[size_t(u) * (p.L + 1) + t + 1] = tok;
           sm.stat[32] = __int_as_float(tok);
         }
       }
@@ -755,23 +784,25 @@ __global__ void __launch_bounds__(NT, 1) dec_persistent_kernel(const __grid_cons
         for (int d = threadIdx.x * 4; d < D; d += NT * 4) {
           const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + size_t(tok) * D + d));
           const float4 q = __ldg(reinterpret_cast<const float4*>(p.pe + size_t(t + 1) * D + d));
-          *reinterpret_cast<float4*>(p.h + size_t(u) * D + d) = make_float4(e.x + q.x, e.y + q.y, e.z + q.z, e.w + q.w);
+          *reinterpret_cast<float4*>(g_h + size_t(u) * D + d) = make_float4(e.x + q.x, e.y + q.y, e.z + q.z, e.w + q.w);
         }
       }
       __syncthreads();
     }
     PHASE_DONE(8)
-    grid_barrier(p.barrier, target);
+    grid_barrier(bar_counter, target, ncta);
     PHASE_DONE(9)
-    if (p.stop_at_eos && ld_acquire_u32(p.done_count) >= (unsigned)B) break;   // uniform: read after the barrier
+    if (p.stop_at_eos && ld_acquire_u32(done_counter) >= (unsigned)B) break;   // uniform: read after the barrier
   }
   // drain: a requested-but-unconsumed prefetch must land before the CTA (and its shared memory) goes away
   if (pre_u >= 0) {
     for (int c = 0; c < min(RING, nchunks); ++c) mbar_wait(&sm.full[c % RING], (ring_parity >> (c % RING)) & 1u);
   }
   if (p.timing && threadIdx.x == 0)
-    for (int i = 0; i < 10; ++i) p.timing[size_t(blockIdx.x) * 10 + i] = tacc[i];
+    for (int i = 0; i < 16; ++i) p.timing[size_t(blockIdx.x) * 16 + i] = tacc[i];
 #undef PHASE_DONE
+#undef SUB_START
+#undef SUB_DONE
 }
 
 }  // namespace
@@ -780,7 +811,7 @@ size_t persistent_smem_bytes(int D, int FF, int V) {
   int kmax = D > FF ? D : FF;
   if (V > kmax) kmax = (V + 127) / 128 * 128;
   return 128 + size_t(RING) * CHUNK_BYTES + size_t(2) * MROWS * (kmax + PAD) * 2 + NW * 8 * 32 * 16 +
-         size_t(4) * kmax * 4 + NW * 64 * 4 + 64 * 4 + RING * 8 + 16;
+         size_t(4) * kmax * 4 + NW * 64 * 4 + 80 * 4 + RING * 8 + 16;
 }
 
 bool persistent_supported(int D, int FF, int V, int H, int nd) {
@@ -807,7 +838,9 @@ int launch_dec_persistent(PersistentParams& p, cudaStream_t s) {
   ASR_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   ASR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dec_persistent_kernel, NT, smem));
   if (per_sm < 1) return set_error(-2, "persistent decoder: kernel does not fit on an SM");
-  ASR_CUDA_OK(cudaMemsetAsync(p.barrier, 0, 2 * sizeof(unsigned), s));   // barrier + done_count are adjacent
+  if (p.teams < 1) p.teams = 1;
+  while (p.teams > 1 && (sms / p.teams) < 8) p.teams >>= 1;
+  ASR_CUDA_OK(cudaMemsetAsync(p.barrier, 0, 2 * PERSIST_MAX_TEAMS * 32 * sizeof(unsigned), s));   // barrier + done arrays
   void* args[] = {&p};
   ASR_CUDA_OK(cudaLaunchCooperativeKernel((void*)dec_persistent_kernel, dim3(sms), dim3(NT), args, smem, s));
   ASR_LAUNCHED(1);

@@ -148,6 +148,7 @@ struct PersistentLayer {
   const bf16* w2; const float* b2;
 };
 constexpr int PERSIST_MAX_LAYERS = 16;
+constexpr int PERSIST_MAX_TEAMS = 16;
 
 struct PersistentParams {
   int B, D, H, FF, V, L, Tp, nd;
@@ -157,10 +158,11 @@ struct PersistentParams {
   const bf16* ckv;        // [nd][B*Tp][2D]
   float *h, *qkv, *ff;    // [B][D], [B][3D], [B][FF]
   int32_t* tokens; int32_t* n_tokens; int32_t* finished; float* step_logits;
-  unsigned* barrier;      // zeroed before launch
-  unsigned* done_count;   // zeroed before launch (stop_at_eos early exit)
-  long long* timing;      // nullable: [gridDim][10] per-phase clock64 totals {A,bar,B,bar,C,bar,D,bar,E,bar}
+  unsigned* barrier;      // [PERSIST_MAX_TEAMS][32] zeroed before launch (one counter per team, 128 B apart)
+  unsigned* done_count;   // [PERSIST_MAX_TEAMS][32] zeroed before launch (stop_at_eos early exit)
+  long long* timing;      // nullable: [gridDim][16] clock64 totals {A,bar,B,bar,C,bar,D,bar,E,bar, B sub-phases x6}
   int eos, pad, stop_at_eos, kmax, sc_ld;
+  int teams;              // independent CTA groups, each with its own batch slice and barrier (>= 1)
   float scale;
 };
 

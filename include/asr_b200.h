@@ -129,7 +129,7 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
  * for the per-kernel step, then entry 9 = the persistent cooperative kernel (all L steps, one launch). */
 int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L, void* ws, size_t ws_bytes,
                        int32_t* tokens, float* ms_per_class, int32_t* launches_per_class,
-                       long long* phase_cycles /* device [#SMs][10], nullable: persistent-kernel phase clocks */,
+                       long long* phase_cycles /* device [#SMs][16], nullable: persistent-kernel phase clocks */,
                        asr_stream_t stream);
 /* Number of kernels this library has launched in the calling process (graph replays counted per kernel). */
 unsigned long long asr_launch_count(void);
