@@ -522,6 +522,11 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
   // Launch mode: "persistent" (default: one cooperative kernel for all L steps), "graph" (one CUDA-graph replay of
   // the 51-kernel step per token) or "eager" (same kernels, launched one by one; bring-up / profiling).
   const char* mode = std::getenv("ASR_B200_DECODE");
+  if (mode && mode[0] == 's' && stream_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers)) {
+    PersistentParams pp;
+    if (int rc = build_persistent(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, pp)) return rc;
+    return launch_dec_stream(pp, s);
+  }
   // configurations whose staging buffers do not fit the persistent kernel's shared memory use the graph path
   const bool can_persist = persistent_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers);
   if ((!mode || !mode[0] || mode[0] == 'p') && can_persist) {
@@ -599,7 +604,7 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
   for (int t = 0; t < L; ++t)
     if (int rc = greedy_step(h, w, B, Tp, L, 0, tokens, nullptr, nullptr, s, &prof)) return rc;
   ASR_CUDA_OK(cudaStreamSynchronize(s));
-  for (int i = 0; i <= DC_COUNT; ++i) {
+  for (int i = 0; i <= DC_COUNT + 1; ++i) {
     ms_per_class[i] = 0.f;
     launches_per_class[i] = 0;
   }
@@ -629,6 +634,30 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
     if (!rc) {
       ASR_CUDA_OK(cudaEventElapsedTime(&ms_per_class[DC_COUNT], e0, e1));
       launches_per_class[DC_COUNT] = 1;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+  }
+  // slot DC_COUNT + 1: the streaming kernel (one CTA per utterance, no barriers)
+  if (stream_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers)) {
+    dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, nullptr, w.finished, w.step, B, L, c.bos_token_id,
+                                                 nullptr);
+    ASR_CUDA_OK(cudaGetLastError());
+    if (int rc = launch_dec_embed(tokens, L + 1, w.step, h->w.embedding, h->w.dec_pe, B, D, c.vocab_size, w.h, s))
+      return rc;
+    PersistentParams pp;
+    if (int rc = build_persistent(h, w, B, Tp, L, 0, tokens, nullptr, nullptr, pp)) return rc;
+    cudaEvent_t e0, e1;
+    ASR_CUDA_OK(cudaEventCreate(&e0));
+    ASR_CUDA_OK(cudaEventCreate(&e1));
+    ASR_CUDA_OK(cudaEventRecord(e0, s));
+    int rc = launch_dec_stream(pp, s);
+    ASR_CUDA_OK(cudaEventRecord(e1, s));
+    ASR_CUDA_OK(cudaStreamSynchronize(s));
+    if (!rc) {
+      ASR_CUDA_OK(cudaEventElapsedTime(&ms_per_class[DC_COUNT + 1], e0, e1));
+      launches_per_class[DC_COUNT + 1] = 1;
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

@@ -1,0 +1,509 @@
+// Streaming greedy decoder: one CTA owns ONE utterance for the whole decode (all L steps, all layers) and everything
+// it reads - the weights of every Linear, the encoder K/V of its utterance, its own self-attention cache - is pulled
+// through a deep shared-memory ring by TMA bulk copies issued by a dedicated producer warp.
+//
+// Restates reference model.py:125-151 (Decoder.evaluate) with a device-resident KV cache.  Why this shape: at the
+// BASELINE batch (64 utterances) a decode step is bound by serialised memory latency and grid-wide barriers, not by
+// bytes.  Utterances never interact, so a CTA that keeps an utterance end to end needs NO inter-CTA synchronisation,
+// and because the order in which it touches memory is static, the producer can run a full ring ahead of the math:
+// latency disappears and the step is bound by the L2 -> shared-memory stream (weights stay L2-resident: evict-last;
+// K/V streams evict-first).  Any batch size works (the grid is simply B CTAs); a finished utterance (stop_at_eos)
+// retires its CTA immediately.
+//
+// Per step the ring carries, in order, for every layer:  Wqkv | self K/V rows 0..t-1 | Wo | Wq(cross) | encoder K/V |
+// Wo(cross) | W1 | W2, and finally the classifier.  Consumers (8 warps) run the chain on CUDA cores with fp32
+// activations straight from shared memory (exact: no bf16 rounding of activations); weights and K/V
+// caches are bf16; LayerNorm / softmax / residual fp32; argmax lowest-index tie-break (model.py:143).
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace asr {
+namespace {
+
+constexpr int NCW = 8;                    // consumer warps
+constexpr int NCT = NCW * 32;             // consumer threads
+constexpr int NTHREADS = NCT + 32;        // + producer warp
+constexpr int STAGE_BYTES = 32768;
+constexpr int NSTAGES = 6;
+
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
+
+struct Ring {
+  uint8_t* buf;
+  uint64_t* full;
+  uint64_t* empty;
+};
+
+// ---- producer side: cut a contiguous segment of `rows` rows (row_bytes each) into ring stages
+struct Producer {
+  Ring r;
+  uint32_t idx;   // running stage counter
+  __device__ __forceinline__ void segment(const void* src, int rows, int row_bytes, uint64_t pol) {
+    const int rps = STAGE_BYTES / row_bytes;          // rows per stage
+    const uint8_t* p = static_cast<const uint8_t*>(src);
+    for (int r0 = 0; r0 < rows; r0 += rps) {
+      const int n = min(rps, rows - r0);
+      const uint32_t s = idx % NSTAGES, round = idx / NSTAGES;
+      mbar_wait(&r.empty[s], (round & 1u) ^ 1u);
+      const uint32_t bytes = uint32_t(n) * row_bytes;
+      mbar_expect_tx(&r.full[s], bytes);
+      bulk_load(r.buf + size_t(s) * STAGE_BYTES, p + size_t(r0) * row_bytes, bytes, &r.full[s], pol);
+      ++idx;
+    }
+  }
+};
+
+// ---- consumer side
+struct Consumer {
+  Ring r;
+  uint32_t idx;
+  __device__ __forceinline__ const uint8_t* acquire() {
+    const uint32_t s = idx % NSTAGES, round = idx / NSTAGES;
+    mbar_wait(&r.full[s], round & 1u);
+    return r.buf + size_t(s) * STAGE_BYTES;
+  }
+  __device__ __forceinline__ void release() {       // every consumer warp calls this once per stage
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&r.empty[idx % NSTAGES]);
+    ++idx;
+  }
+};
+
+__device__ __forceinline__ void fma8(float& acc, const uint4 w, const float4 x0, const float4 x1) {
+  const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&w);
+  const float2 a = __bfloat1622float2(w2[0]), b = __bfloat1622float2(w2[1]), c = __bfloat1622float2(w2[2]),
+               d = __bfloat1622float2(w2[3]);
+  float s0 = a.x * x0.x, s1 = a.y * x0.y;
+  s0 = fmaf(b.x, x0.z, s0); s1 = fmaf(b.y, x0.w, s1);
+  s0 = fmaf(c.x, x1.x, s0); s1 = fmaf(c.y, x1.y, s1);
+  s0 = fmaf(d.x, x1.z, s0); s1 = fmaf(d.y, x1.w, s1);
+  acc += s0 + s1;
+}
+
+// y[n] = (relu?)(W[n,:] . x + bias[n]) (+ resid[n]) for n in [0, N): W streamed through the ring, `rows per stage` =
+// STAGE_BYTES / (2K).  LPR lanes cooperate on one row (16-byte chunks j, j+LPR, ...), fixed-order shuffle reduction.
+__device__ __forceinline__ void matvec_stream(Consumer& c, const float* x, int K, int N_rows, int N, const float* bias,
+                                              int relu, const float* resid, float* y) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int row_bytes = 2 * K;
+  const int rps = STAGE_BYTES / row_bytes;
+  int lpr = 8;                                       // lanes per row: keep all 256 threads busy when a stage is short
+  while (lpr < 32 && (NCT / lpr) > rps) lpr <<= 1;
+  const int rows_per_pass = NCT / lpr;
+  const int j = tid % lpr, rsub = tid / lpr;
+  const int nchunks = K / 8;
+  for (int r0 = 0; r0 < N_rows; r0 += rps) {
+    const int n = min(rps, N_rows - r0);
+    const uint8_t* st = c.acquire();
+    for (int rb = 0; rb < n; rb += rows_per_pass) {
+      const int rl = rb + rsub;
+      float acc = 0.f;
+      if (rl < n) {
+        const uint8_t* wrow = st + size_t(rl) * row_bytes;
+#pragma unroll 4
+        for (int ch = j; ch < nchunks; ch += lpr) {
+          const uint4 w = *reinterpret_cast<const uint4*>(wrow + ch * 16);
+          const float4 x0 = *reinterpret_cast<const float4*>(x + ch * 8);
+          const float4 x1 = *reinterpret_cast<const float4*>(x + ch * 8 + 4);
+          fma8(acc, w, x0, x1);
+        }
+      }
+      for (int off = 1; off < lpr; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      const int row = r0 + rl;
+      if (j == 0 && rl < n && row < N) {
+        float v = acc + (bias ? __ldg(bias + row) : 0.f);
+        if (relu) v = fmaxf(v, 0.f);
+        if (resid) v += resid[row];
+        y[row] = v;
+      }
+    }
+    c.release();
+  }
+}
+
+// in-place-free LayerNorm: dst = LN(src) over D (consumer warp 0), eps 1e-5
+__device__ __forceinline__ void layer_norm(const float* src, float* dst, int D, const float* g, const float* b) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    float sum = 0.f;
+    for (int k = lane; k < D; k += 32) sum += src[k];
+    const float mean = warp_sum(sum) / float(D);
+    float sq = 0.f;
+    for (int k = lane; k < D; k += 32) {
+      const float d = src[k] - mean;
+      sq += d * d;
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / float(D) + 1e-5f);
+    for (int k = lane; k < D; k += 32) dst[k] = (src[k] - mean) * rstd * __ldg(g + k) + __ldg(b + k);
+  }
+}
+
+// ---- single-query attention, flash style (one running (max, sum, acc[8]) per 8-lane key group, log2 units)
+struct Attn {
+  float qv[8];
+  float m, l;
+  float o[8];
+};
+__device__ __forceinline__ void attn_begin(Attn& st, const float* q, int H, float scale) {
+  const int warp = threadIdx.x >> 5, c8 = threadIdx.x & 7;
+  const int h = warp % H;
+  const float4 a = *reinterpret_cast<const float4*>(q + h * 64 + c8 * 8);
+  const float4 b = *reinterpret_cast<const float4*>(q + h * 64 + c8 * 8 + 4);
+  const float sc = scale * 1.4426950408889634f;
+  st.qv[0] = a.x * sc; st.qv[1] = a.y * sc; st.qv[2] = a.z * sc; st.qv[3] = a.w * sc;
+  st.qv[4] = b.x * sc; st.qv[5] = b.y * sc; st.qv[6] = b.z * sc; st.qv[7] = b.w * sc;
+  st.m = -INFINITY;
+  st.l = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) st.o[i] = 0.f;
+}
+template <int NB>
+__device__ __forceinline__ void attn_fold(Attn& st, const uint4 (&kr)[NB], const uint4 (&vr)[NB], const bool (&valid)[NB],
+                                          unsigned gmask) {
+  float sc[NB];
+  float bm = -INFINITY;
+#pragma unroll
+  for (int u = 0; u < NB; ++u) {
+    float sv = 0.f;
+    if (valid[u]) {
+      const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr[u]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(k2[i]);
+        sv = fmaf(st.qv[2 * i], f.x, sv);
+        sv = fmaf(st.qv[2 * i + 1], f.y, sv);
+      }
+    }
+    sv += __shfl_xor_sync(gmask, sv, 1);
+    sv += __shfl_xor_sync(gmask, sv, 2);
+    sv += __shfl_xor_sync(gmask, sv, 4);
+    sc[u] = valid[u] ? sv : -INFINITY;
+    bm = fmaxf(bm, sc[u]);
+  }
+  if (bm == -INFINITY) return;
+  const float m_new = fmaxf(st.m, bm);
+  const float alpha = exp2f(st.m - m_new);
+  st.l *= alpha;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) st.o[i] *= alpha;
+#pragma unroll
+  for (int u = 0; u < NB; ++u) {
+    if (valid[u]) {
+      const float pw = exp2f(sc[u] - m_new);
+      st.l += pw;
+      const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vr[u]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(v2[i]);
+        st.o[2 * i] = fmaf(pw, f.x, st.o[2 * i]);
+        st.o[2 * i + 1] = fmaf(pw, f.y, st.o[2 * i + 1]);
+      }
+    }
+  }
+  st.m = m_new;
+}
+// fold `rows` key rows ([K(H*64) | V(H*64)] bf16, row_bytes = H*256) streamed through the ring
+__device__ __forceinline__ void attn_stream(Attn& st, Consumer& c, int rows, int H) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c8 = lane & 7, sub = lane >> 3;
+  const int wph = NCW / H, h = warp % H, part = warp / H;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  const int stride = wph * 4;                        // key groups per head
+  const int row_bytes = H * 256;
+  const int rps = STAGE_BYTES / row_bytes;           // = 4 * stride: every group owns 4 key slots per stage
+  for (int r0 = 0; r0 < rows; r0 += rps) {
+    const int n = min(rps, rows - r0);
+    const uint8_t* base = c.acquire() + h * 128 + c8 * 16;
+    uint4 kr[4], vr[4];
+    bool valid[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int kl = part * 4 + sub + u * stride;
+      valid[u] = kl < n;
+      if (valid[u]) {
+        kr[u] = *reinterpret_cast<const uint4*>(base + size_t(kl) * row_bytes);
+        vr[u] = *reinterpret_cast<const uint4*>(base + size_t(kl) * row_bytes + H * 128);
+      }
+    }
+    attn_fold<4>(st, kr, vr, valid, gmask);
+    c.release();
+  }
+}
+// fold ONE key row held in shared memory (the current step's k_t / v_t, already rounded to bf16); group 0 of each head
+__device__ __forceinline__ void attn_self_current(Attn& st, const bf16* kv_row, int H) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c8 = lane & 7, sub = lane >> 3;
+  const int h = warp % H, part = warp / H;
+  const unsigned gmask = 0xFFu << (lane & 24);
+  uint4 kr[1], vr[1];
+  bool valid[1];
+  valid[0] = (part == 0 && sub == 0);
+  if (valid[0]) {
+    kr[0] = *reinterpret_cast<const uint4*>(kv_row + h * 64 + c8 * 8);
+    vr[0] = *reinterpret_cast<const uint4*>(kv_row + H * 64 + h * 64 + c8 * 8);
+  }
+  attn_fold<1>(st, kr, vr, valid, gmask);
+}
+__device__ __forceinline__ void attn_finish(Attn& st, int H, float* part_buf, float* stat, float* out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c8 = lane & 7, sub = lane >> 3;
+  const int wph = NCW / H;
+#pragma unroll
+  for (int off = 8; off <= 16; off <<= 1) {
+    const float mo = __shfl_xor_sync(0xffffffffu, st.m, off);
+    const float lo = __shfl_xor_sync(0xffffffffu, st.l, off);
+    const float mn = fmaxf(st.m, mo);
+    const float fa = (st.m == -INFINITY) ? 0.f : exp2f(st.m - mn);
+    const float fb = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
+    st.l = st.l * fa + lo * fb;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float oo = __shfl_xor_sync(0xffffffffu, st.o[i], off);
+      st.o[i] = st.o[i] * fa + oo * fb;
+    }
+    st.m = mn;
+  }
+  if (sub == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part_buf[warp * 64 + c8 * 8 + i] = st.o[i];
+    if (c8 == 0) {
+      stat[warp] = st.m;
+      stat[NCW + warp] = st.l;
+    }
+  }
+  consumer_sync();
+  for (int d = threadIdx.x; d < H * 64; d += NCT) {
+    const int hh = d >> 6, dd = d & 63;
+    float mm = -INFINITY;
+    for (int pI = 0; pI < wph; ++pI) mm = fmaxf(mm, stat[pI * H + hh]);
+    float t = 0.f, ls = 0.f;
+    for (int pI = 0; pI < wph; ++pI) {
+      const float mw = stat[pI * H + hh];
+      const float f = (mw == -INFINITY) ? 0.f : exp2f(mw - mm);
+      t += part_buf[(pI * H + hh) * 64 + dd] * f;
+      ls += stat[NCW + pI * H + hh] * f;
+    }
+    out[d] = ls > 0.f ? t / ls : 0.f;
+  }
+  consumer_sync();
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) dec_stream_kernel(const __grid_constant__ PersistentParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* ptr = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  Ring ring;
+  ring.buf = ptr; ptr += size_t(NSTAGES) * STAGE_BYTES;
+  const int D = p.D, H = p.H, FF = p.FF;
+  float* v_h = reinterpret_cast<float*>(ptr); ptr += D * 4;          // residual row
+  float* v_x = reinterpret_cast<float*>(ptr); ptr += D * 4;          // LayerNorm output / attention output
+  float* v_qkv = reinterpret_cast<float*>(ptr); ptr += 3 * D * 4;    // q | k | v of the current token
+  float* v_f = reinterpret_cast<float*>(ptr); ptr += p.kmax * 4;     // FFN hidden / logits
+  float* part_buf = reinterpret_cast<float*>(ptr); ptr += NCW * 64 * 4;
+  float* stat = reinterpret_cast<float*>(ptr); ptr += 32 * 4;
+  bf16* kv_row = reinterpret_cast<bf16*>(ptr); ptr += 2 * D * 2;     // current k_t | v_t (bf16, as cached)
+  volatile int* ctrl = reinterpret_cast<volatile int*>(ptr); ptr += 16;   // [0] steps completed, [1] stop, [2] token
+  ring.full = reinterpret_cast<uint64_t*>(ptr); ptr += NSTAGES * 8;
+  ring.empty = reinterpret_cast<uint64_t*>(ptr);
+
+  const int u = blockIdx.x;                     // this CTA's utterance
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGES; ++s) {
+      mbar_init(&ring.full[s], 1);
+      mbar_init(&ring.empty[s], NCW);
+    }
+    ctrl[0] = 0;
+    ctrl[1] = 0;
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const size_t cache_layer_stride = size_t(p.B) * p.L * 2 * D;
+  const size_t ckv_layer_stride = size_t(p.B) * p.Tp * 2 * D;
+  bf16* my_cache = p.cache + size_t(u) * p.L * 2 * D;
+  const bf16* my_ckv = p.ckv + size_t(u) * p.Tp * 2 * D;
+
+  if (warp == NCW) {
+    // =============================== producer: one thread walks the static access sequence
+    if (threadIdx.x == NCT) {
+      const uint64_t pol_w = policy_evict_last(), pol_kv = policy_evict_first();
+      Producer pr;
+      pr.r = ring;
+      pr.idx = 0;
+      for (int t = 0; t < p.L; ++t) {
+        // rows 0..t-1 of the self cache were written by this CTA in earlier steps; with stop_at_eos the decision to
+        // run step t at all is also taken there.  ctrl[0] counts completed steps, ctrl[1] is the stop flag.
+        if (p.stop_at_eos) {                       // strict gate: nothing of step t is requested before step t-1 ended
+          while (ctrl[0] < t && !ctrl[1]) {
+          }
+          if (ctrl[1]) break;
+        }
+        for (int l = 0; l < p.nd; ++l) {
+          const PersistentLayer& w = p.layer[l];
+          pr.segment(w.w_qkv, 3 * D, 2 * D, pol_w);
+          if (l == 0)
+            while (ctrl[0] < t) {                    // cache rows < t exist once step t-1 has completed
+            }
+          pr.segment(my_cache + l * cache_layer_stride, t, 4 * D, pol_kv);
+          pr.segment(w.w_o, D, 2 * D, pol_w);
+          pr.segment(w.w_qc, D, 2 * D, pol_w);
+          pr.segment(my_ckv + l * ckv_layer_stride, p.Tp, 4 * D, pol_kv);
+          pr.segment(w.w_oc, D, 2 * D, pol_w);
+          pr.segment(w.w1, FF, 2 * D, pol_w);
+          pr.segment(w.w2, D, 2 * FF, pol_w);
+        }
+        pr.segment(p.classifier, (p.V + 7) / 8 * 8, 2 * D, pol_w);
+      }
+    }
+    return;
+  }
+
+  // ================================= consumers
+  Consumer c;
+  c.r = ring;
+  c.idx = 0;
+  const int tid = threadIdx.x;
+  int32_t* my_tokens = p.tokens + size_t(u) * (p.L + 1);
+  for (int d = tid * 4; d < D; d += NCT * 4)                       // embedding + PE of the first token (by the host-
+    *reinterpret_cast<float4*>(v_h + d) = *reinterpret_cast<const float4*>(p.h + size_t(u) * D + d);   // side init kernel)
+  consumer_sync();
+
+  for (int t = 0; t < p.L; ++t) {
+    for (int l = 0; l < p.nd; ++l) {
+      const PersistentLayer& w = p.layer[l];
+      bf16* cache = my_cache + l * cache_layer_stride;
+      // ---- LN1 -> q, k, v (model.py:67-68, layers.py:16-18)
+      layer_norm(v_h, v_x, D, w.ln1_g, w.ln1_b);
+      consumer_sync();
+      matvec_stream(c, v_x, D, 3 * D, 3 * D, w.b_qkv, 0, nullptr, v_qkv);
+      consumer_sync();
+      // append k_t, v_t (bf16) to the device-resident cache and keep the rounded copy for this step
+      for (int d = tid * 2; d < 2 * D; d += NCT * 2) {
+        const __nv_bfloat162 v2 = __floats2bfloat162_rn(v_qkv[D + d], v_qkv[D + d + 1]);
+        *reinterpret_cast<__nv_bfloat162*>(kv_row + d) = v2;
+        *reinterpret_cast<__nv_bfloat162*>(cache + size_t(t) * 2 * D + d) = v2;
+      }
+      consumer_sync();
+      // ---- causal self attention over keys 0..t
+      Attn st;
+      attn_begin(st, v_qkv, H, p.scale);
+      attn_self_current(st, kv_row, H);
+      attn_stream(st, c, t, H);
+      attn_finish(st, H, part_buf, stat, v_x);
+      matvec_stream(c, v_x, D, D, D, w.b_o, 0, v_h, v_h);          // out projection + residual, in place
+      consumer_sync();
+      // ---- LN2 -> cross-attention query -> attention over the encoder K/V (never masked) (model.py:70-71)
+      layer_norm(v_h, v_x, D, w.ln2_g, w.ln2_b);
+      consumer_sync();
+      matvec_stream(c, v_x, D, D, D, w.b_qc, 0, nullptr, v_qkv);
+      consumer_sync();
+      attn_begin(st, v_qkv, H, p.scale);
+      attn_stream(st, c, p.Tp, H);
+      attn_finish(st, H, part_buf, stat, v_x);
+      matvec_stream(c, v_x, D, D, D, w.b_oc, 0, v_h, v_h);
+      consumer_sync();
+      // ---- LN3 -> FFN (model.py:73-74, layers.py:54-57)
+      layer_norm(v_h, v_x, D, w.ln3_g, w.ln3_b);
+      consumer_sync();
+      matvec_stream(c, v_x, D, FF, FF, w.b1, 1, nullptr, v_f);
+      consumer_sync();
+      matvec_stream(c, v_f, FF, D, D, w.b2, 0, v_h, v_h);
+      consumer_sync();
+    }
+    // ---- classifier WITHOUT the final LayerNorm (model.py:142) -> argmax -> EOS -> next embedding
+    matvec_stream(c, v_h, D, (p.V + 7) / 8 * 8, p.V, nullptr, 0, nullptr, v_f);
+    consumer_sync();
+    if (p.step_logits)
+      for (int v = tid; v < p.V; v += NCT) p.step_logits[(size_t(u) * p.L + t) * p.V + v] = v_f[v];
+    if (tid < 32) {
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+      for (int v = tid; v < p.V; v += 32)
+        if (v_f[v] > best) {
+          best = v_f[v];
+          bi = v;
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) {
+          best = ob;
+          bi = oi;
+        }
+      }
+      if (bi == 0x7fffffff) bi = 0;
+      if (tid == 0) {
+        my_tokens[t + 1] = bi;
+        int stop = 0;
+        if (p.stop_at_eos && bi == p.eos) {
+          if (p.n_tokens) p.n_tokens[u] = t + 2;
+          for (int k = t + 2; k <= p.L; ++k) my_tokens[k] = p.pad;
+          stop = 1;
+        }
+        ctrl[2] = bi;
+        __threadfence();                                   // cache rows / tokens of this step are globally visible
+        asm volatile("fence.proxy.async;" ::: "memory");   // ... also to the async proxy (TMA reads of the cache)
+        if (stop) ctrl[1] = 1;
+        ctrl[0] = t + 1;
+      }
+    }
+    consumer_sync();
+    if (ctrl[1]) break;
+    if (t + 1 < p.L) {
+      const int tok = ctrl[2];
+      for (int d = tid * 4; d < D; d += NCT * 4) {
+        const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + size_t(tok) * D + d));
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p.pe + size_t(t + 1) * D + d));
+        *reinterpret_cast<float4*>(v_h + d) = make_float4(e.x + q.x, e.y + q.y, e.z + q.z, e.w + q.w);
+      }
+    }
+    consumer_sync();
+  }
+}
+
+size_t stream_smem_bytes(int D, int FF, int V) {
+  int kmax = FF > V ? FF : V;
+  if (D > kmax) kmax = D;
+  return 128 + size_t(NSTAGES) * STAGE_BYTES + size_t(5) * D * 4 + size_t(kmax) * 4 + NCW * 64 * 4 + 32 * 4 + 2 * D * 2 +
+         16 + 2 * NSTAGES * 8 + 64;
+}
+
+}  // namespace
+
+bool stream_supported(int D, int FF, int V, int H, int nd) {
+  return nd <= PERSIST_MAX_LAYERS && (H == 2 || H == 4 || H == 8) && D == 64 * H && D % 128 == 0 && FF % 8 == 0 &&
+         2 * FF <= STAGE_BYTES && 4 * D <= STAGE_BYTES && stream_smem_bytes(D, FF, V) <= 227 * 1024;
+}
+
+int launch_dec_stream(PersistentParams& p, cudaStream_t s) {
+  if (!stream_supported(p.D, p.FF, p.V, p.H, p.nd))
+    return set_error(-2, "streaming decoder: unsupported config D=%d FF=%d H=%d", p.D, p.FF, p.H);
+  p.kmax = p.FF > p.V ? p.FF : p.V;
+  if (p.D > p.kmax) p.kmax = p.D;
+  const size_t smem = stream_smem_bytes(p.D, p.FF, p.V);
+  static size_t configured = 0;
+  if (smem > configured) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(dec_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dec_stream_kernel<<<p.B, NTHREADS, smem, s>>>(p);
+  ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
+  return 0;
+}
+
+}  // namespace asr

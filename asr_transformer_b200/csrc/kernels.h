@@ -169,5 +169,8 @@ struct PersistentParams {
 size_t persistent_smem_bytes(int D, int FF, int V);
 bool persistent_supported(int D, int FF, int V, int H, int nd);
 int launch_dec_persistent(PersistentParams& p, cudaStream_t s);
+// streaming decoder (decode_stream.cu): one CTA per utterance, weights + K/V streamed through a TMA ring, no barriers
+bool stream_supported(int D, int FF, int V, int H, int nd);
+int launch_dec_stream(PersistentParams& p, cudaStream_t s);
 
 }  // namespace asr

@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel / per-phase profiling pass")
-    ap.add_argument("--decode-mode", default="", choices=["", "persistent", "graph", "eager"],
+    ap.add_argument("--decode-mode", default="", choices=["", "persistent", "stream", "graph", "eager"],
                     help="sets ASR_B200_DECODE (default: the library default, persistent)")
     return ap.parse_args()
 
@@ -271,8 +271,8 @@ def main():
     elif rank == 0:
         # -------------------------------------------------------------- roofline of the dominant kernel
         ws = eng._ws(batch, 4 * cfg.encoder_seq_len + 3, cfg.decoder_seq_len)
-        ms_cls = (C.c_float * 10)()
-        n_cls = (C.c_int32 * 10)()
+        ms_cls = (C.c_float * 11)()
+        n_cls = (C.c_int32 * 11)()
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         phase = torch.zeros(n_sm, 16, dtype=torch.int64, device=dev)
         for _ in range(2):     # second pass is the measured one (first warms caches / clocks)
@@ -302,9 +302,14 @@ def main():
         result["decode_kernel_profile"] = prof
         result["decode_step"] = {"alg_bytes": int(step_bytes), "per_kernel_step_sum_ms": round(tot, 3),
                                  "roofline_ms_per_decode": round(decode_bytes / (hbm_peak * 1e9) * 1e3, 3)}
-        if mode.startswith("p") and n_cls[9]:
+        result["decode_kernels_ms"] = {"persistent": round(ms_cls[9], 3) if n_cls[9] else None,
+                                       "stream": round(ms_cls[10], 3) if n_cls[10] else None}
+        slot = 10 if mode.startswith("s") else 9
+        if mode[0] in "ps" and n_cls[slot]:
+            ms_cls[9] = ms_cls[slot]
             gbs = decode_bytes / (ms_cls[9] * 1e-3) / 1e9
-            result["roofline"] = {"kernel": "dec_persistent_kernel (all %d decode steps, one cooperative launch)" % cfg.decoder_seq_len,
+            result["roofline"] = {"kernel": ("dec_stream_kernel" if slot == 10 else "dec_persistent_kernel") +
+                                            " (all %d decode steps, one launch)" % cfg.decoder_seq_len,
                                   "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
                                   "frac": round(gbs / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
                                   "alg_bytes_per_launch": int(decode_bytes), "ms_per_launch": round(ms_cls[9], 3)}

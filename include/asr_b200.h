@@ -118,15 +118,17 @@ int asr_decoder_forward(AsrHandle* h, const float* enc_out, int B, int Tp, const
  * tokens[:,t+1].  stop_at_eos == 0 reproduces the reference (exactly L steps, tokens keep flowing after EOS);
  * stop_at_eos != 0 writes pad_token_id after the first EOS (and the persistent kernel leaves early once every
  * utterance has finished).  Launch mode is selected by the environment variable ASR_B200_DECODE: "persistent"
- * (default: one cooperative kernel runs all L steps), "graph" (CUDA-graph replay of the per-kernel step) or "eager". */
+ * (one cooperative kernel runs all L steps, grid barriers between phases), "stream" (one CTA per utterance, weights
+ * and K/V streamed through a TMA ring, no barriers), "graph" (CUDA-graph replay of the per-kernel step) or "eager". */
 int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, int stop_at_eos,
                       const int32_t* first_tokens /* [B] nullable: defaults to bos_token_id */, void* ws,
                       size_t ws_bytes, int32_t* tokens, int32_t* n_tokens, float* step_logits, asr_stream_t stream);
 
 /* Profiling aid for bench.py: the same decode launched eagerly with a CUDA-event pair around every kernel.
- * Synchronises `stream` before returning.  ms_per_class / launches_per_class: 10 entries in the order
+ * Synchronises `stream` before returning.  ms_per_class / launches_per_class: 11 entries in the order
  * {qkv linear, self attention, out projections, cross q linear, cross attention, ffn1, ffn2, classifier, select}
- * for the per-kernel step, then entry 9 = the persistent cooperative kernel (all L steps, one launch). */
+ * for the per-kernel step, entry 9 = the persistent cooperative kernel, entry 10 = the streaming kernel
+ * (each: all L steps in one launch). */
 int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L, void* ws, size_t ws_bytes,
                        int32_t* tokens, float* ms_per_class, int32_t* launches_per_class,
                        long long* phase_cycles /* device [#SMs][16], nullable: persistent-kernel phase clocks */,

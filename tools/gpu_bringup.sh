@@ -21,6 +21,7 @@ case $g in
        $CMD > gpurun_out/ncu_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1; echo "ncu list exit $?"
        $CMD > gpurun_out/ncu_plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:dec_persistent -c 1 -o gpurun_out/prof_persistent $CMD > gpurun_out/ncu_full.log 2>&1; echo "ncu full exit $?"; ls -la gpurun_out/*.ncu-rep ;;
   benchteams) for t in 1 2 8 16; do ASR_B200_TEAMS=$t timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-profile > gpurun_out/bench_t$t.log 2>&1; echo "teams=$t: $(python -c "import json,sys; d=json.loads(open('gpurun_out/bench_t$t.log').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'])")"; done ;;
+  benchstream) timeout 600 python bench.py --steps 5 --warmup 3 --decode-mode stream --no-cpu-baseline > gpurun_out/benchstream.log 2> gpurun_out/benchstream.err; echo "benchstream exit $?"; python -c "import json; d=json.loads(open('gpurun_out/benchstream.log').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['decode_kernels_ms'], d['roofline'])"; tail -n 3 gpurun_out/benchstream.err ;;
   benchref) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/benchref.log 2>&1; echo "benchref exit $?"; tail -c 1500 gpurun_out/benchref.log ;;
 esac
 done
