@@ -316,6 +316,7 @@ static int build_persistent(const AsrHandle* h, const GreedyWs& w, int B, int Tp
     pl.w2 = static_cast<const bf16*>(lw.ffn.w2); pl.b2 = lw.ffn.b2;
   }
   pp.classifier = static_cast<const bf16*>(h->w.classifier_w); pp.emb = h->w.embedding; pp.pe = h->w.dec_pe;
+  pp.dec_small = h->w.dec_small;
   pp.cache = w.cache; pp.ckv = w.ckv; pp.h = w.h; pp.qkv = w.qkv; pp.ff = w.ff;
   pp.tokens = tokens; pp.n_tokens = n_tokens; pp.finished = w.finished; pp.step_logits = step_logits;
   pp.barrier = w.barrier; pp.done_count = w.barrier + PERSIST_MAX_TEAMS * 32;
@@ -522,7 +523,8 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
   // Launch mode: "persistent" (default: one cooperative kernel for all L steps), "graph" (one CUDA-graph replay of
   // the 51-kernel step per token) or "eager" (same kernels, launched one by one; bring-up / profiling).
   const char* mode = std::getenv("ASR_B200_DECODE");
-  if (mode && mode[0] == 's' && stream_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers)) {
+  if (mode && mode[0] == 's' && h->w.dec_small &&
+      stream_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers)) {
     PersistentParams pp;
     if (int rc = build_persistent(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, pp)) return rc;
     return launch_dec_stream(pp, s);
@@ -640,7 +642,7 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
     if (rc) return rc;
   }
   // slot DC_COUNT + 1: the streaming kernel (one CTA per utterance, no barriers)
-  if (stream_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers)) {
+  if (h->w.dec_small && stream_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers)) {
     dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, nullptr, w.finished, w.step, B, L, c.bos_token_id,
                                                  nullptr);
     ASR_CUDA_OK(cudaGetLastError());
@@ -651,6 +653,7 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
     cudaEvent_t e0, e1;
     ASR_CUDA_OK(cudaEventCreate(&e0));
     ASR_CUDA_OK(cudaEventCreate(&e1));
+    pp.timing = phase_cycles ? phase_cycles + size_t(148) * 16 : nullptr;   // second half of the caller's buffer
     ASR_CUDA_OK(cudaEventRecord(e0, s));
     int rc = launch_dec_stream(pp, s);
     ASR_CUDA_OK(cudaEventRecord(e1, s));

@@ -26,6 +26,11 @@ constexpr int NTHREADS = NCT + 32;        // + producer warp
 constexpr int STAGE_BYTES = 32768;
 constexpr int NSTAGES = 6;
 
+}  // namespace
+// floats of one layer's packed small-parameter block (biases + LayerNorm), padded to whole 1 KB rows
+int stream_small_floats(int D, int FF) { return (13 * D + FF + 255) / 256 * 256; }
+namespace {
+
 __device__ __forceinline__ uint64_t policy_evict_last() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -54,13 +59,16 @@ struct Ring {
 struct Producer {
   Ring r;
   uint32_t idx;   // running stage counter
+  long long waited = 0;
   __device__ __forceinline__ void segment(const void* src, int rows, int row_bytes, uint64_t pol) {
     const int rps = STAGE_BYTES / row_bytes;          // rows per stage
     const uint8_t* p = static_cast<const uint8_t*>(src);
     for (int r0 = 0; r0 < rows; r0 += rps) {
       const int n = min(rps, rows - r0);
       const uint32_t s = idx % NSTAGES, round = idx / NSTAGES;
+      const long long w0 = clock64();
       mbar_wait(&r.empty[s], (round & 1u) ^ 1u);
+      waited += clock64() - w0;
       const uint32_t bytes = uint32_t(n) * row_bytes;
       mbar_expect_tx(&r.full[s], bytes);
       bulk_load(r.buf + size_t(s) * STAGE_BYTES, p + size_t(r0) * row_bytes, bytes, &r.full[s], pol);
@@ -73,9 +81,12 @@ struct Producer {
 struct Consumer {
   Ring r;
   uint32_t idx;
+  long long waited = 0;
   __device__ __forceinline__ const uint8_t* acquire() {
     const uint32_t s = idx % NSTAGES, round = idx / NSTAGES;
+    const long long w0 = clock64();
     mbar_wait(&r.full[s], round & 1u);
+    waited += clock64() - w0;
     return r.buf + size_t(s) * STAGE_BYTES;
   }
   __device__ __forceinline__ void release() {       // every consumer warp calls this once per stage
@@ -85,56 +96,83 @@ struct Consumer {
   }
 };
 
-__device__ __forceinline__ void fma8(float& acc, const uint4 w, const float4 x0, const float4 x1) {
+__device__ __forceinline__ void fma8(float& acc, const uint4 w, const float (&x)[8]) {
   const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(&w);
   const float2 a = __bfloat1622float2(w2[0]), b = __bfloat1622float2(w2[1]), c = __bfloat1622float2(w2[2]),
                d = __bfloat1622float2(w2[3]);
-  float s0 = a.x * x0.x, s1 = a.y * x0.y;
-  s0 = fmaf(b.x, x0.z, s0); s1 = fmaf(b.y, x0.w, s1);
-  s0 = fmaf(c.x, x1.x, s0); s1 = fmaf(c.y, x1.y, s1);
-  s0 = fmaf(d.x, x1.z, s0); s1 = fmaf(d.y, x1.w, s1);
+  float s0 = a.x * x[0], s1 = a.y * x[1];
+  s0 = fmaf(b.x, x[2], s0); s1 = fmaf(b.y, x[3], s1);
+  s0 = fmaf(c.x, x[4], s0); s1 = fmaf(c.y, x[5], s1);
+  s0 = fmaf(d.x, x[6], s0); s1 = fmaf(d.y, x[7], s1);
   acc += s0 + s1;
 }
 
-// y[n] = (relu?)(W[n,:] . x + bias[n]) (+ resid[n]) for n in [0, N): W streamed through the ring, `rows per stage` =
-// STAGE_BYTES / (2K).  LPR lanes cooperate on one row (16-byte chunks j, j+LPR, ...), fixed-order shuffle reduction.
+// y[n] = (relu?)(W[n,:] . x + bias[n]) (+ resid[n]) for n in [0, N): W streamed through the ring (rows per stage =
+// STAGE_BYTES / 2K).  XC 16-byte chunks of a row per lane, lpr = K / (8 XC) lanes per row; the lane's slice of x lives
+// in registers for the whole matvec, so shared memory is read for the weights only (once).  Two rows per thread are
+// in flight; the lpr partial sums are combined by a fixed-order shuffle tree.  bias / resid / y are shared memory.
+template <int XC>
 __device__ __forceinline__ void matvec_stream(Consumer& c, const float* x, int K, int N_rows, int N, const float* bias,
                                               int relu, const float* resid, float* y) {
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int row_bytes = 2 * K;
   const int rps = STAGE_BYTES / row_bytes;
-  int lpr = 8;                                       // lanes per row: keep all 256 threads busy when a stage is short
-  while (lpr < 32 && (NCT / lpr) > rps) lpr <<= 1;
+  const int lpr = K / (8 * XC);                      // lanes per row (1..32)
   const int rows_per_pass = NCT / lpr;
   const int j = tid % lpr, rsub = tid / lpr;
-  const int nchunks = K / 8;
+  float xr[XC][8];
+#pragma unroll
+  for (int i = 0; i < XC; ++i) {
+    const float4 a = *reinterpret_cast<const float4*>(x + (j + i * lpr) * 8);
+    const float4 b = *reinterpret_cast<const float4*>(x + (j + i * lpr) * 8 + 4);
+    xr[i][0] = a.x; xr[i][1] = a.y; xr[i][2] = a.z; xr[i][3] = a.w;
+    xr[i][4] = b.x; xr[i][5] = b.y; xr[i][6] = b.z; xr[i][7] = b.w;
+  }
   for (int r0 = 0; r0 < N_rows; r0 += rps) {
     const int n = min(rps, N_rows - r0);
     const uint8_t* st = c.acquire();
-    for (int rb = 0; rb < n; rb += rows_per_pass) {
-      const int rl = rb + rsub;
-      float acc = 0.f;
-      if (rl < n) {
-        const uint8_t* wrow = st + size_t(rl) * row_bytes;
-#pragma unroll 4
-        for (int ch = j; ch < nchunks; ch += lpr) {
-          const uint4 w = *reinterpret_cast<const uint4*>(wrow + ch * 16);
-          const float4 x0 = *reinterpret_cast<const float4*>(x + ch * 8);
-          const float4 x1 = *reinterpret_cast<const float4*>(x + ch * 8 + 4);
-          fma8(acc, w, x0, x1);
-        }
+    for (int rb = 0; rb < n; rb += 2 * rows_per_pass) {
+      const int rl0 = rb + rsub, rl1 = rl0 + rows_per_pass;
+      float acc0 = 0.f, acc1 = 0.f;
+      const uint8_t* w0 = st + size_t(rl0 < n ? rl0 : 0) * row_bytes + j * 16;
+      const uint8_t* w1 = st + size_t(rl1 < n ? rl1 : 0) * row_bytes + j * 16;
+      uint4 wa[XC], wb[XC];
+#pragma unroll
+      for (int i = 0; i < XC; ++i) {
+        wa[i] = *reinterpret_cast<const uint4*>(w0 + i * lpr * 16);
+        wb[i] = *reinterpret_cast<const uint4*>(w1 + i * lpr * 16);
       }
-      for (int off = 1; off < lpr; off <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-      const int row = r0 + rl;
-      if (j == 0 && rl < n && row < N) {
-        float v = acc + (bias ? __ldg(bias + row) : 0.f);
-        if (relu) v = fmaxf(v, 0.f);
-        if (resid) v += resid[row];
-        y[row] = v;
+#pragma unroll
+      for (int i = 0; i < XC; ++i) {
+        fma8(acc0, wa[i], xr[i]);
+        fma8(acc1, wb[i], xr[i]);
+      }
+      for (int off = 1; off < lpr; off <<= 1) {
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, off);
+      }
+      if (j == 0) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int rl = q ? rl1 : rl0;
+          const int row = r0 + rl;
+          if (rl < n && row < N) {
+            float v = (q ? acc1 : acc0) + (bias ? bias[row] : 0.f);
+            if (relu) v = fmaxf(v, 0.f);
+            if (resid) v += resid[row];
+            y[row] = v;
+          }
+        }
       }
     }
     c.release();
   }
+}
+// K-dependent dispatch: 4 chunks per lane up to K = 1024 (lpr <= 32), 8 beyond
+__device__ __forceinline__ void matvec(Consumer& c, const float* x, int K, int N_rows, int N, const float* bias, int relu,
+                                       const float* resid, float* y) {
+  if (K <= 1024) matvec_stream<4>(c, x, K, N_rows, N, bias, relu, resid, y);
+  else matvec_stream<8>(c, x, K, N_rows, N, bias, relu, resid, y);
 }
 
 // in-place-free LayerNorm: dst = LN(src) over D (consumer warp 0), eps 1e-5
@@ -150,7 +188,7 @@ __device__ __forceinline__ void layer_norm(const float* src, float* dst, int D, 
       sq += d * d;
     }
     const float rstd = 1.0f / sqrtf(warp_sum(sq) / float(D) + 1e-5f);
-    for (int k = lane; k < D; k += 32) dst[k] = (src[k] - mean) * rstd * __ldg(g + k) + __ldg(b + k);
+    for (int k = lane; k < D; k += 32) dst[k] = (src[k] - mean) * rstd * g[k] + b[k];
   }
 }
 
@@ -314,6 +352,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_stream_kernel(const __grid_co
   float* part_buf = reinterpret_cast<float*>(ptr); ptr += NCW * 64 * 4;
   float* stat = reinterpret_cast<float*>(ptr); ptr += 32 * 4;
   bf16* kv_row = reinterpret_cast<bf16*>(ptr); ptr += 2 * D * 2;     // current k_t | v_t (bf16, as cached)
+  float* prm = reinterpret_cast<float*>(ptr); ptr += size_t(p.small_floats) * 4;   // this layer's biases + LN params
   volatile int* ctrl = reinterpret_cast<volatile int*>(ptr); ptr += 16;   // [0] steps completed, [1] stop, [2] token
   ring.full = reinterpret_cast<uint64_t*>(ptr); ptr += NSTAGES * 8;
   ring.empty = reinterpret_cast<uint64_t*>(ptr);
@@ -353,6 +392,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_stream_kernel(const __grid_co
         }
         for (int l = 0; l < p.nd; ++l) {
           const PersistentLayer& w = p.layer[l];
+          pr.segment(p.dec_small + size_t(l) * p.small_floats, p.small_floats / 256, 1024, pol_w);
           pr.segment(w.w_qkv, 3 * D, 2 * D, pol_w);
           if (l == 0)
             while (ctrl[0] < t) {                    // cache rows < t exist once step t-1 has completed
@@ -367,6 +407,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_stream_kernel(const __grid_co
         }
         pr.segment(p.classifier, (p.V + 7) / 8 * 8, 2 * D, pol_w);
       }
+      if (p.timing) {
+        p.timing[size_t(blockIdx.x) * 16 + 2] = pr.waited;
+        p.timing[size_t(blockIdx.x) * 16 + 3] = pr.idx;
+      }
     }
     return;
   }
@@ -376,6 +420,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_stream_kernel(const __grid_co
   c.r = ring;
   c.idx = 0;
   const int tid = threadIdx.x;
+  const long long t_begin = clock64();
   int32_t* my_tokens = p.tokens + size_t(u) * (p.L + 1);
   for (int d = tid * 4; d < D; d += NCT * 4)                       // embedding + PE of the first token (by the host-
     *reinterpret_cast<float4*>(v_h + d) = *reinterpret_cast<const float4*>(p.h + size_t(u) * D + d);   // side init kernel)
@@ -383,12 +428,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_stream_kernel(const __grid_co
 
   for (int t = 0; t < p.L; ++t) {
     for (int l = 0; l < p.nd; ++l) {
-      const PersistentLayer& w = p.layer[l];
       bf16* cache = my_cache + l * cache_layer_stride;
+      // ---- this layer's biases and LayerNorm parameters arrive through the ring: copy them out of the stage(s)
+      {
+        const int rows = p.small_floats / 256, rps = STAGE_BYTES / 1024;
+        for (int r0 = 0; r0 < rows; r0 += rps) {
+          const int n = min(rps, rows - r0);
+          const float4* src = reinterpret_cast<const float4*>(c.acquire());
+          float4* dst = reinterpret_cast<float4*>(prm + size_t(r0) * 256);
+          for (int i = tid; i < n * 64; i += NCT) dst[i] = src[i];
+          c.release();
+        }
+        consumer_sync();
+      }
+      const float* b_qkv = prm;
+      const float* b_o = prm + 3 * D;
+      const float* b_qc = prm + 4 * D;
+      const float* b_oc = prm + 5 * D;
+      const float* b_1 = prm + 6 * D;
+      const float* b_2 = prm + 6 * D + FF;
+      const float* ln = prm + 7 * D + FF;            // ln1 g,b | ln2 g,b | ln3 g,b
       // ---- LN1 -> q, k, v (model.py:67-68, layers.py:16-18)
-      layer_norm(v_h, v_x, D, w.ln1_g, w.ln1_b);
+      layer_norm(v_h, v_x, D, ln, ln + D);
       consumer_sync();
-      matvec_stream(c, v_x, D, 3 * D, 3 * D, w.b_qkv, 0, nullptr, v_qkv);
+      matvec(c, v_x, D, 3 * D, 3 * D, b_qkv, 0, nullptr, v_qkv);
       consumer_sync();
       // append k_t, v_t (bf16) to the device-resident cache and keep the rounded copy for this step
       for (int d = tid * 2; d < 2 * D; d += NCT * 2) {
@@ -403,28 +466,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_stream_kernel(const __grid_co
       attn_self_current(st, kv_row, H);
       attn_stream(st, c, t, H);
       attn_finish(st, H, part_buf, stat, v_x);
-      matvec_stream(c, v_x, D, D, D, w.b_o, 0, v_h, v_h);          // out projection + residual, in place
+      matvec(c, v_x, D, D, D, b_o, 0, v_h, v_h);                   // out projection + residual, in place
       consumer_sync();
       // ---- LN2 -> cross-attention query -> attention over the encoder K/V (never masked) (model.py:70-71)
-      layer_norm(v_h, v_x, D, w.ln2_g, w.ln2_b);
+      layer_norm(v_h, v_x, D, ln + 2 * D, ln + 3 * D);
       consumer_sync();
-      matvec_stream(c, v_x, D, D, D, w.b_qc, 0, nullptr, v_qkv);
+      matvec(c, v_x, D, D, D, b_qc, 0, nullptr, v_qkv);
       consumer_sync();
       attn_begin(st, v_qkv, H, p.scale);
       attn_stream(st, c, p.Tp, H);
       attn_finish(st, H, part_buf, stat, v_x);
-      matvec_stream(c, v_x, D, D, D, w.b_oc, 0, v_h, v_h);
+      matvec(c, v_x, D, D, D, b_oc, 0, v_h, v_h);
       consumer_sync();
       // ---- LN3 -> FFN (model.py:73-74, layers.py:54-57)
-      layer_norm(v_h, v_x, D, w.ln3_g, w.ln3_b);
+      layer_norm(v_h, v_x, D, ln + 4 * D, ln + 5 * D);
       consumer_sync();
-      matvec_stream(c, v_x, D, FF, FF, w.b1, 1, nullptr, v_f);
+      matvec(c, v_x, D, FF, FF, b_1, 1, nullptr, v_f);
       consumer_sync();
-      matvec_stream(c, v_f, FF, D, D, w.b2, 0, v_h, v_h);
+      matvec(c, v_f, FF, D, D, b_2, 0, v_h, v_h);
       consumer_sync();
     }
     // ---- classifier WITHOUT the final LayerNorm (model.py:142) -> argmax -> EOS -> next embedding
-    matvec_stream(c, v_h, D, (p.V + 7) / 8 * 8, p.V, nullptr, 0, nullptr, v_f);
+    matvec(c, v_h, D, (p.V + 7) / 8 * 8, p.V, nullptr, 0, nullptr, v_f);
     consumer_sync();
     if (p.step_logits)
       for (int v = tid; v < p.V; v += NCT) p.step_logits[(size_t(u) * p.L + t) * p.V + v] = v_f[v];
@@ -473,23 +536,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) dec_stream_kernel(const __grid_co
     }
     consumer_sync();
   }
+  if (p.timing && tid == 0) {
+    p.timing[size_t(blockIdx.x) * 16 + 0] = clock64() - t_begin;
+    p.timing[size_t(blockIdx.x) * 16 + 1] = c.waited;
+  }
 }
 
 size_t stream_smem_bytes(int D, int FF, int V) {
   int kmax = FF > V ? FF : V;
   if (D > kmax) kmax = D;
   return 128 + size_t(NSTAGES) * STAGE_BYTES + size_t(5) * D * 4 + size_t(kmax) * 4 + NCW * 64 * 4 + 32 * 4 + 2 * D * 2 +
-         16 + 2 * NSTAGES * 8 + 64;
+         size_t(stream_small_floats(D, FF)) * 4 + 16 + 2 * NSTAGES * 8 + 64;
 }
 
 }  // namespace
 
 bool stream_supported(int D, int FF, int V, int H, int nd) {
-  return nd <= PERSIST_MAX_LAYERS && (H == 2 || H == 4 || H == 8) && D == 64 * H && D % 128 == 0 && FF % 8 == 0 &&
+  return nd <= PERSIST_MAX_LAYERS && D % 32 == 0 && FF % 64 == 0 && FF <= 2048 && (H == 2 || H == 4 || H == 8) && D == 64 * H && D % 128 == 0 && FF % 8 == 0 &&
          2 * FF <= STAGE_BYTES && 4 * D <= STAGE_BYTES && stream_smem_bytes(D, FF, V) <= 227 * 1024;
 }
 
 int launch_dec_stream(PersistentParams& p, cudaStream_t s) {
+  if (!p.dec_small) return set_error(-2, "streaming decoder: packed small parameters (AsrWeights.dec_small) missing");
+  p.small_floats = stream_small_floats(p.D, p.FF);
   if (!stream_supported(p.D, p.FF, p.V, p.H, p.nd))
     return set_error(-2, "streaming decoder: unsupported config D=%d FF=%d H=%d", p.D, p.FF, p.H);
   p.kmax = p.FF > p.V ? p.FF : p.V;

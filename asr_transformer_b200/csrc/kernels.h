@@ -162,6 +162,8 @@ struct PersistentParams {
   unsigned* done_count;   // [PERSIST_MAX_TEAMS][32] zeroed before launch (stop_at_eos early exit)
   long long* timing;      // nullable: [gridDim][16] clock64 totals {A,bar,B,bar,C,bar,D,bar,E,bar, B sub-phases x6}
   int eos, pad, stop_at_eos, kmax, sc_ld;
+  const float* dec_small; // [nd][small_floats] packed biases + LayerNorm params per layer (streaming decoder)
+  int small_floats;
   int teams;              // independent CTA groups, each with its own batch slice and barrier (>= 1)
   float scale;
 };
@@ -171,6 +173,7 @@ bool persistent_supported(int D, int FF, int V, int H, int nd);
 int launch_dec_persistent(PersistentParams& p, cudaStream_t s);
 // streaming decoder (decode_stream.cu): one CTA per utterance, weights + K/V streamed through a TMA ring, no barriers
 bool stream_supported(int D, int FF, int V, int H, int nd);
+int stream_small_floats(int D, int FF);
 int launch_dec_stream(PersistentParams& p, cudaStream_t s);
 
 }  // namespace asr

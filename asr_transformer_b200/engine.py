@@ -84,6 +84,23 @@ def pack_classifier(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pack_dec_small(decoder: nn.Module) -> torch.Tensor:
+    """Per decoder layer one contiguous fp32 block (padded to 256 floats) with every bias and LayerNorm parameter, in
+    the order the streaming decoder consumes them: b_qkv(3D) | b_out(D) | cross b_q(D) | cross b_out(D) | b1(FF) |
+    b2(D) | norm1 g,b | norm2 g,b | norm3 g,b."""
+    rows = []
+    for layer in decoder._layers:
+        sa, ca, ff = pack_mha(layer._mask_attention), pack_mha(layer._cross_attention), layer._feedforward
+        D = sa["b_out"].numel()
+        parts = [sa["b_qkv"], sa["b_out"], ca["b_qkv"][:D], ca["b_out"], _f32(ff.squeeze.bias), _f32(ff.unsqueeze.bias)]
+        for ln in (layer._norm1, layer._norm2, layer._norm3):
+            parts += [_f32(ln.weight), _f32(ln.bias)]
+        v = torch.cat([p.reshape(-1) for p in parts])
+        pad = (-v.numel()) % 256
+        rows.append(torch.cat([v, v.new_zeros(pad)]))
+    return torch.stack(rows).contiguous()
+
+
 def _mha_struct(p: dict) -> _l.AsrMhaWeights:
     return _l.AsrMhaWeights(p["w_qkv"].data_ptr(), p["b_qkv"].data_ptr(), p["w_out"].data_ptr(), p["b_out"].data_ptr())
 
@@ -195,6 +212,10 @@ class Engine:
                 FF = layer._feedforward.ff_dim
             keep.append(arr)
             w.dec_layers = arr
+            if len(decoder._layers):
+                small = pack_dec_small(decoder)
+                keep.append(small)
+                w.dec_small = small.data_ptr()
         else:
             cfg.vocab_size, cfg.decoder_seq_len, cfg.decoder_num_layers = 1, 1, 0
         if H is None:   # zero layers everywhere: derive from D

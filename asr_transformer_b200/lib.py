@@ -50,7 +50,7 @@ class AsrWeights(C.Structure):
                 ("enc_layers", C.POINTER(AsrEncoderLayerWeights)), ("enc_norm_out", AsrNormWeights),
                 ("embedding", c_void_p), ("dec_pe", c_void_p),
                 ("dec_layers", C.POINTER(AsrDecoderLayerWeights)), ("dec_norm", AsrNormWeights),
-                ("classifier_w", c_void_p)]
+                ("classifier_w", c_void_p), ("dec_small", c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/asr_b200.h one to one (tests/test_abi.py checks the symbol list)

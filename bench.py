@@ -274,12 +274,16 @@ def main():
         ms_cls = (C.c_float * 11)()
         n_cls = (C.c_int32 * 11)()
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        phase = torch.zeros(n_sm, 16, dtype=torch.int64, device=dev)
+        phase = torch.zeros(2 * max(n_sm, 148, batch), 16, dtype=torch.int64, device=dev)
         for _ in range(2):     # second pass is the measured one (first warms caches / clocks)
             L.check(lib.asr_decode_profile(eng.handle, L.ptr(enc), batch, cfg.encoder_seq_len, cfg.decoder_seq_len,
                                            L.ptr(ws), ws.numel(), L.ptr(tokens), ms_cls, n_cls, L.ptr(phase),
                                            L.stream()), "asr_decode_profile")
         ph = phase.double().cpu()
+        sp = ph[148:148 + batch]
+        result["stream_cycles_per_step"] = {k: round(float(sp[:, i].mean()) / cfg.decoder_seq_len, 1) for i, k in
+                                            enumerate(["total", "consumer_wait_full", "producer_wait_empty", "stages_total"])}
+        ph = ph[:n_sm]
         names = ["A_ln1_qkv", "bar", "B_attn_chain", "bar", "C_ln3_ffn1", "bar", "D_ffn2", "bar", "E_classify", "bar",
                  "B0_load", "B1_self_attn", "B2_out_proj", "B3_ln2_q", "B4_cross_attn", "B5_out_proj"]
         mhz = clocks.get("sm_mhz") or 1965.0

@@ -83,6 +83,9 @@ typedef struct {
   const AsrDecoderLayerWeights* dec_layers;   /* HOST array [decoder_num_layers] */
   AsrNormWeights dec_norm;   /* decoder._norm_layer (applied by forward, skipped by evaluate: model.py:122 vs 142) */
   const void* classifier_w;  /* bf16 [round_up(vocab, 64), D], rows >= vocab zero; no bias (model.py:102) */
+  /* optional (NULL disables the streaming decoder): fp32 [decoder_num_layers][P], P = round_up(13 D + FF, 256):
+   * per layer b_qkv(3D) | b_out(D) | cross b_q(D) | cross b_out(D) | b1(FF) | b2(D) | norm1 g,b | norm2 g,b | norm3 g,b */
+  const float* dec_small;
 } AsrWeights;
 
 const char* asr_last_error(void);
