@@ -333,6 +333,28 @@ static int build_persistent(const AsrHandle* h, const GreedyWs& w, int B, int Tp
   return 0;
 }
 
+static bool cluster_available(const AsrHandle* h) {
+  const AsrConfig& c = h->cfg;
+  ClusterLayout lay;
+  return h->w.dec_image && c.decoder_num_layers > 0 &&
+         cluster_layout(c.embedding_dim, c.num_heads, c.ff_dim, c.vocab_size, c.decoder_num_layers, &lay) &&
+         h->w.dec_image_bytes == lay.total_bytes;
+}
+
+static void build_cluster(const AsrHandle* h, const GreedyWs& w, int B, int Tp, int L, int stop_at_eos, int32_t* tokens,
+                          int32_t* n_tokens, float* step_logits, ClusterParams& cp) {
+  const AsrConfig& c = h->cfg;
+  std::memset(&cp, 0, sizeof(cp));
+  cp.B = B; cp.D = c.embedding_dim; cp.H = c.num_heads; cp.FF = c.ff_dim; cp.V = c.vocab_size; cp.L = L; cp.Tp = Tp;
+  cp.nd = c.decoder_num_layers;
+  cp.image = static_cast<const uint8_t*>(h->w.dec_image); cp.image_bytes = h->w.dec_image_bytes;
+  cp.emb = h->w.embedding; cp.pe = h->w.dec_pe; cp.h0 = w.h;
+  cp.cache = w.cache; cp.ckv = w.ckv;
+  cp.tokens = tokens; cp.n_tokens = n_tokens; cp.step_logits = step_logits;
+  cp.eos = c.eos_token_id; cp.pad = c.pad_token_id; cp.stop_at_eos = stop_at_eos;
+  cp.scale = 1.0f / sqrtf((float)c.embedding_dim);
+}
+
 }  // namespace
 
 extern "C" {
@@ -523,6 +545,14 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
   // Launch mode: "persistent" (default: one cooperative kernel for all L steps), "graph" (one CUDA-graph replay of
   // the 51-kernel step per token) or "eager" (same kernels, launched one by one; bring-up / profiling).
   const char* mode = std::getenv("ASR_B200_DECODE");
+  if (mode && mode[0] == 'c' && !cluster_available(h))
+    return set_error(ASR_E_UNSUPPORTED, "asr_decode_greedy: cluster decoder requested but unavailable (packed image "
+                     "missing or config unsupported: heads must be 2, 4 or 8, ff_dim %% (32 heads) == 0)");
+  if ((!mode || !mode[0] || mode[0] == 'c') && cluster_available(h)) {
+    ClusterParams cp;
+    build_cluster(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, cp);
+    return launch_dec_cluster(cp, s);
+  }
   if (mode && mode[0] == 's' && h->w.dec_small &&
       stream_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers)) {
     PersistentParams pp;
@@ -606,7 +636,7 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
   for (int t = 0; t < L; ++t)
     if (int rc = greedy_step(h, w, B, Tp, L, 0, tokens, nullptr, nullptr, s, &prof)) return rc;
   ASR_CUDA_OK(cudaStreamSynchronize(s));
-  for (int i = 0; i <= DC_COUNT + 1; ++i) {
+  for (int i = 0; i <= DC_COUNT + 2; ++i) {
     ms_per_class[i] = 0.f;
     launches_per_class[i] = 0;
   }
@@ -666,7 +696,40 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
     cudaEventDestroy(e1);
     if (rc) return rc;
   }
+  // slot DC_COUNT + 2: the cluster kernel (one cluster of num_heads CTAs per utterance group, DSMEM all-reduces)
+  if (cluster_available(h)) {
+    dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, nullptr, w.finished, w.step, B, L, c.bos_token_id,
+                                                 nullptr);
+    ASR_CUDA_OK(cudaGetLastError());
+    if (int rc = launch_dec_embed(tokens, L + 1, w.step, h->w.embedding, h->w.dec_pe, B, D, c.vocab_size, w.h, s))
+      return rc;
+    ClusterParams cp;
+    build_cluster(h, w, B, Tp, L, 0, tokens, nullptr, nullptr, cp);
+    cp.timing = phase_cycles ? phase_cycles + size_t(2) * 148 * 16 : nullptr;   // third part of the caller's buffer
+    cudaEvent_t e0, e1;
+    ASR_CUDA_OK(cudaEventCreate(&e0));
+    ASR_CUDA_OK(cudaEventCreate(&e1));
+    ASR_CUDA_OK(cudaEventRecord(e0, s));
+    int rc = launch_dec_cluster(cp, s);
+    ASR_CUDA_OK(cudaEventRecord(e1, s));
+    ASR_CUDA_OK(cudaStreamSynchronize(s));
+    if (!rc) {
+      ASR_CUDA_OK(cudaEventElapsedTime(&ms_per_class[DC_COUNT + 2], e0, e1));
+      launches_per_class[DC_COUNT + 2] = 1;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (rc) return rc;
+  }
   return 0;
+}
+
+size_t asr_decoder_image_bytes(const AsrConfig* cfg) {
+  ClusterLayout lay;
+  if (!cfg || !cluster_layout(cfg->embedding_dim, cfg->num_heads, cfg->ff_dim, cfg->vocab_size, cfg->decoder_num_layers,
+                              &lay))
+    return 0;
+  return lay.total_bytes;
 }
 
 unsigned long long asr_launch_count(void) { return g_kernel_launches; }

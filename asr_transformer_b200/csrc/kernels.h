@@ -27,7 +27,7 @@ extern unsigned long long g_kernel_launches;
 // ---- TMA tensor maps (driver entry point resolved at run time, no link-time libcuda dependency)
 // bf16 tensor, innermost dim contiguous. dims/strides innermost first; strides in BYTES for dims >= 1.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, const uint32_t* elem_strides /*nullable*/);
+                   const uint32_t* box, const uint32_t* elem_strides /*nullable*/, int swizzle_bytes = 128 /* 0 = none */);
 
 // ---- GEMM  Y[M,N] = X[M,K] * W[N,K]^T (+bias)(relu)(+rowvec)(+residual)  (tcgen05 / TMEM / TMA)
 struct GemmEpilogue {
@@ -175,5 +175,32 @@ int launch_dec_persistent(PersistentParams& p, cudaStream_t s);
 bool stream_supported(int D, int FF, int V, int H, int nd);
 int stream_small_floats(int D, int FF);
 int launch_dec_stream(PersistentParams& p, cudaStream_t s);
+
+
+// ---- cluster greedy decoder (decode_cluster.cu): one thread-block cluster (num_heads CTAs, one head each) per group
+// of <= 8 utterances; weights streamed from a fragment-major packed image (AsrWeights.dec_image)
+struct ClusterMat { int MT, KB, KBS, KG; };   // m-tiles (16 rows), k-blocks (32 cols), k-blocks per ring stage, k-groups
+struct ClusterLayout {                        // byte layout of the packed decoder image (see include/asr_b200.h)
+  int CS, FFS, VS, small_floats;
+  size_t small_bytes, off_small, off_qkv, off_wo, off_wqc, off_woc, off_w1, off_w2, layer_bytes, off_cls, rank_bytes,
+      total_bytes;
+};
+bool cluster_layout(int D, int H, int FF, int V, int nd, ClusterLayout* out);
+struct ClusterParams {
+  int B, D, H, FF, V, L, Tp, nd;
+  int GU, GUP, FFS, VS, nstages, kv_evict_first;
+  ClusterMat m_qkv, m_wo, m_wqc, m_w1, m_w2, m_cls;
+  const uint8_t* image; size_t image_bytes, rank_bytes, layer_bytes;
+  size_t off_small, off_qkv, off_wo, off_wqc, off_woc, off_w1, off_w2, off_cls;
+  uint32_t small_bytes;
+  const float* emb; const float* pe; const float* h0;   // h0: fp32 [B][D] embedding + PE of the first token
+  bf16* cache;            // [nd][B][H][K rows | V rows][L][64]  (this kernel's own layout of the self-attention cache)
+  const bf16* ckv;        // [nd][B*Tp][2D]
+  int32_t* tokens; int32_t* n_tokens; float* step_logits;
+  int eos, pad, stop_at_eos;
+  float scale;
+  long long* timing;      // nullable: [gridDim][16] {total, ring wait, exchange wait, producer wait, stages}
+};
+int launch_dec_cluster(ClusterParams& p, cudaStream_t s);
 
 }  // namespace asr

@@ -101,6 +101,97 @@ def pack_dec_small(decoder: nn.Module) -> torch.Tensor:
     return torch.stack(rows).contiguous()
 
 
+def dec_image_layout(D: int, H: int, FF: int, V: int, nd: int) -> Optional[dict]:
+    """Byte layout of the cluster decoder's packed image; mirrors cluster_layout() in csrc/decode_cluster.cu
+    (documented in include/asr_b200.h).  None when the configuration is not supported by that kernel."""
+    if H < 2 or H > 8 or (H & (H - 1)) or D != 64 * H or FF % (32 * H) or V < 1:
+        return None
+    FFS = FF // H
+    VS = ((V + H - 1) // H + 15) // 16 * 16
+    if D > 512 or FFS > 512 or VS > 512:
+        return None
+    lay = {"CS": H, "FFS": FFS, "VS": VS, "small_floats": 256 + FFS + 9 * D}
+    lay["small_bytes"] = (lay["small_floats"] * 4 + 127) // 128 * 128
+    if lay["small_bytes"] > 32768:
+        return None
+    off = 0
+    for name, nbytes in (("small", lay["small_bytes"]), ("qkv", 192 * D * 2), ("wo", D * 64 * 2), ("wqc", 64 * D * 2),
+                         ("woc", D * 64 * 2), ("w1", FFS * D * 2), ("w2", D * FFS * 2)):
+        lay["off_" + name] = off
+        off += nbytes
+    lay["layer_bytes"] = off
+    lay["off_cls"] = nd * off
+    lay["rank_bytes"] = lay["off_cls"] + VS * D * 2
+    lay["total_bytes"] = lay["rank_bytes"] * H
+    return lay
+
+
+def pack_mma_a(w: torch.Tensor) -> torch.Tensor:
+    """bf16 [R, K] (R % 16 == 0, K % 32 == 0) -> flat bf16 in the cluster decoder's fragment-major order
+    [k-block kb (32 cols)][m-tile mt (16 rows)][k-tile s (2)][g (8)][tg (4)][8], the 8 elements being the
+    mma.m16n8k16 A fragment {a0, a1, a2, a3} of lane (g, tg): with r = 16 mt + g and c = 32 kb + 8 tg + 4 s they are
+    w[r, c:c+2], w[r+8, c:c+2], w[r, c+2:c+4], w[r+8, c+2:c+4] - one LDS.128 per lane feeds one MMA directly."""
+    R, K = w.shape
+    assert R % 16 == 0 and K % 32 == 0, (R, K)
+    t = w.reshape(R // 16, 2, 8, K // 32, 4, 2, 2, 2)    # mt, p, g, kb, tg, s, pair, e
+    return t.permute(3, 0, 5, 2, 4, 6, 1, 7).contiguous().reshape(-1)
+
+
+def pack_dec_image(decoder: nn.Module) -> Optional[torch.Tensor]:
+    """Packed weight image of the cluster decoder (uint8): for every head r (= CTA rank) the slices that CTA consumes,
+    in consumption order, per layer: small fp32 block [b_qkv_r(192) | b_qc_r(64) | b1_r(FFS) | b_o(D) | b_oc(D) |
+    b2(D) | ln1 g,b | ln2 g,b | ln3 g,b] (padded to 128 B), then Wqkv rows of head r (q|k|v), Wo[:, head r columns],
+    cross Wq rows of head r, cross Wo[:, head r columns], W1 rows r*FFS.., W2[:, r*FFS..] - each in pack_mma_a order;
+    after the layers the classifier rows r*VS.. (zero padded)."""
+    layers = list(decoder._layers)
+    if not layers:
+        return None
+    D = decoder._embedding.embedding_dim
+    V = decoder._embedding.num_embeddings
+    H = len(layers[0]._mask_attention._heads)
+    FF = layers[0]._feedforward.ff_dim
+    lay = dec_image_layout(D, H, FF, V, len(layers))
+    if lay is None:
+        return None
+    FFS, VS = lay["FFS"], lay["VS"]
+    dev = decoder._embedding.weight.device
+    cls = torch.zeros(H * VS, D, dtype=torch.bfloat16, device=dev)
+    cls[:V] = decoder._classifier.weight.detach().to(torch.bfloat16)
+
+    def u8(t: torch.Tensor) -> torch.Tensor:
+        return t.contiguous().view(torch.uint8).reshape(-1)
+
+    ranks = []
+    for r in range(H):
+        parts = []
+        hs = slice(r * 64, (r + 1) * 64)
+        for layer in layers:
+            sa, ca, ff = pack_mha(layer._mask_attention), pack_mha(layer._cross_attention), pack_ffn(layer._feedforward)
+            rows_qkv = torch.cat([torch.arange(r * 64, (r + 1) * 64) + k * D for k in range(3)]).to(dev)
+            small = [sa["b_qkv"][rows_qkv], ca["b_qkv"][hs], ff["b1"][r * FFS:(r + 1) * FFS], sa["b_out"], ca["b_out"],
+                     ff["b2"]]
+            for ln in (layer._norm1, layer._norm2, layer._norm3):
+                small += [_f32(ln.weight), _f32(ln.bias)]
+            small = torch.cat([x.reshape(-1) for x in small])
+            assert small.numel() == lay["small_floats"]
+            small = torch.cat([small, small.new_zeros(lay["small_bytes"] // 4 - small.numel())])
+            blk = [u8(small),
+                   u8(pack_mma_a(sa["w_qkv"][rows_qkv])),
+                   u8(pack_mma_a(sa["w_out"][:, hs])),
+                   u8(pack_mma_a(ca["w_qkv"][hs])),
+                   u8(pack_mma_a(ca["w_out"][:, hs])),
+                   u8(pack_mma_a(ff["w1"][r * FFS:(r + 1) * FFS])),
+                   u8(pack_mma_a(ff["w2"][:, r * FFS:(r + 1) * FFS]))]
+            blk = torch.cat(blk)
+            assert blk.numel() == lay["layer_bytes"]
+            parts.append(blk)
+        parts.append(u8(pack_mma_a(cls[r * VS:(r + 1) * VS])))
+        rk = torch.cat(parts)
+        assert rk.numel() == lay["rank_bytes"]
+        ranks.append(rk)
+    return torch.cat(ranks).contiguous()
+
+
 def _mha_struct(p: dict) -> _l.AsrMhaWeights:
     return _l.AsrMhaWeights(p["w_qkv"].data_ptr(), p["b_qkv"].data_ptr(), p["w_out"].data_ptr(), p["b_out"].data_ptr())
 
@@ -216,6 +307,10 @@ class Engine:
                 small = pack_dec_small(decoder)
                 keep.append(small)
                 w.dec_small = small.data_ptr()
+                image = pack_dec_image(decoder)
+                if image is not None:
+                    keep.append(image)
+                    w.dec_image, w.dec_image_bytes = image.data_ptr(), image.numel()
         else:
             cfg.vocab_size, cfg.decoder_seq_len, cfg.decoder_num_layers = 1, 1, 0
         if H is None:   # zero layers everywhere: derive from D

@@ -47,8 +47,8 @@ def parse():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel / per-phase profiling pass")
-    ap.add_argument("--decode-mode", default="", choices=["", "persistent", "stream", "graph", "eager"],
-                    help="sets ASR_B200_DECODE (default: the library default, persistent)")
+    ap.add_argument("--decode-mode", default="", choices=["", "cluster", "persistent", "stream", "graph", "eager"],
+                    help="sets ASR_B200_DECODE (default: the library default, cluster)")
     return ap.parse_args()
 
 
@@ -170,7 +170,7 @@ def main():
     args = parse()
     if args.decode_mode:
         os.environ["ASR_B200_DECODE"] = args.decode_mode
-    mode = os.environ.get("ASR_B200_DECODE", "") or "persistent"
+    mode = os.environ.get("ASR_B200_DECODE", "") or "cluster"
     from oracle import speech_transformer as O      # workload registry + synthetic inputs + CPU baseline only
     cfg = O.CONFIGS[args.workload]
     if args.impl == "reference":
@@ -271,10 +271,10 @@ def main():
     elif rank == 0:
         # -------------------------------------------------------------- roofline of the dominant kernel
         ws = eng._ws(batch, 4 * cfg.encoder_seq_len + 3, cfg.decoder_seq_len)
-        ms_cls = (C.c_float * 11)()
-        n_cls = (C.c_int32 * 11)()
+        ms_cls = (C.c_float * 12)()
+        n_cls = (C.c_int32 * 12)()
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        phase = torch.zeros(2 * max(n_sm, 148, batch), 16, dtype=torch.int64, device=dev)
+        phase = torch.zeros(3 * max(n_sm, 148, batch, 256), 16, dtype=torch.int64, device=dev)
         for _ in range(2):     # second pass is the measured one (first warms caches / clocks)
             L.check(lib.asr_decode_profile(eng.handle, L.ptr(enc), batch, cfg.encoder_seq_len, cfg.decoder_seq_len,
                                            L.ptr(ws), ws.numel(), L.ptr(tokens), ms_cls, n_cls, L.ptr(phase),
@@ -283,6 +283,13 @@ def main():
         sp = ph[148:148 + batch]
         result["stream_cycles_per_step"] = {k: round(float(sp[:, i].mean()) / cfg.decoder_seq_len, 1) for i, k in
                                             enumerate(["total", "consumer_wait_full", "producer_wait_empty", "stages_total"])}
+        cp = ph[2 * 148:2 * 148 + 148]
+        cp = cp[cp[:, 0] > 0]
+        if len(cp):
+            result["cluster_cycles_per_step"] = {k: round(float(cp[:, i].mean()) / cfg.decoder_seq_len, 1) for i, k in
+                                                 enumerate(["total", "ring_wait", "exchange_wait", "producer_wait_empty",
+                                                            "stages_total"])}
+            result["cluster_ctas"] = int(len(cp))
         ph = ph[:n_sm]
         names = ["A_ln1_qkv", "bar", "B_attn_chain", "bar", "C_ln3_ffn1", "bar", "D_ffn2", "bar", "E_classify", "bar",
                  "B0_load", "B1_self_attn", "B2_out_proj", "B3_ln2_q", "B4_cross_attn", "B5_out_proj"]
@@ -307,12 +314,13 @@ def main():
         result["decode_step"] = {"alg_bytes": int(step_bytes), "per_kernel_step_sum_ms": round(tot, 3),
                                  "roofline_ms_per_decode": round(decode_bytes / (hbm_peak * 1e9) * 1e3, 3)}
         result["decode_kernels_ms"] = {"persistent": round(ms_cls[9], 3) if n_cls[9] else None,
-                                       "stream": round(ms_cls[10], 3) if n_cls[10] else None}
-        slot = 10 if mode.startswith("s") else 9
-        if mode[0] in "ps" and n_cls[slot]:
+                                       "stream": round(ms_cls[10], 3) if n_cls[10] else None,
+                                       "cluster": round(ms_cls[11], 3) if n_cls[11] else None}
+        slot = {"s": 10, "c": 11}.get(mode[0], 9)
+        if mode[0] in "psc" and n_cls[slot]:
             ms_cls[9] = ms_cls[slot]
             gbs = decode_bytes / (ms_cls[9] * 1e-3) / 1e9
-            result["roofline"] = {"kernel": ("dec_stream_kernel" if slot == 10 else "dec_persistent_kernel") +
+            result["roofline"] = {"kernel": {9: "dec_persistent_kernel", 10: "dec_stream_kernel", 11: "dec_cluster_kernel"}[slot] +
                                             " (all %d decode steps, one launch)" % cfg.decoder_seq_len,
                                   "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
                                   "frac": round(gbs / hbm_peak, 4), "traffic": None, "peak_source": peak_src,

@@ -86,6 +86,20 @@ typedef struct {
   /* optional (NULL disables the streaming decoder): fp32 [decoder_num_layers][P], P = round_up(13 D + FF, 256):
    * per layer b_qkv(3D) | b_out(D) | cross b_q(D) | cross b_out(D) | b1(FF) | b2(D) | norm1 g,b | norm2 g,b | norm3 g,b */
   const float* dec_small;
+  /* optional (NULL disables the cluster decoder): the decoder weights re-packed for the cluster kernel, one contiguous
+   * block per head r (= CTA rank in a cluster of num_heads CTAs), consumed front to back by TMA bulk copies.
+   * Requires num_heads in {2,4,8}, ff_dim % (32 num_heads) == 0; FFS = ff_dim / num_heads, VS = round_up(ceil(V /
+   * num_heads), 16).  Per head r: for each layer
+   *   small : fp32 b_qkv rows of head r (q|k|v: 192) | cross b_q rows of head r (64) | b1[r FFS..] (FFS) | b_out (D) |
+   *           cross b_out (D) | b2 (D) | norm1 g,b | norm2 g,b | norm3 g,b (6 D); zero padded to a multiple of 128 B
+   *   Wqkv rows of head r (192 x D) | Wout[:, 64 r..] (D x 64) | cross Wq rows of head r (64 x D) |
+   *   cross Wout[:, 64 r..] (D x 64) | W1[r FFS.., :] (FFS x D) | W2[:, r FFS..] (D x FFS)
+   * then the classifier rows [r VS, (r+1) VS) (zero padded past vocab).  Every matrix [R x K] is stored bf16 in
+   * mma.m16n8k16 A-fragment order [K/32 k-blocks][R/16 m-tiles][k-tile s 0..1][g 0..7][tg 0..3][8]: with r = 16 mt + g,
+   * c = 32 kb + 8 tg + 4 s the 8 elements are W[r][c..c+1], W[r+8][c..c+1], W[r][c+2..c+3], W[r+8][c+2..c+3].
+   * asr_decoder_image_bytes() gives the total size (0 = shape not compiled into the cluster kernel). */
+  const void* dec_image;
+  size_t dec_image_bytes;
 } AsrWeights;
 
 const char* asr_last_error(void);
@@ -120,7 +134,9 @@ int asr_decoder_forward(AsrHandle* h, const float* enc_out, int B, int Tp, const
  * (L+1 if none); step_logits fp32 (B,L,V) nullable: logits (no final LayerNorm, model.py:142) that chose
  * tokens[:,t+1].  stop_at_eos == 0 reproduces the reference (exactly L steps, tokens keep flowing after EOS);
  * stop_at_eos != 0 writes pad_token_id after the first EOS (and the persistent kernel leaves early once every
- * utterance has finished).  Launch mode is selected by the environment variable ASR_B200_DECODE: "persistent"
+ * utterance has finished).  Launch mode is selected by the environment variable ASR_B200_DECODE: "cluster"
+ * (default when AsrWeights.dec_image is set: one thread-block cluster of num_heads CTAs per group of utterances,
+ * head-parallel layers, all-reduces over distributed shared memory, everything streamed by TMA), "persistent"
  * (one cooperative kernel runs all L steps, grid barriers between phases), "stream" (one CTA per utterance, weights
  * and K/V streamed through a TMA ring, no barriers), "graph" (CUDA-graph replay of the per-kernel step) or "eager". */
 int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, int stop_at_eos,
@@ -128,14 +144,16 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
                       size_t ws_bytes, int32_t* tokens, int32_t* n_tokens, float* step_logits, asr_stream_t stream);
 
 /* Profiling aid for bench.py: the same decode launched eagerly with a CUDA-event pair around every kernel.
- * Synchronises `stream` before returning.  ms_per_class / launches_per_class: 11 entries in the order
+ * Synchronises `stream` before returning.  ms_per_class / launches_per_class: 12 entries in the order
  * {qkv linear, self attention, out projections, cross q linear, cross attention, ffn1, ffn2, classifier, select}
- * for the per-kernel step, entry 9 = the persistent cooperative kernel, entry 10 = the streaming kernel
- * (each: all L steps in one launch). */
+ * for the per-kernel step, entry 9 = the persistent cooperative kernel, entry 10 = the streaming kernel,
+ * entry 11 = the cluster kernel (each: all L steps in one launch).  phase_cycles: device [3][148][16] int64. */
 int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L, void* ws, size_t ws_bytes,
                        int32_t* tokens, float* ms_per_class, int32_t* launches_per_class,
-                       long long* phase_cycles /* device [#SMs][16], nullable: persistent-kernel phase clocks */,
+                       long long* phase_cycles /* nullable: per-CTA clock64 totals of the three one-launch decoders */,
                        asr_stream_t stream);
+/* Size of AsrWeights.dec_image for a configuration (0 = the cluster decoder does not support it). */
+size_t asr_decoder_image_bytes(const AsrConfig* cfg);
 /* Number of kernels this library has launched in the calling process (graph replays counted per kernel). */
 unsigned long long asr_launch_count(void);
 

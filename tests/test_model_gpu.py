@@ -49,7 +49,7 @@ def check_tokens(ref_tokens, ref_logits, got_tokens, min_frac=0.99):
     return r, frac
 
 
-@pytest.mark.parametrize("mode", ["persistent", "stream", "graph", "eager"])
+@pytest.mark.parametrize("mode", ["cluster", "persistent", "stream", "graph", "eager"])
 def test_greedy_tokens_T0(t0, mode, monkeypatch):
     """All three launch modes of asr_decode_greedy (ASR_B200_DECODE) against the reference's tokens and logits."""
     monkeypatch.setenv("ASR_B200_DECODE", mode)
@@ -138,6 +138,30 @@ def test_stream_matches_per_kernel_step_C2(monkeypatch):
     assert_close(ls[same], lg[same], 5e-3, 2e-4, "stream vs graph step logits")
     for b in same:
         assert int(nss[b]) == int(nsg[b]) and torch.equal(ss[b], sg[b])
+
+
+@pytest.mark.parametrize("batch,gu", [(5, ""), (64, ""), (70, ""), (9, "8")])
+def test_cluster_matches_per_kernel_step_C2(batch, gu, monkeypatch):
+    """The cluster kernel (head-parallel CTAs, DSMEM all-reduces) against the per-kernel (graph) step for utterance
+    groups of 1, 2, 4 and 8 per cluster, incl. stop_at_eos and a ragged last cluster."""
+    cfg = O.CONFIGS["C2"]
+    m = build_model(cfg, DEV)
+    L = 40
+    spec = O.structured_spectrum(batch, cfg.frames, cfg.input_dim, seed=23).to(DEV)
+    monkeypatch.setenv("ASR_B200_DECODE", "graph")
+    tg, ng, lg = m.greedy_decode(spec, max_len=L, return_logits=True)
+    sg, nsg = m.greedy_decode(spec, max_len=L, stop_at_eos=True)
+    monkeypatch.setenv("ASR_B200_DECODE", "cluster")
+    monkeypatch.setenv("ASR_B200_CLUSTER_GU", gu)
+    tc, nc, lc = m.greedy_decode(spec, max_len=L, return_logits=True)
+    sc, nsc = m.greedy_decode(spec, max_len=L, stop_at_eos=True)
+    torch.cuda.synchronize()
+    r = O.compare_tokens(tg, lg.cpu(), tc, TAU)
+    assert not r["hard"] and r["identical"] >= 0.9 * batch, r
+    same = [b for b in range(batch) if torch.equal(tg[b], tc[b])]
+    assert_close(lc[same], lg[same], 5e-3, 2e-4, "cluster vs graph step logits")
+    for b in same:
+        assert int(nsc[b]) == int(nsg[b]) and torch.equal(sc[b], sg[b])
 
 
 def test_empty_batch(t0):
