@@ -71,7 +71,7 @@ struct GreedyWs {
     const size_t vpad = (size_t(c.vocab_size) + 63) / 64 * 64;
     enc_bf16 = b.take<bf16>(M * D);
     ckv = b.take<bf16>(size_t(c.decoder_num_layers) * M * 2 * D);
-    cache = b.take<bf16>(size_t(c.decoder_num_layers) * B * L * 2 * D);
+    cache = b.take<bf16>(size_t(c.decoder_num_layers) * B * ((L + 15) / 16 * 16) * 2 * D);   // rows padded to 16-key tiles
     h = b.take<float>(size_t(B) * D);
     qkv = b.take<float>(size_t(B) * 3 * D);
     att = b.take<float>(size_t(B) * D);

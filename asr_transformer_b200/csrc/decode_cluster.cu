@@ -28,7 +28,7 @@
 namespace asr {
 namespace {
 
-constexpr int NCW = 8;                    // consumer warps
+constexpr int NCW = 8;                    // consumer warps (16 measured slower: per-warp fixed costs dominate, not divisible work)
 constexpr int NCT = NCW * 32;             // consumer threads
 constexpr int NTHREADS = NCT + 32;        // + producer warp
 constexpr int STAGE_BYTES = 32768;
@@ -108,23 +108,33 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint4& a, uint32_t
 template <int H_, int FFS_, int VS_, int GUP_>
 struct Shape {
   static constexpr int H = H_, CS = H_, D = 64 * H_, FFS = FFS_, VS = VS_, GUP = GUP_;
-  static constexpr int RPS = (STAGE_BYTES / 256) / GUP;   // key rows per utterance slot per ring stage
+  static constexpr int RPS = (STAGE_BYTES / 128) / GUP;   // key rows per utterance slot per ring stage (K or V rows)
   static constexpr int WPU = NCW / GUP;                   // attention warps per utterance slot
-  static constexpr int NGROUPS = 4 * WPU;                 // 8-lane key groups per utterance slot
+  static constexpr int SC = 2;                            // K stages per super-chunk (softmax granularity)
+  static constexpr int TPW = (RPS / 16) / WPU;            // 16-key tiles per warp per stage
   static constexpr int SMALL_FLOATS = 256 + FFS + 9 * D;
   static constexpr uint32_t SMALL_BYTES = (SMALL_FLOATS * 4 + 127) / 128 * 128;
   static constexpr int LDX = (D + 32) * 2, LDH = (FFS + 32) * 2, LDO = 96 * 2;   // activation row strides (bytes)
 };
-// One packed matrix: MT m-tiles of 16 rows, KB k-blocks of 32 columns; KBS k-blocks per ring stage; the units
-// (m-tile, k-group) are dealt to the 8 warps; KG > 1 only where MT alone does not divide by 8.
+// One packed matrix: MT m-tiles of 16 rows, KB k-blocks of 32 columns; KBS k-blocks per ring stage.  Work units
+// (m-tile mt, k-group kg of KBS / KG k-blocks) are dealt to the NCW warps: unit (mt, kg) -> warp (mt * KG + kg) % NCW.
+// KG (a power of two dividing KBS and NCW) is the smallest split that deals the units evenly (no guards in the loop).
+constexpr int pick_kg(int mt, int kbs) {
+  int kg = 1;
+  while ((mt % (NCW / kg)) != 0 && kg * 2 <= kbs && kg < NCW) kg *= 2;
+  return kg;
+}
 template <int MT_, int KB_>
 struct Mat {
   static constexpr int MT = MT_, KB = KB_;
   static constexpr int KBS = (32 / MT) < 1 ? 1 : ((32 / MT) > KB ? KB : (32 / MT));
-  static constexpr int KG = (MT % 8 == 0) ? 1 : (MT % 4 == 0) ? 2 : (MT % 2 == 0) ? 4 : 8;
-  static constexpr int UPW = MT * KG / 8, KPG = KBS / KG, NST = KB / KBS;
+  static constexpr int KG = pick_kg(MT, KBS);
+  static constexpr int MSTEP = NCW / KG;                               // m-tile stride between a warp's units
+  static constexpr int UPW = (MT + MSTEP - 1) / MSTEP, KPG = KBS / KG, NST = KB / KBS;
+  static constexpr bool EXACT = (MT % MSTEP) == 0;                     // every warp has exactly UPW units
   static constexpr uint32_t ST_BYTES = KBS * MT * 1024u;
-  static_assert(MT >= 1 && MT <= 32 && KBS % KG == 0 && KB % KBS == 0 && (MT * KG) % 8 == 0 && UPW <= 4, "tiling");
+  static_assert(MT >= 1 && MT <= 32 && KBS % KG == 0 && KB % KBS == 0 && NCW % KG == 0 && UPW <= 4 && MT * KG <= 32 &&
+                    EXACT, "tiling");
 };
 
 struct SmemMap {
@@ -148,7 +158,7 @@ __host__ __device__ inline SmemMap smem_map(int nstages) {
   m.hid_lo = take(S::GUP * S::LDH);
   m.o_hi = take(S::GUP * S::LDO);
   m.o_lo = take(S::GUP * S::LDO);
-  m.q = take(S::GUP * 64 * 4);
+  m.q = take(S::GUP * 64 * 4);                         // bf16 hi [GUP][64] | bf16 lo [GUP][64], fragment order
   m.kvrow = take(S::GUP * 128 * 2);
   m.scratch = take(32 * 32 * 16);                      // [KG * MT <= 32][32 lanes] float4 partial tiles
   m.prm = take(S::SMALL_BYTES);
@@ -207,10 +217,15 @@ struct Consumer {
   int slot = 0;
   uint32_t round = 0;
   long long waited = 0;
+  bool timed = false;
   __device__ __forceinline__ const uint8_t* acquire() {
-    const long long w0 = clock64();
-    mbar_wait(&r.full[slot], round & 1u);
-    waited += clock64() - w0;
+    if (timed) {
+      const long long w0 = clock64();
+      mbar_wait(&r.full[slot], round & 1u);
+      waited += clock64() - w0;
+    } else {
+      mbar_wait(&r.full[slot], round & 1u);
+    }
     return r.buf + size_t(slot) * STAGE_BYTES;
   }
   __device__ __forceinline__ void release() {       // every consumer warp calls this once per stage
@@ -236,8 +251,9 @@ struct Consumer {
 template <class M, int GUP, class Epi>
 __device__ __forceinline__ void mm_stream(Consumer& c, const uint8_t* xhi, const uint8_t* xlo, int ldx, float4* scratch,
                                           Epi&& epi) {
+  constexpr bool COLS = 2 * GUP <= 8;   // hi and lo parts of x ride in different N columns of ONE mma (u | GUP + u)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
-  const int kg = warp % M::KG, mt0 = warp / M::KG;          // unit j of this warp: m-tile mt0 + j * (8 / KG)
+  const int kg = warp % M::KG, mt0 = warp / M::KG;          // unit j of this warp: m-tile mt0 + j * MSTEP
   float acc[M::UPW][2][4];
 #pragma unroll
   for (int j = 0; j < M::UPW; ++j)
@@ -245,46 +261,65 @@ __device__ __forceinline__ void mm_stream(Consumer& c, const uint8_t* xhi, const
     for (int s = 0; s < 2; ++s)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[j][s][i] = 0.f;
-  const bool xrow = g < GUP;
-  const uint8_t* xh = xhi + g * ldx + tg * 16 + kg * M::KPG * 64;
+  const bool xrow = g < (COLS ? 2 * GUP : GUP);
+  const uint8_t* xh = ((COLS && g >= GUP) ? xlo + (g - GUP) * ldx : xhi + g * ldx) + tg * 16 + kg * M::KPG * 64;
   const uint8_t* xl = xlo + g * ldx + tg * 16 + kg * M::KPG * 64;
 #pragma unroll 1
   for (int st_i = 0; st_i < M::NST; ++st_i) {
     const uint8_t* st = c.acquire() + lane * 16 + (size_t(kg) * M::KPG * M::MT + mt0) * 1024;
+    uint4 af[M::KPG][M::UPW][2], bh[M::KPG], bl[M::KPG];
 #pragma unroll
-    for (int q = 0; q < M::KPG; ++q) {
-      uint4 bh = make_uint4(0, 0, 0, 0), bl = make_uint4(0, 0, 0, 0);
+    for (int q = 0; q < M::KPG; ++q) {               // every load of the stage is in flight before the first MMA
+      bh[q] = make_uint4(0, 0, 0, 0);
+      bl[q] = make_uint4(0, 0, 0, 0);
       if (xrow) {
-        bh = lds128(xh + (st_i * M::KBS + q) * 64);
-        bl = lds128(xl + (st_i * M::KBS + q) * 64);
+        bh[q] = lds128(xh + (st_i * M::KBS + q) * 64);
+        if (!COLS) bl[q] = lds128(xl + (st_i * M::KBS + q) * 64);
       }
 #pragma unroll
       for (int j = 0; j < M::UPW; ++j) {
-        const uint8_t* a = st + (size_t(q) * M::MT + j * (8 / M::KG)) * 1024;
-        const uint4 a0 = lds128(a), a1 = lds128(a + 512);
-        mma16816(acc[j][0], a0, bh.x, bh.y);
-        mma16816(acc[j][1], a1, bh.z, bh.w);
-        mma16816(acc[j][0], a0, bl.x, bl.y);
-        mma16816(acc[j][1], a1, bl.z, bl.w);
+        const uint8_t* a = st + (size_t(q) * M::MT + j * M::MSTEP) * 1024;
+        af[q][j][0] = lds128(a);
+        af[q][j][1] = lds128(a + 512);
       }
     }
+#pragma unroll
+    for (int q = 0; q < M::KPG; ++q)
+#pragma unroll
+      for (int j = 0; j < M::UPW; ++j) {
+        mma16816(acc[j][0], af[q][j][0], bh[q].x, bh[q].y);
+        mma16816(acc[j][1], af[q][j][1], bh[q].z, bh[q].w);
+        if (!COLS) {
+          mma16816(acc[j][0], af[q][j][0], bl[q].x, bl[q].y);
+          mma16816(acc[j][1], af[q][j][1], bl[q].z, bl[q].w);
+        }
+      }
     c.release();
+  }
+  float4 v[M::UPW];
+#pragma unroll
+  for (int j = 0; j < M::UPW; ++j) {
+    v[j] = make_float4(acc[j][0][0] + acc[j][1][0], acc[j][0][1] + acc[j][1][1], acc[j][0][2] + acc[j][1][2],
+                       acc[j][0][3] + acc[j][1][3]);
+    if (COLS) {   // column u (hi) + column GUP + u (lo): lanes tg and tg ^ (GUP / 2)
+      v[j].x += __shfl_xor_sync(0xffffffffu, v[j].x, GUP / 2);
+      v[j].y += __shfl_xor_sync(0xffffffffu, v[j].y, GUP / 2);
+      v[j].z += __shfl_xor_sync(0xffffffffu, v[j].z, GUP / 2);
+      v[j].w += __shfl_xor_sync(0xffffffffu, v[j].w, GUP / 2);
+    }
   }
   if (M::KG == 1) {
 #pragma unroll
     for (int j = 0; j < M::UPW; ++j) {
-      const int n0 = 16 * (mt0 + j * 8) + g;
+      const int n0 = 16 * (mt0 + j * M::MSTEP) + g;
       if (2 * tg < GUP) {
-        epi(n0, 2 * tg, acc[j][0][0] + acc[j][1][0], acc[j][0][1] + acc[j][1][1]);
-        epi(n0 + 8, 2 * tg, acc[j][0][2] + acc[j][1][2], acc[j][0][3] + acc[j][1][3]);
+        epi(n0, 2 * tg, v[j].x, v[j].y);
+        epi(n0 + 8, 2 * tg, v[j].z, v[j].w);
       }
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < M::UPW; ++j)
-      scratch[(kg * M::MT + mt0 + j * (8 / M::KG)) * 32 + lane] =
-          make_float4(acc[j][0][0] + acc[j][1][0], acc[j][0][1] + acc[j][1][1], acc[j][0][2] + acc[j][1][2],
-                      acc[j][0][3] + acc[j][1][3]);
+    for (int j = 0; j < M::UPW; ++j) scratch[(kg * M::MT + mt0 + j * M::MSTEP) * 32 + lane] = v[j];
     consumer_sync();
     for (int it = threadIdx.x; it < M::MT * 32; it += NCT) {
       const int ln = it & 31, g2 = ln >> 2, tg2 = ln & 3;
@@ -292,8 +327,8 @@ __device__ __forceinline__ void mm_stream(Consumer& c, const uint8_t* xhi, const
         float4 s = scratch[it];
 #pragma unroll
         for (int k = 1; k < M::KG; ++k) {
-          const float4 v = scratch[k * M::MT * 32 + it];
-          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+          const float4 w = scratch[k * M::MT * 32 + it];
+          s.x += w.x; s.y += w.y; s.z += w.z; s.w += w.w;
         }
         const int n0 = 16 * (it >> 5) + g2;
         epi(n0, 2 * tg2, s.x, s.y);
@@ -338,114 +373,269 @@ __device__ __forceinline__ void rows_to_hilo(const float* h, int GU, const float
   }
 }
 
+// LayerNorm of the rows u < GU by ALL consumer warps: warp (part, u) owns D / WPU elements of row u; one pass over
+// x - x[0] (shifted sums: no cancellation), partial (sum, sum of squares) per warp combined through shared memory.
+template <class S>
+__device__ __forceinline__ void ln_rows(const float* h, int GU, const float* gam, const float* bet, bf16* hi, bf16* lo,
+                                        float* red /* [NCW][2] */) {
+  constexpr int D = S::D, WPU = S::WPU, EPL = D / (32 * WPU);
+  static_assert(D % (32 * WPU) == 0, "LayerNorm split");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int u = warp % S::GUP, part = warp / S::GUP;
+  const float* src = h + u * D;
+  const int k0 = part * (D / WPU) + lane;
+  const float c0 = src[0];
+  float x[EPL], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < EPL; ++i) {
+    x[i] = src[k0 + 32 * i] - c0;
+    s1 += x[i];
+    s2 = fmaf(x[i], x[i], s2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) *reinterpret_cast<float2*>(red + 2 * warp) = make_float2(s1, s2);
+  consumer_sync();
+  float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+  for (int pI = 0; pI < WPU; ++pI) {
+    const float2 r = *reinterpret_cast<const float2*>(red + 2 * (pI * S::GUP + u));
+    t1 += r.x;
+    t2 += r.y;
+  }
+  const float mean = t1 * (1.0f / float(D));
+  const float rstd = 1.0f / sqrtf(fmaxf(t2 * (1.0f / float(D)) - mean * mean, 0.f) + 1e-5f);
+  if (u < GU) {
+#pragma unroll
+    for (int i = 0; i < EPL; ++i) {
+      const int k = k0 + 32 * i;
+      const float y = (x[i] - mean) * rstd * gam[k] + bet[k];
+      const bf16 hh = __float2bfloat16(y);
+      hi[u * (D + 32) + k] = hh;
+      lo[u * (D + 32) + k] = __float2bfloat16(y - __bfloat162float(hh));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ attention
-// single-query attention of ONE head, flash style: one running (max, sum, acc[8]) per 8-lane key group, log2 units
-struct Attn {
-  float qv[8];
+// Single-query attention of ONE head on the tensor cores, 16 keys per tile, flash style (log2 units).
+//   S = K q : mma.m16n8k16 with A = the K tile [16 keys x 16 dims] (ldmatrix from the 128-byte-swizzled rows TMA
+//             wrote), B = q with column 0 = bf16 hi part, column 1 = lo part -> score(key) = c(col 0) + c(col 1), exact
+//             to fp32 products; the scores of keys g / g+8 live in lanes (g, tg = 0).
+//   o += V^T p: A = V^T [16 dims x 16 keys] (ldmatrix.trans of the same row-major rows), B = p with columns hi | lo.
+// Running max m is warp-uniform; the running sum l is kept per lane and reduced once at the end.
+struct AttnT {
   float m, l;
-  float o[8];
+  float o[4][4];
 };
-__device__ __forceinline__ void attn_begin(Attn& st, const float* q /* 64 floats, pre-scaled by scale*log2e */) {
-  const int c8 = threadIdx.x & 7;
-  const float4 a = *reinterpret_cast<const float4*>(q + c8 * 8);
-  const float4 b = *reinterpret_cast<const float4*>(q + c8 * 8 + 4);
-  st.qv[0] = a.x; st.qv[1] = a.y; st.qv[2] = a.z; st.qv[3] = a.w;
-  st.qv[4] = b.x; st.qv[5] = b.y; st.qv[6] = b.z; st.qv[7] = b.w;
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint4& r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint4& r) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+}
+__device__ __forceinline__ void attn_init(AttnT& st) {
   st.m = -INFINITY;
   st.l = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) st.o[i] = 0.f;
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st.o[i][j] = 0.f;
 }
-template <int NB>
-__device__ __forceinline__ void attn_fold(Attn& st, const uint4 (&kr)[NB], const uint4 (&vr)[NB], const bool (&valid)[NB],
-                                          unsigned gmask) {
-  float sc[NB];
-  float bm = -INFINITY;
+// q of one utterance is kept as bf16 hi and lo parts in B-fragment order: element d (k-tile kt = d / 16, r = d % 16)
+// lives at index ((tg * 4 + kt) * 4 + slot), tg = (r % 8) / 2, slot = (r / 8) * 2 + (r % 2), so that lane (g, tg) reads
+// its four k-tile fragments {b0, b1} with two LDS.128 (g = 0: hi part = MMA column 0, g = 1: lo part = column 1).
+__device__ __forceinline__ int q_frag_index(int d) {
+  const int kt = d >> 4, r = d & 15;
+  return (((r & 7) >> 1) * 4 + kt) * 4 + (r >> 3) * 2 + (r & 1);
+}
+__device__ __forceinline__ void q_store(bf16* q_hi, bf16* q_lo, int u, int d, float y) {
+  const bf16 h = __float2bfloat16(y);
+  const int i = u * 64 + q_frag_index(d);
+  q_hi[i] = h;
+  q_lo[i] = __float2bfloat16(y - __bfloat162float(h));
+}
+__device__ __forceinline__ void attn_q_frags(const bf16* q_hi, const bf16* q_lo, int u, uint32_t (&qf)[8]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+  if (g < 2) {
+    const bf16* src = (g == 0 ? q_hi : q_lo) + u * 64 + tg * 16;
+    a = lds128(src);
+    b = lds128(src + 8);
+  }
+  qf[0] = a.x; qf[1] = a.y; qf[2] = a.z; qf[3] = a.w;
+  qf[4] = b.x; qf[5] = b.y; qf[6] = b.z; qf[7] = b.w;
+}
+// Tiles of up to 16 keys.  kbase / vbase = shared address of the tile's first K / V row (rows of 128 B, 16-byte
+// chunk c of row r stored at chunk c ^ (r & 7): TMA SWIZZLE_128B; tiles start on multiples of 8 rows).
+// SINGLE: the tile is ONE row (the current step's k_t / v_t) replicated to all 16 key positions, keys >= 1 masked.
+template <bool SINGLE>
+__device__ __forceinline__ void qk_tile(uint32_t kbase, int n_valid, const uint32_t (&qf)[8], float& sa, float& sb) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3, mat = lane >> 3, r = lane & 7;
+  float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const int key = SINGLE ? 0 : (mat & 1) * 8 + r;
+  const uint32_t row = kbase + key * 128;
+  uint4 a[4];
 #pragma unroll
-  for (int u = 0; u < NB; ++u) {
-    float sv = 0.f;
-    if (valid[u]) {
-      const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kr[u]);
+  for (int kt = 0; kt < 4; ++kt) ldsm_x4(row + ((((2 * kt + (mat >> 1)) ^ key) & 7) << 4), a[kt]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __bfloat1622float2(k2[i]);
-        sv = fmaf(st.qv[2 * i], f.x, sv);
-        sv = fmaf(st.qv[2 * i + 1], f.y, sv);
+  for (int kt = 0; kt < 4; ++kt) mma16816(sc[kt & 1], a[kt], qf[2 * kt], qf[2 * kt + 1]);
+  sa = (tg == 0 && g < n_valid) ? (sc[0][0] + sc[1][0]) + (sc[0][1] + sc[1][1]) : -INFINITY;        // key g (lanes tg == 0)
+  sb = (tg == 0 && g + 8 < n_valid) ? (sc[0][2] + sc[1][2]) + (sc[0][3] + sc[1][3]) : -INFINITY;    // key g + 8
+}
+// B fragment of the probabilities: lane (g, tg) holds keys 2tg, 2tg+1 (b0) and 2tg+8, 2tg+9 (b1) of column g
+// (0 = bf16 hi part, 1 = lo part)
+__device__ __forceinline__ void p_frags(float pa, float pb, uint32_t& b0, uint32_t& b1) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const float p0 = __shfl_sync(0xffffffffu, pa, 8 * tg), p1 = __shfl_sync(0xffffffffu, pa, 8 * tg + 4);
+  const float p2 = __shfl_sync(0xffffffffu, pb, 8 * tg), p3 = __shfl_sync(0xffffffffu, pb, 8 * tg + 4);
+  const __nv_bfloat162 h01 = __floats2bfloat162_rn(p0, p1), h23 = __floats2bfloat162_rn(p2, p3);
+  b0 = 0;
+  b1 = 0;
+  if (g == 0) {
+    b0 = *reinterpret_cast<const uint32_t*>(&h01);
+    b1 = *reinterpret_cast<const uint32_t*>(&h23);
+  } else if (g == 1) {
+    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+    b0 = pack_bf16x2(p0 - f01.x, p1 - f01.y);
+    b1 = pack_bf16x2(p2 - f23.x, p3 - f23.y);
+  }
+}
+template <bool SINGLE>
+__device__ __forceinline__ void pv_tile(AttnT& st, uint32_t vbase, uint32_t b0, uint32_t b1) {
+  const int lane = threadIdx.x & 31, mat = lane >> 3, r = lane & 7;
+  const int key = SINGLE ? 0 : (mat >> 1) * 8 + r;
+  const uint32_t row = vbase + key * 128;
+  uint4 a[4];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) ldsm_x4_trans(row + ((((2 * mt + (mat & 1)) ^ key) & 7) << 4), a[mt]);
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) mma16816(st.o[mt], a[mt], b0, b1);
+}
+// Attention of this warp's utterance slot `au` over n_keys rows streamed through the ring as super-chunks of up to SC
+// K stages followed by the matching V stages ([utterance slot][RPS rows][128 B] each); warp partition `apart` owns
+// tiles 2 apart, 2 apart + 1 of every stage.  All scores of a super-chunk are computed first (independent MMAs), then
+// ONE max / exp / sum, then all P V products: one softmax dependency chain per super-chunk instead of one per tile.
+// cur_kb != 0: additionally the single current row (k_t at cur_kb, v_t at cur_kb + 128), merged into the first chunk.
+template <class S, class Mk>
+__device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t (&qf)[8], int n_keys, bool active,
+                                          int au, int apart, uint32_t cur_kb, Mk&& mk) {
+  constexpr int RPS = S::RPS, SC = S::SC, TPW = S::TPW;
+  float ca = -INFINITY, cb = -INFINITY;
+  bool cur = cur_kb != 0;
+  if (cur) qk_tile<true>(cur_kb, 1, qf, ca, cb);
+  const uint32_t slot_off = au * RPS * 128 + apart * (TPW * 2048);
+#pragma unroll 1
+  for (int c0 = 0; c0 < n_keys; c0 += SC * RPS) {
+    const int nk = min(SC * RPS, n_keys - c0);
+    const int ns = (nk + RPS - 1) / RPS;
+    float sa[SC][TPW], sb[SC][TPW];
+    float mx = fmaxf(ca, cb);
+#pragma unroll
+    for (int s = 0; s < SC; ++s) {
+#pragma unroll
+      for (int j = 0; j < TPW; ++j) sa[s][j] = sb[s][j] = -INFINITY;
+      if (s < ns) {
+        const uint32_t stg = smem_u32(c.acquire()) + slot_off;
+        const int n = min(RPS, nk - s * RPS) - 16 * TPW * apart;   // rows of this stage at / after this warp's first tile
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < TPW; ++j)
+            if (n > 16 * j) {
+              qk_tile<false>(stg + j * 2048, min(16, n - 16 * j), qf, sa[s][j], sb[s][j]);
+              mx = fmaxf(mx, fmaxf(sa[s][j], sb[s][j]));
+            }
+        }
+        c.release();
       }
     }
-    sv += __shfl_xor_sync(gmask, sv, 1);
-    sv += __shfl_xor_sync(gmask, sv, 2);
-    sv += __shfl_xor_sync(gmask, sv, 4);
-    sc[u] = valid[u] ? sv : -INFINITY;
-    bm = fmaxf(bm, sc[u]);
-  }
-  if (bm == -INFINITY) return;
-  const float m_new = fmaxf(st.m, bm);
-  const float alpha = exp2f(st.m - m_new);
-  st.l *= alpha;
+    mk(0);
+    const float m_new = fmaxf(st.m, warp_max(mx));
+    uint32_t pb0[SC][TPW], pb1[SC][TPW], cb0 = 0, cb1 = 0;
+    if (m_new != -INFINITY) {                                    // warp-uniform; false only for a warp without keys
+      const float alpha = exp2f(st.m - m_new);
+      float lsum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) st.o[i] *= alpha;
+      for (int s = 0; s < SC; ++s)
 #pragma unroll
-  for (int u = 0; u < NB; ++u) {
-    if (valid[u]) {
-      const float pw = exp2f(sc[u] - m_new);
-      st.l += pw;
-      const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vr[u]);
+        for (int j = 0; j < TPW; ++j) {
+          const float pa = exp2f(sa[s][j] - m_new), pb = exp2f(sb[s][j] - m_new);
+          lsum += pa + pb;
+          p_frags(pa, pb, pb0[s][j], pb1[s][j]);
+        }
+      if (cur) {
+        const float pa = exp2f(ca - m_new);
+        lsum += pa;
+        p_frags(pa, 0.f, cb0, cb1);
+      }
+      st.l = st.l * alpha + lsum;
+      st.m = m_new;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __bfloat1622float2(v2[i]);
-        st.o[2 * i] = fmaf(pw, f.x, st.o[2 * i]);
-        st.o[2 * i + 1] = fmaf(pw, f.y, st.o[2 * i + 1]);
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st.o[i][j] *= alpha;
+    } else {
+#pragma unroll
+      for (int s = 0; s < SC; ++s)
+#pragma unroll
+        for (int j = 0; j < TPW; ++j) pb0[s][j] = pb1[s][j] = 0;
+    }
+    mk(1);
+#pragma unroll
+    for (int s = 0; s < SC; ++s) {
+      if (s < ns) {
+        const uint32_t stg = smem_u32(c.acquire()) + slot_off;
+        const int n = min(RPS, nk - s * RPS) - 16 * TPW * apart;
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < TPW; ++j)
+            if (n > 16 * j) pv_tile<false>(st, stg + j * 2048, pb0[s][j], pb1[s][j]);
+        }
+        c.release();
       }
     }
+    if (cur) {
+      if (m_new != -INFINITY) pv_tile<true>(st, cur_kb + 128, cb0, cb1);
+      cur = false;
+      ca = -INFINITY;
+    }
+    mk(2);
   }
-  st.m = m_new;
+  if (cur) {   // no cached keys at all (first step): the current row alone
+    const float m_new = fmaxf(st.m, warp_max(ca));
+    const float alpha = exp2f(st.m - m_new);
+    const float pa = exp2f(ca - m_new);
+    uint32_t b0, b1;
+    p_frags(pa, 0.f, b0, b1);
+    st.l = st.l * alpha + pa;
+    st.m = m_new;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) st.o[i][j] *= alpha;
+    pv_tile<true>(st, cur_kb + 128, b0, b1);
+  }
 }
-// one ring stage: per utterance slot [K: RPS rows x 128 B][V: RPS rows x 128 B]; this warp's slot holds n_rows keys.
-// Group grp takes rows grp + j * NGROUPS, j = 0..3 (RPS == 4 * NGROUPS).
+// merge the key partitions of every utterance slot and emit o (bf16 hi + lo rows, stride 96 elements)
 template <class S>
-__device__ __forceinline__ void attn_stage(Attn& st, const uint8_t* slot, int n_rows, int grp, bool active) {
-  const int lane = threadIdx.x & 31, c8 = lane & 7;
-  const unsigned gmask = 0xFFu << (lane & 24);
-  const uint8_t* kb = slot + c8 * 16 + grp * 128;
-  uint4 kr[4], vr[4];
-  bool valid[4];
+__device__ __forceinline__ void attn_finish(AttnT& st, int GU, float* part_buf, float* stat, bf16* o_hi, bf16* o_lo) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const float l = warp_sum(st.l);
+  if (tg == 0) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    valid[j] = active && (grp + j * S::NGROUPS) < n_rows;
-    if (valid[j]) {
-      kr[j] = lds128(kb + j * S::NGROUPS * 128);
-      vr[j] = lds128(kb + j * S::NGROUPS * 128 + S::RPS * 128);
+    for (int mt = 0; mt < 4; ++mt) {
+      part_buf[warp * 64 + 16 * mt + g] = st.o[mt][0] + st.o[mt][1];
+      part_buf[warp * 64 + 16 * mt + g + 8] = st.o[mt][2] + st.o[mt][3];
     }
   }
-  attn_fold<4>(st, kr, vr, valid, gmask);
-}
-// merge the key groups of the cluster's utterance slots and emit o (bf16 hi + lo rows, stride 96 elements)
-template <class S>
-__device__ __forceinline__ void attn_finish(Attn& st, int GU, float* part_buf, float* stat, bf16* o_hi, bf16* o_lo) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c8 = lane & 7, sub = lane >> 3;
-#pragma unroll
-  for (int off = 8; off <= 16; off <<= 1) {
-    const float mo = __shfl_xor_sync(0xffffffffu, st.m, off);
-    const float lo = __shfl_xor_sync(0xffffffffu, st.l, off);
-    const float mn = fmaxf(st.m, mo);
-    const float fa = (st.m == -INFINITY) ? 0.f : exp2f(st.m - mn);
-    const float fb = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
-    st.l = st.l * fa + lo * fb;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float oo = __shfl_xor_sync(0xffffffffu, st.o[i], off);
-      st.o[i] = st.o[i] * fa + oo * fb;
-    }
-    st.m = mn;
-  }
-  if (sub == 0) {
-    *reinterpret_cast<float4*>(part_buf + warp * 64 + c8 * 8) = make_float4(st.o[0], st.o[1], st.o[2], st.o[3]);
-    *reinterpret_cast<float4*>(part_buf + warp * 64 + c8 * 8 + 4) = make_float4(st.o[4], st.o[5], st.o[6], st.o[7]);
-    if (c8 == 0) {
-      stat[warp] = st.m;
-      stat[NCW + warp] = st.l;
-    }
+  if (lane == 0) {
+    stat[warp] = st.m;
+    stat[NCW + warp] = l;
   }
   consumer_sync();
   for (int d = threadIdx.x; d < GU * 64; d += NCT) {
@@ -493,7 +683,8 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
   bf16* hid_lo = reinterpret_cast<bf16*>(smem + sm.hid_lo);
   bf16* o_hi = reinterpret_cast<bf16*>(smem + sm.o_hi);
   bf16* o_lo = reinterpret_cast<bf16*>(smem + sm.o_lo);
-  float* s_q = reinterpret_cast<float*>(smem + sm.q);
+  bf16* q_hi = reinterpret_cast<bf16*>(smem + sm.q);
+  bf16* q_lo = q_hi + GUP * 64;
   bf16* kv_row = reinterpret_cast<bf16*>(smem + sm.kvrow);
   float4* scratch = reinterpret_cast<float4*>(smem + sm.scratch);
   float* prm = reinterpret_cast<float*>(smem + sm.prm);
@@ -517,7 +708,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
   const int warp = threadIdx.x >> 5, tid = threadIdx.x;
 
   if (tid == 0) {
-    if (smem_u32(smem) & 127u) __trap();         // TMA destinations need 128-byte alignment
+    if (smem_u32(smem) & 1023u) __trap();        // swizzled TMA destinations need 1024-byte alignment
     for (int s = 0; s < p.nstages; ++s) {
       mbar_init(&ring.full[s], 1);
       mbar_init(&ring.empty[s], NCW);
@@ -533,7 +724,8 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
   __syncthreads();
   cluster_sync_all();   // peers' barriers are initialised before any remote store can arrive
 
-  const size_t cache_head = size_t(2) * p.L * 64;                 // elements per (layer, utterance, head): K rows | V rows
+  const int Lc = (p.L + 15) & ~15;                                // cache rows per (layer, utterance, head, K|V)
+  const size_t cache_head = size_t(2) * Lc * 64;                  // elements per (layer, utterance, head): K rows | V rows
   const uint8_t* my_image = p.image + size_t(rank) * p.rank_bytes;
 
   if (warp == NCW) {
@@ -564,27 +756,33 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
             while (ctrl[2] < need) {
             }
             asm volatile("fence.proxy.async;" ::: "memory");
-            for (int c0 = 0; c0 < t; c0 += RPS) {
-              const int n = min(RPS, t - c0);
-              uint8_t* dst = pr.begin(uint32_t(GU) * 2u * n * 128u);
-              for (int u = 0; u < GU; ++u) {
-                const bf16* kp = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(c0) * 64;
-                bulk_load(dst + u * RPS * 256, kp, n * 128, pr.bar(), pol_kv);
-                bulk_load(dst + u * RPS * 256 + RPS * 128, kp + size_t(p.L) * 64, n * 128, pr.bar(), pol_kv);
-              }
-              pr.end();
+            for (int c0 = 0; c0 < t; c0 += S::SC * RPS) {
+              const int nk = min(S::SC * RPS, t - c0);
+              for (int kv = 0; kv < 2; ++kv)               // K stages of the super-chunk, then its V stages
+                for (int r0 = 0; r0 < nk; r0 += RPS) {
+                  const int n = (min(RPS, nk - r0) + 15) & ~15;   // whole 16-key tiles (rows past t are zero)
+                  uint8_t* dst = pr.begin(uint32_t(GU) * n * 128u);
+                  for (int u = 0; u < GU; ++u) {
+                    const bf16* src = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head +
+                                      size_t(kv) * Lc * 64 + size_t(c0 + r0) * 64;
+                    bulk_load(dst + u * RPS * 128, src, n * 128, pr.bar(), pol_kv);
+                  }
+                  pr.end();
+                }
             }
           }
           pr.mat<MWo>(img + p.off_wo, pol_w);
           pr.mat<MWqc>(img + p.off_wqc, pol_w);
-          for (int c0 = 0; c0 < p.Tp; c0 += RPS) {   // encoder K/V of this head: 2-D boxes [RPS rows][64 columns]
-            uint8_t* dst = pr.begin(uint32_t(GU) * 2u * RPS * 128u);
-            for (int u = 0; u < GU; ++u) {
-              const int row = (l * p.B + ubase + u) * p.Tp + c0;
-              tma_load_2d_hint(dst + u * RPS * 256, &ckv_map, pr.bar(), rank * 64, row, pol_kv);
-              tma_load_2d_hint(dst + u * RPS * 256 + RPS * 128, &ckv_map, pr.bar(), D + rank * 64, row, pol_kv);
-            }
-            pr.end();
+          for (int c0 = 0; c0 < p.Tp; c0 += S::SC * RPS) {   // encoder K/V of this head: 2-D boxes [RPS rows][64 columns]
+            const int nk = min(S::SC * RPS, p.Tp - c0);
+            for (int kv = 0; kv < 2; ++kv)
+              for (int r0 = 0; r0 < nk; r0 += RPS) {
+                uint8_t* dst = pr.begin(uint32_t(GU) * RPS * 128u);
+                for (int u = 0; u < GU; ++u)
+                  tma_load_2d_hint(dst + u * RPS * 128, &ckv_map, pr.bar(), kv * D + rank * 64,
+                                   (l * p.B + ubase + u) * p.Tp + c0 + r0, pol_kv);
+                pr.end();
+              }
           }
           pr.mat<MWo>(img + p.off_woc, pol_w);
           pr.mat<MW1>(img + p.off_w1, pol_w);
@@ -602,11 +800,13 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
     // ================================= consumers
     Consumer c;
     c.r = ring;
+    const bool timed = p.timing != nullptr;
+    c.timed = timed;
     const long long t_begin = clock64();
     long long t_xchg = 0;
     uint32_t n_xchg = 0, n_arg = 0;
-    const int lane = tid & 31, sub = lane >> 3;
-    const int au = warp % GUP, agrp = (warp / GUP) * 4 + sub;       // attention: utterance slot / key group
+    const int lane = tid & 31;
+    const int au = warp % GUP, apart = warp / GUP;                  // attention: utterance slot / 16-key tile of a stage
     const bool a_active = au < GU;
     const float qscale = p.scale * LOG2E;
     const uint8_t* xh = reinterpret_cast<const uint8_t*>(xn_hi);
@@ -649,6 +849,15 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
       ++n_xchg;
     };
 
+    long long ph[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // per-phase clock totals (thread 0; written if p.timing)
+    long long ph_t = clock64();
+    auto mark = [&](int i) {
+      if (timed) {
+        const long long now = clock64();
+        ph[i] += now - ph_t;
+        ph_t = now;
+      }
+    };
     int t = 0;
 #pragma unroll 1
     for (; t < p.L; ++t) {
@@ -670,78 +879,79 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
         const float* b_2 = b_oc + D;
         const float* ln = b_2 + D;                // ln1 g,b | ln2 g,b | ln3 g,b
 
+        mark(0);
         // ---- LN1 -> q, k, v of this head (model.py:67-68, layers.py:16-18)
-        rows_to_hilo<D>(s_h, GU, ln, ln + D, xn_hi, xn_lo, D + 32);
+        ln_rows<S>(s_h, GU, ln, ln + D, xn_hi, xn_lo, stat);
         consumer_sync();
+        mark(1);
         mm_stream<MQkv, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
           const float y0 = v0 + b_qkv[n], y1 = v1 + b_qkv[n];
           if (n < 64) {
-            s_q[u0 * 64 + n] = y0 * qscale;
-            s_q[(u0 + 1) * 64 + n] = y1 * qscale;
+            q_store(q_hi, q_lo, u0, n, y0 * qscale);
+            q_store(q_hi, q_lo, u0 + 1, n, y1 * qscale);
           } else {
             kv_row[u0 * 128 + (n - 64)] = __float2bfloat16(y0);
             kv_row[(u0 + 1) * 128 + (n - 64)] = __float2bfloat16(y1);
           }
         });
         consumer_sync();
-        // append k_t, v_t (bf16) to the device-resident cache: [layer][utterance][head][K rows | V rows][64]
+        mark(2);
+        // append k_t, v_t (bf16) to the device-resident cache: [layer][utterance][head][K rows | V rows][Lc][64], the
+        // 16-byte chunks of row t stored swizzled (chunk ^ (t & 7)) so that the bulk copy lands ldmatrix-ready.  The
+        // first row of every 16-row block also zeroes the block's other rows: whole 16-key tiles are always finite.
         if (tid < GU * 16) {
           const int u = tid >> 4, ch = tid & 15, kv = ch >> 3, c16 = ch & 7;
-          bf16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * p.L * 64 +
-                      size_t(t) * 64 + c16 * 8;
+          bf16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * Lc * 64 +
+                      size_t(t) * 64 + ((c16 ^ (t & 7)) << 3);
           *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(kv_row + u * 128 + kv * 64 + c16 * 8);
-          asm volatile("fence.proxy.async;" ::: "memory");   // later read back by the producer's bulk copies
         }
-        // ---- causal self attention over keys 0..t (the current row comes from shared memory)
-        Attn st;
-        attn_begin(st, s_q + au * 64);
-        {
-          uint4 kr[1], vr[1];
-          bool valid[1];
-          valid[0] = a_active && agrp == 0;
-          if (valid[0]) {
-            kr[0] = lds128(kv_row + au * 128 + (lane & 7) * 8);
-            vr[0] = lds128(kv_row + au * 128 + 64 + (lane & 7) * 8);
+        if ((t & 15) == 0)
+          for (int i = tid; i < GU * 2 * 15 * 8; i += NCT) {
+            const int u = i / 240, rem = i - u * 240, kv = rem / 120, w = rem - kv * 120;   // w: 16-byte word in 15 rows
+            bf16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * Lc * 64 +
+                        size_t(t + 1) * 64 + w * 8;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
           }
-          attn_fold<1>(st, kr, vr, valid, 0xFFu << (lane & 24));
-        }
-#pragma unroll 1
-        for (int c0 = 0; c0 < t; c0 += RPS) {
-          const uint8_t* stg = c.acquire();
-          attn_stage<S>(st, stg + au * RPS * 256, min(RPS, t - c0), agrp, a_active);
-          c.release();
-        }
+        // ---- causal self attention over keys 0..t: cached rows from the ring, the current row from shared memory
+        AttnT st;
+        uint32_t qf[8];
+        attn_init(st);
+        attn_q_frags(q_hi, q_lo, au, qf);
+        attention<S>(c, st, qf, t, a_active, au, apart,
+                     (a_active && apart == S::WPU - 1) ? smem_u32(kv_row) + au * 256 : 0u, [](int) {});
+        asm volatile("fence.proxy.async;" ::: "memory");     // this step's cache rows: later read by the producer's TMA
         attn_finish<S>(st, GU, part_buf, stat, o_hi, o_lo);   // (two consumer barriers inside)
         if (tid == 0) {                                       // cache row t of this layer is published
           __threadfence_block();
           ctrl[2] = t * p.nd + l + 1;
         }
+        mark(3);
         mm_stream<MWo, GUP>(c, reinterpret_cast<const uint8_t*>(o_hi), reinterpret_cast<const uint8_t*>(o_lo), S::LDO,
                             scratch, send_partial);
         all_reduce_finish(b_o);                               // out projection + residual (model.py:68)
+        mark(4);
 
         // ---- LN2 -> cross-attention query -> attention over the encoder K/V, never masked (model.py:70-71)
-        rows_to_hilo<D>(s_h, GU, ln + 2 * D, ln + 3 * D, xn_hi, xn_lo, D + 32);
+        ln_rows<S>(s_h, GU, ln + 2 * D, ln + 3 * D, xn_hi, xn_lo, stat);
         consumer_sync();
         mm_stream<MWqc, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
-          s_q[u0 * 64 + n] = (v0 + b_qc[n]) * qscale;
-          s_q[(u0 + 1) * 64 + n] = (v1 + b_qc[n]) * qscale;
+          q_store(q_hi, q_lo, u0, n, (v0 + b_qc[n]) * qscale);
+          q_store(q_hi, q_lo, u0 + 1, n, (v1 + b_qc[n]) * qscale);
         });
         consumer_sync();
-        attn_begin(st, s_q + au * 64);
-#pragma unroll 1
-        for (int c0 = 0; c0 < p.Tp; c0 += RPS) {
-          const uint8_t* stg = c.acquire();
-          attn_stage<S>(st, stg + au * RPS * 256, min(RPS, p.Tp - c0), agrp, a_active);
-          c.release();
-        }
+        mark(5);
+        attn_init(st);
+        attn_q_frags(q_hi, q_lo, au, qf);
+        mark(6);
+        attention<S>(c, st, qf, p.Tp, a_active, au, apart, 0u, [&](int i) { mark(7 + i); });
         attn_finish<S>(st, GU, part_buf, stat, o_hi, o_lo);
+        mark(10);
         mm_stream<MWo, GUP>(c, reinterpret_cast<const uint8_t*>(o_hi), reinterpret_cast<const uint8_t*>(o_lo), S::LDO,
                             scratch, send_partial);
         all_reduce_finish(b_oc);
 
         // ---- LN3 -> FFN: squeeze rows of this CTA + ReLU, then the matching K-slice of unsqueeze (model.py:73-74)
-        rows_to_hilo<D>(s_h, GU, ln + 4 * D, ln + 5 * D, xn_hi, xn_lo, D + 32);
+        ln_rows<S>(s_h, GU, ln + 4 * D, ln + 5 * D, xn_hi, xn_lo, stat);
         consumer_sync();
         mm_stream<MW1, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
           const float y0 = fmaxf(v0 + b_1[n], 0.f), y1 = fmaxf(v1 + b_1[n], 0.f);
@@ -755,6 +965,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
         mm_stream<MW2, GUP>(c, reinterpret_cast<const uint8_t*>(hid_hi), reinterpret_cast<const uint8_t*>(hid_lo),
                             S::LDH, scratch, send_partial);
         all_reduce_finish(b_2);
+        mark(5);
       }
 
       // ---- classifier WITHOUT the final LayerNorm (model.py:142): VS vocabulary rows per CTA
@@ -868,6 +1079,8 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
       p.timing[size_t(blockIdx.x) * 16 + 0] = clock64() - t_begin;
       p.timing[size_t(blockIdx.x) * 16 + 1] = c.waited;
       p.timing[size_t(blockIdx.x) * 16 + 2] = t_xchg;
+      mark(0);
+      for (int i = 0; i < 11; ++i) p.timing[size_t(blockIdx.x) * 16 + 5 + i] = ph[i];
     }
   }
   cluster_sync_all();   // no CTA leaves while a peer may still write into its shared memory
@@ -983,11 +1196,11 @@ int launch_dec_cluster(ClusterParams& p, cudaStream_t s) {
 
   // encoder K/V as a 2-D tensor: [nd * B * Tp rows][2D columns] bf16; box = [RPS rows][64 columns] (one head)
   CUtensorMap map;
-  const int rps = (STAGE_BYTES / 256) / p.GUP;
+  const int rps = (STAGE_BYTES / 128) / p.GUP;
   const uint64_t dims[2] = {uint64_t(2 * p.D), uint64_t(p.nd) * p.B * p.Tp};
   const uint64_t strides[2] = {0, uint64_t(4 * p.D)};
   const uint32_t box[2] = {64u, uint32_t(rps)};
-  if (int rc = make_tmap_bf16(&map, p.ckv, 2, dims, strides, box, nullptr, /*swizzle=*/0)) return rc;
+  if (int rc = make_tmap_bf16(&map, p.ckv, 2, dims, strides, box, nullptr, /*swizzle=*/128)) return rc;
 
   const int n_clusters = (p.B + p.GU - 1) / p.GU;
   cudaLaunchConfig_t cfg{};

@@ -290,6 +290,10 @@ def main():
                                                  enumerate(["total", "ring_wait", "exchange_wait", "producer_wait_empty",
                                                             "stages_total"])}
             result["cluster_ctas"] = int(len(cp))
+            names_c = ["small_params+classifier", "ln1", "qkv", "self_attn", "wo_allreduce", "wo2+ffn(+ln2_q)", "x_qfrags", "x_qk_stages",
+                       "x_softmax", "x_pv_stages", "x_finish"]
+            result["cluster_phase_cycles_per_step"] = {n: round(float(cp[:, 5 + i].mean()) / cfg.decoder_seq_len, 1)
+                                                       for i, n in enumerate(names_c)}
         ph = ph[:n_sm]
         names = ["A_ln1_qkv", "bar", "B_attn_chain", "bar", "C_ln3_ffn1", "bar", "D_ffn2", "bar", "E_classify", "bar",
                  "B0_load", "B1_self_attn", "B2_out_proj", "B3_ln2_q", "B4_cross_attn", "B5_out_proj"]

@@ -23,7 +23,7 @@ case $g in
   benchteams) for t in 1 2 8 16; do ASR_B200_TEAMS=$t timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-profile > gpurun_out/bench_t$t.log 2>&1; echo "teams=$t: $(python -c "import json,sys; d=json.loads(open('gpurun_out/bench_t$t.log').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'])")"; done ;;
   benchstream) timeout 600 python bench.py --steps 5 --warmup 3 --decode-mode stream --no-cpu-baseline > gpurun_out/benchstream.log 2> gpurun_out/benchstream.err; echo "benchstream exit $?"; python -c "import json; d=json.loads(open('gpurun_out/benchstream.log').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['decode_kernels_ms'], d['roofline'])"; tail -n 3 gpurun_out/benchstream.err ;;
   cluster) run cluster tests/test_model_gpu.py -m gpu -k "cluster" ;;
-  benchcluster) timeout 600 python bench.py --steps 5 --warmup 3 --decode-mode cluster --no-cpu-baseline > gpurun_out/benchcluster.log 2> gpurun_out/benchcluster.err; echo "benchcluster exit $?"; python -c "import json; d=json.loads(open('gpurun_out/benchcluster.log').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e'], d['decode_kernels_ms'], d['roofline'], d.get('cluster_cycles_per_step'), d.get('cluster_ctas'))"; tail -n 3 gpurun_out/benchcluster.err ;;
+  benchcluster) timeout 600 python bench.py --steps 5 --warmup 3 --decode-mode cluster --no-cpu-baseline > gpurun_out/benchcluster.log 2> gpurun_out/benchcluster.err; echo "benchcluster exit $?"; python -c "import json; d=json.loads(open('gpurun_out/benchcluster.log').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e'], d['decode_kernels_ms'], d['roofline'], d.get('cluster_cycles_per_step'), d.get('cluster_ctas'), d.get('cluster_phase_cycles_per_step'))"; tail -n 3 gpurun_out/benchcluster.err ;;
   benchref) timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/benchref.log 2>&1; echo "benchref exit $?"; tail -c 1500 gpurun_out/benchref.log ;;
 esac
 done
