@@ -7,6 +7,8 @@
 //   warp 4  : TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B, 64-wide K blocks, STAGES-deep mbarrier ring)
 //   warp 5  : UMMA issuer   (one elected thread, tcgen05.mma kind::f16, fp32 accumulators in TMEM)
 //   warps 0-3: epilogue     (tcgen05.ld 32 lanes x 32 columns per warp -> registers -> fused epilogue -> HBM)
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -20,16 +22,57 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 
 template <int BN, int STAGES>
 constexpr size_t gemm_smem_bytes() {
-  return size_t(STAGES) * (A_STAGE_BYTES + BN * BK * 2) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  return size_t(STAGES) * (A_STAGE_BYTES + BN * BK * 2) + (2 * STAGES + 1) * 8 + 32 + BN * 4 + 1024;
 }
 
+// sbias: this CTA's bias slice in shared memory (nullptr = no bias), indexed by column - n0
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], int row, int col0,
-                                               int n_store) {
+                                               int n_store, const float* sbias, int n0) {
   // 32 consecutive columns of one row, processed 4 at a time.
   const bool res_vec = ep.residual && (ep.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
   const bool f32_vec = ep.out_f32 && (ep.ld_f32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.out_f32) & 15) == 0);
   const bool b16_vec = ep.out_bf16 && (ep.ld_bf16 % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 7) == 0);
   const float* pe_row = ep.rowvec ? ep.rowvec + size_t(row % ep.rowvec_period) * ep.ld_rowvec : nullptr;
+  if (col0 + 32 <= n_store && (!ep.residual || res_vec) && (!ep.out_f32 || f32_vec) && (!ep.out_bf16 || b16_vec) &&
+      (!pe_row || ((ep.ld_rowvec % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.rowvec) & 15) == 0)))) {
+    // fast path: every global load of the chunk is in flight before the first use (the epilogue is latency-bound)
+    float4 res[8], pe[8];
+    if (ep.residual) {
+      const float4* rp = reinterpret_cast<const float4*>(ep.residual + size_t(row) * ep.ld_res + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) res[j] = rp[j];
+    }
+    if (pe_row) {
+      const float4* pp = reinterpret_cast<const float4*>(pe_row + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pe[j] = __ldg(pp + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[4 * j + i]);
+      if (sbias) {
+        const float4 b = *reinterpret_cast<const float4*>(sbias + col0 - n0 + 4 * j);
+        v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+      }
+      if (ep.relu) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (pe_row) { v[0] += pe[j].x; v[1] += pe[j].y; v[2] += pe[j].z; v[3] += pe[j].w; }
+      if (ep.residual) { v[0] += res[j].x; v[1] += res[j].y; v[2] += res[j].z; v[3] += res[j].w; }
+      if (ep.out_f32)
+        *reinterpret_cast<float4*>(ep.out_f32 + size_t(row) * ep.ld_f32 + col0 + 4 * j) = make_float4(v[0], v[1], v[2], v[3]);
+      if (ep.out_bf16) {
+        uint2 t;
+        t.x = pack_bf16x2(v[0], v[1]);
+        t.y = pack_bf16x2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(ep.out_bf16 + size_t(row) * ep.ld_bf16 + col0 + 4 * j) = t;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const int col = col0 + j;
@@ -89,8 +132,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
   }
 }
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int STAGES, int MINB>
+__global__ void __launch_bounds__(192, MINB)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
                int M, int n_store, int K) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
@@ -102,6 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~uintptr_t(15));   // [BN] bias slice
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,6 +161,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
+  if (warp < 4 && ep.bias)
+    for (int i = threadIdx.x; i < BN; i += 128) sbias[i] = (n0 + i < n_store) ? __ldg(ep.bias + n0 + i) : 0.f;
   if (warp == 4) {
     if (lane == 0) {
       tma_prefetch_desc(&tmA);
@@ -168,7 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t r[32];
       tmem_ld32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(c * 32), r);
       tmem_ld_wait();
-      if (row < M) epilogue_chunk(ep, r, row, n0 + c * 32, n_store);
+      if (row < M) epilogue_chunk(ep, r, row, n0 + c * 32, n_store, ep.bias ? sbias : nullptr, n0);
     }
   }
   tc_fence_before();
@@ -176,10 +222,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 4) tmem_dealloc(tmem_base, BN);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MINB>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int n_store, int n_pad,
                int K, cudaStream_t s) {
-  auto kern = gemm_tc_kernel<BN, STAGES>;
+  auto kern = gemm_tc_kernel<BN, STAGES, MINB>;
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
   static bool attr_set = false;
   if (!attr_set) {
@@ -227,12 +273,17 @@ int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N,
     int rc = make_tmap_bf16(&tmA, X, 2, dims, str, box, nullptr);
     if (rc) return rc;
   }
-  // pick the N tile: largest of 256/128/64 dividing n_pad that still gives >= ~1 wave of CTAs when possible
+  // Tile / pipeline choice.  These GEMMs have short K (256 .. 1216) and are bound by the epilogue's latency, not by
+  // the tensor pipe: what pays is CTAs in flight per SM (TMEM: 128 columns each), so the default is a 128-wide tile
+  // with a shallow TMA ring (2 stages = 64 KB -> 3 CTAs/SM; 3 stages for long K -> 2 CTAs/SM).  ASR_B200_GEMM_TILE
+  // (256 / 128 / 64) forces a width for experiments.
   const int mt = (M + BM - 1) / BM;
-  int bn = 64;
-  if (n_pad % 256 == 0 && mt * (n_pad / 256) >= 148) bn = 256;
-  else if (n_pad % 128 == 0 && mt * (n_pad / 128) >= 148) bn = 128;
-  else if (n_pad % 128 == 0 && mt * (n_pad / 64) > 4 * 148) bn = 128;
+  int bn = (n_pad % 128 == 0) ? 128 : 64;
+  if (const char* e = std::getenv("ASR_B200_GEMM_TILE")) {
+    const int f = std::atoi(e);
+    if ((f == 256 || f == 128 || f == 64) && n_pad % f == 0) bn = f;
+  }
+  (void)mt;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)n_pad};
     uint64_t str[2] = {2, (uint64_t)ldw * 2};
@@ -240,10 +291,13 @@ int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N,
     int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box, nullptr);
     if (rc) return rc;
   }
+  const bool deep = K > 512;
   switch (bn) {
-    case 256: return launch_one<256, 4>(tmA, tmB, ep, M, n_store, n_pad, K, s);
-    case 128: return launch_one<128, 4>(tmA, tmB, ep, M, n_store, n_pad, K, s);
-    default: return launch_one<64, 4>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+    case 256: return launch_one<256, 4, 1>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+    case 128: return deep ? launch_one<128, 3, 2>(tmA, tmB, ep, M, n_store, n_pad, K, s)
+                          : launch_one<128, 2, 3>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+    default: return deep ? launch_one<64, 4, 2>(tmA, tmB, ep, M, n_store, n_pad, K, s)
+                         : launch_one<64, 2, 4>(tmA, tmB, ep, M, n_store, n_pad, K, s);
   }
 }
 
