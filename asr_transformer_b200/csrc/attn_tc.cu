@@ -43,7 +43,7 @@ struct AttnDev {
   int mask_B;
 };
 
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(160, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, AttnDev p) {
   extern __shared__ uint8_t smem_raw[];
@@ -153,6 +153,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (p.k_lens) k_lim = min(k_lim, max(0, p.k_lens[b]));
     if (p.causal) k_lim = min(k_lim, qi + 1);
     if (row_masked) k_lim = 0;
+    const bool fast = !kvalid && !dmask;
 
     float m = -INFINITY, l = 0.f;
     float o[DH];
@@ -170,13 +171,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         uint32_t rr[32];
         tmem_ld32(tmem_S + lane_addr + uint32_t(c * 32), rr);
         tmem_ld_wait();
+        if (fast && kbase + c * 32 + 32 <= k_lim) {      // unmasked chunk: no per-element predicates
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kj = kbase + c * 32 + i;
-          bool ok = kj < k_lim;
-          if (kvalid && ok) ok = kvalid[kj] != 0;
-          if (dmask && ok) ok = dmask[kj] == 0;
-          if (ok) mx = fmaxf(mx, __uint_as_float(rr[i]) * p.scale_log2);
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(rr[i]));
+          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2);   // scale > 0
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kj = kbase + c * 32 + i;
+            bool ok = kj < k_lim;
+            if (kvalid && ok) ok = kvalid[kj] != 0;
+            if (dmask && ok) ok = dmask[kj] == 0;
+            if (ok) mx = fmaxf(mx, __uint_as_float(rr[i]) * p.scale_log2);
+          }
         }
       }
       const float m_new = fmaxf(m, mx);
@@ -204,19 +212,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_ld32(tmem_S + lane_addr + uint32_t(c * 32), rr);
         tmem_ld_wait();
         uint32_t packed[16];
+        if (fast && kbase + c * 32 + 32 <= k_lim) {
+          float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float pv[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int kj = kbase + c * 32 + i + u;
-            bool ok = kj < k_lim;
-            if (kvalid && ok) ok = kvalid[kj] != 0;
-            if (dmask && ok) ok = dmask[kj] == 0;
-            pv[u] = ok ? fast_exp2(__uint_as_float(rr[i + u]) * p.scale_log2 - m_new) : 0.f;
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_new));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -m_new));
+            l4[(i >> 1) & 3] += p0 + p1;
+            packed[i >> 1] = pack_bf16x2(p0, p1);
           }
-          lsum += pv[0] + pv[1];
-          packed[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+          lsum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float pv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int kj = kbase + c * 32 + i + u;
+              bool ok = kj < k_lim;
+              if (kvalid && ok) ok = kvalid[kj] != 0;
+              if (dmask && ok) ok = dmask[kj] == 0;
+              pv[u] = ok ? fast_exp2(__uint_as_float(rr[i + u]) * p.scale_log2 - m_new) : 0.f;
+            }
+            lsum += pv[0] + pv[1];
+            packed[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+          }
         }
         uint8_t* blk = sP + (c >> 1) * (BQ * 128) + r * 128;
 #pragma unroll
