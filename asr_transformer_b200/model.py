@@ -199,3 +199,72 @@ class Transformer(nn.Module):
         enc = self.encode(spectrum, lengths)
         tokens, n_tok, step_logits = self._eng().decode_greedy(enc, max_len, stop_at_eos, None, return_logits)
         return (tokens, n_tok, step_logits) if return_logits else (tokens, n_tok)
+
+    def greedy_decode_batches(self, batches, max_len: Optional[int] = None, stop_at_eos: bool = False,
+                              gather=None):
+        """Pipelined greedy ASR over an iterable of HOST batches ((B,1,F,T) fp32, ideally pinned): the upload of batch
+        i+1 and the download of batch i-1's transcripts run on side streams under the decode of batch i, so a serving
+        loop is bound by the GPU, not by PCIe.  Yields (tokens (B,L+1) int32, n_tokens (B,) int32) as CPU tensors,
+        in order.  ``gather`` (optional callable (tokens, n_tokens) -> (tokens, n_tokens)) runs on the device before
+        the download, e.g. ``parallel.gather_tokens`` for the multi-GPU transcript gather."""
+        _require_eval(self)
+        from collections import deque
+        dev = next(self.parameters()).device
+        main = torch.cuda.current_stream(dev)
+        streams = self.__dict__.setdefault("_side_streams", {})   # persistent: the caching allocator pools blocks per
+        if dev not in streams:                                     # stream, fresh streams would mean fresh cudaMallocs
+            streams[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        up_s, down_s = streams[dev]
+
+        def upload(x):
+            if x is None:
+                return None
+            with torch.cuda.stream(up_s):
+                d = x.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(up_s)
+            return d, ev
+
+        staging = self.__dict__.setdefault("_pinned_staging", {})   # pinned D2H buffers live with the model:
+        # cudaHostAlloc costs milliseconds, so they are allocated once per shape and reused by every call
+
+        def pinned(t, slot):
+            key = (slot, tuple(t.shape), t.dtype)
+            if key not in staging:
+                staging[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            return staging[key]
+
+        it = iter(batches)
+        nxt = upload(next(it, None))
+        pending = deque()
+        step = 0
+        while nxt is not None:
+            cur, ev = nxt
+            nxt = upload(next(it, None))          # next batch's H2D overlaps this batch's compute
+            main.wait_event(ev)
+            cur.record_stream(main)
+            tokens, n_tok = self.greedy_decode(cur, max_len=max_len, stop_at_eos=stop_at_eos)
+            if gather is not None:
+                tokens, n_tok = gather(tokens, n_tok)
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(down_s):
+                down_s.wait_event(done)
+                th, nh = pinned(tokens, (step % 3, 0)), pinned(n_tok, (step % 3, 1))
+                th.copy_(tokens, non_blocking=True)
+                nh.copy_(n_tok, non_blocking=True)
+                fin = torch.cuda.Event()
+                fin.record(down_s)
+            tokens.record_stream(down_s)
+            n_tok.record_stream(down_s)
+            pending.append((th, nh, fin))
+            step += 1
+            if len(pending) > 1:
+                a, b, e = pending.popleft()
+                e.synchronize()
+                yield a.clone(), b.clone()
+        while pending:
+            a, b, e = pending.popleft()
+            e.synchronize()
+            yield a.clone(), b.clone()
+

@@ -89,6 +89,10 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for l in self.lines:
@@ -103,6 +107,17 @@ class ClockSampler:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_traffic(kernel):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json:
+    {kernel: {"dram_bytes": ..., "source": ...}}); None when no capture of this kernel has been committed."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        d = json.load(open(p)).get(kernel)
+        if d:
+            return d.get("dram_bytes")
+    return None
 
 
 def measured_peaks():
@@ -208,8 +223,12 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     eng = model._eng()
 
-    def step_device():
+    mid = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+
+    def step_device(mark=None):
         eng.encode(spec_dev, out=enc)
+        if mark is not None:
+            mark.record()
         eng.decode_greedy(enc, tokens_out=tokens, n_tokens_out=n_tok)
 
     for _ in range(max(args.warmup, 3)):
@@ -222,15 +241,17 @@ def main():
     launches0 = lib.asr_launch_count()
     sampler.start()
     barrier()
-    for s, e in ev:
+    for (s, e), m in zip(ev, mid):
         flush.fill_(1)                      # evict L2 (126 MB) between timed iterations
         s.record()
-        step_device()
+        step_device(m)
         e.record()
     barrier()
     clocks = sampler.stop()
     launches = lib.asr_launch_count() - launches0
     ms = [s.elapsed_time(e) for s, e in ev]
+    enc_ms = sum(s.elapsed_time(m) for (s, _), m in zip(ev, mid)) / args.steps
+    dec_ms = sum(m.elapsed_time(e) for (_, e), m in zip(ev, mid)) / args.steps
     total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -238,23 +259,48 @@ def main():
     value = world * batch * args.steps / (total_ms / 1e3)
 
     # ------------------------------------------------------------------ end to end through the public API
-    def step_e2e():
+    # Every step uploads its own spectrogram batch from pinned host memory and downloads its transcripts; the public
+    # serving call (Transformer.greedy_decode_batches) overlaps those copies with the neighbouring steps' compute.
+    gather = gather_tokens if dist is not None else None
+
+    def run_e2e(n, trace=None):
+        out = None
+        t_start = time.perf_counter()
+        for out in model.greedy_decode_batches((spec_host for _ in range(n)), gather=gather):
+            if trace is not None:
+                trace.append(round(1e3 * (time.perf_counter() - t_start), 2))
+        return out
+
+    run_e2e(4)
+    barrier()
+    t0 = time.perf_counter()
+    trace = []
+    out_tokens, _ = run_e2e(args.steps, trace)
+    barrier()
+    if os.environ.get("ASR_B200_BENCH_TRACE"):
+        print("e2e yield times (ms):", trace, file=sys.stderr)
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * batch * args.steps / float(e2e_s.item())
+
+    def step_serial():      # the same work without overlap: one blocking call per batch
         x = spec_host.to(dev, non_blocking=True)
         t, n = model.greedy_decode(x)
         if dist is not None:
             t, n = gather_tokens(t, n)
         return t.cpu(), n.cpu()
 
-    step_e2e()
+    step_serial()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out_tokens, _ = step_e2e()
+        step_serial()
     barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    ser_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if dist is not None:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * batch * args.steps / float(e2e_s.item())
+        dist.all_reduce(ser_s, op=dist.ReduceOp.MAX)
+    e2e_serial = world * batch * args.steps / float(ser_s.item())
     h2d = spec_host.numel() * 4
     d2h = out_tokens.numel() * 4 + out_tokens.shape[0] * 4
 
@@ -262,8 +308,11 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "config": workload_desc(cfg, batch, world), "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "Transformer.greedy_decode_batches (pinned host batches in, CPU transcripts out; copies of "
+                       "neighbouring steps overlap compute)", "serial_value": e2e_serial},
         "gpu_launches": int(launches),
+        "phase_ms": {"conv_frontend+encoder": round(enc_ms, 3), "cross_kv+greedy_decode": round(dec_ms, 3)},
     }
 
     if rank == 0 and args.no_profile:
@@ -324,10 +373,12 @@ def main():
         if mode[0] in "psc" and n_cls[slot]:
             ms_cls[9] = ms_cls[slot]
             gbs = decode_bytes / (ms_cls[9] * 1e-3) / 1e9
-            result["roofline"] = {"kernel": {9: "dec_persistent_kernel", 10: "dec_stream_kernel", 11: "dec_cluster_kernel"}[slot] +
-                                            " (all %d decode steps, one launch)" % cfg.decoder_seq_len,
+            kname = {9: "dec_persistent_kernel", 10: "dec_stream_kernel", 11: "dec_cluster_kernel"}[slot]
+            result["roofline"] = {"kernel": kname + " (all %d decode steps, one launch)" % cfg.decoder_seq_len,
                                   "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
-                                  "frac": round(gbs / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                                  "frac": round(gbs / hbm_peak, 4),
+                                  "traffic": measured_traffic(kname) if (args.workload == WORKLOAD and batch == cfg.batch) else None,
+                                  "peak_source": peak_src,
                                   "alg_bytes_per_launch": int(decode_bytes), "ms_per_launch": round(ms_cls[9], 3)}
         else:
             top = max(prof, key=lambda k: prof[k]["share"])

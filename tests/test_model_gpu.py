@@ -237,3 +237,15 @@ def test_long_form_encoder_C4():
     tokens, _ = m.greedy_decode(spec.to(DEV), max_len=48)
     r, frac = check_tokens(tok_ref, logits_ref, tokens)
     assert frac == 1.0 or not r["hard"]
+
+
+def test_pipelined_batches_match_single_calls(t0):
+    """greedy_decode_batches (H2D / D2H on side streams) returns exactly what per-batch greedy_decode returns."""
+    cfg, fx, m, spec = t0
+    host = [spec.cpu().pin_memory(), spec.flip(0).cpu().pin_memory(), spec[:2].cpu().pin_memory()]
+    outs = list(m.greedy_decode_batches(host))
+    assert len(outs) == 3
+    for x, (tok, n) in zip(host, outs):
+        t_ref, n_ref = m.greedy_decode(x.to(DEV))
+        assert not tok.is_cuda and torch.equal(tok, t_ref.cpu()) and torch.equal(n, n_ref.cpu())
+    assert list(m.greedy_decode_batches([])) == []
