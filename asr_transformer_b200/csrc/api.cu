@@ -516,8 +516,8 @@ int asr_decoder_forward(AsrHandle* h, const float* enc_out, int B, int Tp, const
 }
 
 int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, int stop_at_eos,
-                      const int32_t* first_tokens, void* ws, size_t ws_bytes, int32_t* tokens, int32_t* n_tokens,
-                      float* step_logits, asr_stream_t stream) {
+                      const int32_t* first_tokens, const int32_t* enc_lens, void* ws, size_t ws_bytes, int32_t* tokens,
+                      int32_t* n_tokens, float* step_logits, asr_stream_t stream) {
   if (!h || !h->loaded) return set_error(ASR_E_INVALID, "asr_decode_greedy: weights not loaded");
   if (B == 0) return 0;
   if (!enc_out || !tokens || !ws || B < 0 || Tp <= 0 || L <= 0)
@@ -551,8 +551,12 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
   if ((!mode || !mode[0] || mode[0] == 'c') && cluster_available(h)) {
     ClusterParams cp;
     build_cluster(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, cp);
+    cp.enc_lens = enc_lens;
     return launch_dec_cluster(cp, s);
   }
+  if (enc_lens)
+    return set_error(ASR_E_UNSUPPORTED, "asr_decode_greedy: encoder lengths (cross-attention key padding) need the "
+                     "cluster decoder, which is unavailable for this configuration / ASR_B200_DECODE mode");
   if (mode && mode[0] == 's' && h->w.dec_small &&
       stream_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers)) {
     PersistentParams pp;

@@ -112,7 +112,7 @@ struct Shape {
   static constexpr int WPU = NCW / GUP;                   // attention warps per utterance slot
   static constexpr int SC = 2;                            // K stages per super-chunk (softmax granularity)
   static constexpr int TPW = (RPS / 16) / WPU;            // 16-key tiles per warp per stage
-  static constexpr int SMALL_FLOATS = 256 + FFS + 9 * D;
+  static constexpr int SMALL_FLOATS = 256 + FFS + 11 * D;   // ... | ln1 | ln2 | ln3 | ln1 of the NEXT layer
   static constexpr uint32_t SMALL_BYTES = (SMALL_FLOATS * 4 + 127) / 128 * 128;
   static constexpr int LDX = (D + 32) * 2, LDH = (FFS + 32) * 2, LDO = 96 * 2;   // activation row strides (bytes)
 };
@@ -134,11 +134,11 @@ struct Mat {
   static constexpr bool EXACT = (MT % MSTEP) == 0;                     // every warp has exactly UPW units
   static constexpr uint32_t ST_BYTES = KBS * MT * 1024u;
   static_assert(MT >= 1 && MT <= 32 && KBS % KG == 0 && KB % KBS == 0 && NCW % KG == 0 && UPW <= 4 && MT * KG <= 32 &&
-                    EXACT, "tiling");
+                    (KG == 1 || MT * KG <= 24) && EXACT, "tiling");
 };
 
 struct SmemMap {
-  uint32_t ring, h, xn_hi, xn_lo, hid_hi, hid_lo, o_hi, o_lo, q, kvrow, scratch, prm, lg, recv, arg, part, stat, tok,
+  uint32_t ring, h, xn_hi, xn_lo, hid_hi, hid_lo, o_hi, o_lo, q, kvrow, scratch, prm, lg, recv, arg, part, stat, red, tok,
       ctrl, bars, total;
 };
 template <class S>
@@ -160,13 +160,14 @@ __host__ __device__ inline SmemMap smem_map(int nstages) {
   m.o_lo = take(S::GUP * S::LDO);
   m.q = take(S::GUP * 64 * 4);                         // bf16 hi [GUP][64] | bf16 lo [GUP][64], fragment order
   m.kvrow = take(S::GUP * 128 * 2);
-  m.scratch = take(32 * 32 * 16);                      // [KG * MT <= 32][32 lanes] float4 partial tiles
+  m.scratch = take(24 * 32 * 16);                      // [KG * MT <= 24 when KG > 1][32 lanes] float4 partial tiles
   m.prm = take(S::SMALL_BYTES);
   m.lg = take(S::GUP * S::VS * 4);
   m.recv = take(2 * S::CS * S::D * S::GUP * 4);        // [parity][source rank][D][GUP] fp32 partial sums
   m.arg = take(2 * S::CS * S::GUP * 8);                // [parity][source rank][GUP] (value, index)
   m.part = take(NCW * 64 * 4);
   m.stat = take(2 * NCW * 4);
+  m.red = take(NCW * 8 * 8);                           // LayerNorm partials [warp][utterance slot] (sum, sum of squares)
   m.tok = take(2 * 8 * 4);                             // [0..7] next tokens, [8..15] finished flags
   m.ctrl = take(16);                                   // [0] steps done, [1] stop, [2] cache rows written
   m.bars = take((2 * MAX_STAGES + 4) * 8);
@@ -522,9 +523,11 @@ __device__ __forceinline__ void pv_tile(AttnT& st, uint32_t vbase, uint32_t b0, 
 // tiles 2 apart, 2 apart + 1 of every stage.  All scores of a super-chunk are computed first (independent MMAs), then
 // ONE max / exp / sum, then all P V products: one softmax dependency chain per super-chunk instead of one per tile.
 // cur_kb != 0: additionally the single current row (k_t at cur_kb, v_t at cur_kb + 128), merged into the first chunk.
+// n_keys rows are streamed (uniform over the CTA); only the first n_mine of them are valid keys of THIS warp's
+// utterance (key-padding: cross attention with encoder lengths), the rest are masked.
 template <class S, class Mk>
-__device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t (&qf)[8], int n_keys, bool active,
-                                          int au, int apart, uint32_t cur_kb, Mk&& mk) {
+__device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t (&qf)[8], int n_keys, int n_mine,
+                                          bool active, int au, int apart, uint32_t cur_kb, Mk&& mk) {
   constexpr int RPS = S::RPS, SC = S::SC, TPW = S::TPW;
   float ca = -INFINITY, cb = -INFINITY;
   bool cur = cur_kb != 0;
@@ -542,7 +545,7 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t
       for (int j = 0; j < TPW; ++j) sa[s][j] = sb[s][j] = -INFINITY;
       if (s < ns) {
         const uint32_t stg = smem_u32(c.acquire()) + slot_off;
-        const int n = min(RPS, nk - s * RPS) - 16 * TPW * apart;   // rows of this stage at / after this warp's first tile
+        const int n = min(RPS, min(nk, n_mine - c0) - s * RPS) - 16 * TPW * apart;   // valid rows at / after my first tile
         if (active) {
 #pragma unroll
           for (int j = 0; j < TPW; ++j)
@@ -590,7 +593,7 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t
     for (int s = 0; s < SC; ++s) {
       if (s < ns) {
         const uint32_t stg = smem_u32(c.acquire()) + slot_off;
-        const int n = min(RPS, nk - s * RPS) - 16 * TPW * apart;
+        const int n = min(RPS, min(nk, n_mine - c0) - s * RPS) - 16 * TPW * apart;
         if (active) {
 #pragma unroll
           for (int j = 0; j < TPW; ++j)
@@ -693,6 +696,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
   float2* arg = reinterpret_cast<float2*>(smem + sm.arg);
   float* part_buf = reinterpret_cast<float*>(smem + sm.part);
   float* stat = reinterpret_cast<float*>(smem + sm.stat);
+  float2* red = reinterpret_cast<float2*>(smem + sm.red);
   int* s_tok = reinterpret_cast<int*>(smem + sm.tok);
   volatile int* ctrl = reinterpret_cast<volatile int*>(smem + sm.ctrl);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);
@@ -808,6 +812,8 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
     const int lane = tid & 31;
     const int au = warp % GUP, apart = warp / GUP;                  // attention: utterance slot / 16-key tile of a stage
     const bool a_active = au < GU;
+    // key-padding mask of the cross attention: encoder frames >= enc_lens[utterance] are not attended (nullable)
+    const int n_cross = (p.enc_lens && a_active) ? max(0, min(p.Tp, p.enc_lens[ubase + au])) : p.Tp;
     const float qscale = p.scale * LOG2E;
     const uint8_t* xh = reinterpret_cast<const uint8_t*>(xn_hi);
     const uint8_t* xl = reinterpret_cast<const uint8_t*>(xn_lo);
@@ -828,21 +834,67 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
       for (int r = 0; r < CS; ++r)
         if (r != rank) st_async_v2(mapa_u32(ma, r), v0, v1, mapa_u32(ba, r));
     };
-    auto all_reduce_finish = [&](const float* bias) {
+    // ... and, fused into its tail, what follows every all-reduce: LayerNorm of the new rows (gam != nullptr) or the
+    // plain bf16 hi | lo split (classifier input).  Thread tid owns elements idx = tid + NCT k: utterance u = tid % GUP,
+    // n = idx / GUP; the new values stay in registers between the sum and the normalisation.  Variance from one pass
+    // over (x - c), c = the row's previous first element (same for every thread: read before the first barrier).
+    auto all_reduce_finish = [&](const float* bias, const float* gam, const float* bet) {
+      constexpr int EP = D * GUP / NCT;
+      static_assert(D * GUP % NCT == 0 && NCT % GUP == 0, "all-reduce element split");
       const uint32_t par = n_xchg & 1u, phase = (n_xchg >> 1) & 1u;
+      const int u = tid % GUP, nb = tid / GUP;
+      const float c0 = s_h[u * D];
       if (tid == 0) mbar_expect_tx(&xbar[par], uint32_t(CS - 1) * D * GUP * 4u);
-      consumer_sync();                                     // own slot written by every thread
-      const long long w0 = clock64();
-      mbar_wait_cluster(&xbar[par], phase);
-      t_xchg += clock64() - w0;
+      consumer_sync();                                     // own slot written by every thread; c0 read by every thread
+      if (timed) {
+        const long long w0 = clock64();
+        mbar_wait_cluster(&xbar[par], phase);
+        t_xchg += clock64() - w0;
+      } else {
+        mbar_wait_cluster(&xbar[par], phase);
+      }
       const float* rv = recv + size_t(par) * CS * D * GUP;
-      for (int idx = tid; idx < D * GUP; idx += NCT) {
-        const int n = idx / GUP, u = idx % GUP;
-        if (u < GU) {
-          float s = 0.f;
+      float hv[EP], s1 = 0.f, s2 = 0.f;
 #pragma unroll
-          for (int r = 0; r < CS; ++r) s += rv[r * D * GUP + idx];
-          s_h[u * D + n] += s + bias[n];
+      for (int k = 0; k < EP; ++k) {
+        const int idx = tid + NCT * k, n = nb + k * (NCT / GUP);
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < CS; ++r) s += rv[r * D * GUP + idx];
+        hv[k] = s_h[u * D + n] + (s + bias[n]);
+        if (u < GU) s_h[u * D + n] = hv[k];
+        const float d = hv[k] - c0;
+        s1 += d;
+        s2 = fmaf(d, d, s2);
+      }
+      float mean = 0.f, rstd = 1.f;
+      if (gam) {
+#pragma unroll
+        for (int o = 16; o >= GUP; o >>= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane < GUP) red[warp * GUP + lane] = make_float2(s1, s2);
+        consumer_sync();
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < NCW; ++w) {
+          const float2 r = red[w * GUP + u];
+          t1 += r.x;
+          t2 += r.y;
+        }
+        mean = t1 * (1.0f / float(D));
+        rstd = 1.0f / sqrtf(fmaxf(t2 * (1.0f / float(D)) - mean * mean, 0.f) + 1e-5f);
+        mean += c0;
+      }
+      if (u < GU) {
+#pragma unroll
+        for (int k = 0; k < EP; ++k) {
+          const int n = nb + k * (NCT / GUP);
+          const float y = gam ? (hv[k] - mean) * rstd * gam[n] + bet[n] : hv[k];
+          const bf16 hh = __float2bfloat16(y);
+          xn_hi[u * (D + 32) + n] = hh;
+          xn_lo[u * (D + 32) + n] = __float2bfloat16(y - __bfloat162float(hh));
         }
       }
       consumer_sync();
@@ -880,9 +932,11 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
         const float* ln = b_2 + D;                // ln1 g,b | ln2 g,b | ln3 g,b
 
         mark(0);
-        // ---- LN1 -> q, k, v of this head (model.py:67-68, layers.py:16-18)
-        ln_rows<S>(s_h, GU, ln, ln + D, xn_hi, xn_lo, stat);
-        consumer_sync();
+        // ---- LN1 -> q, k, v of this head (model.py:67-68, layers.py:16-18); layers > 0 got LN1 from the all-reduce
+        if (l == 0) {
+          ln_rows<S>(s_h, GU, ln, ln + D, xn_hi, xn_lo, stat);
+          consumer_sync();
+        }
         mark(1);
         mm_stream<MQkv, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
           const float y0 = v0 + b_qkv[n], y1 = v1 + b_qkv[n];
@@ -917,7 +971,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
         uint32_t qf[8];
         attn_init(st);
         attn_q_frags(q_hi, q_lo, au, qf);
-        attention<S>(c, st, qf, t, a_active, au, apart,
+        attention<S>(c, st, qf, t, t, a_active, au, apart,
                      (a_active && apart == S::WPU - 1) ? smem_u32(kv_row) + au * 256 : 0u, [](int) {});
         asm volatile("fence.proxy.async;" ::: "memory");     // this step's cache rows: later read by the producer's TMA
         attn_finish<S>(st, GU, part_buf, stat, o_hi, o_lo);   // (two consumer barriers inside)
@@ -928,12 +982,10 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
         mark(3);
         mm_stream<MWo, GUP>(c, reinterpret_cast<const uint8_t*>(o_hi), reinterpret_cast<const uint8_t*>(o_lo), S::LDO,
                             scratch, send_partial);
-        all_reduce_finish(b_o);                               // out projection + residual (model.py:68)
+        all_reduce_finish(b_o, ln + 2 * D, ln + 3 * D);       // out projection + residual (model.py:68) -> LN2 (:70)
         mark(4);
 
-        // ---- LN2 -> cross-attention query -> attention over the encoder K/V, never masked (model.py:70-71)
-        ln_rows<S>(s_h, GU, ln + 2 * D, ln + 3 * D, xn_hi, xn_lo, stat);
-        consumer_sync();
+        // ---- cross-attention query -> attention over the encoder K/V, never masked (model.py:70-71)
         mm_stream<MWqc, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
           q_store(q_hi, q_lo, u0, n, (v0 + b_qc[n]) * qscale);
           q_store(q_hi, q_lo, u0 + 1, n, (v1 + b_qc[n]) * qscale);
@@ -943,16 +995,14 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
         attn_init(st);
         attn_q_frags(q_hi, q_lo, au, qf);
         mark(6);
-        attention<S>(c, st, qf, p.Tp, a_active, au, apart, 0u, [&](int i) { mark(7 + i); });
+        attention<S>(c, st, qf, p.Tp, n_cross, a_active, au, apart, 0u, [&](int i) { mark(7 + i); });
         attn_finish<S>(st, GU, part_buf, stat, o_hi, o_lo);
         mark(10);
         mm_stream<MWo, GUP>(c, reinterpret_cast<const uint8_t*>(o_hi), reinterpret_cast<const uint8_t*>(o_lo), S::LDO,
                             scratch, send_partial);
-        all_reduce_finish(b_oc);
+        all_reduce_finish(b_oc, ln + 4 * D, ln + 5 * D);      // -> LN3 (model.py:73)
 
-        // ---- LN3 -> FFN: squeeze rows of this CTA + ReLU, then the matching K-slice of unsqueeze (model.py:73-74)
-        ln_rows<S>(s_h, GU, ln + 4 * D, ln + 5 * D, xn_hi, xn_lo, stat);
-        consumer_sync();
+        // ---- FFN: squeeze rows of this CTA + ReLU, then the matching K-slice of unsqueeze (model.py:73-74)
         mm_stream<MW1, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
           const float y0 = fmaxf(v0 + b_1[n], 0.f), y1 = fmaxf(v1 + b_1[n], 0.f);
           const bf16 h0 = __float2bfloat16(y0), h1 = __float2bfloat16(y1);
@@ -964,13 +1014,17 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
         consumer_sync();
         mm_stream<MW2, GUP>(c, reinterpret_cast<const uint8_t*>(hid_hi), reinterpret_cast<const uint8_t*>(hid_lo),
                             S::LDH, scratch, send_partial);
-        all_reduce_finish(b_2);
+        // -> LN1 of the next layer (its parameters travel in this layer's block), or the classifier's plain split
+        if (l + 1 < p.nd) all_reduce_finish(b_2, ln + 6 * D, ln + 7 * D);
+        else all_reduce_finish(b_2, nullptr, nullptr);
         mark(5);
       }
 
       // ---- classifier WITHOUT the final LayerNorm (model.py:142): VS vocabulary rows per CTA
-      rows_to_hilo<D>(s_h, GU, nullptr, nullptr, xn_hi, xn_lo, D + 32);
-      consumer_sync();
+      if (p.nd == 0) {
+        rows_to_hilo<D>(s_h, GU, nullptr, nullptr, xn_hi, xn_lo, D + 32);
+        consumer_sync();
+      }
       mm_stream<MCls, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
         s_lg[u0 * VS + n] = v0;
         s_lg[(u0 + 1) * VS + n] = v1;
@@ -1114,7 +1168,7 @@ bool cluster_layout(int D, int H, int FF, int V, int nd, ClusterLayout* out) {
   L.FFS = FF / H;
   L.VS = ((V + H - 1) / H + 15) / 16 * 16;
   if (!find_instance(H, L.FFS, L.VS, 2)) return false;   // only the compiled shapes
-  L.small_floats = 256 + L.FFS + 9 * D;
+  L.small_floats = 256 + L.FFS + 11 * D;
   L.small_bytes = (size_t(L.small_floats) * 4 + 127) / 128 * 128;
   size_t off = 0;
   L.off_small = off; off += L.small_bytes;

@@ -196,6 +196,7 @@ struct ClusterParams {
   const float* emb; const float* pe; const float* h0;   // h0: fp32 [B][D] embedding + PE of the first token
   bf16* cache;            // [nd][B][H][K rows | V rows][L][64]  (this kernel's own layout of the self-attention cache)
   const bf16* ckv;        // [nd][B*Tp][2D]
+  const int32_t* enc_lens;   // nullable [B]: valid encoder frames per utterance (cross-attention key-padding mask)
   int32_t* tokens; int32_t* n_tokens; float* step_logits;
   int eos, pad, stop_at_eos;
   float scale;

@@ -110,7 +110,7 @@ def dec_image_layout(D: int, H: int, FF: int, V: int, nd: int) -> Optional[dict]
     VS = ((V + H - 1) // H + 15) // 16 * 16
     if D > 512 or FFS > 512 or VS > 512:
         return None
-    lay = {"CS": H, "FFS": FFS, "VS": VS, "small_floats": 256 + FFS + 9 * D}
+    lay = {"CS": H, "FFS": FFS, "VS": VS, "small_floats": 256 + FFS + 11 * D}
     lay["small_bytes"] = (lay["small_floats"] * 4 + 127) // 128 * 128
     if lay["small_bytes"] > 32768:
         return None
@@ -140,7 +140,7 @@ def pack_mma_a(w: torch.Tensor) -> torch.Tensor:
 def pack_dec_image(decoder: nn.Module) -> Optional[torch.Tensor]:
     """Packed weight image of the cluster decoder (uint8): for every head r (= CTA rank) the slices that CTA consumes,
     in consumption order, per layer: small fp32 block [b_qkv_r(192) | b_qc_r(64) | b1_r(FFS) | b_o(D) | b_oc(D) |
-    b2(D) | ln1 g,b | ln2 g,b | ln3 g,b] (padded to 128 B), then Wqkv rows of head r (q|k|v), Wo[:, head r columns],
+    b2(D) | ln1 g,b | ln2 g,b | ln3 g,b | ln1 g,b of the next layer] (padded to 128 B), then Wqkv rows of head r (q|k|v), Wo[:, head r columns],
     cross Wq rows of head r, cross Wo[:, head r columns], W1 rows r*FFS.., W2[:, r*FFS..] - each in pack_mma_a order;
     after the layers the classifier rows r*VS.. (zero padded)."""
     layers = list(decoder._layers)
@@ -172,6 +172,9 @@ def pack_dec_image(decoder: nn.Module) -> Optional[torch.Tensor]:
                      ff["b2"]]
             for ln in (layer._norm1, layer._norm2, layer._norm3):
                 small += [_f32(ln.weight), _f32(ln.bias)]
+            li = layers.index(layer)          # ... followed by norm1 of the NEXT layer (fused into this layer's last
+            nxt = layers[li + 1]._norm1 if li + 1 < len(layers) else None          # all-reduce); zeros after the last
+            small += [_f32(nxt.weight), _f32(nxt.bias)] if nxt is not None else [torch.zeros(2 * D, device=dev)]
             small = torch.cat([x.reshape(-1) for x in small])
             assert small.numel() == lay["small_floats"]
             small = torch.cat([small, small.new_zeros(lay["small_bytes"] // 4 - small.numel())])
@@ -370,7 +373,8 @@ class Engine:
 
     def decode_greedy(self, enc_out: torch.Tensor, max_len: Optional[int] = None, stop_at_eos: bool = False,
                       first_tokens: Optional[torch.Tensor] = None, want_logits: bool = False,
-                      tokens_out: Optional[torch.Tensor] = None, n_tokens_out: Optional[torch.Tensor] = None):
+                      tokens_out: Optional[torch.Tensor] = None, n_tokens_out: Optional[torch.Tensor] = None,
+                      enc_lens: Optional[torch.Tensor] = None):
         B, Tp, _ = enc_out.shape
         L = int(max_len or self.cfg.decoder_seq_len)
         enc_out = enc_out.to(torch.float32).contiguous()
@@ -379,8 +383,9 @@ class Engine:
         n_tok = n_tokens_out if n_tokens_out is not None else torch.empty(B, dtype=torch.int32, device=dev)
         step_logits = torch.empty(B, L, self.cfg.vocab_size, dtype=torch.float32, device=dev) if want_logits else None
         first = None if first_tokens is None else first_tokens.to(device=dev, dtype=torch.int32).contiguous()
+        lens = None if enc_lens is None else enc_lens.to(device=dev, dtype=torch.int32).contiguous()
         ws = self._ws(B, 4 * Tp + 3, L)
         _l.check(_l.load().asr_decode_greedy(self.handle, _l.ptr(enc_out), B, Tp, L, int(bool(stop_at_eos)),
-                                             _l.ptr(first), _l.ptr(ws), ws.numel(), _l.ptr(tokens), _l.ptr(n_tok),
+                                             _l.ptr(first), _l.ptr(lens), _l.ptr(ws), ws.numel(), _l.ptr(tokens), _l.ptr(n_tok),
                                              _l.ptr(step_logits), _l.stream()), "asr_decode_greedy")
         return tokens, n_tok, step_logits

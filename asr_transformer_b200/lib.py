@@ -66,8 +66,8 @@ _SIGNATURES = {
     "asr_encoder_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "asr_decoder_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                                     c_void_p, c_void_p]),
-    "asr_decode_greedy": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t,
-                                  c_void_p, c_void_p, c_void_p, c_void_p]),
+    "asr_decode_greedy": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "asr_decode_profile": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),
     "asr_launch_count": (C.c_ulonglong, []),

@@ -181,23 +181,30 @@ class Transformer(nn.Module):
         return _evaluate(eng, text, eng.encode(spectrum), self.decoder._seq_len, self.decoder._eos_token_id)
 
     # ---- additive API ----------------------------------------------------------------------------------
+    @staticmethod
+    def encoder_lengths(lengths: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """Input frames per utterance -> encoder frames after the two stride-2 valid convolutions (model.py:168-171)."""
+        if lengths is None:
+            return None
+        l1 = torch.div(lengths - 3, 2, rounding_mode="floor") + 1
+        return (torch.div(l1 - 3, 2, rounding_mode="floor") + 1).clamp_min(0)
+
     def encode(self, spectrum, lengths: Optional[torch.Tensor] = None):
         """Front-end + encoder. ``lengths`` (input frames per utterance) switches on the key-padding mask that the
         reference root encoder lacks; leave None for reference parity."""
         _require_eval(self)
-        enc_lens = None
-        if lengths is not None:
-            l1 = torch.div(lengths - 3, 2, rounding_mode="floor") + 1
-            enc_lens = (torch.div(l1 - 3, 2, rounding_mode="floor") + 1).clamp_min(0)
-        return self._eng().encode(spectrum, enc_lens)
+        return self._eng().encode(spectrum, self.encoder_lengths(lengths))
 
     def greedy_decode(self, spectrum, lengths: Optional[torch.Tensor] = None, max_len: Optional[int] = None,
                       stop_at_eos: bool = False, return_logits: bool = False):
         """Batched greedy ASR: (B,1,F,T) -> tokens (B, L+1) int32 (column 0 = BOS), n_tokens (B,) int32
-        [, step_logits (B,L,V)].  stop_at_eos=False decodes exactly L steps like the reference."""
+        [, step_logits (B,L,V)].  stop_at_eos=False decodes exactly L steps like the reference.  ``lengths`` (input
+        frames per utterance) masks the zero padding end to end: encoder self attention AND the decoder's cross
+        attention ignore the padded frames, so a padded utterance decodes like the unpadded one."""
         _require_eval(self)
         enc = self.encode(spectrum, lengths)
-        tokens, n_tok, step_logits = self._eng().decode_greedy(enc, max_len, stop_at_eos, None, return_logits)
+        tokens, n_tok, step_logits = self._eng().decode_greedy(enc, max_len, stop_at_eos, None, return_logits,
+                                                               enc_lens=self.encoder_lengths(lengths))
         return (tokens, n_tok, step_logits) if return_logits else (tokens, n_tok)
 
     def greedy_decode_batches(self, batches, max_len: Optional[int] = None, stop_at_eos: bool = False,

@@ -91,7 +91,8 @@ typedef struct {
    * Requires num_heads in {2,4,8}, ff_dim % (32 num_heads) == 0; FFS = ff_dim / num_heads, VS = round_up(ceil(V /
    * num_heads), 16).  Per head r: for each layer
    *   small : fp32 b_qkv rows of head r (q|k|v: 192) | cross b_q rows of head r (64) | b1[r FFS..] (FFS) | b_out (D) |
-   *           cross b_out (D) | b2 (D) | norm1 g,b | norm2 g,b | norm3 g,b (6 D); zero padded to a multiple of 128 B
+   *           cross b_out (D) | b2 (D) | norm1 g,b | norm2 g,b | norm3 g,b | norm1 g,b of layer l+1 (zeros after the last
+   *           layer) (8 D); zero padded to a multiple of 128 B
    *   Wqkv rows of head r (192 x D) | Wout[:, 64 r..] (D x 64) | cross Wq rows of head r (64 x D) |
    *   cross Wout[:, 64 r..] (D x 64) | W1[r FFS.., :] (FFS x D) | W2[:, r FFS..] (D x FFS)
    * then the classifier rows [r VS, (r+1) VS) (zero padded past vocab).  Every matrix [R x K] is stored bf16 in
@@ -140,8 +141,11 @@ int asr_decoder_forward(AsrHandle* h, const float* enc_out, int B, int Tp, const
  * (one cooperative kernel runs all L steps, grid barriers between phases), "stream" (one CTA per utterance, weights
  * and K/V streamed through a TMA ring, no barriers), "graph" (CUDA-graph replay of the per-kernel step) or "eager". */
 int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, int stop_at_eos,
-                      const int32_t* first_tokens /* [B] nullable: defaults to bos_token_id */, void* ws,
-                      size_t ws_bytes, int32_t* tokens, int32_t* n_tokens, float* step_logits, asr_stream_t stream);
+                      const int32_t* first_tokens /* [B] nullable: defaults to bos_token_id */,
+                      const int32_t* enc_lens /* [B] nullable: valid encoder frames per utterance; cross attention
+                                                 masks the rest (the key-padding mask the reference lacks, Q6) */,
+                      void* ws, size_t ws_bytes, int32_t* tokens, int32_t* n_tokens, float* step_logits,
+                      asr_stream_t stream);
 
 /* Profiling aid for bench.py: the same decode launched eagerly with a CUDA-event pair around every kernel.
  * Synchronises `stream` before returning.  ms_per_class / launches_per_class: 12 entries in the order

@@ -115,6 +115,12 @@ def test_image_layout_and_contents(name):
             assert torch.equal(small[256 + FFS:256 + FFS + D], sa["b_out"])
             assert torch.equal(small[256 + FFS + 2 * D:256 + FFS + 3 * D], ff["b2"])
             assert torch.equal(small[256 + FFS + 7 * D:256 + FFS + 8 * D], layer._norm3.weight.detach())
+            nxt = small[256 + FFS + 9 * D:256 + FFS + 11 * D]          # norm1 of the next layer rides along
+            if l + 1 < nd:
+                assert torch.equal(nxt[:D], dec._layers[l + 1]._norm1.weight.detach())
+                assert torch.equal(nxt[D:], dec._layers[l + 1]._norm1.bias.detach())
+            else:
+                assert not nxt.any()
         cls = torch.zeros(H * VS, D, dtype=torch.bfloat16)
         cls[:V] = dec._classifier.weight.detach().to(torch.bfloat16)
         assert torch.equal(mat(r, -1, "cls", VS, D), cls[r * VS:(r + 1) * VS])

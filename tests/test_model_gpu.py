@@ -249,3 +249,23 @@ def test_pipelined_batches_match_single_calls(t0):
         t_ref, n_ref = m.greedy_decode(x.to(DEV))
         assert not tok.is_cuda and torch.equal(tok, t_ref.cpu()) and torch.equal(n, n_ref.cpu())
     assert list(m.greedy_decode_batches([])) == []
+
+
+def test_key_padding_end_to_end_decode(t0):
+    """Masks on, end to end: a zero-padded utterance decoded with its length gives the tokens of
+    the unpadded utterance decoded alone (encoder self attention and decoder cross attention both ignore the padding)."""
+    cfg, fx, m, spec = t0
+    T_short = 131
+    padded = spec.clone()
+    padded[1, :, :, T_short:] = 0
+    lengths = torch.tensor([cfg.frames, T_short, cfg.frames], device=DEV)
+    tok, _, lg = m.greedy_decode(padded, lengths=lengths, return_logits=True)
+    alone, _, lg1 = m.greedy_decode(spec[1:2, :, :, :T_short].contiguous(), return_logits=True)
+    full, _ = m.greedy_decode(spec)
+    assert torch.equal(tok[0], full[0]) and torch.equal(tok[2], full[2])       # unpadded rows unaffected
+    assert_close(lg[1], lg1[0], 2e-2, 2e-3, "masked batch row == unpadded utterance (step logits)")
+    r = O.compare_tokens(alone.cpu(), lg1.cpu(), tok[1:2].cpu(), TAU)
+    assert not r["hard"], r
+    # without the lengths the padded frames leak into the cross attention: the logits differ
+    _, _, lg_nomask = m.greedy_decode(padded, return_logits=True)
+    assert (lg_nomask[1] - lg1[0]).abs().max() > 1e-3
