@@ -96,6 +96,13 @@ __device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* m
       ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
       : "memory");
 }
+// TMA store of a small contiguous block shared -> global (async proxy), tracked by the thread's bulk group
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
 __device__ __forceinline__ uint4 lds128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
@@ -229,6 +236,17 @@ struct Consumer {
     }
     return r.buf + size_t(slot) * STAGE_BYTES;
   }
+  // wait for the stage i slots ahead of the current one (0 = current) without consuming it
+  __device__ __forceinline__ const uint8_t* acquire_ahead(int i) {
+    int sl = slot + i;
+    uint32_t rd = round;
+    if (sl >= r.nstages) {
+      sl -= r.nstages;
+      ++rd;
+    }
+    mbar_wait(&r.full[sl], rd & 1u);
+    return r.buf + size_t(sl) * STAGE_BYTES;
+  }
   __device__ __forceinline__ void release() {       // every consumer warp calls this once per stage
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&r.empty[slot]);
@@ -265,37 +283,48 @@ __device__ __forceinline__ void mm_stream(Consumer& c, const uint8_t* xhi, const
   const bool xrow = g < (COLS ? 2 * GUP : GUP);
   const uint8_t* xh = ((COLS && g >= GUP) ? xlo + (g - GUP) * ldx : xhi + g * ldx) + tg * 16 + kg * M::KPG * 64;
   const uint8_t* xl = xlo + g * ldx + tg * 16 + kg * M::KPG * 64;
+  // SPI stages per iteration: both waits, then every load of both stages, then the MMAs, then both releases (halves
+  // the number of exposed wait -> LDS -> HMMA latency chains for the 4-stage matrices)
+  constexpr int SPI = 1;   // 2 (pairs of stages) measured slower: the second wait delays the first stage's work
 #pragma unroll 1
-  for (int st_i = 0; st_i < M::NST; ++st_i) {
-    const uint8_t* st = c.acquire() + lane * 16 + (size_t(kg) * M::KPG * M::MT + mt0) * 1024;
-    uint4 af[M::KPG][M::UPW][2], bh[M::KPG], bl[M::KPG];
+  for (int st_i = 0; st_i < M::NST; st_i += SPI) {
+    const uint8_t* st[SPI];
 #pragma unroll
-    for (int q = 0; q < M::KPG; ++q) {               // every load of the stage is in flight before the first MMA
-      bh[q] = make_uint4(0, 0, 0, 0);
-      bl[q] = make_uint4(0, 0, 0, 0);
-      if (xrow) {
-        bh[q] = lds128(xh + (st_i * M::KBS + q) * 64);
-        if (!COLS) bl[q] = lds128(xl + (st_i * M::KBS + q) * 64);
-      }
+    for (int i = 0; i < SPI; ++i)
+      st[i] = (SPI == 1 ? c.acquire() : c.acquire_ahead(i)) + lane * 16 + (size_t(kg) * M::KPG * M::MT + mt0) * 1024;
+    uint4 af[SPI][M::KPG][M::UPW][2], bh[SPI][M::KPG], bl[SPI][M::KPG];
 #pragma unroll
-      for (int j = 0; j < M::UPW; ++j) {
-        const uint8_t* a = st + (size_t(q) * M::MT + j * M::MSTEP) * 1024;
-        af[q][j][0] = lds128(a);
-        af[q][j][1] = lds128(a + 512);
-      }
-    }
+    for (int i = 0; i < SPI; ++i)
 #pragma unroll
-    for (int q = 0; q < M::KPG; ++q)
+      for (int q = 0; q < M::KPG; ++q) {             // every load is in flight before the first MMA
+        bh[i][q] = make_uint4(0, 0, 0, 0);
+        bl[i][q] = make_uint4(0, 0, 0, 0);
+        if (xrow) {
+          bh[i][q] = lds128(xh + ((st_i + i) * M::KBS + q) * 64);
+          if (!COLS) bl[i][q] = lds128(xl + ((st_i + i) * M::KBS + q) * 64);
+        }
 #pragma unroll
-      for (int j = 0; j < M::UPW; ++j) {
-        mma16816(acc[j][0], af[q][j][0], bh[q].x, bh[q].y);
-        mma16816(acc[j][1], af[q][j][1], bh[q].z, bh[q].w);
-        if (!COLS) {
-          mma16816(acc[j][0], af[q][j][0], bl[q].x, bl[q].y);
-          mma16816(acc[j][1], af[q][j][1], bl[q].z, bl[q].w);
+        for (int j = 0; j < M::UPW; ++j) {
+          const uint8_t* a = st[i] + (size_t(q) * M::MT + j * M::MSTEP) * 1024;
+          af[i][q][j][0] = lds128(a);
+          af[i][q][j][1] = lds128(a + 512);
         }
       }
-    c.release();
+#pragma unroll
+    for (int i = 0; i < SPI; ++i)
+#pragma unroll
+      for (int q = 0; q < M::KPG; ++q)
+#pragma unroll
+        for (int j = 0; j < M::UPW; ++j) {
+          mma16816(acc[j][0], af[i][q][j][0], bh[i][q].x, bh[i][q].y);
+          mma16816(acc[j][1], af[i][q][j][1], bh[i][q].z, bh[i][q].w);
+          if (!COLS) {
+            mma16816(acc[j][0], af[i][q][j][0], bl[i][q].x, bl[i][q].y);
+            mma16816(acc[j][1], af[i][q][j][1], bl[i][q].z, bl[i][q].w);
+          }
+        }
+#pragma unroll
+    for (int i = 0; i < SPI; ++i) c.release();
   }
   float4 v[M::UPW];
 #pragma unroll
@@ -476,14 +505,16 @@ __device__ __forceinline__ void attn_q_frags(const bf16* q_hi, const bf16* q_lo,
 // chunk c of row r stored at chunk c ^ (r & 7): TMA SWIZZLE_128B; tiles start on multiples of 8 rows).
 // SINGLE: the tile is ONE row (the current step's k_t / v_t) replicated to all 16 key positions, keys >= 1 masked.
 template <bool SINGLE>
-__device__ __forceinline__ void qk_tile(uint32_t kbase, int n_valid, const uint32_t (&qf)[8], float& sa, float& sb) {
+__device__ __forceinline__ void qk_tile(uint32_t kbase, int n_valid, const uint32_t (&qf)[8], float& sa, float& sb,
+                                        int swz = 0) {
   const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3, mat = lane >> 3, r = lane & 7;
   float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   const int key = SINGLE ? 0 : (mat & 1) * 8 + r;
+  const int xr = SINGLE ? swz : key;                 // swizzle key: the row's index within its 8-row group
   const uint32_t row = kbase + key * 128;
   uint4 a[4];
 #pragma unroll
-  for (int kt = 0; kt < 4; ++kt) ldsm_x4(row + ((((2 * kt + (mat >> 1)) ^ key) & 7) << 4), a[kt]);
+  for (int kt = 0; kt < 4; ++kt) ldsm_x4(row + ((((2 * kt + (mat >> 1)) ^ xr) & 7) << 4), a[kt]);
 #pragma unroll
   for (int kt = 0; kt < 4; ++kt) mma16816(sc[kt & 1], a[kt], qf[2 * kt], qf[2 * kt + 1]);
   sa = (tg == 0 && g < n_valid) ? (sc[0][0] + sc[1][0]) + (sc[0][1] + sc[1][1]) : -INFINITY;        // key g (lanes tg == 0)
@@ -508,13 +539,14 @@ __device__ __forceinline__ void p_frags(float pa, float pb, uint32_t& b0, uint32
   }
 }
 template <bool SINGLE>
-__device__ __forceinline__ void pv_tile(AttnT& st, uint32_t vbase, uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void pv_tile(AttnT& st, uint32_t vbase, uint32_t b0, uint32_t b1, int swz = 0) {
   const int lane = threadIdx.x & 31, mat = lane >> 3, r = lane & 7;
   const int key = SINGLE ? 0 : (mat >> 1) * 8 + r;
+  const int xr = SINGLE ? swz : key;
   const uint32_t row = vbase + key * 128;
   uint4 a[4];
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) ldsm_x4_trans(row + ((((2 * mt + (mat & 1)) ^ key) & 7) << 4), a[mt]);
+  for (int mt = 0; mt < 4; ++mt) ldsm_x4_trans(row + ((((2 * mt + (mat & 1)) ^ xr) & 7) << 4), a[mt]);
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) mma16816(st.o[mt], a[mt], b0, b1);
 }
@@ -527,22 +559,26 @@ __device__ __forceinline__ void pv_tile(AttnT& st, uint32_t vbase, uint32_t b0, 
 // utterance (key-padding: cross attention with encoder lengths), the rest are masked.
 template <class S, class Mk>
 __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t (&qf)[8], int n_keys, int n_mine,
-                                          bool active, int au, int apart, uint32_t cur_kb, Mk&& mk) {
+                                          bool active, int au, int apart, uint32_t cur_kb, int cur_swz, Mk&& mk) {
   constexpr int RPS = S::RPS, SC = S::SC, TPW = S::TPW;
   float ca = -INFINITY, cb = -INFINITY;
   bool cur = cur_kb != 0;
-  if (cur) qk_tile<true>(cur_kb, 1, qf, ca, cb);
+  if (cur) qk_tile<true>(cur_kb, 1, qf, ca, cb, cur_swz);
   const uint32_t slot_off = au * RPS * 128 + apart * (TPW * 2048);
 #pragma unroll 1
   for (int c0 = 0; c0 < n_keys; c0 += SC * RPS) {
     const int nk = min(SC * RPS, n_keys - c0);
     const int ns = (nk + RPS - 1) / RPS;
     float sa[SC][TPW], sb[SC][TPW];
+    bool tv[SC][TPW];                                            // tile has valid keys (warp-uniform)
     float mx = fmaxf(ca, cb);
 #pragma unroll
     for (int s = 0; s < SC; ++s) {
 #pragma unroll
-      for (int j = 0; j < TPW; ++j) sa[s][j] = sb[s][j] = -INFINITY;
+      for (int j = 0; j < TPW; ++j) {
+        sa[s][j] = sb[s][j] = -INFINITY;
+        tv[s][j] = false;
+      }
       if (s < ns) {
         const uint32_t stg = smem_u32(c.acquire()) + slot_off;
         const int n = min(RPS, min(nk, n_mine - c0) - s * RPS) - 16 * TPW * apart;   // valid rows at / after my first tile
@@ -550,6 +586,7 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t
 #pragma unroll
           for (int j = 0; j < TPW; ++j)
             if (n > 16 * j) {
+              tv[s][j] = true;
               qk_tile<false>(stg + j * 2048, min(16, n - 16 * j), qf, sa[s][j], sb[s][j]);
               mx = fmaxf(mx, fmaxf(sa[s][j], sb[s][j]));
             }
@@ -567,9 +604,12 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t
       for (int s = 0; s < SC; ++s)
 #pragma unroll
         for (int j = 0; j < TPW; ++j) {
-          const float pa = exp2f(sa[s][j] - m_new), pb = exp2f(sb[s][j] - m_new);
-          lsum += pa + pb;
-          p_frags(pa, pb, pb0[s][j], pb1[s][j]);
+          pb0[s][j] = pb1[s][j] = 0;
+          if (tv[s][j]) {
+            const float pa = exp2f(sa[s][j] - m_new), pb = exp2f(sb[s][j] - m_new);
+            lsum += pa + pb;
+            p_frags(pa, pb, pb0[s][j], pb1[s][j]);
+          }
         }
       if (cur) {
         const float pa = exp2f(ca - m_new);
@@ -597,13 +637,13 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t
         if (active) {
 #pragma unroll
           for (int j = 0; j < TPW; ++j)
-            if (n > 16 * j) pv_tile<false>(st, stg + j * 2048, pb0[s][j], pb1[s][j]);
+            if (tv[s][j]) pv_tile<false>(st, stg + j * 2048, pb0[s][j], pb1[s][j]);
         }
         c.release();
       }
     }
     if (cur) {
-      if (m_new != -INFINITY) pv_tile<true>(st, cur_kb + 128, cb0, cb1);
+      if (m_new != -INFINITY) pv_tile<true>(st, cur_kb + 128, cb0, cb1, cur_swz);
       cur = false;
       ca = -INFINITY;
     }
@@ -621,7 +661,7 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) st.o[i][j] *= alpha;
-    pv_tile<true>(st, cur_kb + 128, b0, b1);
+    pv_tile<true>(st, cur_kb + 128, b0, b1, cur_swz);
   }
 }
 // merge the key partitions of every utterance slot and emit o (bf16 hi + lo rows, stride 96 elements)
@@ -943,37 +983,44 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
           if (n < 64) {
             q_store(q_hi, q_lo, u0, n, y0 * qscale);
             q_store(q_hi, q_lo, u0 + 1, n, y1 * qscale);
-          } else {
-            kv_row[u0 * 128 + (n - 64)] = __float2bfloat16(y0);
-            kv_row[(u0 + 1) * 128 + (n - 64)] = __float2bfloat16(y1);
+          } else {   // k_t | v_t rows in the cache's swizzled chunk order (chunk ^ (t & 7)): TMA-stored as they are
+            const int e = n - 64, pos = (e & 64) + ((((e & 63) >> 3) ^ (t & 7)) << 3) + (e & 7);
+            kv_row[u0 * 128 + pos] = __float2bfloat16(y0);
+            kv_row[(u0 + 1) * 128 + pos] = __float2bfloat16(y1);
           }
         });
+        fence_proxy_async();                                   // kv_row: generic writes -> the TMA store below
         consumer_sync();
         mark(2);
         // append k_t, v_t (bf16) to the device-resident cache: [layer][utterance][head][K rows | V rows][Lc][64], the
         // 16-byte chunks of row t stored swizzled (chunk ^ (t & 7)) so that the bulk copy lands ldmatrix-ready.  The
         // first row of every 16-row block also zeroes the block's other rows: whole 16-key tiles are always finite.
-        if (tid < GU * 16) {
-          const int u = tid >> 4, ch = tid & 15, kv = ch >> 3, c16 = ch & 7;
+        if (tid < GU * 2) {                                    // one 128-byte TMA store per (utterance, K | V)
+          const int u = tid >> 1, kv = tid & 1;
           bf16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * Lc * 64 +
-                      size_t(t) * 64 + ((c16 ^ (t & 7)) << 3);
-          *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(kv_row + u * 128 + kv * 64 + c16 * 8);
+                      size_t(t) * 64;
+          bulk_store(dst, kv_row + u * 128 + kv * 64, 128);
         }
-        if ((t & 15) == 0)
+        if ((t & 15) == 0) {
           for (int i = tid; i < GU * 2 * 15 * 8; i += NCT) {
             const int u = i / 240, rem = i - u * 240, kv = rem / 120, w = rem - kv * 120;   // w: 16-byte word in 15 rows
             bf16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * Lc * 64 +
                         size_t(t + 1) * 64 + w * 8;
             *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
           }
+          asm volatile("fence.proxy.async;" ::: "memory");   // generic zero fill -> later TMA reads (1 step in 16)
+        }
         // ---- causal self attention over keys 0..t: cached rows from the ring, the current row from shared memory
         AttnT st;
         uint32_t qf[8];
         attn_init(st);
         attn_q_frags(q_hi, q_lo, au, qf);
+        mark(6);
         attention<S>(c, st, qf, t, t, a_active, au, apart,
-                     (a_active && apart == S::WPU - 1) ? smem_u32(kv_row) + au * 256 : 0u, [](int) {});
-        asm volatile("fence.proxy.async;" ::: "memory");     // this step's cache rows: later read by the producer's TMA
+                     (a_active && apart == S::WPU - 1) ? smem_u32(kv_row) + au * 256 : 0u, t & 7,
+                     [&](int i) { mark(7 + i); });
+        if (tid < GU * 2) bulk_store_wait();                  // this step's cache rows are written (published below)
+        mark(10);
         attn_finish<S>(st, GU, part_buf, stat, o_hi, o_lo);   // (two consumer barriers inside)
         if (tid == 0) {                                       // cache row t of this layer is published
           __threadfence_block();
@@ -994,10 +1041,8 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
         mark(5);
         attn_init(st);
         attn_q_frags(q_hi, q_lo, au, qf);
-        mark(6);
-        attention<S>(c, st, qf, p.Tp, n_cross, a_active, au, apart, 0u, [&](int i) { mark(7 + i); });
+        attention<S>(c, st, qf, p.Tp, n_cross, a_active, au, apart, 0u, 0, [](int) {});
         attn_finish<S>(st, GU, part_buf, stat, o_hi, o_lo);
-        mark(10);
         mm_stream<MWo, GUP>(c, reinterpret_cast<const uint8_t*>(o_hi), reinterpret_cast<const uint8_t*>(o_lo), S::LDO,
                             scratch, send_partial);
         all_reduce_finish(b_oc, ln + 4 * D, ln + 5 * D);      // -> LN3 (model.py:73)
@@ -1211,6 +1256,8 @@ int launch_dec_cluster(ClusterParams& p, cudaStream_t s) {
     const Instance* inst = find_instance(p.H, p.FFS, p.VS, gu < 2 ? 2 : gu);
     if (!inst) break;
     int nst = MAX_STAGES;
+    if (const char* se = std::getenv("ASR_B200_CLUSTER_STAGES"))
+      if (std::atoi(se) >= 3 && std::atoi(se) <= MAX_STAGES) nst = std::atoi(se);
     while (nst >= 3 && inst->map(nst).total > (uint32_t)max_smem) --nst;
     if (nst < 3) break;   // larger groups need even more shared memory
     static const void* configured[16] = {};

@@ -339,8 +339,8 @@ def main():
                                                  enumerate(["total", "ring_wait", "exchange_wait", "producer_wait_empty",
                                                             "stages_total"])}
             result["cluster_ctas"] = int(len(cp))
-            names_c = ["small_params+classifier", "ln1", "qkv", "self_attn", "wo_allreduce", "wo2+ffn(+ln2_q)", "x_qfrags", "x_qk_stages",
-                       "x_softmax", "x_pv_stages", "x_finish"]
+            names_c = ["small_params+classifier", "ln1", "qkv", "self_finish", "wo_allreduce", "cross+wo2+ffn", "s_cachewrite_qfrags", "s_qk_stages",
+                       "s_softmax", "s_pv_stages", "s_fence"]
             result["cluster_phase_cycles_per_step"] = {n: round(float(cp[:, 5 + i].mean()) / cfg.decoder_seq_len, 1)
                                                        for i, n in enumerate(names_c)}
         ph = ph[:n_sm]
