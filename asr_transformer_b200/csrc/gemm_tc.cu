@@ -22,7 +22,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 
 template <int BN, int STAGES>
 constexpr size_t gemm_smem_bytes() {
-  return size_t(STAGES) * (A_STAGE_BYTES + BN * BK * 2) + (2 * STAGES + 1) * 8 + 32 + BN * 4 + 1024;
+  return size_t(STAGES) * (A_STAGE_BYTES + BN * BK * 2) + (2 * STAGES + 4) * 8 + 32 + 2 * BN * 4 + 1024;
 }
 
 // sbias: this CTA's bias slice in shared memory (nullptr = no bias), indexed by column - n0
@@ -47,6 +47,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
 #pragma unroll
       for (int j = 0; j < 8; ++j) pe[j] = __ldg(pp + j);
     }
+    const bool b16_wide = ep.out_bf16 && (ep.ld_bf16 % 8 == 0) && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0);
+    uint32_t pk[2] = {0, 0};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       float v[4];
@@ -68,7 +70,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
         uint2 t;
         t.x = pack_bf16x2(v[0], v[1]);
         t.y = pack_bf16x2(v[2], v[3]);
-        *reinterpret_cast<uint2*>(ep.out_bf16 + size_t(row) * ep.ld_bf16 + col0 + 4 * j) = t;
+        if (!b16_wide) {
+          *reinterpret_cast<uint2*>(ep.out_bf16 + size_t(row) * ep.ld_bf16 + col0 + 4 * j) = t;
+        } else if (j & 1) {      // 16-byte stores: half the L2 write transactions of this row-per-thread layout
+          *reinterpret_cast<uint4*>(ep.out_bf16 + size_t(row) * ep.ld_bf16 + col0 + 4 * (j - 1)) =
+              make_uint4(pk[0], pk[1], t.x, t.y);
+        } else {
+          pk[0] = t.x;
+          pk[1] = t.y;
+        }
       }
     }
     return;
@@ -132,10 +142,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
   }
 }
 
-template <int BN, int STAGES, int MINB>
-__global__ void __launch_bounds__(192, MINB)
+// Persistent kernel: one CTA per SM walks the output tiles (n fastest, so concurrently processed tiles share their A
+// rows in L2); the fp32 accumulator is double-buffered in TMEM, so the epilogue of tile i (8 warps: 4 lane quadrants x
+// 2 column halves) overlaps the TMA loads and MMAs of tile i+1.  These GEMMs have short K (256 .. 1216): what bounds
+// them is the epilogue and per-tile fixed latency, not the tensor pipe - hence persistent + overlapped, not bigger tiles.
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = (EPI_WARPS + 2) * 32;
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
-               int M, int n_store, int K) {
+               int M, int n_store, int K, int tiles_n, int n_tiles) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -143,33 +160,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~uintptr_t(15));   // [BN] bias slice
+  uint64_t* tmem_full = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~uintptr_t(15));   // [2][BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM;
-  const int n0 = blockIdx.x * BN;
   const int nk = K / BK;
 
-  if (warp == 5 && lane == 0) {
+  if (warp == EPI_WARPS + 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], EPI_WARPS);
+    }
     fence_barrier_init();
   }
-  if (warp < 4 && ep.bias)
-    for (int i = threadIdx.x; i < BN; i += 128) sbias[i] = (n0 + i < n_store) ? __ldg(ep.bias + n0 + i) : 0.f;
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
     if (lane == 0) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr, BN);
+    tmem_alloc(tmem_ptr, 2 * BN);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -177,63 +194,94 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 4) {
+  if (warp == EPI_WARPS) {
+    // ------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
-        tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BK, m0);
-        tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
+          tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BK, m0);
+          tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+        }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == EPI_WARPS + 1) {
+    // ------------------------------------------------ UMMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1, use = lt >> 1;
+        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);      // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(sA + s * A_STAGE_BYTES), 16, 1024);
-        const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + s * B_STAGE_BYTES), 16, 1024);
+        const uint32_t acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(sA + s * A_STAGE_BYTES), 16, 1024);
+          const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + s * B_STAGE_BYTES), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k)   // +32 B per 16-element K step inside the 128 B swizzle row
-          umma_bf16_ss(tmem_base, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0);
-        umma_commit(&empty_bar[s]);
+          for (int k = 0; k < BK / 16; ++k)   // +32 B per 16-element K step inside the 128 B swizzle row
+            umma_bf16_ss(acc, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[buf]);
       }
-      umma_commit(tmem_full_bar);
     }
   } else {
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int row = m0 + warp * 32 + lane;
+    // ------------------------------------------------ epilogue: warp w -> TMEM lanes 32 (w % 4).., columns half w / 4
+    const int quad = warp & 3, half = warp >> 2;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t buf = lt & 1, use = lt >> 1;
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      float* sb = sbias + buf * BN;
+      if (ep.bias)
+        for (int i = threadIdx.x; i < BN; i += EPI_WARPS * 32) sb[i] = (n0 + i < n_store) ? __ldg(ep.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");   // bias slice visible to the epilogue warps
+      mbar_wait(&tmem_full[buf], use & 1);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + (uint32_t(warp * 32) << 16) + uint32_t(c * 32), r);
-      tmem_ld_wait();
-      if (row < M) epilogue_chunk(ep, r, row, n0 + c * 32, n_store, ep.bias ? sbias : nullptr, n0);
+      for (int c = 0; c < BN / 64; ++c) {
+        const int col = half * (BN / 2) + c * 32;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + buf * BN + (uint32_t(quad * 32) << 16) + uint32_t(col), r);
+        tmem_ld_wait();
+        if (row < M) epilogue_chunk(ep, r, row, n0 + col, n_store, ep.bias ? sb : nullptr, n0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, BN);
+  if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 2 * BN);
 }
 
-template <int BN, int STAGES, int MINB>
+template <int BN, int STAGES>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int n_store, int n_pad,
                int K, cudaStream_t s) {
-  auto kern = gemm_tc_kernel<BN, STAGES, MINB>;
+  auto kern = gemm_tc_kernel<BN, STAGES>;
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
   static bool attr_set = false;
+  static int n_sm = 0;
   if (!attr_set) {
     ASR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    ASR_CUDA_OK(cudaGetDevice(&dev));
+    ASR_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true;
   }
-  dim3 grid(n_pad / BN, (M + BM - 1) / BM);
-  kern<<<grid, 192, smem, s>>>(tmA, tmB, ep, M, n_store, K);
+  const int tiles_n = n_pad / BN, n_tiles = tiles_n * ((M + BM - 1) / BM);
+  const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+  kern<<<grid, GEMM_THREADS, smem, s>>>(tmA, tmB, ep, M, n_store, K, tiles_n, n_tiles);
   ASR_CUDA_OK(cudaGetLastError());
   ASR_LAUNCHED(1);
   return 0;
@@ -273,17 +321,13 @@ int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N,
     int rc = make_tmap_bf16(&tmA, X, 2, dims, str, box, nullptr);
     if (rc) return rc;
   }
-  // Tile / pipeline choice.  These GEMMs have short K (256 .. 1216) and are bound by the epilogue's latency, not by
-  // the tensor pipe: what pays is CTAs in flight per SM (TMEM: 128 columns each), so the default is a 128-wide tile
-  // with a shallow TMA ring (2 stages = 64 KB -> 3 CTAs/SM; 3 stages for long K -> 2 CTAs/SM).  ASR_B200_GEMM_TILE
-  // (256 / 128 / 64) forces a width for experiments.
-  const int mt = (M + BM - 1) / BM;
+  // Tile choice: 128-wide tiles (2 x 128 TMEM columns), 6-stage TMA ring (192 KB); 64-wide when N is not a multiple
+  // of 128.  ASR_B200_GEMM_TILE (256 / 128 / 64) forces a width for experiments.
   int bn = (n_pad % 128 == 0) ? 128 : 64;
   if (const char* e = std::getenv("ASR_B200_GEMM_TILE")) {
     const int f = std::atoi(e);
     if ((f == 256 || f == 128 || f == 64) && n_pad % f == 0) bn = f;
   }
-  (void)mt;
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)n_pad};
     uint64_t str[2] = {2, (uint64_t)ldw * 2};
@@ -291,13 +335,10 @@ int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N,
     int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box, nullptr);
     if (rc) return rc;
   }
-  const bool deep = K > 512;
   switch (bn) {
-    case 256: return launch_one<256, 4, 1>(tmA, tmB, ep, M, n_store, n_pad, K, s);
-    case 128: return deep ? launch_one<128, 3, 2>(tmA, tmB, ep, M, n_store, n_pad, K, s)
-                          : launch_one<128, 2, 3>(tmA, tmB, ep, M, n_store, n_pad, K, s);
-    default: return deep ? launch_one<64, 4, 2>(tmA, tmB, ep, M, n_store, n_pad, K, s)
-                         : launch_one<64, 2, 4>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+    case 256: return launch_one<256, 4>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+    case 128: return launch_one<128, 6>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+    default: return launch_one<64, 8>(tmA, tmB, ep, M, n_store, n_pad, K, s);
   }
 }
 
