@@ -92,41 +92,58 @@ __global__ void f32_to_bf16_tail_kernel(const float* x, bf16* y, size_t start, s
 }
 
 // ---------------------------------------------------------------- conv1: Conv2d(1,64,3,stride 2) + ReLU
-// spectrum fp32 (B,1,F,T) -> y1 bf16 channels-last (B, T1, F1, 64).  C_in = 1, so this is CUDA-core work:
-// 8 threads per output pixel, each producing 8 channels and one 16-byte store (128 B per pixel, coalesced).
+// spectrum fp32 (B,1,F,T) -> y1 bf16 channels-last (B, T1, F1, 64).  C_in = 1, so this is CUDA-core work bound by
+// the 128 B / pixel output stream.  One CTA per (utterance, CONV1_TT consecutive output frames): the F x (2 TT + 1)
+// input patch is staged in shared memory with loads coalesced along T (the input's contiguous axis), then 8 threads
+// per output pixel produce 8 channels each and one 16-byte store (pixels of a frame are contiguous: coalesced).
+constexpr int CONV1_TT = 32;
 __global__ void __launch_bounds__(256)
 conv1_kernel(const float* __restrict__ spec, const float* __restrict__ w1, const float* __restrict__ b1, int B, int F,
              int T, int F1, int T1, bf16* __restrict__ y1) {
-  __shared__ float sw[9 * 64];
-  __shared__ float sb[64];
+  extern __shared__ float conv1_smem[];
+  float* sw = conv1_smem;            // [9][64]
+  float* sb = sw + 9 * 64;           // [64]
+  float* sx = sb + 64;               // [F][2 TT + 1]
+  constexpr int W = 2 * CONV1_TT + 1;
+  const int b = blockIdx.y, t10 = blockIdx.x * CONV1_TT;
+  const int nt1 = min(CONV1_TT, T1 - t10), wcols = 2 * nt1 + 1;
   for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) sw[i] = w1[i];
   if (threadIdx.x < 64) sb[threadIdx.x] = b1[threadIdx.x];
+  const float* xin = spec + size_t(b) * F * T + 2 * t10;
+  for (int i = threadIdx.x; i < F * W; i += blockDim.x) {
+    const int f = i / W, c = i - f * W;
+    sx[i] = (c < wcols) ? __ldg(xin + size_t(f) * T + c) : 0.f;
+  }
   __syncthreads();
-  const size_t total = size_t(B) * T1 * F1;
   const int cg = threadIdx.x & 7;
-  for (size_t pix = size_t(blockIdx.x) * 32 + (threadIdx.x >> 3); pix < total; pix += size_t(gridDim.x) * 32) {
-    const int f1 = int(pix % F1);
-    const int t1 = int((pix / F1) % T1);
-    const int b = int(pix / (size_t(F1) * T1));
-    const float* xp = spec + (size_t(b) * F + 2 * f1) * T + 2 * t1;
-    float in[9];
+  float wr[9][8], bias[8];
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) wr[tap][c] = sw[tap * 64 + cg * 8 + c];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) bias[c] = sb[cg * 8 + c];
+  bf16* yout = y1 + (size_t(b) * T1 + t10) * F1 * 64;
+  for (int pix = threadIdx.x >> 3; pix < nt1 * F1; pix += 32) {
+    const int tl = pix / F1, f1 = pix - tl * F1;
+    const float* xp = sx + (2 * f1) * W + 2 * tl;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = bias[c];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) in[kh * 3 + kw] = __ldg(xp + size_t(kh) * T + kw);
-    float acc[8];
+      for (int kw = 0; kw < 3; ++kw) {
+        const float x = xp[kh * W + kw];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = sb[cg * 8 + c];
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) acc[c] = fmaf(in[tap], sw[tap * 64 + cg * 8 + c], acc[c]);
+        for (int c = 0; c < 8; ++c) acc[c] = fmaf(x, wr[kh * 3 + kw][c], acc[c]);
+      }
     uint4 o;
     o.x = pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
     o.y = pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
     o.z = pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
     o.w = pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
-    *reinterpret_cast<uint4*>(y1 + pix * 64 + cg * 8) = o;
+    *reinterpret_cast<uint4*>(yout + size_t(pix) * 64 + cg * 8) = o;
   }
 }
 
@@ -246,9 +263,15 @@ int launch_f32_to_bf16(const float* x, bf16* y, size_t n, cudaStream_t s) {
 int launch_conv1(const float* spec, const float* w1, const float* b1, int B, int F, int T, bf16* y1, cudaStream_t s) {
   const int F1 = (F - 3) / 2 + 1, T1 = (T - 3) / 2 + 1;
   if (F1 <= 0 || T1 <= 0) return set_error(-2, "conv1: input %dx%d too small", F, T);
-  const size_t total = size_t(B) * T1 * F1;
-  const int blocks = (int)((total + 31) / 32 < 148 * 16 ? (total + 31) / 32 : 148 * 16);
-  conv1_kernel<<<blocks, 256, 0, s>>>(spec, w1, b1, B, F, T, F1, T1, y1);
+  const size_t smem = (size_t(9 * 64 + 64) + size_t(F) * (2 * CONV1_TT + 1)) * sizeof(float);
+  if (smem > 200 * 1024) return set_error(-2, "conv1: input_dim %d too large for the shared-memory patch", F);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid((T1 + CONV1_TT - 1) / CONV1_TT, B);
+  conv1_kernel<<<grid, 256, smem, s>>>(spec, w1, b1, B, F, T, F1, T1, y1);
   ASR_CUDA_OK(cudaGetLastError());
   ASR_LAUNCHED(1);
   return 0;
