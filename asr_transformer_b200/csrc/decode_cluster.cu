@@ -865,14 +865,21 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
 
     // partial sums over the full model dimension (this CTA's K-slice) -> all-reduce across the cluster:
     // h[u][n] += sum over ranks + bias[n].  Called right after the mm_stream that sent the partial tiles.
+    // peer windows of the receive buffer / parity barriers, mapped once (mapa is linear inside a CTA's window);
+    // peer k = rank (rank + 1 + k) % CS
+    uint32_t peer_recv[CS - 1], peer_bar[CS - 1];
+#pragma unroll
+    for (int k = 0; k < CS - 1; ++k) {
+      const uint32_t r = uint32_t(rank + 1 + k) % CS;
+      peer_recv[k] = mapa_u32(smem_u32(recv), r);
+      peer_bar[k] = mapa_u32(smem_u32(&xbar[0]), r);
+    }
     auto send_partial = [&](int n, int u0, float v0, float v1) {
       const uint32_t par = n_xchg & 1u;
-      float* mine = recv + ((size_t(par) * CS + rank) * D + n) * GUP + u0;
-      *reinterpret_cast<float2*>(mine) = make_float2(v0, v1);
-      const uint32_t ma = smem_u32(mine), ba = smem_u32(&xbar[par]);
+      const uint32_t off = uint32_t(((size_t(par) * CS + rank) * D + n) * GUP + u0) * 4u;
+      *reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(recv) + off) = make_float2(v0, v1);
 #pragma unroll
-      for (int r = 0; r < CS; ++r)
-        if (r != rank) st_async_v2(mapa_u32(ma, r), v0, v1, mapa_u32(ba, r));
+      for (int k = 0; k < CS - 1; ++k) st_async_v2(peer_recv[k] + off, v0, v1, peer_bar[k] + par * 8u);
     };
     // ... and, fused into its tail, what follows every all-reduce: LayerNorm of the new rows (gam != nullptr) or the
     // plain bf16 hi | lo split (classifier input).  Thread tid owns elements idx = tid + NCT k: utterance u = tid % GUP,
