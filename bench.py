@@ -329,9 +329,6 @@ def main():
                                            L.ptr(ws), ws.numel(), L.ptr(tokens), ms_cls, n_cls, L.ptr(phase),
                                            L.stream()), "asr_decode_profile")
         ph = phase.double().cpu()
-        sp = ph[148:148 + batch]
-        result["stream_cycles_per_step"] = {k: round(float(sp[:, i].mean()) / cfg.decoder_seq_len, 1) for i, k in
-                                            enumerate(["total", "consumer_wait_full", "producer_wait_empty", "stages_total"])}
         cp = ph[2 * 148:2 * 148 + 148]
         cp = cp[cp[:, 0] > 0]
         if len(cp):
@@ -343,14 +340,7 @@ def main():
                        "s_softmax", "s_pv_stages", "s_fence"]
             result["cluster_phase_cycles_per_step"] = {n: round(float(cp[:, 5 + i].mean()) / cfg.decoder_seq_len, 1)
                                                        for i, n in enumerate(names_c)}
-        ph = ph[:n_sm]
-        names = ["A_ln1_qkv", "bar", "B_attn_chain", "bar", "C_ln3_ffn1", "bar", "D_ffn2", "bar", "E_classify", "bar",
-                 "B0_load", "B1_self_attn", "B2_out_proj", "B3_ln2_q", "B4_cross_attn", "B5_out_proj"]
         mhz = clocks.get("sm_mhz") or 1965.0
-        per_step = ph / cfg.decoder_seq_len / mhz       # us per decode step
-        result["persistent_phase_us_per_step"] = {
-            f"{i}_{n}": {"mean": round(float(per_step[:, i].mean()), 2), "max": round(float(per_step[:, i].max()), 2),
-                         "cta0": round(float(per_step[0, i]), 2)} for i, n in enumerate(names)}
         hbm_peak, tf_peak, peak_src = measured_peaks()
         bytes_cls = decode_class_bytes(cfg, batch)
         prof = {}
