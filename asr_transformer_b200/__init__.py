@@ -8,6 +8,7 @@ behind the C-ABI declared in ``include/asr_b200.h``.  No CPU path, no Triton, no
 from .layers import MHA, MHAHead, FeedForward, TrainablePositionalEncoding, LayerNorm
 from .model import Transformer, Encoder, Decoder, EncoderLayer, DecoderLayer, ConvFrontEnd
 from .text import Detokenizer
+from .frontend import Spectrogram
 
 __all__ = ["Transformer", "Encoder", "Decoder", "EncoderLayer", "DecoderLayer", "ConvFrontEnd", "MHA", "MHAHead",
-           "FeedForward", "TrainablePositionalEncoding", "LayerNorm", "Detokenizer"]
+           "FeedForward", "TrainablePositionalEncoding", "LayerNorm", "Detokenizer", "Spectrogram"]

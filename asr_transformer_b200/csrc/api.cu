@@ -874,6 +874,13 @@ int asr_conv_frontend(const float* spectrum, const float* conv1_w, const float* 
                       static_cast<bf16*>(z_bf16), s);
 }
 
+int asr_spectrogram(const float* audio, int B, int n_samples, int n_fft, int hop, int T, float* spec,
+                    asr_stream_t stream) {
+  if (B == 0) return 0;
+  if (!audio || !spec || B < 0 || n_samples < 0) return set_error(ASR_E_INVALID, "asr_spectrogram: bad argument");
+  return launch_spectrogram(audio, B, n_samples, n_fft, hop, T, spec, static_cast<cudaStream_t>(stream));
+}
+
 int asr_embed_pe(const int32_t* tokens, const float* emb, const float* pe, int B, int L, int D, int vocab, float* out,
                  asr_stream_t stream) {
   if (B == 0 || L == 0) return 0;

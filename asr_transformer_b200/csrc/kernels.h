@@ -87,6 +87,10 @@ int launch_conv1(const float* spec, const float* w1 /*[9][64]*/, const float* b1
 int launch_conv2(const bf16* y1, const bf16* w2 /*[64 co][9][64 ci]*/, const float* b2, int B, int F1, int T1,
                  bf16* z, cudaStream_t s);
 
+// ---- power spectrogram front-end (reference dataset.py:34-35): audio (B, N) -> spec (B,1,n_fft/2+1,T), frames >= the
+// signal's frame count zero-filled
+int launch_spectrogram(const float* audio, int B, int n_samples, int n_fft, int hop, int T, float* spec, cudaStream_t s);
+
 // ---- greedy decode step kernels
 struct DecLinear {
   const float* x = nullptr;      // fp32 [B, K]

@@ -88,6 +88,7 @@ _SIGNATURES = {
     "asr_conv_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "asr_conv_frontend": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                   c_size_t, c_void_p, c_void_p]),
+    "asr_spectrogram": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "asr_embed_pe": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "asr_dec_linear": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                c_int, c_void_p, c_void_p]),

@@ -191,6 +191,13 @@ size_t asr_conv_workspace_bytes(int B, int F, int T);
 int asr_conv_frontend(const float* spectrum, const float* conv1_w, const float* conv1_b, const void* conv2_wfrag,
                       const float* conv2_b, int B, int F, int T, void* ws, size_t ws_bytes, void* z_bf16,
                       asr_stream_t stream);
+/* Power spectrogram, the step before the hot path: replaces torchaudio.transforms.Spectrogram(n_fft,
+ * center=False) of reference modules/dataset.py:34-35,51 (periodic Hann window of n_fft samples, hop = n_fft / 2 in the
+ * reference, power 2, one-sided).  audio fp32 (B, n_samples) -> spec fp32 (B, 1, n_fft/2 + 1, T); frames past
+ * floor((n_samples - n_fft) / hop) + 1 are zero-filled (the dataset's padding, dataset.py:53-55).  n_fft: a power of
+ * two in [64, 2048]. */
+int asr_spectrogram(const float* audio, int B, int n_samples, int n_fft, int hop, int T, float* spec,
+                    asr_stream_t stream);
 /* embedding + positional encoding (model.py:117): out fp32 (B,L,D) */
 int asr_embed_pe(const int32_t* tokens, const float* emb, const float* pe, int B, int L, int D, int vocab, float* out,
                  asr_stream_t stream);
