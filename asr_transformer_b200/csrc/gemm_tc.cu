@@ -25,6 +25,59 @@ constexpr size_t gemm_smem_bytes() {
   return size_t(STAGES) * (A_STAGE_BYTES + BN * BK * 2) + (2 * STAGES + 4) * 8 + 32 + 2 * BN * 4 + 1024;
 }
 
+// Compile-time specialised epilogue of one full, vector-aligned 32-column chunk (the common case): only the loads,
+// math and stores of this GEMM's epilogue are emitted.  FLAGS: 1 bias, 2 relu, 4 positional rowvec, 8 residual,
+// 16 fp32 out, 32 bf16 out.
+enum { EF_BIAS = 1, EF_RELU = 2, EF_PE = 4, EF_RES = 8, EF_F32 = 16, EF_B16 = 32 };
+template <int FLAGS>
+__device__ __forceinline__ void epilogue_chunk_fast(const GemmEpilogue& ep, const uint32_t (&r)[32], int row, int col0,
+                                                    const float* sbias_chunk) {
+  float4 res[8], pe[8];
+  if (FLAGS & EF_RES) {
+    const float4* rp = reinterpret_cast<const float4*>(ep.residual + size_t(row) * ep.ld_res + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) res[j] = rp[j];
+  }
+  if (FLAGS & EF_PE) {
+    const float4* pp = reinterpret_cast<const float4*>(ep.rowvec + size_t(row % ep.rowvec_period) * ep.ld_rowvec + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) pe[j] = __ldg(pp + j);
+  }
+  float* of = (FLAGS & EF_F32) ? ep.out_f32 + size_t(row) * ep.ld_f32 + col0 : nullptr;
+  bf16* ob = (FLAGS & EF_B16) ? ep.out_bf16 + size_t(row) * ep.ld_bf16 + col0 : nullptr;
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[4 * j + i]);
+    if (FLAGS & EF_BIAS) {
+      const float4 b0 = *reinterpret_cast<const float4*>(sbias_chunk + 4 * j);
+      const float4 b1 = *reinterpret_cast<const float4*>(sbias_chunk + 4 * j + 4);
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (FLAGS & EF_RELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (FLAGS & EF_PE) {
+      v[0] += pe[j].x; v[1] += pe[j].y; v[2] += pe[j].z; v[3] += pe[j].w;
+      v[4] += pe[j + 1].x; v[5] += pe[j + 1].y; v[6] += pe[j + 1].z; v[7] += pe[j + 1].w;
+    }
+    if (FLAGS & EF_RES) {
+      v[0] += res[j].x; v[1] += res[j].y; v[2] += res[j].z; v[3] += res[j].w;
+      v[4] += res[j + 1].x; v[5] += res[j + 1].y; v[6] += res[j + 1].z; v[7] += res[j + 1].w;
+    }
+    if (FLAGS & EF_F32) {
+      *reinterpret_cast<float4*>(of + 4 * j) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(of + 4 * j + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (FLAGS & EF_B16)
+      *reinterpret_cast<uint4*>(ob + 4 * j) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
 // sbias: this CTA's bias slice in shared memory (nullptr = no bias), indexed by column - n0
 __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uint32_t (&r)[32], int row, int col0,
                                                int n_store, const float* sbias, int n0) {
@@ -149,7 +202,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
 constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = (EPI_WARPS + 2) * 32;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int FLAGS>   // FLAGS >= 0: the specialised epilogue this launch uses; -1: generic
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
                int M, int n_store, int K, int tiles_n, int n_tiles) {
@@ -253,7 +306,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t r[32];
         tmem_ld32(tmem_base + buf * BN + (uint32_t(quad * 32) << 16) + uint32_t(col), r);
         tmem_ld_wait();
-        if (row < M) epilogue_chunk(ep, r, row, n0 + col, n_store, ep.bias ? sb : nullptr, n0);
+        if (row < M) {
+          const int c0 = n0 + col;
+          if (FLAGS >= 0 && c0 + 32 <= n_store) epilogue_chunk_fast<(FLAGS >= 0 ? FLAGS : 0)>(ep, r, row, c0, sb + col);
+          else epilogue_chunk(ep, r, row, c0, n_store, ep.bias ? sb : nullptr, n0);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -265,10 +322,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 2 * BN);
 }
 
-template <int BN, int STAGES>
-int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int n_store, int n_pad,
-               int K, cudaStream_t s) {
-  auto kern = gemm_tc_kernel<BN, STAGES>;
+template <int BN, int STAGES, int FLAGS>
+int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int n_store, int n_pad,
+                int K, cudaStream_t s) {
+  auto kern = gemm_tc_kernel<BN, STAGES, FLAGS>;
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
   static bool attr_set = false;
   static int n_sm = 0;
@@ -285,6 +342,34 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogu
   ASR_CUDA_OK(cudaGetLastError());
   ASR_LAUNCHED(1);
   return 0;
+}
+
+// pick the compile-time epilogue: the flag combinations of this path's GEMMs when every pointer / leading dimension
+// allows 16-byte accesses, the generic (fully predicated) epilogue otherwise
+template <int BN, int STAGES>
+int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int n_store, int n_pad,
+               int K, cudaStream_t s) {
+  const int flags = (ep.bias ? EF_BIAS : 0) | (ep.relu ? EF_RELU : 0) | (ep.rowvec ? EF_PE : 0) |
+                    (ep.residual ? EF_RES : 0) | (ep.out_f32 ? EF_F32 : 0) | (ep.out_bf16 ? EF_B16 : 0);
+  const bool aligned =
+      (!ep.residual || ((ep.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0))) &&
+      (!ep.out_f32 || ((ep.ld_f32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.out_f32) & 15) == 0))) &&
+      (!ep.out_bf16 || ((ep.ld_bf16 % 8 == 0) && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0))) &&
+      (!ep.rowvec || ((ep.ld_rowvec % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.rowvec) & 15) == 0)));
+  if (aligned) {
+    switch (flags) {
+      case EF_BIAS | EF_B16: return launch_inst<BN, STAGES, EF_BIAS | EF_B16>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+      case EF_BIAS | EF_RELU | EF_B16:
+        return launch_inst<BN, STAGES, EF_BIAS | EF_RELU | EF_B16>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+      case EF_BIAS | EF_RES | EF_F32:
+        return launch_inst<BN, STAGES, EF_BIAS | EF_RES | EF_F32>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+      case EF_BIAS | EF_PE | EF_F32:
+        return launch_inst<BN, STAGES, EF_BIAS | EF_PE | EF_F32>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+      case EF_F32: return launch_inst<BN, STAGES, EF_F32>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+      default: break;
+    }
+  }
+  return launch_inst<BN, STAGES, -1>(tmA, tmB, ep, M, n_store, n_pad, K, s);
 }
 
 __global__ void gemm_naive_kernel(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N, int K,
@@ -322,11 +407,11 @@ int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N,
     if (rc) return rc;
   }
   // Tile choice: 128-wide tiles (2 x 128 TMEM columns), 6-stage TMA ring (192 KB); 64-wide when N is not a multiple
-  // of 128.  ASR_B200_GEMM_TILE (256 / 128 / 64) forces a width for experiments.
+  // of 128.  ASR_B200_GEMM_TILE (128 / 64) forces a width for experiments.
   int bn = (n_pad % 128 == 0) ? 128 : 64;
   if (const char* e = std::getenv("ASR_B200_GEMM_TILE")) {
     const int f = std::atoi(e);
-    if ((f == 256 || f == 128 || f == 64) && n_pad % f == 0) bn = f;
+    if ((f == 128 || f == 64) && n_pad % f == 0) bn = f;
   }
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)n_pad};
@@ -336,7 +421,6 @@ int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N,
     if (rc) return rc;
   }
   switch (bn) {
-    case 256: return launch_one<256, 4>(tmA, tmB, ep, M, n_store, n_pad, K, s);
     case 128: return launch_one<128, 6>(tmA, tmB, ep, M, n_store, n_pad, K, s);
     default: return launch_one<64, 8>(tmA, tmB, ep, M, n_store, n_pad, K, s);
   }
