@@ -140,7 +140,7 @@ def test_stream_matches_per_kernel_step_C2(monkeypatch):
         assert int(nss[b]) == int(nsg[b]) and torch.equal(ss[b], sg[b])
 
 
-@pytest.mark.parametrize("batch,gu", [(5, ""), (64, ""), (70, ""), (9, "8")])
+@pytest.mark.parametrize("batch,gu", [(5, ""), (64, ""), (70, ""), (9, "8"), (200, "")])
 def test_cluster_matches_per_kernel_step_C2(batch, gu, monkeypatch):
     """The cluster kernel (head-parallel CTAs, DSMEM all-reduces) against the per-kernel (graph) step for utterance
     groups of 1, 2, 4 and 8 per cluster, incl. stop_at_eos and a ragged last cluster."""
