@@ -515,9 +515,11 @@ int asr_decoder_forward(AsrHandle* h, const float* enc_out, int B, int Tp, const
   return gemm(w.xn, D, h->w.classifier_w, R, c.vocab_size, D, e, s);
 }
 
-int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, int stop_at_eos,
-                      const int32_t* first_tokens, const int32_t* enc_lens, void* ws, size_t ws_bytes, int32_t* tokens,
-                      int32_t* n_tokens, float* step_logits, asr_stream_t stream) {
+// phases: 1 = prepare (cross-attention K/V of every layer, token / state initialisation), 2 = run (the decode loop on
+// a prepared workspace), 3 = both
+static int decode_greedy_impl(int phases, AsrHandle* h, const float* enc_out, int B, int Tp, int L, int stop_at_eos,
+                              const int32_t* first_tokens, const int32_t* enc_lens, void* ws, size_t ws_bytes,
+                              int32_t* tokens, int32_t* n_tokens, float* step_logits, asr_stream_t stream) {
   if (!h || !h->loaded) return set_error(ASR_E_INVALID, "asr_decode_greedy: weights not loaded");
   if (B == 0) return 0;
   if (!enc_out || !tokens || !ws || B < 0 || Tp <= 0 || L <= 0)
@@ -533,14 +535,17 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
     return set_error(ASR_E_WORKSPACE, "asr_decode_greedy: workspace %zu < %zu bytes", ws_bytes, bump.off);
   const int D = c.embedding_dim, M = B * Tp;
 
-  if (int rc = launch_f32_to_bf16(enc_out, w.enc_bf16, size_t(M) * D, s)) return rc;
-  if (int rc = cross_kv(h, w.enc_bf16, w.ckv, M, s)) return rc;
-  dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, n_tokens, w.finished, w.step, B, L, c.bos_token_id,
-                                               first_tokens);
-  ASR_CUDA_OK(cudaGetLastError());
-  ASR_LAUNCHED(1);
-  if (int rc = launch_dec_embed(tokens, L + 1, w.step, h->w.embedding, h->w.dec_pe, B, D, c.vocab_size, w.h, s))
-    return rc;
+  if (phases & 1) {
+    if (int rc = launch_f32_to_bf16(enc_out, w.enc_bf16, size_t(M) * D, s)) return rc;
+    if (int rc = cross_kv(h, w.enc_bf16, w.ckv, M, s)) return rc;
+    dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, n_tokens, w.finished, w.step, B, L, c.bos_token_id,
+                                                 first_tokens);
+    ASR_CUDA_OK(cudaGetLastError());
+    ASR_LAUNCHED(1);
+    if (int rc = launch_dec_embed(tokens, L + 1, w.step, h->w.embedding, h->w.dec_pe, B, D, c.vocab_size, w.h, s))
+      return rc;
+  }
+  if (!(phases & 2)) return 0;
 
   // Launch mode: "persistent" (default: one cooperative kernel for all L steps), "graph" (one CUDA-graph replay of
   // the 51-kernel step per token) or "eager" (same kernels, launched one by one; bring-up / profiling).
@@ -611,6 +616,27 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
   for (int t = first; t < L; ++t) ASR_CUDA_OK(cudaGraphLaunch(h->graph_exec, s));
   ASR_LAUNCHED(h->graph_kernels * (unsigned long long)(L - first));
   return 0;
+}
+
+int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, int stop_at_eos,
+                      const int32_t* first_tokens, const int32_t* enc_lens, void* ws, size_t ws_bytes, int32_t* tokens,
+                      int32_t* n_tokens, float* step_logits, asr_stream_t stream) {
+  return decode_greedy_impl(3, h, enc_out, B, Tp, L, stop_at_eos, first_tokens, enc_lens, ws, ws_bytes, tokens, n_tokens,
+                            step_logits, stream);
+}
+
+int asr_decode_prepare(AsrHandle* h, const float* enc_out, int B, int Tp, int L, int stop_at_eos,
+                       const int32_t* first_tokens, const int32_t* enc_lens, void* ws, size_t ws_bytes, int32_t* tokens,
+                       int32_t* n_tokens, float* step_logits, asr_stream_t stream) {
+  return decode_greedy_impl(1, h, enc_out, B, Tp, L, stop_at_eos, first_tokens, enc_lens, ws, ws_bytes, tokens, n_tokens,
+                            step_logits, stream);
+}
+
+int asr_decode_run(AsrHandle* h, const float* enc_out, int B, int Tp, int L, int stop_at_eos,
+                   const int32_t* first_tokens, const int32_t* enc_lens, void* ws, size_t ws_bytes, int32_t* tokens,
+                   int32_t* n_tokens, float* step_logits, asr_stream_t stream) {
+  return decode_greedy_impl(2, h, enc_out, B, Tp, L, stop_at_eos, first_tokens, enc_lens, ws, ws_bytes, tokens, n_tokens,
+                            step_logits, stream);
 }
 
 // Same work as asr_decode_greedy, launched eagerly with a CUDA event pair around every kernel; synchronises the

@@ -328,13 +328,15 @@ class Engine:
         return self
 
     # ------------------------------------------------------------------ calls
-    def _ws(self, B: int, T: int, Ldec: int) -> torch.Tensor:
+    def _ws(self, B: int, T: int, Ldec: int, tag: str = "model") -> torch.Tensor:
+        """Scratch for one call.  Calls that may run concurrently on different streams (the pipelined serving loop:
+        encode of batch i+1 under the decode of batch i) must use different tags."""
         n = C.c_size_t()
         _l.check(_l.load().asr_workspace_bytes(self.handle, B, max(T, 7), max(Ldec, 1), C.byref(n)), "workspace_bytes")
-        return _l.workspace(n.value, self.device, "model")
+        return _l.workspace(n.value, self.device, tag)
 
     def encode(self, spectrum: torch.Tensor, enc_lens: Optional[torch.Tensor] = None,
-               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, ws_tag: str = "model") -> torch.Tensor:
         """Transformer.input_layer + Encoder.forward: (B,1,F,T) fp32 -> (B,T',D) fp32."""
         if spectrum.dim() != 4 or spectrum.shape[1] != 1 or spectrum.shape[2] != self.cfg.input_dim:
             raise RuntimeError(f"expected spectrum (B,1,{self.cfg.input_dim},T), got {tuple(spectrum.shape)}")
@@ -343,7 +345,7 @@ class Engine:
         Tp = conv_len(conv_len(T))
         if out is None:
             out = torch.empty(B, Tp, self.cfg.embedding_dim, dtype=torch.float32, device=spectrum.device)
-        ws = self._ws(B, T, self.cfg.decoder_seq_len)
+        ws = self._ws(B, T, self.cfg.decoder_seq_len, ws_tag)
         lens = None if enc_lens is None else enc_lens.to(device=spectrum.device, dtype=torch.int32).contiguous()
         _l.check(_l.load().asr_encode(self.handle, _l.ptr(spectrum), B, T, _l.ptr(lens), _l.ptr(ws), ws.numel(),
                                       _l.ptr(out), _l.stream()), "asr_encode")
@@ -374,7 +376,13 @@ class Engine:
     def decode_greedy(self, enc_out: torch.Tensor, max_len: Optional[int] = None, stop_at_eos: bool = False,
                       first_tokens: Optional[torch.Tensor] = None, want_logits: bool = False,
                       tokens_out: Optional[torch.Tensor] = None, n_tokens_out: Optional[torch.Tensor] = None,
-                      enc_lens: Optional[torch.Tensor] = None):
+                      enc_lens: Optional[torch.Tensor] = None, ws_tag: str = "model", phase: str = "both"):
+        """``phase``: "both" (asr_decode_greedy), "prepare" (cross K/V + state init, returns the call context) or a
+        context returned by "prepare" (runs the decode loop on it: the two halves may sit on different streams)."""
+        if isinstance(phase, dict):
+            ctx = phase
+            _l.check(_l.load().asr_decode_run(*ctx["args"], _l.stream()), "asr_decode_run")
+            return ctx["tokens"], ctx["n_tok"], ctx["step_logits"]
         B, Tp, _ = enc_out.shape
         L = int(max_len or self.cfg.decoder_seq_len)
         enc_out = enc_out.to(torch.float32).contiguous()
@@ -384,8 +392,12 @@ class Engine:
         step_logits = torch.empty(B, L, self.cfg.vocab_size, dtype=torch.float32, device=dev) if want_logits else None
         first = None if first_tokens is None else first_tokens.to(device=dev, dtype=torch.int32).contiguous()
         lens = None if enc_lens is None else enc_lens.to(device=dev, dtype=torch.int32).contiguous()
-        ws = self._ws(B, 4 * Tp + 3, L)
-        _l.check(_l.load().asr_decode_greedy(self.handle, _l.ptr(enc_out), B, Tp, L, int(bool(stop_at_eos)),
-                                             _l.ptr(first), _l.ptr(lens), _l.ptr(ws), ws.numel(), _l.ptr(tokens), _l.ptr(n_tok),
-                                             _l.ptr(step_logits), _l.stream()), "asr_decode_greedy")
+        ws = self._ws(B, 4 * Tp + 3, L, ws_tag)
+        args = (self.handle, _l.ptr(enc_out), B, Tp, L, int(bool(stop_at_eos)), _l.ptr(first), _l.ptr(lens), _l.ptr(ws),
+                ws.numel(), _l.ptr(tokens), _l.ptr(n_tok), _l.ptr(step_logits))
+        if phase == "prepare":
+            _l.check(_l.load().asr_decode_prepare(*args, _l.stream()), "asr_decode_prepare")
+            return {"args": args, "tokens": tokens, "n_tok": n_tok, "step_logits": step_logits,
+                    "keep": (enc_out, first, lens, ws)}
+        _l.check(_l.load().asr_decode_greedy(*args, _l.stream()), "asr_decode_greedy")
         return tokens, n_tok, step_logits

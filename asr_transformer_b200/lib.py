@@ -68,6 +68,10 @@ _SIGNATURES = {
                                     c_void_p, c_void_p]),
     "asr_decode_greedy": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "asr_decode_prepare": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "asr_decode_run": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                               c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "asr_decode_profile": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),
     "asr_launch_count": (C.c_ulonglong, []),

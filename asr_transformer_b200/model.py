@@ -208,30 +208,26 @@ class Transformer(nn.Module):
         return (tokens, n_tok, step_logits) if return_logits else (tokens, n_tok)
 
     def greedy_decode_batches(self, batches, max_len: Optional[int] = None, stop_at_eos: bool = False,
-                              gather=None):
-        """Pipelined greedy ASR over an iterable of HOST batches ((B,1,F,T) fp32, ideally pinned): the upload of batch
-        i+1 and the download of batch i-1's transcripts run on side streams under the decode of batch i, so a serving
-        loop is bound by the GPU, not by PCIe.  Yields (tokens (B,L+1) int32, n_tokens (B,) int32) as CPU tensors,
-        in order.  ``gather`` (optional callable (tokens, n_tokens) -> (tokens, n_tokens)) runs on the device before
-        the download, e.g. ``parallel.gather_tokens`` for the multi-GPU transcript gather."""
+                              gather=None, to_host: bool = True):
+        """Pipelined greedy ASR over an iterable of batches ((B,1,F,T) fp32; HOST tensors, ideally pinned, or tensors
+        already on the device).  Four streams keep every engine busy: the upload of batch i+1, the ENCODER of batch i+1
+        (it runs on the SMs the decoder leaves idle: the cluster decoder occupies num_heads x ceil(B / group) SMs and
+        is latency-bound, so the two overlap), the decoder of batch i (high priority), and the download of batch i-1's
+        transcripts.  Yields (tokens (B,L+1) int32, n_tokens (B,) int32) in order: CPU tensors (``to_host``) or device
+        tensors.  ``gather`` (optional callable (tokens, n_tokens) -> (tokens, n_tokens)) runs on the device before the
+        download, e.g. ``parallel.gather_tokens`` for the multi-GPU transcript gather."""
         _require_eval(self)
         from collections import deque
         dev = next(self.parameters()).device
-        main = torch.cuda.current_stream(dev)
+        eng = self._eng()
         streams = self.__dict__.setdefault("_side_streams", {})   # persistent: the caching allocator pools blocks per
         if dev not in streams:                                     # stream, fresh streams would mean fresh cudaMallocs
-            streams[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
-        up_s, down_s = streams[dev]
-
-        def upload(x):
-            if x is None:
-                return None
-            with torch.cuda.stream(up_s):
-                d = x.to(dev, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(up_s)
-            return d, ev
-
+            streams[dev] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev),
+                            torch.cuda.Stream(dev, priority=-1))
+        up_s, down_s, enc_s, dec_s = streams[dev]
+        caller = torch.cuda.current_stream(dev)
+        for st in (up_s, enc_s, dec_s):
+            st.wait_stream(caller)                                 # inputs produced on the caller's stream
         staging = self.__dict__.setdefault("_pinned_staging", {})   # pinned D2H buffers live with the model:
         # cudaHostAlloc costs milliseconds, so they are allocated once per shape and reused by every call
 
@@ -241,37 +237,79 @@ class Transformer(nn.Module):
                 staging[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             return staging[key]
 
+        def stage_in(x):
+            """H2D (if needed) on the upload stream, then the front-end + encoder on the encoder stream."""
+            if x is None:
+                return None
+            if not x.is_cuda:
+                with torch.cuda.stream(up_s):
+                    x = x.to(dev, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(up_s)
+                enc_s.wait_event(ev)
+            x.record_stream(enc_s)
+            with torch.cuda.stream(enc_s):
+                enc = eng.encode(x, ws_tag="pipe_enc")
+                # cross-attention K/V + decoder state of this batch: also under the previous batch's decode loop.  Two
+                # decode workspaces alternate; a slot is reused only after the decode that last ran on it has finished.
+                slot = n_in[0] & 1
+                if ws_done[slot] is not None:
+                    enc_s.wait_event(ws_done[slot])
+                ctx = eng.decode_greedy(enc, max_len, stop_at_eos, ws_tag="pipe_dec%d" % slot, phase="prepare")
+                ctx["slot"] = slot
+                n_in[0] += 1
+                ev = torch.cuda.Event()
+                ev.record(enc_s)
+            return ctx, ev
+
+        n_in = [0]
+        ws_done = [None, None]
         it = iter(batches)
-        nxt = upload(next(it, None))
+        nxt = stage_in(next(it, None))
         pending = deque()
         step = 0
         while nxt is not None:
-            cur, ev = nxt
-            nxt = upload(next(it, None))          # next batch's H2D overlaps this batch's compute
-            main.wait_event(ev)
-            cur.record_stream(main)
-            tokens, n_tok = self.greedy_decode(cur, max_len=max_len, stop_at_eos=stop_at_eos)
-            if gather is not None:
-                tokens, n_tok = gather(tokens, n_tok)
-            done = torch.cuda.Event()
-            done.record(main)
-            with torch.cuda.stream(down_s):
-                down_s.wait_event(done)
-                th, nh = pinned(tokens, (step % 3, 0)), pinned(n_tok, (step % 3, 1))
-                th.copy_(tokens, non_blocking=True)
-                nh.copy_(n_tok, non_blocking=True)
-                fin = torch.cuda.Event()
-                fin.record(down_s)
-            tokens.record_stream(down_s)
-            n_tok.record_stream(down_s)
-            pending.append((th, nh, fin))
+            ctx, ev = nxt
+            dec_s.wait_event(ev)
+            for t in (ctx["keep"][0], ctx["tokens"], ctx["n_tok"]):
+                t.record_stream(dec_s)
+            with torch.cuda.stream(dec_s):
+                tokens, n_tok, _ = eng.decode_greedy(None, phase=ctx)
+                if gather is not None:
+                    tokens, n_tok = gather(tokens, n_tok)
+                done = torch.cuda.Event()
+                done.record(dec_s)
+            ws_done[ctx["slot"]] = done
+            nxt = stage_in(next(it, None))            # next batch: upload + encoder under this batch's decode
+            if to_host:
+                with torch.cuda.stream(down_s):
+                    down_s.wait_event(done)
+                    th, nh = pinned(tokens, (step % 3, 0)), pinned(n_tok, (step % 3, 1))
+                    th.copy_(tokens, non_blocking=True)
+                    nh.copy_(n_tok, non_blocking=True)
+                    fin = torch.cuda.Event()
+                    fin.record(down_s)
+                tokens.record_stream(down_s)
+                n_tok.record_stream(down_s)
+                pending.append((th, nh, fin))
+            else:
+                tokens.record_stream(caller)
+                n_tok.record_stream(caller)
+                pending.append((tokens, n_tok, done))
             step += 1
             if len(pending) > 1:
                 a, b, e = pending.popleft()
-                e.synchronize()
-                yield a.clone(), b.clone()
+                if to_host:
+                    e.synchronize()
+                    yield a.clone(), b.clone()
+                else:
+                    caller.wait_event(e)
+                    yield a, b
         while pending:
             a, b, e = pending.popleft()
-            e.synchronize()
-            yield a.clone(), b.clone()
-
+            if to_host:
+                e.synchronize()
+                yield a.clone(), b.clone()
+            else:
+                caller.wait_event(e)
+                yield a, b

@@ -147,6 +147,17 @@ int asr_decode_greedy(AsrHandle* h, const float* enc_out, int B, int Tp, int L, 
                       void* ws, size_t ws_bytes, int32_t* tokens, int32_t* n_tokens, float* step_logits,
                       asr_stream_t stream);
 
+/* asr_decode_greedy in two halves, for pipelined serving: asr_decode_prepare computes the cross-attention K/V of every
+ * layer from enc_out and initialises tokens / decoder state in the workspace; asr_decode_run runs the decode loop on a
+ * workspace prepared with the same arguments.  The halves may be enqueued on different streams (ordered by an event),
+ * so the prepare of batch i+1 can overlap the run of batch i on a second workspace. */
+int asr_decode_prepare(AsrHandle* h, const float* enc_out, int B, int Tp, int L, int stop_at_eos,
+                       const int32_t* first_tokens, const int32_t* enc_lens, void* ws, size_t ws_bytes, int32_t* tokens,
+                       int32_t* n_tokens, float* step_logits, asr_stream_t stream);
+int asr_decode_run(AsrHandle* h, const float* enc_out, int B, int Tp, int L, int stop_at_eos,
+                   const int32_t* first_tokens, const int32_t* enc_lens, void* ws, size_t ws_bytes, int32_t* tokens,
+                   int32_t* n_tokens, float* step_logits, asr_stream_t stream);
+
 /* Profiling aid for bench.py: the same decode launched eagerly with a CUDA-event pair around every kernel.
  * Synchronises `stream` before returning.  ms_per_class / launches_per_class: 12 entries in the order
  * {qkv linear, self attention, out projections, cross q linear, cross attention, ffn1, ffn2, classifier, select}
