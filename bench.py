@@ -52,6 +52,11 @@ def parse():
     return ap.parse_args()
 
 
+def coalesce_of(batch):
+    """Batches per decode launch chosen by Transformer.greedy_decode_batches (coalesce=None)."""
+    return max(1, min(4, 128 // max(1, batch)))
+
+
 def workload_desc(cfg, batch, n_gpus):
     return {
         "workload": f"{cfg.name}: repo-default Speech-Transformer ({cfg.encoder_num_layers} enc / "
@@ -61,7 +66,11 @@ def workload_desc(cfg, batch, n_gpus):
         "batch_per_gpu": batch, "global_batch": batch * n_gpus, "frames": cfg.frames,
         "encoder_frames": cfg.encoder_seq_len, "decode_steps": cfg.decoder_seq_len,
         "l2": "inputs rotate over 8 distinct device-resident batches (164 MB > 126 MB L2), no flush: consecutive steps "
-              "overlap (encoder of step i+1 under the decoder of step i); the serial pass in phase_ms flushes L2",
+              "overlap (encoder of the next steps under the decoder of the current ones); the serial pass in phase_ms "
+              "flushes L2",
+        "coalesce": "the serving loop (Transformer.greedy_decode_batches) decodes %d consecutive steps' batches per "
+                    "launch (%d utterances = 4 per CTA cluster); every step's batch is fully processed and returned "
+                    "separately" % (coalesce_of(batch), coalesce_of(batch) * batch),
         "parallelism": f"dp{n_gpus}: utterance sharding, one process per GPU, no collective on the compute path, "
                        "final all_gather of token ids",
     }
@@ -110,13 +119,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def measured_traffic(kernel):
+def measured_traffic(kernel, utterances):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json:
-    {kernel: {"dram_bytes": ..., "source": ...}}); None when no capture of this kernel has been committed."""
+    {kernel: {"dram_bytes": ..., "utterances": ..., "source": ...}}); None when no capture of this kernel at this
+    launch size has been committed."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         d = json.load(open(p)).get(kernel)
-        if d:
+        if d and d.get("utterances", 64) == utterances:
             return d.get("dram_bytes")
     return None
 
@@ -350,14 +360,19 @@ def main():
         print(json.dumps(result))
     elif rank == 0:
         # -------------------------------------------------------------- roofline of the dominant kernel
-        ws = eng._ws(batch, 4 * cfg.encoder_seq_len + 3, cfg.decoder_seq_len)
+        # the decode launch of the timed region covers `co` coalesced batches: profile that launch
+        co = coalesce_of(batch)
+        pb = co * batch
+        enc_p = enc if co == 1 else torch.cat([eng.encode(spec_rot[i % N_ROT]) for i in range(co)], 0)
+        tokens_p = torch.empty(pb, cfg.decoder_seq_len + 1, dtype=torch.int32, device=dev)
+        ws = eng._ws(pb, 4 * cfg.encoder_seq_len + 3, cfg.decoder_seq_len)
         ms_cls = (C.c_float * 12)()
         n_cls = (C.c_int32 * 12)()
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        phase = torch.zeros(3 * max(n_sm, 148, batch, 256), 16, dtype=torch.int64, device=dev)
+        phase = torch.zeros(3 * max(n_sm, 148, pb, 256), 16, dtype=torch.int64, device=dev)
         for _ in range(2):     # second pass is the measured one (first warms caches / clocks)
-            L.check(lib.asr_decode_profile(eng.handle, L.ptr(enc), batch, cfg.encoder_seq_len, cfg.decoder_seq_len,
-                                           L.ptr(ws), ws.numel(), L.ptr(tokens), ms_cls, n_cls, L.ptr(phase),
+            L.check(lib.asr_decode_profile(eng.handle, L.ptr(enc_p), pb, cfg.encoder_seq_len, cfg.decoder_seq_len,
+                                           L.ptr(ws), ws.numel(), L.ptr(tokens_p), ms_cls, n_cls, L.ptr(phase),
                                            L.stream()), "asr_decode_profile")
         ph = phase.double().cpu()
         cp = ph[2 * 148:2 * 148 + 148]
@@ -373,7 +388,7 @@ def main():
                                                        for i, n in enumerate(names_c)}
         mhz = clocks.get("sm_mhz") or 1965.0
         hbm_peak, tf_peak, peak_src = measured_peaks()
-        bytes_cls = decode_class_bytes(cfg, batch)
+        bytes_cls = decode_class_bytes(cfg, pb)
         prof = {}
         tot = sum(ms_cls[:9])
         for i, name in enumerate(DEC_CLASSES):
@@ -395,10 +410,11 @@ def main():
             ms_cls[9] = ms_cls[slot]
             gbs = decode_bytes / (ms_cls[9] * 1e-3) / 1e9
             kname = {9: "dec_persistent_kernel", 10: "dec_stream_kernel", 11: "dec_cluster_kernel"}[slot]
-            result["roofline"] = {"kernel": kname + " (all %d decode steps, one launch)" % cfg.decoder_seq_len,
+            result["roofline"] = {"kernel": kname + " (all %d decode steps of %d utterances, one launch)"
+                                            % (cfg.decoder_seq_len, pb),
                                   "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
                                   "frac": round(gbs / hbm_peak, 4),
-                                  "traffic": measured_traffic(kname) if (args.workload == WORKLOAD and batch == cfg.batch) else None,
+                                  "traffic": measured_traffic(kname, pb) if args.workload == WORKLOAD else None,
                                   "peak_source": peak_src,
                                   "alg_bytes_per_launch": int(decode_bytes), "ms_per_launch": round(ms_cls[9], 3)}
         else:

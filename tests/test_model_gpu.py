@@ -251,6 +251,22 @@ def test_pipelined_batches_match_single_calls(t0):
     assert list(m.greedy_decode_batches([])) == []
 
 
+@pytest.mark.parametrize("coalesce", [1, 2, 3])
+def test_coalesced_batches_match_single_calls(t0, coalesce):
+    """Coalescing consecutive batches into one decode launch (serving throughput) never changes an utterance's tokens:
+    host and device inputs, groups cut by the limit, by a shape change and by the end of the stream."""
+    cfg, fx, m, spec = t0
+    xs = [spec, spec.flip(0), spec.roll(1, 0), spec[:3], spec[:3].flip(0), spec]
+    ref = [m.greedy_decode(x.to(DEV)) for x in xs]
+    for place in ("host", "device"):
+        ins = [x.cpu().pin_memory() if place == "host" else x.to(DEV) for x in xs]
+        outs = list(m.greedy_decode_batches(ins, coalesce=coalesce, to_host=(place == "host")))
+        assert len(outs) == len(xs)
+        for (t_ref, n_ref), (tok, n) in zip(ref, outs):
+            assert tok.is_cuda == (place == "device")
+            assert torch.equal(tok.cpu(), t_ref.cpu()) and torch.equal(n.cpu(), n_ref.cpu())
+
+
 def test_key_padding_end_to_end_decode(t0):
     """Masks on, end to end: a zero-padded utterance decoded with its length gives the tokens of
     the unpadded utterance decoded alone (encoder self attention and decoder cross attention both ignore the padding)."""
