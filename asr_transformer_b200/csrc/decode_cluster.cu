@@ -117,7 +117,8 @@ struct Shape {
   static constexpr int H = H_, CS = H_, D = 64 * H_, FFS = FFS_, VS = VS_, GUP = GUP_;
   static constexpr int RPS = (STAGE_BYTES / 128) / GUP;   // key rows per utterance slot per ring stage (K or V rows)
   static constexpr int WPU = NCW / GUP;                   // attention warps per utterance slot
-  static constexpr int SC = 2;                            // K stages per super-chunk (softmax granularity)
+  static constexpr int SC = 2;                            // K stages per super-chunk (softmax granularity), self attention
+  static constexpr int SCX = GUP >= 4 ? 4 : 2;            // ... cross attention: one super-chunk covers 256 encoder frames
   static constexpr int TPW = (RPS / 16) / WPU;            // 16-key tiles per warp per stage
   static constexpr int SMALL_FLOATS = 256 + FFS + 11 * D;   // ... | ln1 | ln2 | ln3 | ln1 of the NEXT layer
   static constexpr uint32_t SMALL_BYTES = (SMALL_FLOATS * 4 + 127) / 128 * 128;
@@ -520,23 +521,30 @@ __device__ __forceinline__ void qk_tile(uint32_t kbase, int n_valid, const uint3
   sa = (tg == 0 && g < n_valid) ? (sc[0][0] + sc[1][0]) + (sc[0][1] + sc[1][1]) : -INFINITY;        // key g (lanes tg == 0)
   sb = (tg == 0 && g + 8 < n_valid) ? (sc[0][2] + sc[1][2]) + (sc[0][3] + sc[1][3]) : -INFINITY;    // key g + 8
 }
-// B fragment of the probabilities: lane (g, tg) holds keys 2tg, 2tg+1 (b0) and 2tg+8, 2tg+9 (b1) of column g
-// (0 = bf16 hi part, 1 = lo part)
-__device__ __forceinline__ void p_frags(float pa, float pb, uint32_t& b0, uint32_t& b1) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
-  const float p0 = __shfl_sync(0xffffffffu, pa, 8 * tg), p1 = __shfl_sync(0xffffffffu, pa, 8 * tg + 4);
-  const float p2 = __shfl_sync(0xffffffffu, pb, 8 * tg), p3 = __shfl_sync(0xffffffffu, pb, 8 * tg + 4);
-  const __nv_bfloat162 h01 = __floats2bfloat162_rn(p0, p1), h23 = __floats2bfloat162_rn(p2, p3);
-  b0 = 0;
-  b1 = 0;
-  if (g == 0) {
-    b0 = *reinterpret_cast<const uint32_t*>(&h01);
-    b1 = *reinterpret_cast<const uint32_t*>(&h23);
-  } else if (g == 1) {
-    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-    b0 = pack_bf16x2(p0 - f01.x, p1 - f01.y);
-    b1 = pack_bf16x2(p2 - f23.x, p3 - f23.y);
-  }
+// exp2 on the SFU (ex2.approx.ftz: 2 ulp, -inf -> +0); the library exp2f costs three more instructions per value
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// p -> (bf16 hi part) | (bf16 lo part) << 16 with hi + lo == p to 2^-17 relative
+__device__ __forceinline__ uint32_t hilo_pack(float p) {
+  const float r = p - __bfloat162float(__float2bfloat16_rn(p));
+  uint32_t x;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(r), "f"(p));   // upper half = bf16(r), lower half = bf16(p)
+  return x;
+}
+// B fragment of the probabilities: lane (g, tg) holds keys 2tg, 2tg+1 (b0) and 2tg+8, 2tg+9 (b1) of column g.  Column
+// 0 carries the bf16 hi parts, column 1 the lo parts; the other columns are never read (they repeat hi / lo by the
+// parity of g, so no lane needs a zero).  xa / xb: hilo_pack of the probabilities of keys g / g + 8 (lanes tg == 0).
+// Always called by the whole warp, outside data-dependent branches (plain SHFL, no divergence guards).
+__device__ __forceinline__ void p_frags(uint32_t xa, uint32_t xb, uint32_t& b0, uint32_t& b1) {
+  const int lane = threadIdx.x & 31, tg = lane & 3;
+  const uint32_t sel = (lane & 4) ? 0x7632u : 0x5410u;
+  const uint32_t a0 = __shfl_sync(0xffffffffu, xa, 8 * tg), a1 = __shfl_sync(0xffffffffu, xa, 8 * tg + 4);
+  const uint32_t c0 = __shfl_sync(0xffffffffu, xb, 8 * tg), c1 = __shfl_sync(0xffffffffu, xb, 8 * tg + 4);
+  b0 = __byte_perm(a0, a1, sel);
+  b1 = __byte_perm(c0, c1, sel);
 }
 template <bool SINGLE>
 __device__ __forceinline__ void pv_tile(AttnT& st, uint32_t vbase, uint32_t b0, uint32_t b1, int swz = 0) {
@@ -552,117 +560,94 @@ __device__ __forceinline__ void pv_tile(AttnT& st, uint32_t vbase, uint32_t b0, 
 }
 // Attention of this warp's utterance slot `au` over n_keys rows streamed through the ring as super-chunks of up to SC
 // K stages followed by the matching V stages ([utterance slot][RPS rows][128 B] each); warp partition `apart` owns
-// tiles 2 apart, 2 apart + 1 of every stage.  All scores of a super-chunk are computed first (independent MMAs), then
-// ONE max / exp / sum, then all P V products: one softmax dependency chain per super-chunk instead of one per tile.
-// cur_kb != 0: additionally the single current row (k_t at cur_kb, v_t at cur_kb + 128), merged into the first chunk.
-// n_keys rows are streamed (uniform over the CTA); only the first n_mine of them are valid keys of THIS warp's
-// utterance (key-padding: cross attention with encoder lengths), the rest are masked.
-template <class S, class Mk>
+// tiles TPW apart .. TPW apart + TPW - 1 of every stage.  All scores of a super-chunk are computed first (independent
+// MMAs), then ONE max / exp / sum, then all P V products: one softmax dependency chain per super-chunk instead of one
+// per tile.  HAS_CUR: additionally the single current row (k_t at cur_kb, v_t at cur_kb + 128; cur_kb == 0 for the
+// warps that do not own it), merged into the first chunk.  n_keys rows are streamed (uniform over the CTA); only the
+// first n_mine of them are valid keys of THIS warp's utterance (key padding: cross attention with encoder lengths), the
+// rest are masked.  Control flow: stage presence (s < ns) is CTA-uniform; the shuffles of the softmax sit outside every
+// thread-dependent branch (masked tiles carry score -inf -> p = 0), only ldmatrix / MMA blocks are skipped per tile.
+template <class S, int SC, bool HAS_CUR>
 __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t (&qf)[8], int n_keys, int n_mine,
-                                          bool active, int au, int apart, uint32_t cur_kb, int cur_swz, Mk&& mk) {
-  constexpr int RPS = S::RPS, SC = S::SC, TPW = S::TPW;
-  float ca = -INFINITY, cb = -INFINITY;
-  bool cur = cur_kb != 0;
-  if (cur) qk_tile<true>(cur_kb, 1, qf, ca, cb, cur_swz);
+                                          bool active, int au, int apart, uint32_t cur_kb, int cur_swz) {
+  constexpr int RPS = S::RPS, TPW = S::TPW;
+  float ca = -INFINITY;
+  bool cur = HAS_CUR && cur_kb != 0;
+  if (HAS_CUR) {
+    float cb;
+    if (cur) qk_tile<true>(cur_kb, 1, qf, ca, cb, cur_swz);
+  }
   const uint32_t slot_off = au * RPS * 128 + apart * (TPW * 2048);
+  int c0 = 0;
 #pragma unroll 1
-  for (int c0 = 0; c0 < n_keys; c0 += SC * RPS) {
-    const int nk = min(SC * RPS, n_keys - c0);
+  do {
+    const int nk = min(SC * RPS, n_keys - c0);                  // CTA-uniform
     const int ns = (nk + RPS - 1) / RPS;
+    const int lim = active ? min(nk, n_mine - c0) - 16 * TPW * apart : 0;   // my valid rows from my first tile of stage 0
     float sa[SC][TPW], sb[SC][TPW];
-    bool tv[SC][TPW];                                            // tile has valid keys (warp-uniform)
-    float mx = fmaxf(ca, cb);
+    float mx = ca;
 #pragma unroll
     for (int s = 0; s < SC; ++s) {
 #pragma unroll
-      for (int j = 0; j < TPW; ++j) {
-        sa[s][j] = sb[s][j] = -INFINITY;
-        tv[s][j] = false;
-      }
+      for (int j = 0; j < TPW; ++j) sa[s][j] = sb[s][j] = -INFINITY;
       if (s < ns) {
         const uint32_t stg = smem_u32(c.acquire()) + slot_off;
-        const int n = min(RPS, min(nk, n_mine - c0) - s * RPS) - 16 * TPW * apart;   // valid rows at / after my first tile
-        if (active) {
+        const int n = lim - s * RPS;
 #pragma unroll
-          for (int j = 0; j < TPW; ++j)
-            if (n > 16 * j) {
-              tv[s][j] = true;
-              qk_tile<false>(stg + j * 2048, min(16, n - 16 * j), qf, sa[s][j], sb[s][j]);
-              mx = fmaxf(mx, fmaxf(sa[s][j], sb[s][j]));
-            }
-        }
+        for (int j = 0; j < TPW; ++j)
+          if (n > 16 * j) {
+            qk_tile<false>(stg + j * 2048, n - 16 * j, qf, sa[s][j], sb[s][j]);
+            mx = fmaxf(mx, fmaxf(sa[s][j], sb[s][j]));
+          }
         c.release();
       }
     }
-    mk(0);
-    const float m_new = fmaxf(st.m, warp_max(mx));
-    uint32_t pb0[SC][TPW], pb1[SC][TPW], cb0 = 0, cb1 = 0;
-    if (m_new != -INFINITY) {                                    // warp-uniform; false only for a warp without keys
-      const float alpha = exp2f(st.m - m_new);
-      float lsum = 0.f;
+    // scores live in the lanes tg == 0 (-inf elsewhere): fold the 8 key rows, then broadcast
 #pragma unroll
-      for (int s = 0; s < SC; ++s)
+    for (int o = 16; o >= 4; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float m_new = fmaxf(st.m, __shfl_sync(0xffffffffu, mx, 0));
+    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;     // a warp without any key: every p = ex2(-inf) = 0
+    const float alpha = ex2(st.m - m_use);
+    float lsum = 0.f;
+    uint32_t pb0[SC][TPW], pb1[SC][TPW], cb0 = 0, cb1 = 0;
+#pragma unroll
+    for (int s = 0; s < SC; ++s)
+      if (s < ns) {
 #pragma unroll
         for (int j = 0; j < TPW; ++j) {
-          pb0[s][j] = pb1[s][j] = 0;
-          if (tv[s][j]) {
-            const float pa = exp2f(sa[s][j] - m_new), pb = exp2f(sb[s][j] - m_new);
-            lsum += pa + pb;
-            p_frags(pa, pb, pb0[s][j], pb1[s][j]);
-          }
+          const float pa = ex2(sa[s][j] - m_use), pb = ex2(sb[s][j] - m_use);
+          lsum += pa + pb;
+          p_frags(hilo_pack(pa), hilo_pack(pb), pb0[s][j], pb1[s][j]);
         }
-      if (cur) {
-        const float pa = exp2f(ca - m_new);
-        lsum += pa;
-        p_frags(pa, 0.f, cb0, cb1);
       }
-      st.l = st.l * alpha + lsum;
-      st.m = m_new;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) st.o[i][j] *= alpha;
-    } else {
-#pragma unroll
-      for (int s = 0; s < SC; ++s)
-#pragma unroll
-        for (int j = 0; j < TPW; ++j) pb0[s][j] = pb1[s][j] = 0;
+    if (HAS_CUR) {
+      const float pa = ex2(ca - m_use);
+      lsum += pa;
+      p_frags(hilo_pack(pa), 0u, cb0, cb1);
     }
-    mk(1);
-#pragma unroll
-    for (int s = 0; s < SC; ++s) {
-      if (s < ns) {
-        const uint32_t stg = smem_u32(c.acquire()) + slot_off;
-        const int n = min(RPS, min(nk, n_mine - c0) - s * RPS) - 16 * TPW * apart;
-        if (active) {
-#pragma unroll
-          for (int j = 0; j < TPW; ++j)
-            if (tv[s][j]) pv_tile<false>(st, stg + j * 2048, pb0[s][j], pb1[s][j]);
-        }
-        c.release();
-      }
-    }
-    if (cur) {
-      if (m_new != -INFINITY) pv_tile<true>(st, cur_kb + 128, cb0, cb1, cur_swz);
-      cur = false;
-      ca = -INFINITY;
-    }
-    mk(2);
-  }
-  if (cur) {   // no cached keys at all (first step): the current row alone
-    const float m_new = fmaxf(st.m, warp_max(ca));
-    const float alpha = exp2f(st.m - m_new);
-    const float pa = exp2f(ca - m_new);
-    uint32_t b0, b1;
-    p_frags(pa, 0.f, b0, b1);
-    st.l = st.l * alpha + pa;
+    st.l = st.l * alpha + lsum;
     st.m = m_new;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) st.o[i][j] *= alpha;
-    pv_tile<true>(st, cur_kb + 128, b0, b1, cur_swz);
-  }
+#pragma unroll
+    for (int s = 0; s < SC; ++s)
+      if (s < ns) {
+        const uint32_t stg = smem_u32(c.acquire()) + slot_off;
+        const int n = lim - s * RPS;
+#pragma unroll
+        for (int j = 0; j < TPW; ++j)
+          if (n > 16 * j) pv_tile<false>(st, stg + j * 2048, pb0[s][j], pb1[s][j]);
+        c.release();
+      }
+    if (HAS_CUR) {
+      if (cur) pv_tile<true>(st, cur_kb + 128, cb0, cb1, cur_swz);
+      cur = false;
+      ca = -INFINITY;
+    }
+    c0 += SC * RPS;
+  } while (c0 < n_keys);
 }
 // merge the key partitions of every utterance slot and emit o (bf16 hi + lo rows, stride 96 elements)
 template <class S>
@@ -690,7 +675,7 @@ __device__ __forceinline__ void attn_finish(AttnT& st, int GU, float* part_buf, 
 #pragma unroll
     for (int pI = 0; pI < S::WPU; ++pI) {
       const float mw = stat[pI * S::GUP + uu];
-      const float f = (mw == -INFINITY) ? 0.f : exp2f(mw - mm);
+      const float f = (mw == -INFINITY) ? 0.f : ex2(mw - mm);
       t += part_buf[(pI * S::GUP + uu) * 64 + dd] * f;
       ls += stat[NCW + pI * S::GUP + uu] * f;
     }
@@ -817,8 +802,8 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
           }
           pr.mat<MWo>(img + p.off_wo, pol_w);
           pr.mat<MWqc>(img + p.off_wqc, pol_w);
-          for (int c0 = 0; c0 < p.Tp; c0 += S::SC * RPS) {   // encoder K/V of this head: 2-D boxes [RPS rows][64 columns]
-            const int nk = min(S::SC * RPS, p.Tp - c0);
+          for (int c0 = 0; c0 < p.Tp; c0 += S::SCX * RPS) {   // encoder K/V of this head: 2-D boxes [RPS rows][64 columns]
+            const int nk = min(S::SCX * RPS, p.Tp - c0);
             for (int kv = 0; kv < 2; ++kv)
               for (int r0 = 0; r0 < nk; r0 += RPS) {
                 uint8_t* dst = pr.begin(uint32_t(GU) * RPS * 128u);
@@ -1022,22 +1007,21 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
         uint32_t qf[8];
         attn_init(st);
         attn_q_frags(q_hi, q_lo, au, qf);
-        mark(6);
-        attention<S>(c, st, qf, t, t, a_active, au, apart,
-                     (a_active && apart == S::WPU - 1) ? smem_u32(kv_row) + au * 256 : 0u, t & 7,
-                     [&](int i) { mark(7 + i); });
+        attention<S, S::SC, true>(c, st, qf, t, t, a_active, au, apart,
+                                  (a_active && apart == S::WPU - 1) ? smem_u32(kv_row) + au * 256 : 0u, t & 7);
         if (tid < GU * 2) bulk_store_wait();                  // this step's cache rows are written (published below)
-        mark(10);
+        mark(3);
         attn_finish<S>(st, GU, part_buf, stat, o_hi, o_lo);   // (two consumer barriers inside)
         if (tid == 0) {                                       // cache row t of this layer is published
           __threadfence_block();
           ctrl[2] = t * p.nd + l + 1;
         }
-        mark(3);
+        mark(4);
         mm_stream<MWo, GUP>(c, reinterpret_cast<const uint8_t*>(o_hi), reinterpret_cast<const uint8_t*>(o_lo), S::LDO,
                             scratch, send_partial);
+        mark(5);
         all_reduce_finish(b_o, ln + 2 * D, ln + 3 * D);       // out projection + residual (model.py:68) -> LN2 (:70)
-        mark(4);
+        mark(6);
 
         // ---- cross-attention query -> attention over the encoder K/V, never masked (model.py:70-71)
         mm_stream<MWqc, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
@@ -1045,14 +1029,18 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
           q_store(q_hi, q_lo, u0 + 1, n, (v1 + b_qc[n]) * qscale);
         });
         consumer_sync();
-        mark(5);
+        mark(7);
         attn_init(st);
         attn_q_frags(q_hi, q_lo, au, qf);
-        attention<S>(c, st, qf, p.Tp, n_cross, a_active, au, apart, 0u, 0, [](int) {});
+        attention<S, S::SCX, false>(c, st, qf, p.Tp, n_cross, a_active, au, apart, 0u, 0);
+        mark(8);
         attn_finish<S>(st, GU, part_buf, stat, o_hi, o_lo);
+        mark(4);
         mm_stream<MWo, GUP>(c, reinterpret_cast<const uint8_t*>(o_hi), reinterpret_cast<const uint8_t*>(o_lo), S::LDO,
                             scratch, send_partial);
+        mark(5);
         all_reduce_finish(b_oc, ln + 4 * D, ln + 5 * D);      // -> LN3 (model.py:73)
+        mark(6);
 
         // ---- FFN: squeeze rows of this CTA + ReLU, then the matching K-slice of unsqueeze (model.py:73-74)
         mm_stream<MW1, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
@@ -1064,12 +1052,14 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
           hid_lo[(u0 + 1) * (FFS + 32) + n] = __float2bfloat16(y1 - __bfloat162float(h1));
         });
         consumer_sync();
+        mark(9);
         mm_stream<MW2, GUP>(c, reinterpret_cast<const uint8_t*>(hid_hi), reinterpret_cast<const uint8_t*>(hid_lo),
                             S::LDH, scratch, send_partial);
+        mark(10);
         // -> LN1 of the next layer (its parameters travel in this layer's block), or the classifier's plain split
         if (l + 1 < p.nd) all_reduce_finish(b_2, ln + 6 * D, ln + 7 * D);
         else all_reduce_finish(b_2, nullptr, nullptr);
-        mark(5);
+        mark(6);
       }
 
       // ---- classifier WITHOUT the final LayerNorm (model.py:142): VS vocabulary rows per CTA

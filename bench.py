@@ -382,8 +382,8 @@ def main():
                                                  enumerate(["total", "ring_wait", "exchange_wait", "producer_wait_empty",
                                                             "stages_total"])}
             result["cluster_ctas"] = int(len(cp))
-            names_c = ["small_params+classifier", "ln1", "qkv", "self_finish", "wo_allreduce", "cross+wo2+ffn", "s_cachewrite_qfrags", "s_qk_stages",
-                       "s_softmax", "s_pv_stages", "s_fence"]
+            names_c = ["small_params+classifier+argmax", "ln1", "qkv_mm", "self_attention", "attn_finish(x2)",
+                       "wo_mm(x2)", "all_reduce+ln(x3)", "cross_q_mm", "cross_attention", "ffn_w1_mm", "ffn_w2_mm"]
             result["cluster_phase_cycles_per_step"] = {n: round(float(cp[:, 5 + i].mean()) / cfg.decoder_seq_len, 1)
                                                        for i, n in enumerate(names_c)}
         mhz = clocks.get("sm_mhz") or 1965.0
