@@ -30,7 +30,7 @@ namespace {
 
 constexpr int NCW = 8;                    // consumer warps (16 measured slower: per-warp fixed costs dominate, not divisible work)
 constexpr int NCT = NCW * 32;             // consumer threads
-constexpr int NTHREADS = NCT + 32;        // + producer warp
+constexpr int NTHREADS = NCT + 128;       // + producer warpgroup (one working thread; it exists to donate registers)
 constexpr int STAGE_BYTES = 32768;
 constexpr int MAX_STAGES = 6;
 constexpr float LOG2E = 1.4426950408889634f;
@@ -284,48 +284,46 @@ __device__ __forceinline__ void mm_stream(Consumer& c, const uint8_t* xhi, const
   const bool xrow = g < (COLS ? 2 * GUP : GUP);
   const uint8_t* xh = ((COLS && g >= GUP) ? xlo + (g - GUP) * ldx : xhi + g * ldx) + tg * 16 + kg * M::KPG * 64;
   const uint8_t* xl = xlo + g * ldx + tg * 16 + kg * M::KPG * 64;
-  // SPI stages per iteration: both waits, then every load of both stages, then the MMAs, then both releases (halves
-  // the number of exposed wait -> LDS -> HMMA latency chains for the 4-stage matrices)
-  constexpr int SPI = 1;   // 2 (pairs of stages) measured slower: the second wait delays the first stage's work
-#pragma unroll 1
-  for (int st_i = 0; st_i < M::NST; st_i += SPI) {
-    const uint8_t* st[SPI];
+  // Software pipeline over the stages of the matrix (fully unrolled, two register buffers): the fragments of stage
+  // i + 1 are loaded BEFORE the MMAs of stage i are issued, so the shared-memory reads of the eight warps (the LSU pipe
+  // needs 4 cycles per LDS.128) overlap the tensor-core work instead of alternating with it; a stage is released as
+  // soon as its MMAs have been issued (their operands are in registers by then).
+  uint4 af[2][M::KPG][M::UPW][2], bh[2][M::KPG], bl[2][M::KPG];
+  auto load_stage = [&](int buf, int st_i, const uint8_t* base) {
+    const uint8_t* stp = base + lane * 16 + (size_t(kg) * M::KPG * M::MT + mt0) * 1024;
 #pragma unroll
-    for (int i = 0; i < SPI; ++i)
-      st[i] = (SPI == 1 ? c.acquire() : c.acquire_ahead(i)) + lane * 16 + (size_t(kg) * M::KPG * M::MT + mt0) * 1024;
-    uint4 af[SPI][M::KPG][M::UPW][2], bh[SPI][M::KPG], bl[SPI][M::KPG];
-#pragma unroll
-    for (int i = 0; i < SPI; ++i)
-#pragma unroll
-      for (int q = 0; q < M::KPG; ++q) {             // every load is in flight before the first MMA
-        bh[i][q] = make_uint4(0, 0, 0, 0);
-        bl[i][q] = make_uint4(0, 0, 0, 0);
-        if (xrow) {
-          bh[i][q] = lds128(xh + ((st_i + i) * M::KBS + q) * 64);
-          if (!COLS) bl[i][q] = lds128(xl + ((st_i + i) * M::KBS + q) * 64);
-        }
-#pragma unroll
-        for (int j = 0; j < M::UPW; ++j) {
-          const uint8_t* a = st[i] + (size_t(q) * M::MT + j * M::MSTEP) * 1024;
-          af[i][q][j][0] = lds128(a);
-          af[i][q][j][1] = lds128(a + 512);
-        }
+    for (int q = 0; q < M::KPG; ++q) {
+      bh[buf][q] = make_uint4(0, 0, 0, 0);
+      bl[buf][q] = make_uint4(0, 0, 0, 0);
+      if (xrow) {
+        bh[buf][q] = lds128(xh + (st_i * M::KBS + q) * 64);
+        if (!COLS) bl[buf][q] = lds128(xl + (st_i * M::KBS + q) * 64);
       }
 #pragma unroll
-    for (int i = 0; i < SPI; ++i)
+      for (int j = 0; j < M::UPW; ++j) {
+        const uint8_t* a = stp + (size_t(q) * M::MT + j * M::MSTEP) * 1024;
+        af[buf][q][j][0] = lds128(a);
+        af[buf][q][j][1] = lds128(a + 512);
+      }
+    }
+  };
+  load_stage(0, 0, c.acquire());
 #pragma unroll
-      for (int q = 0; q < M::KPG; ++q)
+  for (int st_i = 0; st_i < M::NST; ++st_i) {
+    const int cur = st_i & 1;
+    if (st_i + 1 < M::NST) load_stage(cur ^ 1, st_i + 1, c.acquire_ahead(1));
 #pragma unroll
-        for (int j = 0; j < M::UPW; ++j) {
-          mma16816(acc[j][0], af[i][q][j][0], bh[i][q].x, bh[i][q].y);
-          mma16816(acc[j][1], af[i][q][j][1], bh[i][q].z, bh[i][q].w);
-          if (!COLS) {
-            mma16816(acc[j][0], af[i][q][j][0], bl[i][q].x, bl[i][q].y);
-            mma16816(acc[j][1], af[i][q][j][1], bl[i][q].z, bl[i][q].w);
-          }
+    for (int q = 0; q < M::KPG; ++q)
+#pragma unroll
+      for (int j = 0; j < M::UPW; ++j) {
+        mma16816(acc[j][0], af[cur][q][j][0], bh[cur][q].x, bh[cur][q].y);
+        mma16816(acc[j][1], af[cur][q][j][1], bh[cur][q].z, bh[cur][q].w);
+        if (!COLS) {
+          mma16816(acc[j][0], af[cur][q][j][0], bl[cur][q].x, bl[cur][q].y);
+          mma16816(acc[j][1], af[cur][q][j][1], bl[cur][q].z, bl[cur][q].w);
         }
-#pragma unroll
-    for (int i = 0; i < SPI; ++i) c.release();
+      }
+    c.release();
   }
   float4 v[M::UPW];
 #pragma unroll
@@ -688,6 +686,8 @@ __device__ __forceinline__ void attn_finish(AttnT& st, int GU, float* part_buf, 
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+// Registers: 12 warps = 3 per scheduler = 168 per thread at launch (512 per scheduler lane).  The producer warpgroup
+// then shrinks to 40 and the two consumer warpgroups grow to 232 (setmaxnreg moves registers inside the CTA's pool).
 template <class S>
 __global__ void __launch_bounds__(NTHREADS, 1)
 dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constant__ CUtensorMap ckv_map) {
@@ -757,8 +757,9 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
   const size_t cache_head = size_t(2) * Lc * 64;                  // elements per (layer, utterance, head): K rows | V rows
   const uint8_t* my_image = p.image + size_t(rank) * p.rank_bytes;
 
-  if (warp == NCW) {
+  if (warp >= NCW) {
     // =============================== producer: one thread walks the static access sequence
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (tid == NCT) {
       const uint64_t pol_w = policy_evict_last();
       const uint64_t pol_kv = p.kv_evict_first ? policy_evict_first() : policy_evict_last();
@@ -827,6 +828,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
     __syncwarp();
   } else {
     // ================================= consumers
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     Consumer c;
     c.r = ring;
     const bool timed = p.timing != nullptr;
