@@ -221,7 +221,9 @@ class Transformer(nn.Module):
         front-end/encoder pass and ONE decode launch per group).  A decode step costs a fixed weight stream per cluster
         of CTAs however many utterances share it, so 4 utterances per cluster (128 per launch on a 148-SM part) decode
         in 1.3x the time of 2 per cluster: the default (None) fills launches up to 128 utterances.  Utterances are
-        independent and the kernels batch-invariant, so the tokens equal those of per-batch ``greedy_decode``."""
+        independent; the group size only changes how the attention keys are dealt to the warps (fp32 summation order),
+        so the tokens equal those of per-batch ``greedy_decode`` except at argmax near-ties (``coalesce=1`` is
+        bit-identical to the per-batch call)."""
         _require_eval(self)
         from collections import deque
         dev = next(self.parameters()).device

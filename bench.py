@@ -285,10 +285,12 @@ def main():
     t_s, t_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.asr_launch_count()
     barrier()
+    torch.cuda.cudart().cudaProfilerStart()     # `ncu --profile-from-start off` lists exactly the timed region
     t_s.record()
     run_device(args.steps)
     t_e.record()
     barrier()
+    torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.stop()
     launches = lib.asr_launch_count() - launches0
     total_ms = torch.tensor([t_s.elapsed_time(t_e)], dtype=torch.float64, device=dev)

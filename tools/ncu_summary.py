@@ -57,6 +57,15 @@ def launches(src, dst, title=""):
         for (k, g, b), (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| `{k}` | {g} | {b} | {n} | {ns/1e3:.1f} | {ns/1e3/n:.2f} | {ns/total:.3f} |\n")
         f.write(f"\ntotal {total/1e6:.3f} ms over {sum(a[0] for a in agg.values())} launches\n")
+        fam = OrderedDict()
+        for (k, g, b), (n, ns) in agg.items():
+            name = re.sub(r"<.*$", "", k).split("::")[-1]
+            fa = fam.setdefault(name, [0, 0.0])
+            fa[0] += n
+            fa[1] += ns
+        f.write("\n| kernel family | launches | total us | share |\n|---|---:|---:|---:|\n")
+        for name, (n, ns) in sorted(fam.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| `{name}` | {n} | {ns/1e3:.1f} | {ns/total:.3f} |\n")
 
 
 def full(src, dst, title=""):
