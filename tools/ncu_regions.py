@@ -76,6 +76,8 @@ src_cache = {}
 def src(key):
     f, n = key
     p = os.path.join(os.path.dirname(os.path.abspath(obj)), "..", "csrc", f)
+    if not os.path.exists(p):
+        p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "asr_transformer_b200", "csrc", f)
     if f not in src_cache:
         src_cache[f] = open(p).read().splitlines() if os.path.exists(p) else []
     L = src_cache[f]
