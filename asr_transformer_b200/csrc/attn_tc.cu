@@ -22,7 +22,7 @@ constexpr int BKV = 128;  // keys per tile
 constexpr int DH = 64;
 constexpr int TILE_BYTES = BKV * DH * 2;  // 16 KB (Q, K and V tiles alike)
 constexpr int P_BYTES = BQ * BKV * 2;     // 32 KB
-constexpr size_t ATTN_SMEM = TILE_BYTES * 5 + P_BYTES + 128 + 1024;
+constexpr size_t ATTN_SMEM = TILE_BYTES * 5 + P_BYTES + 128;   // 112.1 KB: two CTAs per SM (228 KB, 1 KB reserved each)
 constexpr uint32_t TMEM_COLS = 256;       // S: [0,128), O_j: [128,192)
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -46,8 +46,8 @@ struct AttnDev {
 __global__ void __launch_bounds__(160, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, AttnDev p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];   // no static shared memory in this kernel: the base is 1 KB aligned
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();   // swizzled TMA / UMMA tiles need it
   uint8_t* sQ = smem;
   uint8_t* sK = smem + TILE_BYTES;          // 2 stages
   uint8_t* sV = smem + 3 * TILE_BYTES;      // 2 stages
