@@ -65,12 +65,15 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_cluster_slow(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait_cluster(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) __trap();   // a protocol bug must surface as a launch failure, not a hang
   }
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  mbar_wait_cluster_slow(bar, parity);
 }
 __device__ __forceinline__ uint64_t policy_evict_last() {
   uint64_t pol;
@@ -117,8 +120,7 @@ struct Shape {
   static constexpr int H = H_, CS = H_, D = 64 * H_, FFS = FFS_, VS = VS_, GUP = GUP_;
   static constexpr int RPS = (STAGE_BYTES / 128) / GUP;   // key rows per utterance slot per ring stage (K or V rows)
   static constexpr int WPU = NCW / GUP;                   // attention warps per utterance slot
-  static constexpr int SC = 2;                            // K stages per super-chunk (softmax granularity), self attention
-  static constexpr int SCX = GUP >= 4 ? 4 : 2;            // ... cross attention: one super-chunk covers 256 encoder frames
+  static constexpr int SCX = GUP >= 4 ? 4 : 2;            // K stages per super-chunk (softmax granularity): 256 keys (128 at GUP 8)
   static constexpr int TPW = (RPS / 16) / WPU;            // 16-key tiles per warp per stage
   static constexpr int SMALL_FLOATS = 256 + FFS + 11 * D;   // ... | ln1 | ln2 | ln3 | ln1 of the NEXT layer
   static constexpr uint32_t SMALL_BYTES = (SMALL_FLOATS * 4 + 127) / 128 * 128;
@@ -228,12 +230,10 @@ struct Consumer {
   long long waited = 0;
   bool timed = false;
   __device__ __forceinline__ const uint8_t* acquire() {
-    if (timed) {
-      const long long w0 = clock64();
-      mbar_wait(&r.full[slot], round & 1u);
-      waited += clock64() - w0;
-    } else {
-      mbar_wait(&r.full[slot], round & 1u);
+    if (!mbar_try_wait(&r.full[slot], round & 1u)) {   // stage not there yet: the (rare, out-of-line) slow path is timed
+      const long long w0 = timed ? clock64() : 0;
+      mbar_wait_slow(smem_u32(&r.full[slot]), round & 1u);
+      if (timed) waited += clock64() - w0;
     }
     return r.buf + size_t(slot) * STAGE_BYTES;
   }
@@ -560,18 +560,18 @@ __device__ __forceinline__ void pv_tile(AttnT& st, uint32_t vbase, uint32_t b0, 
 // K stages followed by the matching V stages ([utterance slot][RPS rows][128 B] each); warp partition `apart` owns
 // tiles TPW apart .. TPW apart + TPW - 1 of every stage.  All scores of a super-chunk are computed first (independent
 // MMAs), then ONE max / exp / sum, then all P V products: one softmax dependency chain per super-chunk instead of one
-// per tile.  HAS_CUR: additionally the single current row (k_t at cur_kb, v_t at cur_kb + 128; cur_kb == 0 for the
-// warps that do not own it), merged into the first chunk.  n_keys rows are streamed (uniform over the CTA); only the
+// per tile.  Additionally the single current row of the self attention (k_t at cur_kb, v_t at cur_kb + 128; 0 for the
+// warps that do not own it and for the cross attention), merged into the first chunk.  n_keys rows are streamed (uniform over the CTA); only the
 // first n_mine of them are valid keys of THIS warp's utterance (key padding: cross attention with encoder lengths), the
 // rest are masked.  Control flow: stage presence (s < ns) is CTA-uniform; the shuffles of the softmax sit outside every
 // thread-dependent branch (masked tiles carry score -inf -> p = 0), only ldmatrix / MMA blocks are skipped per tile.
-template <class S, int SC, bool HAS_CUR>
+template <class S, int SC>
 __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t (&qf)[8], int n_keys, int n_mine,
                                           bool active, int au, int apart, uint32_t cur_kb, int cur_swz) {
   constexpr int RPS = S::RPS, TPW = S::TPW;
   float ca = -INFINITY;
-  bool cur = HAS_CUR && cur_kb != 0;
-  if (HAS_CUR) {
+  bool cur = cur_kb != 0;
+  {
     float cb;
     if (cur) qk_tile<true>(cur_kb, 1, qf, ca, cb, cur_swz);
   }
@@ -618,8 +618,8 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t
           p_frags(hilo_pack(pa), hilo_pack(pb), pb0[s][j], pb1[s][j]);
         }
       }
-    if (HAS_CUR) {
-      const float pa = ex2(ca - m_use);
+    {
+      const float pa = ex2(ca - m_use);                          // -inf -> 0 when this warp has no current row
       lsum += pa;
       p_frags(hilo_pack(pa), 0u, cb0, cb1);
     }
@@ -639,11 +639,9 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t
           if (n > 16 * j) pv_tile<false>(st, stg + j * 2048, pb0[s][j], pb1[s][j]);
         c.release();
       }
-    if (HAS_CUR) {
-      if (cur) pv_tile<true>(st, cur_kb + 128, cb0, cb1, cur_swz);
-      cur = false;
-      ca = -INFINITY;
-    }
+    if (cur) pv_tile<true>(st, cur_kb + 128, cb0, cb1, cur_swz);
+    cur = false;
+    ca = -INFINITY;
     c0 += SC * RPS;
   } while (c0 < n_keys);
 }
@@ -786,8 +784,8 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
             while (ctrl[2] < need) {
             }
             asm volatile("fence.proxy.async;" ::: "memory");
-            for (int c0 = 0; c0 < t; c0 += S::SC * RPS) {
-              const int nk = min(S::SC * RPS, t - c0);
+            for (int c0 = 0; c0 < t; c0 += S::SCX * RPS) {
+              const int nk = min(S::SCX * RPS, t - c0);
               for (int kv = 0; kv < 2; ++kv)               // K stages of the super-chunk, then its V stages
                 for (int r0 = 0; r0 < nk; r0 += RPS) {
                   const int n = (min(RPS, nk - r0) + 15) & ~15;   // whole 16-key tiles (rows past t are zero)
@@ -971,97 +969,112 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
           ln_rows<S>(s_h, GU, ln, ln + D, xn_hi, xn_lo, stat);
           consumer_sync();
         }
-        mark(1);
-        mm_stream<MQkv, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
-          const float y0 = v0 + b_qkv[n], y1 = v1 + b_qkv[n];
-          if (n < 64) {
-            q_store(q_hi, q_lo, u0, n, y0 * qscale);
-            q_store(q_hi, q_lo, u0 + 1, n, y1 * qscale);
-          } else {   // k_t | v_t rows in the cache's swizzled chunk order (chunk ^ (t & 7)): TMA-stored as they are
-            const int e = n - 64, pos = (e & 64) + ((((e & 63) >> 3) ^ (t & 7)) << 3) + (e & 7);
-            kv_row[u0 * 128 + pos] = __float2bfloat16(y0);
-            kv_row[(u0 + 1) * 128 + pos] = __float2bfloat16(y1);
+        // The layer is three residual sub-blocks.  They run as three passes of ONE loop body so that the attention
+        // core, its merge, the out projection and the all-reduce tail exist once in the instruction stream (the two
+        // attentions differ only in runtime arguments): the kernel's hot loop has to stay inside the SM's instruction
+        // cache, which it shares with nothing when alone but loses to co-running kernels.
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {
+          const float* ar_bias;
+          const float* ar_gam;
+          if (pass < 2) {
+            int n_keys, n_mine;
+            uint32_t cur_kb = 0;
+            if (pass == 0) {
+              // ---- masked self attention (model.py:67-68): q, k, v of this head, cache append, keys 0..t
+              mark(1);
+              mm_stream<MQkv, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
+                const float y0 = v0 + b_qkv[n], y1 = v1 + b_qkv[n];
+                if (n < 64) {
+                  q_store(q_hi, q_lo, u0, n, y0 * qscale);
+                  q_store(q_hi, q_lo, u0 + 1, n, y1 * qscale);
+                } else {   // k_t | v_t rows in the cache's swizzled chunk order (chunk ^ (t & 7)): TMA-stored as they are
+                  const int e = n - 64, pos = (e & 64) + ((((e & 63) >> 3) ^ (t & 7)) << 3) + (e & 7);
+                  kv_row[u0 * 128 + pos] = __float2bfloat16(y0);
+                  kv_row[(u0 + 1) * 128 + pos] = __float2bfloat16(y1);
+                }
+              });
+              fence_proxy_async();                                   // kv_row: generic writes -> the TMA store below
+              consumer_sync();
+              mark(2);
+              // append k_t, v_t (bf16) to the device-resident cache: [layer][utterance][head][K rows | V rows][Lc][64], the
+              // 16-byte chunks of row t stored swizzled (chunk ^ (t & 7)) so that the bulk copy lands ldmatrix-ready.  The
+              // first row of every 16-row block also zeroes the block's other rows: whole 16-key tiles are always finite.
+              if (tid < GU * 2) {                                    // one 128-byte TMA store per (utterance, K | V)
+                const int u = tid >> 1, kv = tid & 1;
+                bf16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * Lc * 64 +
+                            size_t(t) * 64;
+                bulk_store(dst, kv_row + u * 128 + kv * 64, 128);
+              }
+              if ((t & 15) == 0) {
+                for (int i = tid; i < GU * 2 * 15 * 8; i += NCT) {
+                  const int u = i / 240, rem = i - u * 240, kv = rem / 120, w = rem - kv * 120;   // w: 16-byte word in 15 rows
+                  bf16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * Lc * 64 +
+                              size_t(t + 1) * 64 + w * 8;
+                  *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+                }
+                asm volatile("fence.proxy.async;" ::: "memory");   // generic zero fill -> later TMA reads (1 step in 16)
+              }
+              n_keys = t;
+              n_mine = t;
+              cur_kb = (a_active && apart == S::WPU - 1) ? smem_u32(kv_row) + au * 256 : 0u;   // current row: from smem
+              ar_bias = b_o;
+              ar_gam = ln + 2 * D;                              // out projection + residual (model.py:68) -> LN2 (:70)
+            } else {
+              // ---- cross-attention query -> attention over the encoder K/V (model.py:70-71)
+              mm_stream<MWqc, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
+                q_store(q_hi, q_lo, u0, n, (v0 + b_qc[n]) * qscale);
+                q_store(q_hi, q_lo, u0 + 1, n, (v1 + b_qc[n]) * qscale);
+              });
+              consumer_sync();
+              mark(7);
+              n_keys = p.Tp;
+              n_mine = n_cross;
+              ar_bias = b_oc;
+              ar_gam = ln + 4 * D;                              // -> LN3 (model.py:73)
+            }
+            AttnT st;
+            uint32_t qf[8];
+            attn_init(st);
+            attn_q_frags(q_hi, q_lo, au, qf);
+            attention<S, S::SCX>(c, st, qf, n_keys, n_mine, a_active, au, apart, cur_kb, t & 7);
+            if (pass == 0) {
+              if (tid < GU * 2) bulk_store_wait();              // this step's cache rows are written (published below)
+              mark(3);
+            } else {
+              mark(8);
+            }
+            attn_finish<S>(st, GU, part_buf, stat, o_hi, o_lo);   // (two consumer barriers inside)
+            if (pass == 0 && tid == 0) {                          // cache row t of this layer is published
+              __threadfence_block();
+              ctrl[2] = t * p.nd + l + 1;
+            }
+            mark(4);
+            mm_stream<MWo, GUP>(c, reinterpret_cast<const uint8_t*>(o_hi), reinterpret_cast<const uint8_t*>(o_lo),
+                                S::LDO, scratch, send_partial);
+            mark(5);
+          } else {
+            // ---- FFN: squeeze rows of this CTA + ReLU, then the matching K-slice of unsqueeze (model.py:73-74)
+            mm_stream<MW1, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
+              const float y0 = fmaxf(v0 + b_1[n], 0.f), y1 = fmaxf(v1 + b_1[n], 0.f);
+              const bf16 h0 = __float2bfloat16(y0), h1 = __float2bfloat16(y1);
+              hid_hi[u0 * (FFS + 32) + n] = h0;
+              hid_lo[u0 * (FFS + 32) + n] = __float2bfloat16(y0 - __bfloat162float(h0));
+              hid_hi[(u0 + 1) * (FFS + 32) + n] = h1;
+              hid_lo[(u0 + 1) * (FFS + 32) + n] = __float2bfloat16(y1 - __bfloat162float(h1));
+            });
+            consumer_sync();
+            mark(9);
+            mm_stream<MW2, GUP>(c, reinterpret_cast<const uint8_t*>(hid_hi), reinterpret_cast<const uint8_t*>(hid_lo),
+                                S::LDH, scratch, send_partial);
+            mark(10);
+            // -> LN1 of the next layer (its parameters travel in this layer's block), or the classifier's plain split
+            ar_bias = b_2;
+            ar_gam = (l + 1 < p.nd) ? ln + 6 * D : nullptr;
           }
-        });
-        fence_proxy_async();                                   // kv_row: generic writes -> the TMA store below
-        consumer_sync();
-        mark(2);
-        // append k_t, v_t (bf16) to the device-resident cache: [layer][utterance][head][K rows | V rows][Lc][64], the
-        // 16-byte chunks of row t stored swizzled (chunk ^ (t & 7)) so that the bulk copy lands ldmatrix-ready.  The
-        // first row of every 16-row block also zeroes the block's other rows: whole 16-key tiles are always finite.
-        if (tid < GU * 2) {                                    // one 128-byte TMA store per (utterance, K | V)
-          const int u = tid >> 1, kv = tid & 1;
-          bf16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * Lc * 64 +
-                      size_t(t) * 64;
-          bulk_store(dst, kv_row + u * 128 + kv * 64, 128);
+          all_reduce_finish(ar_bias, ar_gam, ar_gam + D);         // beta follows gamma in the parameter block
+          mark(6);
         }
-        if ((t & 15) == 0) {
-          for (int i = tid; i < GU * 2 * 15 * 8; i += NCT) {
-            const int u = i / 240, rem = i - u * 240, kv = rem / 120, w = rem - kv * 120;   // w: 16-byte word in 15 rows
-            bf16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * Lc * 64 +
-                        size_t(t + 1) * 64 + w * 8;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-          }
-          asm volatile("fence.proxy.async;" ::: "memory");   // generic zero fill -> later TMA reads (1 step in 16)
-        }
-        // ---- causal self attention over keys 0..t: cached rows from the ring, the current row from shared memory
-        AttnT st;
-        uint32_t qf[8];
-        attn_init(st);
-        attn_q_frags(q_hi, q_lo, au, qf);
-        attention<S, S::SC, true>(c, st, qf, t, t, a_active, au, apart,
-                                  (a_active && apart == S::WPU - 1) ? smem_u32(kv_row) + au * 256 : 0u, t & 7);
-        if (tid < GU * 2) bulk_store_wait();                  // this step's cache rows are written (published below)
-        mark(3);
-        attn_finish<S>(st, GU, part_buf, stat, o_hi, o_lo);   // (two consumer barriers inside)
-        if (tid == 0) {                                       // cache row t of this layer is published
-          __threadfence_block();
-          ctrl[2] = t * p.nd + l + 1;
-        }
-        mark(4);
-        mm_stream<MWo, GUP>(c, reinterpret_cast<const uint8_t*>(o_hi), reinterpret_cast<const uint8_t*>(o_lo), S::LDO,
-                            scratch, send_partial);
-        mark(5);
-        all_reduce_finish(b_o, ln + 2 * D, ln + 3 * D);       // out projection + residual (model.py:68) -> LN2 (:70)
-        mark(6);
-
-        // ---- cross-attention query -> attention over the encoder K/V, never masked (model.py:70-71)
-        mm_stream<MWqc, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
-          q_store(q_hi, q_lo, u0, n, (v0 + b_qc[n]) * qscale);
-          q_store(q_hi, q_lo, u0 + 1, n, (v1 + b_qc[n]) * qscale);
-        });
-        consumer_sync();
-        mark(7);
-        attn_init(st);
-        attn_q_frags(q_hi, q_lo, au, qf);
-        attention<S, S::SCX, false>(c, st, qf, p.Tp, n_cross, a_active, au, apart, 0u, 0);
-        mark(8);
-        attn_finish<S>(st, GU, part_buf, stat, o_hi, o_lo);
-        mark(4);
-        mm_stream<MWo, GUP>(c, reinterpret_cast<const uint8_t*>(o_hi), reinterpret_cast<const uint8_t*>(o_lo), S::LDO,
-                            scratch, send_partial);
-        mark(5);
-        all_reduce_finish(b_oc, ln + 4 * D, ln + 5 * D);      // -> LN3 (model.py:73)
-        mark(6);
-
-        // ---- FFN: squeeze rows of this CTA + ReLU, then the matching K-slice of unsqueeze (model.py:73-74)
-        mm_stream<MW1, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
-          const float y0 = fmaxf(v0 + b_1[n], 0.f), y1 = fmaxf(v1 + b_1[n], 0.f);
-          const bf16 h0 = __float2bfloat16(y0), h1 = __float2bfloat16(y1);
-          hid_hi[u0 * (FFS + 32) + n] = h0;
-          hid_lo[u0 * (FFS + 32) + n] = __float2bfloat16(y0 - __bfloat162float(h0));
-          hid_hi[(u0 + 1) * (FFS + 32) + n] = h1;
-          hid_lo[(u0 + 1) * (FFS + 32) + n] = __float2bfloat16(y1 - __bfloat162float(h1));
-        });
-        consumer_sync();
-        mark(9);
-        mm_stream<MW2, GUP>(c, reinterpret_cast<const uint8_t*>(hid_hi), reinterpret_cast<const uint8_t*>(hid_lo),
-                            S::LDH, scratch, send_partial);
-        mark(10);
-        // -> LN1 of the next layer (its parameters travel in this layer's block), or the classifier's plain split
-        if (l + 1 < p.nd) all_reduce_finish(b_2, ln + 6 * D, ln + 7 * D);
-        else all_reduce_finish(b_2, nullptr, nullptr);
-        mark(6);
       }
 
       // ---- classifier WITHOUT the final LayerNorm (model.py:142): VS vocabulary rows per CTA
