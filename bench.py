@@ -20,7 +20,6 @@ import ctypes as C
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -40,7 +39,7 @@ DEC_CLASSES = ["dec_linear_qkv", "dec_attn_self", "dec_linear_out_proj", "dec_li
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="utterances per GPU (default: the workload's batch)")
@@ -77,46 +76,56 @@ def workload_desc(cfg, batch, n_gpus):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe), through NVML in this
+    process: an `nvidia-smi -lms` loop beside the bench stalls the multi-stream launch path for milliseconds per
+    sample (measured: -6 % throughput at 20 ms sampling), the two NVML calls used here do not."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+    def __init__(self, gpu_index, period_s=0.02):
+        self.idx, self.period, self.samples, self.reasons = gpu_index, period_s, [], set()
+        self.stop_flag, self.thread, self.h, self.max_mhz = threading.Event(), None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+            import pynvml
+            pynvml.nvmlInit()
+            if "CUDA_VISIBLE_DEVICES" in os.environ and os.environ["CUDA_VISIBLE_DEVICES"].strip():
+                vis = os.environ["CUDA_VISIBLE_DEVICES"].split(",")[self.idx].strip()
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(int(vis)) if vis.isdigit() else \
+                    pynvml.nvmlDeviceGetHandleByUUID(vis)
+            else:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
         except Exception:
-            self.proc = None
+            self.h = None
+            return
+
+        def loop():
+            while not self.stop_flag.is_set():
+                try:
+                    mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                    rs = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    self.samples.append((time.perf_counter(), float(mhz), int(rs)))
+                except Exception:
+                    pass
+                self.stop_flag.wait(self.period)
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    def clear(self):
+        self.samples.clear()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
-            f = [x.strip() for x in l.split(",")]
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                for n, v in zip(names, f[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except (ValueError, IndexError):
-                pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable"]}
+        self.stop_flag.set()
+        self.thread.join(timeout=2)
+        sm = [m for _, m, _ in self.samples]
+        reasons = sorted({n for _, _, r in self.samples for n, bit in self.BAD.items() if r & bit})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "samples": len(sm),
+                "reasons": reasons, "how": "NVML clock + clocks-event reasons every %d ms during the timed region"
+                                           % int(self.period * 1e3)}
 
 
 def measured_traffic(kernel, utterances):
@@ -274,14 +283,14 @@ def main():
             pass
         return out
 
-    # the clock sampler (an nvidia-smi loop) is started BEFORE the warm-up: its NVML start-up contends for the driver
-    # lock with the multi-stream enqueue and would otherwise starve the first timed steps
+    # the clock sampler is started BEFORE the warm-up: NVML start-up contends for the driver lock with the multi-stream
+    # enqueue and would otherwise starve the first timed steps
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
     sampler.start()
     time.sleep(0.5)
     run_device(max(args.warmup, 3))
     barrier()
-    sampler.lines.clear()                   # keep only the samples taken during the timed region
+    sampler.clear()                         # keep only the samples taken during the timed region
     t_s, t_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = lib.asr_launch_count()
     barrier()
