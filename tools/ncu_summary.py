@@ -59,7 +59,7 @@ def launches(src, dst, title=""):
         f.write(f"\ntotal {total/1e6:.3f} ms over {sum(a[0] for a in agg.values())} launches\n")
         fam = OrderedDict()
         for (k, g, b), (n, ns) in agg.items():
-            name = re.sub(r"<.*$", "", k).split("::")[-1]
+            name = re.sub(r"<.*$", "", k.replace("<unnamed>::", "")).split("::")[-1]
             fa = fam.setdefault(name, [0, 0.0])
             fa[0] += n
             fa[1] += ns
