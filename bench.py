@@ -170,7 +170,7 @@ def run_reference(args, cfg):
     """Reference arm: the reference's CPU algorithm (literal restatement, oracle/speech_transformer.py) on the host
     cores.  One step = ONE utterance of the same workload (bounded sample; the reference costs O(L^2) per utterance)."""
     from oracle import speech_transformer as O
-    from tests.util import build_model, cpu_state
+    from asr_transformer_b200.workloads import build_model, cpu_state
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -206,12 +206,12 @@ def main():
     if args.decode_mode:
         os.environ["ASR_B200_DECODE"] = args.decode_mode
     mode = os.environ.get("ASR_B200_DECODE", "") or "cluster"
-    from oracle import speech_transformer as O      # workload registry + synthetic inputs + CPU baseline only
-    cfg = O.CONFIGS[args.workload]
+    from asr_transformer_b200 import workloads as W   # workload registry + synthetic inputs (no oracle on this arm)
+    cfg = W.CONFIGS[args.workload]
     if args.impl == "reference":
         return run_reference(args, cfg)
 
-    from tests.util import build_model, cpu_state
+    from asr_transformer_b200.workloads import build_model, cpu_state
     from asr_transformer_b200 import lib as L
     from asr_transformer_b200.parallel import gather_tokens
 
@@ -235,7 +235,7 @@ def main():
     model = build_model(cfg, dev)
     lib = L.load()
     # every rank decodes its own utterances (different seed per rank): weak scaling
-    spec_host = O.structured_spectrum(batch, cfg.frames, cfg.input_dim, seed=1 + rank).pin_memory()
+    spec_host = W.structured_spectrum(batch, cfg.frames, cfg.input_dim, seed=1 + rank).pin_memory()
     spec_dev = spec_host.to(dev)
     tokens = torch.empty(batch, cfg.decoder_seq_len + 1, dtype=torch.int32, device=dev)
     n_tok = torch.empty(batch, dtype=torch.int32, device=dev)
@@ -274,7 +274,7 @@ def main():
     # decoder of step i leaves idle.  Inputs rotate over N_ROT distinct device-resident batches (> L2) instead of an L2
     # flush, which would serialise the steps.
     N_ROT = 8
-    spec_rot = [spec_dev] + [O.structured_spectrum(batch, cfg.frames, cfg.input_dim, seed=1000 * (rank + 1) + i).to(dev)
+    spec_rot = [spec_dev] + [W.structured_spectrum(batch, cfg.frames, cfg.input_dim, seed=1000 * (rank + 1) + i).to(dev)
                              for i in range(1, N_ROT)]
 
     def run_device(n):
@@ -437,6 +437,7 @@ def main():
 
         # -------------------------------------------------------------- CPU baseline (reference algorithm, host cores)
         if world == 1 and not args.no_cpu_baseline:
+            from oracle import speech_transformer as O      # the ONLY use of oracle/ on this arm: the timed CPU baseline
             torch.set_num_threads(os.cpu_count() or 1)
             sd = cpu_state(model)
             n_cpu = 2

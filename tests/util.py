@@ -27,20 +27,7 @@ def state_checksum(sd) -> str:
     return h.hexdigest()
 
 
-def build_model(cfg: O.Config, device="cpu"):
-    """Our drop-in Transformer with the reference's seed-0 default init, rounded to bf16-representable fp32."""
-    import asr_transformer_b200 as A
-    torch.manual_seed(0)
-    m = A.Transformer(**cfg.ctor_kwargs())
-    with torch.no_grad():
-        for p in m.parameters():
-            O.bf16_representable_(p)
-    m.eval()
-    return m.to(device)
-
-
-def cpu_state(m):
-    return {k: v.detach().cpu().float() if v.is_floating_point() else v.detach().cpu() for k, v in m.state_dict().items()}
+from asr_transformer_b200.workloads import build_model, cpu_state  # noqa: E402,F401
 
 
 def assert_close(got, ref, tol_max=TOL_MAX, tol_mean=TOL_MEAN, what=""):

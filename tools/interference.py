@@ -11,8 +11,8 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 from asr_transformer_b200 import lib as L  # noqa: E402
-from oracle import speech_transformer as O  # noqa: E402
-from tests.util import build_model  # noqa: E402
+from asr_transformer_b200 import workloads as O  # noqa: E402  (workload registry + synthetic inputs)
+from asr_transformer_b200.workloads import build_model  # noqa: E402
 
 cfg = O.CONFIGS["C2"]
 dev = torch.device("cuda", 0)

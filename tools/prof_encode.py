@@ -13,8 +13,8 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--workload", default="C2")
 a = ap.parse_args()
-from oracle import speech_transformer as O  # noqa: E402  (workload registry + synthetic inputs only)
-from tests.util import build_model  # noqa: E402
+from asr_transformer_b200 import workloads as O  # noqa: E402  (workload registry + synthetic inputs)
+from asr_transformer_b200.workloads import build_model  # noqa: E402
 
 cfg = O.CONFIGS[a.workload]
 dev = torch.device("cuda", 0)

@@ -1,7 +1,7 @@
 import os, sys, torch
 sys.path.insert(0, os.getcwd())
-from oracle import speech_transformer as O
-from tests.util import build_model
+from asr_transformer_b200 import workloads as O  # noqa: E402  (workload registry + synthetic inputs)
+from asr_transformer_b200.workloads import build_model
 cfg = O.CONFIGS["C2"]; dev = torch.device("cuda", 0)
 m = build_model(cfg, dev)
 specs = [O.structured_spectrum(64, cfg.frames, cfg.input_dim, seed=1 + i).to(dev) for i in range(8)]
