@@ -176,6 +176,12 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(rr[i]));
           mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2);   // scale > 0
+        } else if (fast) {                               // index-only mask (sequence end / causal edge): selects, no loads
+          const int nv = k_lim - (kbase + c * 32);       // valid keys of this chunk (may be <= 0)
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], i < nv ? __uint_as_float(rr[i]) : -INFINITY);
+          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])) * p.scale_log2);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -218,6 +224,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           for (int i = 0; i < 32; i += 2) {
             const float p0 = fast_exp2(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_new));
             const float p1 = fast_exp2(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -m_new));
+            l4[(i >> 1) & 3] += p0 + p1;
+            packed[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          lsum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        } else if (fast) {
+          const int nv = k_lim - (kbase + c * 32);
+          float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = i < nv ? fast_exp2(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_new)) : 0.f;
+            const float p1 = i + 1 < nv ? fast_exp2(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -m_new)) : 0.f;
             l4[(i >> 1) & 3] += p0 + p1;
             packed[i >> 1] = pack_bf16x2(p0, p1);
           }

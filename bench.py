@@ -440,7 +440,7 @@ def main():
             from oracle import speech_transformer as O      # the ONLY use of oracle/ on this arm: the timed CPU baseline
             torch.set_num_threads(os.cpu_count() or 1)
             sd = cpu_state(model)
-            n_cpu = 2
+            n_cpu = 16
             with torch.no_grad():
                 import dataclasses
                 O.evaluate_reference_style(sd, spec_host[:1].contiguous(), dataclasses.replace(cfg, decoder_seq_len=4))  # warm-up
