@@ -3,10 +3,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/asr_b200.h"
 #include "kernels.h"
+#include "ptx.cuh"
 
 using namespace asr;
 
@@ -133,6 +135,138 @@ __global__ void dec_init_kernel(int32_t* tokens, int ld_tok, int32_t* n_tokens, 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ beam search
+// One CTA per utterance: log-softmax of the K hypothesis rows, candidate score = hypothesis score + log p(token)
+// (finished hypotheses: a single candidate, themselves, extended with pad), then the K best of the K x V candidates by
+// K rounds of a block-wide arg-max; ties go to the lower flat index k * V + token (the lowest-index rule of argmax,
+// model.py:143).  Semantics = oracle/speech_transformer.py: beam_search_kv_cached.
+__global__ void __launch_bounds__(256)
+beam_select_kernel(const float* __restrict__ logits, int ld, int V, int K, float* score, int32_t* finished,
+                   int32_t* parent, int32_t* token, int eos, int pad) {
+  extern __shared__ float cand[];                 // [K * V] candidate scores
+  __shared__ float s_red[8];
+  __shared__ int s_redi[8];
+  __shared__ float s_score[16];
+  __shared__ int s_fin[16], s_par[16], s_tok[16];
+  __shared__ float s_new[16];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < K) {
+    s_score[tid] = score[b * K + tid];
+    s_fin[tid] = finished[b * K + tid];
+  }
+  __syncthreads();
+  for (int k = warp; k < K; k += 8) {             // one warp per hypothesis row
+    const float* row = logits + size_t(b * K + k) * ld;
+    float* out = cand + k * V;
+    if (s_fin[k]) {
+      for (int v = lane; v < V; v += 32) out[v] = (v == pad) ? s_score[k] : -INFINITY;
+      continue;
+    }
+    float mx = -INFINITY;
+    for (int v = lane; v < V; v += 32) mx = fmaxf(mx, row[v]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int v = lane; v < V; v += 32) sum += expf(row[v] - mx);
+    const float lse = mx + logf(warp_sum(sum));
+    for (int v = lane; v < V; v += 32) out[v] = s_score[k] + (row[v] - lse);   // -inf + x = -inf: dead hypotheses
+  }
+  __syncthreads();
+  const int n = K * V;
+  for (int j = 0; j < K; ++j) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < n; i += 256) {
+      const float x = cand[i];
+      if (x > best || (x == best && i < bi)) {
+        best = x;
+        bi = i;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      s_red[warp] = best;
+      s_redi[warp] = bi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (s_red[w] > best || (s_red[w] == best && s_redi[w] < bi)) {
+          best = s_red[w];
+          bi = s_redi[w];
+        }
+      s_par[j] = bi / V;
+      s_tok[j] = bi % V;
+      s_new[j] = best;
+      cand[bi] = __int_as_float(0xffc00000);      // NaN: compares false against everything, never selected again
+    }
+    __syncthreads();
+  }
+  if (tid < K) {
+    const int par = s_par[tid], tok = s_tok[tid];
+    parent[b * K + tid] = par;
+    token[b * K + tid] = tok;
+    score[b * K + tid] = s_new[tid];
+    finished[b * K + tid] = (s_fin[par] || tok == eos) ? 1 : 0;
+  }
+}
+
+// Survivors inherit their parent's state: self K/V cache rows 0..t of every layer and the token history, gathered into
+// the second buffer set (grid: hypothesis row x layer); the new token lands at position t + 1; the device step counter
+// (cache append position / attention length of the next step) advances.
+__global__ void __launch_bounds__(256)
+beam_reorder_kernel(const bf16* __restrict__ cache_src, bf16* __restrict__ cache_dst, const int32_t* __restrict__ tok_src,
+                    int32_t* __restrict__ tok_dst, const int32_t* __restrict__ parent, const int32_t* __restrict__ token,
+                    int32_t* step, int R, int K, int L, int D2, int t) {
+  const int r = blockIdx.x, l = blockIdx.y;
+  const int src_r = (r / K) * K + parent[r];
+  const size_t row_elems = size_t(L) * D2;
+  const uint4* src = reinterpret_cast<const uint4*>(cache_src + (size_t(l) * R + src_r) * row_elems);
+  uint4* dst = reinterpret_cast<uint4*>(cache_dst + (size_t(l) * R + r) * row_elems);
+  const int n16 = (t + 1) * D2 / 8;
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
+  if (l == 0) {
+    for (int i = threadIdx.x; i <= t; i += blockDim.x) tok_dst[size_t(r) * (L + 1) + i] = tok_src[size_t(src_r) * (L + 1) + i];
+    if (threadIdx.x == 0) tok_dst[size_t(r) * (L + 1) + t + 1] = token[r];
+    if (r == 0 && threadIdx.x == 0) *step = t + 1;
+  }
+}
+
+__global__ void beam_init_kernel(int32_t* tok, int ld_tok, float* score, int32_t* finished, int32_t* step, int R, int K,
+                                 int bos) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r == 0) *step = 0;
+  if (r < R) {
+    tok[size_t(r) * ld_tok] = bos;
+    score[r] = (r % K == 0) ? 0.f : -INFINITY;    // one live hypothesis per utterance at step 0
+    finished[r] = 0;
+  }
+}
+
+struct BeamWs {
+  GreedyWs g;
+  bf16* cache_alt;
+  int32_t *tok_a, *tok_b, *parent, *token;
+  float* score;
+  void carve(Bump& b, const AsrConfig& c, int R, int Tp, int L) {
+    g.carve(b, c, R, Tp, L);
+    cache_alt = b.take<bf16>(size_t(c.decoder_num_layers) * R * ((L + 15) / 16 * 16) * 2 * c.embedding_dim);
+    tok_a = b.take<int32_t>(size_t(R) * (L + 1));
+    tok_b = b.take<int32_t>(size_t(R) * (L + 1));
+    parent = b.take<int32_t>(R);
+    token = b.take<int32_t>(R);
+    score = b.take<float>(R);
+  }
+};
+
 }  // namespace
 
 struct AsrHandle {
@@ -214,7 +348,7 @@ int cross_kv(const AsrHandle* h, const bf16* enc_bf16, bf16* ckv, int M, cudaStr
 }
 
 int greedy_step(const AsrHandle* h, const GreedyWs& ws, int B, int Tp, int L, int stop_at_eos, int32_t* tokens,
-                int32_t* n_tokens, float* step_logits, cudaStream_t s, StepProf* prof = nullptr) {
+                int32_t* n_tokens, float* step_logits, cudaStream_t s, StepProf* prof = nullptr, bool select = true) {
   const AsrConfig& c = h->cfg;
   const int D = c.embedding_dim, FF = c.ff_dim, H = c.num_heads;
   const float scale = 1.0f / sqrtf((float)D);
@@ -285,6 +419,7 @@ int greedy_step(const AsrHandle* h, const GreedyWs& ws, int B, int Tp, int L, in
     p.B = B; p.N = c.vocab_size; p.K = D; p.out = ws.logits; p.ldo = vpad;
     PROF(prof, DC_CLASSIFIER, launch_dec_linear(p, s));
   }
+  if (!select) return 0;   // beam search picks the survivors itself (logits are in ws.logits)
   DecSelect sel;
   sel.logits = ws.logits; sel.ld = vpad; sel.V = c.vocab_size; sel.B = B;
   sel.tokens = tokens; sel.ld_tok = L + 1; sel.n_tokens = n_tokens; sel.finished = ws.finished; sel.step = ws.step;
@@ -637,6 +772,77 @@ int asr_decode_run(AsrHandle* h, const float* enc_out, int B, int Tp, int L, int
                    int32_t* n_tokens, float* step_logits, asr_stream_t stream) {
   return decode_greedy_impl(2, h, enc_out, B, Tp, L, stop_at_eos, first_tokens, enc_lens, ws, ws_bytes, tokens, n_tokens,
                             step_logits, stream);
+}
+
+int asr_beam_workspace_bytes(const AsrHandle* h, int B, int beam, int T, int L, size_t* bytes) {
+  if (!h || !bytes || B < 0 || beam < 1 || beam > 16 || T < 7 || L <= 0)
+    return set_error(ASR_E_INVALID, "asr_beam_workspace_bytes: bad argument (1 <= beam <= 16)");
+  Bump b(nullptr);
+  BeamWs w;
+  w.carve(b, h->cfg, B * beam, conv_len(conv_len(T)), L);
+  *bytes = b.off + 256;
+  return 0;
+}
+
+// Beam search on the KV-cached decode step (the reference lists it as a TODO, README.md:30, so
+// the semantics are those of oracle/speech_transformer.py: beam_search_kv_cached).  enc_rep: the encoder output with
+// every utterance repeated `beam` times, (B * beam, Tp, D) fp32 - hypotheses are ordinary batch rows of the step
+// kernels.  tokens int32 (B, beam, L+1) best first; scores fp32 (B, beam) = sum of token log-probabilities.
+int asr_decode_beam(AsrHandle* h, const float* enc_rep, int B, int beam, int Tp, int L, void* ws, size_t ws_bytes,
+                    int32_t* tokens, float* scores, asr_stream_t stream) {
+  if (!h || !h->loaded) return set_error(ASR_E_INVALID, "asr_decode_beam: weights not loaded");
+  if (B == 0) return 0;
+  if (!enc_rep || !tokens || !scores || !ws || B < 0 || beam < 1 || beam > 16 || Tp <= 0 || L <= 0)
+    return set_error(ASR_E_INVALID, "asr_decode_beam: bad argument (1 <= beam <= 16)");
+  const AsrConfig& c = h->cfg;
+  if (L > c.decoder_seq_len)
+    return set_error(ASR_E_INVALID, "asr_decode_beam: L=%d exceeds decoder_seq_len %d", L, c.decoder_seq_len);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int R = B * beam, D = c.embedding_dim, V = c.vocab_size;
+  Bump bump(ws);
+  BeamWs w;
+  w.carve(bump, c, R, Tp, L);
+  if (bump.off > ws_bytes)
+    return set_error(ASR_E_WORKSPACE, "asr_decode_beam: workspace %zu < %zu bytes", ws_bytes, bump.off);
+  const size_t smem = size_t(beam) * V * sizeof(float);
+  if (smem > 200 * 1024) return set_error(ASR_E_UNSUPPORTED, "asr_decode_beam: beam x vocabulary too large");
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(beam_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int M = R * Tp;
+  if (int rc = launch_f32_to_bf16(enc_rep, w.g.enc_bf16, size_t(M) * D, s)) return rc;
+  if (int rc = cross_kv(h, w.g.enc_bf16, w.g.ckv, M, s)) return rc;
+  int32_t* tok_cur = w.tok_a;
+  int32_t* tok_nxt = w.tok_b;
+  bf16* cache_cur = w.g.cache;
+  bf16* cache_nxt = w.cache_alt;
+  beam_init_kernel<<<(R + 127) / 128, 128, 0, s>>>(tok_cur, L + 1, w.score, w.g.finished, w.g.step, R, beam,
+                                                  c.bos_token_id);
+  ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
+  if (int rc = launch_dec_embed(tok_cur, L + 1, w.g.step, h->w.embedding, h->w.dec_pe, R, D, V, w.g.h, s)) return rc;
+  const int vpad = (V + 63) / 64 * 64;
+  for (int t = 0; t < L; ++t) {
+    GreedyWs g = w.g;
+    g.cache = cache_cur;
+    if (int rc = greedy_step(h, g, R, Tp, L, 0, nullptr, nullptr, nullptr, s, nullptr, /*select=*/false)) return rc;
+    beam_select_kernel<<<B, 256, smem, s>>>(g.logits, vpad, V, beam, w.score, w.g.finished, w.parent, w.token,
+                                            c.eos_token_id, c.pad_token_id);
+    ASR_CUDA_OK(cudaGetLastError());
+    beam_reorder_kernel<<<dim3(R, c.decoder_num_layers), 256, 0, s>>>(cache_cur, cache_nxt, tok_cur, tok_nxt, w.parent,
+                                                                      w.token, w.g.step, R, beam, L, 2 * D, t);
+    ASR_CUDA_OK(cudaGetLastError());
+    ASR_LAUNCHED(2);
+    std::swap(cache_cur, cache_nxt);
+    std::swap(tok_cur, tok_nxt);
+    if (t + 1 < L)
+      if (int rc = launch_dec_embed(tok_cur, L + 1, w.g.step, h->w.embedding, h->w.dec_pe, R, D, V, w.g.h, s)) return rc;
+  }
+  ASR_CUDA_OK(cudaMemcpyAsync(tokens, tok_cur, size_t(R) * (L + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+  ASR_CUDA_OK(cudaMemcpyAsync(scores, w.score, size_t(R) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
 }
 
 // Same work as asr_decode_greedy, launched eagerly with a CUDA event pair around every kernel; synchronises the

@@ -401,3 +401,23 @@ class Engine:
                     "keep": (enc_out, first, lens, ws)}
         _l.check(_l.load().asr_decode_greedy(*args, _l.stream()), "asr_decode_greedy")
         return tokens, n_tok, step_logits
+
+    def decode_beam(self, enc_out: torch.Tensor, beam: int, max_len: Optional[int] = None):
+        """Beam search on the KV-cached decode step (asr_decode_beam): enc_out (B,T',D) -> tokens (B, beam, L+1) int32
+        best first, scores (B, beam) fp32 (sum of token log-probabilities, no length normalisation)."""
+        B, Tp, _ = enc_out.shape
+        beam = int(beam)
+        L = int(max_len or self.cfg.decoder_seq_len)
+        dev = enc_out.device
+        tokens = torch.empty(B, beam, L + 1, dtype=torch.int32, device=dev)
+        scores = torch.empty(B, beam, dtype=torch.float32, device=dev)
+        if B == 0:
+            return tokens, scores
+        enc_rep = enc_out.to(torch.float32).repeat_interleave(beam, 0).contiguous()   # hypotheses are batch rows
+        n = C.c_size_t()
+        _l.check(_l.load().asr_beam_workspace_bytes(self.handle, B, beam, 4 * Tp + 3, L, C.byref(n)),
+                 "asr_beam_workspace_bytes")
+        ws = _l.workspace(n.value, self.device, "beam")
+        _l.check(_l.load().asr_decode_beam(self.handle, _l.ptr(enc_rep), B, beam, Tp, L, _l.ptr(ws), ws.numel(),
+                                           _l.ptr(tokens), _l.ptr(scores), _l.stream()), "asr_decode_beam")
+        return tokens, scores

@@ -66,6 +66,9 @@ _SIGNATURES = {
     "asr_encoder_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "asr_decoder_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
                                     c_void_p, c_void_p]),
+    "asr_beam_workspace_bytes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, C.POINTER(c_size_t)]),
+    "asr_decode_beam": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p,
+                                c_void_p]),
     "asr_decode_greedy": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]),
     "asr_decode_prepare": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

@@ -207,6 +207,17 @@ class Transformer(nn.Module):
                                                                enc_lens=self.encoder_lengths(lengths))
         return (tokens, n_tok, step_logits) if return_logits else (tokens, n_tok)
 
+    def beam_search(self, spectrum, beam: int = 4, lengths: Optional[torch.Tensor] = None,
+                    max_len: Optional[int] = None):
+        """Beam search (the reference's README TODO; semantics in ``include/asr_b200.h: asr_decode_beam``):
+        (B,1,F,T) -> tokens (B, beam, L+1) int32 with the best hypothesis first, scores (B, beam) fp32 = sum of the
+        token log-probabilities.  ``beam=1`` equals ``greedy_decode(stop_at_eos=True)``."""
+        _require_eval(self)
+        if not 1 <= int(beam) <= 16:
+            raise ValueError("beam must be in 1..16")
+        enc = self.encode(spectrum, lengths)
+        return self._eng().decode_beam(enc, beam, max_len)
+
     def greedy_decode_batches(self, batches, max_len: Optional[int] = None, stop_at_eos: bool = False,
                               gather=None, to_host: bool = True, coalesce: Optional[int] = None):
         """Pipelined greedy ASR over an iterable of batches ((B,1,F,T) fp32; HOST tensors, ideally pinned, or tensors

@@ -130,6 +130,16 @@ int asr_encoder_forward(AsrHandle* h, const void* z_bf16, int B, int Tp, const i
 int asr_decoder_forward(AsrHandle* h, const float* enc_out, int B, int Tp, const int32_t* text, const uint8_t* valid,
                         int L, void* ws, size_t ws_bytes, float* logits, asr_stream_t stream);
 
+/* Beam search on the KV-cached decode step.  The reference has no beam search (README.md:30 lists
+ * it as a TODO), so the semantics are defined by oracle/speech_transformer.py: beam_search_kv_cached: candidate score =
+ * hypothesis score + log_softmax(logits without the final LayerNorm, model.py:142), no length normalisation, finished
+ * hypotheses (EOS emitted) are carried with pad tokens, ties go to the lower (beam, token) index, exactly L steps.
+ * enc_rep fp32 (B*beam, Tp, D): the encoder output with every utterance repeated `beam` times; tokens int32
+ * (B, beam, L+1) best first; scores fp32 (B, beam).  1 <= beam <= 16; beam == 1 is greedy search that pads after EOS. */
+int asr_beam_workspace_bytes(const AsrHandle* h, int B, int beam, int T, int L, size_t* bytes);
+int asr_decode_beam(AsrHandle* h, const float* enc_rep, int B, int beam, int Tp, int L, void* ws, size_t ws_bytes,
+                    int32_t* tokens, float* scores, asr_stream_t stream);
+
 /* Replaces Decoder.evaluate (model.py:125-151) for the whole batch at once with a device-resident KV cache.
  * tokens int32 (B,L+1) (column 0 = BOS); n_tokens int32 [B] (nullable) = tokens up to and including the first EOS
  * (L+1 if none); step_logits fp32 (B,L,V) nullable: logits (no final LayerNorm, model.py:142) that chose

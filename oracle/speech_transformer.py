@@ -266,6 +266,86 @@ def greedy_kv_cached(sd: StateDict, enc_x: Tensor, cfg: Config, max_len: Optiona
     return tokens, logits_all
 
 
+def beam_search_kv_cached(sd: StateDict, enc_x: Tensor, cfg: Config, beam: int, max_len: Optional[int] = None,
+                          prefix: str = "decoder") -> Tuple[Tensor, Tensor]:
+    """Beam search on the step of :func:`greedy_kv_cached` (same logits: no final LayerNorm, model.py:142).
+
+    The reference has NO beam search (README.md:30 lists it as a TODO), so this function DEFINES the semantics the CUDA
+    path is held to ("parity unpinned" by the reference for this row):
+      * every utterance keeps ``beam`` hypotheses; step 0 starts from one live hypothesis [BOS] with score 0, the others
+        are dead (score -inf);
+      * candidate score = hypothesis score + log_softmax(logits)[token], no length normalisation; a hypothesis that has
+        emitted EOS is finished: its only candidate is itself (same score), extended with the pad token;
+      * the ``beam`` best of the beam x V candidates survive, ties broken by the lower flat index (beam-major, then
+        token) - the lowest-index rule of ``argmax`` (model.py:143) carried over; exactly L steps run.
+    ``beam == 1`` is greedy search that pads after EOS.  Returns (tokens (B, beam, L+1) int64 best first, scores
+    (B, beam) fp32)."""
+    B, Tp, D = enc_x.shape
+    K = int(beam)
+    R = B * K
+    H = cfg.num_heads
+    dh = D // H
+    L = max_len or cfg.decoder_seq_len
+    nl = _num_layers(sd, prefix)
+    scale = D ** (-0.5)
+    emb = sd[prefix + "._embedding.weight"]
+    pe = sd[prefix + "._pe.pe"][0]
+    Wc = sd[prefix + "._classifier.weight"]
+    V = Wc.shape[0]
+    enc_r = enc_x.repeat_interleave(K, 0)
+
+    def heads(t):
+        return t.view(R, -1, H, dh).transpose(1, 2)
+
+    packs = []
+    for l in range(nl):
+        lp = f"{prefix}._layers.{l}"
+        sq, sk, sv = (_packed_heads(sd, lp + "._mask_attention", n) for n in ("_q", "_k", "_v"))
+        cq, ck, cv = (_packed_heads(sd, lp + "._cross_attention", n) for n in ("_q", "_k", "_v"))
+        packs.append((lp, sq, sk, sv, cq, heads(F.linear(enc_r, *ck)), heads(F.linear(enc_r, *cv))))
+
+    tokens = torch.full((R, L + 1), cfg.bos_token_id, dtype=torch.int64)
+    score = torch.full((B, K), float("-inf"))
+    score[:, 0] = 0.0
+    finished = torch.zeros(B, K, dtype=torch.bool)
+    kc = [torch.zeros(R, H, L, dh) for _ in range(nl)]
+    vc = [torch.zeros(R, H, L, dh) for _ in range(nl)]
+    base = (torch.arange(B) * K)[:, None]
+    for t in range(L):
+        h = emb[tokens[:, t]] + pe[t]
+        for l, (lp, sq, sk, sv, cq, ck_x, cv_x) in enumerate(packs):
+            a = layer_norm(sd, lp + "._norm1", h)
+            q = F.linear(a, *sq).view(R, H, 1, dh)
+            kc[l][:, :, t] = F.linear(a, *sk).view(R, H, dh)
+            vc[l][:, :, t] = F.linear(a, *sv).view(R, H, dh)
+            s = (q @ kc[l][:, :, :t + 1].transpose(2, 3)) * scale
+            o = torch.softmax(s, -1) @ vc[l][:, :, :t + 1]
+            h = linear(sd, lp + "._mask_attention._out_linear", o.transpose(1, 2).reshape(R, D)) + h
+            a = layer_norm(sd, lp + "._norm2", h)
+            q = F.linear(a, *cq).view(R, H, 1, dh)
+            s = (q @ ck_x.transpose(2, 3)) * scale
+            o = torch.softmax(s, -1) @ cv_x
+            h = linear(sd, lp + "._cross_attention._out_linear", o.transpose(1, 2).reshape(R, D)) + h
+            h = feed_forward(sd, lp + "._feedforward", layer_norm(sd, lp + "._norm3", h)) + h
+        logp = torch.log_softmax(F.linear(h, Wc), -1).view(B, K, V)
+        cand = score[:, :, None] + logp
+        keep = torch.full((B, K, V), float("-inf"))
+        keep[:, :, cfg.pad_token_id] = score
+        cand = torch.where(finished[:, :, None], keep, cand).view(B, K * V)
+        val, idx = torch.sort(cand, dim=1, descending=True, stable=True)       # stable: lower flat index wins ties
+        val, idx = val[:, :K], idx[:, :K]
+        parent, tok = idx // V, idx % V
+        rows = (base + parent).reshape(-1)
+        tokens = tokens[rows]
+        tokens[:, t + 1] = tok.reshape(-1)
+        for l in range(nl):
+            kc[l] = kc[l][rows]
+            vc[l] = vc[l][rows]
+        finished = torch.gather(finished, 1, parent) | (tok == cfg.eos_token_id)
+        score = val
+    return tokens.view(B, K, L + 1), score
+
+
 def greedy(sd: StateDict, spectrum: Tensor, cfg: Config) -> Tuple[Tensor, Tensor]:
     return greedy_kv_cached(sd, encode(sd, spectrum), cfg)
 

@@ -304,3 +304,47 @@ def test_key_padding_end_to_end_decode(t0):
     # without the lengths the padded frames leak into the cross attention: the logits differ
     _, _, lg_nomask = m.greedy_decode(padded, return_logits=True)
     assert (lg_nomask[1] - lg1[0]).abs().max() > 1e-3
+
+
+# ----------------------------------------------------------------------------------------------- beam search (8f rank 4)
+def _check_beams(tok_ref, sc_ref, tok, sc, what):
+    """Identical hypotheses, or - when fp32 rounding reorders two candidates - scores that agree to 1e-3."""
+    tok, sc = tok.cpu().long(), sc.cpu()
+    assert tok.shape == tok_ref.shape and sc.shape == sc_ref.shape, what
+    fin = torch.isfinite(sc_ref)
+    assert torch.equal(fin, torch.isfinite(sc)), what
+    assert (sc[fin] - sc_ref[fin]).abs().max().item() < 5e-2, (what, sc, sc_ref)
+    same = int((tok == tok_ref).all(-1).sum())
+    best_same = int((tok[:, 0] == tok_ref[:, 0]).all(-1).sum())
+    return same / max(1, tok_ref.shape[0] * tok_ref.shape[1]), best_same / max(1, tok_ref.shape[0])
+
+
+@pytest.mark.parametrize("beam", [1, 3, 4])
+def test_beam_search_T0(t0, beam):
+    """The CUDA beam search against the CPU oracle's definition on the tiny config; beam 1 == greedy that pads at EOS."""
+    cfg, fx, m, spec = t0
+    sd = cpu_state(m)
+    tok_ref, sc_ref = O.beam_search_kv_cached(sd, O.encode(sd, spec.cpu()), cfg, beam)
+    tok, sc = m.beam_search(spec, beam=beam)
+    frac, best = _check_beams(tok_ref, sc_ref, tok, sc, f"beam {beam}")
+    assert best == 1.0 and frac >= 0.9, (frac, best)
+    if beam == 1:
+        tg, _ = m.greedy_decode(spec, stop_at_eos=True)
+        assert torch.equal(tok[:, 0], tg)
+    else:   # a wider beam never scores worse than greedy under the same scoring
+        t1, s1 = m.beam_search(spec, beam=1)
+        assert (sc[:, 0] >= s1[:, 0] - 1e-4).all()
+        assert (sc[:, :-1] >= sc[:, 1:]).all()
+
+
+def test_beam_search_C2_sizes():
+    """BASELINE model size (C2 weights, 10 s utterances), 8 utterances x beam 4, 48 steps, against the oracle."""
+    cfg = O.CONFIGS["C2"]
+    m = build_model(cfg, DEV)
+    sd = cpu_state(m)
+    spec = O.structured_spectrum(8, cfg.frames, cfg.input_dim, seed=41)
+    torch.set_num_threads(os.cpu_count() or 1)
+    tok_ref, sc_ref = O.beam_search_kv_cached(sd, O.encode(sd, spec), cfg, 4, max_len=48)
+    tok, sc = m.beam_search(spec.to(DEV), beam=4, max_len=48)
+    frac, best = _check_beams(tok_ref, sc_ref, tok, sc, "C2 beam 4")
+    assert best >= 0.75 and frac >= 0.6, (frac, best)   # bf16 operands may swap near-equal hypotheses

@@ -130,3 +130,30 @@ def test_oracle_against_live_reference():
         tok_o, probs_o, _ = O.evaluate_reference_style(sd, spec, cfg)
         assert torch.equal(tok_ref, tok_o) and len(probs_ref) == len(probs_o)
         assert all(torch.allclose(a, b, atol=2e-4) for a, b in zip(probs_ref, probs_o))
+
+
+def test_beam_search_definition():
+    """The oracle's beam search (the semantics the CUDA path is held to; the reference has none, README.md:30):
+    beam 1 is the greedy search of model.py:125-151 padded after EOS, a wider beam never scores worse, hypotheses
+    come out best first, and every reported score is the sum of the log-probabilities of its tokens."""
+    cfg = O.CONFIGS["T0"]
+    m = build_model(cfg)
+    sd = cpu_state(m)
+    spec = O.structured_spectrum(cfg.batch, cfg.frames, cfg.input_dim, seed=1)
+    enc = O.encode(sd, spec)
+    tg, lg = O.greedy_kv_cached(sd, enc, cfg)
+    t1, s1 = O.beam_search_kv_cached(sd, enc, cfg, 1)
+    for b in range(cfg.batch):
+        ref = tg[b].clone()
+        eos = (ref[1:] == cfg.eos_token_id).nonzero()
+        if eos.numel():
+            ref[int(eos[0]) + 2:] = cfg.pad_token_id
+        assert torch.equal(t1[b, 0], ref)
+        n = int(eos[0]) + 1 if eos.numel() else cfg.decoder_seq_len        # scored steps
+        lp = torch.log_softmax(lg[b], -1)
+        want = sum(float(lp[t, tg[b, t + 1]]) for t in range(n))
+        assert abs(float(s1[b, 0]) - want) < 1e-3
+    t4, s4 = O.beam_search_kv_cached(sd, enc, cfg, 4)
+    assert t4.shape == (cfg.batch, 4, cfg.decoder_seq_len + 1)
+    assert (s4[:, 0] >= s1[:, 0] - 1e-5).all() and (s4[:, :-1] >= s4[:, 1:]).all()
+    assert len({tuple(r.tolist()) for r in t4[0]}) == 4                   # distinct hypotheses
