@@ -7,6 +7,7 @@
 //   warp 4  : TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B, 64-wide K blocks, STAGES-deep mbarrier ring)
 //   warp 5  : UMMA issuer   (one elected thread, tcgen05.mma kind::f16, fp32 accumulators in TMEM)
 //   warps 0-3: epilogue     (tcgen05.ld 32 lanes x 32 columns per warp -> registers -> fused epilogue -> HBM)
+#include <cstdio>
 #include <cstdlib>
 
 #include "kernels.h"
@@ -331,11 +332,16 @@ int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilog
   static int n_slots = 0;   // resident CTAs on the device (persistent grid size)
   if (!attr_set) {
     ASR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // ask for the largest shared-memory carve-out: with the default one a single 98 KB CTA is all an SM gets
+    ASR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int dev = 0, n_sm = 0, occ = 1;
     ASR_CUDA_OK(cudaGetDevice(&dev));
     ASR_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     ASR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GEMM_THREADS, smem));
     n_slots = n_sm * (occ < 1 ? 1 : occ);
+    if (std::getenv("ASR_B200_DEBUG"))
+      fprintf(stderr, "gemm_tc<%d,%d,%d>: smem %zu B, occupancy %d CTAs/SM, %d persistent CTAs\n", BN, STAGES, FLAGS, smem,
+              occ, n_slots);
     attr_set = true;
   }
   const int tiles_n = n_pad / BN, n_tiles = tiles_n * ((M + BM - 1) / BM);
@@ -408,8 +414,8 @@ int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N,
     int rc = make_tmap_bf16(&tmA, X, 2, dims, str, box, nullptr);
     if (rc) return rc;
   }
-  // Tile choice: 128-wide tiles (2 x 128 TMEM columns), 3-stage TMA ring (97 KB, two CTAs per SM; ASR_B200_GEMM_STAGES=6
-  // selects the 192 KB one-CTA variant); 64-wide when N is not a multiple of 128.  ASR_B200_GEMM_TILE (128 / 64)
+  // Tile choice: 128-wide tiles (2 x 128 TMEM columns), 3-stage TMA ring (98 KB; ASR_B200_GEMM_STAGES=6 selects the
+  // 192 KB variant); 64-wide when N is not a multiple of 128.  ASR_B200_GEMM_TILE (128 / 64)
   // forces a width for experiments.
   int bn = (n_pad % 128 == 0) ? 128 : 64;
   if (const char* e = std::getenv("ASR_B200_GEMM_TILE")) {
@@ -429,9 +435,10 @@ int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N,
   }();
   switch (bn) {
     case 128:
-      // 3-stage ring = 97 KB: two persistent CTAs per SM.  Alone the 6-stage / one-CTA variant is 4 % faster, but the
-      // encoder runs beside the cluster decoder on the ~20 SMs it leaves free, where two CTAs per SM hide the
-      // epilogue latency better and disturb the decoder less (serving loop: 12.22 -> 12.06 ms per 128 utterances)
+      // 3-stage ring (98 KB) by default.  Alone the 6-stage (192 KB) variant is 4 % faster, but the encoder runs beside
+      // the cluster decoder on the ~20 SMs it leaves free, and there the shallower ring measured better for both
+      // (serving loop: 12.22 -> 12.06 ms per 128 utterances).  The grid follows the occupancy the runtime reports
+      // (1 CTA per SM on the B200 driver used here; forcing 2 per SM changed nothing in the serving loop).
       if (stages == 6) return launch_one<128, 6>(tmA, tmB, ep, M, n_store, n_pad, K, s);
       return launch_one<128, 3>(tmA, tmB, ep, M, n_store, n_pad, K, s);
     default: return launch_one<64, 8>(tmA, tmB, ep, M, n_store, n_pad, K, s);

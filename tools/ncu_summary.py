@@ -84,7 +84,39 @@ def full(src, dst, title=""):
             f.write("\n")
 
 
+def table(src, dst, title=""):
+    """One row per captured launch: duration, tensor-pipe activity, DRAM throughput, occupancy."""
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr = rows[0]
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full, one row per launch ({src})\n\n{title}\n\n")
+        f.write("| kernel | grid | block | time us | tensor pipe active % | DRAM GB/s (read+write) | DRAM % of peak | L2 % | "
+                "regs | warps active % | CTAs/SM limit (smem) |\n|---|---|---|---:|---:|---:|---:|---:|---:|---:|---:|\n")
+        for r in rows[2:]:
+            d = dict(zip(hdr, r))
+
+            def g(k, default=0.0):
+                try:
+                    return float(d.get(k, default))
+                except ValueError:
+                    return default
+            t_us = g("gpu__time_duration.sum")
+            unit = dict(zip(hdr, rows[1])).get("gpu__time_duration.sum", "us")
+            t_us *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(unit, 1.0)
+            units = dict(zip(hdr, rows[1]))
+            def to_bytes(k):
+                return g(k) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units.get(k, "byte"), 1)
+            by = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+            f.write(f"| `{short(d.get('Kernel Name', ''))}` | {d.get('Grid Size')} | {d.get('Block Size')} | {t_us:.1f} | "
+                    f"{g('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'):.1f} | "
+                    f"{by / max(t_us, 1e-9) / 1e3:.0f} | {g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
+                    f"{g('lts__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | {int(g('launch__registers_per_thread'))} | "
+                    f"{g('sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | "
+                    f"{int(g('launch__occupancy_limit_shared_mem'))} |\n")
+
+
 if __name__ == "__main__":
     mode, src, dst = sys.argv[1:4]
     title = sys.argv[4] if len(sys.argv) > 4 else ""
-    (launches if mode == "launches" else full)(src, dst, title)
+    {"launches": launches, "full": full, "table": table}[mode](src, dst, title)
