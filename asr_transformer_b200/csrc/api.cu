@@ -542,6 +542,19 @@ int asr_workspace_bytes(const AsrHandle* h, int B, int T, int L, size_t* bytes) 
   return 0;
 }
 
+// Transformer.input_layer: the fused kernel when its tile fits shared memory (ASR_B200_CONV=split forces the two-kernel
+// path, kept as the fallback for very wide inputs and as the cross-check in the tests)
+static int conv_frontend(const float* spec, const float* w1, const float* b1, const bf16* w2frag, const float* b2, int B,
+                         int F, int T, bf16* y1, bf16* z, cudaStream_t s) {
+  const char* e = std::getenv("ASR_B200_CONV");
+  if (!(e && e[0] == 's')) {
+    const int rc = launch_conv_fused(spec, w1, b1, w2frag, b2, B, F, T, z, s);
+    if (rc <= 0) return rc;
+  }
+  if (int rc = launch_conv1(spec, w1, b1, B, F, T, y1, s)) return rc;
+  return launch_conv2(y1, w2frag, b2, B, conv_len(F), conv_len(T), z, s);
+}
+
 static int encoder_core(AsrHandle* h, const EncodeWs& w, int B, int T2, const int32_t* enc_lens, float* enc_out,
                         cudaStream_t s) {
   const AsrConfig& c = h->cfg;
@@ -579,8 +592,9 @@ int asr_encode(AsrHandle* h, const float* spectrum, int B, int T, const int32_t*
   EncodeWs w;
   w.carve(bump, c, B, T);
   if (bump.off > ws_bytes) return set_error(ASR_E_WORKSPACE, "asr_encode: workspace %zu < %zu bytes", ws_bytes, bump.off);
-  if (int rc = launch_conv1(spectrum, h->w.conv1_w, h->w.conv1_b, B, c.input_dim, T, w.y1, s)) return rc;
-  if (int rc = launch_conv2(w.y1, static_cast<const bf16*>(h->w.conv2_wfrag), h->w.conv2_b, B, F1, T1, w.z, s)) return rc;
+  if (int rc = conv_frontend(spectrum, h->w.conv1_w, h->w.conv1_b, static_cast<const bf16*>(h->w.conv2_wfrag),
+                             h->w.conv2_b, B, c.input_dim, T, w.y1, w.z, s))
+    return rc;
   return encoder_core(h, w, B, T2, enc_lens, enc_out, s);
 }
 
@@ -1101,9 +1115,8 @@ int asr_conv_frontend(const float* spectrum, const float* conv1_w, const float* 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Bump b(ws);
   bf16* y1 = b.take<bf16>(size_t(B) * conv_len(T) * conv_len(F) * 64);
-  if (int rc = launch_conv1(spectrum, conv1_w, conv1_b, B, F, T, y1, s)) return rc;
-  return launch_conv2(y1, static_cast<const bf16*>(conv2_wfrag), conv2_b, B, conv_len(F), conv_len(T),
-                      static_cast<bf16*>(z_bf16), s);
+  return conv_frontend(spectrum, conv1_w, conv1_b, static_cast<const bf16*>(conv2_wfrag), conv2_b, B, F, T, y1,
+                       static_cast<bf16*>(z_bf16), s);
 }
 
 int asr_spectrogram(const float* audio, int B, int n_samples, int n_fft, int hop, int T, float* spec,

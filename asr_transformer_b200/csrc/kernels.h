@@ -84,6 +84,10 @@ int launch_f32_to_bf16(const float* x, bf16* y, size_t n, cudaStream_t s);
 int launch_conv1(const float* spec, const float* w1 /*[9][64]*/, const float* b1, int B, int F, int T, bf16* y1,
                  cudaStream_t s);
 // conv2: y1 -> z bf16 (B, T2, F2*64) with column order (f, c)
+// conv1 + conv2 in one kernel (the bf16 intermediate stays in shared memory); returns 1 if it does not fit -> use the
+// two kernels below.  w2frag: pack_conv2_fragments order.
+int launch_conv_fused(const float* spec, const float* w1, const float* b1, const bf16* w2frag, const float* b2, int B,
+                      int F, int T, bf16* z, cudaStream_t s);
 int launch_conv2(const bf16* y1, const bf16* w2 /*[64 co][9][64 ci]*/, const float* b2, int B, int F1, int T1,
                  bf16* z, cudaStream_t s);
 

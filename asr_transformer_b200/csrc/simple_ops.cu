@@ -224,6 +224,134 @@ conv2_kernel(const bf16* __restrict__ y1, const uint2* __restrict__ wfrag, const
   }
 }
 
+
+// ---------------------------------------------------------------- fused front-end: conv1 + ReLU + conv2 + ReLU
+// One kernel for Transformer.input_layer (model.py:168-171).  The (B, T1, F1, 64) bf16 intermediate (159 MB at C2) never
+// leaves the SM: a persistent CTA owns a tile of TT2 output frames x all F2 output bins of one utterance, computes the
+// conv1 patch it needs ((2 TT2 + 1) x F1 pixels x 64 channels, fp32 FMAs from a shared-memory patch of the spectrogram)
+// into shared memory as bf16 and runs conv2 on it as an implicit GEMM with mma.sync (same fragment-packed weights and
+// the same arithmetic as conv1_kernel + conv2_kernel, so the two paths give identical bits).  The patch stores the
+// 16-byte channel chunks of a pixel XOR-swizzled by bit 1 of its frequency index, which makes the A-fragment loads of
+// neighbouring output pixels (input pixels two apart) land in different bank halves.
+constexpr int CONVF_THREADS = 256;
+__global__ void __launch_bounds__(CONVF_THREADS, 1)
+conv_fused_kernel(const float* __restrict__ spec, const float* __restrict__ w1, const float* __restrict__ b1,
+                  const uint2* __restrict__ wfrag, const float* __restrict__ b2, int B, int F, int T, int F1, int F2,
+                  int T2, int TT2, int n_tt, bf16* __restrict__ z) {
+  extern __shared__ __align__(16) uint8_t convf_smem[];
+  uint2* sw = reinterpret_cast<uint2*>(convf_smem);                        // [36][8][32] conv2 fragments
+  float* sw1 = reinterpret_cast<float*>(convf_smem + CONV2_W_BYTES);       // [9][64] conv1 taps
+  float* sb1 = sw1 + 9 * 64;                                               // [64]
+  float* sx = sb1 + 64;                                                    // [F][W] spectrogram patch
+  const int W = 4 * TT2 + 3;
+  bf16* sy = reinterpret_cast<bf16*>(sx + ((size_t(F) * W + 3) & ~size_t(3)));   // [(2 TT2 + 1)][F1][64] conv1 patch
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, c = lane & 3;
+  for (int i = tid; i < CONV2_KSTEPS * 8 * 32; i += CONVF_THREADS) sw[i] = wfrag[i];
+  for (int i = tid; i < 9 * 64; i += CONVF_THREADS) sw1[i] = w1[i];
+  if (tid < 64) sb1[tid] = b1[tid];
+  const int n_tiles = B * n_tt;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / n_tt, t20 = (tile - b * n_tt) * TT2, ntt = min(TT2, T2 - t20);
+    __syncthreads();                                     // the previous tile's MMAs are done with sx / sy
+    // ---- spectrogram patch: all F bins x the 4 ntt + 3 input frames of this tile
+    const int c0 = 4 * t20, wcols = 4 * ntt + 3;
+    const float* xin = spec + size_t(b) * F * T + c0;
+    for (int i = tid; i < F * W; i += CONVF_THREADS) {
+      const int f = i / W, cc = i - f * W;
+      sx[i] = (cc < wcols && c0 + cc < T) ? __ldg(xin + size_t(f) * T + cc) : 0.f;
+    }
+    __syncthreads();
+    // ---- conv1 + ReLU -> bf16 patch; 8 threads per pixel, 8 channels each (the arithmetic of conv1_kernel)
+    {
+      const int cg = tid & 7;
+      float wr[9][8], bias[8];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) wr[tap][k] = sw1[tap * 64 + cg * 8 + k];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) bias[k] = sb1[cg * 8 + k];
+      const int npix = (2 * ntt + 1) * F1;
+      for (int pix = tid >> 3; pix < npix; pix += CONVF_THREADS / 8) {
+        const int r = pix / F1, f1 = pix - r * F1;
+        const float* xp = sx + (2 * f1) * W + 2 * r;
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = bias[k];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float x = xp[kh * W + kw];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = fmaf(x, wr[kh * 3 + kw][k], acc[k]);
+          }
+        uint4 o;
+        o.x = pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
+        o.y = pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
+        o.z = pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
+        o.w = pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+        *reinterpret_cast<uint4*>(sy + size_t(pix) * 64 + ((cg ^ (((f1 >> 1) & 1) << 2)) << 3)) = o;
+      }
+    }
+    __syncthreads();
+    // ---- conv2 + ReLU: implicit GEMM, 16 output pixels x 64 channels per warp pass
+    const int npx = ntt * F2, n_mt = (npx + 15) >> 4;
+    for (int mt = warp; mt < n_mt; mt += CONVF_THREADS / 32) {
+      const int m_lo = mt * 16 + g, m_hi = m_lo + 8;
+      int pbase[2], fpar[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int m = min(i ? m_hi : m_lo, npx - 1);       // clamp (stores are predicated)
+        const int tt = m / F2, f2 = m - tt * F2;
+        pbase[i] = (2 * tt) * F1 + 2 * f2;
+        fpar[i] = f2 & 1;
+      }
+      float acc[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap) {
+        const int kh = tap / 3, kw = tap - kh * 3;
+        const int poff = kw * F1 + kh;
+        const int s0 = ((fpar[0] + (kh >> 1)) & 1) << 2, s1 = ((fpar[1] + (kh >> 1)) & 1) << 2;   // swizzle of the input pixel
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint4 vlo = *reinterpret_cast<const uint4*>(sy + size_t(pbase[0] + poff) * 64 + (((half * 4 + c) ^ s0) << 3));
+          const uint4 vhi = *reinterpret_cast<const uint4*>(sy + size_t(pbase[1] + poff) * 64 + (((half * 4 + c) ^ s1) << 3));
+          const uint2* wk = sw + size_t((tap * 2 + half) * 2) * 8 * 32 + lane;
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) {
+            const uint2 w0 = wk[nt * 32];
+            const uint2 w1v = wk[8 * 32 + nt * 32];
+            mma_bf16_16816(acc[nt], vlo.x, vhi.x, vlo.y, vhi.y, w0.x, w0.y);
+            mma_bf16_16816(acc[nt], vlo.z, vhi.z, vlo.w, vhi.w, w1v.x, w1v.y);
+          }
+        }
+      }
+      bf16* zb = z + (size_t(b) * T2 + t20) * F2 * 64;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int co = nt * 8 + 2 * c;
+        const float bb0 = __ldg(b2 + co), bb1 = __ldg(b2 + co + 1);
+        if (m_lo < npx)
+          *reinterpret_cast<uint32_t*>(zb + size_t(m_lo) * 64 + co) =
+              pack_bf16x2(fmaxf(acc[nt][0] + bb0, 0.f), fmaxf(acc[nt][1] + bb1, 0.f));
+        if (m_hi < npx)
+          *reinterpret_cast<uint32_t*>(zb + size_t(m_hi) * 64 + co) =
+              pack_bf16x2(fmaxf(acc[nt][2] + bb0, 0.f), fmaxf(acc[nt][3] + bb1, 0.f));
+      }
+    }
+  }
+}
+
+size_t conv_fused_smem(int F, int F1, int TT2) {
+  const size_t W = 4 * size_t(TT2) + 3;
+  return CONV2_W_BYTES + (9 * 64 + 64) * 4 + ((size_t(F) * W + 3) & ~size_t(3)) * 4 + (2 * size_t(TT2) + 1) * F1 * 128;
+}
+
 }  // namespace
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int D, float eps, float* y_f32,
@@ -272,6 +400,41 @@ int launch_conv1(const float* spec, const float* w1, const float* b1, int B, int
   }
   dim3 grid((T1 + CONV1_TT - 1) / CONV1_TT, B);
   conv1_kernel<<<grid, 256, smem, s>>>(spec, w1, b1, B, F, T, F1, T1, y1);
+  ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
+  return 0;
+}
+
+// Fused front-end; returns 1 (and launches nothing) when no tile size fits the shared memory, so that the caller can
+// fall back to conv1_kernel + conv2_kernel.
+int launch_conv_fused(const float* spec, const float* w1, const float* b1, const bf16* w2frag, const float* b2, int B,
+                      int F, int T, bf16* z, cudaStream_t s) {
+  const int F1 = (F - 3) / 2 + 1, T1 = (T - 3) / 2 + 1, F2 = (F1 - 3) / 2 + 1, T2 = (T1 - 3) / 2 + 1;
+  if (F2 <= 0 || T2 <= 0) return set_error(-2, "conv: input %dx%d too small", F, T);
+  static int n_sm = 0, max_smem = 0;
+  if (!n_sm) {
+    int dev = 0;
+    ASR_CUDA_OK(cudaGetDevice(&dev));
+    ASR_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    ASR_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // frames per tile: fill the 8 warps' 16-pixel passes (128 pixels) without exceeding the shared memory
+  int TT2 = 0;
+  for (int t = 1; t <= 8 && t <= T2; ++t)
+    if (conv_fused_smem(F, F1, t) <= size_t(max_smem) && t * F2 <= 128) TT2 = t;
+  if (TT2 == 0 && conv_fused_smem(F, F1, 1) <= size_t(max_smem)) TT2 = 1;
+  if (TT2 == 0) return 1;
+  const size_t smem = conv_fused_smem(F, F1, TT2);
+  static size_t configured = 0;
+  if (smem > configured) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(conv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int n_tt = (T2 + TT2 - 1) / TT2;
+  const long long n_tiles = (long long)B * n_tt;
+  const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
+  conv_fused_kernel<<<grid, CONVF_THREADS, smem, s>>>(spec, w1, b1, reinterpret_cast<const uint2*>(w2frag), b2, B, F, T,
+                                                      F1, F2, T2, TT2, n_tt, z);
   ASR_CUDA_OK(cudaGetLastError());
   ASR_LAUNCHED(1);
   return 0;

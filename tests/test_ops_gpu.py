@@ -244,6 +244,23 @@ def test_conv_frontend(B, Fdim, T):
     assert_close(out, ref, 6e-2, 4e-3, "conv front-end")    # conv1 output and conv2 result are rounded to bf16
 
 
+@pytest.mark.parametrize("B,Fdim,T", [(2, 80, 200), (3, 80, 1000), (3, 33, 71), (1, 513, 311), (2, 80, 7), (1, 11, 45)])
+def test_conv_fused_equals_split(B, Fdim, T, monkeypatch):
+    """The fused front-end (conv1 patch kept in shared memory) and the two-kernel path do the same arithmetic in the
+    same order: bit-identical outputs, including ragged last tiles and inputs wider than one tile."""
+    import asr_transformer_b200 as A
+    torch.manual_seed(3)
+    front = A.ConvFrontEnd(torch.nn.Conv2d(1, 64, 3, stride=2), torch.nn.ReLU(), torch.nn.Conv2d(64, 64, 3, stride=2),
+                           torch.nn.ReLU()).to(DEV)
+    spec = O.structured_spectrum(B, T, Fdim, seed=4).to(DEV)
+    monkeypatch.setenv("ASR_B200_CONV", "split")
+    ref = front(spec)
+    monkeypatch.setenv("ASR_B200_CONV", "")
+    out = front(spec)
+    sync()
+    assert out.shape == ref.shape and torch.equal(out, ref)
+
+
 def test_embed_pe():
     V, D, B, Ls = 250, 256, 3, 17
     emb, pe = rnd(V, D, seed=40), rnd(64, D, seed=41)
