@@ -30,7 +30,7 @@ namespace {
 
 constexpr int NCW = 8;                    // consumer warps (16 measured slower: per-warp fixed costs dominate, not divisible work)
 constexpr int NCT = NCW * 32;             // consumer threads
-constexpr int NTHREADS = NCT + 128;       // + producer warpgroup (one working thread; it exists to donate registers)
+constexpr int NTHREADS = NCT + 32;        // + producer warp (one working thread)
 constexpr int STAGE_BYTES = 32768;
 constexpr int MAX_STAGES = 6;
 constexpr float LOG2E = 1.4426950408889634f;
@@ -684,8 +684,8 @@ __device__ __forceinline__ void attn_finish(AttnT& st, int GU, float* part_buf, 
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-// Registers: 12 warps = 3 per scheduler = 168 per thread at launch (512 per scheduler lane).  The producer warpgroup
-// then shrinks to 40 and the two consumer warpgroups grow to 232 (setmaxnreg moves registers inside the CTA's pool).
+// Registers: 9 warps put three on one scheduler, so ptxas stops at 168 per thread; the bodies need 151 (no spills).
+// (setmaxnreg with a donor warpgroup was tried: ptxas drops the pair unless the producer branch fits 40 registers.)
 template <class S>
 __global__ void __launch_bounds__(NTHREADS, 1)
 dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constant__ CUtensorMap ckv_map) {
@@ -757,7 +757,6 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
 
   if (warp >= NCW) {
     // =============================== producer: one thread walks the static access sequence
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (tid == NCT) {
       const uint64_t pol_w = policy_evict_last();
       const uint64_t pol_kv = p.kv_evict_first ? policy_evict_first() : policy_evict_last();
@@ -826,7 +825,6 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
     __syncwarp();
   } else {
     // ================================= consumers
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     Consumer c;
     c.r = ring;
     const bool timed = p.timing != nullptr;
