@@ -261,36 +261,39 @@ conv_fused_kernel(const float* __restrict__ spec, const float* __restrict__ w1, 
       sx[i] = (cc < wcols && c0 + cc < T) ? __ldg(xin + size_t(f) * T + cc) : 0.f;
     }
     __syncthreads();
-    // ---- conv1 + ReLU -> bf16 patch; 8 threads per pixel, 8 channels each (the arithmetic of conv1_kernel)
+    // ---- conv1 + ReLU -> bf16 patch; 8 threads per pixel, 8 channels each.  The arithmetic of conv1_kernel (one
+    // fused multiply-add per tap and channel, taps in the same order), issued as packed fp32x2 FMAs (FFMA2, sm_100):
+    // same bits, half the issue slots - this phase is what bounds the kernel.
     {
       const int cg = tid & 7;
-      float wr[9][8], bias[8];
+      float2 wr[9][4], bias[4];
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) wr[tap][k] = sw1[tap * 64 + cg * 8 + k];
+        for (int k = 0; k < 4; ++k) wr[tap][k] = *reinterpret_cast<const float2*>(sw1 + tap * 64 + cg * 8 + 2 * k);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) bias[k] = sb1[cg * 8 + k];
+      for (int k = 0; k < 4; ++k) bias[k] = *reinterpret_cast<const float2*>(sb1 + cg * 8 + 2 * k);
       const int npix = (2 * ntt + 1) * F1;
       for (int pix = tid >> 3; pix < npix; pix += CONVF_THREADS / 8) {
         const int r = pix / F1, f1 = pix - r * F1;
         const float* xp = sx + (2 * f1) * W + 2 * r;
-        float acc[8];
+        float2 acc[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[k] = bias[k];
+        for (int k = 0; k < 4; ++k) acc[k] = bias[k];
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) {
             const float x = xp[kh * W + kw];
+            const float2 xx = make_float2(x, x);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) acc[k] = fmaf(x, wr[kh * 3 + kw][k], acc[k]);
+            for (int k = 0; k < 4; ++k) acc[k] = __ffma2_rn(xx, wr[kh * 3 + kw][k], acc[k]);
           }
         uint4 o;
-        o.x = pack_bf16x2(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f));
-        o.y = pack_bf16x2(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f));
-        o.z = pack_bf16x2(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f));
-        o.w = pack_bf16x2(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f));
+        o.x = pack_bf16x2(fmaxf(acc[0].x, 0.f), fmaxf(acc[0].y, 0.f));
+        o.y = pack_bf16x2(fmaxf(acc[1].x, 0.f), fmaxf(acc[1].y, 0.f));
+        o.z = pack_bf16x2(fmaxf(acc[2].x, 0.f), fmaxf(acc[2].y, 0.f));
+        o.w = pack_bf16x2(fmaxf(acc[3].x, 0.f), fmaxf(acc[3].y, 0.f));
         *reinterpret_cast<uint4*>(sy + size_t(pix) * 64 + ((cg ^ (((f1 >> 1) & 1) << 2)) << 3)) = o;
       }
     }
