@@ -250,20 +250,33 @@ conv_fused_kernel(const float* __restrict__ spec, const float* __restrict__ w1, 
   for (int i = tid; i < 9 * 64; i += CONVF_THREADS) sw1[i] = w1[i];
   if (tid < 64) sb1[tid] = b1[tid];
   const int n_tiles = B * n_tt;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int b = tile / n_tt, t20 = (tile - b * n_tt) * TT2, ntt = min(TT2, T2 - t20);
-    __syncthreads();                                     // the previous tile's MMAs are done with sx / sy
-    // ---- spectrogram patch: all F bins x the 4 ntt + 3 input frames of this tile
+  // spectrogram patch of a tile: all F bins x its 4 ntt + 3 input frames, fetched with 4-byte cp.async so that every
+  // load of the patch is in flight at once; the patch of tile i + 1 is requested as soon as conv1 of tile i has consumed
+  // sx and lands under the MMAs of tile i
+  auto load_patch = [&](int tl) {
+    const int b = tl / n_tt, t20 = (tl - b * n_tt) * TT2, ntt = min(TT2, T2 - t20);
     const int c0 = 4 * t20, wcols = 4 * ntt + 3;
     const float* xin = spec + size_t(b) * F * T + c0;
     for (int i = tid; i < F * W; i += CONVF_THREADS) {
       const int f = i / W, cc = i - f * W;
-      sx[i] = (cc < wcols && c0 + cc < T) ? __ldg(xin + size_t(f) * T + cc) : 0.f;
+      if (cc < wcols && c0 + cc < T) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(sx + i)), "l"(xin + size_t(f) * T + cc)
+                     : "memory");
+      } else {
+        sx[i] = 0.f;
+      }
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (blockIdx.x < n_tiles) load_patch(blockIdx.x);
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int b = tile / n_tt, t20 = (tile - b * n_tt) * TT2, ntt = min(TT2, T2 - t20);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                     // patch complete; the previous tile's MMAs are done with sy
     // ---- conv1 + ReLU -> bf16 patch; 8 threads per pixel, 8 channels each.  The arithmetic of conv1_kernel (one
     // fused multiply-add per tap and channel, taps in the same order), issued as packed fp32x2 FMAs (FFMA2, sm_100):
-    // same bits, half the issue slots - this phase is what bounds the kernel.
+    // same bits, half the issue slots.  (The kernel is instruction-bound overall: 34 k warp instructions per tile at
+    // 1.7 IPC, a third of them the m16n8k16 MMAs and their per-MMA weight-fragment loads.)
     {
       const int cg = tid & 7;
       float2 wr[9][4], bias[4];
@@ -298,6 +311,7 @@ conv_fused_kernel(const float* __restrict__ spec, const float* __restrict__ w1, 
       }
     }
     __syncthreads();
+    if (tile + int(gridDim.x) < n_tiles) load_patch(tile + gridDim.x);   // sx is free: prefetch under the MMAs
     // ---- conv2 + ReLU: implicit GEMM, 16 output pixels x 64 channels per warp pass
     const int npx = ntt * F2, n_mt = (npx + 15) >> 4;
     for (int mt = warp; mt < n_mt; mt += CONVF_THREADS / 32) {
