@@ -327,6 +327,16 @@ class Transformer(nn.Module):
                 t.record_stream(dec_s)
             with torch.cuda.stream(dec_s):
                 tokens, n_tok, _ = eng.decode_greedy(None, phase=ctx)
+                done = torch.cuda.Event()
+                done.record(dec_s)
+            ws_done[ctx["slot"]] = done
+            nxt = stage_in(next(it, None))            # next group: upload + encoder under this group's decode
+            # transcript side (its own stream, so that neither the multi-GPU gather - a rendezvous of all ranks - nor
+            # the download ever sits between two decode launches)
+            with torch.cuda.stream(down_s):
+                down_s.wait_event(done)
+                tokens.record_stream(down_s)
+                n_tok.record_stream(down_s)
                 if gather is not None:                 # per input batch: every rank contributes its slice of batch j
                     o, tl, nl = 0, [], []
                     for sz in sizes:
@@ -336,25 +346,18 @@ class Transformer(nn.Module):
                         o += sz
                     sizes = [int(t.shape[0]) for t in tl]
                     tokens, n_tok = (tl[0], nl[0]) if len(tl) == 1 else (torch.cat(tl, 0), torch.cat(nl, 0))
-                done = torch.cuda.Event()
-                done.record(dec_s)
-            ws_done[ctx["slot"]] = done
-            nxt = stage_in(next(it, None))            # next group: upload + encoder under this group's decode
-            if to_host:
-                with torch.cuda.stream(down_s):
-                    down_s.wait_event(done)
+                if to_host:
                     th, nh = pinned(tokens, (step % 3, 0)), pinned(n_tok, (step % 3, 1))
                     th.copy_(tokens, non_blocking=True)
                     nh.copy_(n_tok, non_blocking=True)
-                    fin = torch.cuda.Event()
-                    fin.record(down_s)
-                tokens.record_stream(down_s)
-                n_tok.record_stream(down_s)
+                fin = torch.cuda.Event()
+                fin.record(down_s)
+            if to_host:
                 pending.append((th, nh, fin, sizes))
             else:
                 tokens.record_stream(caller)
                 n_tok.record_stream(caller)
-                pending.append((tokens, n_tok, done, sizes))
+                pending.append((tokens, n_tok, fin, sizes))
             step += 1
             if len(pending) > 1:
                 a, b, e, sz = pending.popleft()
