@@ -221,7 +221,7 @@ class Transformer(nn.Module):
     def greedy_decode_batches(self, batches, max_len: Optional[int] = None, stop_at_eos: bool = False,
                               gather=None, to_host: bool = True, coalesce: Optional[int] = None):
         """Pipelined greedy ASR over an iterable of batches ((B,1,F,T) fp32; HOST tensors, ideally pinned, or tensors
-        already on the device).  Four streams keep every engine busy: the upload of group i+1, the ENCODER of group i+1
+        already on the device; an item may also be a pair (batch, lengths) to mask the zero padding of each utterance).  Four streams keep every engine busy: the upload of group i+1, the ENCODER of group i+1
         (it runs on the SMs the decoder leaves idle: the cluster decoder occupies num_heads x ceil(B / group) SMs and
         is latency-bound, so the two overlap), the decoder of group i (high priority), and the download of group i-1's
         transcripts.  Yields (tokens (B,L+1) int32, n_tokens (B,) int32) per input batch, in order: CPU tensors
@@ -257,23 +257,30 @@ class Transformer(nn.Module):
             return staging[key]
 
         def groups():
-            """Consecutive batches of one shape / placement, up to `coalesce` per group."""
-            cur, limit = [], 1
-            for x in batches:
-                if cur and (x.shape != cur[0].shape or x.is_cuda != cur[0].is_cuda or len(cur) >= limit):
-                    yield cur
-                    cur = []
+            """Consecutive batches of one shape / placement / masking, up to `coalesce` per group.  An item is a
+            spectrogram batch or a pair (spectrogram batch, lengths): input frames per utterance, which switch on the
+            key-padding masks end to end like ``greedy_decode(lengths=...)``."""
+            cur, lens, limit = [], [], 1
+            for item in batches:
+                x, ln = item if isinstance(item, (tuple, list)) else (item, None)
+                if cur and (x.shape != cur[0].shape or x.is_cuda != cur[0].is_cuda or (ln is None) != (lens[0] is None)
+                            or len(cur) >= limit):
+                    yield cur, lens
+                    cur, lens = [], []
                 if not cur:
                     limit = coalesce if coalesce else max(1, min(4, 128 // max(1, x.shape[0])))
                 cur.append(x)
+                lens.append(ln)
             if cur:
-                yield cur
+                yield cur, lens
 
         def stage_in(group):
             """H2D (if needed) on the upload stream, then the front-end + encoder on the encoder stream."""
             if group is None:
                 return None
+            group, lens = group
             sizes = [int(x.shape[0]) for x in group]
+            lens_all = None if lens[0] is None else torch.cat([torch.as_tensor(l).reshape(-1) for l in lens])
             if not group[0].is_cuda:
                 with torch.cuda.stream(up_s):
                     x = torch.empty((sum(sizes),) + tuple(group[0].shape[1:]), dtype=torch.float32, device=dev)
@@ -292,13 +299,15 @@ class Transformer(nn.Module):
             with torch.cuda.stream(enc_s):
                 if x is None:
                     x = group[0] if len(group) == 1 else torch.cat(group, 0)
-                enc = eng.encode(x, ws_tag="pipe_enc")
+                enc_lens = None if lens_all is None else self.encoder_lengths(lens_all.to(device=dev, dtype=torch.int32))
+                enc = eng.encode(x, enc_lens, ws_tag="pipe_enc")
                 # cross-attention K/V + decoder state of this group: also under the previous group's decode loop.  Two
                 # decode workspaces alternate; a slot is reused only after the decode that last ran on it has finished.
                 slot = n_in[0] & 1
                 if ws_done[slot] is not None:
                     enc_s.wait_event(ws_done[slot])
-                ctx = eng.decode_greedy(enc, max_len, stop_at_eos, ws_tag="pipe_dec%d" % slot, phase="prepare")
+                ctx = eng.decode_greedy(enc, max_len, stop_at_eos, ws_tag="pipe_dec%d" % slot, phase="prepare",
+                                        enc_lens=enc_lens)
                 ctx["slot"] = slot
                 ctx["sizes"] = sizes
                 n_in[0] += 1

@@ -29,6 +29,16 @@ def balanced_assignment(lengths: Sequence[int], world: int) -> List[List[int]]:
     return [order[r::world] for r in range(world)]
 
 
+def bucket_by_length(lengths: Sequence[int], batch_size: int) -> List[List[int]]:
+    """Length-bucketed batching: utterance indices grouped into batches of ``batch_size``
+    neighbours in length (longest first), so that a batch is padded to its own longest utterance instead of the
+    longest of the corpus.  Every index appears exactly once; the last batch may be short."""
+    if batch_size <= 0:
+        raise ValueError("batch_size must be positive")
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    return [order[i:i + batch_size] for i in range(0, len(order), batch_size)]
+
+
 def gather_tokens(tokens: torch.Tensor, n_tokens: torch.Tensor, counts: Optional[Sequence[int]] = None,
                   group=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Final transcript gather: every rank contributes (b_r, L+1) int32 tokens and (b_r,) lengths and receives the

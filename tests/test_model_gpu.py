@@ -309,6 +309,24 @@ def test_coalesced_serving_C2_full_size():
     assert len({tuple(r) for r in outs[0][0].tolist()}) >= 0.9 * cfg.batch
 
 
+def test_pipelined_batches_with_lengths(t0):
+    """(batch, lengths) items switch the key-padding masks on inside the serving loop: same tokens as the per-batch call
+    with lengths, for coalesced groups as well, and different from the unmasked decode of the padded input."""
+    cfg, fx, m, spec = t0
+    lens = torch.tensor([cfg.frames, 131, 160])[:spec.shape[0]]
+    padded = spec.clone()
+    for b, n in enumerate(lens.tolist()):
+        padded[b, :, :, n:] = 0
+    items = [(padded.cpu().pin_memory(), lens), (padded.flip(0).cpu().pin_memory(), lens.flip(0)), (padded.cpu(), lens)]
+    outs = list(m.greedy_decode_batches(items))
+    assert len(outs) == 3
+    for (x, ln), (tok, n) in zip(items, outs):
+        t_ref, n_ref = m.greedy_decode(x.to(DEV), lengths=ln.to(DEV))
+        assert torch.equal(tok, t_ref.cpu()) and torch.equal(n, n_ref.cpu())
+    t_unmasked, _ = m.greedy_decode(padded)
+    assert not torch.equal(outs[0][0], t_unmasked.cpu())
+
+
 def test_key_padding_end_to_end_decode(t0):
     """Masks on, end to end: a zero-padded utterance decoded with its length gives the tokens of
     the unpadded utterance decoded alone (encoder self attention and decoder cross attention both ignore the padding)."""

@@ -1,5 +1,7 @@
 """World-size-2 gloo test of the multi-GPU host logic (sharding + final transcript gather) on CPU."""
 import os
+
+import pytest
 import socket
 
 import torch
@@ -57,3 +59,15 @@ def test_gather_tokens_world2_gloo():
     for p in procs:
         p.join(60)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_bucket_by_length():
+    from asr_transformer_b200.parallel import bucket_by_length
+    lens = [500, 1000, 400, 990, 410, 700, 1000]
+    b = bucket_by_length(lens, 3)
+    assert sorted(i for g in b for i in g) == list(range(len(lens)))
+    assert b == [[1, 6, 3], [5, 0, 4], [2]]
+    assert max(lens[i] for i in b[1]) - min(lens[i] for i in b[1]) < max(lens) - min(lens)
+    assert bucket_by_length([], 4) == []
+    with pytest.raises(ValueError):
+        bucket_by_length(lens, 0)
