@@ -207,6 +207,23 @@ class Transformer(nn.Module):
                                                                enc_lens=self.encoder_lengths(lengths))
         return (tokens, n_tok, step_logits) if return_logits else (tokens, n_tok)
 
+    def transcribe(self, audio_batches, spectrogram, detokenizer, frames: Optional[int] = None,
+                   max_len: Optional[int] = None):
+        """Raw audio to text through the whole pipeline (the callers on either side of the hot path, SURVEY.md 8f rows
+        2-3): every item of ``audio_batches`` is (B, N) fp32 audio (host or device); ``spectrogram`` a
+        ``frontend.Spectrogram`` (the reference's dataset.py:34-35 configuration), ``frames`` the frame count the
+        spectrograms are zero-padded / cut to (dataset.py:53-55; default: each batch's own length), ``detokenizer`` a
+        ``text.Detokenizer``.  Spectrograms are computed on the device and fed to ``greedy_decode_batches`` (decode
+        stops at EOS); yields one list of strings per batch."""
+        dev = next(self.parameters()).device
+
+        def specs():
+            for a in audio_batches:
+                yield spectrogram(a.to(dev, non_blocking=True), frames_out=frames)
+
+        for tokens, n_tok in self.greedy_decode_batches(specs(), max_len=max_len, stop_at_eos=True):
+            yield detokenizer.decode_batch(tokens, n_tok)
+
     def beam_search(self, spectrum, beam: int = 4, lengths: Optional[torch.Tensor] = None,
                     max_len: Optional[int] = None):
         """Beam search (the reference's README TODO; semantics in ``include/asr_b200.h: asr_decode_beam``):

@@ -78,3 +78,26 @@ def test_gpu_audio_to_tokens_no_host_round_trip():
     assert float(d.max()) < 6e-2 and float(d.mean()) < 6e-3
     tokens, _ = m.greedy_decode(spec)
     assert tokens.shape == (2, 9)
+
+
+@pytest.mark.gpu
+def test_gpu_transcribe_audio_to_text():
+    """Transformer.transcribe = Spectrogram -> serving loop (stop at EOS) -> Detokenizer, batch by batch."""
+    import dataclasses
+    import json
+    from asr_transformer_b200 import Detokenizer, Spectrogram
+    from tests.util import build_model
+    from oracle import speech_transformer as O
+    cfg = dataclasses.replace(O.CONFIGS["C0"], encoder_num_layers=1, decoder_num_layers=1, decoder_seq_len=12, batch=2)
+    m = build_model(cfg, "cuda")
+    fx = json.load(open(os.path.join(HERE, "golden", "text_detok.json"), encoding="utf-8"))
+    detok = Detokenizer(fx["vocab"], fx["special_ids"], fx["suffix"]) if "vocab" in fx else None
+    if detok is None:
+        pytest.skip("detokeniser fixture without an embedded vocabulary")
+    sp = Spectrogram()
+    audios = [S.synthetic_audio(2, 160000, seed=7), S.synthetic_audio(2, 160000, seed=8).cuda()]
+    texts = list(m.transcribe(audios, sp, detok))
+    assert len(texts) == 2 and all(len(t) == 2 and all(isinstance(x, str) for x in t) for t in texts)
+    for a, got in zip(audios, texts):
+        tok, n = m.greedy_decode(sp(a.cuda()), stop_at_eos=True)
+        assert got == detok.decode_batch(tok.cpu(), n.cpu())
