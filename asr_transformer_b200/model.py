@@ -273,6 +273,14 @@ class Transformer(nn.Module):
                 staging[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             return staging[key]
 
+        bufs = self.__dict__.setdefault("_pipe_bufs", {})
+
+        def stage_buf(kind, shape):
+            key = (str(dev),) + kind + tuple(shape)
+            if key not in bufs:
+                bufs[key] = torch.empty(shape, dtype=torch.float32, device=dev)
+            return bufs[key]
+
         def groups():
             """Consecutive batches of one shape / placement / masking, up to `coalesce` per group.  An item is a
             spectrogram batch or a pair (spectrogram batch, lengths): input frames per utterance, which switch on the
@@ -298,9 +306,17 @@ class Transformer(nn.Module):
             group, lens = group
             sizes = [int(x.shape[0]) for x in group]
             lens_all = None if lens[0] is None else torch.cat([torch.as_tensor(l).reshape(-1) for l in lens])
+            # Device staging (input batch of the group, encoder output) is persistent per pipeline slot: the caching
+            # allocator would otherwise have to serve ~70 MB per group across three streams, and a cudaMalloc in the
+            # middle of the loop serialises every stream.  Slot k & 1 is reused by group k + 2: its encoder pass
+            # (encoder stream) must have finished before the upload stream overwrites the input buffer.
+            slot = n_in[0] & 1
+            single = len(group) == 1 and group[0].is_cuda
+            x = group[0] if single else stage_buf(("x", slot), (sum(sizes),) + tuple(group[0].shape[1:]))
             if not group[0].is_cuda:
                 with torch.cuda.stream(up_s):
-                    x = torch.empty((sum(sizes),) + tuple(group[0].shape[1:]), dtype=torch.float32, device=dev)
+                    if x_free[slot] is not None:
+                        up_s.wait_event(x_free[slot])
                     o = 0
                     for xb in group:
                         x[o:o + xb.shape[0]].copy_(xb, non_blocking=True)
@@ -308,19 +324,23 @@ class Transformer(nn.Module):
                     ev = torch.cuda.Event()
                     ev.record(up_s)
                 enc_s.wait_event(ev)
-                x.record_stream(enc_s)
             else:
                 for xb in group:
                     xb.record_stream(enc_s)
-                x = None
             with torch.cuda.stream(enc_s):
-                if x is None:
-                    x = group[0] if len(group) == 1 else torch.cat(group, 0)
+                if group[0].is_cuda and not single:
+                    o = 0
+                    for xb in group:
+                        x[o:o + xb.shape[0]].copy_(xb, non_blocking=True)
+                        o += xb.shape[0]
                 enc_lens = None if lens_all is None else self.encoder_lengths(lens_all.to(device=dev, dtype=torch.int32))
-                enc = eng.encode(x, enc_lens, ws_tag="pipe_enc")
+                Tp = conv_len(conv_len(int(x.shape[-1])))
+                enc = eng.encode(x, enc_lens, out=stage_buf(("enc", slot), (sum(sizes), Tp, eng.cfg.embedding_dim)),
+                                 ws_tag="pipe_enc")
+                x_free[slot] = torch.cuda.Event()
+                x_free[slot].record(enc_s)
                 # cross-attention K/V + decoder state of this group: also under the previous group's decode loop.  Two
                 # decode workspaces alternate; a slot is reused only after the decode that last ran on it has finished.
-                slot = n_in[0] & 1
                 if ws_done[slot] is not None:
                     enc_s.wait_event(ws_done[slot])
                 ctx = eng.decode_greedy(enc, max_len, stop_at_eos, ws_tag="pipe_dec%d" % slot, phase="prepare",
@@ -341,6 +361,7 @@ class Transformer(nn.Module):
 
         n_in = [0]
         ws_done = [None, None]
+        x_free = [None, None]
         it = groups()
         nxt = stage_in(next(it, None))
         pending = deque()
