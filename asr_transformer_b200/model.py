@@ -238,8 +238,9 @@ class Transformer(nn.Module):
     def greedy_decode_batches(self, batches, max_len: Optional[int] = None, stop_at_eos: bool = False,
                               gather=None, to_host: bool = True, coalesce: Optional[int] = None):
         """Pipelined greedy ASR over an iterable of batches ((B,1,F,T) fp32; HOST tensors, ideally pinned, or tensors
-        already on the device; an item may also be a pair (batch, lengths) to mask the zero padding of each utterance).  Four streams keep every engine busy: the upload of group i+1, the ENCODER of group i+1
-        (it runs on the SMs the decoder leaves idle: the cluster decoder occupies num_heads x ceil(B / group) SMs and
+        already on the device; an item may also be a pair (batch, lengths) to mask the zero padding of each utterance).
+        Four streams keep every engine busy: the upload of group i+1, the ENCODER of group i+1 (it runs on the SMs the
+        decoder leaves idle: the cluster decoder occupies num_heads x ceil(B / group) SMs and
         is latency-bound, so the two overlap), the decoder of group i (high priority), and the download of group i-1's
         transcripts.  Yields (tokens (B,L+1) int32, n_tokens (B,) int32) per input batch, in order: CPU tensors
         (``to_host``) or device tensors.  ``gather`` (optional callable (tokens, n_tokens) -> (tokens, n_tokens)) runs
@@ -264,6 +265,8 @@ class Transformer(nn.Module):
         caller = torch.cuda.current_stream(dev)
         for st in (up_s, enc_s, dec_s):
             st.wait_stream(caller)                                 # inputs produced on the caller's stream
+        up_s.wait_stream(enc_s)      # the staging buffers and decode workspaces are persistent: a previous call that was
+        enc_s.wait_stream(dec_s)     # abandoned half way may still have work in flight on them
         staging = self.__dict__.setdefault("_pinned_staging", {})   # pinned D2H buffers live with the model:
         # cudaHostAlloc costs milliseconds, so they are allocated once per shape and reused by every call
 
