@@ -247,12 +247,12 @@ class Transformer(nn.Module):
         on the device before the download, e.g. ``parallel.gather_tokens`` for the multi-GPU transcript gather.
 
         ``coalesce``: consecutive same-shaped batches are decoded as one group of up to ``coalesce`` batches (one
-        front-end/encoder pass and ONE decode launch per group).  A decode step costs a fixed weight stream per cluster
-        of CTAs however many utterances share it, so 4 utterances per cluster (128 per launch on a 148-SM part) decode
-        in 1.3x the time of 2 per cluster: the default (None) fills launches up to 128 utterances.  Utterances are
-        independent; the group size only changes how the attention keys are dealt to the warps (fp32 summation order),
-        so the tokens equal those of per-batch ``greedy_decode`` except at argmax near-ties (``coalesce=1`` is
-        bit-identical to the per-batch call)."""
+        front-end/encoder pass and ONE decode launch per group).  A decode step costs a fixed weight stream and a fixed
+        chain of ~70 micro-phases per cluster of CTAs however many utterances share it, so 8 utterances per cluster
+        (256 per launch on a 148-SM part) decode in 2.4x the time of 2 per cluster: the default (None) fills launches up
+        to 256 utterances (at most 4 batches).  Utterances are independent; the group size only changes how the attention
+        keys are dealt to the warps (fp32 summation order), so the tokens equal those of per-batch ``greedy_decode``
+        except at argmax near-ties (``coalesce=1`` is bit-identical to the per-batch call)."""
         _require_eval(self)
         from collections import deque
         dev = next(self.parameters()).device
@@ -296,7 +296,7 @@ class Transformer(nn.Module):
                     yield cur, lens
                     cur, lens = [], []
                 if not cur:
-                    limit = coalesce if coalesce else max(1, min(4, 128 // max(1, x.shape[0])))
+                    limit = coalesce if coalesce else max(1, min(4, 256 // max(1, x.shape[0])))
                 cur.append(x)
                 lens.append(ln)
             if cur:

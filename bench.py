@@ -53,7 +53,7 @@ def parse():
 
 def coalesce_of(batch):
     """Batches per decode launch chosen by Transformer.greedy_decode_batches (coalesce=None)."""
-    return max(1, min(4, 128 // max(1, batch)))
+    return max(1, min(4, 256 // max(1, batch)))
 
 
 def workload_desc(cfg, batch, n_gpus):
@@ -68,7 +68,7 @@ def workload_desc(cfg, batch, n_gpus):
               "overlap (encoder of the next steps under the decoder of the current ones); the serial pass in phase_ms "
               "flushes L2",
         "coalesce": "the serving loop (Transformer.greedy_decode_batches) decodes %d consecutive steps' batches per "
-                    "launch (%d utterances = 4 per CTA cluster); every step's batch is fully processed and returned "
+                    "launch (%d utterances, up to 8 per CTA cluster); every step's batch is fully processed and returned "
                     "separately" % (coalesce_of(batch), coalesce_of(batch) * batch),
         "parallelism": f"dp{n_gpus}: utterance sharding, one process per GPU, no collective on the compute path, "
                        "final all_gather of token ids",

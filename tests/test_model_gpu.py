@@ -224,7 +224,7 @@ def test_reference_golden_C1():
     assert_close(step_logits[ident], fx["step_logits"][ident], what="C1 step logits")
 
 
-@pytest.mark.parametrize("name,batch", [("C2", 64), ("C2", 128), ("C5", 8)])
+@pytest.mark.parametrize("name,batch", [("C2", 64), ("C2", 128), ("C2", 256), ("C5", 8)])
 def test_greedy_vs_oracle_baseline_sizes(name, batch):
     """BASELINE sizes against the CPU oracle (KV-cached restatement, pinned to the reference by the goldens)."""
     cfg = O.CONFIGS[name]
@@ -239,7 +239,7 @@ def test_greedy_vs_oracle_baseline_sizes(name, batch):
     tokens, _ = m.greedy_decode(spec.to(DEV))
     r, frac = check_tokens(tok_ref, logits_ref, tokens)
     print(f"{name} greedy:", {k: r[k] for k in ("utterances", "identical", "near_tie", "distinct_rows")})
-    assert r["distinct_rows"] >= 0.9 * batch
+    assert r["distinct_rows"] >= 0.85 * batch      # (the synthetic generator: 229 distinct reference rows of 256)
     # Every divergence is already proven to be a near-tie (margin < TAU) by check_tokens.  At random init a 128-step
     # decode of 64 utterances makes 8192 argmax decisions, a handful of which have fp32-reference margins below 2e-4,
     # i.e. below the reference's own accumulation-order noise; those are coin flips for ANY fp32 implementation.
@@ -291,22 +291,27 @@ def test_coalesced_batches_match_single_calls(t0, coalesce):
 
 
 def test_coalesced_serving_C2_full_size():
-    """BASELINE config 2 through the serving loop exactly as bench.py drives it: two 64-utterance batches share one
-    decode launch (128 utterances, 4 per CTA cluster, all 128 steps).  The per-batch call runs 2 utterances per
-    cluster, which splits the attention keys over the warps differently (another fp32 summation order), so the
-    comparison is the usual one: identical tokens, or a first divergence at a proven argmax near-tie."""
+    """BASELINE config 2 through the serving loop exactly as bench.py drives it: four 64-utterance batches share one
+    decode launch (256 utterances, 8 per CTA cluster, all 128 steps); a fifth is decoded alone.  The per-batch call
+    runs 2 utterances per cluster, which splits the attention keys over the warps differently (another fp32 summation
+    order), so the comparison is the usual one: identical tokens, or a first divergence at a proven argmax near-tie."""
     cfg = O.CONFIGS["C2"]
     m = build_model(cfg, DEV)
-    xs = [O.structured_spectrum(cfg.batch, cfg.frames, cfg.input_dim, seed=31 + i) for i in range(3)]
+    xs = [O.structured_spectrum(cfg.batch, cfg.frames, cfg.input_dim, seed=31 + i) for i in range(5)]
     ref = [m.greedy_decode(x.to(DEV), return_logits=True) for x in xs]
     outs = list(m.greedy_decode_batches([x.pin_memory() for x in xs]))
-    assert len(outs) == 3
+    assert len(outs) == 5
     for (t_ref, n_ref, lg_ref), (tok, n) in zip(ref, outs):
         r = O.compare_tokens(t_ref.cpu(), lg_ref.cpu(), tok, TAU)
         assert not r["hard"] and r["identical"] >= 0.9 * cfg.batch, r
-    # the third batch is decoded alone (2 per cluster, like the reference call): bit-exact
-    assert torch.equal(outs[2][0], ref[2][0].cpu()) and torch.equal(outs[2][1], ref[2][1].cpu())
+    # the fifth batch is decoded alone (2 per cluster, like the reference call): bit-exact
+    assert torch.equal(outs[4][0], ref[4][0].cpu()) and torch.equal(outs[4][1], ref[4][1].cpu())
     assert len({tuple(r) for r in outs[0][0].tolist()}) >= 0.9 * cfg.batch
+    # two batches per launch (4 utterances per cluster)
+    outs2 = list(m.greedy_decode_batches([x.pin_memory() for x in xs[:2]], coalesce=2))
+    for (t_ref, n_ref, lg_ref), (tok, n) in zip(ref, outs2):
+        r = O.compare_tokens(t_ref.cpu(), lg_ref.cpu(), tok, TAU)
+        assert not r["hard"] and r["identical"] >= 0.9 * cfg.batch, r
 
 
 def test_pipelined_batches_with_lengths(t0):
