@@ -338,6 +338,14 @@ class Transformer(nn.Module):
                         o += xb.shape[0]
                 enc_lens = None if lens_all is None else self.encoder_lengths(lens_all.to(device=dev, dtype=torch.int32))
                 Tp = conv_len(conv_len(int(x.shape[-1])))
+                if n_in[0] == 0:
+                    # size the OTHER slot's buffers like this group's right away: the first group pays every
+                    # allocation of the loop, no cudaMalloc (a device-wide synchronisation) happens later
+                    L_ws = int(max_len or eng.cfg.decoder_seq_len)
+                    eng._ws(sum(sizes), 4 * Tp + 3, L_ws, "pipe_dec1")
+                    if not single:
+                        stage_buf(("x", 1), tuple(x.shape))
+                    stage_buf(("enc", 1), (sum(sizes), Tp, eng.cfg.embedding_dim))
                 enc = eng.encode(x, enc_lens, out=stage_buf(("enc", slot), (sum(sizes), Tp, eng.cfg.embedding_dim)),
                                  ws_tag="pipe_enc")
                 x_free[slot] = torch.cuda.Event()

@@ -304,7 +304,7 @@ def main():
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local_rank)
     sampler.start()
     time.sleep(0.5)
-    run_device(max(args.warmup, 6))          # (extra untimed steps: the loop's buffers and allocator pools settle)
+    run_device(max(args.warmup, 8))          # (two full groups untimed: the loop's buffers and allocator pools settle)
     barrier()
     sampler.clear()                         # keep only the samples taken during the timed region
     t_s, t_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
