@@ -16,6 +16,16 @@ namespace {
 
 inline int conv_len(int n) { return (n - 3) / 2 + 1; }
 
+// Activations that feed a Linear / conv2 as the tensor-core A operand travel as fp16 hi | lo pairs (x = hi + lo to
+// 2^-22) and are multiplied twice (a_split GEMMs): measured necessary for the 99 %-identical-tokens bar (a single fp16
+// rounding of every linear input flips ~0.3 % of the utterances).  ASR_B200_SPLIT=0 switches to
+// single fp16 operands (half the MMAs; for A/B measurements only).
+int g_split = [] {
+  const char* e = std::getenv("ASR_B200_SPLIT");
+  return (e && e[0] == '0') ? 0 : 1;
+}();
+inline int SP() { return g_split ? 2 : 1; }
+
 // Bump allocator over the caller's workspace (base == nullptr: size-only dry run).
 struct Bump {
   uint8_t* base;
@@ -31,49 +41,48 @@ struct Bump {
 };
 
 struct EncodeWs {
-  bf16 *y1, *z, *xn, *qkv, *att, *ff, *enc_bf16;
+  f16 *y1, *z, *xn, *qkv, *att, *ff, *enc_f16;
   float* h;
   void carve(Bump& b, const AsrConfig& c, int B, int T) {
     const int F1 = conv_len(c.input_dim), T1 = conv_len(T), F2 = conv_len(F1), T2 = conv_len(T1);
     const size_t M = size_t(B) * T2, D = c.embedding_dim;
-    y1 = b.take<bf16>(size_t(B) * T1 * F1 * 64);
-    z = b.take<bf16>(M * F2 * 64);
+    y1 = b.take<f16>(size_t(B) * T1 * F1 * 64 * 2);   // (hi | lo planes / halves: see g_split)
+    z = b.take<f16>(M * F2 * 64 * 2);
     h = b.take<float>(M * D);
-    xn = b.take<bf16>(M * D);
-    qkv = b.take<bf16>(M * 3 * D);
-    att = b.take<bf16>(M * D);
-    ff = b.take<bf16>(M * c.ff_dim);
-    enc_bf16 = b.take<bf16>(M * D);
+    xn = b.take<f16>(M * D * 2);
+    qkv = b.take<f16>(M * 3 * D);
+    att = b.take<f16>(M * D * 2);
+    ff = b.take<f16>(M * c.ff_dim * 2);
+    enc_f16 = b.take<f16>(M * D * 2);
   }
 };
 
 struct DecFwdWs {
-  bf16 *enc_bf16, *ckv, *xn, *qkv, *qc, *att, *ff;
+  f16 *enc_f16, *ckv, *xn, *qkv, *qc, *att, *ff;
   float* h;
   void carve(Bump& b, const AsrConfig& c, int B, int Tp, int L) {
     const size_t M = size_t(B) * Tp, R = size_t(B) * L, D = c.embedding_dim;
-    enc_bf16 = b.take<bf16>(M * D);
-    ckv = b.take<bf16>(size_t(c.decoder_num_layers) * M * 2 * D);
+    enc_f16 = b.take<f16>(M * D * 2);
+    ckv = b.take<f16>(size_t(c.decoder_num_layers) * M * 2 * D);
     h = b.take<float>(R * D);
-    xn = b.take<bf16>(R * D);
-    qkv = b.take<bf16>(R * 3 * D);
-    qc = b.take<bf16>(R * D);
-    att = b.take<bf16>(R * D);
-    ff = b.take<bf16>(R * c.ff_dim);
+    xn = b.take<f16>(R * D * 2);
+    qkv = b.take<f16>(R * 3 * D);
+    qc = b.take<f16>(R * D);
+    att = b.take<f16>(R * D * 2);
+    ff = b.take<f16>(R * c.ff_dim * 2);
   }
 };
 
 struct GreedyWs {
-  bf16 *enc_bf16, *ckv, *cache;
+  f16 *enc_f16, *ckv, *cache;
   float *h, *qkv, *att, *qc, *ff, *logits;
   int32_t *step, *finished;
-  unsigned* barrier;   // [2][PERSIST_MAX_TEAMS][32]: per-team barrier counters, finished-utterance counters
   void carve(Bump& b, const AsrConfig& c, int B, int Tp, int L) {
     const size_t M = size_t(B) * Tp, D = c.embedding_dim;
     const size_t vpad = (size_t(c.vocab_size) + 63) / 64 * 64;
-    enc_bf16 = b.take<bf16>(M * D);
-    ckv = b.take<bf16>(size_t(c.decoder_num_layers) * M * 2 * D);
-    cache = b.take<bf16>(size_t(c.decoder_num_layers) * B * ((L + 15) / 16 * 16) * 2 * D);   // rows padded to 16-key tiles
+    enc_f16 = b.take<f16>(M * D * 2);
+    ckv = b.take<f16>(size_t(c.decoder_num_layers) * M * 2 * D);
+    cache = b.take<f16>(size_t(c.decoder_num_layers) * B * ((L + 15) / 16 * 16) * 2 * D);   // rows padded to 16-key tiles
     h = b.take<float>(size_t(B) * D);
     qkv = b.take<float>(size_t(B) * 3 * D);
     att = b.take<float>(size_t(B) * D);
@@ -82,7 +91,6 @@ struct GreedyWs {
     logits = b.take<float>(size_t(B) * vpad);
     step = b.take<int32_t>(1);
     finished = b.take<int32_t>(B);
-    barrier = b.take<unsigned>(2 * PERSIST_MAX_TEAMS * 32);
   }
 };
 
@@ -223,7 +231,7 @@ beam_select_kernel(const float* __restrict__ logits, int ld, int V, int K, float
 // the second buffer set (grid: hypothesis row x layer); the new token lands at position t + 1; the device step counter
 // (cache append position / attention length of the next step) advances.
 __global__ void __launch_bounds__(256)
-beam_reorder_kernel(const bf16* __restrict__ cache_src, bf16* __restrict__ cache_dst, const int32_t* __restrict__ tok_src,
+beam_reorder_kernel(const f16* __restrict__ cache_src, f16* __restrict__ cache_dst, const int32_t* __restrict__ tok_src,
                     int32_t* __restrict__ tok_dst, const int32_t* __restrict__ parent, const int32_t* __restrict__ token,
                     int32_t* step, int R, int K, int L, int D2, int t) {
   const int r = blockIdx.x, l = blockIdx.y;
@@ -253,12 +261,12 @@ __global__ void beam_init_kernel(int32_t* tok, int ld_tok, float* score, int32_t
 
 struct BeamWs {
   GreedyWs g;
-  bf16* cache_alt;
+  f16* cache_alt;
   int32_t *tok_a, *tok_b, *parent, *token;
   float* score;
   void carve(Bump& b, const AsrConfig& c, int R, int Tp, int L) {
     g.carve(b, c, R, Tp, L);
-    cache_alt = b.take<bf16>(size_t(c.decoder_num_layers) * R * ((L + 15) / 16 * 16) * 2 * c.embedding_dim);
+    cache_alt = b.take<f16>(size_t(c.decoder_num_layers) * R * ((L + 15) / 16 * 16) * 2 * c.embedding_dim);
     tok_a = b.take<int32_t>(size_t(R) * (L + 1));
     tok_b = b.take<int32_t>(size_t(R) * (L + 1));
     parent = b.take<int32_t>(R);
@@ -298,51 +306,55 @@ int check_cfg(const AsrConfig& c) {
   return 0;
 }
 
-int gemm(const bf16* X, int ldx, const void* W, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s) {
-  return launch_gemm_tc(X, ldx, static_cast<const bf16*>(W), K, M, N, K, ep, s);
+// X: the activation operand, [M, K] or, with split, [M, 2K] = [hi | lo]
+int gemm(const f16* X, int ldx, const void* W, int M, int N, int K, const GemmEpilogue& ep, cudaStream_t s,
+         int split = 0) {
+  return launch_gemm_tc(X, ldx, static_cast<const f16*>(W), K, M, N, K, ep, s, split);
 }
 
-// x (bf16, normalised) -> self attention block output added to the fp32 residual stream h (in place)
-int self_attention_block(const AsrConfig& c, const AsrMhaWeights& w, const bf16* xn, bf16* qkv, bf16* att, float* h,
+// x (f16, normalised) -> self attention block output added to the fp32 residual stream h (in place)
+int self_attention_block(const AsrConfig& c, const AsrMhaWeights& w, const f16* xn, f16* qkv, f16* att, float* h,
                          int B, int S, int causal, const uint8_t* valid, const int32_t* k_lens, cudaStream_t s) {
-  const int D = c.embedding_dim, M = B * S;
+  const int D = c.embedding_dim, M = B * S, sp = SP();
   GemmEpilogue e1;
-  e1.bias = w.b_qkv; e1.out_bf16 = qkv; e1.ld_bf16 = 3 * D;
-  if (int rc = gemm(xn, D, w.w_qkv, M, 3 * D, D, e1, s)) return rc;
+  e1.bias = w.b_qkv; e1.out_f16 = qkv; e1.ld_f16 = 3 * D;
+  if (int rc = gemm(xn, sp * D, w.w_qkv, M, 3 * D, D, e1, s, g_split)) return rc;
   AttnParams a;
   a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D;
   a.ldq = a.ldk = a.ldv = 3 * D;
   a.q_batch_stride = a.k_batch_stride = a.v_batch_stride = (long long)S * 3 * D;
-  a.out = att; a.ldo = D; a.o_batch_stride = (long long)S * D;
+  a.out = att; a.ldo = sp * D; a.o_batch_stride = (long long)S * sp * D; a.out_lo_off = g_split ? D : 0;
   a.B = B; a.H = c.num_heads; a.Sq = S; a.Sk = S;
   a.scale = 1.0f / sqrtf((float)D);
   a.causal = causal; a.q_valid = valid; a.k_valid = valid; a.k_lens = k_lens;
   if (int rc = launch_attention_tc(a, s)) return rc;
   GemmEpilogue e2;
   e2.bias = w.b_out; e2.residual = h; e2.ld_res = D; e2.out_f32 = h; e2.ld_f32 = D;
-  return gemm(att, D, w.w_out, M, D, D, e2, s);
+  return gemm(att, sp * D, w.w_out, M, D, D, e2, s, g_split);
 }
 
-int ffn_block(const AsrConfig& c, const AsrFfnWeights& w, const bf16* xn, bf16* ff, float* h, int M, cudaStream_t s) {
-  const int D = c.embedding_dim, FF = c.ff_dim;
+int ffn_block(const AsrConfig& c, const AsrFfnWeights& w, const f16* xn, f16* ff, float* h, int M, cudaStream_t s) {
+  const int D = c.embedding_dim, FF = c.ff_dim, sp = SP();
   GemmEpilogue e1;
-  e1.bias = w.b1; e1.relu = 1; e1.out_bf16 = ff; e1.ld_bf16 = FF;
-  if (int rc = gemm(xn, D, w.w1, M, FF, D, e1, s)) return rc;
+  e1.bias = w.b1; e1.relu = 1; e1.out_f16 = ff; e1.ld_f16 = sp * FF; e1.f16_lo_off = g_split ? FF : 0;
+  if (int rc = gemm(xn, sp * D, w.w1, M, FF, D, e1, s, g_split)) return rc;
   GemmEpilogue e2;
   e2.bias = w.b2; e2.residual = h; e2.ld_res = D; e2.out_f32 = h; e2.ld_f32 = D;
-  return gemm(ff, FF, w.w2, M, D, FF, e2, s);
+  return gemm(ff, sp * FF, w.w2, M, D, FF, e2, s, g_split);
 }
 
-// cross-attention K/V of every decoder layer, once per utterance: ckv[l] = enc * [Wk; Wv]^T + b  (bf16 [M, 2D])
-int cross_kv(const AsrHandle* h, const bf16* enc_bf16, bf16* ckv, int M, cudaStream_t s) {
+// cross-attention K/V of every decoder layer, once per utterance: ckv[l] = enc * [Wk; Wv]^T + b  (f16 [M, 2D]).
+// enc_out fp32 -> enc_sp f16 [M, 2D] = [hi | lo] (always split: the encoder output enters the K/V projections exactly)
+int cross_kv(const AsrHandle* h, const float* enc_out, f16* enc_sp, f16* ckv, int M, cudaStream_t s) {
   const int D = h->cfg.embedding_dim;
+  if (int rc = launch_f32_to_f16_split(enc_out, enc_sp, size_t(M), D, s)) return rc;
   for (int l = 0; l < h->cfg.decoder_num_layers; ++l) {
     const AsrMhaWeights& w = h->dec[l].cross_attn;
     GemmEpilogue e;
     e.bias = w.b_qkv + D;
-    e.out_bf16 = ckv + size_t(l) * M * 2 * D;
-    e.ld_bf16 = 2 * D;
-    if (int rc = gemm(enc_bf16, D, static_cast<const bf16*>(w.w_qkv) + size_t(D) * D, M, 2 * D, D, e, s)) return rc;
+    e.out_f16 = ckv + size_t(l) * M * 2 * D;
+    e.ld_f16 = 2 * D;
+    if (int rc = gemm(enc_sp, 2 * D, static_cast<const f16*>(w.w_qkv) + size_t(D) * D, M, 2 * D, D, e, s, 1)) return rc;
   }
   return 0;
 }
@@ -355,12 +367,12 @@ int greedy_step(const AsrHandle* h, const GreedyWs& ws, int B, int Tp, int L, in
   const size_t M = size_t(B) * Tp;
   for (int l = 0; l < c.decoder_num_layers; ++l) {
     const AsrDecoderLayerWeights& w = h->dec[l];
-    bf16* cache = ws.cache + size_t(l) * B * L * 2 * D;
-    const bf16* ckv = ws.ckv + size_t(l) * M * 2 * D;
+    f16* cache = ws.cache + size_t(l) * B * L * 2 * D;
+    const f16* ckv = ws.ckv + size_t(l) * M * 2 * D;
     {  // LN1 -> packed QKV; K/V rows appended to the cache (model.py:67-68, layers.py:16-18)
       DecLinear p;
       p.x = ws.h; p.ldx = D; p.ln_gamma = w.norm1.gamma; p.ln_beta = w.norm1.beta;
-      p.w = static_cast<const bf16*>(w.self_attn.w_qkv); p.bias = w.self_attn.b_qkv;
+      p.w = static_cast<const f16*>(w.self_attn.w_qkv); p.bias = w.self_attn.b_qkv;
       p.B = B; p.N = 3 * D; p.K = D; p.out = ws.qkv; p.ldo = 3 * D;
       p.kv_cache = cache; p.kv_col0 = D; p.kv_rows = L; p.step = ws.step;
       PROF(prof, DC_QKV, launch_dec_linear(p, s));
@@ -374,14 +386,14 @@ int greedy_step(const AsrHandle* h, const GreedyWs& ws, int B, int Tp, int L, in
     }
     {  // out projection + residual
       DecLinear p;
-      p.x = ws.att; p.ldx = D; p.w = static_cast<const bf16*>(w.self_attn.w_out); p.bias = w.self_attn.b_out;
+      p.x = ws.att; p.ldx = D; p.w = static_cast<const f16*>(w.self_attn.w_out); p.bias = w.self_attn.b_out;
       p.B = B; p.N = D; p.K = D; p.out = ws.h; p.ldo = D; p.residual = ws.h; p.ld_res = D;
       PROF(prof, DC_OUT_PROJ, launch_dec_linear(p, s));
     }
     {  // LN2 -> cross-attention query (model.py:70-71)
       DecLinear p;
       p.x = ws.h; p.ldx = D; p.ln_gamma = w.norm2.gamma; p.ln_beta = w.norm2.beta;
-      p.w = static_cast<const bf16*>(w.cross_attn.w_qkv); p.bias = w.cross_attn.b_qkv;
+      p.w = static_cast<const f16*>(w.cross_attn.w_qkv); p.bias = w.cross_attn.b_qkv;
       p.B = B; p.N = D; p.K = D; p.out = ws.qc; p.ldo = D;
       PROF(prof, DC_CROSS_Q, launch_dec_linear(p, s));
     }
@@ -394,20 +406,20 @@ int greedy_step(const AsrHandle* h, const GreedyWs& ws, int B, int Tp, int L, in
     }
     {
       DecLinear p;
-      p.x = ws.att; p.ldx = D; p.w = static_cast<const bf16*>(w.cross_attn.w_out); p.bias = w.cross_attn.b_out;
+      p.x = ws.att; p.ldx = D; p.w = static_cast<const f16*>(w.cross_attn.w_out); p.bias = w.cross_attn.b_out;
       p.B = B; p.N = D; p.K = D; p.out = ws.h; p.ldo = D; p.residual = ws.h; p.ld_res = D;
       PROF(prof, DC_OUT_PROJ, launch_dec_linear(p, s));
     }
     {  // LN3 -> FFN (model.py:73-74)
       DecLinear p;
       p.x = ws.h; p.ldx = D; p.ln_gamma = w.norm3.gamma; p.ln_beta = w.norm3.beta;
-      p.w = static_cast<const bf16*>(w.ffn.w1); p.bias = w.ffn.b1; p.relu = 1;
+      p.w = static_cast<const f16*>(w.ffn.w1); p.bias = w.ffn.b1; p.relu = 1;
       p.B = B; p.N = FF; p.K = D; p.out = ws.ff; p.ldo = FF;
       PROF(prof, DC_FFN1, launch_dec_linear(p, s));
     }
     {
       DecLinear p;
-      p.x = ws.ff; p.ldx = FF; p.w = static_cast<const bf16*>(w.ffn.w2); p.bias = w.ffn.b2;
+      p.x = ws.ff; p.ldx = FF; p.w = static_cast<const f16*>(w.ffn.w2); p.bias = w.ffn.b2;
       p.B = B; p.N = D; p.K = FF; p.out = ws.h; p.ldo = D; p.residual = ws.h; p.ld_res = D;
       PROF(prof, DC_FFN2, launch_dec_linear(p, s));
     }
@@ -415,7 +427,7 @@ int greedy_step(const AsrHandle* h, const GreedyWs& ws, int B, int Tp, int L, in
   const int vpad = (c.vocab_size + 63) / 64 * 64;
   {  // classifier WITHOUT the final LayerNorm (model.py:142)
     DecLinear p;
-    p.x = ws.h; p.ldx = D; p.w = static_cast<const bf16*>(h->w.classifier_w);
+    p.x = ws.h; p.ldx = D; p.w = static_cast<const f16*>(h->w.classifier_w);
     p.B = B; p.N = c.vocab_size; p.K = D; p.out = ws.logits; p.ldo = vpad;
     PROF(prof, DC_CLASSIFIER, launch_dec_linear(p, s));
   }
@@ -426,45 +438,6 @@ int greedy_step(const AsrHandle* h, const GreedyWs& ws, int B, int Tp, int L, in
   sel.step_logits = step_logits; sel.L = L; sel.eos = c.eos_token_id; sel.pad = c.pad_token_id;
   sel.stop_at_eos = stop_at_eos;
   PROF(prof, DC_SELECT, launch_dec_select_embed(sel, h->w.embedding, h->w.dec_pe, D, ws.h, s));
-  return 0;
-}
-
-static int build_persistent(const AsrHandle* h, const GreedyWs& w, int B, int Tp, int L, int stop_at_eos,
-                            int32_t* tokens, int32_t* n_tokens, float* step_logits, PersistentParams& pp) {
-  const AsrConfig& c = h->cfg;
-  const int D = c.embedding_dim;
-    std::memset(&pp, 0, sizeof(pp));
-  pp.B = B; pp.D = D; pp.H = c.num_heads; pp.FF = c.ff_dim; pp.V = c.vocab_size; pp.L = L; pp.Tp = Tp;
-  pp.nd = c.decoder_num_layers;
-  if (pp.nd > PERSIST_MAX_LAYERS) return set_error(ASR_E_UNSUPPORTED, "more than %d decoder layers", PERSIST_MAX_LAYERS);
-  for (int l = 0; l < pp.nd; ++l) {
-    const AsrDecoderLayerWeights& lw = h->dec[l];
-    PersistentLayer& pl = pp.layer[l];
-    pl.ln1_g = lw.norm1.gamma; pl.ln1_b = lw.norm1.beta;
-    pl.w_qkv = static_cast<const bf16*>(lw.self_attn.w_qkv); pl.b_qkv = lw.self_attn.b_qkv;
-    pl.w_o = static_cast<const bf16*>(lw.self_attn.w_out); pl.b_o = lw.self_attn.b_out;
-    pl.ln2_g = lw.norm2.gamma; pl.ln2_b = lw.norm2.beta;
-    pl.w_qc = static_cast<const bf16*>(lw.cross_attn.w_qkv); pl.b_qc = lw.cross_attn.b_qkv;
-    pl.w_oc = static_cast<const bf16*>(lw.cross_attn.w_out); pl.b_oc = lw.cross_attn.b_out;
-    pl.ln3_g = lw.norm3.gamma; pl.ln3_b = lw.norm3.beta;
-    pl.w1 = static_cast<const bf16*>(lw.ffn.w1); pl.b1 = lw.ffn.b1;
-    pl.w2 = static_cast<const bf16*>(lw.ffn.w2); pl.b2 = lw.ffn.b2;
-  }
-  pp.classifier = static_cast<const bf16*>(h->w.classifier_w); pp.emb = h->w.embedding; pp.pe = h->w.dec_pe;
-  pp.dec_small = h->w.dec_small;
-  pp.cache = w.cache; pp.ckv = w.ckv; pp.h = w.h; pp.qkv = w.qkv; pp.ff = w.ff;
-  pp.tokens = tokens; pp.n_tokens = n_tokens; pp.finished = w.finished; pp.step_logits = step_logits;
-  pp.barrier = w.barrier; pp.done_count = w.barrier + PERSIST_MAX_TEAMS * 32;
-  {  // teams: one m16 row block (16 utterances) per team unless overridden (ASR_B200_TEAMS)
-    const char* te = std::getenv("ASR_B200_TEAMS");
-    int teams = te && te[0] ? std::atoi(te) : (B + 15) / 16;
-    if (teams < 1) teams = 1;
-    if (teams > PERSIST_MAX_TEAMS) teams = PERSIST_MAX_TEAMS;
-    if (teams > B) teams = B;
-    pp.teams = teams;
-  }
-  pp.eos = c.eos_token_id; pp.pad = c.pad_token_id; pp.stop_at_eos = stop_at_eos;
-  pp.scale = 1.0f / sqrtf((float)D);
   return 0;
 }
 
@@ -544,15 +517,15 @@ int asr_workspace_bytes(const AsrHandle* h, int B, int T, int L, size_t* bytes) 
 
 // Transformer.input_layer: the fused kernel when its tile fits shared memory (ASR_B200_CONV=split forces the two-kernel
 // path, kept as the fallback for very wide inputs and as the cross-check in the tests)
-static int conv_frontend(const float* spec, const float* w1, const float* b1, const bf16* w2frag, const float* b2, int B,
-                         int F, int T, bf16* y1, bf16* z, cudaStream_t s) {
+static int conv_frontend(const float* spec, const float* w1, const float* b1, const f16* w2frag, const float* b2, int B,
+                         int F, int T, f16* y1, f16* z, cudaStream_t s) {
   const char* e = std::getenv("ASR_B200_CONV");
   if (!(e && e[0] == 's')) {
-    const int rc = launch_conv_fused(spec, w1, b1, w2frag, b2, B, F, T, z, s);
+    const int rc = launch_conv_fused(spec, w1, b1, w2frag, b2, B, F, T, z, s, g_split);
     if (rc <= 0) return rc;
   }
-  if (int rc = launch_conv1(spec, w1, b1, B, F, T, y1, s)) return rc;
-  return launch_conv2(y1, w2frag, b2, B, conv_len(F), conv_len(T), z, s);
+  if (int rc = launch_conv1(spec, w1, b1, B, F, T, y1, s, g_split)) return rc;
+  return launch_conv2(y1, w2frag, b2, B, conv_len(F), conv_len(T), z, s, g_split);
 }
 
 static int encoder_core(AsrHandle* h, const EncodeWs& w, int B, int T2, const int32_t* enc_lens, float* enc_out,
@@ -564,13 +537,13 @@ static int encoder_core(AsrHandle* h, const EncodeWs& w, int B, int T2, const in
     GemmEpilogue e;
     e.bias = h->w.lin_in_b; e.rowvec = h->w.enc_pe; e.rowvec_period = T2; e.ld_rowvec = D;
     e.out_f32 = w.h; e.ld_f32 = D;
-    if (int rc = gemm(w.z, Kin, h->w.lin_in_w, M, D, Kin, e, s)) return rc;
+    if (int rc = gemm(w.z, SP() * Kin, h->w.lin_in_w, M, D, Kin, e, s, g_split)) return rc;
   }
   for (int l = 0; l < c.encoder_num_layers; ++l) {
     const AsrEncoderLayerWeights& lw = h->enc[l];
-    if (int rc = launch_layernorm(w.h, lw.norm1.gamma, lw.norm1.beta, M, D, 1e-5f, nullptr, w.xn, s)) return rc;
+    if (int rc = launch_layernorm(w.h, lw.norm1.gamma, lw.norm1.beta, M, D, 1e-5f, nullptr, w.xn, s, g_split)) return rc;
     if (int rc = self_attention_block(c, lw.attn, w.xn, w.qkv, w.att, w.h, B, T2, 0, nullptr, enc_lens, s)) return rc;
-    if (int rc = launch_layernorm(w.h, lw.norm2.gamma, lw.norm2.beta, M, D, 1e-5f, nullptr, w.xn, s)) return rc;
+    if (int rc = launch_layernorm(w.h, lw.norm2.gamma, lw.norm2.beta, M, D, 1e-5f, nullptr, w.xn, s, g_split)) return rc;
     if (int rc = ffn_block(c, lw.ffn, w.xn, w.ff, w.h, M, s)) return rc;
   }
   return launch_layernorm(w.h, h->w.enc_norm_out.gamma, h->w.enc_norm_out.beta, M, D, 1e-5f, enc_out, nullptr, s);
@@ -592,17 +565,17 @@ int asr_encode(AsrHandle* h, const float* spectrum, int B, int T, const int32_t*
   EncodeWs w;
   w.carve(bump, c, B, T);
   if (bump.off > ws_bytes) return set_error(ASR_E_WORKSPACE, "asr_encode: workspace %zu < %zu bytes", ws_bytes, bump.off);
-  if (int rc = conv_frontend(spectrum, h->w.conv1_w, h->w.conv1_b, static_cast<const bf16*>(h->w.conv2_wfrag),
+  if (int rc = conv_frontend(spectrum, h->w.conv1_w, h->w.conv1_b, static_cast<const f16*>(h->w.conv2_wfrag),
                              h->w.conv2_b, B, c.input_dim, T, w.y1, w.z, s))
     return rc;
   return encoder_core(h, w, B, T2, enc_lens, enc_out, s);
 }
 
-int asr_encoder_forward(AsrHandle* h, const void* z_bf16, int B, int Tp, const int32_t* enc_lens, void* ws,
+int asr_encoder_forward(AsrHandle* h, const void* z_f16, int B, int Tp, const int32_t* enc_lens, void* ws,
                         size_t ws_bytes, float* enc_out, asr_stream_t stream) {
   if (!h || !h->loaded) return set_error(ASR_E_INVALID, "asr_encoder_forward: weights not loaded");
   if (B == 0) return 0;
-  if (!z_bf16 || !enc_out || !ws || B < 0 || Tp <= 0) return set_error(ASR_E_INVALID, "asr_encoder_forward: bad argument");
+  if (!z_f16 || !enc_out || !ws || B < 0 || Tp <= 0) return set_error(ASR_E_INVALID, "asr_encoder_forward: bad argument");
   const AsrConfig& c = h->cfg;
   if (Tp > c.encoder_seq_len)
     return set_error(ASR_E_INVALID, "asr_encoder_forward: %d frames exceed encoder_seq_len %d", Tp, c.encoder_seq_len);
@@ -611,7 +584,7 @@ int asr_encoder_forward(AsrHandle* h, const void* z_bf16, int B, int Tp, const i
   w.carve(bump, c, B, 4 * Tp + 3);   // smallest T with subsampled length Tp; same layout as asr_encode
   if (bump.off > ws_bytes)
     return set_error(ASR_E_WORKSPACE, "asr_encoder_forward: workspace %zu < %zu bytes", ws_bytes, bump.off);
-  w.z = const_cast<bf16*>(static_cast<const bf16*>(z_bf16));
+  w.z = const_cast<f16*>(static_cast<const f16*>(z_f16));
   return encoder_core(h, w, B, Tp, enc_lens, enc_out, static_cast<cudaStream_t>(stream));
 }
 
@@ -631,37 +604,38 @@ int asr_decoder_forward(AsrHandle* h, const float* enc_out, int B, int Tp, const
   if (bump.off > ws_bytes)
     return set_error(ASR_E_WORKSPACE, "asr_decoder_forward: workspace %zu < %zu bytes", ws_bytes, bump.off);
   const int D = c.embedding_dim, M = B * Tp, R = B * L;
-  if (int rc = launch_f32_to_bf16(enc_out, w.enc_bf16, size_t(M) * D, s)) return rc;
-  if (int rc = cross_kv(h, w.enc_bf16, w.ckv, M, s)) return rc;
+  if (int rc = cross_kv(h, enc_out, w.enc_f16, w.ckv, M, s)) return rc;
   if (int rc = launch_embed_pe(text, L, h->w.embedding, h->w.dec_pe, B, L, D, c.vocab_size, w.h, s)) return rc;
   for (int l = 0; l < c.decoder_num_layers; ++l) {
     const AsrDecoderLayerWeights& lw = h->dec[l];
-    if (int rc = launch_layernorm(w.h, lw.norm1.gamma, lw.norm1.beta, R, D, 1e-5f, nullptr, w.xn, s)) return rc;
+    if (int rc = launch_layernorm(w.h, lw.norm1.gamma, lw.norm1.beta, R, D, 1e-5f, nullptr, w.xn, s, g_split)) return rc;
     if (int rc = self_attention_block(c, lw.self_attn, w.xn, w.qkv, w.att, w.h, B, L, 1, valid, nullptr, s)) return rc;
-    if (int rc = launch_layernorm(w.h, lw.norm2.gamma, lw.norm2.beta, R, D, 1e-5f, nullptr, w.xn, s)) return rc;
+    if (int rc = launch_layernorm(w.h, lw.norm2.gamma, lw.norm2.beta, R, D, 1e-5f, nullptr, w.xn, s, g_split)) return rc;
+    const int sp = SP();
     {  // cross attention: q from the decoder stream, K/V precomputed from the encoder output; never masked
       GemmEpilogue e1;
-      e1.bias = lw.cross_attn.b_qkv; e1.out_bf16 = w.qc; e1.ld_bf16 = D;
-      if (int rc = gemm(w.xn, D, lw.cross_attn.w_qkv, R, D, D, e1, s)) return rc;
-      const bf16* ckv = w.ckv + size_t(l) * M * 2 * D;
+      e1.bias = lw.cross_attn.b_qkv; e1.out_f16 = w.qc; e1.ld_f16 = D;
+      if (int rc = gemm(w.xn, sp * D, lw.cross_attn.w_qkv, R, D, D, e1, s, g_split)) return rc;
+      const f16* ckv = w.ckv + size_t(l) * M * 2 * D;
       AttnParams a;
       a.q = w.qc; a.ldq = D; a.q_batch_stride = (long long)L * D;
       a.k = ckv; a.v = ckv + D; a.ldk = a.ldv = 2 * D;
       a.k_batch_stride = a.v_batch_stride = (long long)Tp * 2 * D;
-      a.out = w.att; a.ldo = D; a.o_batch_stride = (long long)L * D;
+      a.out = w.att; a.ldo = sp * D; a.o_batch_stride = (long long)L * sp * D; a.out_lo_off = g_split ? D : 0;
       a.B = B; a.H = c.num_heads; a.Sq = L; a.Sk = Tp; a.scale = 1.0f / sqrtf((float)D);
       if (int rc = launch_attention_tc(a, s)) return rc;
       GemmEpilogue e2;
       e2.bias = lw.cross_attn.b_out; e2.residual = w.h; e2.ld_res = D; e2.out_f32 = w.h; e2.ld_f32 = D;
-      if (int rc = gemm(w.att, D, lw.cross_attn.w_out, R, D, D, e2, s)) return rc;
+      if (int rc = gemm(w.att, sp * D, lw.cross_attn.w_out, R, D, D, e2, s, g_split)) return rc;
     }
-    if (int rc = launch_layernorm(w.h, lw.norm3.gamma, lw.norm3.beta, R, D, 1e-5f, nullptr, w.xn, s)) return rc;
+    if (int rc = launch_layernorm(w.h, lw.norm3.gamma, lw.norm3.beta, R, D, 1e-5f, nullptr, w.xn, s, g_split)) return rc;
     if (int rc = ffn_block(c, lw.ffn, w.xn, w.ff, w.h, R, s)) return rc;
   }
-  if (int rc = launch_layernorm(w.h, h->w.dec_norm.gamma, h->w.dec_norm.beta, R, D, 1e-5f, nullptr, w.xn, s)) return rc;
+  if (int rc = launch_layernorm(w.h, h->w.dec_norm.gamma, h->w.dec_norm.beta, R, D, 1e-5f, nullptr, w.xn, s, g_split))
+    return rc;
   GemmEpilogue e;
   e.out_f32 = logits; e.ld_f32 = c.vocab_size; e.n_store = c.vocab_size;
-  return gemm(w.xn, D, h->w.classifier_w, R, c.vocab_size, D, e, s);
+  return gemm(w.xn, SP() * D, h->w.classifier_w, R, c.vocab_size, D, e, s, g_split);
 }
 
 // phases: 1 = prepare (cross-attention K/V of every layer, token / state initialisation), 2 = run (the decode loop on
@@ -685,8 +659,7 @@ static int decode_greedy_impl(int phases, AsrHandle* h, const float* enc_out, in
   const int D = c.embedding_dim, M = B * Tp;
 
   if (phases & 1) {
-    if (int rc = launch_f32_to_bf16(enc_out, w.enc_bf16, size_t(M) * D, s)) return rc;
-    if (int rc = cross_kv(h, w.enc_bf16, w.ckv, M, s)) return rc;
+    if (int rc = cross_kv(h, enc_out, w.enc_f16, w.ckv, M, s)) return rc;
     dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, n_tokens, w.finished, w.step, B, L, c.bos_token_id,
                                                  first_tokens);
     ASR_CUDA_OK(cudaGetLastError());
@@ -696,8 +669,9 @@ static int decode_greedy_impl(int phases, AsrHandle* h, const float* enc_out, in
   }
   if (!(phases & 2)) return 0;
 
-  // Launch mode: "persistent" (default: one cooperative kernel for all L steps), "graph" (one CUDA-graph replay of
-  // the 51-kernel step per token) or "eager" (same kernels, launched one by one; bring-up / profiling).
+  // Launch mode (ASR_B200_DECODE): "cluster" (default: one launch of dec_cluster_kernel for all L steps), "graph" (one
+  // CUDA-graph replay of the per-kernel step per token; the fallback for configurations the cluster kernel is not
+  // compiled for) or "eager" (same kernels, launched one by one; bring-up / profiling).
   const char* mode = std::getenv("ASR_B200_DECODE");
   if (mode && mode[0] == 'c' && !cluster_available(h))
     return set_error(ASR_E_UNSUPPORTED, "asr_decode_greedy: cluster decoder requested but unavailable (packed image "
@@ -711,19 +685,6 @@ static int decode_greedy_impl(int phases, AsrHandle* h, const float* enc_out, in
   if (enc_lens)
     return set_error(ASR_E_UNSUPPORTED, "asr_decode_greedy: encoder lengths (cross-attention key padding) need the "
                      "cluster decoder, which is unavailable for this configuration / ASR_B200_DECODE mode");
-  if (mode && mode[0] == 's' && h->w.dec_small &&
-      stream_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers)) {
-    PersistentParams pp;
-    if (int rc = build_persistent(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, pp)) return rc;
-    return launch_dec_stream(pp, s);
-  }
-  // configurations whose staging buffers do not fit the persistent kernel's shared memory use the graph path
-  const bool can_persist = persistent_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers);
-  if ((!mode || !mode[0] || mode[0] == 'p') && can_persist) {
-    PersistentParams pp;
-    if (int rc = build_persistent(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, pp)) return rc;
-    return launch_dec_persistent(pp, s);
-  }
   if (mode && mode[0] == 'e') {
     for (int t = 0; t < L; ++t)
       if (int rc = greedy_step(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, s)) return rc;
@@ -826,12 +787,11 @@ int asr_decode_beam(AsrHandle* h, const float* enc_rep, int B, int beam, int Tp,
     configured = smem;
   }
   const int M = R * Tp;
-  if (int rc = launch_f32_to_bf16(enc_rep, w.g.enc_bf16, size_t(M) * D, s)) return rc;
-  if (int rc = cross_kv(h, w.g.enc_bf16, w.g.ckv, M, s)) return rc;
+  if (int rc = cross_kv(h, enc_rep, w.g.enc_f16, w.g.ckv, M, s)) return rc;
   int32_t* tok_cur = w.tok_a;
   int32_t* tok_nxt = w.tok_b;
-  bf16* cache_cur = w.g.cache;
-  bf16* cache_nxt = w.cache_alt;
+  f16* cache_cur = w.g.cache;
+  f16* cache_nxt = w.cache_alt;
   beam_init_kernel<<<(R + 127) / 128, 128, 0, s>>>(tok_cur, L + 1, w.score, w.g.finished, w.g.step, R, beam,
                                                   c.bos_token_id);
   ASR_CUDA_OK(cudaGetLastError());
@@ -874,8 +834,7 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
   w.carve(bump, c, B, Tp, L);
   if (bump.off > ws_bytes) return set_error(ASR_E_WORKSPACE, "asr_decode_profile: workspace too small");
   const int D = c.embedding_dim, M = B * Tp;
-  if (int rc = launch_f32_to_bf16(enc_out, w.enc_bf16, size_t(M) * D, s)) return rc;
-  if (int rc = cross_kv(h, w.enc_bf16, w.ckv, M, s)) return rc;
+  if (int rc = cross_kv(h, enc_out, w.enc_f16, w.ckv, M, s)) return rc;
   dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, nullptr, w.finished, w.step, B, L, c.bos_token_id,
                                                nullptr);
   ASR_CUDA_OK(cudaGetLastError());
@@ -886,7 +845,7 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
   for (int t = 0; t < L; ++t)
     if (int rc = greedy_step(h, w, B, Tp, L, 0, tokens, nullptr, nullptr, s, &prof)) return rc;
   ASR_CUDA_OK(cudaStreamSynchronize(s));
-  for (int i = 0; i <= DC_COUNT + 2; ++i) {
+  for (int i = 0; i <= DC_COUNT; ++i) {
     ms_per_class[i] = 0.f;
     launches_per_class[i] = 0;
   }
@@ -896,57 +855,7 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
     ms_per_class[prof.cls[i]] += ms;
     launches_per_class[prof.cls[i]] += 1;
   }
-  // slot DC_COUNT: the persistent cooperative kernel (all L steps in one launch), timed on its own
-  if (persistent_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers)) {
-    dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, nullptr, w.finished, w.step, B, L, c.bos_token_id,
-                                                 nullptr);
-    ASR_CUDA_OK(cudaGetLastError());
-    if (int rc = launch_dec_embed(tokens, L + 1, w.step, h->w.embedding, h->w.dec_pe, B, D, c.vocab_size, w.h, s))
-      return rc;
-    PersistentParams pp;
-    if (int rc = build_persistent(h, w, B, Tp, L, 0, tokens, nullptr, nullptr, pp)) return rc;
-    pp.timing = phase_cycles;   // device buffer [#SMs][16], nullable
-    cudaEvent_t e0, e1;
-    ASR_CUDA_OK(cudaEventCreate(&e0));
-    ASR_CUDA_OK(cudaEventCreate(&e1));
-    ASR_CUDA_OK(cudaEventRecord(e0, s));
-    int rc = launch_dec_persistent(pp, s);
-    ASR_CUDA_OK(cudaEventRecord(e1, s));
-    ASR_CUDA_OK(cudaStreamSynchronize(s));
-    if (!rc) {
-      ASR_CUDA_OK(cudaEventElapsedTime(&ms_per_class[DC_COUNT], e0, e1));
-      launches_per_class[DC_COUNT] = 1;
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    if (rc) return rc;
-  }
-  // slot DC_COUNT + 1: the streaming kernel (one CTA per utterance, no barriers)
-  if (h->w.dec_small && stream_supported(D, c.ff_dim, c.vocab_size, c.num_heads, c.decoder_num_layers)) {
-    dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, nullptr, w.finished, w.step, B, L, c.bos_token_id,
-                                                 nullptr);
-    ASR_CUDA_OK(cudaGetLastError());
-    if (int rc = launch_dec_embed(tokens, L + 1, w.step, h->w.embedding, h->w.dec_pe, B, D, c.vocab_size, w.h, s))
-      return rc;
-    PersistentParams pp;
-    if (int rc = build_persistent(h, w, B, Tp, L, 0, tokens, nullptr, nullptr, pp)) return rc;
-    cudaEvent_t e0, e1;
-    ASR_CUDA_OK(cudaEventCreate(&e0));
-    ASR_CUDA_OK(cudaEventCreate(&e1));
-    pp.timing = phase_cycles ? phase_cycles + size_t(148) * 16 : nullptr;   // second half of the caller's buffer
-    ASR_CUDA_OK(cudaEventRecord(e0, s));
-    int rc = launch_dec_stream(pp, s);
-    ASR_CUDA_OK(cudaEventRecord(e1, s));
-    ASR_CUDA_OK(cudaStreamSynchronize(s));
-    if (!rc) {
-      ASR_CUDA_OK(cudaEventElapsedTime(&ms_per_class[DC_COUNT + 1], e0, e1));
-      launches_per_class[DC_COUNT + 1] = 1;
-    }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    if (rc) return rc;
-  }
-  // slot DC_COUNT + 2: the cluster kernel (one cluster of num_heads CTAs per utterance group, DSMEM all-reduces)
+  // slot DC_COUNT: the cluster kernel (one cluster of num_heads CTAs per utterance group, DSMEM all-reduces)
   if (cluster_available(h)) {
     dec_init_kernel<<<(B + 127) / 128, 128, 0, s>>>(tokens, L + 1, nullptr, w.finished, w.step, B, L, c.bos_token_id,
                                                  nullptr);
@@ -955,7 +864,7 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
       return rc;
     ClusterParams cp;
     build_cluster(h, w, B, Tp, L, 0, tokens, nullptr, nullptr, cp);
-    cp.timing = phase_cycles ? phase_cycles + size_t(2) * 148 * 16 : nullptr;   // third part of the caller's buffer
+    cp.timing = phase_cycles;
     cudaEvent_t e0, e1;
     ASR_CUDA_OK(cudaEventCreate(&e0));
     ASR_CUDA_OK(cudaEventCreate(&e1));
@@ -964,8 +873,8 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
     ASR_CUDA_OK(cudaEventRecord(e1, s));
     ASR_CUDA_OK(cudaStreamSynchronize(s));
     if (!rc) {
-      ASR_CUDA_OK(cudaEventElapsedTime(&ms_per_class[DC_COUNT + 2], e0, e1));
-      launches_per_class[DC_COUNT + 2] = 1;
+      ASR_CUDA_OK(cudaEventElapsedTime(&ms_per_class[DC_COUNT], e0, e1));
+      launches_per_class[DC_COUNT] = 1;
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
@@ -984,31 +893,50 @@ size_t asr_decoder_image_bytes(const AsrConfig* cfg) {
 
 unsigned long long asr_launch_count(void) { return g_kernel_launches; }
 
+int asr_split_operands(void) { return g_split; }
+
 // ------------------------------------------------------------------------------------------- operators
-int asr_layernorm(const float* x, const float* gamma, const float* beta, int rows, int D, float* y_f32, void* y_bf16,
+int asr_layernorm(const float* x, const float* gamma, const float* beta, int rows, int D, float* y_f32, void* y_f16,
                   asr_stream_t stream) {
   if (rows == 0) return 0;
-  if (!x || !gamma || !beta || (!y_f32 && !y_bf16) || rows < 0) return set_error(ASR_E_INVALID, "asr_layernorm: bad argument");
-  return launch_layernorm(x, gamma, beta, rows, D, 1e-5f, y_f32, static_cast<bf16*>(y_bf16), static_cast<cudaStream_t>(stream));
+  if (!x || !gamma || !beta || (!y_f32 && !y_f16) || rows < 0) return set_error(ASR_E_INVALID, "asr_layernorm: bad argument");
+  return launch_layernorm(x, gamma, beta, rows, D, 1e-5f, y_f32, static_cast<f16*>(y_f16), static_cast<cudaStream_t>(stream));
 }
 
-int asr_f32_to_bf16(const float* x, void* y, size_t n, asr_stream_t stream) {
-  if (n && (!x || !y)) return set_error(ASR_E_INVALID, "asr_f32_to_bf16: null argument");
-  return launch_f32_to_bf16(x, static_cast<bf16*>(y), n, static_cast<cudaStream_t>(stream));
+int asr_f32_to_f16(const float* x, void* y, size_t n, asr_stream_t stream) {
+  if (n && (!x || !y)) return set_error(ASR_E_INVALID, "asr_f32_to_f16: null argument");
+  return launch_f32_to_f16(x, static_cast<f16*>(y), n, static_cast<cudaStream_t>(stream));
 }
 
-int asr_gemm_bf16(const void* x, const void* w, const float* bias, const float* residual, const float* pe,
-                  int pe_period, int M, int N, int K, int relu, float* y_f32, void* y_bf16, int impl,
+int asr_gemm_f16(const void* x, const void* w, const float* bias, const float* residual, const float* pe,
+                  int pe_period, int M, int N, int K, int relu, float* y_f32, void* y_f16, int impl,
                   asr_stream_t stream) {
   if (M == 0) return 0;
-  if (!x || !w || (!y_f32 && !y_bf16) || M < 0 || N <= 0 || K <= 0) return set_error(ASR_E_INVALID, "asr_gemm_bf16: bad argument");
+  if (!x || !w || (!y_f32 && !y_f16) || M < 0 || N <= 0 || K <= 0) return set_error(ASR_E_INVALID, "asr_gemm_f16: bad argument");
   GemmEpilogue e;
   e.bias = bias; e.residual = residual; e.ld_res = N; e.rowvec = pe; e.rowvec_period = pe_period > 0 ? pe_period : 1;
-  e.ld_rowvec = N; e.out_f32 = y_f32; e.ld_f32 = N; e.out_bf16 = static_cast<bf16*>(y_bf16); e.ld_bf16 = N;
+  e.ld_rowvec = N; e.out_f32 = y_f32; e.ld_f32 = N; e.out_f16 = static_cast<f16*>(y_f16); e.ld_f16 = N;
   e.relu = relu; e.n_store = N;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (impl == 1) return launch_gemm_naive(static_cast<const bf16*>(x), K, static_cast<const bf16*>(w), K, M, N, K, e, s);
-  return launch_gemm_tc(static_cast<const bf16*>(x), K, static_cast<const bf16*>(w), K, M, N, K, e, s);
+  if (impl == 1) return launch_gemm_naive(static_cast<const f16*>(x), K, static_cast<const f16*>(w), K, M, N, K, e, s);
+  return launch_gemm_tc(static_cast<const f16*>(x), K, static_cast<const f16*>(w), K, M, N, K, e, s);
+}
+
+int asr_gemm_split(const float* x, const void* w, const float* bias, int M, int N, int K, int relu, float* y_f32,
+                   void* y_f16_hilo, void* ws, size_t ws_bytes, asr_stream_t stream) {
+  if (M == 0) return 0;
+  if (!x || !w || (!y_f32 && !y_f16_hilo) || !ws || M < 0 || N <= 0 || K <= 0 || K % 8 != 0)
+    return set_error(ASR_E_INVALID, "asr_gemm_split: bad argument");
+  if (ws_bytes < size_t(M) * K * 4) return set_error(ASR_E_WORKSPACE, "asr_gemm_split: workspace < M * K * 4 bytes");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  f16* xs = static_cast<f16*>(ws);
+  if (int rc = launch_f32_to_f16_split(x, xs, size_t(M), K, s)) return rc;
+  GemmEpilogue e;
+  e.bias = bias; e.relu = relu; e.out_f32 = y_f32; e.ld_f32 = N; e.n_store = N;
+  if (y_f16_hilo) {
+    e.out_f16 = static_cast<f16*>(y_f16_hilo); e.ld_f16 = 2 * N; e.f16_lo_off = N;
+  }
+  return launch_gemm_tc(xs, 2 * K, static_cast<const f16*>(w), K, M, N, K, e, s, 1);
 }
 
 int asr_attention(const void* q, int ldq, long long q_bs, const void* k, int ldk, long long k_bs, const void* v,
@@ -1017,10 +945,10 @@ int asr_attention(const void* q, int ldq, long long q_bs, const void* k, int ldk
                   const uint8_t* dense_mask, int mask_B, int impl, asr_stream_t stream) {
   if (B == 0 || Sq == 0) return 0;
   AttnParams a;
-  a.q = static_cast<const bf16*>(q); a.ldq = ldq; a.q_batch_stride = q_bs;
-  a.k = static_cast<const bf16*>(k); a.ldk = ldk; a.k_batch_stride = k_bs;
-  a.v = static_cast<const bf16*>(v); a.ldv = ldv; a.v_batch_stride = v_bs;
-  a.out = static_cast<bf16*>(out); a.ldo = ldo; a.o_batch_stride = o_bs;
+  a.q = static_cast<const f16*>(q); a.ldq = ldq; a.q_batch_stride = q_bs;
+  a.k = static_cast<const f16*>(k); a.ldk = ldk; a.k_batch_stride = k_bs;
+  a.v = static_cast<const f16*>(v); a.ldv = ldv; a.v_batch_stride = v_bs;
+  a.out = static_cast<f16*>(out); a.ldo = ldo; a.o_batch_stride = o_bs;
   a.B = B; a.H = H; a.Sq = Sq; a.Sk = Sk; a.scale = scale; a.causal = causal;
   a.k_lens = k_lens; a.q_valid = q_valid; a.k_valid = k_valid; a.dense_mask = dense_mask; a.mask_B = mask_B;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1029,7 +957,7 @@ int asr_attention(const void* q, int ldq, long long q_bs, const void* k, int ldk
 
 size_t asr_mha_workspace_bytes(int B, int Sq, int Sk, int D) {
   const size_t rq = size_t(B) * Sq, rk = size_t(B) * Sk;
-  return (rq * D + rk * D + rq * 3 * D + rk * 2 * D + rq * D) * 2 + 8 * 256;
+  return (2 * rq * D + 2 * rk * D + rq * 3 * D + rk * 2 * D + 2 * rq * D) * 2 + 8 * 256;
 }
 
 int asr_mha(const float* x, const float* src, const AsrMhaWeights* w, int B, int Sq, int Sk, int D, int H, int causal,
@@ -1042,44 +970,51 @@ int asr_mha(const float* x, const float* src, const AsrMhaWeights* w, int B, int
   if (Sk <= 0) return set_error(ASR_E_INVALID, "asr_mha: empty key sequence");
   if (ws_bytes < asr_mha_workspace_bytes(B, Sq, Sk, D)) return set_error(ASR_E_WORKSPACE, "asr_mha: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int Rq = B * Sq, Rk = B * Sk;
+  const int Rq = B * Sq, Rk = B * Sk, sp = SP();
   Bump b(ws);
-  bf16* xb = b.take<bf16>(size_t(Rq) * D);
-  bf16* sb = b.take<bf16>(size_t(Rk) * D);
-  bf16* qkv = b.take<bf16>(size_t(Rq) * 3 * D);
-  bf16* kv = b.take<bf16>(size_t(Rk) * 2 * D);
-  bf16* att = b.take<bf16>(size_t(Rq) * D);
-  if (int rc = launch_f32_to_bf16(x, xb, size_t(Rq) * D, s)) return rc;
+  f16* xb = b.take<f16>(size_t(Rq) * D * 2);
+  f16* sb = b.take<f16>(size_t(Rk) * D * 2);
+  f16* qkv = b.take<f16>(size_t(Rq) * 3 * D);
+  f16* kv = b.take<f16>(size_t(Rk) * 2 * D);
+  f16* att = b.take<f16>(size_t(Rq) * D * 2);
+  // the inputs enter the projections as fp16 hi | lo pairs (or single fp16 with ASR_B200_SPLIT=0), like in the model path
+  auto to_operand = [&](const float* src_f32, f16* dst, int rows) {
+    return g_split ? launch_f32_to_f16_split(src_f32, dst, size_t(rows), D, s)
+                   : launch_f32_to_f16(src_f32, dst, size_t(rows) * D, s);
+  };
+  if (int rc = to_operand(x, xb, Rq)) return rc;
   AttnParams a;
   if (!src) {
     GemmEpilogue e;
-    e.bias = w->b_qkv; e.out_bf16 = qkv; e.ld_bf16 = 3 * D;
-    if (int rc = launch_gemm_tc(xb, D, static_cast<const bf16*>(w->w_qkv), D, Rq, 3 * D, D, e, s)) return rc;
+    e.bias = w->b_qkv; e.out_f16 = qkv; e.ld_f16 = 3 * D;
+    if (int rc = launch_gemm_tc(xb, sp * D, static_cast<const f16*>(w->w_qkv), D, Rq, 3 * D, D, e, s, g_split)) return rc;
     a.q = qkv; a.k = qkv + D; a.v = qkv + 2 * D;
     a.ldq = a.ldk = a.ldv = 3 * D;
     a.q_batch_stride = a.k_batch_stride = a.v_batch_stride = (long long)Sq * 3 * D;
   } else {
-    if (int rc = launch_f32_to_bf16(src, sb, size_t(Rk) * D, s)) return rc;
+    if (int rc = to_operand(src, sb, Rk)) return rc;
     GemmEpilogue e;
-    e.bias = w->b_qkv; e.out_bf16 = qkv; e.ld_bf16 = D;
-    if (int rc = launch_gemm_tc(xb, D, static_cast<const bf16*>(w->w_qkv), D, Rq, D, D, e, s)) return rc;
+    e.bias = w->b_qkv; e.out_f16 = qkv; e.ld_f16 = D;
+    if (int rc = launch_gemm_tc(xb, sp * D, static_cast<const f16*>(w->w_qkv), D, Rq, D, D, e, s, g_split)) return rc;
     GemmEpilogue e2;
-    e2.bias = w->b_qkv + D; e2.out_bf16 = kv; e2.ld_bf16 = 2 * D;
-    if (int rc = launch_gemm_tc(sb, D, static_cast<const bf16*>(w->w_qkv) + size_t(D) * D, D, Rk, 2 * D, D, e2, s)) return rc;
+    e2.bias = w->b_qkv + D; e2.out_f16 = kv; e2.ld_f16 = 2 * D;
+    if (int rc = launch_gemm_tc(sb, sp * D, static_cast<const f16*>(w->w_qkv) + size_t(D) * D, D, Rk, 2 * D, D, e2, s,
+                                g_split))
+      return rc;
     a.q = qkv; a.ldq = D; a.q_batch_stride = (long long)Sq * D;
     a.k = kv; a.v = kv + D; a.ldk = a.ldv = 2 * D;
     a.k_batch_stride = a.v_batch_stride = (long long)Sk * 2 * D;
   }
-  a.out = att; a.ldo = D; a.o_batch_stride = (long long)Sq * D;
+  a.out = att; a.ldo = sp * D; a.o_batch_stride = (long long)Sq * sp * D; a.out_lo_off = g_split ? D : 0;
   a.B = B; a.H = H; a.Sq = Sq; a.Sk = Sk; a.scale = 1.0f / sqrtf((float)D); a.causal = causal;
   a.q_valid = q_valid; a.k_valid = k_valid; a.dense_mask = dense_mask; a.mask_B = mask_B;
   if (int rc = launch_attention_tc(a, s)) return rc;
   GemmEpilogue e3;
   e3.bias = w->b_out; e3.out_f32 = out; e3.ld_f32 = D;
-  return launch_gemm_tc(att, D, static_cast<const bf16*>(w->w_out), D, Rq, D, D, e3, s);
+  return launch_gemm_tc(att, sp * D, static_cast<const f16*>(w->w_out), D, Rq, D, D, e3, s, g_split);
 }
 
-size_t asr_ffn_workspace_bytes(int rows, int D, int FF) { return (size_t(rows) * D + size_t(rows) * FF) * 2 + 4 * 256; }
+size_t asr_ffn_workspace_bytes(int rows, int D, int FF) { return (size_t(rows) * D + size_t(rows) * FF) * 4 + 4 * 256; }
 
 int asr_ffn(const float* x, const AsrFfnWeights* w, int rows, int D, int FF, void* ws, size_t ws_bytes, float* out,
             asr_stream_t stream) {
@@ -1088,35 +1023,37 @@ int asr_ffn(const float* x, const AsrFfnWeights* w, int rows, int D, int FF, voi
   if (D % 64 != 0 || FF % 64 != 0) return set_error(ASR_E_UNSUPPORTED, "asr_ffn: D and FF must be multiples of 64");
   if (ws_bytes < asr_ffn_workspace_bytes(rows, D, FF)) return set_error(ASR_E_WORKSPACE, "asr_ffn: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int sp = SP();
   Bump b(ws);
-  bf16* xb = b.take<bf16>(size_t(rows) * D);
-  bf16* ff = b.take<bf16>(size_t(rows) * FF);
-  if (int rc = launch_f32_to_bf16(x, xb, size_t(rows) * D, s)) return rc;
+  f16* xb = b.take<f16>(size_t(rows) * D * 2);
+  f16* ff = b.take<f16>(size_t(rows) * FF * 2);
+  if (int rc = g_split ? launch_f32_to_f16_split(x, xb, size_t(rows), D, s) : launch_f32_to_f16(x, xb, size_t(rows) * D, s))
+    return rc;
   GemmEpilogue e1;
-  e1.bias = w->b1; e1.relu = 1; e1.out_bf16 = ff; e1.ld_bf16 = FF;
-  if (int rc = launch_gemm_tc(xb, D, static_cast<const bf16*>(w->w1), D, rows, FF, D, e1, s)) return rc;
+  e1.bias = w->b1; e1.relu = 1; e1.out_f16 = ff; e1.ld_f16 = sp * FF; e1.f16_lo_off = g_split ? FF : 0;
+  if (int rc = launch_gemm_tc(xb, sp * D, static_cast<const f16*>(w->w1), D, rows, FF, D, e1, s, g_split)) return rc;
   GemmEpilogue e2;
   e2.bias = w->b2; e2.out_f32 = out; e2.ld_f32 = D;
-  return launch_gemm_tc(ff, FF, static_cast<const bf16*>(w->w2), FF, rows, D, FF, e2, s);
+  return launch_gemm_tc(ff, sp * FF, static_cast<const f16*>(w->w2), FF, rows, D, FF, e2, s, g_split);
 }
 
 size_t asr_conv_workspace_bytes(int B, int F, int T) {
-  return size_t(B) * conv_len(T) * conv_len(F) * 64 * 2 + 512;
+  return size_t(B) * conv_len(T) * conv_len(F) * 64 * 2 * 2 + 512;
 }
 
 int asr_conv_frontend(const float* spectrum, const float* conv1_w, const float* conv1_b, const void* conv2_wfrag,
-                      const float* conv2_b, int B, int F, int T, void* ws, size_t ws_bytes, void* z_bf16,
+                      const float* conv2_b, int B, int F, int T, void* ws, size_t ws_bytes, void* z_f16,
                       asr_stream_t stream) {
   if (B == 0) return 0;
-  if (!spectrum || !conv1_w || !conv1_b || !conv2_wfrag || !conv2_b || !ws || !z_bf16 || B < 0)
+  if (!spectrum || !conv1_w || !conv1_b || !conv2_wfrag || !conv2_b || !ws || !z_f16 || B < 0)
     return set_error(ASR_E_INVALID, "asr_conv_frontend: bad argument");
   if (conv_len(conv_len(F)) < 1 || conv_len(conv_len(T)) < 1) return set_error(ASR_E_INVALID, "asr_conv_frontend: input too small");
   if (ws_bytes < asr_conv_workspace_bytes(B, F, T)) return set_error(ASR_E_WORKSPACE, "asr_conv_frontend: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   Bump b(ws);
-  bf16* y1 = b.take<bf16>(size_t(B) * conv_len(T) * conv_len(F) * 64);
-  return conv_frontend(spectrum, conv1_w, conv1_b, static_cast<const bf16*>(conv2_wfrag), conv2_b, B, F, T, y1,
-                       static_cast<bf16*>(z_bf16), s);
+  f16* y1 = b.take<f16>(size_t(B) * conv_len(T) * conv_len(F) * 64 * 2);
+  return conv_frontend(spectrum, conv1_w, conv1_b, static_cast<const f16*>(conv2_wfrag), conv2_b, B, F, T, y1,
+                       static_cast<f16*>(z_f16), s);
 }
 
 int asr_spectrogram(const float* audio, int B, int n_samples, int n_fft, int hop, int T, float* spec,
@@ -1138,7 +1075,7 @@ int asr_dec_linear(const float* x, const float* ln_gamma, const float* ln_beta, 
   if (B == 0) return 0;
   if (!x || !w || !out) return set_error(ASR_E_INVALID, "asr_dec_linear: null argument");
   DecLinear p;
-  p.x = x; p.ldx = K; p.ln_gamma = ln_gamma; p.ln_beta = ln_beta; p.w = static_cast<const bf16*>(w); p.bias = bias;
+  p.x = x; p.ldx = K; p.ln_gamma = ln_gamma; p.ln_beta = ln_beta; p.w = static_cast<const f16*>(w); p.bias = bias;
   p.B = B; p.N = N; p.K = K; p.relu = relu; p.out = out; p.ldo = N; p.residual = residual; p.ld_res = N;
   return launch_dec_linear(p, static_cast<cudaStream_t>(stream));
 }
@@ -1148,14 +1085,14 @@ int asr_dec_attention(const float* q, const void* k, const void* v, int ldkv, lo
   if (B == 0) return 0;
   if (!q || !k || !v || !out || n_keys <= 0) return set_error(ASR_E_INVALID, "asr_dec_attention: bad argument");
   DecAttn a;
-  a.q = q; a.ldq = H * 64; a.k = static_cast<const bf16*>(k); a.v = static_cast<const bf16*>(v); a.ldkv = ldkv;
+  a.q = q; a.ldq = H * 64; a.k = static_cast<const f16*>(k); a.v = static_cast<const f16*>(v); a.ldkv = ldkv;
   a.kv_batch_stride = kv_bs; a.n_keys = n_keys; a.out = out; a.ldo = H * 64; a.B = B; a.H = H; a.scale = scale;
   return launch_dec_attention(a, static_cast<cudaStream_t>(stream));
 }
 
 int asr_umma_probe(const void* a, const void* b, float* d, int N, int b_mn_major, asr_stream_t stream) {
   if (!a || !b || !d) return set_error(ASR_E_INVALID, "asr_umma_probe: null argument");
-  return launch_umma_probe(static_cast<const bf16*>(a), static_cast<const bf16*>(b), d, N, b_mn_major,
+  return launch_umma_probe(static_cast<const f16*>(a), static_cast<const f16*>(b), d, N, b_mn_major,
                            static_cast<cudaStream_t>(stream));
 }
 

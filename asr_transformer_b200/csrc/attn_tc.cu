@@ -9,7 +9,7 @@
 //                                tcgen05.mma issue: S = Q K^T (M128 N128 K64) and O_j = P V (M128 N64 K128,
 //                                V consumed in place as an MN-major B operand, P from shared memory).
 //   warps 0-3 (one query row per thread): tcgen05.ld S from TMEM, scale + mask + online softmax in fp32,
-//                                P -> bf16 into the swizzled smem A-operand tile, per-tile partial O_j read back
+//                                P -> f16 into the swizzled smem A-operand tile, per-tile partial O_j read back
 //                                from TMEM and folded into fp32 register accumulators (no TMEM rescale needed).
 #include "kernels.h"
 #include "ptx.cuh"
@@ -32,7 +32,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 struct AttnDev {
-  bf16* out; int ldo; long long o_batch_stride;
+  f16* out; int ldo; long long o_batch_stride; int out_lo_off;
   int H, Sq, Sk;
   float scale_log2;
   int causal;
@@ -106,8 +106,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tma_load_3d(sK + j * TILE_BYTES, &tmK, &kv_full[j], h * DH, j * BKV, b);
         tma_load_3d(sV + j * TILE_BYTES, &tmV, &kv_full[j], h * DH, j * BKV, b);
       }
-      constexpr uint32_t idesc_S = umma_idesc_bf16(BQ, BKV, 0, 0);
-      constexpr uint32_t idesc_O = umma_idesc_bf16(BQ, DH, 0, 1);   // B = V tile, MN-major
+      constexpr uint32_t idesc_S = umma_idesc_f16(BQ, BKV, 0, 0);
+      constexpr uint32_t idesc_O = umma_idesc_f16(BQ, DH, 0, 1);   // B = V tile, MN-major
       const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
       mbar_wait(q_full, 0);
       for (int j = 0; j < nkv; ++j) {
@@ -117,7 +117,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(sK + s * TILE_BYTES), 16, 1024);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k)
-          umma_bf16_ss(tmem_S, q_desc + uint64_t(k * 2), k_desc + uint64_t(k * 2), idesc_S, k != 0);
+          umma_f16_ss(tmem_S, q_desc + uint64_t(k * 2), k_desc + uint64_t(k * 2), idesc_S, k != 0);
         umma_commit(s_full);
         if (j >= 1 && j + 1 < nkv) {   // refill the stage tile j-1 used, once P V_{j-1} has drained it
           const int sp = (j - 1) & 1;
@@ -132,7 +132,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           const uint64_t p_desc = umma_smem_desc_sw128(smem_u32(sP + (k >> 2) * (BQ * 128)), 16, 1024) + uint64_t((k & 3) * 2);
-          umma_bf16_ss(tmem_O, p_desc, v_desc + uint64_t(k * (2048 >> 4)), idesc_O, k != 0);
+          umma_f16_ss(tmem_O, p_desc, v_desc + uint64_t(k * (2048 >> 4)), idesc_O, k != 0);
         }
         umma_commit(o_full);
         umma_commit(&kv_empty[s]);
@@ -210,7 +210,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
 #pragma unroll
       for (int d = 0; d < DH; ++d) o[d] *= alpha;
-      // pass 2: probabilities -> bf16 P tile (swizzled K-major A operand), row sum in fp32
+      // pass 2: probabilities -> f16 P tile (swizzled K-major A operand), row sum in fp32
       float lsum = 0.f;
 #pragma unroll 1
       for (int c = 0; c < BKV / 32; ++c) {
@@ -225,7 +225,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const float p0 = fast_exp2(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_new));
             const float p1 = fast_exp2(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -m_new));
             l4[(i >> 1) & 3] += p0 + p1;
-            packed[i >> 1] = pack_bf16x2(p0, p1);
+            packed[i >> 1] = pack_f16x2(p0, p1);
           }
           lsum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
         } else if (fast) {
@@ -236,7 +236,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const float p0 = i < nv ? fast_exp2(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_new)) : 0.f;
             const float p1 = i + 1 < nv ? fast_exp2(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -m_new)) : 0.f;
             l4[(i >> 1) & 3] += p0 + p1;
-            packed[i >> 1] = pack_bf16x2(p0, p1);
+            packed[i >> 1] = pack_f16x2(p0, p1);
           }
           lsum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
         } else {
@@ -252,7 +252,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               pv[u] = ok ? fast_exp2(__uint_as_float(rr[i + u]) * p.scale_log2 - m_new) : 0.f;
             }
             lsum += pv[0] + pv[1];
-            packed[i >> 1] = pack_bf16x2(pv[0], pv[1]);
+            packed[i >> 1] = pack_f16x2(pv[0], pv[1]);
           }
         }
         uint8_t* blk = sP + (c >> 1) * (BQ * 128) + r * 128;
@@ -283,15 +283,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     if (qi < p.Sq) {
       const float inv = l > 0.f ? 1.f / l : 0.f;   // fully masked row -> zeros (layers.py:25)
-      bf16* op = p.out + size_t(b) * p.o_batch_stride + size_t(qi) * p.ldo + h * DH;
+      f16* op = p.out + size_t(b) * p.o_batch_stride + size_t(qi) * p.ldo + h * DH;
 #pragma unroll
       for (int d = 0; d < DH; d += 8) {
         uint4 t;
-        t.x = pack_bf16x2(o[d + 0] * inv, o[d + 1] * inv);
-        t.y = pack_bf16x2(o[d + 2] * inv, o[d + 3] * inv);
-        t.z = pack_bf16x2(o[d + 4] * inv, o[d + 5] * inv);
-        t.w = pack_bf16x2(o[d + 6] * inv, o[d + 7] * inv);
+        t.x = pack_f16x2(o[d + 0] * inv, o[d + 1] * inv);
+        t.y = pack_f16x2(o[d + 2] * inv, o[d + 3] * inv);
+        t.z = pack_f16x2(o[d + 4] * inv, o[d + 5] * inv);
+        t.w = pack_f16x2(o[d + 6] * inv, o[d + 7] * inv);
         *reinterpret_cast<uint4*>(op + d) = t;
+        if (p.out_lo_off)
+          *reinterpret_cast<uint4*>(op + p.out_lo_off + d) =
+              make_uint4(f16x2_residual(o[d + 0] * inv, o[d + 1] * inv, t.x), f16x2_residual(o[d + 2] * inv, o[d + 3] * inv, t.y),
+                         f16x2_residual(o[d + 4] * inv, o[d + 5] * inv, t.z), f16x2_residual(o[d + 6] * inv, o[d + 7] * inv, t.w));
       }
     }
   }
@@ -304,8 +308,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 __global__ void attn_naive_kernel(AttnParams p) {
   const int qi = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int lane = threadIdx.x;
-  const bf16* q = p.q + size_t(b) * p.q_batch_stride + size_t(qi) * p.ldq + h * DH;
-  const float q0 = __bfloat162float(q[lane * 2]), q1 = __bfloat162float(q[lane * 2 + 1]);
+  const f16* q = p.q + size_t(b) * p.q_batch_stride + size_t(qi) * p.ldq + h * DH;
+  const float q0 = __half2float(q[lane * 2]), q1 = __half2float(q[lane * 2 + 1]);
   bool row_masked = p.q_valid && p.q_valid[size_t(b) * p.Sq + qi] == 0;
   float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
   for (int kj = 0; kj < p.Sk; ++kj) {
@@ -315,21 +319,26 @@ __global__ void attn_naive_kernel(AttnParams p) {
     if (p.k_valid && p.k_valid[size_t(b) * p.Sk + kj] == 0) ok = false;
     if (p.dense_mask && p.dense_mask[(size_t(p.mask_B > 1 ? b : 0) * p.Sq + qi) * p.Sk + kj] != 0) ok = false;
     if (!ok) continue;
-    const bf16* k = p.k + size_t(b) * p.k_batch_stride + size_t(kj) * p.ldk + h * DH;
-    const bf16* v = p.v + size_t(b) * p.v_batch_stride + size_t(kj) * p.ldv + h * DH;
-    float s = q0 * __bfloat162float(k[lane * 2]) + q1 * __bfloat162float(k[lane * 2 + 1]);
+    const f16* k = p.k + size_t(b) * p.k_batch_stride + size_t(kj) * p.ldk + h * DH;
+    const f16* v = p.v + size_t(b) * p.v_batch_stride + size_t(kj) * p.ldv + h * DH;
+    float s = q0 * __half2float(k[lane * 2]) + q1 * __half2float(k[lane * 2 + 1]);
     s = warp_sum(s) * p.scale;
     const float m_new = fmaxf(m, s);
     const float a = expf(m - m_new), pw = expf(s - m_new);
     l = l * a + pw;
-    o0 = o0 * a + pw * __bfloat162float(v[lane * 2]);
-    o1 = o1 * a + pw * __bfloat162float(v[lane * 2 + 1]);
+    o0 = o0 * a + pw * __half2float(v[lane * 2]);
+    o1 = o1 * a + pw * __half2float(v[lane * 2 + 1]);
     m = m_new;
   }
   const float inv = l > 0.f ? 1.f / l : 0.f;
-  bf16* op = p.out + size_t(b) * p.o_batch_stride + size_t(qi) * p.ldo + h * DH;
-  op[lane * 2] = __float2bfloat16(o0 * inv);
-  op[lane * 2 + 1] = __float2bfloat16(o1 * inv);
+  f16* op = p.out + size_t(b) * p.o_batch_stride + size_t(qi) * p.ldo + h * DH;
+  const f16 h0 = f16_sat(o0 * inv), h1 = f16_sat(o1 * inv);
+  op[lane * 2] = h0;
+  op[lane * 2 + 1] = h1;
+  if (p.out_lo_off) {
+    op[p.out_lo_off + lane * 2] = f16_sat(o0 * inv - __half2float(h0));
+    op[p.out_lo_off + lane * 2 + 1] = f16_sat(o1 * inv - __half2float(h1));
+  }
 }
 
 int check_params(const AttnParams& p) {
@@ -347,18 +356,18 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t s) {
   {
     uint64_t dims[3] = {(uint64_t)p.H * DH, (uint64_t)p.Sq, (uint64_t)p.B};
     uint64_t str[3] = {2, (uint64_t)p.ldq * 2, (uint64_t)p.q_batch_stride * 2};
-    if (int rc = make_tmap_bf16(&tmQ, p.q, 3, dims, str, box, nullptr)) return rc;
+    if (int rc = make_tmap_f16(&tmQ, p.q, 3, dims, str, box, nullptr)) return rc;
   }
   {
     uint64_t dims[3] = {(uint64_t)p.H * DH, (uint64_t)p.Sk, (uint64_t)p.B};
     uint64_t str[3] = {2, (uint64_t)p.ldk * 2, (uint64_t)p.k_batch_stride * 2};
-    if (int rc = make_tmap_bf16(&tmK, p.k, 3, dims, str, box, nullptr)) return rc;
+    if (int rc = make_tmap_f16(&tmK, p.k, 3, dims, str, box, nullptr)) return rc;
     str[1] = (uint64_t)p.ldv * 2;
     str[2] = (uint64_t)p.v_batch_stride * 2;
-    if (int rc = make_tmap_bf16(&tmV, p.v, 3, dims, str, box, nullptr)) return rc;
+    if (int rc = make_tmap_f16(&tmV, p.v, 3, dims, str, box, nullptr)) return rc;
   }
   AttnDev d;
-  d.out = p.out; d.ldo = p.ldo; d.o_batch_stride = p.o_batch_stride;
+  d.out = p.out; d.ldo = p.ldo; d.o_batch_stride = p.o_batch_stride; d.out_lo_off = p.out_lo_off;
   d.H = p.H; d.Sq = p.Sq; d.Sk = p.Sk;
   d.scale_log2 = p.scale * 1.4426950408889634f;
   d.causal = p.causal; d.k_lens = p.k_lens; d.q_valid = p.q_valid; d.k_valid = p.k_valid;

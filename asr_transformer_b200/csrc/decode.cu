@@ -1,9 +1,9 @@
 // Greedy decode step kernels (reference model.py:125-151, restated with a device-resident KV cache).
 //
 // Precision rule: the decode-step Linear layers must see fp32-accurate activations or the
-// autoregressive token stream drifts from the fp32 reference.  Activations are therefore split into bf16
+// autoregressive token stream drifts from the fp32 reference.  Activations are therefore split into f16
 // hi + lo parts (x = hi + lo up to 2^-17 relative) and each weight tile is multiplied by both on the tensor
-// cores (mma.sync m16n8k16, fp32 accumulate); weights are stored as bf16.  These kernels are bound by HBM/L2
+// cores (mma.sync m16n8k16, fp32 accumulate); weights are stored as f16.  These kernels are bound by HBM/L2
 // traffic (weights + K/V caches), not by the tensor pipe.
 #include "kernels.h"
 #include "ptx.cuh"
@@ -11,10 +11,10 @@
 namespace asr {
 namespace {
 
-__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                uint32_t b0, uint32_t b1) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -28,8 +28,8 @@ constexpr int DL_LD = DL_KC + 32;          // row stride (elements): 576 B == 64
 
 __global__ void __launch_bounds__(128)
 dec_linear_kernel(DecLinear p) {
-  __shared__ __align__(16) bf16 s_hi[DL_ROWS * DL_LD];
-  __shared__ __align__(16) bf16 s_lo[DL_ROWS * DL_LD];
+  __shared__ __align__(16) f16 s_hi[DL_ROWS * DL_LD];
+  __shared__ __align__(16) f16 s_lo[DL_ROWS * DL_LD];
   __shared__ float s_mean[DL_ROWS], s_rstd[DL_ROWS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, c = lane & 3;
@@ -71,12 +71,12 @@ dec_linear_kernel(DecLinear p) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[mt][i] = 0.f;
 
-  const bf16* wrow = p.w + size_t(n_base + g) * p.K + c * 8;
+  const f16* wrow = p.w + size_t(n_base + g) * p.K + c * 8;
 
   for (int kc = 0; kc < p.K; kc += DL_KC) {
     const int kw = min(DL_KC, p.K - kc);   // multiple of 32
     if (kc > 0) __syncthreads();
-    // stage activations: fp32 -> (LayerNorm) -> bf16 hi / lo
+    // stage activations: fp32 -> (LayerNorm) -> f16 hi / lo
     for (int idx = threadIdx.x; idx < DL_ROWS * (DL_KC / 4); idx += blockDim.x) {
       const int r = idx / (DL_KC / 4);
       const int k = (idx % (DL_KC / 4)) * 4;
@@ -94,13 +94,13 @@ dec_linear_kernel(DecLinear p) {
           v.w = (v.w - mean) * rstd * gm.w + bt.w;
         }
       }
-      const bf16 h0 = __float2bfloat16(v.x), h1 = __float2bfloat16(v.y), h2 = __float2bfloat16(v.z),
-                 h3 = __float2bfloat16(v.w);
+      const f16 h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z),
+                 h3 = __float2half_rn(v.w);
       uint2 hi, lo;
-      hi.x = pack_bf16x2(__bfloat162float(h0), __bfloat162float(h1));
-      hi.y = pack_bf16x2(__bfloat162float(h2), __bfloat162float(h3));
-      lo.x = pack_bf16x2(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1));
-      lo.y = pack_bf16x2(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
+      hi.x = pack_f16x2(__half2float(h0), __half2float(h1));
+      hi.y = pack_f16x2(__half2float(h2), __half2float(h3));
+      lo.x = pack_f16x2(v.x - __half2float(h0), v.y - __half2float(h1));
+      lo.y = pack_f16x2(v.z - __half2float(h2), v.w - __half2float(h3));
       *reinterpret_cast<uint2*>(s_hi + r * DL_LD + k) = hi;
       *reinterpret_cast<uint2*>(s_lo + r * DL_LD + k) = lo;
     }
@@ -122,10 +122,10 @@ dec_linear_kernel(DecLinear p) {
           const uint4 h_b = *reinterpret_cast<const uint4*>(s_hi + (r0 + 8) * DL_LD + kb * 32 + c * 8);
           const uint4 l_a = *reinterpret_cast<const uint4*>(s_lo + r0 * DL_LD + kb * 32 + c * 8);
           const uint4 l_b = *reinterpret_cast<const uint4*>(s_lo + (r0 + 8) * DL_LD + kb * 32 + c * 8);
-          mma_bf16_16816(acc[mt], h_a.x, h_b.x, h_a.y, h_b.y, wv[kb].x, wv[kb].y);
-          mma_bf16_16816(acc[mt], h_a.z, h_b.z, h_a.w, h_b.w, wv[kb].z, wv[kb].w);
-          mma_bf16_16816(acc[mt], l_a.x, l_b.x, l_a.y, l_b.y, wv[kb].x, wv[kb].y);
-          mma_bf16_16816(acc[mt], l_a.z, l_b.z, l_a.w, l_b.w, wv[kb].z, wv[kb].w);
+          mma_f16_16816(acc[mt], h_a.x, h_b.x, h_a.y, h_b.y, wv[kb].x, wv[kb].y);
+          mma_f16_16816(acc[mt], h_a.z, h_b.z, h_a.w, h_b.w, wv[kb].z, wv[kb].w);
+          mma_f16_16816(acc[mt], l_a.x, l_b.x, l_a.y, l_b.y, wv[kb].x, wv[kb].y);
+          mma_f16_16816(acc[mt], l_a.z, l_b.z, l_a.w, l_b.w, wv[kb].z, wv[kb].w);
         }
       }
     }
@@ -159,15 +159,15 @@ dec_linear_kernel(DecLinear p) {
       if (two) op[1] = v1;
       if (p.kv_cache && col >= p.kv_col0) {
         const int w = p.N - p.kv_col0;
-        bf16* kp = p.kv_cache + (size_t(row) * p.kv_rows + step) * w + (col - p.kv_col0);
-        kp[0] = __float2bfloat16(v0);
-        if (two) kp[1] = __float2bfloat16(v1);
+        f16* kp = p.kv_cache + (size_t(row) * p.kv_rows + step) * w + (col - p.kv_col0);
+        kp[0] = __float2half_rn(v0);
+        if (two) kp[1] = __float2half_rn(v1);
       }
     }
   }
 }
 
-// ---------------------------------------------------------------- single-query attention over a bf16 K/V cache
+// ---------------------------------------------------------------- single-query attention over a f16 K/V cache
 // One CTA per (head, utterance); 8 lanes per key row (8 x 16 B = the 128-byte head slice), fp32 math.
 __global__ void __launch_bounds__(128)
 dec_attn_kernel(DecAttn p) {
@@ -187,18 +187,18 @@ dec_attn_kernel(DecAttn p) {
     q[0] = a.x * p.scale; q[1] = a.y * p.scale; q[2] = a.z * p.scale; q[3] = a.w * p.scale;
     q[4] = bq.x * p.scale; q[5] = bq.y * p.scale; q[6] = bq.z * p.scale; q[7] = bq.w * p.scale;
   }
-  const bf16* kb = p.k + size_t(b) * p.kv_batch_stride + h * 64 + c8 * 8;
-  const bf16* vb = p.v + size_t(b) * p.kv_batch_stride + h * 64 + c8 * 8;
+  const f16* kb = p.k + size_t(b) * p.kv_batch_stride + h * 64 + c8 * 8;
+  const f16* vb = p.v + size_t(b) * p.kv_batch_stride + h * 64 + c8 * 8;
 
   const unsigned gmask = 0xFFu << (lane & 24);
   float mx = -INFINITY;
   for (int kj = grp; kj < n; kj += 16) {
     const uint4 kv = __ldg(reinterpret_cast<const uint4*>(kb + size_t(kj) * p.ldkv));
-    const __nv_bfloat162* k2 = reinterpret_cast<const __nv_bfloat162*>(&kv);
+    const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(k2[i]);
+      const float2 f = __half22float2(k2[i]);
       s = fmaf(q[2 * i], f.x, s);
       s = fmaf(q[2 * i + 1], f.y, s);
     }
@@ -229,10 +229,10 @@ dec_attn_kernel(DecAttn p) {
   for (int kj = grp; kj < n; kj += 16) {
     const float pw = s_sc[kj];
     const uint4 vv = __ldg(reinterpret_cast<const uint4*>(vb + size_t(kj) * p.ldkv));
-    const __nv_bfloat162* v2 = reinterpret_cast<const __nv_bfloat162*>(&vv);
+    const __half2* v2 = reinterpret_cast<const __half2*>(&vv);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 f = __bfloat1622float2(v2[i]);
+      const float2 f = __half22float2(v2[i]);
       o[2 * i] = fmaf(pw, f.x, o[2 * i]);
       o[2 * i + 1] = fmaf(pw, f.y, o[2 * i + 1]);
     }

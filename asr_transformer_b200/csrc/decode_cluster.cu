@@ -17,8 +17,8 @@
 //     the access sequence is static, so memory latency is hidden and the step is bound by the L2 -> SM stream;
 //   * Linear layers run on the tensor cores with the roles swapped (weights = A operand, the <= 8 utterances of the
 //     cluster = N dimension of mma.m16n8k16) from a fragment-major packed image: one conflict-free LDS.128 IS the A
-//     fragment of one MMA; activations are fp32-accurate (bf16 hi + lo split, two passes, fp32 accumulate - Q13).
-// LayerNorm / softmax / residual / logits are fp32; K/V caches bf16; argmax lowest-index tie-break (model.py:143).
+//     fragment of one MMA; activations are fp32-accurate (f16 hi + lo split, two passes, fp32 accumulate - Q13).
+// LayerNorm / softmax / residual / logits are fp32; K/V caches f16; argmax lowest-index tie-break (model.py:143).
 // The kernel is specialised at compile time for (heads, FFN rows per CTA, vocabulary rows per CTA, utterance slots).
 #include <cstdlib>
 
@@ -109,7 +109,7 @@ __device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
 __device__ __forceinline__ uint4 lds128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
-  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
 }
@@ -168,7 +168,7 @@ __host__ __device__ inline SmemMap smem_map(int nstages) {
   m.hid_lo = take(S::GUP * S::LDH);
   m.o_hi = take(S::GUP * S::LDO);
   m.o_lo = take(S::GUP * S::LDO);
-  m.q = take(S::GUP * 64 * 4);                         // bf16 hi [GUP][64] | bf16 lo [GUP][64], fragment order
+  m.q = take(S::GUP * 64 * 4);                         // f16 hi [GUP][64] | f16 lo [GUP][64], fragment order
   m.kvrow = take(S::GUP * 128 * 2);
   m.scratch = take(24 * 32 * 16);                      // [KG * MT <= 24 when KG > 1][32 lanes] float4 partial tiles
   m.prm = take(S::SMALL_BYTES);
@@ -264,7 +264,7 @@ struct Consumer {
 // [k-tile s (2)][lane = g*4 + tg (32)][16 B] with the 16 bytes = the mma.m16n8k16 A fragment {a0,a1,a2,a3} of that
 // lane: {W[g][c..c+1], W[g+8][c..c+1], W[g][c+2..c+3], W[g+8][c+2..c+3]}, c = 32 kb + 8 tg + 4 s, i.e. the K
 // permutation k_mma {2tg, 2tg+1, 2tg+8, 2tg+9} <-> columns {c..c+3}.  The B fragment applies the same permutation:
-// lane (g, tg) reads the 16 bytes x[u = g][32 kb + 8 tg .. +7] (bf16 hi and lo copies; row stride == 64 mod 128 B:
+// lane (g, tg) reads the 16 bytes x[u = g][32 kb + 8 tg .. +7] (f16 hi and lo copies; row stride == 64 mod 128 B:
 // conflict free) and feeds halves s = 0 / 1 to the two MMAs.  Unit (m-tile mt, k-group kg) belongs to warp
 // (mt * KG + kg) % 8.  The finished tile {(n = 16mt+g, u = 2tg), (n, u+1), (n+8, u), (n+8, u+1)} goes to
 // epi(n, u0, v(u0), v(u0+1)); with KG > 1 the k-group partials are first combined through `scratch`.
@@ -368,10 +368,10 @@ __device__ __forceinline__ void mm_stream(Consumer& c, const uint8_t* xhi, const
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm / split
-// rows u < GU of h (fp32, stride D) -> bf16 hi + lo rows (stride ld elements); warp u handles row u.
+// rows u < GU of h (fp32, stride D) -> f16 hi + lo rows (stride ld elements); warp u handles row u.
 template <int D>
-__device__ __forceinline__ void rows_to_hilo(const float* h, int GU, const float* gam, const float* bet, bf16* hi,
-                                             bf16* lo, int ld) {
+__device__ __forceinline__ void rows_to_hilo(const float* h, int GU, const float* gam, const float* bet, f16* hi,
+                                             f16* lo, int ld) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp < GU) {
     const float* src = h + warp * D;
@@ -395,9 +395,9 @@ __device__ __forceinline__ void rows_to_hilo(const float* h, int GU, const float
     }
 #pragma unroll
     for (int i = 0; i < D / 32; ++i) {
-      const bf16 hh = __float2bfloat16(x[i]);
+      const f16 hh = __float2half_rn(x[i]);
       hi[warp * ld + lane + 32 * i] = hh;
-      lo[warp * ld + lane + 32 * i] = __float2bfloat16(x[i] - __bfloat162float(hh));
+      lo[warp * ld + lane + 32 * i] = __float2half_rn(x[i] - __half2float(hh));
     }
   }
 }
@@ -405,7 +405,7 @@ __device__ __forceinline__ void rows_to_hilo(const float* h, int GU, const float
 // LayerNorm of the rows u < GU by ALL consumer warps: warp (part, u) owns D / WPU elements of row u; one pass over
 // x - x[0] (shifted sums: no cancellation), partial (sum, sum of squares) per warp combined through shared memory.
 template <class S>
-__device__ __forceinline__ void ln_rows(const float* h, int GU, const float* gam, const float* bet, bf16* hi, bf16* lo,
+__device__ __forceinline__ void ln_rows(const float* h, int GU, const float* gam, const float* bet, f16* hi, f16* lo,
                                         float* red /* [NCW][2] */) {
   constexpr int D = S::D, WPU = S::WPU, EPL = D / (32 * WPU);
   static_assert(D % (32 * WPU) == 0, "LayerNorm split");
@@ -442,9 +442,9 @@ __device__ __forceinline__ void ln_rows(const float* h, int GU, const float* gam
     for (int i = 0; i < EPL; ++i) {
       const int k = k0 + 32 * i;
       const float y = (x[i] - mean) * rstd * gam[k] + bet[k];
-      const bf16 hh = __float2bfloat16(y);
+      const f16 hh = __float2half_rn(y);
       hi[u * (D + 32) + k] = hh;
-      lo[u * (D + 32) + k] = __float2bfloat16(y - __bfloat162float(hh));
+      lo[u * (D + 32) + k] = __float2half_rn(y - __half2float(hh));
     }
   }
 }
@@ -452,7 +452,7 @@ __device__ __forceinline__ void ln_rows(const float* h, int GU, const float* gam
 // ------------------------------------------------------------------------------------------------ attention
 // Single-query attention of ONE head on the tensor cores, 16 keys per tile, flash style (log2 units).
 //   S = K q : mma.m16n8k16 with A = the K tile [16 keys x 16 dims] (ldmatrix from the 128-byte-swizzled rows TMA
-//             wrote), B = q with column 0 = bf16 hi part, column 1 = lo part -> score(key) = c(col 0) + c(col 1), exact
+//             wrote), B = q with column 0 = f16 hi part, column 1 = lo part -> score(key) = c(col 0) + c(col 1), exact
 //             to fp32 products; the scores of keys g / g+8 live in lanes (g, tg = 0).
 //   o += V^T p: A = V^T [16 dims x 16 keys] (ldmatrix.trans of the same row-major rows), B = p with columns hi | lo.
 // Running max m is warp-uniform; the running sum l is kept per lane and reduced once at the end.
@@ -476,24 +476,24 @@ __device__ __forceinline__ void attn_init(AttnT& st) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) st.o[i][j] = 0.f;
 }
-// q of one utterance is kept as bf16 hi and lo parts in B-fragment order: element d (k-tile kt = d / 16, r = d % 16)
+// q of one utterance is kept as f16 hi and lo parts in B-fragment order: element d (k-tile kt = d / 16, r = d % 16)
 // lives at index ((tg * 4 + kt) * 4 + slot), tg = (r % 8) / 2, slot = (r / 8) * 2 + (r % 2), so that lane (g, tg) reads
 // its four k-tile fragments {b0, b1} with two LDS.128 (g = 0: hi part = MMA column 0, g = 1: lo part = column 1).
 __device__ __forceinline__ int q_frag_index(int d) {
   const int kt = d >> 4, r = d & 15;
   return (((r & 7) >> 1) * 4 + kt) * 4 + (r >> 3) * 2 + (r & 1);
 }
-__device__ __forceinline__ void q_store(bf16* q_hi, bf16* q_lo, int u, int d, float y) {
-  const bf16 h = __float2bfloat16(y);
+__device__ __forceinline__ void q_store(f16* q_hi, f16* q_lo, int u, int d, float y) {
+  const f16 h = __float2half_rn(y);
   const int i = u * 64 + q_frag_index(d);
   q_hi[i] = h;
-  q_lo[i] = __float2bfloat16(y - __bfloat162float(h));
+  q_lo[i] = __float2half_rn(y - __half2float(h));
 }
-__device__ __forceinline__ void attn_q_frags(const bf16* q_hi, const bf16* q_lo, int u, uint32_t (&qf)[8]) {
+__device__ __forceinline__ void attn_q_frags(const f16* q_hi, const f16* q_lo, int u, uint32_t (&qf)[8]) {
   const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
   if (g < 2) {
-    const bf16* src = (g == 0 ? q_hi : q_lo) + u * 64 + tg * 16;
+    const f16* src = (g == 0 ? q_hi : q_lo) + u * 64 + tg * 16;
     a = lds128(src);
     b = lds128(src + 8);
   }
@@ -525,15 +525,15 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// p -> (bf16 hi part) | (bf16 lo part) << 16 with hi + lo == p to 2^-17 relative
+// p -> (f16 hi part) | (f16 lo part) << 16 with hi + lo == p to 2^-17 relative
 __device__ __forceinline__ uint32_t hilo_pack(float p) {
-  const float r = p - __bfloat162float(__float2bfloat16_rn(p));
+  const float r = p - __half2float(__float2half_rn(p));
   uint32_t x;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(r), "f"(p));   // upper half = bf16(r), lower half = bf16(p)
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(r), "f"(p));   // upper half = f16(r), lower half = f16(p)
   return x;
 }
 // B fragment of the probabilities: lane (g, tg) holds keys 2tg, 2tg+1 (b0) and 2tg+8, 2tg+9 (b1) of column g.  Column
-// 0 carries the bf16 hi parts, column 1 the lo parts; the other columns are never read (they repeat hi / lo by the
+// 0 carries the f16 hi parts, column 1 the lo parts; the other columns are never read (they repeat hi / lo by the
 // parity of g, so no lane needs a zero).  xa / xb: hilo_pack of the probabilities of keys g / g + 8 (lanes tg == 0).
 // Always called by the whole warp, outside data-dependent branches (plain SHFL, no divergence guards).
 __device__ __forceinline__ void p_frags(uint32_t xa, uint32_t xb, uint32_t& b0, uint32_t& b1) {
@@ -645,9 +645,9 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t
     c0 += SC * RPS;
   } while (c0 < n_keys);
 }
-// merge the key partitions of every utterance slot and emit o (bf16 hi + lo rows, stride 96 elements)
+// merge the key partitions of every utterance slot and emit o (f16 hi + lo rows, stride 96 elements)
 template <class S>
-__device__ __forceinline__ void attn_finish(AttnT& st, int GU, float* part_buf, float* stat, bf16* o_hi, bf16* o_lo) {
+__device__ __forceinline__ void attn_finish(AttnT& st, int GU, float* part_buf, float* stat, f16* o_hi, f16* o_lo) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
   const float l = warp_sum(st.l);
   if (tg == 0) {
@@ -676,9 +676,9 @@ __device__ __forceinline__ void attn_finish(AttnT& st, int GU, float* part_buf, 
       ls += stat[NCW + pI * S::GUP + uu] * f;
     }
     const float y = ls > 0.f ? t / ls : 0.f;
-    const bf16 hh = __float2bfloat16(y);
+    const f16 hh = __float2half_rn(y);
     o_hi[uu * 96 + dd] = hh;
-    o_lo[uu * 96 + dd] = __float2bfloat16(y - __bfloat162float(hh));
+    o_lo[uu * 96 + dd] = __float2half_rn(y - __half2float(hh));
   }
   consumer_sync();
 }
@@ -703,15 +703,15 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
   ring.buf = smem + sm.ring;
   ring.nstages = p.nstages;
   float* s_h = reinterpret_cast<float*>(smem + sm.h);
-  bf16* xn_hi = reinterpret_cast<bf16*>(smem + sm.xn_hi);
-  bf16* xn_lo = reinterpret_cast<bf16*>(smem + sm.xn_lo);
-  bf16* hid_hi = reinterpret_cast<bf16*>(smem + sm.hid_hi);
-  bf16* hid_lo = reinterpret_cast<bf16*>(smem + sm.hid_lo);
-  bf16* o_hi = reinterpret_cast<bf16*>(smem + sm.o_hi);
-  bf16* o_lo = reinterpret_cast<bf16*>(smem + sm.o_lo);
-  bf16* q_hi = reinterpret_cast<bf16*>(smem + sm.q);
-  bf16* q_lo = q_hi + GUP * 64;
-  bf16* kv_row = reinterpret_cast<bf16*>(smem + sm.kvrow);
+  f16* xn_hi = reinterpret_cast<f16*>(smem + sm.xn_hi);
+  f16* xn_lo = reinterpret_cast<f16*>(smem + sm.xn_lo);
+  f16* hid_hi = reinterpret_cast<f16*>(smem + sm.hid_hi);
+  f16* hid_lo = reinterpret_cast<f16*>(smem + sm.hid_lo);
+  f16* o_hi = reinterpret_cast<f16*>(smem + sm.o_hi);
+  f16* o_lo = reinterpret_cast<f16*>(smem + sm.o_lo);
+  f16* q_hi = reinterpret_cast<f16*>(smem + sm.q);
+  f16* q_lo = q_hi + GUP * 64;
+  f16* kv_row = reinterpret_cast<f16*>(smem + sm.kvrow);
   float4* scratch = reinterpret_cast<float4*>(smem + sm.scratch);
   float* prm = reinterpret_cast<float*>(smem + sm.prm);
   float* s_lg = reinterpret_cast<float*>(smem + sm.lg);
@@ -790,7 +790,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
                   const int n = (min(RPS, nk - r0) + 15) & ~15;   // whole 16-key tiles (rows past t are zero)
                   uint8_t* dst = pr.begin(uint32_t(GU) * n * 128u);
                   for (int u = 0; u < GU; ++u) {
-                    const bf16* src = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head +
+                    const f16* src = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head +
                                       size_t(kv) * Lc * 64 + size_t(c0 + r0) * 64;
                     bulk_load(dst + u * RPS * 128, src, n * 128, pr.bar(), pol_kv);
                   }
@@ -865,7 +865,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
       for (int k = 0; k < CS - 1; ++k) st_async_v2(peer_recv[k] + off, v0, v1, peer_bar[k] + par * 8u);
     };
     // ... and, fused into its tail, what follows every all-reduce: LayerNorm of the new rows (gam != nullptr) or the
-    // plain bf16 hi | lo split (classifier input).  Thread tid owns elements idx = tid + NCT k: utterance u = tid % GUP,
+    // plain f16 hi | lo split (classifier input).  Thread tid owns elements idx = tid + NCT k: utterance u = tid % GUP,
     // n = idx / GUP; the new values stay in registers between the sum and the normalisation.  Variance from one pass
     // over (x - c), c = the row's previous first element (same for every thread: read before the first barrier).
     auto all_reduce_finish = [&](const float* bias, const float* gam, const float* bet) {
@@ -922,9 +922,9 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
         for (int k = 0; k < EP; ++k) {
           const int n = nb + k * (NCT / GUP);
           const float y = gam ? (hv[k] - mean) * rstd * gam[n] + bet[n] : hv[k];
-          const bf16 hh = __float2bfloat16(y);
+          const f16 hh = __float2half_rn(y);
           xn_hi[u * (D + 32) + n] = hh;
-          xn_lo[u * (D + 32) + n] = __float2bfloat16(y - __bfloat162float(hh));
+          xn_lo[u * (D + 32) + n] = __float2half_rn(y - __half2float(hh));
         }
       }
       consumer_sync();
@@ -988,26 +988,26 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
                   q_store(q_hi, q_lo, u0 + 1, n, y1 * qscale);
                 } else {   // k_t | v_t rows in the cache's swizzled chunk order (chunk ^ (t & 7)): TMA-stored as they are
                   const int e = n - 64, pos = (e & 64) + ((((e & 63) >> 3) ^ (t & 7)) << 3) + (e & 7);
-                  kv_row[u0 * 128 + pos] = __float2bfloat16(y0);
-                  kv_row[(u0 + 1) * 128 + pos] = __float2bfloat16(y1);
+                  kv_row[u0 * 128 + pos] = __float2half_rn(y0);
+                  kv_row[(u0 + 1) * 128 + pos] = __float2half_rn(y1);
                 }
               });
               fence_proxy_async();                                   // kv_row: generic writes -> the TMA store below
               consumer_sync();
               mark(2);
-              // append k_t, v_t (bf16) to the device-resident cache: [layer][utterance][head][K rows | V rows][Lc][64], the
+              // append k_t, v_t (f16) to the device-resident cache: [layer][utterance][head][K rows | V rows][Lc][64], the
               // 16-byte chunks of row t stored swizzled (chunk ^ (t & 7)) so that the bulk copy lands ldmatrix-ready.  The
               // first row of every 16-row block also zeroes the block's other rows: whole 16-key tiles are always finite.
               if (tid < GU * 2) {                                    // one 128-byte TMA store per (utterance, K | V)
                 const int u = tid >> 1, kv = tid & 1;
-                bf16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * Lc * 64 +
+                f16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * Lc * 64 +
                             size_t(t) * 64;
                 bulk_store(dst, kv_row + u * 128 + kv * 64, 128);
               }
               if ((t & 15) == 0) {
                 for (int i = tid; i < GU * 2 * 15 * 8; i += NCT) {
                   const int u = i / 240, rem = i - u * 240, kv = rem / 120, w = rem - kv * 120;   // w: 16-byte word in 15 rows
-                  bf16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * Lc * 64 +
+                  f16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * Lc * 64 +
                               size_t(t + 1) * 64 + w * 8;
                   *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
                 }
@@ -1055,11 +1055,11 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
             // ---- FFN: squeeze rows of this CTA + ReLU, then the matching K-slice of unsqueeze (model.py:73-74)
             mm_stream<MW1, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
               const float y0 = fmaxf(v0 + b_1[n], 0.f), y1 = fmaxf(v1 + b_1[n], 0.f);
-              const bf16 h0 = __float2bfloat16(y0), h1 = __float2bfloat16(y1);
+              const f16 h0 = __float2half_rn(y0), h1 = __float2half_rn(y1);
               hid_hi[u0 * (FFS + 32) + n] = h0;
-              hid_lo[u0 * (FFS + 32) + n] = __float2bfloat16(y0 - __bfloat162float(h0));
+              hid_lo[u0 * (FFS + 32) + n] = __float2half_rn(y0 - __half2float(h0));
               hid_hi[(u0 + 1) * (FFS + 32) + n] = h1;
-              hid_lo[(u0 + 1) * (FFS + 32) + n] = __float2bfloat16(y1 - __bfloat162float(h1));
+              hid_lo[(u0 + 1) * (FFS + 32) + n] = __float2half_rn(y1 - __half2float(h1));
             });
             consumer_sync();
             mark(9);
@@ -1305,13 +1305,13 @@ int launch_dec_cluster(ClusterParams& p, cudaStream_t s) {
     p.kv_evict_first = !(e && e[0] == 'l');
   }
 
-  // encoder K/V as a 2-D tensor: [nd * B * Tp rows][2D columns] bf16; box = [RPS rows][64 columns] (one head)
+  // encoder K/V as a 2-D tensor: [nd * B * Tp rows][2D columns] f16; box = [RPS rows][64 columns] (one head)
   CUtensorMap map;
   const int rps = (STAGE_BYTES / 128) / p.GUP;
   const uint64_t dims[2] = {uint64_t(2 * p.D), uint64_t(p.nd) * p.B * p.Tp};
   const uint64_t strides[2] = {0, uint64_t(4 * p.D)};
   const uint32_t box[2] = {64u, uint32_t(rps)};
-  if (int rc = make_tmap_bf16(&map, p.ckv, 2, dims, strides, box, nullptr, /*swizzle=*/128)) return rc;
+  if (int rc = make_tmap_f16(&map, p.ckv, 2, dims, strides, box, nullptr, /*swizzle=*/128)) return rc;
 
   const int n_clusters = (p.B + p.GU - 1) / p.GU;
   cudaLaunchConfig_t cfg{};

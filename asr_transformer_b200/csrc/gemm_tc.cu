@@ -28,8 +28,9 @@ constexpr size_t gemm_smem_bytes() {
 
 // Compile-time specialised epilogue of one full, vector-aligned 32-column chunk (the common case): only the loads,
 // math and stores of this GEMM's epilogue are emitted.  FLAGS: 1 bias, 2 relu, 4 positional rowvec, 8 residual,
-// 16 fp32 out, 32 bf16 out.
-enum { EF_BIAS = 1, EF_RELU = 2, EF_PE = 4, EF_RES = 8, EF_F32 = 16, EF_B16 = 32 };
+// 16 fp32 out, 32 f16 out, 64 f16 out as a hi | lo pair (lo = f16(v - hi) stored f16_lo_off elements further: the
+// A operand of a following a_split GEMM, fp32-accurate to 2^-22).
+enum { EF_BIAS = 1, EF_RELU = 2, EF_PE = 4, EF_RES = 8, EF_F32 = 16, EF_H16 = 32, EF_SPLIT = 64 };
 template <int FLAGS>
 __device__ __forceinline__ void epilogue_chunk_fast(const GemmEpilogue& ep, const uint32_t (&r)[32], int row, int col0,
                                                     const float* sbias_chunk) {
@@ -45,7 +46,7 @@ __device__ __forceinline__ void epilogue_chunk_fast(const GemmEpilogue& ep, cons
     for (int j = 0; j < 8; ++j) pe[j] = __ldg(pp + j);
   }
   float* of = (FLAGS & EF_F32) ? ep.out_f32 + size_t(row) * ep.ld_f32 + col0 : nullptr;
-  bf16* ob = (FLAGS & EF_B16) ? ep.out_bf16 + size_t(row) * ep.ld_bf16 + col0 : nullptr;
+  f16* ob = (FLAGS & EF_H16) ? ep.out_f16 + size_t(row) * ep.ld_f16 + col0 : nullptr;
 #pragma unroll
   for (int j = 0; j < 8; j += 2) {
     float v[8];
@@ -73,9 +74,14 @@ __device__ __forceinline__ void epilogue_chunk_fast(const GemmEpilogue& ep, cons
       *reinterpret_cast<float4*>(of + 4 * j) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(of + 4 * j + 4) = make_float4(v[4], v[5], v[6], v[7]);
     }
-    if (FLAGS & EF_B16)
-      *reinterpret_cast<uint4*>(ob + 4 * j) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                         pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    if (FLAGS & EF_H16) {
+      uint4 hi = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+      *reinterpret_cast<uint4*>(ob + 4 * j) = hi;
+      if (FLAGS & EF_SPLIT)
+        *reinterpret_cast<uint4*>(ob + ep.f16_lo_off + 4 * j) =
+            make_uint4(f16x2_residual(v[0], v[1], hi.x), f16x2_residual(v[2], v[3], hi.y),
+                       f16x2_residual(v[4], v[5], hi.z), f16x2_residual(v[6], v[7], hi.w));
+    }
   }
 }
 
@@ -85,9 +91,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
   // 32 consecutive columns of one row, processed 4 at a time.
   const bool res_vec = ep.residual && (ep.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
   const bool f32_vec = ep.out_f32 && (ep.ld_f32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.out_f32) & 15) == 0);
-  const bool b16_vec = ep.out_bf16 && (ep.ld_bf16 % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 7) == 0);
+  const bool h16_vec = ep.out_f16 && (ep.ld_f16 % 4 == 0) && (ep.f16_lo_off % 4 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(ep.out_f16) & 7) == 0);
   const float* pe_row = ep.rowvec ? ep.rowvec + size_t(row % ep.rowvec_period) * ep.ld_rowvec : nullptr;
-  if (col0 + 32 <= n_store && (!ep.residual || res_vec) && (!ep.out_f32 || f32_vec) && (!ep.out_bf16 || b16_vec) &&
+  if (col0 + 32 <= n_store && (!ep.residual || res_vec) && (!ep.out_f32 || f32_vec) && (!ep.out_f16 || h16_vec) &&
       (!pe_row || ((ep.ld_rowvec % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.rowvec) & 15) == 0)))) {
     // fast path: every global load of the chunk is in flight before the first use (the epilogue is latency-bound)
     float4 res[8], pe[8];
@@ -101,7 +108,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
 #pragma unroll
       for (int j = 0; j < 8; ++j) pe[j] = __ldg(pp + j);
     }
-    const bool b16_wide = ep.out_bf16 && (ep.ld_bf16 % 8 == 0) && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0);
+    const bool h16_wide = ep.out_f16 && (ep.ld_f16 % 8 == 0) && ((reinterpret_cast<uintptr_t>(ep.out_f16) & 15) == 0);
     uint32_t pk[2] = {0, 0};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -120,14 +127,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
       if (ep.residual) { v[0] += res[j].x; v[1] += res[j].y; v[2] += res[j].z; v[3] += res[j].w; }
       if (ep.out_f32)
         *reinterpret_cast<float4*>(ep.out_f32 + size_t(row) * ep.ld_f32 + col0 + 4 * j) = make_float4(v[0], v[1], v[2], v[3]);
-      if (ep.out_bf16) {
+      if (ep.out_f16) {
         uint2 t;
-        t.x = pack_bf16x2(v[0], v[1]);
-        t.y = pack_bf16x2(v[2], v[3]);
-        if (!b16_wide) {
-          *reinterpret_cast<uint2*>(ep.out_bf16 + size_t(row) * ep.ld_bf16 + col0 + 4 * j) = t;
+        t.x = pack_f16x2(v[0], v[1]);
+        t.y = pack_f16x2(v[2], v[3]);
+        if (ep.f16_lo_off)
+          *reinterpret_cast<uint2*>(ep.out_f16 + size_t(row) * ep.ld_f16 + ep.f16_lo_off + col0 + 4 * j) =
+              make_uint2(f16x2_residual(v[0], v[1], t.x), f16x2_residual(v[2], v[3], t.y));
+        if (!h16_wide) {
+          *reinterpret_cast<uint2*>(ep.out_f16 + size_t(row) * ep.ld_f16 + col0 + 4 * j) = t;
         } else if (j & 1) {      // 16-byte stores: half the L2 write transactions of this row-per-thread layout
-          *reinterpret_cast<uint4*>(ep.out_bf16 + size_t(row) * ep.ld_bf16 + col0 + 4 * (j - 1)) =
+          *reinterpret_cast<uint4*>(ep.out_f16 + size_t(row) * ep.ld_f16 + col0 + 4 * (j - 1)) =
               make_uint4(pk[0], pk[1], t.x, t.y);
         } else {
           pk[0] = t.x;
@@ -180,17 +190,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
           if (col + i < n_store) op[i] = v[i];
       }
     }
-    if (ep.out_bf16) {
-      bf16* op = ep.out_bf16 + size_t(row) * ep.ld_bf16 + col;
-      if (full && b16_vec) {
+    if (ep.out_f16) {
+      f16* op = ep.out_f16 + size_t(row) * ep.ld_f16 + col;
+      if (full && h16_vec) {
         uint2 t;
-        t.x = pack_bf16x2(v[0], v[1]);
-        t.y = pack_bf16x2(v[2], v[3]);
+        t.x = pack_f16x2(v[0], v[1]);
+        t.y = pack_f16x2(v[2], v[3]);
         *reinterpret_cast<uint2*>(op) = t;
+        if (ep.f16_lo_off)
+          *reinterpret_cast<uint2*>(op + ep.f16_lo_off) =
+              make_uint2(f16x2_residual(v[0], v[1], t.x), f16x2_residual(v[2], v[3], t.y));
       } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (col + i < n_store) op[i] = __float2bfloat16(v[i]);
+          if (col + i < n_store) {
+            const f16 hh = f16_sat(v[i]);
+            op[i] = hh;
+            if (ep.f16_lo_off) op[ep.f16_lo_off + i] = f16_sat(v[i] - __half2float(hh));
+          }
       }
     }
   }
@@ -206,7 +223,7 @@ constexpr int GEMM_THREADS = (EPI_WARPS + 2) * 32;
 template <int BN, int STAGES, int FLAGS>   // FLAGS >= 0: the specialised epilogue this launch uses; -1: generic
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
-               int M, int n_store, int K, int tiles_n, int n_tiles) {
+               int M, int n_store, int K, int nkw, int tiles_n, int n_tiles) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -259,14 +276,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
           tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BK, m0);
-          tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, &full_bar[s], kb * BK, n0);
+          tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, &full_bar[s], (kb < nkw ? kb : kb - nkw) * BK, n0);   // a_split: W twice
         }
       }
     }
   } else if (warp == EPI_WARPS + 1) {
     // ------------------------------------------------ UMMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0, 0);
       uint32_t it = 0, lt = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
         const uint32_t buf = lt & 1, use = lt >> 1;
@@ -281,7 +298,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + s * B_STAGE_BYTES), 16, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)   // +32 B per 16-element K step inside the 128 B swizzle row
-            umma_bf16_ss(acc, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0);
+            umma_f16_ss(acc, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0);
           umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full[buf]);
@@ -325,7 +342,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 template <int BN, int STAGES, int FLAGS>
 int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int n_store, int n_pad,
-                int K, cudaStream_t s) {
+                int K, int nkw, cudaStream_t s) {
   auto kern = gemm_tc_kernel<BN, STAGES, FLAGS>;
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
   static bool attr_set = false;
@@ -346,7 +363,7 @@ int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilog
   }
   const int tiles_n = n_pad / BN, n_tiles = tiles_n * ((M + BM - 1) / BM);
   const int grid = n_tiles < n_slots ? n_tiles : n_slots;
-  kern<<<grid, GEMM_THREADS, smem, s>>>(tmA, tmB, ep, M, n_store, K, tiles_n, n_tiles);
+  kern<<<grid, GEMM_THREADS, smem, s>>>(tmA, tmB, ep, M, n_store, K, nkw, tiles_n, n_tiles);
   ASR_CUDA_OK(cudaGetLastError());
   ASR_LAUNCHED(1);
   return 0;
@@ -356,51 +373,56 @@ int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilog
 // allows 16-byte accesses, the generic (fully predicated) epilogue otherwise
 template <int BN, int STAGES>
 int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int n_store, int n_pad,
-               int K, cudaStream_t s) {
+               int K, int nkw, cudaStream_t s) {
   const int flags = (ep.bias ? EF_BIAS : 0) | (ep.relu ? EF_RELU : 0) | (ep.rowvec ? EF_PE : 0) |
-                    (ep.residual ? EF_RES : 0) | (ep.out_f32 ? EF_F32 : 0) | (ep.out_bf16 ? EF_B16 : 0);
+                    (ep.residual ? EF_RES : 0) | (ep.out_f32 ? EF_F32 : 0) | (ep.out_f16 ? EF_H16 : 0) |
+                    ((ep.out_f16 && ep.f16_lo_off) ? EF_SPLIT : 0);
   const bool aligned =
       (!ep.residual || ((ep.ld_res % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0))) &&
       (!ep.out_f32 || ((ep.ld_f32 % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.out_f32) & 15) == 0))) &&
-      (!ep.out_bf16 || ((ep.ld_bf16 % 8 == 0) && ((reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) == 0))) &&
+      (!ep.out_f16 || ((ep.ld_f16 % 8 == 0) && (ep.f16_lo_off % 8 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(ep.out_f16) & 15) == 0))) &&
       (!ep.rowvec || ((ep.ld_rowvec % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.rowvec) & 15) == 0)));
   if (aligned) {
     switch (flags) {
-      case EF_BIAS | EF_B16: return launch_inst<BN, STAGES, EF_BIAS | EF_B16>(tmA, tmB, ep, M, n_store, n_pad, K, s);
-      case EF_BIAS | EF_RELU | EF_B16:
-        return launch_inst<BN, STAGES, EF_BIAS | EF_RELU | EF_B16>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+      case EF_BIAS | EF_H16: return launch_inst<BN, STAGES, EF_BIAS | EF_H16>(tmA, tmB, ep, M, n_store, n_pad, K, nkw, s);
+      case EF_BIAS | EF_RELU | EF_H16:
+        return launch_inst<BN, STAGES, EF_BIAS | EF_RELU | EF_H16>(tmA, tmB, ep, M, n_store, n_pad, K, nkw, s);
+      case EF_BIAS | EF_RELU | EF_H16 | EF_SPLIT:
+        return launch_inst<BN, STAGES, EF_BIAS | EF_RELU | EF_H16 | EF_SPLIT>(tmA, tmB, ep, M, n_store, n_pad, K, nkw, s);
       case EF_BIAS | EF_RES | EF_F32:
-        return launch_inst<BN, STAGES, EF_BIAS | EF_RES | EF_F32>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+        return launch_inst<BN, STAGES, EF_BIAS | EF_RES | EF_F32>(tmA, tmB, ep, M, n_store, n_pad, K, nkw, s);
       case EF_BIAS | EF_PE | EF_F32:
-        return launch_inst<BN, STAGES, EF_BIAS | EF_PE | EF_F32>(tmA, tmB, ep, M, n_store, n_pad, K, s);
-      case EF_F32: return launch_inst<BN, STAGES, EF_F32>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+        return launch_inst<BN, STAGES, EF_BIAS | EF_PE | EF_F32>(tmA, tmB, ep, M, n_store, n_pad, K, nkw, s);
+      case EF_F32: return launch_inst<BN, STAGES, EF_F32>(tmA, tmB, ep, M, n_store, n_pad, K, nkw, s);
       default: break;
     }
   }
-  return launch_inst<BN, STAGES, -1>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+  return launch_inst<BN, STAGES, -1>(tmA, tmB, ep, M, n_store, n_pad, K, nkw, s);
 }
 
-__global__ void gemm_naive_kernel(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N, int K,
+__global__ void gemm_naive_kernel(const f16* X, int ldx, const f16* W, int ldw, int M, int N, int K,
                                   GemmEpilogue ep) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int row = blockIdx.y;
   if (col >= N || row >= M) return;
   float acc = 0.f;
   for (int k = 0; k < K; ++k)
-    acc = fmaf(__bfloat162float(X[size_t(row) * ldx + k]), __bfloat162float(W[size_t(col) * ldw + k]), acc);
+    acc = fmaf(__half2float(X[size_t(row) * ldx + k]), __half2float(W[size_t(col) * ldw + k]), acc);
   if (ep.bias) acc += ep.bias[col];
   if (ep.relu) acc = fmaxf(acc, 0.f);
   if (ep.rowvec) acc += ep.rowvec[size_t(row % ep.rowvec_period) * ep.ld_rowvec + col];
   if (ep.residual) acc += ep.residual[size_t(row) * ep.ld_res + col];
   if (ep.out_f32) ep.out_f32[size_t(row) * ep.ld_f32 + col] = acc;
-  if (ep.out_bf16) ep.out_bf16[size_t(row) * ep.ld_bf16 + col] = __float2bfloat16(acc);
+  if (ep.out_f16) ep.out_f16[size_t(row) * ep.ld_f16 + col] = __float2half_rn(acc);
 }
 
 }  // namespace
 
-int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep_in,
-                   cudaStream_t s) {
+int launch_gemm_tc(const f16* X, int ldx, const f16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep_in,
+                   cudaStream_t s, int a_split) {
   if (M <= 0) return 0;
+  const int KA = a_split ? 2 * K : K;   // a_split: X = [hi | lo] halves of K columns each, both multiplied by W
   if (K % BK != 0 || K <= 0) return set_error(-2, "gemm: K=%d must be a positive multiple of 64", K);
   const int n_pad = (N + 63) / 64 * 64;   // W must hold n_pad rows (zero rows past N)
   GemmEpilogue ep = ep_in;
@@ -408,10 +430,10 @@ int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N,
 
   CUtensorMap tmA, tmB;
   {
-    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t dims[2] = {(uint64_t)KA, (uint64_t)M};
     uint64_t str[2] = {2, (uint64_t)ldx * 2};
     uint32_t box[2] = {BK, BM};
-    int rc = make_tmap_bf16(&tmA, X, 2, dims, str, box, nullptr);
+    int rc = make_tmap_f16(&tmA, X, 2, dims, str, box, nullptr);
     if (rc) return rc;
   }
   // Tile choice: 128-wide tiles (2 x 128 TMEM columns), 3-stage TMA ring (98 KB; ASR_B200_GEMM_STAGES=6 selects the
@@ -426,7 +448,7 @@ int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N,
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)n_pad};
     uint64_t str[2] = {2, (uint64_t)ldw * 2};
     uint32_t box[2] = {BK, (uint32_t)bn};
-    int rc = make_tmap_bf16(&tmB, W, 2, dims, str, box, nullptr);
+    int rc = make_tmap_f16(&tmB, W, 2, dims, str, box, nullptr);
     if (rc) return rc;
   }
   static const int stages = [] {
@@ -439,13 +461,13 @@ int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N,
       // the cluster decoder on the ~20 SMs it leaves free, and there the shallower ring measured better for both
       // (serving loop: 12.22 -> 12.06 ms per 128 utterances).  The grid follows the occupancy the runtime reports
       // (1 CTA per SM on the B200 driver used here; forcing 2 per SM changed nothing in the serving loop).
-      if (stages == 6) return launch_one<128, 6>(tmA, tmB, ep, M, n_store, n_pad, K, s);
-      return launch_one<128, 3>(tmA, tmB, ep, M, n_store, n_pad, K, s);
-    default: return launch_one<64, 8>(tmA, tmB, ep, M, n_store, n_pad, K, s);
+      if (stages == 6) return launch_one<128, 6>(tmA, tmB, ep, M, n_store, n_pad, KA, K / BK, s);
+      return launch_one<128, 3>(tmA, tmB, ep, M, n_store, n_pad, KA, K / BK, s);
+    default: return launch_one<64, 8>(tmA, tmB, ep, M, n_store, n_pad, KA, K / BK, s);
   }
 }
 
-int launch_gemm_naive(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+int launch_gemm_naive(const f16* X, int ldx, const f16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
                       cudaStream_t s) {
   if (M <= 0) return 0;
   const int n = ep.n_store > 0 ? ep.n_store : N;
@@ -492,13 +514,13 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tma_load_2d(sB, &tmB, &bar[0], 0, 0);
     mbar_wait(&bar[0], 0);
     tc_fence_after();
-    const uint32_t idesc = umma_idesc_bf16(128, N, 0, b_mn_major);
+    const uint32_t idesc = umma_idesc_f16(128, N, 0, b_mn_major);
     const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(sA), 16, 1024);
     const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB), b_mn_major ? 1024 : 16, 1024);
     for (int k = 0; k < 4; ++k) {
       // K-major: +32 B per K step; MN-major: 16 K rows of 128 B = +2048 B per K step
       const uint64_t b_adv = b_mn_major ? uint64_t(k * (2048 >> 4)) : uint64_t(k * 2);
-      umma_bf16_ss(tmem_base, a_desc + uint64_t(k * 2), b_desc + b_adv, idesc, k != 0);
+      umma_f16_ss(tmem_base, a_desc + uint64_t(k * 2), b_desc + b_adv, idesc, k != 0);
     }
     umma_commit(&bar[1]);
   }
@@ -518,7 +540,7 @@ umma_probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 }  // namespace
 
-int launch_umma_probe(const bf16* A, const bf16* Bm, float* D, int N, int b_mn_major, cudaStream_t s) {
+int launch_umma_probe(const f16* A, const f16* Bm, float* D, int N, int b_mn_major, cudaStream_t s) {
   if (b_mn_major ? (N != 64) : (N % 32 != 0 || N < 32 || N > 128))
     return set_error(-2, "umma_probe: unsupported N=%d for b_mn_major=%d", N, b_mn_major);
   CUtensorMap tmA, tmB;
@@ -526,14 +548,14 @@ int launch_umma_probe(const bf16* A, const bf16* Bm, float* D, int N, int b_mn_m
     uint64_t dims[2] = {64, 128};
     uint64_t str[2] = {2, 128};
     uint32_t box[2] = {64, 128};
-    int rc = make_tmap_bf16(&tmA, A, 2, dims, str, box, nullptr);
+    int rc = make_tmap_f16(&tmA, A, 2, dims, str, box, nullptr);
     if (rc) return rc;
   }
   {
     uint64_t dims[2] = {64, (uint64_t)(b_mn_major ? 64 : N)};
     uint64_t str[2] = {2, 128};
     uint32_t box[2] = {64, (uint32_t)(b_mn_major ? 64 : N)};
-    int rc = make_tmap_bf16(&tmB, Bm, 2, dims, str, box, nullptr);
+    int rc = make_tmap_f16(&tmB, Bm, 2, dims, str, box, nullptr);
     if (rc) return rc;
   }
   const size_t smem = 32768 + 64 + 1024;

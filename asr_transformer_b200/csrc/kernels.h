@@ -1,14 +1,14 @@
 // Internal launcher interface between the C-ABI layer (api.cu) and the sm_100a kernels.
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
 
 namespace asr {
 
-typedef __nv_bfloat16 bf16;
+typedef __half f16;
 
 // ---- error plumbing (thread-local message, negative return codes; never throws / aborts)
 int set_error(int code, const char* fmt, ...);
@@ -25,8 +25,8 @@ extern unsigned long long g_kernel_launches;
 #define ASR_LAUNCHED(n) (::asr::g_kernel_launches += (n))
 
 // ---- TMA tensor maps (driver entry point resolved at run time, no link-time libcuda dependency)
-// bf16 tensor, innermost dim contiguous. dims/strides innermost first; strides in BYTES for dims >= 1.
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+// f16 tensor, innermost dim contiguous. dims/strides innermost first; strides in BYTES for dims >= 1.
+int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, const uint32_t* elem_strides /*nullable*/, int swizzle_bytes = 128 /* 0 = none */);
 
 // ---- GEMM  Y[M,N] = X[M,K] * W[N,K]^T (+bias)(relu)(+rowvec)(+residual)  (tcgen05 / TMEM / TMA)
@@ -39,24 +39,28 @@ struct GemmEpilogue {
   int ld_rowvec = 0;
   float* out_f32 = nullptr;          // [M, ld_f32]
   int ld_f32 = 0;
-  bf16* out_bf16 = nullptr;          // [M, ld_bf16]
-  int ld_bf16 = 0;
+  f16* out_f16 = nullptr;          // [M, ld_f16]
+  int ld_f16 = 0;
+  int f16_lo_off = 0;                // != 0: also store lo = f16(v - f16(v)) at column + f16_lo_off (hi | lo A operand)
   int relu = 0;
   int n_store = 0;                   // columns >= n_store are not stored (0 => N)
 };
-// X: bf16 [M, K] (row stride ldx elements), W: bf16 [N_pad, K] (row stride ldw), K % 64 == 0, N_pad % 64 == 0.
-int launch_gemm_tc(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
-                   cudaStream_t s);
+// X: f16 [M, K] (row stride ldx elements), W: f16 [N_pad, K] (row stride ldw), K % 64 == 0, N_pad % 64 == 0.
+// a_split != 0: X is [M, 2K] = [hi | lo] (x = hi + lo to 2^-22): Y = (hi + lo) W^T, i.e. fp32-accurate activations on the
+// fp16 tensor cores for twice the MMAs (the K loop runs over both halves, W is streamed twice).
+int launch_gemm_tc(const f16* X, int ldx, const f16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+                   cudaStream_t s, int a_split = 0);
 // Debug / cross-check: same contract, one thread per output element on CUDA cores.
-int launch_gemm_naive(const bf16* X, int ldx, const bf16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+int launch_gemm_naive(const f16* X, int ldx, const f16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
                       cudaStream_t s);
 
 // ---- multi-head attention core (flash style, tcgen05).  dh = 64 only.
 struct AttnParams {
-  const bf16* q = nullptr;  int ldq = 0;  long long q_batch_stride = 0;   // element strides; head h at column h*64
-  const bf16* k = nullptr;  int ldk = 0;  long long k_batch_stride = 0;
-  const bf16* v = nullptr;  int ldv = 0;  long long v_batch_stride = 0;
-  bf16* out = nullptr;      int ldo = 0;  long long o_batch_stride = 0;   // [B, Sq, H*64]
+  const f16* q = nullptr;  int ldq = 0;  long long q_batch_stride = 0;   // element strides; head h at column h*64
+  const f16* k = nullptr;  int ldk = 0;  long long k_batch_stride = 0;
+  const f16* v = nullptr;  int ldv = 0;  long long v_batch_stride = 0;
+  f16* out = nullptr;      int ldo = 0;  long long o_batch_stride = 0;   // [B, Sq, H*64]
+  int out_lo_off = 0;                  // != 0: also store lo = f16(o - f16(o)) at column + out_lo_off (hi | lo rows)
   int B = 0, H = 0, Sq = 0, Sk = 0;
   float scale = 1.f;                   // emb_dim ** -0.5 (reference layers.py:20), NOT head_dim ** -0.5
   int causal = 0;                      // mask key j > query i
@@ -70,26 +74,31 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t s);
 int launch_attention_naive(const AttnParams& p, cudaStream_t s);
 
 // ---- UMMA probe (bring-up / regression check of descriptor encodings)
-int launch_umma_probe(const bf16* A, const bf16* Bm, float* D, int N, int b_mn_major, cudaStream_t s);
+int launch_umma_probe(const f16* A, const f16* Bm, float* D, int N, int b_mn_major, cudaStream_t s);
 
 // ---- elementwise / normalisation
+// split != 0: y_f16 rows are [hi (D) | lo (D)] (row stride 2D): the A operand of an a_split GEMM
 int launch_layernorm(const float* x, const float* gamma, const float* beta, int rows, int D, float eps, float* y_f32,
-                     bf16* y_bf16, cudaStream_t s);
+                     f16* y_f16, cudaStream_t s, int split = 0);
+int launch_f32_to_f16_split(const float* x, f16* y, size_t rows, int D, cudaStream_t s);   // y [rows, 2D] = [hi | lo]
 int launch_embed_pe(const int32_t* tokens, int ld_tok, const float* emb, const float* pe, int B, int L, int D,
                     int vocab, float* out, cudaStream_t s);
-int launch_f32_to_bf16(const float* x, bf16* y, size_t n, cudaStream_t s);
+int launch_f32_to_f16(const float* x, f16* y, size_t n, cudaStream_t s);
 
 // ---- conv front-end (reference model.py:168-171)
-// conv1: spectrum fp32 (B,1,F,T) -> y1 bf16 channels-last (B, T1, F1, 64)
-int launch_conv1(const float* spec, const float* w1 /*[9][64]*/, const float* b1, int B, int F, int T, bf16* y1,
-                 cudaStream_t s);
-// conv2: y1 -> z bf16 (B, T2, F2*64) with column order (f, c)
-// conv1 + conv2 in one kernel (the bf16 intermediate stays in shared memory); returns 1 if it does not fit -> use the
+// conv1: spectrum fp32 (B,1,F,T) -> y1 f16 channels-last (B, T1, F1, 64)
+// split != 0 (all three): activations travel as fp16 hi | lo pairs (x = hi + lo to 2^-22) and are multiplied twice on
+// the tensor cores: y1 gets a second plane of lo parts (B*T1*F1*64 elements further), z rows become
+// [hi (F2*64) | lo (F2*64)] (the A operand of the a_split _lin_in GEMM).
+int launch_conv1(const float* spec, const float* w1 /*[9][64]*/, const float* b1, int B, int F, int T, f16* y1,
+                 cudaStream_t s, int split = 0);
+// conv2: y1 -> z f16 (B, T2, F2*64) with column order (f, c)
+// conv1 + conv2 in one kernel (the f16 intermediate stays in shared memory); returns 1 if it does not fit -> use the
 // two kernels below.  w2frag: pack_conv2_fragments order.
-int launch_conv_fused(const float* spec, const float* w1, const float* b1, const bf16* w2frag, const float* b2, int B,
-                      int F, int T, bf16* z, cudaStream_t s);
-int launch_conv2(const bf16* y1, const bf16* w2 /*[64 co][9][64 ci]*/, const float* b2, int B, int F1, int T1,
-                 bf16* z, cudaStream_t s);
+int launch_conv_fused(const float* spec, const float* w1, const float* b1, const f16* w2frag, const float* b2, int B,
+                      int F, int T, f16* z, cudaStream_t s, int split = 0);
+int launch_conv2(const f16* y1, const f16* w2 /*[64 co][9][64 ci]*/, const float* b2, int B, int F1, int T1,
+                 f16* z, cudaStream_t s, int split = 0);
 
 // ---- power spectrogram front-end (reference dataset.py:34-35): audio (B, N) -> spec (B,1,n_fft/2+1,T), frames >= the
 // signal's frame count zero-filled
@@ -100,7 +109,7 @@ struct DecLinear {
   const float* x = nullptr;      // fp32 [B, K]
   int ldx = 0;
   const float* ln_gamma = nullptr, *ln_beta = nullptr;   // optional LayerNorm prologue over K (K == D)
-  const bf16* w = nullptr;       // bf16 [N_pad, K]
+  const f16* w = nullptr;       // f16 [N_pad, K]
   const float* bias = nullptr;   // [N] nullable
   int B = 0, N = 0, K = 0;
   int relu = 0;
@@ -108,8 +117,8 @@ struct DecLinear {
   int ldo = 0;
   const float* residual = nullptr;
   int ld_res = 0;
-  // QKV-append mode: columns [kv_col0, N) are also written as bf16 into the cache row of step t
-  bf16* kv_cache = nullptr;      // [B, kv_rows, N - kv_col0]
+  // QKV-append mode: columns [kv_col0, N) are also written as f16 into the cache row of step t
+  f16* kv_cache = nullptr;      // [B, kv_rows, N - kv_col0]
   int kv_col0 = 0, kv_rows = 0;
   const int32_t* step = nullptr; // device step counter (row index into the cache)
 };
@@ -117,7 +126,7 @@ int launch_dec_linear(const DecLinear& p, cudaStream_t s);
 
 struct DecAttn {
   const float* q = nullptr; int ldq = 0;          // fp32 [B, ldq], head h at col h*64
-  const bf16* k = nullptr;  const bf16* v = nullptr;
+  const f16* k = nullptr;  const f16* v = nullptr;
   int ldkv = 0; long long kv_batch_stride = 0;    // element strides
   int n_keys = 0;                                 // used when step == nullptr
   const int32_t* step = nullptr;                  // n_keys = *step + 1 (self attention over the cache)
@@ -143,48 +152,6 @@ int launch_dec_select_embed(const DecSelect& p, const float* emb, const float* p
 int launch_dec_embed(const int32_t* tokens, int ld_tok, const int32_t* step, const float* emb, const float* pe, int B,
                      int D, int vocab, float* h, cudaStream_t s);
 
-// ---- persistent cooperative greedy decoder (decode_persistent.cu): one launch for all L steps
-struct PersistentLayer {
-  const float *ln1_g, *ln1_b;
-  const bf16* w_qkv; const float* b_qkv;
-  const bf16* w_o; const float* b_o;
-  const float *ln2_g, *ln2_b;
-  const bf16* w_qc; const float* b_qc;
-  const bf16* w_oc; const float* b_oc;
-  const float *ln3_g, *ln3_b;
-  const bf16* w1; const float* b1;
-  const bf16* w2; const float* b2;
-};
-constexpr int PERSIST_MAX_LAYERS = 16;
-constexpr int PERSIST_MAX_TEAMS = 16;
-
-struct PersistentParams {
-  int B, D, H, FF, V, L, Tp, nd;
-  PersistentLayer layer[PERSIST_MAX_LAYERS];
-  const bf16* classifier; const float* emb; const float* pe;
-  bf16* cache;            // [nd][B][L][2D]
-  const bf16* ckv;        // [nd][B*Tp][2D]
-  float *h, *qkv, *ff;    // [B][D], [B][3D], [B][FF]
-  int32_t* tokens; int32_t* n_tokens; int32_t* finished; float* step_logits;
-  unsigned* barrier;      // [PERSIST_MAX_TEAMS][32] zeroed before launch (one counter per team, 128 B apart)
-  unsigned* done_count;   // [PERSIST_MAX_TEAMS][32] zeroed before launch (stop_at_eos early exit)
-  long long* timing;      // nullable: [gridDim][16] clock64 totals {A,bar,B,bar,C,bar,D,bar,E,bar, B sub-phases x6}
-  int eos, pad, stop_at_eos, kmax, sc_ld;
-  const float* dec_small; // [nd][small_floats] packed biases + LayerNorm params per layer (streaming decoder)
-  int small_floats;
-  int teams;              // independent CTA groups, each with its own batch slice and barrier (>= 1)
-  float scale;
-};
-
-size_t persistent_smem_bytes(int D, int FF, int V);
-bool persistent_supported(int D, int FF, int V, int H, int nd);
-int launch_dec_persistent(PersistentParams& p, cudaStream_t s);
-// streaming decoder (decode_stream.cu): one CTA per utterance, weights + K/V streamed through a TMA ring, no barriers
-bool stream_supported(int D, int FF, int V, int H, int nd);
-int stream_small_floats(int D, int FF);
-int launch_dec_stream(PersistentParams& p, cudaStream_t s);
-
-
 // ---- cluster greedy decoder (decode_cluster.cu): one thread-block cluster (num_heads CTAs, one head each) per group
 // of <= 8 utterances; weights streamed from a fragment-major packed image (AsrWeights.dec_image)
 struct ClusterMat { int MT, KB, KBS, KG; };   // m-tiles (16 rows), k-blocks (32 cols), k-blocks per ring stage, k-groups
@@ -202,8 +169,8 @@ struct ClusterParams {
   size_t off_small, off_qkv, off_wo, off_wqc, off_woc, off_w1, off_w2, off_cls;
   uint32_t small_bytes;
   const float* emb; const float* pe; const float* h0;   // h0: fp32 [B][D] embedding + PE of the first token
-  bf16* cache;            // [nd][B][H][K rows | V rows][L][64]  (this kernel's own layout of the self-attention cache)
-  const bf16* ckv;        // [nd][B*Tp][2D]
+  f16* cache;            // [nd][B][H][K rows | V rows][L][64]  (this kernel's own layout of the self-attention cache)
+  const f16* ckv;        // [nd][B*Tp][2D]
   const int32_t* enc_lens;   // nullable [B]: valid encoder frames per utterance (cross-attention key-padding mask)
   int32_t* tokens; int32_t* n_tokens; float* step_logits;
   int eos, pad, stop_at_eos;

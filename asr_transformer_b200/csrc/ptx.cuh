@@ -2,7 +2,7 @@
 // Everything here is hand-written for Blackwell; there is no fallback for other architectures.
 #pragma once
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -106,8 +106,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 operands, fp32 accumulate. One thread issues.
-__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+// D[tmem] (+)= A[smem desc] * B[smem desc], f16 operands, fp32 accumulate. One thread issues.
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -139,7 +139,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ---------------------------------------------------------------- UMMA descriptors
 // Shared-memory matrix descriptor (sm_100 version field = 1), SWIZZLE_128B.
-//  K-major operand : rows of 64 bf16 (128 B), 8-row swizzle atoms of 1024 B; SBO = stride between atoms.
+//  K-major operand : rows of 64 f16 (128 B), 8-row swizzle atoms of 1024 B; SBO = stride between atoms.
 //  MN-major operand: 128 B of contiguous MN elements per K index, 8 K-rows per 1024 B atom;
 //                    SBO = stride between 8-K groups, LBO = stride between 64-element MN atoms.
 __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -151,20 +151,30 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
   d |= 2ull << 61;   // LayoutType::SWIZZLE_128B
   return d;
 }
-// Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4)                       // D format F32
-         | (1u << 7)                     // A format BF16
-         | (1u << 10)                    // B format BF16
+// Instruction descriptor for kind::f16 with fp16 A/B (format field 0; 1 would be bf16) and fp32 D.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4)                       // D format F32; A format (bits 7-9) = 0 and B format (bits 10-12) = 0: F16
          | (uint32_t(a_mn_major) << 15)  // A major (0 = K)
          | (uint32_t(b_mn_major) << 16)  // B major (0 = K)
          | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- small math / packing helpers
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+// two fp32 -> packed fp16 pair (lo in the low half), round to nearest, saturating to +-65504 instead of +-inf
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t v;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(v) : "f"(hi), "f"(lo));
+  return v;
+}
+__device__ __forceinline__ __half f16_sat(float x) {
+  unsigned short v;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(v) : "f"(x));
+  return __ushort_as_half(v);
+}
+// lo halves of a hi | lo split: f16(a - hi.lo), f16(b - hi.hi) for the packed pair hi = pack_f16x2(a, b)
+__device__ __forceinline__ uint32_t f16x2_residual(float a, float b, uint32_t hi) {
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  return pack_f16x2(a - h.x, b - h.y);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

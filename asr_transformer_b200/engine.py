@@ -1,12 +1,13 @@
 """Weight packing and the per-model engine that owns the C-ABI handle.
 
 Packing happens once per weight version:
-  * per-head ``_q/_k/_v`` Linear(D, 64) -> one bf16 ``[3D, D]`` matrix (rows: q heads | k heads | v heads),
-  * ``input_layer.0.weight`` -> fp32 ``[9 taps, 64]``; ``input_layer.2.weight`` -> bf16 mma-fragment order,
+  * per-head ``_q/_k/_v`` Linear(D, 64) -> one fp16 ``[3D, D]`` matrix (rows: q heads | k heads | v heads),
+  * ``input_layer.0.weight`` -> fp32 ``[9 taps, 64]``; ``input_layer.2.weight`` -> fp16 mma-fragment order,
   * ``encoder._lin_in.weight`` columns permuted from the reference's ``c*F'+f`` (model.py:43-45) to ``f*64+c``,
     which is the order the conv kernel writes, so no transpose/contiguous pass exists at run time,
   * ``decoder._classifier.weight`` zero-padded to a multiple of 64 rows.
-GEMM weights are stored as bf16 (lossless when the checkpoint is bf16-representable, as in the parity tests).
+GEMM weights are stored as fp16 (lossless when the checkpoint is bf16-representable, as in the parity tests: fp16 has
+three more mantissa bits; only magnitudes below 2^-14 round, by at most 2^-25).
 """
 from __future__ import annotations
 
@@ -23,8 +24,8 @@ def conv_len(n: int) -> int:
     return (n - 3) // 2 + 1
 
 
-def _bf16(t: torch.Tensor) -> torch.Tensor:
-    return t.detach().to(torch.bfloat16).contiguous()
+def _f16(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float16).contiguous()
 
 
 def _f32(t: torch.Tensor) -> torch.Tensor:
@@ -40,13 +41,13 @@ def pack_mha(mha: nn.Module) -> dict:
     bq = torch.cat([h._q.bias for h in heads], 0)
     bk = torch.cat([h._k.bias for h in heads], 0)
     bv = torch.cat([h._v.bias for h in heads], 0)
-    return {"w_qkv": _bf16(torch.cat([wq, wk, wv], 0)), "b_qkv": _f32(torch.cat([bq, bk, bv], 0)),
-            "w_out": _bf16(mha._out_linear.weight), "b_out": _f32(mha._out_linear.bias)}
+    return {"w_qkv": _f16(torch.cat([wq, wk, wv], 0)), "b_qkv": _f32(torch.cat([bq, bk, bv], 0)),
+            "w_out": _f16(mha._out_linear.weight), "b_out": _f32(mha._out_linear.bias)}
 
 
 def pack_ffn(ff: nn.Module) -> dict:
-    return {"w1": _bf16(ff.squeeze.weight), "b1": _f32(ff.squeeze.bias),
-            "w2": _bf16(ff.unsqueeze.weight), "b2": _f32(ff.unsqueeze.bias)}
+    return {"w1": _f16(ff.squeeze.weight), "b1": _f32(ff.squeeze.bias),
+            "w2": _f16(ff.unsqueeze.weight), "b2": _f32(ff.unsqueeze.bias)}
 
 
 def pack_norm(ln: nn.Module) -> dict:
@@ -59,46 +60,29 @@ def pack_conv1(w: torch.Tensor) -> torch.Tensor:
 
 
 def pack_conv2_fragments(w: torch.Tensor) -> torch.Tensor:
-    """(co=64, ci=64, kh, kw) -> bf16 [36 k-steps][8 n-tiles][32 lanes][4] in mma.m16n8k16 B-fragment order.
+    """(co=64, ci=64, kh, kw) -> fp16 [36 k-steps][8 n-tiles][32 lanes][4] in mma.m16n8k16 B-fragment order.
 
     k-step ks = (tap*2 + half)*2 + sub covers channels half*32 + c*8 + sub*4 + {0..3} for lane (g, c) = divmod(lane, 4)
     and output channel co = nt*8 + g (see conv2_kernel in csrc/simple_ops.cu)."""
     taps = w.detach().permute(2, 3, 0, 1).reshape(9, 64, 64)          # [tap, co, ci]
     t = taps.reshape(9, 8, 8, 2, 4, 2, 4)                              # tap, nt, g, half, c, sub, j
     t = t.permute(0, 3, 5, 1, 2, 4, 6)                                 # tap, half, sub, nt, g, c, j
-    return _bf16(t.reshape(36, 8, 32, 4))
+    return _f16(t.reshape(36, 8, 32, 4))
 
 
 def pack_lin_in(w: torch.Tensor) -> torch.Tensor:
     """(D, 64*F') columns c*F'+f -> f*64+c."""
     D, K = w.shape
     Fp = K // 64
-    return _bf16(w.detach().reshape(D, 64, Fp).permute(0, 2, 1).reshape(D, K))
+    return _f16(w.detach().reshape(D, 64, Fp).permute(0, 2, 1).reshape(D, K))
 
 
 def pack_classifier(w: torch.Tensor) -> torch.Tensor:
     V, D = w.shape
     vpad = (V + 63) // 64 * 64
-    out = torch.zeros(vpad, D, dtype=torch.bfloat16, device=w.device)
-    out[:V] = w.detach().to(torch.bfloat16)
+    out = torch.zeros(vpad, D, dtype=torch.float16, device=w.device)
+    out[:V] = w.detach().to(torch.float16)
     return out
-
-
-def pack_dec_small(decoder: nn.Module) -> torch.Tensor:
-    """Per decoder layer one contiguous fp32 block (padded to 256 floats) with every bias and LayerNorm parameter, in
-    the order the streaming decoder consumes them: b_qkv(3D) | b_out(D) | cross b_q(D) | cross b_out(D) | b1(FF) |
-    b2(D) | norm1 g,b | norm2 g,b | norm3 g,b."""
-    rows = []
-    for layer in decoder._layers:
-        sa, ca, ff = pack_mha(layer._mask_attention), pack_mha(layer._cross_attention), layer._feedforward
-        D = sa["b_out"].numel()
-        parts = [sa["b_qkv"], sa["b_out"], ca["b_qkv"][:D], ca["b_out"], _f32(ff.squeeze.bias), _f32(ff.unsqueeze.bias)]
-        for ln in (layer._norm1, layer._norm2, layer._norm3):
-            parts += [_f32(ln.weight), _f32(ln.bias)]
-        v = torch.cat([p.reshape(-1) for p in parts])
-        pad = (-v.numel()) % 256
-        rows.append(torch.cat([v, v.new_zeros(pad)]))
-    return torch.stack(rows).contiguous()
 
 
 def dec_image_layout(D: int, H: int, FF: int, V: int, nd: int) -> Optional[dict]:
@@ -127,7 +111,7 @@ def dec_image_layout(D: int, H: int, FF: int, V: int, nd: int) -> Optional[dict]
 
 
 def pack_mma_a(w: torch.Tensor) -> torch.Tensor:
-    """bf16 [R, K] (R % 16 == 0, K % 32 == 0) -> flat bf16 in the cluster decoder's fragment-major order
+    """fp16 [R, K] (R % 16 == 0, K % 32 == 0) -> flat fp16 in the cluster decoder's fragment-major order
     [k-block kb (32 cols)][m-tile mt (16 rows)][k-tile s (2)][g (8)][tg (4)][8], the 8 elements being the
     mma.m16n8k16 A fragment {a0, a1, a2, a3} of lane (g, tg): with r = 16 mt + g and c = 32 kb + 8 tg + 4 s they are
     w[r, c:c+2], w[r+8, c:c+2], w[r, c+2:c+4], w[r+8, c+2:c+4] - one LDS.128 per lane feeds one MMA directly."""
@@ -155,8 +139,8 @@ def pack_dec_image(decoder: nn.Module) -> Optional[torch.Tensor]:
         return None
     FFS, VS = lay["FFS"], lay["VS"]
     dev = decoder._embedding.weight.device
-    cls = torch.zeros(H * VS, D, dtype=torch.bfloat16, device=dev)
-    cls[:V] = decoder._classifier.weight.detach().to(torch.bfloat16)
+    cls = torch.zeros(H * VS, D, dtype=torch.float16, device=dev)
+    cls[:V] = decoder._classifier.weight.detach().to(torch.float16)
 
     def u8(t: torch.Tensor) -> torch.Tensor:
         return t.contiguous().view(torch.uint8).reshape(-1)
@@ -307,9 +291,6 @@ class Engine:
             keep.append(arr)
             w.dec_layers = arr
             if len(decoder._layers):
-                small = pack_dec_small(decoder)
-                keep.append(small)
-                w.dec_small = small.data_ptr()
                 image = pack_dec_image(decoder)
                 if image is not None:
                     keep.append(image)
@@ -351,12 +332,12 @@ class Engine:
                                       _l.ptr(out), _l.stream()), "asr_encode")
         return out
 
-    def encoder_forward(self, z_bf16: torch.Tensor, enc_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
-        B, Tp, _ = z_bf16.shape
-        out = torch.empty(B, Tp, self.cfg.embedding_dim, dtype=torch.float32, device=z_bf16.device)
+    def encoder_forward(self, z_f16: torch.Tensor, enc_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
+        B, Tp, _ = z_f16.shape
+        out = torch.empty(B, Tp, self.cfg.embedding_dim, dtype=torch.float32, device=z_f16.device)
         ws = self._ws(B, 4 * Tp + 3, self.cfg.decoder_seq_len)
-        lens = None if enc_lens is None else enc_lens.to(device=z_bf16.device, dtype=torch.int32).contiguous()
-        _l.check(_l.load().asr_encoder_forward(self.handle, _l.ptr(z_bf16), B, Tp, _l.ptr(lens), _l.ptr(ws),
+        lens = None if enc_lens is None else enc_lens.to(device=z_f16.device, dtype=torch.int32).contiguous()
+        _l.check(_l.load().asr_encoder_forward(self.handle, _l.ptr(z_f16), B, Tp, _l.ptr(lens), _l.ptr(ws),
                                                ws.numel(), _l.ptr(out), _l.stream()), "asr_encoder_forward")
         return out
 

@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from . import lib as _l
-from .engine import pack_ffn, pack_mha, weights_version, _bf16, _f32
+from .engine import pack_ffn, pack_mha, weights_version, _f16, _f32
 
 
 def _require_eval(m: nn.Module) -> None:
@@ -54,26 +54,26 @@ class MHAHead(nn.Module):
         B, Sq, D = x.shape
         Sk = src.shape[1]
         dev = x.device
-        w = _bf16(torch.cat([self._q.weight, self._k.weight, self._v.weight], 0))       # [192, D]
+        w = _f16(torch.cat([self._q.weight, self._k.weight, self._v.weight], 0))       # [192, D]
         b = _f32(torch.cat([self._q.bias, self._k.bias, self._v.bias], 0))
-        xb = torch.empty(B * Sq, D, dtype=torch.bfloat16, device=dev)
+        xb = torch.empty(B * Sq, D, dtype=torch.float16, device=dev)
         xf = x.to(torch.float32).contiguous()
-        _l.check(L.asr_f32_to_bf16(_l.ptr(xf), _l.ptr(xb), xb.numel(), _l.stream()))
-        q = torch.empty(B * Sq, 64, dtype=torch.bfloat16, device=dev)
-        kv = torch.empty(B * Sk, 128, dtype=torch.bfloat16, device=dev)
-        _l.check(L.asr_gemm_bf16(_l.ptr(xb), _l.ptr(w), _l.ptr(b), None, None, 1, B * Sq, 64, D, 0, None, _l.ptr(q), 0,
+        _l.check(L.asr_f32_to_f16(_l.ptr(xf), _l.ptr(xb), xb.numel(), _l.stream()))
+        q = torch.empty(B * Sq, 64, dtype=torch.float16, device=dev)
+        kv = torch.empty(B * Sk, 128, dtype=torch.float16, device=dev)
+        _l.check(L.asr_gemm_f16(_l.ptr(xb), _l.ptr(w), _l.ptr(b), None, None, 1, B * Sq, 64, D, 0, None, _l.ptr(q), 0,
                                  _l.stream()))
         if enc_x is None:
             sb = xb
         else:
             sf = src.to(torch.float32).contiguous()
-            sb = torch.empty(B * Sk, D, dtype=torch.bfloat16, device=dev)
-            _l.check(L.asr_f32_to_bf16(_l.ptr(sf), _l.ptr(sb), sb.numel(), _l.stream()))
+            sb = torch.empty(B * Sk, D, dtype=torch.float16, device=dev)
+            _l.check(L.asr_f32_to_f16(_l.ptr(sf), _l.ptr(sb), sb.numel(), _l.stream()))
         wkv, bkv = w[64:].contiguous(), b[64:].contiguous()
-        _l.check(L.asr_gemm_bf16(_l.ptr(sb), _l.ptr(wkv), _l.ptr(bkv), None, None, 1, B * Sk, 128, D, 0, None,
+        _l.check(L.asr_gemm_f16(_l.ptr(sb), _l.ptr(wkv), _l.ptr(bkv), None, None, 1, B * Sk, 128, D, 0, None,
                                  _l.ptr(kv), 0, _l.stream()))
         dense, mask_b = _dense_mask(attention_mask, B, Sq, Sk, dev)
-        out = torch.empty(B, Sq, 64, dtype=torch.bfloat16, device=dev)
+        out = torch.empty(B, Sq, 64, dtype=torch.float16, device=dev)
         _l.check(L.asr_attention(_l.ptr(q), 64, Sq * 64, _l.ptr(kv), 128, Sk * 128, kv.data_ptr() + 128, 128, Sk * 128,
                                  _l.ptr(out), 64, Sq * 64, B, 1, Sq, Sk, float(self._emb_dim) ** -0.5, 0, None, None,
                                  None, _l.ptr(dense), mask_b, 0, _l.stream()), "asr_attention")

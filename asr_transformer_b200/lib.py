@@ -50,11 +50,11 @@ class AsrWeights(C.Structure):
                 ("enc_layers", C.POINTER(AsrEncoderLayerWeights)), ("enc_norm_out", AsrNormWeights),
                 ("embedding", c_void_p), ("dec_pe", c_void_p),
                 ("dec_layers", C.POINTER(AsrDecoderLayerWeights)), ("dec_norm", AsrNormWeights),
-                ("classifier_w", c_void_p), ("dec_small", c_void_p), ("dec_image", c_void_p),
+                ("classifier_w", c_void_p), ("dec_image", c_void_p),
                 ("dec_image_bytes", c_size_t)]
 
 
-# name -> (restype, argtypes); mirrors include/asr_b200.h one to one (tests/test_abi.py checks the symbol list)
+# name -> (restype, argtypes); mirrors include/asr_b200.h one to one (tests/test_host.py checks the symbol list against the header)
 _SIGNATURES = {
     "asr_last_error": (C.c_char_p, []),
     "asr_version": (c_int, []),
@@ -78,11 +78,14 @@ _SIGNATURES = {
     "asr_decode_profile": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),
     "asr_launch_count": (C.c_ulonglong, []),
+    "asr_split_operands": (c_int, []),
     "asr_decoder_image_bytes": (c_size_t, [C.POINTER(AsrConfig)]),
     "asr_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "asr_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
-    "asr_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+    "asr_f32_to_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "asr_gemm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                               c_void_p, c_void_p, c_int, c_void_p]),
+    "asr_gemm_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                               c_size_t, c_void_p]),
     "asr_attention": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_int, c_longlong,
                               c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

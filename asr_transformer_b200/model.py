@@ -50,9 +50,13 @@ class Encoder(nn.Module):
         _require_eval(self)
         eng = self._engine.sync(self, encoder=self)
         B, Cc, Fp, Tp = x.shape
-        # NCHW -> the kernel's (B, T', f*64 + c) bf16 feature layout (replaces view/transpose/contiguous, model.py:43-45)
-        z = x.permute(0, 3, 2, 1).reshape(B, Tp, Fp * Cc).to(torch.bfloat16).contiguous()
-        return eng.encoder_forward(z)
+        # NCHW -> the kernel's (B, T', f*64 + c) fp16 feature layout (replaces view/transpose/contiguous, model.py:43-45);
+        # rows are [hi | lo] pairs when the library runs with split operands (include/asr_b200.h: asr_split_operands)
+        zf = x.permute(0, 3, 2, 1).reshape(B, Tp, Fp * Cc).to(torch.float32)
+        z = zf.clamp(-65504.0, 65504.0).to(torch.float16)
+        if _l.load().asr_split_operands():
+            z = torch.cat([z, (zf - z.float()).to(torch.float16)], -1)
+        return eng.encoder_forward(z.contiguous())
 
 
 class DecoderLayer(nn.Module):
@@ -135,12 +139,14 @@ class ConvFrontEnd(nn.Sequential):
         dev = spectrum.device
         w1, b1 = pack_conv1(self[0].weight), _f32(self[0].bias)
         w2, b2 = pack_conv2_fragments(self[2].weight), _f32(self[2].bias)
-        z = torch.empty(B, Tp, Fp * 64, dtype=torch.bfloat16, device=dev)
+        sp = 2 if L.asr_split_operands() else 1
+        z = torch.empty(B, Tp, sp * Fp * 64, dtype=torch.float16, device=dev)
         ws = _l.workspace(L.asr_conv_workspace_bytes(B, F, T), dev, "op")
         _l.check(L.asr_conv_frontend(_l.ptr(spectrum), _l.ptr(w1), _l.ptr(b1), _l.ptr(w2), _l.ptr(b2), B, F, T,
                                      _l.ptr(ws), ws.numel(), _l.ptr(z), _l.stream()), "asr_conv_frontend")
-        # kernel layout (B, T', f*64+c) -> the reference's NCHW (B, 64, F', T')
-        return z.view(B, Tp, Fp, 64).permute(0, 3, 2, 1).float()
+        # kernel layout (B, T', f*64+c) [hi | lo halves] -> the reference's NCHW (B, 64, F', T')
+        zf = z[..., :Fp * 64].float() + (z[..., Fp * 64:].float() if sp == 2 else 0.0)
+        return zf.view(B, Tp, Fp, 64).permute(0, 3, 2, 1).contiguous()
 
 
 class Transformer(nn.Module):

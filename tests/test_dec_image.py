@@ -66,7 +66,7 @@ def emulate_mm_stream(image, R, K, x):
 @pytest.mark.parametrize("R,K", [(192, 128), (64, 256), (32, 64), (128, 32)])
 def test_fragment_order_matches_kernel_indexing(R, K):
     g = torch.Generator().manual_seed(R * 1000 + K)
-    w = torch.randn(R, K, generator=g).to(torch.bfloat16)
+    w = torch.randn(R, K, generator=g).to(torch.float16)
     x = torch.randn(8, K, generator=g).double().numpy()
     img = E.pack_mma_a(w).double().numpy()
     got = emulate_mm_stream(img, R, K, x)
@@ -92,7 +92,7 @@ def test_image_layout_and_contents(name):
 
     def mat(r, l, key, R, K):
         off = r * lay["rank_bytes"] + (l * lay["layer_bytes"] + lay["off_" + key] if l >= 0 else lay["off_cls"])
-        return unpack_mma_a(img[off:off + R * K * 2].view(torch.bfloat16), R, K)
+        return unpack_mma_a(img[off:off + R * K * 2].view(torch.float16), R, K)
 
     for r in (0, H - 1):
         for l in (0, nd - 1):
@@ -121,8 +121,8 @@ def test_image_layout_and_contents(name):
                 assert torch.equal(nxt[D:], dec._layers[l + 1]._norm1.bias.detach())
             else:
                 assert not nxt.any()
-        cls = torch.zeros(H * VS, D, dtype=torch.bfloat16)
-        cls[:V] = dec._classifier.weight.detach().to(torch.bfloat16)
+        cls = torch.zeros(H * VS, D, dtype=torch.float16)
+        cls[:V] = dec._classifier.weight.detach().to(torch.float16)
         assert torch.equal(mat(r, -1, "cls", VS, D), cls[r * VS:(r + 1) * VS])
 
 

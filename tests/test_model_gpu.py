@@ -43,13 +43,16 @@ def test_forward_logits_T0(t0):
 
 
 def check_tokens(ref_tokens, ref_logits, got_tokens, min_frac=0.99):
+    """The north-star bar: greedy tokens identical on >= 99 % of the utterances, every divergence a proven argmax
+    near-tie (fp32 reference top1 - top2 margin < TAU at the first differing step)."""
     r = O.compare_tokens(ref_tokens, ref_logits, got_tokens, TAU)
     assert not r["hard"], f"token divergence not explained by an argmax near-tie: {r['hard']}"
     frac = r["identical"] / r["utterances"]
+    assert frac >= min_frac, f"only {r['identical']}/{r['utterances']} utterances token-identical (< {min_frac}): {r}"
     return r, frac
 
 
-@pytest.mark.parametrize("mode", ["cluster", "persistent", "stream", "graph", "eager"])
+@pytest.mark.parametrize("mode", ["cluster", "graph", "eager"])
 def test_greedy_tokens_T0(t0, mode, monkeypatch):
     """All three launch modes of asr_decode_greedy (ASR_B200_DECODE) against the reference's tokens and logits."""
     monkeypatch.setenv("ASR_B200_DECODE", mode)
@@ -106,40 +109,6 @@ def test_batch_invariance_T0(t0):
     assert torch.equal(t3[:cfg.batch], full) and torch.equal(t3[2 * cfg.batch:], full)
 
 
-def test_persistent_matches_per_kernel_step_C2(monkeypatch):
-    """The persistent cooperative kernel and the per-kernel (graph) step are two schedules of the same arithmetic."""
-    cfg = O.CONFIGS["C2"]
-    m = build_model(cfg, DEV)
-    spec = O.structured_spectrum(64, cfg.frames, cfg.input_dim, seed=21).to(DEV)
-    monkeypatch.setenv("ASR_B200_DECODE", "graph")
-    tg, _, lg = m.greedy_decode(spec, return_logits=True)
-    monkeypatch.setenv("ASR_B200_DECODE", "persistent")
-    tp, _, lp = m.greedy_decode(spec, return_logits=True)
-    r = O.compare_tokens(tg, lg.cpu(), tp, TAU)
-    assert not r["hard"] and r["identical"] >= 62, r
-    same = [b for b in range(64) if torch.equal(tg[b], tp[b])]
-    assert_close(lp[same], lg[same], 5e-3, 2e-4, "persistent vs graph step logits")   # bf16 cache roundings may flip
-
-
-def test_stream_matches_per_kernel_step_C2(monkeypatch):
-    """The streaming kernel (one CTA per utterance) against the per-kernel (graph) step, incl. stop_at_eos."""
-    cfg = O.CONFIGS["C2"]
-    m = build_model(cfg, DEV)
-    spec = O.structured_spectrum(40, cfg.frames, cfg.input_dim, seed=22).to(DEV)
-    monkeypatch.setenv("ASR_B200_DECODE", "graph")
-    tg, ng, lg = m.greedy_decode(spec, return_logits=True)
-    sg, nsg = m.greedy_decode(spec, stop_at_eos=True)
-    monkeypatch.setenv("ASR_B200_DECODE", "stream")
-    ts, ns, ls = m.greedy_decode(spec, return_logits=True)
-    ss, nss = m.greedy_decode(spec, stop_at_eos=True)
-    r = O.compare_tokens(tg, lg.cpu(), ts, TAU)
-    assert not r["hard"] and r["identical"] >= 37, r
-    same = [b for b in range(40) if torch.equal(tg[b], ts[b])]
-    assert_close(ls[same], lg[same], 5e-3, 2e-4, "stream vs graph step logits")
-    for b in same:
-        assert int(nss[b]) == int(nsg[b]) and torch.equal(ss[b], sg[b])
-
-
 @pytest.mark.parametrize("batch,gu", [(5, ""), (64, ""), (70, ""), (128, ""), (9, "8"), (200, "")])
 def test_cluster_matches_per_kernel_step_C2(batch, gu, monkeypatch):
     """The cluster kernel (head-parallel CTAs, DSMEM all-reduces) against the per-kernel (graph) step for utterance
@@ -157,7 +126,7 @@ def test_cluster_matches_per_kernel_step_C2(batch, gu, monkeypatch):
     sc, nsc = m.greedy_decode(spec, max_len=L, stop_at_eos=True)
     torch.cuda.synchronize()
     r = O.compare_tokens(tg, lg.cpu(), tc, TAU)
-    assert not r["hard"] and r["identical"] >= 0.9 * batch, r
+    assert not r["hard"] and r["identical"] >= batch - max(1, batch // 50), r    # two fp32 summation orders of one arithmetic
     same = [b for b in range(batch) if torch.equal(tg[b], tc[b])]
     assert_close(lc[same], lg[same], 5e-3, 2e-4, "cluster vs graph step logits")
     for b in same:
@@ -217,14 +186,13 @@ def test_reference_golden_C1():
     logits = m(spec, fx["text"].to(DEV), fx["mask"].to(DEV))
     assert_close(logits, fx["forward_logits"], what="C1 forward logits")
     tokens, n_tok, step_logits = m.greedy_decode(spec, return_logits=True)
-    r, frac = check_tokens(fx["tokens"], fx["step_logits"], tokens)
+    r, frac = check_tokens(fx["tokens"], fx["step_logits"], tokens, min_frac=1.0)   # 8/8 against the reference's tokens
     print("C1 greedy:", r)
-    assert frac >= 0.99 or r["utterances"] - r["identical"] <= 1, r
     ident = [b for b in range(cfg.batch) if torch.equal(tokens[b].cpu().long(), fx["tokens"][b])]
     assert_close(step_logits[ident], fx["step_logits"][ident], what="C1 step logits")
 
 
-@pytest.mark.parametrize("name,batch", [("C2", 64), ("C2", 128), ("C2", 256), ("C5", 8)])
+@pytest.mark.parametrize("name,batch", [("C2", 64), ("C2", 128), ("C2", 256), ("C3", 64), ("C5", 8)])
 def test_greedy_vs_oracle_baseline_sizes(name, batch):
     """BASELINE sizes against the CPU oracle (KV-cached restatement, pinned to the reference by the goldens)."""
     cfg = O.CONFIGS[name]
@@ -236,16 +204,16 @@ def test_greedy_vs_oracle_baseline_sizes(name, batch):
     tok_ref, logits_ref = O.greedy_kv_cached(sd, enc_ref, cfg)
     enc = m.encode(spec.to(DEV))
     assert_close(enc, enc_ref, what=f"{name} enc_out")
-    tokens, _ = m.greedy_decode(spec.to(DEV))
-    r, frac = check_tokens(tok_ref, logits_ref, tokens)
-    print(f"{name} greedy:", {k: r[k] for k in ("utterances", "identical", "near_tie", "distinct_rows")})
+    tokens, _, step_logits = m.greedy_decode(spec.to(DEV), return_logits=True)
+    # the north-star bar (>= 99 % identical utterances, every divergence a proven near-tie) is enforced by check_tokens
+    r, frac = check_tokens(tok_ref, logits_ref, tokens, min_frac=0.99)
+    print(f"{name}@{batch} greedy:", {k: r[k] for k in ("utterances", "identical", "near_tie", "distinct_rows")})
     assert r["distinct_rows"] >= 0.85 * batch      # (the synthetic generator: 229 distinct reference rows of 256)
-    # Every divergence is already proven to be a near-tie (margin < TAU) by check_tokens.  At random init a 128-step
-    # decode of 64 utterances makes 8192 argmax decisions, a handful of which have fp32-reference margins below 2e-4,
-    # i.e. below the reference's own accumulation-order noise; those are coin flips for ANY fp32 implementation.
-    # (observed: <= 1.3e-3 over 24.6 k decisions, against a logit tolerance of 3e-2 and tau = 2e-2)
-    assert all(m < 5e-3 for _, _, m in r["near_tie"]), r
-    assert frac >= 0.9, r
+    assert all(mg < 1e-3 for _, _, mg in r["near_tie"]), r      # what flips is far below the 2e-2 near-tie threshold
+    ident = [b for b in range(batch) if torch.equal(tokens[b].cpu().long(), tok_ref[b])]
+    d = (step_logits[ident].cpu() - logits_ref[ident]).abs()
+    print(f"{name}@{batch} step logits of the identical utterances: max |d| {d.max():.2e}, mean |d| {d.mean():.2e}")
+    assert d.max() < 5e-3 and d.mean() < 2e-4
 
 
 def test_long_form_encoder_C4():
@@ -303,7 +271,7 @@ def test_coalesced_serving_C2_full_size():
     assert len(outs) == 5
     for (t_ref, n_ref, lg_ref), (tok, n) in zip(ref, outs):
         r = O.compare_tokens(t_ref.cpu(), lg_ref.cpu(), tok, TAU)
-        assert not r["hard"] and r["identical"] >= 0.9 * cfg.batch, r
+        assert not r["hard"] and r["identical"] >= cfg.batch - 1, r
     # the fifth batch is decoded alone (2 per cluster, like the reference call): bit-exact
     assert torch.equal(outs[4][0], ref[4][0].cpu()) and torch.equal(outs[4][1], ref[4][1].cpu())
     assert len({tuple(r) for r in outs[0][0].tolist()}) >= 0.9 * cfg.batch
@@ -311,7 +279,7 @@ def test_coalesced_serving_C2_full_size():
     outs2 = list(m.greedy_decode_batches([x.pin_memory() for x in xs[:2]], coalesce=2))
     for (t_ref, n_ref, lg_ref), (tok, n) in zip(ref, outs2):
         r = O.compare_tokens(t_ref.cpu(), lg_ref.cpu(), tok, TAU)
-        assert not r["hard"] and r["identical"] >= 0.9 * cfg.batch, r
+        assert not r["hard"] and r["identical"] >= cfg.batch - 1, r
 
 
 def test_pipelined_batches_with_lengths(t0):
@@ -393,4 +361,4 @@ def test_beam_search_C2_sizes():
     tok_ref, sc_ref = O.beam_search_kv_cached(sd, O.encode(sd, spec), cfg, 4, max_len=48)
     tok, sc = m.beam_search(spec.to(DEV), beam=4, max_len=48)
     frac, best = _check_beams(tok_ref, sc_ref, tok, sc, "C2 beam 4")
-    assert best >= 0.75 and frac >= 0.6, (frac, best)   # bf16 operands may swap near-equal hypotheses
+    assert best >= 0.75 and frac >= 0.6, (frac, best)   # near-equal hypotheses may swap places

@@ -32,8 +32,8 @@ def rnd(*shape, seed=0, scale=1.0, dtype=torch.float32):
 # ----------------------------------------------------------------------------------------------- tcgen05 probe
 @pytest.mark.parametrize("N", [32, 64, 128])
 def test_umma_probe_k_major(N):
-    a = rnd(128, 64, seed=1, dtype=torch.bfloat16)
-    b = rnd(N, 64, seed=2, dtype=torch.bfloat16)
+    a = rnd(128, 64, seed=1, dtype=torch.float16)
+    b = rnd(N, 64, seed=2, dtype=torch.float16)
     d = torch.zeros(128, N, device=DEV)
     L.check(lib().asr_umma_probe(L.ptr(a), L.ptr(b), L.ptr(d), N, 0, L.stream()))
     sync()
@@ -41,8 +41,8 @@ def test_umma_probe_k_major(N):
 
 
 def test_umma_probe_mn_major():
-    a = rnd(128, 64, seed=3, dtype=torch.bfloat16)
-    b = rnd(64, 64, seed=4, dtype=torch.bfloat16)       # [k, n], n contiguous (a V tile)
+    a = rnd(128, 64, seed=3, dtype=torch.float16)
+    b = rnd(64, 64, seed=4, dtype=torch.float16)       # [k, n], n contiguous (a V tile)
     d = torch.zeros(128, 64, device=DEV)
     L.check(lib().asr_umma_probe(L.ptr(a), L.ptr(b), L.ptr(d), 64, 1, L.stream()))
     sync()
@@ -55,12 +55,12 @@ def test_layernorm(rows, D):
     x = rnd(rows, D, seed=5, scale=3.0) + 0.7
     g, b = rnd(D, seed=6) * 0.2 + 1.0, rnd(D, seed=7) * 0.1
     y32 = torch.empty_like(x)
-    y16 = torch.empty(rows, D, dtype=torch.bfloat16, device=DEV)
+    y16 = torch.empty(rows, D, dtype=torch.float16, device=DEV)
     L.check(lib().asr_layernorm(L.ptr(x), L.ptr(g), L.ptr(b), rows, D, L.ptr(y32), L.ptr(y16), L.stream()))
     sync()
     ref = F.layer_norm(x, (D,), g, b, 1e-5)
     assert_close(y32, ref, TOL_FP32, TOL_FP32, "layernorm fp32")
-    assert torch.equal(y16, y32.to(torch.bfloat16))
+    assert torch.equal(y16, y32.to(torch.float16))
 
 
 def test_layernorm_rejects_bad_width():
@@ -73,8 +73,8 @@ def test_layernorm_rejects_bad_width():
 def run_gemm(x, w, bias, res, pe, period, relu, impl, N):
     M, K = x.shape
     y32 = torch.zeros(M, N, device=DEV)
-    y16 = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
-    L.check(lib().asr_gemm_bf16(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(res), L.ptr(pe), period, M, N, K, relu,
+    y16 = torch.zeros(M, N, dtype=torch.float16, device=DEV)
+    L.check(lib().asr_gemm_f16(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(res), L.ptr(pe), period, M, N, K, relu,
                                 L.ptr(y32), L.ptr(y16), impl, L.stream()), "gemm")
     sync()
     return y32, y16
@@ -84,10 +84,10 @@ def run_gemm(x, w, bias, res, pe, period, relu, impl, N):
                                    (777, 256, 1024), (2000, 256, 1216), (257, 250, 128), (15936, 768, 256),
                                    (5, 512, 512)])
 def test_gemm_tc_plain(M, N, K):
-    x = rnd(M, K, seed=8, dtype=torch.bfloat16)
+    x = rnd(M, K, seed=8, dtype=torch.float16)
     npad = (N + 63) // 64 * 64
-    w = torch.zeros(npad, K, dtype=torch.bfloat16, device=DEV)
-    w[:N] = rnd(N, K, seed=9, scale=K ** -0.5, dtype=torch.bfloat16)
+    w = torch.zeros(npad, K, dtype=torch.float16, device=DEV)
+    w[:N] = rnd(N, K, seed=9, scale=K ** -0.5, dtype=torch.float16)
     y32, y16 = run_gemm(x, w, None, None, None, 1, 0, 0, N)
     ref = x.float() @ w[:N].float().t()
     assert_close(y32, ref, 2e-3, 2e-4, f"gemm {M}x{N}x{K}")
@@ -99,8 +99,8 @@ def test_gemm_tc_plain(M, N, K):
 @pytest.mark.parametrize("relu,use_res,use_pe", [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 1)])
 def test_gemm_tc_epilogues(relu, use_res, use_pe):
     M, N, K, period = 498, 256, 256, 249
-    x = rnd(M, K, seed=10, dtype=torch.bfloat16)
-    w = rnd(N, K, seed=11, scale=K ** -0.5, dtype=torch.bfloat16)
+    x = rnd(M, K, seed=10, dtype=torch.float16)
+    w = rnd(N, K, seed=11, scale=K ** -0.5, dtype=torch.float16)
     bias = rnd(N, seed=12)
     res = rnd(M, N, seed=13) if use_res else None
     pe = rnd(period, N, seed=14) if use_pe else None
@@ -113,7 +113,31 @@ def test_gemm_tc_epilogues(relu, use_res, use_pe):
     if use_res:
         ref = ref + res
     assert_close(y32, ref, 2e-3, 2e-4, "gemm epilogue")
-    assert torch.equal(y16, y32.to(torch.bfloat16))
+    assert torch.equal(y16, y32.to(torch.float16))
+
+
+@pytest.mark.parametrize("M,N,K,relu", [(300, 256, 256, 0), (1000, 1024, 256, 1), (515, 256, 1024, 0), (77, 250, 1216, 0)])
+def test_gemm_split_is_fp32_accurate(M, N, K, relu):
+    """hi | lo split activations (the model path's operand format): the tensor-core product equals the fp64 product of
+    the fp32 activations to fp32 rounding, and the hi | lo output pair reassembles the fp32 result to 2^-21."""
+    x = rnd(M, K, seed=15, scale=2.0) + 0.3
+    npad = (N + 63) // 64 * 64
+    w = torch.zeros(npad, K, dtype=torch.float16, device=DEV)
+    w[:N] = rnd(N, K, seed=16, scale=K ** -0.5, dtype=torch.float16)
+    bias = rnd(N, seed=17)
+    y32 = torch.zeros(M, N, device=DEV)
+    y16 = torch.zeros(M, 2 * N, dtype=torch.float16, device=DEV) if N % 8 == 0 else None
+    ws = torch.empty(M * K * 4, dtype=torch.uint8, device=DEV)
+    L.check(lib().asr_gemm_split(L.ptr(x), L.ptr(w), L.ptr(bias), M, N, K, relu, L.ptr(y32), L.ptr(y16), L.ptr(ws),
+                                 ws.numel(), L.stream()), "gemm_split")
+    sync()
+    ref = x.double() @ w[:N].double().t() + bias.double()
+    if relu:
+        ref = ref.relu()
+    assert_close(y32, ref.float(), 2e-5 * K ** 0.5, 2e-6 * K ** 0.5, "split gemm (fp32-accurate)")
+    if y16 is not None:
+        back = y16[:, :N].float() + y16[:, N:].float()
+        assert_close(back, y32, 4e-6, 4e-7, "hi | lo output pair")
 
 
 # ----------------------------------------------------------------------------------------------- attention core
@@ -141,7 +165,7 @@ def attn_reference(q, k, v, scale, causal=False, k_lens=None, q_valid=None, k_va
 def run_attn(q, k, v, scale, impl=0, causal=0, k_lens=None, q_valid=None, k_valid=None, dense=None):
     B, Sq, H, _ = q.shape
     Sk = k.shape[1]
-    out = torch.full((B, Sq, H * 64), float("nan"), dtype=torch.bfloat16, device=DEV)
+    out = torch.full((B, Sq, H * 64), float("nan"), dtype=torch.float16, device=DEV)
     mask_b = 1 if dense is None else dense.shape[0]
     L.check(lib().asr_attention(L.ptr(q), H * 64, Sq * H * 64, L.ptr(k), H * 64, Sk * H * 64, L.ptr(v), H * 64,
                                 Sk * H * 64, L.ptr(out), H * 64, Sq * H * 64, B, H, Sq, Sk, scale, causal,
@@ -155,7 +179,7 @@ def run_attn(q, k, v, scale, impl=0, causal=0, k_lens=None, q_valid=None, k_vali
                                        (1, 8, 749, 749), (2, 2, 130, 1)])
 @pytest.mark.parametrize("impl", [0, 1])
 def test_attention_nomask(B, H, Sq, Sk, impl):
-    q, k, v = (rnd(B, S, H, 64, seed=20 + i, dtype=torch.bfloat16) for i, S in enumerate((Sq, Sk, Sk)))
+    q, k, v = (rnd(B, S, H, 64, seed=20 + i, dtype=torch.float16) for i, S in enumerate((Sq, Sk, Sk)))
     scale = (64 * H) ** -0.5          # emb_dim ** -0.5, reference layers.py:20
     out = run_attn(q, k, v, scale, impl)
     assert_close(out, attn_reference(q, k, v, scale), 2e-2, 2e-3, f"attention impl={impl}")
@@ -164,7 +188,7 @@ def test_attention_nomask(B, H, Sq, Sk, impl):
 @pytest.mark.parametrize("impl", [0, 1])
 def test_attention_masks(impl):
     B, H, S = 3, 2, 200
-    q, k, v = (rnd(B, S, H, 64, seed=30 + i, scale=2.0, dtype=torch.bfloat16) for i in range(3))
+    q, k, v = (rnd(B, S, H, 64, seed=30 + i, scale=2.0, dtype=torch.float16) for i in range(3))
     scale = 128 ** -0.5
     out = run_attn(q, k, v, scale, impl, causal=1)
     assert_close(out, attn_reference(q, k, v, scale, causal=True), 2e-2, 2e-3, "causal")
@@ -277,8 +301,8 @@ def test_embed_pe():
 def test_dec_linear_fp32_accurate(B, N, K, ln, relu, res):
     x = rnd(B, K, seed=50, scale=2.0) + 0.3
     npad = (N + 63) // 64 * 64
-    w = torch.zeros(npad, K, dtype=torch.bfloat16, device=DEV)
-    w[:N] = rnd(N, K, seed=51, scale=K ** -0.5, dtype=torch.bfloat16)
+    w = torch.zeros(npad, K, dtype=torch.float16, device=DEV)
+    w[:N] = rnd(N, K, seed=51, scale=K ** -0.5, dtype=torch.float16)
     bias = rnd(N, seed=52)
     g, b = (rnd(K, seed=53) * 0.2 + 1.0, rnd(K, seed=54) * 0.1) if ln else (None, None)
     resid = rnd(B, N, seed=55) if res else None
@@ -299,7 +323,7 @@ def test_dec_linear_fp32_accurate(B, N, K, ln, relu, res):
 def test_dec_attention(B, H, n):
     D = 64 * H
     q = rnd(B, D, seed=60)
-    kv = rnd(B, n, 2 * D, seed=61, dtype=torch.bfloat16)
+    kv = rnd(B, n, 2 * D, seed=61, dtype=torch.float16)
     out = torch.zeros(B, D, device=DEV)
     scale = D ** -0.5
     L.check(lib().asr_dec_attention(L.ptr(q), L.ptr(kv), kv.data_ptr() + 2 * D, 2 * D, n * 2 * D, n, B, H, scale,

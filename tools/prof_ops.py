@@ -44,17 +44,17 @@ def timeit(name, fn, flops=0.0, bytes_=0.0):
 
 
 def gemm(N, K, relu=0, res=False, pe=False, f32=False, b16=True, name=""):
-    x = rnd(M, K, dtype=torch.bfloat16)
-    w = rnd((N + 63) // 64 * 64, K, dtype=torch.bfloat16, scale=K ** -0.5)
+    x = rnd(M, K, dtype=torch.float16)
+    w = rnd((N + 63) // 64 * 64, K, dtype=torch.float16, scale=K ** -0.5)
     bias = rnd(N)
     r = rnd(M, N) if res else None
     p = rnd(Tp, N) if pe else None
     y32 = torch.empty(M, N, device=dev) if f32 else None
-    y16 = torch.empty(M, N, dtype=torch.bfloat16, device=dev) if b16 else None
+    y16 = torch.empty(M, N, dtype=torch.float16, device=dev) if b16 else None
     by = M * K * 2 + N * K * 2 + (M * N * 4 if res else 0) + (M * N * 4 if f32 else 0) + (M * N * 2 if b16 else 0)
 
     def fn():
-        L.check(lib.asr_gemm_bf16(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(r), L.ptr(p), Tp, M, N, K, relu, L.ptr(y32),
+        L.check(lib.asr_gemm_f16(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(r), L.ptr(p), Tp, M, N, K, relu, L.ptr(y32),
                                   L.ptr(y16), 0, L.stream()), "gemm")
     return timeit(f"gemm {name} M={M} N={N} K={K}", fn, 2.0 * M * N * K, by)
 
@@ -68,8 +68,8 @@ t_f1 = gemm(1024, 256, relu=1, name="ffn1+relu")
 t_f2 = gemm(256, 1024, res=True, f32=True, b16=False, name="ffn2+res")
 t_ckv = gemm(512, 256, name="cross kv")
 
-qkv = rnd(B, Tp, 3 * D, dtype=torch.bfloat16)
-out = torch.empty(B, Tp, D, dtype=torch.bfloat16, device=dev)
+qkv = rnd(B, Tp, 3 * D, dtype=torch.float16)
+out = torch.empty(B, Tp, D, dtype=torch.float16, device=dev)
 
 
 def attn():
@@ -91,7 +91,7 @@ def attn_ptr():
 t_attn = timeit(f"attention B={B} H={H} S={Tp}", attn_ptr, 4.0 * B * H * Tp * Tp * 64, B * Tp * 4 * D * 2)
 x = rnd(M, D)
 g, bt = rnd(D), rnd(D)
-y16 = torch.empty(M, D, dtype=torch.bfloat16, device=dev)
+y16 = torch.empty(M, D, dtype=torch.float16, device=dev)
 t_ln = timeit("layernorm -> bf16", lambda: L.check(lib.asr_layernorm(L.ptr(x), L.ptr(g), L.ptr(bt), M, D, None,
                                                                       L.ptr(y16), L.stream()), "ln"), 0, M * D * 6)
 
@@ -99,11 +99,11 @@ t_ln = timeit("layernorm -> bf16", lambda: L.check(lib.asr_layernorm(L.ptr(x), L
 F_, T_ = 80, 1000
 spec = rnd(B, 1, F_, T_)
 w1, b1 = rnd(9, 64), rnd(64)
-w2 = rnd(36, 8, 32, 4, dtype=torch.bfloat16)
+w2 = rnd(36, 8, 32, 4, dtype=torch.float16)
 b2 = rnd(64)
 nws = lib.asr_conv_workspace_bytes(B, F_, T_)
 ws = torch.empty(nws, dtype=torch.uint8, device=dev)
-z = torch.empty(B, Tp, 19 * 64, dtype=torch.bfloat16, device=dev)
+z = torch.empty(B, Tp, 19 * 64, dtype=torch.float16, device=dev)
 t_conv = timeit("conv front-end (conv1 + conv2)",
                 lambda: L.check(lib.asr_conv_frontend(L.ptr(spec), L.ptr(w1), L.ptr(b1), L.ptr(w2), L.ptr(b2), B, F_, T_,
                                                       L.ptr(ws), nws, L.ptr(z), L.stream()), "conv"),
