@@ -10,8 +10,14 @@ no collective on the compute path, one final all_gather of the token matrices.
 
 Prints ONE JSON line (rank 0).  `value` is device-timed (CUDA events) with inputs resident in HBM; `e2e` goes through
 the public API with pinned HOST buffers, H2D of the spectrogram and D2H of the transcripts inside the timed region.
-`--impl reference` times the reference's own CPU algorithm (the oracle's literal restatement of model.py:125-151:
-per-utterance, no KV cache; the reference is pure Python and cannot travel to the GPU box).
+`--impl reference` times the UNMODIFIED reference (`Transformer.evaluate`, imported from the git-ignored
+baseline/_ref/ that tools/install_ref.sh fills; kind "reference") on the host cores, one utterance per step; only when
+baseline/_ref is absent does it fall back to the oracle's literal restatement of model.py:125-151 (kind "port").
+
+Beside the headline (C2, weak scaling) the same run reports three short extra passes under their own keys: `c3_strong`
+(BASELINE config 3: paper-size model, global batch 256 split over the N GPUs), `c5_masks` (config 5: widened model,
+mixed-length batch with key-padding masks on, length-balanced over the ranks) and `cross_n_tokens` (every N decodes
+the same seed-1 global batch; SHA-256 of the gathered tokens against the N=1 value in tests/golden/).
 """
 from __future__ import annotations
 
@@ -46,8 +52,9 @@ def parse():
     ap.add_argument("--workload", default=WORKLOAD)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel / per-phase profiling pass")
-    ap.add_argument("--decode-mode", default="", choices=["", "cluster", "persistent", "stream", "graph", "eager"],
+    ap.add_argument("--decode-mode", default="", choices=["", "cluster", "graph", "eager"],
                     help="sets ASR_B200_DECODE (default: the library default, cluster)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c3_strong / c5_masks / cross_n_tokens passes")
     return ap.parse_args()
 
 
@@ -71,7 +78,7 @@ def workload_desc(cfg, batch, n_gpus):
                     "launch (%d utterances, up to 8 per CTA cluster); every step's batch is fully processed and returned "
                     "separately" % (coalesce_of(batch), coalesce_of(batch) * batch),
         "parallelism": f"dp{n_gpus}: utterance sharding, one process per GPU, no collective on the compute path, "
-                       "final all_gather of token ids",
+                       "every rank downloads its own transcripts, ONE all_gather of the token ids at the end",
     }
 
 
@@ -128,32 +135,43 @@ class ClockSampler:
                                            % int(self.period * 1e3)}
 
 
+def file_sha(path):
+    import hashlib
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()[:16] if os.path.exists(path) else None
+
+
 def measured_traffic(kernel, utterances):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json:
-    {kernel: {"dram_bytes": ..., "utterances": ..., "source": ...}}); None when no capture of this kernel at this
-    launch size has been committed."""
+    {kernel: {"dram_bytes", "utterances", "source", "kernel_source_sha"}}).  None when no capture of this kernel at this
+    launch size has been committed OR the kernel's source changed since the capture (stale numbers are not reported)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         d = json.load(open(p)).get(kernel)
         if d and d.get("utterances", 64) == utterances:
-            return d.get("dram_bytes")
+            sha = file_sha(os.path.join(ROOT, "asr_transformer_b200", "csrc", "decode_cluster.cu"))
+            if d.get("kernel_source_sha") in (None, sha):
+                return d.get("dram_bytes")
     return None
 
 
 def attention_tensor_pipe():
-    """sm__pipe_tensor_cycles_active of the encoder flash-attention kernel from profiles/r01f_encoder_kernels.md."""
-    p = os.path.join(ROOT, "profiles", "r01f_encoder_kernels.md")
-    if not os.path.exists(p):
+    """sm__pipe_tensor_cycles_active of the encoder flash-attention kernel from the newest committed encoder profile."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_encoder_kernels.md")))
+    if not files:
         return None
+    p = files[-1]
     rows = [l.split("|") for l in open(p) if "attn_tc_kernel" in l]
     if not rows:
         return None
-    pct = [float(r[5]) for r in rows]
-    us = [float(r[4]) for r in rows]
-    return {"kernel": "attn_tc_kernel (encoder self attention, C2: 64 x 4 heads x 249 x 249)",
+    try:
+        pct = [float(r[5]) for r in rows]
+        us = [float(r[4]) for r in rows]
+    except (ValueError, IndexError):
+        return None
+    return {"kernel": "attn_tc_kernel (encoder self attention)",
             "tensor_pipe_active_pct": round(sum(pct) / len(pct), 1), "us_per_launch": round(sum(us) / len(us), 1),
-            "source": "profiles/r01f_encoder_kernels.md (ncu --set full, cold cache); exp-bound at head dim 64, "
-                      "2 CTAs per SM"}
+            "source": os.path.relpath(p, ROOT) + " (ncu --set full, cold cache; quoted, not measured in this run)"}
 
 
 def measured_peaks():
@@ -182,28 +200,73 @@ def decode_class_bytes(cfg, B):
     }
 
 
-def run_reference(args, cfg):
-    """Reference arm: the reference's CPU algorithm (literal restatement, oracle/speech_transformer.py) on the host
-    cores.  One step = ONE utterance of the same workload (bounded sample; the reference costs O(L^2) per utterance)."""
+def decode_alg_bytes(cfg, B):
+    """algorithmic HBM bytes of ONE greedy decode of B utterances (all L steps): the 16-bit
+    weights once per step, shared by the batch, + per utterance and step the cross K/V, the self K/V read (t + 1 rows at
+    step t) and write, and the fp32 logits.  (11.138 MB + B x 1.933 MB per step at C2.)"""
+    D, FF, V, Tp, L, nd = (cfg.embedding_dim, cfg.ff_dim, cfg.vocab_size, cfg.encoder_seq_len, cfg.decoder_seq_len,
+                           cfg.decoder_num_layers)
+    weights = 2 * (nd * (6 * D * D + 2 * D * FF) + D * V)
+    per_utt = nd * 2 * Tp * D * 2 + nd * 2 * ((L + 1) / 2) * D * 2 + nd * 2 * D * 2 + 4 * V
+    return {"weights_per_step": weights, "per_utterance_step": per_utt, "per_step": weights + B * per_utt,
+            "per_decode": (weights + B * per_utt) * L}
+
+
+def load_reference():
+    """The unmodified reference Transformer class from baseline/_ref (tools/install_ref.sh), or None."""
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_root, "modules", "Transformer", "model.py")):
+        return None
+    if ref_root not in sys.path:
+        sys.path.insert(0, ref_root)
+    from modules.Transformer.model import Transformer as RefTransformer
+    return RefTransformer
+
+
+def reference_evaluator(cfg, state):
+    """Returns (fn(spectrum (b,1,F,T)) -> None running the reference's greedy path, kind)."""
+    Ref = load_reference()
+    if Ref is not None:
+        torch.manual_seed(0)
+        ref = Ref(**cfg.ctor_kwargs())
+        ref.load_state_dict(state, strict=True)
+        ref.eval()
+
+        def fn(spec):
+            with torch.no_grad():
+                for b in range(spec.shape[0]):    # per utterance: evaluate() returns the last sample's tokens only (Q4)
+                    ref.evaluate(spec[b:b + 1], torch.full((1, 1), cfg.bos_token_id, dtype=torch.int32))
+        return fn, "reference"
     from oracle import speech_transformer as O
-    from asr_transformer_b200.workloads import build_model, cpu_state
+
+    def fn(spec):
+        with torch.no_grad():
+            O.evaluate_reference_style(state, spec, cfg)
+    return fn, "port"
+
+
+def run_reference(args, cfg):
+    """Reference arm: the reference's own CPU implementation of the path (baseline/_ref: the unmodified
+    Transformer.evaluate; the oracle's literal restatement only when that is absent) on the host cores.  One step = ONE
+    utterance of the same workload (bounded sample; the reference costs O(L^2) per utterance)."""
+    from asr_transformer_b200.workloads import build_model, cpu_state, structured_spectrum
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
     model = build_model(cfg)
     sd = cpu_state(model)
+    fn, kind = reference_evaluator(cfg, sd)
     batch = args.batch or cfg.batch
-    spec = O.structured_spectrum(batch, cfg.frames, cfg.input_dim, seed=1)
+    spec = structured_spectrum(batch, cfg.frames, cfg.input_dim, seed=1)
     times = []
-    with torch.no_grad():
-        for i in range(args.warmup + args.steps):
-            b = i % batch
-            t0 = time.perf_counter()
-            O.evaluate_reference_style(sd, spec[b:b + 1], cfg)
-            dt = time.perf_counter() - t0
-            if i >= args.warmup:
-                times.append(dt)
+    for i in range(args.warmup + args.steps):
+        b = i % batch
+        t0 = time.perf_counter()
+        fn(spec[b:b + 1])
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
     total = sum(times)
     value = len(times) / total
     sample = f"1 utterance per step ({cfg.frames} frames, {cfg.decoder_seq_len} decode steps), {len(times)} timed steps"
@@ -211,7 +274,7 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_desc(cfg, batch, args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -327,15 +390,22 @@ def main():
     # ------------------------------------------------------------------ end to end through the public API
     # Every step uploads its own spectrogram batch from pinned host memory and downloads its transcripts; the public
     # serving call (Transformer.greedy_decode_batches) overlaps those copies with the neighbouring steps' compute.
-    gather = gather_tokens if dist is not None else None
-
+    # Multi-GPU: every rank downloads ITS OWN transcripts per batch (plain D2H, no rendezvous in the loop);
+    # the only collective is ONE all_gather of all the steps' token ids at the very end, inside the timed region.
     def run_e2e(n, trace=None):
-        out = None
+        outs = []
         t_start = time.perf_counter()
-        for out in model.greedy_decode_batches((spec_host for _ in range(n)), gather=gather):
+        for out in model.greedy_decode_batches((spec_host for _ in range(n))):
+            outs.append(out)
             if trace is not None:
                 trace.append(round(1e3 * (time.perf_counter() - t_start), 2))
-        return out
+        if dist is not None and outs:
+            tok = torch.cat([o[0] for o in outs], 0).to(dev, non_blocking=True)
+            ntk = torch.cat([o[1] for o in outs], 0).to(dev, non_blocking=True)
+            tok, ntk = gather_tokens(tok, ntk)
+            run_e2e.gathered_rows = int(tok.shape[0])
+            torch.cuda.synchronize()
+        return outs[-1] if outs else None
 
     run_e2e(4)
     barrier()
@@ -353,8 +423,6 @@ def main():
     def step_serial():      # the same work without overlap: one blocking call per batch
         x = spec_host.to(dev, non_blocking=True)
         t, n = model.greedy_decode(x)
-        if dist is not None:
-            t, n = gather_tokens(t, n)
         return t.cpu(), n.cpu()
 
     step_serial()
@@ -373,15 +441,24 @@ def main():
     result = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic", "config": workload_desc(cfg, batch, world), "clocks": clocks,
+        "dtype": "fp16 tensor-core operands (hi|lo split activations into every linear layer), fp32 accumulate",
+        "data": "synthetic", "config": workload_desc(cfg, batch, world), "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "Transformer.greedy_decode_batches (pinned host batches in, CPU transcripts out; copies of "
-                       "neighbouring steps overlap compute)", "serial_value": e2e_serial},
+                       "neighbouring steps overlap compute; multi-GPU: per-rank D2H, one all_gather of the token ids at "
+                       "the end of the run)", "serial_value": e2e_serial,
+                "final_gather_rows": getattr(run_e2e, "gathered_rows", None)},
         "gpu_launches": int(launches),
         "phase_ms": {"conv_frontend+encoder": round(enc_ms, 3), "cross_kv+greedy_decode": round(dec_ms, 3),
                      "serial_step": round(serial_ms, 3),
                      "note": "one batch at a time with an L2 flush between steps; `value` overlaps consecutive steps"},
+        "split_operands": int(lib.asr_split_operands()),
     }
+
+    # ------------------------------------------------------------------ extra passes (all ranks): BASELINE configs 3 / 5
+    # and the cross-N token identity check.  Short (2 timed steps each), device-timed, max over ranks.
+    if not args.no_extras and args.workload == WORKLOAD:
+        result.update(run_extras(model, dev, rank, world, dist, barrier))
 
     if rank == 0 and args.no_profile:
         print(json.dumps(result))
@@ -390,20 +467,26 @@ def main():
         # the decode launch of the timed region covers `co` coalesced batches: profile that launch
         co = coalesce_of(batch)
         pb = co * batch
-        enc_p = enc if co == 1 else torch.cat([eng.encode(spec_rot[i % N_ROT]) for i in range(co)], 0)
-        tokens_p = torch.empty(pb, cfg.decoder_seq_len + 1, dtype=torch.int32, device=dev)
-        ws = eng._ws(pb, 4 * cfg.encoder_seq_len + 3, cfg.decoder_seq_len)
-        ms_cls = (C.c_float * 12)()
-        n_cls = (C.c_int32 * 12)()
-        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        phase = torch.zeros(3 * max(n_sm, 148, pb, 256), 16, dtype=torch.int64, device=dev)
-        for _ in range(2):     # second pass is the measured one (first warms caches / clocks)
-            L.check(lib.asr_decode_profile(eng.handle, L.ptr(enc_p), pb, cfg.encoder_seq_len, cfg.decoder_seq_len,
-                                           L.ptr(ws), ws.numel(), L.ptr(tokens_p), ms_cls, n_cls, L.ptr(phase),
-                                           L.stream()), "asr_decode_profile")
-        ph = phase.double().cpu()
-        cp = ph[2 * 148:2 * 148 + 148]
-        cp = cp[cp[:, 0] > 0]
+        hbm_peak, tf_peak, peak_src = measured_peaks()
+        prof_launches = {}
+        for name_l, nb in (("bench_launch", pb), ("single_batch", batch)):
+            enc_p = enc if nb == batch else torch.cat([eng.encode(spec_rot[i % N_ROT]) for i in range(co)], 0)
+            tokens_p = torch.empty(nb, cfg.decoder_seq_len + 1, dtype=torch.int32, device=dev)
+            ws = eng._ws(nb, 4 * cfg.encoder_seq_len + 3, cfg.decoder_seq_len)
+            ms_cls = (C.c_float * 12)()
+            n_cls = (C.c_int32 * 12)()
+            phase = torch.zeros(max(148, torch.cuda.get_device_properties(dev).multi_processor_count), 16,
+                                dtype=torch.int64, device=dev)
+            for _ in range(2):     # second pass is the measured one (first warms caches / clocks)
+                L.check(lib.asr_decode_profile(eng.handle, L.ptr(enc_p), nb, cfg.encoder_seq_len, cfg.decoder_seq_len,
+                                               L.ptr(ws), ws.numel(), L.ptr(tokens_p), ms_cls, n_cls, L.ptr(phase),
+                                               L.stream()), "asr_decode_profile")
+            prof_launches[name_l] = (nb, list(ms_cls), list(n_cls), phase.double().cpu())
+            if nb == batch and co == 1:
+                prof_launches["bench_launch"] = prof_launches[name_l]
+                break
+        nb, ms_cls, n_cls, ph = prof_launches["bench_launch"]
+        cp = ph[ph[:, 0] > 0]
         if len(cp):
             result["cluster_cycles_per_step"] = {k: round(float(cp[:, i].mean()) / cfg.decoder_seq_len, 1) for i, k in
                                                  enumerate(["total", "ring_wait", "exchange_wait", "producer_wait_empty",
@@ -413,9 +496,8 @@ def main():
                        "wo_mm(x2)", "all_reduce+ln(x3)", "cross_q_mm", "cross_attention", "ffn_w1_mm", "ffn_w2_mm"]
             result["cluster_phase_cycles_per_step"] = {n: round(float(cp[:, 5 + i].mean()) / cfg.decoder_seq_len, 1)
                                                        for i, n in enumerate(names_c)}
-        mhz = clocks.get("sm_mhz") or 1965.0
-        hbm_peak, tf_peak, peak_src = measured_peaks()
-        bytes_cls = decode_class_bytes(cfg, pb)
+        # per-kernel classes of the graph (fallback) path, with that path's own per-kernel byte counts
+        bytes_cls = decode_class_bytes(cfg, nb)
         prof = {}
         tot = sum(ms_cls[:9])
         for i, name in enumerate(DEC_CLASSES):
@@ -424,26 +506,31 @@ def main():
                 prof[name] = {"launches": int(n_cls[i]), "avg_us": round(avg_us, 3), "share": round(ms_cls[i] / tot, 4),
                               "alg_bytes_per_launch": int(bytes_cls[name]),
                               "gbs": round(bytes_cls[name] / (avg_us * 1e-6) / 1e9, 1)}
-        step_bytes = sum(bytes_cls[k] * (prof[k]["launches"] / cfg.decoder_seq_len) for k in prof)
-        decode_bytes = step_bytes * cfg.decoder_seq_len
-        result["decode_kernel_profile"] = prof
-        result["decode_step"] = {"alg_bytes": int(step_bytes), "per_kernel_step_sum_ms": round(tot, 3),
-                                 "roofline_ms_per_decode": round(decode_bytes / (hbm_peak * 1e9) * 1e3, 3)}
-        result["decode_kernels_ms"] = {"persistent": round(ms_cls[9], 3) if n_cls[9] else None,
-                                       "stream": round(ms_cls[10], 3) if n_cls[10] else None,
-                                       "cluster": round(ms_cls[11], 3) if n_cls[11] else None}
-        slot = {"s": 10, "c": 11}.get(mode[0], 9)
-        if mode[0] in "psc" and n_cls[slot]:
-            ms_cls[9] = ms_cls[slot]
-            gbs = decode_bytes / (ms_cls[9] * 1e-3) / 1e9
-            kname = {9: "dec_persistent_kernel", 10: "dec_stream_kernel", 11: "dec_cluster_kernel"}[slot]
-            result["roofline"] = {"kernel": kname + " (all %d decode steps of %d utterances, one launch)"
-                                            % (cfg.decoder_seq_len, pb),
+        result["graph_path_kernel_profile"] = prof
+        # the roofline of the dominant kernel: SURVEY.md 8(d) algorithmic bytes (weights once per step + per-utterance
+        # K/V and logits) over the measured duration of ONE launch of dec_cluster_kernel
+        alg = decode_alg_bytes(cfg, nb)
+        result["decode_step"] = {"alg_bytes": int(alg["per_step"]), "weights_bytes": int(alg["weights_per_step"]),
+                                 "per_utterance_bytes": int(alg["per_utterance_step"]), "utterances": nb,
+                                 "roofline_ms_per_decode": round(alg["per_decode"] / (hbm_peak * 1e9) * 1e3, 3)}
+        if mode[0] == "c" and n_cls[9]:
+            gbs = alg["per_decode"] / (ms_cls[9] * 1e-3) / 1e9
+            result["roofline"] = {"kernel": "dec_cluster_kernel (all %d decode steps of %d utterances, one launch)"
+                                            % (cfg.decoder_seq_len, nb),
                                   "bound": "hbm", "achieved": round(gbs, 1), "peak": hbm_peak, "unit": "GB/s",
                                   "frac": round(gbs / hbm_peak, 4),
-                                  "traffic": measured_traffic(kname, pb) if args.workload == WORKLOAD else None,
+                                  "traffic": measured_traffic("dec_cluster_kernel", nb) if args.workload == WORKLOAD else None,
                                   "peak_source": peak_src,
-                                  "alg_bytes_per_launch": int(decode_bytes), "ms_per_launch": round(ms_cls[9], 3)}
+                                  "alg_bytes_per_launch": int(alg["per_decode"]), "ms_per_launch": round(ms_cls[9], 3),
+                                  "how": "SURVEY.md 8(d) bytes per step x L / CUDA-event time of the launch on its stream"}
+            if "single_batch" in prof_launches and prof_launches["single_batch"][0] != nb:
+                nb1, ms1, n1, _ = prof_launches["single_batch"]
+                alg1 = decode_alg_bytes(cfg, nb1)
+                if n1[9]:
+                    g1 = alg1["per_decode"] / (ms1[9] * 1e-3) / 1e9
+                    result["roofline_single_batch"] = {"utterances": nb1, "ms_per_launch": round(ms1[9], 3),
+                                                       "achieved": round(g1, 1), "frac": round(g1 / hbm_peak, 4),
+                                                       "alg_bytes_per_launch": int(alg1["per_decode"])}
         else:
             top = max(prof, key=lambda k: prof[k]["share"])
             result["roofline"] = {"kernel": top, "bound": "hbm", "achieved": prof[top]["gbs"], "peak": hbm_peak,
@@ -456,26 +543,115 @@ def main():
         if att:
             result["attention_tensor_pipe"] = att
 
-        # -------------------------------------------------------------- CPU baseline (reference algorithm, host cores)
+        # -------------------------------------------------------------- CPU baseline (the reference itself, host cores)
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import speech_transformer as O      # the ONLY use of oracle/ on this arm: the timed CPU baseline
             torch.set_num_threads(os.cpu_count() or 1)
             sd = cpu_state(model)
+            fn, kind = reference_evaluator(cfg, sd)     # baseline/_ref (unmodified reference) or the oracle port
             n_cpu = 16
-            with torch.no_grad():
-                import dataclasses
-                O.evaluate_reference_style(sd, spec_host[:1].contiguous(), dataclasses.replace(cfg, decoder_seq_len=4))  # warm-up
-                t0 = time.perf_counter()
-                O.evaluate_reference_style(sd, spec_host[:n_cpu].contiguous(), cfg)
-                dt = time.perf_counter() - t0
+            import dataclasses
+            fn_w, _ = reference_evaluator(dataclasses.replace(cfg, decoder_seq_len=4), sd)
+            fn_w(spec_host[:1].contiguous())            # warm-up
+            t0 = time.perf_counter()
+            fn(spec_host[:n_cpu].contiguous())
+            dt = time.perf_counter() - t0
             result["cpu_baseline"] = {
-                "value": n_cpu / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                "sample": f"{n_cpu} utterances of the same workload through the oracle's literal restatement of the "
-                          f"reference greedy loop (model.py:125-151: per utterance, no KV cache), {dt:.1f} s"}
+                "value": n_cpu / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                "sample": f"{n_cpu} utterances of the same workload through "
+                          + ("the unmodified reference Transformer.evaluate (baseline/_ref)" if kind == "reference" else
+                             "the oracle's literal restatement of the reference greedy loop")
+                          + f" (model.py:125-151: per utterance, no KV cache), {dt:.1f} s"}
         print(json.dumps(result))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_extras(model, dev, rank, world, dist, barrier):
+    """BASELINE configs 3 and 5 and the cross-N token identity check, inside the same bench run (the driver only passes
+    --gpus / --steps / --warmup).  Every pass is device-timed between barriers, max over ranks."""
+    import hashlib
+    from asr_transformer_b200 import workloads as W
+    from asr_transformer_b200.parallel import (balanced_assignment, bucket_by_length, decode_sharded, gather_tokens,
+                                               shard_range)
+    out = {}
+
+    def timed(fn, steps=2, warm=1):
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    # ---- cross-N token identity (SURVEY.md 8e / H7): every N decodes the SAME seed-1 global batch of 64 utterances,
+    # sharded contiguously over the ranks, gathered; the SHA-256 must equal the committed N=1 value
+    c2 = W.CONFIGS["C2"]
+    spec_g = W.structured_spectrum(64, c2.frames, c2.input_dim, seed=1)
+    tok, ntk = decode_sharded(model, spec_g, dev)
+    torch.cuda.synchronize()
+    sha = hashlib.sha256(tok.cpu().to(torch.int32).contiguous().numpy().tobytes()).hexdigest()
+    gp = os.path.join(ROOT, "tests", "golden", "cross_n_tokens.json")
+    gold = json.load(open(gp)).get("C2_seed1_B64_sha256") if os.path.exists(gp) else None
+    out["cross_n_tokens"] = {"workload": "C2, global batch 64 (seed 1), contiguous shards over %d rank(s)" % world,
+                             "sha256": sha, "golden_n1": gold, "matches_golden": (sha == gold) if gold else None,
+                             "distinct_rows": len({tuple(r) for r in tok.cpu().tolist()})}
+
+    # ---- C3 strong scaling: paper-size model (12 encoder layers), global batch 256 split over the N GPUs
+    c3 = W.CONFIGS["C3"]
+    m3 = W.build_model(c3, dev)
+    lo, hi = shard_range(c3.batch, rank, world)
+    counts = [shard_range(c3.batch, r, world)[1] - shard_range(c3.batch, r, world)[0] for r in range(world)]
+    x3 = W.structured_spectrum(c3.batch, c3.frames, c3.input_dim, seed=3)[lo:hi].to(dev)
+
+    def step3():
+        t, n = m3.greedy_decode(x3)
+        if dist is not None:
+            gather_tokens(t, n, counts)
+    ms3 = timed(step3)
+    out["c3_strong"] = {"workload": "C3: 12 enc / 6 dec, d_model 256, global batch 256 split over %d GPU(s) (%d per "
+                                    "GPU), greedy decode 128 steps, inputs resident, token all_gather included" %
+                                    (world, hi - lo),
+                        "value": c3.batch / (ms3 / 1e3), "unit": UNIT, "ms_per_step": round(ms3, 3), "scaling": "strong"}
+    del m3, x3
+    torch.cuda.empty_cache()
+
+    # ---- C5: widened model, mixed-length batch (len ~ U{400..1000}) with key-padding masks ON, 64 utterances per GPU,
+    # length-balanced over the ranks, length-bucketed into batches of 16 (each padded to its own longest utterance)
+    c5 = W.CONFIGS["C5"]
+    m5 = W.build_model(c5, dev)
+    G = 64 * world
+    g = torch.Generator().manual_seed(5)
+    lens = torch.randint(400, 1001, (G,), generator=g)
+    mine = balanced_assignment(lens.tolist(), world)[rank]
+    items = []
+    for b in bucket_by_length([int(lens[i]) for i in mine], 16):
+        idx = [mine[j] for j in b]
+        ln = lens[idx]
+        T = int(ln.max())
+        x = W.structured_spectrum(len(idx), T, c5.input_dim, seed=500 + idx[0], lengths=ln).to(dev)
+        items.append((x, ln.to(dev)))
+
+    def step5():
+        for x, ln in items:
+            m5.greedy_decode(x, lengths=ln)
+    ms5 = timed(step5)
+    out["c5_masks"] = {"workload": "C5: 12 enc / 6 dec, d_model 512, 8 heads, FFN 2048; %d utterances per GPU, lengths "
+                                   "U{400..1000} frames, key-padding masks on (encoder self attention + decoder cross "
+                                   "attention), balanced_assignment over %d rank(s), 4 length buckets of 16" % (64, world),
+                       "value": G / (ms5 / 1e3), "unit": UNIT, "ms_per_step": round(ms5, 3), "scaling": "weak",
+                       "frames_processed_frac": round(float(sum(int(x.shape[-1]) * x.shape[0] for x, _ in items)) /
+                                                      (64 * 1000), 3)}
+    del m5, items
+    torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":

@@ -3,7 +3,7 @@
 # usage: tools/gpu_bringup.sh [groups...]   (default: all)
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-run() { name=$1; shift; timeout 420 python -m pytest "$@" -q --tb=short -p no:cacheprovider --timeout 90 > gpurun_out/$name.log 2>&1; echo "$name exit $?"; tail -n 3 gpurun_out/$name.log; }
+run() { name=$1; shift; timeout 1800 python -m pytest "$@" -q --tb=short -p no:cacheprovider --timeout 400 -s > gpurun_out/$name.log 2>&1; echo "$name exit $?"; tail -n 3 gpurun_out/$name.log; }
 groups=${@:-"probe ln gemm attn modules dec model smoke bench"}
 for g in $groups; do
 case $g in
