@@ -449,14 +449,6 @@ static bool cluster_available(const AsrHandle* h) {
          h->w.dec_image_bytes == lay.total_bytes;
 }
 
-static bool cluster2_available(const AsrHandle* h) {
-  const AsrConfig& c = h->cfg;
-  ClusterLayout lay;
-  return h->w.dec_image2 && c.decoder_num_layers > 0 &&
-         cluster2_layout(c.embedding_dim, c.num_heads, c.ff_dim, c.vocab_size, c.decoder_num_layers, &lay) &&
-         h->w.dec_image2_bytes == lay.total_bytes;
-}
-
 static void build_cluster(const AsrHandle* h, const GreedyWs& w, int B, int Tp, int L, int stop_at_eos, int32_t* tokens,
                           int32_t* n_tokens, float* step_logits, ClusterParams& cp) {
   const AsrConfig& c = h->cfg;
@@ -684,14 +676,6 @@ static int decode_greedy_impl(int phases, AsrHandle* h, const float* enc_out, in
   if (mode && mode[0] == 'c' && !cluster_available(h))
     return set_error(ASR_E_UNSUPPORTED, "asr_decode_greedy: cluster decoder requested but unavailable (packed image "
                      "missing or config unsupported: heads must be 2, 4 or 8, ff_dim %% (32 heads) == 0)");
-  if (mode && !std::strcmp(mode, "cluster2")) {
-    if (!cluster2_available(h)) return set_error(ASR_E_UNSUPPORTED, "asr_decode_greedy: tcgen05 cluster decoder unavailable");
-    ClusterParams cp;
-    build_cluster(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, cp);
-    cp.image = static_cast<const uint8_t*>(h->w.dec_image2); cp.image_bytes = h->w.dec_image2_bytes;
-    cp.enc_lens = enc_lens;
-    return launch_dec_cluster2(cp, s);
-  }
   if ((!mode || !mode[0] || mode[0] == 'c') && cluster_available(h)) {
     ClusterParams cp;
     build_cluster(h, w, B, Tp, L, stop_at_eos, tokens, n_tokens, step_logits, cp);
@@ -885,12 +869,7 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
     ASR_CUDA_OK(cudaEventCreate(&e0));
     ASR_CUDA_OK(cudaEventCreate(&e1));
     ASR_CUDA_OK(cudaEventRecord(e0, s));
-    const char* pm = std::getenv("ASR_B200_DECODE");
-    const bool v2 = pm && !std::strcmp(pm, "cluster2") && cluster2_available(h);
-    if (v2) {
-      cp.image = static_cast<const uint8_t*>(h->w.dec_image2); cp.image_bytes = h->w.dec_image2_bytes;
-    }
-    int rc = v2 ? launch_dec_cluster2(cp, s) : launch_dec_cluster(cp, s);
+    int rc = launch_dec_cluster(cp, s);
     ASR_CUDA_OK(cudaEventRecord(e1, s));
     ASR_CUDA_OK(cudaStreamSynchronize(s));
     if (!rc) {
@@ -908,14 +887,6 @@ size_t asr_decoder_image_bytes(const AsrConfig* cfg) {
   ClusterLayout lay;
   if (!cfg || !cluster_layout(cfg->embedding_dim, cfg->num_heads, cfg->ff_dim, cfg->vocab_size, cfg->decoder_num_layers,
                               &lay))
-    return 0;
-  return lay.total_bytes;
-}
-
-size_t asr_decoder_image2_bytes(const AsrConfig* cfg) {
-  ClusterLayout lay;
-  if (!cfg || !cluster2_layout(cfg->embedding_dim, cfg->num_heads, cfg->ff_dim, cfg->vocab_size, cfg->decoder_num_layers,
-                               &lay))
     return 0;
   return lay.total_bytes;
 }

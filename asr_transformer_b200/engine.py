@@ -179,108 +179,6 @@ def pack_dec_image(decoder: nn.Module) -> Optional[torch.Tensor]:
     return torch.cat(ranks).contiguous()
 
 
-def pack_umma_tiles(w: torch.Tensor) -> torch.Tensor:
-    """fp16 [R, K] (K % 64 == 0) -> uint8 operand tiles of the tcgen05 cluster decoder: rows zero-padded to a multiple
-    of 128, tiles ordered [m-tile][k-block], each 128 rows x 64 columns (16 KB) in the canonical K-major SWIZZLE_128B
-    layout (row r at byte 128 r, its 16-byte chunk c stored at chunk position c ^ (r & 7)): a 1-D bulk copy of a tile
-    lands exactly what a TMA tensor-map load would have written, i.e. a ready UMMA A operand."""
-    R, K = w.shape
-    assert K % 64 == 0, (R, K)
-    Rp = (R + 127) // 128 * 128
-    wp = torch.zeros(Rp, K, dtype=torch.float16, device=w.device)
-    wp[:R] = w.to(torch.float16)
-    t = wp.reshape(Rp // 128, 128, K // 64, 8, 8).permute(0, 2, 1, 3, 4)          # mt, kb, r, chunk, e
-    r = torch.arange(128, device=w.device)
-    pos = torch.arange(8, device=w.device)
-    src_chunk = pos[None, :] ^ (r[:, None] & 7)                                    # position p of row r holds chunk p ^ (r & 7)
-    t = t[:, :, r[:, None], src_chunk, :]                                          # mt, kb, r, pos, e
-    return t.contiguous().view(torch.uint8).reshape(-1)
-
-
-def dec_image2_layout(D: int, H: int, FF: int, V: int, nd: int) -> Optional[dict]:
-    """Byte layout of the tcgen05 cluster decoder's image; mirrors cluster2_layout() in csrc/decode_cluster2.cu."""
-    if H < 2 or H > 8 or (H & (H - 1)) or D != 64 * H or FF % (128 * H) or V < 1 or nd < 1:
-        return None
-    FFS = FF // H
-    VS = ((V + H - 1) // H + 15) // 16 * 16
-    if (H, FFS, VS) not in ((4, 256, 64), (2, 128, 128), (8, 256, 32)):
-        return None
-    T = 16384
-    tiles = lambda rows: (rows + 127) // 128
-    lay = {"CS": H, "FFS": FFS, "VS": VS, "small_floats": 256 + FFS + 3 * 64 + 8 * D}
-    lay["small_bytes"] = (lay["small_floats"] * 4 + 127) // 128 * 128
-    off = 0
-    for name, nbytes in (("small", (lay["small_bytes"] + 1023) // 1024 * 1024), ("qkv", 2 * (D // 64) * T),
-                         ("wo", tiles(D) * T), ("wqc", (D // 64) * T), ("woc", tiles(D) * T),
-                         ("w1", tiles(FFS) * (D // 64) * T), ("w2", tiles(D) * (FFS // 64) * T)):
-        lay["off_" + name] = off
-        off += nbytes
-    lay["layer_bytes"] = off
-    lay["off_cls"] = nd * off
-    lay["rank_bytes"] = lay["off_cls"] + tiles(VS) * (D // 64) * T
-    lay["total_bytes"] = lay["rank_bytes"] * H
-    return lay
-
-
-def pack_dec_image2(decoder: nn.Module) -> Optional[torch.Tensor]:
-    """Packed weight image of the tcgen05 cluster decoder (uint8): for every head r (= CTA rank) the operand tiles that
-    CTA consumes, in consumption order.  Per layer: a small fp32 block [b_qkv rows of head r (q|k|v: 192) | cross b_q
-    rows of head r (64) | b1[r FFS..] (FFS) | b_out[64 r..] | cross b_out[64 r..] | b2[64 r..] (the 64 residual rows the
-    CTA owns) | ln1 g,b | ln2 g,b | ln3 g,b | ln1 g,b of the next layer (zeros after the last)], then pack_umma_tiles of
-    [Wq_r; Wk_r] and [Wv_r; 0] (two 128-row tiles), Wout[:, 64 r..], cross Wq_r (padded to 128 rows), cross
-    Wout[:, 64 r..], W1[r FFS.., :], W2[:, r FFS..]; after the layers the classifier rows r VS.. (zero padded)."""
-    layers = list(decoder._layers)
-    if not layers:
-        return None
-    D = decoder._embedding.embedding_dim
-    V = decoder._embedding.num_embeddings
-    H = len(layers[0]._mask_attention._heads)
-    FF = layers[0]._feedforward.ff_dim
-    lay = dec_image2_layout(D, H, FF, V, len(layers))
-    if lay is None:
-        return None
-    FFS, VS = lay["FFS"], lay["VS"]
-    dev = decoder._embedding.weight.device
-    cls = torch.zeros(H * VS, D, dtype=torch.float16, device=dev)
-    cls[:V] = decoder._classifier.weight.detach().to(torch.float16)
-
-    def u8(t: torch.Tensor) -> torch.Tensor:
-        return t.contiguous().view(torch.uint8).reshape(-1)
-
-    packs = [(pack_mha(l._mask_attention), pack_mha(l._cross_attention), pack_ffn(l._feedforward)) for l in layers]
-    ranks = []
-    for r in range(H):
-        parts = []
-        hs = slice(r * 64, (r + 1) * 64)
-        for li, layer in enumerate(layers):
-            sa, ca, ff = packs[li]
-            rows_qkv = torch.cat([torch.arange(r * 64, (r + 1) * 64) + k * D for k in range(3)]).to(dev)
-            small = [sa["b_qkv"][rows_qkv], ca["b_qkv"][hs], ff["b1"][r * FFS:(r + 1) * FFS], sa["b_out"][hs],
-                     ca["b_out"][hs], ff["b2"][hs]]
-            for ln in (layer._norm1, layer._norm2, layer._norm3):
-                small += [_f32(ln.weight), _f32(ln.bias)]
-            nxt = layers[li + 1]._norm1 if li + 1 < len(layers) else None
-            small += [_f32(nxt.weight), _f32(nxt.bias)] if nxt is not None else [torch.zeros(2 * D, device=dev)]
-            small = torch.cat([x.reshape(-1) for x in small])
-            assert small.numel() == lay["small_floats"]
-            small = torch.cat([small, small.new_zeros(lay["off_qkv"] // 4 - small.numel())])
-            wq, wk, wv = (sa["w_qkv"][rows_qkv[i * 64:(i + 1) * 64]] for i in range(3))
-            blk = torch.cat([u8(small),
-                             pack_umma_tiles(torch.cat([wq, wk], 0)), pack_umma_tiles(wv),
-                             pack_umma_tiles(sa["w_out"][:, hs]),
-                             pack_umma_tiles(ca["w_qkv"][hs]),
-                             pack_umma_tiles(ca["w_out"][:, hs]),
-                             pack_umma_tiles(ff["w1"][r * FFS:(r + 1) * FFS]),
-                             pack_umma_tiles(ff["w2"][:, r * FFS:(r + 1) * FFS])])
-            assert blk.numel() == lay["layer_bytes"], (blk.numel(), lay["layer_bytes"])
-            parts.append(blk)
-        parts.append(pack_umma_tiles(cls[r * VS:(r + 1) * VS]))
-        rk = torch.cat(parts)
-        assert rk.numel() == lay["rank_bytes"]
-        ranks.append(rk)
-    return torch.cat(ranks).contiguous()
-
-
 def _mha_struct(p: dict) -> _l.AsrMhaWeights:
     return _l.AsrMhaWeights(p["w_qkv"].data_ptr(), p["b_qkv"].data_ptr(), p["w_out"].data_ptr(), p["b_out"].data_ptr())
 
@@ -397,10 +295,6 @@ class Engine:
                 if image is not None:
                     keep.append(image)
                     w.dec_image, w.dec_image_bytes = image.data_ptr(), image.numel()
-                image2 = pack_dec_image2(decoder)
-                if image2 is not None:
-                    keep.append(image2)
-                    w.dec_image2, w.dec_image2_bytes = image2.data_ptr(), image2.numel()
         else:
             cfg.vocab_size, cfg.decoder_seq_len, cfg.decoder_num_layers = 1, 1, 0
         if H is None:   # zero layers everywhere: derive from D

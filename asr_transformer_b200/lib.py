@@ -51,7 +51,7 @@ class AsrWeights(C.Structure):
                 ("embedding", c_void_p), ("dec_pe", c_void_p),
                 ("dec_layers", C.POINTER(AsrDecoderLayerWeights)), ("dec_norm", AsrNormWeights),
                 ("classifier_w", c_void_p), ("dec_image", c_void_p),
-                ("dec_image_bytes", c_size_t), ("dec_image2", c_void_p), ("dec_image2_bytes", c_size_t)]
+                ("dec_image_bytes", c_size_t)]
 
 
 # name -> (restype, argtypes); mirrors include/asr_b200.h one to one (tests/test_host.py checks the symbol list against the header)
@@ -80,7 +80,6 @@ _SIGNATURES = {
     "asr_launch_count": (C.c_ulonglong, []),
     "asr_split_operands": (c_int, []),
     "asr_decoder_image_bytes": (c_size_t, [C.POINTER(AsrConfig)]),
-    "asr_decoder_image2_bytes": (c_size_t, [C.POINTER(AsrConfig)]),
     "asr_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "asr_f32_to_f16": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "asr_gemm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

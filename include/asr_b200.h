@@ -101,10 +101,6 @@ typedef struct {
    * asr_decoder_image_bytes() gives the total size (0 = shape not compiled into the cluster kernel). */
   const void* dec_image;
   size_t dec_image_bytes;
-  /* optional: the decoder weights packed as tcgen05 operand tiles for the tcgen05 cluster decoder (decode_cluster2.cu;
-   * layout in asr_transformer_b200/engine.py: pack_dec_image2).  asr_decoder_image2_bytes() gives the size. */
-  const void* dec_image2;
-  size_t dec_image2_bytes;
 } AsrWeights;
 
 const char* asr_last_error(void);
@@ -183,7 +179,6 @@ int asr_decode_profile(AsrHandle* h, const float* enc_out, int B, int Tp, int L,
                        asr_stream_t stream);
 /* Size of AsrWeights.dec_image for a configuration (0 = the cluster decoder does not support it). */
 size_t asr_decoder_image_bytes(const AsrConfig* cfg);
-size_t asr_decoder_image2_bytes(const AsrConfig* cfg);
 /* Number of kernels this library has launched in the calling process (graph replays counted per kernel). */
 unsigned long long asr_launch_count(void);
 /* 1 (default): every activation that feeds a Linear layer or conv2 as a tensor-core operand travels as an fp16
