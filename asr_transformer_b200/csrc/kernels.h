@@ -178,8 +178,5 @@ struct ClusterParams {
   long long* timing;      // nullable: [gridDim][16] {total, ring wait, exchange wait, producer wait, stages}
 };
 int launch_dec_cluster(ClusterParams& p, cudaStream_t s);
-// tcgen05 edition (decode_cluster2.cu): same ClusterParams, its own packed image (UMMA operand tiles)
-bool cluster2_layout(int D, int H, int FF, int V, int nd, ClusterLayout* out);
-int launch_dec_cluster2(ClusterParams& p, cudaStream_t s);
 
 }  // namespace asr
