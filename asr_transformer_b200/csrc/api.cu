@@ -312,9 +312,24 @@ int gemm(const f16* X, int ldx, const void* W, int M, int N, int K, const GemmEp
   return launch_gemm_tc(X, ldx, static_cast<const f16*>(W), K, M, N, K, ep, s, split);
 }
 
+// h_out = X W^T + ep terms, then xn_out = LayerNorm(h_out): ONE launch when the full-row kernel supports the shape
+// (N == 256), otherwise GEMM + LayerNorm kernel.  ln_f16: the next GEMM's A operand (hi | lo pair under g_split), ln_f32:
+// fp32 LayerNorm output (the encoder's final norm).
+int gemm_ln(const f16* X, int ldx, const void* W, int M, int N, int K, const GemmEpilogue& ep, const AsrNormWeights& nw,
+            f16* ln_f16, float* ln_f32, cudaStream_t s, int split) {
+  LnEpilogue ln;
+  ln.gamma = nw.gamma; ln.beta = nw.beta; ln.out_f16 = ln_f16; ln.split = g_split; ln.out_f32 = ln_f32;
+  const int rc = launch_gemm_ln(X, ldx, static_cast<const f16*>(W), K, M, N, K, ep, ln, s, split);
+  if (rc <= 0) return rc;
+  if (int rc2 = launch_gemm_tc(X, ldx, static_cast<const f16*>(W), K, M, N, K, ep, s, split)) return rc2;
+  return launch_layernorm(ep.out_f32, nw.gamma, nw.beta, M, N, 1e-5f, ln_f32, ln_f16, s, g_split);
+}
+
 // x (f16, normalised) -> self attention block output added to the fp32 residual stream h (in place)
+// next_ln: the LayerNorm that follows in the layer (fused into the out projection's epilogue), written to xn_out
 int self_attention_block(const AsrConfig& c, const AsrMhaWeights& w, const f16* xn, f16* qkv, f16* att, float* h,
-                         int B, int S, int causal, const uint8_t* valid, const int32_t* k_lens, cudaStream_t s) {
+                         int B, int S, int causal, const uint8_t* valid, const int32_t* k_lens, cudaStream_t s,
+                         const AsrNormWeights* next_ln = nullptr, f16* xn_out = nullptr) {
   const int D = c.embedding_dim, M = B * S, sp = SP();
   GemmEpilogue e1;
   e1.bias = w.b_qkv; e1.out_f16 = qkv; e1.ld_f16 = 3 * D;
@@ -330,16 +345,20 @@ int self_attention_block(const AsrConfig& c, const AsrMhaWeights& w, const f16* 
   if (int rc = launch_attention_tc(a, s)) return rc;
   GemmEpilogue e2;
   e2.bias = w.b_out; e2.residual = h; e2.ld_res = D; e2.out_f32 = h; e2.ld_f32 = D;
+  if (next_ln) return gemm_ln(att, sp * D, w.w_out, M, D, D, e2, *next_ln, xn_out, nullptr, s, g_split);
   return gemm(att, sp * D, w.w_out, M, D, D, e2, s, g_split);
 }
 
-int ffn_block(const AsrConfig& c, const AsrFfnWeights& w, const f16* xn, f16* ff, float* h, int M, cudaStream_t s) {
+// next_ln (optional): the LayerNorm applied to the block's output, fused into the second GEMM's epilogue
+int ffn_block(const AsrConfig& c, const AsrFfnWeights& w, const f16* xn, f16* ff, float* h, int M, cudaStream_t s,
+              const AsrNormWeights* next_ln = nullptr, f16* xn_out = nullptr, float* ln_f32 = nullptr) {
   const int D = c.embedding_dim, FF = c.ff_dim, sp = SP();
   GemmEpilogue e1;
   e1.bias = w.b1; e1.relu = 1; e1.out_f16 = ff; e1.ld_f16 = sp * FF; e1.f16_lo_off = g_split ? FF : 0;
   if (int rc = gemm(xn, sp * D, w.w1, M, FF, D, e1, s, g_split)) return rc;
   GemmEpilogue e2;
   e2.bias = w.b2; e2.residual = h; e2.ld_res = D; e2.out_f32 = h; e2.ld_f32 = D;
+  if (next_ln) return gemm_ln(ff, sp * FF, w.w2, M, D, FF, e2, *next_ln, xn_out, ln_f32, s, g_split);
   return gemm(ff, sp * FF, w.w2, M, D, FF, e2, s, g_split);
 }
 
@@ -533,20 +552,28 @@ static int encoder_core(AsrHandle* h, const EncodeWs& w, int B, int T2, const in
   const AsrConfig& c = h->cfg;
   const int F2 = conv_len(conv_len(c.input_dim));
   const int D = c.embedding_dim, M = B * T2, Kin = 64 * F2;
+  // Every LayerNorm of the pre-LN stack (model.py:20,23,52) rides in the epilogue of the GEMM that produces its input:
+  // _lin_in -> norm1 of layer 0; out projection -> norm2; FFN unsqueeze -> norm1 of the next layer / _norm_out.
+  const int nl = c.encoder_num_layers;
   {  // _lin_in + positional encoding (model.py:47)
     GemmEpilogue e;
     e.bias = h->w.lin_in_b; e.rowvec = h->w.enc_pe; e.rowvec_period = T2; e.ld_rowvec = D;
     e.out_f32 = w.h; e.ld_f32 = D;
-    if (int rc = gemm(w.z, SP() * Kin, h->w.lin_in_w, M, D, Kin, e, s, g_split)) return rc;
+    const AsrNormWeights& first = nl ? h->enc[0].norm1 : h->w.enc_norm_out;
+    if (int rc = gemm_ln(w.z, SP() * Kin, h->w.lin_in_w, M, D, Kin, e, first, nl ? w.xn : nullptr, nl ? nullptr : enc_out, s,
+                         g_split))
+      return rc;
   }
-  for (int l = 0; l < c.encoder_num_layers; ++l) {
+  for (int l = 0; l < nl; ++l) {
     const AsrEncoderLayerWeights& lw = h->enc[l];
-    if (int rc = launch_layernorm(w.h, lw.norm1.gamma, lw.norm1.beta, M, D, 1e-5f, nullptr, w.xn, s, g_split)) return rc;
-    if (int rc = self_attention_block(c, lw.attn, w.xn, w.qkv, w.att, w.h, B, T2, 0, nullptr, enc_lens, s)) return rc;
-    if (int rc = launch_layernorm(w.h, lw.norm2.gamma, lw.norm2.beta, M, D, 1e-5f, nullptr, w.xn, s, g_split)) return rc;
-    if (int rc = ffn_block(c, lw.ffn, w.xn, w.ff, w.h, M, s)) return rc;
+    if (int rc = self_attention_block(c, lw.attn, w.xn, w.qkv, w.att, w.h, B, T2, 0, nullptr, enc_lens, s, &lw.norm2, w.xn))
+      return rc;
+    const bool last = l + 1 == nl;
+    if (int rc = ffn_block(c, lw.ffn, w.xn, w.ff, w.h, M, s, last ? &h->w.enc_norm_out : &h->enc[l + 1].norm1,
+                           last ? nullptr : w.xn, last ? enc_out : nullptr))
+      return rc;
   }
-  return launch_layernorm(w.h, h->w.enc_norm_out.gamma, h->w.enc_norm_out.beta, M, D, 1e-5f, enc_out, nullptr, s);
+  return 0;
 }
 
 int asr_encode(AsrHandle* h, const float* spectrum, int B, int T, const int32_t* enc_lens, void* ws, size_t ws_bytes,
@@ -606,11 +633,17 @@ int asr_decoder_forward(AsrHandle* h, const float* enc_out, int B, int Tp, const
   const int D = c.embedding_dim, M = B * Tp, R = B * L;
   if (int rc = cross_kv(h, enc_out, w.enc_f16, w.ckv, M, s)) return rc;
   if (int rc = launch_embed_pe(text, L, h->w.embedding, h->w.dec_pe, B, L, D, c.vocab_size, w.h, s)) return rc;
-  for (int l = 0; l < c.decoder_num_layers; ++l) {
+  // norm1 of layer 0 (or, without layers, the final norm) is the only stand-alone LayerNorm: every other one rides in the
+  // epilogue of the GEMM that produces its input (out projections -> norm2 / norm3, FFN -> next norm1 / _norm_layer)
+  const int nd = c.decoder_num_layers;
+  {
+    const AsrNormWeights& first = nd ? h->dec[0].norm1 : h->w.dec_norm;
+    if (int rc = launch_layernorm(w.h, first.gamma, first.beta, R, D, 1e-5f, nullptr, w.xn, s, g_split)) return rc;
+  }
+  for (int l = 0; l < nd; ++l) {
     const AsrDecoderLayerWeights& lw = h->dec[l];
-    if (int rc = launch_layernorm(w.h, lw.norm1.gamma, lw.norm1.beta, R, D, 1e-5f, nullptr, w.xn, s, g_split)) return rc;
-    if (int rc = self_attention_block(c, lw.self_attn, w.xn, w.qkv, w.att, w.h, B, L, 1, valid, nullptr, s)) return rc;
-    if (int rc = launch_layernorm(w.h, lw.norm2.gamma, lw.norm2.beta, R, D, 1e-5f, nullptr, w.xn, s, g_split)) return rc;
+    if (int rc = self_attention_block(c, lw.self_attn, w.xn, w.qkv, w.att, w.h, B, L, 1, valid, nullptr, s, &lw.norm2, w.xn))
+      return rc;
     const int sp = SP();
     {  // cross attention: q from the decoder stream, K/V precomputed from the encoder output; never masked
       GemmEpilogue e1;
@@ -626,13 +659,11 @@ int asr_decoder_forward(AsrHandle* h, const float* enc_out, int B, int Tp, const
       if (int rc = launch_attention_tc(a, s)) return rc;
       GemmEpilogue e2;
       e2.bias = lw.cross_attn.b_out; e2.residual = w.h; e2.ld_res = D; e2.out_f32 = w.h; e2.ld_f32 = D;
-      if (int rc = gemm(w.att, sp * D, lw.cross_attn.w_out, R, D, D, e2, s, g_split)) return rc;
+      if (int rc = gemm_ln(w.att, sp * D, lw.cross_attn.w_out, R, D, D, e2, lw.norm3, w.xn, nullptr, s, g_split)) return rc;
     }
-    if (int rc = launch_layernorm(w.h, lw.norm3.gamma, lw.norm3.beta, R, D, 1e-5f, nullptr, w.xn, s, g_split)) return rc;
-    if (int rc = ffn_block(c, lw.ffn, w.xn, w.ff, w.h, R, s)) return rc;
+    const bool last = l + 1 == nd;
+    if (int rc = ffn_block(c, lw.ffn, w.xn, w.ff, w.h, R, s, last ? &h->w.dec_norm : &h->dec[l + 1].norm1, w.xn)) return rc;
   }
-  if (int rc = launch_layernorm(w.h, h->w.dec_norm.gamma, h->w.dec_norm.beta, R, D, 1e-5f, nullptr, w.xn, s, g_split))
-    return rc;
   GemmEpilogue e;
   e.out_f32 = logits; e.ld_f32 = c.vocab_size; e.n_store = c.vocab_size;
   return gemm(w.xn, SP() * D, h->w.classifier_w, R, c.vocab_size, D, e, s, g_split);
@@ -937,6 +968,26 @@ int asr_gemm_split(const float* x, const void* w, const float* bias, int M, int 
     e.out_f16 = static_cast<f16*>(y_f16_hilo); e.ld_f16 = 2 * N; e.f16_lo_off = N;
   }
   return launch_gemm_tc(xs, 2 * K, static_cast<const f16*>(w), K, M, N, K, e, s, 1);
+}
+
+int asr_gemm_ln(const float* x, const void* w, const float* bias, const float* residual, const float* pe, int pe_period,
+                const float* gamma, const float* beta, int M, int N, int K, float* h_out, float* y_f32, void* y_f16_hilo,
+                void* ws, size_t ws_bytes, asr_stream_t stream) {
+  if (M == 0) return 0;
+  if (!x || !w || !gamma || !beta || (!y_f32 && !y_f16_hilo) || !ws || M < 0 || N <= 0 || K <= 0 || K % 8 != 0)
+    return set_error(ASR_E_INVALID, "asr_gemm_ln: bad argument");
+  if (ws_bytes < size_t(M) * K * 4) return set_error(ASR_E_WORKSPACE, "asr_gemm_ln: workspace < M * K * 4 bytes");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  f16* xs = static_cast<f16*>(ws);
+  if (int rc = launch_f32_to_f16_split(x, xs, size_t(M), K, s)) return rc;
+  GemmEpilogue e;
+  e.bias = bias; e.residual = residual; e.ld_res = N; e.rowvec = pe; e.rowvec_period = pe_period > 0 ? pe_period : 1;
+  e.ld_rowvec = N; e.out_f32 = h_out; e.ld_f32 = N;
+  LnEpilogue ln;
+  ln.gamma = gamma; ln.beta = beta; ln.out_f32 = y_f32; ln.out_f16 = static_cast<f16*>(y_f16_hilo); ln.split = 1;
+  const int rc = launch_gemm_ln(xs, 2 * K, static_cast<const f16*>(w), K, M, N, K, e, ln, s, 1);
+  if (rc == 1) return set_error(ASR_E_UNSUPPORTED, "asr_gemm_ln: only N == 256 with 16-byte aligned operands is fused");
+  return rc;
 }
 
 int asr_attention(const void* q, int ldq, long long q_bs, const void* k, int ldk, long long k_bs, const void* v,

@@ -401,6 +401,217 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogu
   return launch_inst<BN, STAGES, -1>(tmA, tmB, ep, M, n_store, n_pad, K, nkw, s);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Full-row GEMM + LayerNorm: one 128 x 256 output tile per CTA step holds WHOLE rows of the model dimension, so the
+// LayerNorm that follows every out projection / FFN / input projection of the pre-LN layers (model.py:20,23,52,67,70,73)
+// runs in the epilogue instead of in its own launch: pass 1 reads the accumulator, adds bias / positional encoding /
+// residual, stores the new residual row (fp32) and writes the value back to TMEM (tcgen05.st) while accumulating shifted
+// row statistics; the two column halves of a row (two warps) combine their (mean, M2) through shared memory (Chan's
+// formula); pass 2 re-reads TMEM, normalises and stores the next GEMM's A operand (fp16, hi | lo pair when split).
+// 48 KB per pipeline stage (A 128 x 64 + B 256 x 64), accumulator double-buffered: all 512 TMEM columns.
+constexpr int LN_BN = 256;
+constexpr int LN_B_STAGE = LN_BN * BK * 2;
+template <int STAGES>
+constexpr size_t gemm_ln_smem() {
+  return size_t(STAGES) * (A_STAGE_BYTES + LN_B_STAGE) + (2 * STAGES + 4) * 8 + 32 + 3 * LN_BN * 4 + 2 * BM * 2 * 8 + 1024;
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
+               LnEpilogue ln, int M, int K, int nkw, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * LN_B_STAGE);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~uintptr_t(15));   // [256]
+  float* sgamma = sbias + LN_BN;
+  float* sbeta = sgamma + LN_BN;
+  float2* sstat = reinterpret_cast<float2*>(sbeta + LN_BN);     // [tile parity][row][column half] (mean, M2)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nk = K / BK;
+
+  if (warp == EPI_WARPS + 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == EPI_WARPS) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 2 * LN_BN);
+    tmem_relinquish();
+  }
+  if (threadIdx.x < LN_BN) {
+    sbias[threadIdx.x] = ep.bias ? __ldg(ep.bias + threadIdx.x) : 0.f;
+    sgamma[threadIdx.x] = __ldg(ln.gamma + threadIdx.x);
+    sbeta[threadIdx.x] = __ldg(ln.beta + threadIdx.x);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == EPI_WARPS) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = tile * BM;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + LN_B_STAGE);
+          tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, &full_bar[s], kb * BK, m0);
+          tma_load_2d(sB + s * LN_B_STAGE, &tmB, &full_bar[s], (kb < nkw ? kb : kb - nkw) * BK, 0);   // a_split: W twice
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, LN_BN, 0, 0);
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t buf = lt & 1, use = lt >> 1;
+        mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * LN_BN;
+        for (int kb = 0; kb < nk; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(sA + s * A_STAGE_BYTES), 16, 1024);
+          const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(sB + s * LN_B_STAGE), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_ss(acc, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else {
+    // ---- epilogue: warp w -> TMEM lanes 32 (w % 4).., column half w / 4 (128 columns of the row)
+    const int quad = warp & 3, half = warp >> 2;
+    const int rl = quad * 32 + lane;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t buf = lt & 1, use = lt >> 1;
+      const int row = tile * BM + rl;
+      const bool live = row < M;
+      mbar_wait(&tmem_full[buf], use & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + buf * LN_BN + (uint32_t(quad * 32) << 16) + uint32_t(half * 128);
+      const float* pe_row = ep.rowvec ? ep.rowvec + size_t(row % ep.rowvec_period) * ep.ld_rowvec : nullptr;
+      float shift = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col = half * 128 + c * 32;
+        uint32_t r[32];
+        tmem_ld32(tacc + uint32_t(c * 32), r);
+        tmem_ld_wait();
+        float4 res[8], pe[8];
+        if (ep.residual && live) {
+          const float4* rp = reinterpret_cast<const float4*>(ep.residual + size_t(row) * ep.ld_res + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) res[j] = rp[j];
+        }
+        if (pe_row && live) {
+          const float4* pp = reinterpret_cast<const float4*>(pe_row + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pe[j] = __ldg(pp + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[4 * j + i]) + sbias[col + 4 * j + i];
+          if (ep.relu) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (pe_row && live) { v[0] += pe[j].x; v[1] += pe[j].y; v[2] += pe[j].z; v[3] += pe[j].w; }
+          if (ep.residual && live) { v[0] += res[j].x; v[1] += res[j].y; v[2] += res[j].z; v[3] += res[j].w; }
+          if (ep.out_f32 && live)
+            *reinterpret_cast<float4*>(ep.out_f32 + size_t(row) * ep.ld_f32 + col + 4 * j) = make_float4(v[0], v[1], v[2], v[3]);
+          if (c == 0 && j == 0) shift = v[0];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float d = v[i] - shift;
+            s1 += d;
+            s2 = fmaf(d, d, s2);
+            r[4 * j + i] = __float_as_uint(v[i]);
+          }
+        }
+        tmem_st32(tacc + uint32_t(c * 32), r);      // the finished row values go back to TMEM for the second pass
+      }
+      tmem_st_wait();
+      const float mean_h = shift + s1 * (1.0f / 128.0f);
+      const float m2_h = fmaxf(s2 - s1 * s1 * (1.0f / 128.0f), 0.f);
+      float2* st = sstat + (size_t(buf) * BM + rl) * 2;
+      st[half] = make_float2(mean_h, m2_h);
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      const float2 other = st[half ^ 1];
+      const float mean = 0.5f * (mean_h + other.x);
+      const float dm = mean_h - other.x;
+      const float var = (m2_h + other.y + dm * dm * 64.0f) * (1.0f / 256.0f);
+      const float rstd = 1.0f / sqrtf(var + ln.eps);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col = half * 128 + c * 32;
+        uint32_t r[32];
+        tmem_ld32(tacc + uint32_t(c * 32), r);
+        tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              y[i] = (__uint_as_float(r[8 * j + i]) - mean) * rstd * sgamma[col + 8 * j + i] + sbeta[col + 8 * j + i];
+            if (ln.out_f32) {
+              float* op = ln.out_f32 + size_t(row) * LN_BN + col + 8 * j;
+              *reinterpret_cast<float4*>(op) = make_float4(y[0], y[1], y[2], y[3]);
+              *reinterpret_cast<float4*>(op + 4) = make_float4(y[4], y[5], y[6], y[7]);
+            }
+            if (ln.out_f16) {
+              f16* op = ln.out_f16 + size_t(row) * (ln.split ? 2 * LN_BN : LN_BN) + col + 8 * j;
+              const uint4 hi = make_uint4(pack_f16x2(y[0], y[1]), pack_f16x2(y[2], y[3]), pack_f16x2(y[4], y[5]),
+                                          pack_f16x2(y[6], y[7]));
+              *reinterpret_cast<uint4*>(op) = hi;
+              if (ln.split)
+                *reinterpret_cast<uint4*>(op + LN_BN) =
+                    make_uint4(f16x2_residual(y[0], y[1], hi.x), f16x2_residual(y[2], y[3], hi.y),
+                               f16x2_residual(y[4], y[5], hi.z), f16x2_residual(y[6], y[7], hi.w));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 2 * LN_BN);
+}
+
 __global__ void gemm_naive_kernel(const f16* X, int ldx, const f16* W, int ldw, int M, int N, int K,
                                   GemmEpilogue ep) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
@@ -465,6 +676,53 @@ int launch_gemm_tc(const f16* X, int ldx, const f16* W, int ldw, int M, int N, i
       return launch_one<128, 3>(tmA, tmB, ep, M, n_store, n_pad, KA, K / BK, s);
     default: return launch_one<64, 8>(tmA, tmB, ep, M, n_store, n_pad, KA, K / BK, s);
   }
+}
+
+int launch_gemm_ln(const f16* X, int ldx, const f16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+                   const LnEpilogue& ln, cudaStream_t s, int a_split) {
+  if (M <= 0) return 0;
+  static const bool disabled = [] {
+    const char* e = std::getenv("ASR_B200_FUSE_LN");
+    return e && e[0] == '0';
+  }();
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (disabled || N != LN_BN || K % BK != 0 || K <= 0 || !ln.gamma || !ln.beta || (!ln.out_f16 && !ln.out_f32) ||
+      ep.out_f16 || (ep.n_store && ep.n_store != N) ||
+      (ep.residual && (ep.ld_res % 4 != 0 || !al16(ep.residual))) || (ep.out_f32 && (ep.ld_f32 % 4 != 0 || !al16(ep.out_f32))) ||
+      (ep.rowvec && (ep.ld_rowvec % 4 != 0 || !al16(ep.rowvec))) || !al16(ln.out_f16) || !al16(ln.out_f32))
+    return 1;
+  const int KA = a_split ? 2 * K : K;
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)KA, (uint64_t)M};
+    uint64_t str[2] = {2, (uint64_t)ldx * 2};
+    uint32_t box[2] = {BK, BM};
+    if (int rc = make_tmap_f16(&tmA, X, 2, dims, str, box, nullptr)) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)LN_BN};
+    uint64_t str[2] = {2, (uint64_t)ldw * 2};
+    uint32_t box[2] = {BK, (uint32_t)LN_BN};
+    if (int rc = make_tmap_f16(&tmB, W, 2, dims, str, box, nullptr)) return rc;
+  }
+  constexpr int STAGES = 4;
+  auto kern = gemm_ln_kernel<STAGES>;
+  constexpr size_t smem = gemm_ln_smem<STAGES>();
+  static int n_sm_dev[16] = {};          // per device ordinal (the function attribute is per device)
+  int dev = 0;
+  ASR_CUDA_OK(cudaGetDevice(&dev));
+  if (!n_sm_dev[dev & 15]) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int n_sm = 0;
+    ASR_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    n_sm_dev[dev & 15] = n_sm;
+  }
+  const int n_tiles = (M + BM - 1) / BM;
+  const int grid = n_tiles < n_sm_dev[dev & 15] ? n_tiles : n_sm_dev[dev & 15];
+  kern<<<grid, GEMM_THREADS, smem, s>>>(tmA, tmB, ep, ln, M, KA, K / BK, n_tiles);
+  ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
+  return 0;
 }
 
 int launch_gemm_naive(const f16* X, int ldx, const f16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,

@@ -50,6 +50,20 @@ struct GemmEpilogue {
 // fp16 tensor cores for twice the MMAs (the K loop runs over both halves, W is streamed twice).
 int launch_gemm_tc(const f16* X, int ldx, const f16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
                    cudaStream_t s, int a_split = 0);
+// Full-row GEMM with the LayerNorm that follows it fused into the epilogue (N == 256 only: one 128 x 256 tile holds whole
+// rows): h = X W^T + bias (+rowvec) (+residual) -> ep.out_f32; y = LayerNorm(h) * gamma + beta -> ln.out_f16 (hi | lo pair
+// when ln.split) and / or ln.out_f32.  Returns 1 (nothing launched) when the shape is unsupported: the caller then runs
+// launch_gemm_tc + launch_layernorm.  Replaces the nn.LayerNorm launches at model.py:20,23,52,67,70,73,122.
+struct LnEpilogue {
+  const float* gamma = nullptr;
+  const float* beta = nullptr;
+  float eps = 1e-5f;
+  f16* out_f16 = nullptr;      // [M, D] or, with split, [M, 2D] = [hi | lo]
+  int split = 0;
+  float* out_f32 = nullptr;    // [M, D]
+};
+int launch_gemm_ln(const f16* X, int ldx, const f16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
+                   const LnEpilogue& ln, cudaStream_t s, int a_split = 0);
 // Debug / cross-check: same contract, one thread per output element on CUDA cores.
 int launch_gemm_naive(const f16* X, int ldx, const f16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
                       cudaStream_t s);

@@ -86,6 +86,8 @@ _SIGNATURES = {
                               c_void_p, c_void_p, c_int, c_void_p]),
     "asr_gemm_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                c_size_t, c_void_p]),
+    "asr_gemm_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                            c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "asr_attention": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_int, c_longlong, c_void_p, c_int, c_longlong,
                               c_void_p, c_int, c_longlong, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

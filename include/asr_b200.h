@@ -203,6 +203,13 @@ int asr_gemm_f16(const void* x, const void* w, const float* bias, const float* r
  * y_f32 [M,N] and / or y_f16_hilo [M, 2N] = [hi | lo] of Y (the operand layout of a following split GEMM). */
 int asr_gemm_split(const float* x, const void* w, const float* bias, int M, int N, int K, int relu, float* y_f32,
                    void* y_f16_hilo, void* ws, size_t ws_bytes, asr_stream_t stream);
+/* The full-row GEMM with the following LayerNorm fused into its epilogue (the model path's replacement of every
+ * nn.LayerNorm launch but the first; N == 256 only, else ASR_E_UNSUPPORTED): h = x W^T + bias (+pe[row % period])
+ * (+residual) -> h_out fp32 [M,N] (nullable; may alias residual); y = LayerNorm(h) gamma + beta -> y_f32 [M,N] and / or
+ * y_f16_hilo [M,2N].  x fp32 [M,K] enters as an fp16 hi | lo pair (ws: M*K*4 bytes). */
+int asr_gemm_ln(const float* x, const void* w, const float* bias, const float* residual, const float* pe, int pe_period,
+                const float* gamma, const float* beta, int M, int N, int K, float* h_out, float* y_f32, void* y_f16_hilo,
+                void* ws, size_t ws_bytes, asr_stream_t stream);
 /* softmax(mask(q k^T * scale)) v per head (layers.py:20-27); q/k/v/out f16 with row strides ld* (elements) and
  * batch strides; head h lives at column h*64. Masks nullable. impl as above. */
 int asr_attention(const void* q, int ldq, long long q_bs, const void* k, int ldk, long long k_bs, const void* v,

@@ -140,6 +140,35 @@ def test_gemm_split_is_fp32_accurate(M, N, K, relu):
         assert_close(back, y32, 4e-6, 4e-7, "hi | lo output pair")
 
 
+@pytest.mark.parametrize("M,K,use_res,use_pe", [(300, 256, 1, 0), (1000, 1024, 1, 0), (515, 1216, 0, 1), (15936, 256, 1, 0),
+                                                (77, 64, 0, 0)])
+def test_gemm_ln_fused(M, K, use_res, use_pe):
+    """Full-row GEMM + fused LayerNorm epilogue (the replacement of the LayerNorm launches) against fp64 torch."""
+    N, period = 256, 249
+    x = rnd(M, K, seed=18, scale=1.5) + 0.2
+    w = rnd(N, K, seed=19, scale=K ** -0.5, dtype=torch.float16)
+    bias = rnd(N, seed=20)
+    res = (rnd(M, N, seed=21, scale=2.0) + 1.0) if use_res else None
+    pe = rnd(period, N, seed=22) if use_pe else None
+    g, b = rnd(N, seed=23) * 0.2 + 1.0, rnd(N, seed=24) * 0.1
+    h_out = torch.zeros(M, N, device=DEV)
+    y32 = torch.zeros(M, N, device=DEV)
+    y16 = torch.zeros(M, 2 * N, dtype=torch.float16, device=DEV)
+    ws = torch.empty(M * K * 4, dtype=torch.uint8, device=DEV)
+    L.check(lib().asr_gemm_ln(L.ptr(x), L.ptr(w), L.ptr(bias), L.ptr(res), L.ptr(pe), period, L.ptr(g), L.ptr(b), M, N, K,
+                              L.ptr(h_out), L.ptr(y32), L.ptr(y16), L.ptr(ws), ws.numel(), L.stream()), "gemm_ln")
+    sync()
+    h = x.double() @ w.double().t() + bias.double()
+    if use_pe:
+        h = h + pe.double().repeat((M + period - 1) // period, 1)[:M]
+    if use_res:
+        h = h + res.double()
+    ref = F.layer_norm(h, (N,), g.double(), b.double(), 1e-5)
+    assert_close(h_out, h.float(), 2e-5 * K ** 0.5, 2e-6 * K ** 0.5, "fused gemm: residual row")
+    assert_close(y32, ref.float(), 3e-5 * K ** 0.5, 3e-6 * K ** 0.5, "fused LayerNorm fp32")
+    assert_close(y16[:, :N].float() + y16[:, N:].float(), y32, 4e-6, 4e-7, "fused LayerNorm hi | lo")
+
+
 # ----------------------------------------------------------------------------------------------- attention core
 def attn_reference(q, k, v, scale, causal=False, k_lens=None, q_valid=None, k_valid=None, dense=None):
     """q (B,Sq,H,64) etc. fp32 math on the bf16 values; masked rows -> zeros (reference layers.py:20-27)."""
