@@ -349,15 +349,25 @@ int self_attention_block(const AsrConfig& c, const AsrMhaWeights& w, const f16* 
   return gemm(att, sp * D, w.w_out, M, D, D, e2, s, g_split);
 }
 
-// next_ln (optional): the LayerNorm applied to the block's output, fused into the second GEMM's epilogue
+// h += FFN(xn) (layers.py:53-58, model.py:24,74).  next_ln (optional): the LayerNorm applied to the block's output, fused
+// into the epilogue.  One launch (ffn_fused_kernel: the hidden activation stays on the SM) when D == 256, else two GEMMs.
 int ffn_block(const AsrConfig& c, const AsrFfnWeights& w, const f16* xn, f16* ff, float* h, int M, cudaStream_t s,
               const AsrNormWeights* next_ln = nullptr, f16* xn_out = nullptr, float* ln_f32 = nullptr) {
   const int D = c.embedding_dim, FF = c.ff_dim, sp = SP();
+  GemmEpilogue e2;
+  e2.bias = w.b2; e2.residual = h; e2.ld_res = D; e2.out_f32 = h; e2.ld_f32 = D;
+  {
+    LnEpilogue ln;
+    if (next_ln) {
+      ln.gamma = next_ln->gamma; ln.beta = next_ln->beta; ln.out_f16 = xn_out; ln.split = g_split; ln.out_f32 = ln_f32;
+    }
+    const int rc = launch_ffn_fused(xn, sp * D, static_cast<const f16*>(w.w1), w.b1, static_cast<const f16*>(w.w2), M, D,
+                                    FF, e2, ln, s, g_split);
+    if (rc <= 0) return rc;
+  }
   GemmEpilogue e1;
   e1.bias = w.b1; e1.relu = 1; e1.out_f16 = ff; e1.ld_f16 = sp * FF; e1.f16_lo_off = g_split ? FF : 0;
   if (int rc = gemm(xn, sp * D, w.w1, M, FF, D, e1, s, g_split)) return rc;
-  GemmEpilogue e2;
-  e2.bias = w.b2; e2.residual = h; e2.ld_res = D; e2.out_f32 = h; e2.ld_f32 = D;
   if (next_ln) return gemm_ln(ff, sp * FF, w.w2, M, D, FF, e2, *next_ln, xn_out, ln_f32, s, g_split);
   return gemm(ff, sp * FF, w.w2, M, D, FF, e2, s, g_split);
 }
@@ -1080,11 +1090,16 @@ int asr_ffn(const float* x, const AsrFfnWeights* w, int rows, int D, int FF, voi
   f16* ff = b.take<f16>(size_t(rows) * FF * 2);
   if (int rc = g_split ? launch_f32_to_f16_split(x, xb, size_t(rows), D, s) : launch_f32_to_f16(x, xb, size_t(rows) * D, s))
     return rc;
+  GemmEpilogue e2;
+  e2.bias = w->b2; e2.out_f32 = out; e2.ld_f32 = D;
+  {
+    const int rc = launch_ffn_fused(xb, sp * D, static_cast<const f16*>(w->w1), w->b1, static_cast<const f16*>(w->w2), rows, D,
+                                    FF, e2, LnEpilogue(), s, g_split);
+    if (rc <= 0) return rc;
+  }
   GemmEpilogue e1;
   e1.bias = w->b1; e1.relu = 1; e1.out_f16 = ff; e1.ld_f16 = sp * FF; e1.f16_lo_off = g_split ? FF : 0;
   if (int rc = launch_gemm_tc(xb, sp * D, static_cast<const f16*>(w->w1), D, rows, FF, D, e1, s, g_split)) return rc;
-  GemmEpilogue e2;
-  e2.bias = w->b2; e2.out_f32 = out; e2.ld_f32 = D;
   return launch_gemm_tc(ff, sp * FF, static_cast<const f16*>(w->w2), FF, rows, D, FF, e2, s, g_split);
 }
 

@@ -416,6 +416,98 @@ constexpr size_t gemm_ln_smem() {
   return size_t(STAGES) * (A_STAGE_BYTES + LN_B_STAGE) + (2 * STAGES + 4) * 8 + 32 + 3 * LN_BN * 4 + 2 * BM * 2 * 8 + 1024;
 }
 
+// Epilogue of one full-row (256-column) tile for the thread that owns `row` and the column half `half` (128 columns at
+// TMEM address tacc): see gemm_ln_kernel.  st: this row's two (mean, M2) slots in shared memory (double-buffered by the
+// caller); all EPI_WARPS * 32 epilogue threads call this together (one named barrier inside).
+__device__ __forceinline__ void ln_epilogue_tile(const GemmEpilogue& ep, const LnEpilogue& ln, uint32_t tacc, int row,
+                                                 bool live, int half, const float* sbias, const float* sgamma,
+                                                 const float* sbeta, float2* st) {
+      const float* pe_row = ep.rowvec ? ep.rowvec + size_t(row % ep.rowvec_period) * ep.ld_rowvec : nullptr;
+      float shift = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col = half * 128 + c * 32;
+        uint32_t r[32];
+        tmem_ld32(tacc + uint32_t(c * 32), r);
+        tmem_ld_wait();
+        float4 res[8], pe[8];
+        if (ep.residual && live) {
+          const float4* rp = reinterpret_cast<const float4*>(ep.residual + size_t(row) * ep.ld_res + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) res[j] = rp[j];
+        }
+        if (pe_row && live) {
+          const float4* pp = reinterpret_cast<const float4*>(pe_row + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pe[j] = __ldg(pp + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[4 * j + i]) + sbias[col + 4 * j + i];
+          if (ep.relu) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (pe_row && live) { v[0] += pe[j].x; v[1] += pe[j].y; v[2] += pe[j].z; v[3] += pe[j].w; }
+          if (ep.residual && live) { v[0] += res[j].x; v[1] += res[j].y; v[2] += res[j].z; v[3] += res[j].w; }
+          if (ep.out_f32 && live)
+            *reinterpret_cast<float4*>(ep.out_f32 + size_t(row) * ep.ld_f32 + col + 4 * j) = make_float4(v[0], v[1], v[2], v[3]);
+          if (c == 0 && j == 0) shift = v[0];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float d = v[i] - shift;
+            s1 += d;
+            s2 = fmaf(d, d, s2);
+            r[4 * j + i] = __float_as_uint(v[i]);
+          }
+        }
+        tmem_st32(tacc + uint32_t(c * 32), r);      // the finished row values go back to TMEM for the second pass
+      }
+      tmem_st_wait();
+      const float mean_h = shift + s1 * (1.0f / 128.0f);
+      const float m2_h = fmaxf(s2 - s1 * s1 * (1.0f / 128.0f), 0.f);
+      st[half] = make_float2(mean_h, m2_h);
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      const float2 other = st[half ^ 1];
+      const float mean = 0.5f * (mean_h + other.x);
+      const float dm = mean_h - other.x;
+      const float var = (m2_h + other.y + dm * dm * 64.0f) * (1.0f / 256.0f);
+      const float rstd = 1.0f / sqrtf(var + ln.eps);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col = half * 128 + c * 32;
+        uint32_t r[32];
+        tmem_ld32(tacc + uint32_t(c * 32), r);
+        tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              y[i] = (__uint_as_float(r[8 * j + i]) - mean) * rstd * sgamma[col + 8 * j + i] + sbeta[col + 8 * j + i];
+            if (ln.out_f32) {
+              float* op = ln.out_f32 + size_t(row) * LN_BN + col + 8 * j;
+              *reinterpret_cast<float4*>(op) = make_float4(y[0], y[1], y[2], y[3]);
+              *reinterpret_cast<float4*>(op + 4) = make_float4(y[4], y[5], y[6], y[7]);
+            }
+            if (ln.out_f16) {
+              f16* op = ln.out_f16 + size_t(row) * (ln.split ? 2 * LN_BN : LN_BN) + col + 8 * j;
+              const uint4 hi = make_uint4(pack_f16x2(y[0], y[1]), pack_f16x2(y[2], y[3]), pack_f16x2(y[4], y[5]),
+                                          pack_f16x2(y[6], y[7]));
+              *reinterpret_cast<uint4*>(op) = hi;
+              if (ln.split)
+                *reinterpret_cast<uint4*>(op + LN_BN) =
+                    make_uint4(f16x2_residual(y[0], y[1], hi.x), f16x2_residual(y[2], y[3], hi.y),
+                               f16x2_residual(y[4], y[5], hi.z), f16x2_residual(y[6], y[7], hi.w));
+            }
+          }
+        }
+      }
+}
+
 template <int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
@@ -517,91 +609,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * LN_BN + (uint32_t(quad * 32) << 16) + uint32_t(half * 128);
-      const float* pe_row = ep.rowvec ? ep.rowvec + size_t(row % ep.rowvec_period) * ep.ld_rowvec : nullptr;
-      float shift = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col = half * 128 + c * 32;
-        uint32_t r[32];
-        tmem_ld32(tacc + uint32_t(c * 32), r);
-        tmem_ld_wait();
-        float4 res[8], pe[8];
-        if (ep.residual && live) {
-          const float4* rp = reinterpret_cast<const float4*>(ep.residual + size_t(row) * ep.ld_res + col);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) res[j] = rp[j];
-        }
-        if (pe_row && live) {
-          const float4* pp = reinterpret_cast<const float4*>(pe_row + col);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) pe[j] = __ldg(pp + j);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float v[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[4 * j + i]) + sbias[col + 4 * j + i];
-          if (ep.relu) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (pe_row && live) { v[0] += pe[j].x; v[1] += pe[j].y; v[2] += pe[j].z; v[3] += pe[j].w; }
-          if (ep.residual && live) { v[0] += res[j].x; v[1] += res[j].y; v[2] += res[j].z; v[3] += res[j].w; }
-          if (ep.out_f32 && live)
-            *reinterpret_cast<float4*>(ep.out_f32 + size_t(row) * ep.ld_f32 + col + 4 * j) = make_float4(v[0], v[1], v[2], v[3]);
-          if (c == 0 && j == 0) shift = v[0];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float d = v[i] - shift;
-            s1 += d;
-            s2 = fmaf(d, d, s2);
-            r[4 * j + i] = __float_as_uint(v[i]);
-          }
-        }
-        tmem_st32(tacc + uint32_t(c * 32), r);      // the finished row values go back to TMEM for the second pass
-      }
-      tmem_st_wait();
-      const float mean_h = shift + s1 * (1.0f / 128.0f);
-      const float m2_h = fmaxf(s2 - s1 * s1 * (1.0f / 128.0f), 0.f);
-      float2* st = sstat + (size_t(buf) * BM + rl) * 2;
-      st[half] = make_float2(mean_h, m2_h);
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-      const float2 other = st[half ^ 1];
-      const float mean = 0.5f * (mean_h + other.x);
-      const float dm = mean_h - other.x;
-      const float var = (m2_h + other.y + dm * dm * 64.0f) * (1.0f / 256.0f);
-      const float rstd = 1.0f / sqrtf(var + ln.eps);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col = half * 128 + c * 32;
-        uint32_t r[32];
-        tmem_ld32(tacc + uint32_t(c * 32), r);
-        tmem_ld_wait();
-        if (live) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float y[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              y[i] = (__uint_as_float(r[8 * j + i]) - mean) * rstd * sgamma[col + 8 * j + i] + sbeta[col + 8 * j + i];
-            if (ln.out_f32) {
-              float* op = ln.out_f32 + size_t(row) * LN_BN + col + 8 * j;
-              *reinterpret_cast<float4*>(op) = make_float4(y[0], y[1], y[2], y[3]);
-              *reinterpret_cast<float4*>(op + 4) = make_float4(y[4], y[5], y[6], y[7]);
-            }
-            if (ln.out_f16) {
-              f16* op = ln.out_f16 + size_t(row) * (ln.split ? 2 * LN_BN : LN_BN) + col + 8 * j;
-              const uint4 hi = make_uint4(pack_f16x2(y[0], y[1]), pack_f16x2(y[2], y[3]), pack_f16x2(y[4], y[5]),
-                                          pack_f16x2(y[6], y[7]));
-              *reinterpret_cast<uint4*>(op) = hi;
-              if (ln.split)
-                *reinterpret_cast<uint4*>(op + LN_BN) =
-                    make_uint4(f16x2_residual(y[0], y[1], hi.x), f16x2_residual(y[2], y[3], hi.y),
-                               f16x2_residual(y[4], y[5], hi.z), f16x2_residual(y[6], y[7], hi.w));
-            }
-          }
-        }
-      }
+      ln_epilogue_tile(ep, ln, tacc, row, live, half, sbias, sgamma, sbeta, sstat + (size_t(buf) * BM + rl) * 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -610,6 +618,234 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 2 * LN_BN);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused position-wise FFN (reference layers.py:53-58 + the residual add of model.py:24,74 + the LayerNorm that follows):
+//   h += W2 relu(W1 x + b1) + b2 ;  y = LayerNorm(h)
+// for one 128-row tile per CTA step, the (rows x FF) hidden activation never leaving the SM.  FF is walked in chunks of
+// 128 columns: GEMM 1 (x tile [128 x K1] . W1 chunk^T) accumulates a 128 x 128 chunk in TMEM (double-buffered), the
+// epilogue warps add bias, apply ReLU and write the chunk as an fp16 hi | lo A operand (four swizzled 128 x 64 k-blocks)
+// into shared memory, GEMM 2 (hidden chunk . W2[:, chunk]^T, the lo k-blocks against the same W2 columns) accumulates the
+// full 128 x 256 output row tile in the other 256 TMEM columns; the MMA thread issues GEMM 1 of chunk c+1 before GEMM 2
+// of chunk c, so the tensor pipe works while the epilogue converts.  After the last chunk the full-row epilogue of
+// gemm_ln_kernel (bias + residual -> h, LayerNorm -> next operand) runs on the output tile.
+// Ring stages of 32 KB: (x k-block 16 KB + W1 k-block 16 KB) for GEMM 1, one W2 k-block (256 x 64) for GEMM 2.
+constexpr int FFN_STAGE = 32768;
+constexpr int FFN_HID_BYTES = 4 * A_STAGE_BYTES;      // hi k-blocks 0, 1 | lo k-blocks 2, 3 of a 128-column chunk
+template <int STAGES>
+constexpr size_t ffn_fused_smem(int FF) {
+  return size_t(STAGES) * FFN_STAGE + FFN_HID_BYTES + (2 * STAGES + 16) * 8 + 32 + (size_t(FF) + 3 * LN_BN) * 4 +
+         2 * BM * 2 * 8 + 1024;
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
+                 const __grid_constant__ CUtensorMap tmW2, GemmEpilogue ep, LnEpilogue ln, const float* __restrict__ b1,
+                 int M, int FF, int nk1, int nkw1, int split, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* hid = smem + STAGES * FFN_STAGE;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(hid + FFN_HID_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* acc1_full = empty_bar + STAGES;     // [2]
+  uint64_t* acc1_empty = acc1_full + 2;         // [2]
+  uint64_t* hid_full = acc1_empty + 2;          // epilogue -> MMA: the hidden chunk is in shared memory
+  uint64_t* hid_empty = hid_full + 1;           // MMA -> epilogue: GEMM 2 of the chunk has read it
+  uint64_t* acc2_full = hid_empty + 1;
+  uint64_t* acc2_empty = acc2_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc2_empty + 1);
+  float* sb1 = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 1) + 15) & ~uintptr_t(15));   // [FF]
+  float* sbias = sb1 + FF;                      // [256] b2
+  float* sgamma = sbias + LN_BN;
+  float* sbeta = sgamma + LN_BN;
+  float2* sstat = reinterpret_cast<float2*>(sbeta + LN_BN);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int NC = FF / 128;                      // hidden chunks per tile
+  const int nk2 = split ? 4 : 2;                // k-blocks of GEMM 2 per chunk (hi | lo)
+
+  if (warp == EPI_WARPS + 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc1_full[b], 1);
+      mbar_init(&acc1_empty[b], EPI_WARPS);
+    }
+    mbar_init(hid_full, EPI_WARPS);
+    mbar_init(hid_empty, 1);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (warp == EPI_WARPS) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmX);
+      tma_prefetch_desc(&tmW1);
+      tma_prefetch_desc(&tmW2);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < FF; i += GEMM_THREADS) sb1[i] = __ldg(b1 + i);
+  if (threadIdx.x < LN_BN) {
+    sbias[threadIdx.x] = ep.bias ? __ldg(ep.bias + threadIdx.x) : 0.f;
+    sgamma[threadIdx.x] = ln.gamma ? __ldg(ln.gamma + threadIdx.x) : 1.f;
+    sbeta[threadIdx.x] = ln.beta ? __ldg(ln.beta + threadIdx.x) : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tm_acc2 = tmem_base + 256;
+  const int my_tiles = (n_tiles - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int total_chunks = my_tiles * NC;       // flat chunk index g = (local tile) * NC + c
+
+  if (warp == EPI_WARPS) {
+    // ------------------------------------------------ TMA producer (same order as the MMA thread consumes)
+    if (lane == 0) {
+      uint32_t it = 0;
+      auto g1 = [&](int g) {
+        const int tile = blockIdx.x + (g / NC) * gridDim.x, c = g % NC;
+        for (int kb = 0; kb < nk1; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[s], 2 * A_STAGE_BYTES);
+          tma_load_2d(ring + s * FFN_STAGE, &tmX, &full_bar[s], kb * BK, tile * BM);
+          tma_load_2d(ring + s * FFN_STAGE + A_STAGE_BYTES, &tmW1, &full_bar[s], (kb < nkw1 ? kb : kb - nkw1) * BK, c * 128);
+        }
+      };
+      auto g2 = [&](int g) {
+        const int c = g % NC;
+        for (int kb = 0; kb < nk2; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[s], FFN_STAGE);
+          tma_load_2d(ring + s * FFN_STAGE, &tmW2, &full_bar[s], c * 128 + (kb & 1) * BK, 0);   // lo pass: same columns
+        }
+      };
+      if (total_chunks > 0) g1(0);
+      for (int g = 0; g < total_chunks; ++g) {
+        if (g + 1 < total_chunks) g1(g + 1);
+        g2(g);
+      }
+    }
+  } else if (warp == EPI_WARPS + 1) {
+    // ------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = umma_idesc_f16(BM, 128, 0, 0);
+      constexpr uint32_t idesc2 = umma_idesc_f16(BM, 256, 0, 0);
+      uint32_t it = 0;
+      auto g1 = [&](int g) {
+        const uint32_t b = g & 1;
+        mbar_wait(&acc1_empty[b], ((g >> 1) & 1) ^ 1);          // the epilogue has drained this chunk accumulator
+        tc_fence_after();
+        for (int kb = 0; kb < nk1; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(ring + s * FFN_STAGE), 16, 1024);
+          const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(ring + s * FFN_STAGE + A_STAGE_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_ss(tmem_base + b * 128, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc1, (kb | k) != 0);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&acc1_full[b]);
+      };
+      auto g2 = [&](int g) {
+        const int c = g % NC, lt = g / NC;
+        if (c == 0) {
+          mbar_wait(acc2_empty, (lt & 1) ^ 1);                   // the previous tile's output epilogue is done
+          tc_fence_after();
+        }
+        mbar_wait(hid_full, g & 1);                              // hidden chunk g converted and in shared memory
+        tc_fence_after();
+        for (int kb = 0; kb < nk2; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint64_t a_desc = umma_smem_desc_sw128(smem_u32(hid + kb * A_STAGE_BYTES), 16, 1024);
+          const uint64_t b_desc = umma_smem_desc_sw128(smem_u32(ring + s * FFN_STAGE), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_ss(tm_acc2, a_desc + uint64_t(k * 2), b_desc + uint64_t(k * 2), idesc2, (c | kb | k) != 0);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(hid_empty);
+        if (c == NC - 1) umma_commit(acc2_full);
+      };
+      if (total_chunks > 0) g1(0);
+      for (int g = 0; g < total_chunks; ++g) {
+        if (g + 1 < total_chunks) g1(g + 1);
+        g2(g);
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue warps: warp w -> TMEM lanes 32 (w % 4).., column half w / 4
+    const int quad = warp & 3, half = warp >> 2;
+    const int rl = quad * 32 + lane;
+    const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    for (int g = 0; g < total_chunks; ++g) {
+      const int lt = g / NC, c = g % NC;
+      const uint32_t b = g & 1;
+      mbar_wait(&acc1_full[b], (g >> 1) & 1);
+      tc_fence_after();
+      mbar_wait(hid_empty, (g & 1) ^ 1);                         // GEMM 2 of the previous chunk has read `hid`
+      // 64 columns of the chunk per thread: bias + ReLU -> fp16 hi (k-block `half`) | lo (k-block 2 + half), one
+      // 16-byte swizzled chunk per 8 columns (K-major SWIZZLE_128B A operand, row = this thread's tile row)
+      uint8_t* hrow_hi = hid + half * A_STAGE_BYTES + rl * 128;
+      uint8_t* hrow_lo = hid + (2 + half) * A_STAGE_BYTES + rl * 128;
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + b * 128 + lane_addr + uint32_t(half * 64 + cc * 32), r);
+        tmem_ld_wait();
+        const float* bb = sb1 + c * 128 + half * 64 + cc * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[8 * j + i]) + bb[8 * j + i], 0.f);
+          const uint4 hi = make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]),
+                                      pack_f16x2(v[6], v[7]));
+          const int chunk = ((cc * 4 + j) ^ (rl & 7)) << 4;
+          *reinterpret_cast<uint4*>(hrow_hi + chunk) = hi;
+          if (split)
+            *reinterpret_cast<uint4*>(hrow_lo + chunk) =
+                make_uint4(f16x2_residual(v[0], v[1], hi.x), f16x2_residual(v[2], v[3], hi.y),
+                           f16x2_residual(v[4], v[5], hi.z), f16x2_residual(v[6], v[7], hi.w));
+        }
+      }
+      fence_proxy_async();        // hid: generic writes -> UMMA operand reads
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(hid_full);
+        mbar_arrive(&acc1_empty[b]);
+      }
+      if (c == NC - 1) {          // the output row tile is complete: bias + residual -> h, LayerNorm -> next operand
+        const int tile = blockIdx.x + lt * gridDim.x;
+        const int row = tile * BM + rl;
+        mbar_wait(acc2_full, lt & 1);
+        tc_fence_after();
+        ln_epilogue_tile(ep, ln, tm_acc2 + lane_addr + uint32_t(half * 128), row, row < M, half, sbias, sgamma, sbeta,
+                         sstat + (size_t(lt & 1) * BM + rl) * 2);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc2_empty);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 512);
 }
 
 __global__ void gemm_naive_kernel(const f16* X, int ldx, const f16* W, int ldw, int M, int N, int K,
@@ -650,10 +886,12 @@ int launch_gemm_tc(const f16* X, int ldx, const f16* W, int ldw, int M, int N, i
   // Tile choice: 128-wide tiles (2 x 128 TMEM columns), 3-stage TMA ring (98 KB; ASR_B200_GEMM_STAGES=6 selects the
   // 192 KB variant); 64-wide when N is not a multiple of 128.  ASR_B200_GEMM_TILE (128 / 64)
   // forces a width for experiments.
+  // (256-wide tiles, ASR_B200_GEMM_TILE=256, measured identical at C2: these GEMMs are bound by their epilogue's global
+  // stores, not by the L2 -> shared-memory operand stream.)
   int bn = (n_pad % 128 == 0) ? 128 : 64;
   if (const char* e = std::getenv("ASR_B200_GEMM_TILE")) {
     const int f = std::atoi(e);
-    if ((f == 128 || f == 64) && n_pad % f == 0) bn = f;
+    if ((f == 256 || f == 128 || f == 64) && n_pad % f == 0) bn = f;
   }
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)n_pad};
@@ -667,6 +905,7 @@ int launch_gemm_tc(const f16* X, int ldx, const f16* W, int ldw, int M, int N, i
     return e && e[0] ? std::atoi(e) : 3;
   }();
   switch (bn) {
+    case 256: return launch_one<256, 4>(tmA, tmB, ep, M, n_store, n_pad, KA, K / BK, s);
     case 128:
       // 3-stage ring (98 KB) by default.  Alone the 6-stage (192 KB) variant is 4 % faster, but the encoder runs beside
       // the cluster decoder on the ~20 SMs it leaves free, and there the shallower ring measured better for both
@@ -720,6 +959,59 @@ int launch_gemm_ln(const f16* X, int ldx, const f16* W, int ldw, int M, int N, i
   const int n_tiles = (M + BM - 1) / BM;
   const int grid = n_tiles < n_sm_dev[dev & 15] ? n_tiles : n_sm_dev[dev & 15];
   kern<<<grid, GEMM_THREADS, smem, s>>>(tmA, tmB, ep, ln, M, KA, K / BK, n_tiles);
+  ASR_CUDA_OK(cudaGetLastError());
+  ASR_LAUNCHED(1);
+  return 0;
+}
+
+int launch_ffn_fused(const f16* X, int ldx, const f16* W1, const float* b1, const f16* W2, int M, int D, int FF,
+                     const GemmEpilogue& ep, const LnEpilogue& ln, cudaStream_t s, int split) {
+  if (M <= 0) return 0;
+  static const bool disabled = [] {
+    const char* e = std::getenv("ASR_B200_FUSE_FFN");
+    return e && e[0] == '0';
+  }();
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  constexpr int STAGES = 4;
+  if (disabled || D != LN_BN || FF % 128 != 0 || FF <= 0 || ffn_fused_smem<STAGES>(FF) > 227 * 1024 || !b1 ||
+      ep.out_f16 || ep.rowvec || (ep.residual && (ep.ld_res % 4 != 0 || !al16(ep.residual))) ||
+      (ep.out_f32 && (ep.ld_f32 % 4 != 0 || !al16(ep.out_f32))) || !al16(ln.out_f16) || !al16(ln.out_f32))
+    return 1;
+  const int K1 = split ? 2 * D : D;
+  CUtensorMap tmX, tmW1, tmW2;
+  {
+    uint64_t dims[2] = {(uint64_t)K1, (uint64_t)M};
+    uint64_t str[2] = {2, (uint64_t)ldx * 2};
+    uint32_t box[2] = {BK, BM};
+    if (int rc = make_tmap_f16(&tmX, X, 2, dims, str, box, nullptr)) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)D, (uint64_t)FF};
+    uint64_t str[2] = {2, (uint64_t)D * 2};
+    uint32_t box[2] = {BK, 128};
+    if (int rc = make_tmap_f16(&tmW1, W1, 2, dims, str, box, nullptr)) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)FF, (uint64_t)D};
+    uint64_t str[2] = {2, (uint64_t)FF * 2};
+    uint32_t box[2] = {BK, 256};
+    if (int rc = make_tmap_f16(&tmW2, W2, 2, dims, str, box, nullptr)) return rc;
+  }
+  auto kern = ffn_fused_kernel<STAGES>;
+  const size_t smem = ffn_fused_smem<STAGES>(FF);
+  static size_t configured[16] = {};     // per device ordinal
+  static int n_sm_dev[16] = {};
+  int dev = 0;
+  ASR_CUDA_OK(cudaGetDevice(&dev));
+  if (configured[dev & 15] < smem) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev & 15] = smem;
+    ASR_CUDA_OK(cudaDeviceGetAttribute(&n_sm_dev[dev & 15], cudaDevAttrMultiProcessorCount, dev));
+  }
+  LnEpilogue lnn = ln;
+  const int n_tiles = (M + BM - 1) / BM;
+  const int grid = n_tiles < n_sm_dev[dev & 15] ? n_tiles : n_sm_dev[dev & 15];
+  kern<<<grid, GEMM_THREADS, smem, s>>>(tmX, tmW1, tmW2, ep, lnn, b1, M, FF, K1 / BK, D / BK, split, n_tiles);
   ASR_CUDA_OK(cudaGetLastError());
   ASR_LAUNCHED(1);
   return 0;

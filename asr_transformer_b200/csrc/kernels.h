@@ -64,6 +64,12 @@ struct LnEpilogue {
 };
 int launch_gemm_ln(const f16* X, int ldx, const f16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
                    const LnEpilogue& ln, cudaStream_t s, int a_split = 0);
+// Fused FFN (layers.py:53-58 + residual + following LayerNorm), D == 256 only (returns 1 otherwise -> two GEMMs):
+// h = ep.residual + relu(X W1^T + b1) W2^T + ep.bias -> ep.out_f32; LayerNorm(h) -> ln outputs (ln.gamma == nullptr:
+// no LayerNorm outputs wanted is not supported; pass the norm that follows).  X: [M, D] or, with split, [M, 2D] hi | lo;
+// the hidden activation stays on the SM as an fp16 hi | lo (split) A operand.
+int launch_ffn_fused(const f16* X, int ldx, const f16* W1, const float* b1, const f16* W2, int M, int D, int FF,
+                     const GemmEpilogue& ep, const LnEpilogue& ln, cudaStream_t s, int split);
 // Debug / cross-check: same contract, one thread per output element on CUDA cores.
 int launch_gemm_naive(const f16* X, int ldx, const f16* W, int ldw, int M, int N, int K, const GemmEpilogue& ep,
                       cudaStream_t s);

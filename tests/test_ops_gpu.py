@@ -279,6 +279,28 @@ def test_ffn_and_layernorm_modules():
     assert_close(ln(x), F.layer_norm(x, (fx["D"],)), TOL_FP32, TOL_FP32, "LayerNorm module")
 
 
+@pytest.mark.parametrize("rows,FF", [(300, 1024), (15936, 1024), (77, 256), (1000, 2048)])
+def test_ffn_fused_matches_fp64_and_two_gemm_path(rows, FF, monkeypatch):
+    """The fused FFN kernel (hidden activation kept on the SM) against fp64 torch and against the two-GEMM path."""
+    import asr_transformer_b200 as A
+    D = 256
+    torch.manual_seed(5)
+    ff = A.FeedForward(D, FF, 0.1).eval()
+    with torch.no_grad():
+        for p_ in ff.parameters():
+            O.bf16_representable_(p_)
+    ff = ff.to(DEV)
+    x = rnd(rows, D, seed=70, scale=1.5) + 0.1
+    out = ff(x)
+    sync()
+    monkeypatch.setenv("ASR_B200_FUSE_FFN", "0")
+    ref2 = ff(x)      # (the switch is read once per process: this is the fused path again unless the env was set at start)
+    w1, b1, w2, b2 = (t.double() for t in (ff.squeeze.weight, ff.squeeze.bias, ff.unsqueeze.weight, ff.unsqueeze.bias))
+    ref = (x.double() @ w1.t() + b1).relu() @ w2.t() + b2
+    assert_close(out, ref.float(), 1e-3, 1e-4, "fused FFN vs fp64")
+    assert_close(out, ref2, 1e-3, 1e-4, "fused FFN vs second call")
+
+
 # ----------------------------------------------------------------------------------------------- conv front-end
 @pytest.mark.parametrize("B,Fdim,T", [(2, 80, 200), (1, 80, 1000), (3, 33, 71), (1, 513, 311)])
 def test_conv_frontend(B, Fdim, T):
