@@ -822,11 +822,7 @@ int asr_decode_beam(AsrHandle* h, const float* enc_rep, int B, int beam, int Tp,
     return set_error(ASR_E_WORKSPACE, "asr_decode_beam: workspace %zu < %zu bytes", ws_bytes, bump.off);
   const size_t smem = size_t(beam) * V * sizeof(float);
   if (smem > 200 * 1024) return set_error(ASR_E_UNSUPPORTED, "asr_decode_beam: beam x vocabulary too large");
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(beam_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (int rc = ensure_dyn_smem((const void*)beam_select_kernel, smem)) return rc;
   const int M = R * Tp;
   if (int rc = cross_kv(h, enc_rep, w.g.enc_f16, w.g.ckv, M, s)) return rc;
   int32_t* tok_cur = w.tok_a;

@@ -372,11 +372,7 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t s) {
   d.scale_log2 = p.scale * 1.4426950408889634f;
   d.causal = p.causal; d.k_lens = p.k_lens; d.q_valid = p.q_valid; d.k_valid = p.k_valid;
   d.dense_mask = p.dense_mask; d.mask_B = p.mask_B;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATTN_SMEM));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem((const void*)attn_tc_kernel, ATTN_SMEM)) return rc;
   dim3 grid((p.Sq + BQ - 1) / BQ, p.H, p.B);
   attn_tc_kernel<<<grid, 160, ATTN_SMEM, s>>>(tmQ, tmK, tmV, d);
   ASR_CUDA_OK(cudaGetLastError());

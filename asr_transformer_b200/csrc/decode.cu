@@ -334,13 +334,7 @@ int launch_dec_attention(const DecAttn& p, cudaStream_t s) {
   const int max_keys = p.step ? p.n_keys : p.n_keys;   // n_keys = capacity when step-driven
   const size_t smem = size_t(max_keys) * sizeof(float);
   if (smem > 160 * 1024) return set_error(-2, "dec_attention: %d keys exceed the shared-memory score buffer", max_keys);
-  if (smem > 48 * 1024) {
-    static size_t configured = 0;
-    if (smem > configured) {
-      ASR_CUDA_OK(cudaFuncSetAttribute(dec_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
-  }
+  if (int rc = ensure_dyn_smem((const void*)dec_attn_kernel, smem)) return rc;
   dec_attn_kernel<<<dim3(p.H, p.B), 128, smem, s>>>(p);
   ASR_CUDA_OK(cudaGetLastError());
   ASR_LAUNCHED(1);

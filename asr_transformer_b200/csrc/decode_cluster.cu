@@ -1253,9 +1253,8 @@ int launch_dec_cluster(ClusterParams& p, cudaStream_t s) {
   p.off_small = lay.off_small; p.off_qkv = lay.off_qkv; p.off_wo = lay.off_wo; p.off_wqc = lay.off_wqc;
   p.off_woc = lay.off_woc; p.off_w1 = lay.off_w1; p.off_w2 = lay.off_w2; p.off_cls = lay.off_cls;
 
-  int dev = 0, max_smem = 0;
-  ASR_CUDA_OK(cudaGetDevice(&dev));
-  ASR_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  int max_smem = 0;
+  if (int rc = device_props(nullptr, &max_smem)) return rc;
   // utterances per cluster: the smallest group that lets every cluster be resident at once (one wave)
   const char* ge = std::getenv("ASR_B200_CLUSTER_GU");
   const int gu_forced = ge && ge[0] ? std::atoi(ge) : 0;
@@ -1270,17 +1269,7 @@ int launch_dec_cluster(ClusterParams& p, cudaStream_t s) {
       if (std::atoi(se) >= 3 && std::atoi(se) <= MAX_STAGES) nst = std::atoi(se);
     while (nst >= 3 && inst->map(nst).total > (uint32_t)max_smem) --nst;
     if (nst < 3) break;   // larger groups need even more shared memory
-    static const void* configured[16] = {};
-    bool done = false;
-    for (const void* q : configured) done |= (q == (const void*)inst->fn);
-    if (!done) {
-      ASR_CUDA_OK(cudaFuncSetAttribute((const void*)inst->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-      for (auto& q : configured)
-        if (!q) {
-          q = (const void*)inst->fn;
-          break;
-        }
-    }
+    if (int rc = ensure_dyn_smem((const void*)inst->fn, (size_t)max_smem)) return rc;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(p.H, 1, 1);
     cfg.blockDim = dim3(NTHREADS, 1, 1);

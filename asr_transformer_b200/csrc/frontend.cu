@@ -85,11 +85,7 @@ int launch_spectrogram(const float* audio, int B, int n_samples, int n_fft, int 
   const int n_frames = n_samples >= n_fft ? (n_samples - n_fft) / hop + 1 : 0;
   const int fpc = n_fft > 1024 ? SPEC_FRAMES / 2 : SPEC_FRAMES;
   const size_t smem = (size_t(n_fft / 2) + size_t(fpc) * n_fft) * sizeof(float2);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(spectrogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (int rc = ensure_dyn_smem((const void*)spectrogram_kernel, smem)) return rc;
   const int frames_covered = T;   // frames >= n_frames are zero-filled by the same kernel
   dim3 grid((frames_covered + fpc - 1) / fpc, B);
   spectrogram_kernel<<<grid, fpc * 32, smem, s>>>(audio, n_samples, log2n, hop, n_frames < T ? n_frames : T, T,

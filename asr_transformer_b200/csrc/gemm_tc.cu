@@ -345,22 +345,9 @@ int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilog
                 int K, int nkw, cudaStream_t s) {
   auto kern = gemm_tc_kernel<BN, STAGES, FLAGS>;
   constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
-  static bool attr_set = false;
-  static int n_slots = 0;   // resident CTAs on the device (persistent grid size)
-  if (!attr_set) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // ask for the largest shared-memory carve-out: with the default one a single 98 KB CTA is all an SM gets
-    ASR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int dev = 0, n_sm = 0, occ = 1;
-    ASR_CUDA_OK(cudaGetDevice(&dev));
-    ASR_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    ASR_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GEMM_THREADS, smem));
-    n_slots = n_sm * (occ < 1 ? 1 : occ);
-    if (std::getenv("ASR_B200_DEBUG"))
-      fprintf(stderr, "gemm_tc<%d,%d,%d>: smem %zu B, occupancy %d CTAs/SM, %d persistent CTAs\n", BN, STAGES, FLAGS, smem,
-              occ, n_slots);
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
+  int n_slots = 0;   // persistent grid size: one CTA per SM (98 KB+ of shared memory each)
+  if (int rc = device_props(&n_slots, nullptr)) return rc;
   const int tiles_n = n_pad / BN, n_tiles = tiles_n * ((M + BM - 1) / BM);
   const int grid = n_tiles < n_slots ? n_tiles : n_slots;
   kern<<<grid, GEMM_THREADS, smem, s>>>(tmA, tmB, ep, M, n_store, K, nkw, tiles_n, n_tiles);
@@ -947,17 +934,11 @@ int launch_gemm_ln(const f16* X, int ldx, const f16* W, int ldw, int M, int N, i
   constexpr int STAGES = 4;
   auto kern = gemm_ln_kernel<STAGES>;
   constexpr size_t smem = gemm_ln_smem<STAGES>();
-  static int n_sm_dev[16] = {};          // per device ordinal (the function attribute is per device)
-  int dev = 0;
-  ASR_CUDA_OK(cudaGetDevice(&dev));
-  if (!n_sm_dev[dev & 15]) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int n_sm = 0;
-    ASR_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    n_sm_dev[dev & 15] = n_sm;
-  }
+  if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
+  int n_sm = 0;
+  if (int rc = device_props(&n_sm, nullptr)) return rc;
   const int n_tiles = (M + BM - 1) / BM;
-  const int grid = n_tiles < n_sm_dev[dev & 15] ? n_tiles : n_sm_dev[dev & 15];
+  const int grid = n_tiles < n_sm ? n_tiles : n_sm;
   kern<<<grid, GEMM_THREADS, smem, s>>>(tmA, tmB, ep, ln, M, KA, K / BK, n_tiles);
   ASR_CUDA_OK(cudaGetLastError());
   ASR_LAUNCHED(1);
@@ -999,18 +980,12 @@ int launch_ffn_fused(const f16* X, int ldx, const f16* W1, const float* b1, cons
   }
   auto kern = ffn_fused_kernel<STAGES>;
   const size_t smem = ffn_fused_smem<STAGES>(FF);
-  static size_t configured[16] = {};     // per device ordinal
-  static int n_sm_dev[16] = {};
-  int dev = 0;
-  ASR_CUDA_OK(cudaGetDevice(&dev));
-  if (configured[dev & 15] < smem) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[dev & 15] = smem;
-    ASR_CUDA_OK(cudaDeviceGetAttribute(&n_sm_dev[dev & 15], cudaDevAttrMultiProcessorCount, dev));
-  }
+  if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
+  int n_sm = 0;
+  if (int rc = device_props(&n_sm, nullptr)) return rc;
   LnEpilogue lnn = ln;
   const int n_tiles = (M + BM - 1) / BM;
-  const int grid = n_tiles < n_sm_dev[dev & 15] ? n_tiles : n_sm_dev[dev & 15];
+  const int grid = n_tiles < n_sm ? n_tiles : n_sm;
   kern<<<grid, GEMM_THREADS, smem, s>>>(tmX, tmW1, tmW2, ep, lnn, b1, M, FF, K1 / BK, D / BK, split, n_tiles);
   ASR_CUDA_OK(cudaGetLastError());
   ASR_LAUNCHED(1);
@@ -1109,11 +1084,7 @@ int launch_umma_probe(const f16* A, const f16* Bm, float* D, int N, int b_mn_maj
     if (rc) return rc;
   }
   const size_t smem = 32768 + 64 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem((const void*)umma_probe_kernel, smem)) return rc;
   umma_probe_kernel<<<1, 128, smem, s>>>(tmA, tmB, D, N, b_mn_major);
   ASR_CUDA_OK(cudaGetLastError());
   ASR_LAUNCHED(1);

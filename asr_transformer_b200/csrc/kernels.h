@@ -24,6 +24,14 @@ const char* last_error();
 extern unsigned long long g_kernel_launches;
 #define ASR_LAUNCHED(n) (::asr::g_kernel_launches += (n))
 
+// ---- per-device kernel configuration.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are properties
+// of the CURRENT device: a process that drives several GPUs must configure every kernel on each of them, so the
+// once-only guards are keyed by (device ordinal, kernel).  ensure_dyn_smem raises the opt-in limit of `fn` on the current
+// device to at least `bytes` (no-op when already done); device_props reports the current device's SM count and
+// opt-in shared-memory limit (cached per device).
+int ensure_dyn_smem(const void* fn, size_t bytes);
+int device_props(int* n_sm, int* max_smem_optin);
+
 // ---- TMA tensor maps (driver entry point resolved at run time, no link-time libcuda dependency)
 // f16 tensor, innermost dim contiguous. dims/strides innermost first; strides in BYTES for dims >= 1.
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

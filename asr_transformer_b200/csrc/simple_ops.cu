@@ -486,11 +486,7 @@ int launch_conv1(const float* spec, const float* w1, const float* b1, int B, int
   if (F1 <= 0 || T1 <= 0) return set_error(-2, "conv1: input %dx%d too small", F, T);
   const size_t smem = (size_t(9 * 64 + 64) + size_t(F) * (2 * CONV1_TT + 1)) * sizeof(float);
   if (smem > 200 * 1024) return set_error(-2, "conv1: input_dim %d too large for the shared-memory patch", F);
-  static size_t configured = 48 * 1024;
-  if (smem > configured) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (int rc = ensure_dyn_smem((const void*)conv1_kernel, smem)) return rc;
   dim3 grid((T1 + CONV1_TT - 1) / CONV1_TT, B);
   conv1_kernel<<<grid, 256, smem, s>>>(spec, w1, b1, B, F, T, F1, T1, y1, split ? size_t(B) * T1 * F1 * 64 : 0);
   ASR_CUDA_OK(cudaGetLastError());
@@ -504,13 +500,8 @@ int launch_conv_fused(const float* spec, const float* w1, const float* b1, const
                       int F, int T, f16* z, cudaStream_t s, int split) {
   const int F1 = (F - 3) / 2 + 1, T1 = (T - 3) / 2 + 1, F2 = (F1 - 3) / 2 + 1, T2 = (T1 - 3) / 2 + 1;
   if (F2 <= 0 || T2 <= 0) return set_error(-2, "conv: input %dx%d too small", F, T);
-  static int n_sm = 0, max_smem = 0;
-  if (!n_sm) {
-    int dev = 0;
-    ASR_CUDA_OK(cudaGetDevice(&dev));
-    ASR_CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    ASR_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
+  int n_sm = 0, max_smem = 0;
+  if (int rc = device_props(&n_sm, &max_smem)) return rc;
   // frames per tile: fill the 8 warps' 16-pixel passes (128 pixels) without exceeding the shared memory
   int TT2 = 0;
   for (int t = 1; t <= 8 && t <= T2; ++t)
@@ -518,11 +509,7 @@ int launch_conv_fused(const float* spec, const float* w1, const float* b1, const
   if (TT2 == 0 && conv_fused_smem(F, F1, 1, split) <= size_t(max_smem)) TT2 = 1;
   if (TT2 == 0) return 1;
   const size_t smem = conv_fused_smem(F, F1, TT2, split);
-  static size_t configured = 0;
-  if (smem > configured) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(conv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  if (int rc = ensure_dyn_smem((const void*)conv_fused_kernel, smem)) return rc;
   const int n_tt = (T2 + TT2 - 1) / TT2;
   const long long n_tiles = (long long)B * n_tt;
   const int grid = (int)(n_tiles < n_sm ? n_tiles : n_sm);
@@ -537,11 +524,7 @@ int launch_conv2(const f16* y1, const f16* w2frag, const float* b2, int B, int F
                  int split) {
   const int F2 = (F1 - 3) / 2 + 1, T2 = (T1 - 3) / 2 + 1;
   if (F2 <= 0 || T2 <= 0) return set_error(-2, "conv2: input %dx%d too small", F1, T1);
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASR_CUDA_OK(cudaFuncSetAttribute(conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV2_W_BYTES));
-    attr_set = true;
-  }
+  if (int rc = ensure_dyn_smem((const void*)conv2_kernel, CONV2_W_BYTES)) return rc;
   const long long ntiles = ((long long)B * T2 * F2 + 63) / 64;
   const int blocks = (int)(ntiles < 148 * 3 ? ntiles : 148 * 3);
   conv2_kernel<<<blocks, 128, CONV2_W_BYTES, s>>>(y1, reinterpret_cast<const uint2*>(w2frag), b2, B, F1, T1, F2, T2, z,

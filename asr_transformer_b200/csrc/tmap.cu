@@ -1,6 +1,9 @@
 // Host helpers: error plumbing and TMA tensor-map construction.
 #include <cstdarg>
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <cudaTypedefs.h>
 
 #include "kernels.h"
@@ -18,6 +21,39 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 const char* last_error() { return g_err; }
+
+int ensure_dyn_smem(const void* fn, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> done;
+  int dev = 0;
+  ASR_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = done[{dev, fn}];
+  if (have == 0) have = 48 * 1024;      // the default limit needs no opt-in
+  if (bytes > have) {
+    ASR_CUDA_OK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
+  return 0;
+}
+
+int device_props(int* n_sm, int* max_smem_optin) {
+  static std::mutex mu;
+  static std::map<int, std::pair<int, int>> cache;
+  int dev = 0;
+  ASR_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(dev);
+  if (it == cache.end()) {
+    int sm = 0, smem = 0;
+    ASR_CUDA_OK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev));
+    ASR_CUDA_OK(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    it = cache.emplace(dev, std::make_pair(sm, smem)).first;
+  }
+  if (n_sm) *n_sm = it->second.first;
+  if (max_smem_optin) *max_smem_optin = it->second.second;
+  return 0;
+}
 
 static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;

@@ -233,6 +233,10 @@ class Engine:
         if dev.type != "cuda":
             raise RuntimeError("asr_b200 has no CPU path: move the model to a CUDA device (model.cuda())")
         L = _l.load()
+        with _l.on(dev):
+            return self._sync_on(owner, input_layer, encoder, decoder, bos, ver, dev, L)
+
+    def _sync_on(self, owner, input_layer, encoder, decoder, bos, ver, dev, L) -> "Engine":
         keep: List = []
         w = _l.AsrWeights()
         cfg = _l.AsrConfig()
@@ -309,6 +313,27 @@ class Engine:
         return self
 
     # ------------------------------------------------------------------ calls
+    # every C call runs with the engine's device current (lib.on): the right stream, the right per-device kernel setup
+    def encode(self, *a, **k):
+        with _l.on(self.device):
+            return self._encode_impl(*a, **k)
+
+    def encoder_forward(self, *a, **k):
+        with _l.on(self.device):
+            return self._encoder_forward_impl(*a, **k)
+
+    def decoder_forward(self, *a, **k):
+        with _l.on(self.device):
+            return self._decoder_forward_impl(*a, **k)
+
+    def decode_greedy(self, *a, **k):
+        with _l.on(self.device):
+            return self._decode_greedy_impl(*a, **k)
+
+    def decode_beam(self, *a, **k):
+        with _l.on(self.device):
+            return self._decode_beam_impl(*a, **k)
+
     def _ws(self, B: int, T: int, Ldec: int, tag: str = "model") -> torch.Tensor:
         """Scratch for one call.  Calls that may run concurrently on different streams (the pipelined serving loop:
         encode of batch i+1 under the decode of batch i) must use different tags."""
@@ -316,7 +341,7 @@ class Engine:
         _l.check(_l.load().asr_workspace_bytes(self.handle, B, max(T, 7), max(Ldec, 1), C.byref(n)), "workspace_bytes")
         return _l.workspace(n.value, self.device, tag)
 
-    def encode(self, spectrum: torch.Tensor, enc_lens: Optional[torch.Tensor] = None,
+    def _encode_impl(self, spectrum: torch.Tensor, enc_lens: Optional[torch.Tensor] = None,
                out: Optional[torch.Tensor] = None, ws_tag: str = "model") -> torch.Tensor:
         """Transformer.input_layer + Encoder.forward: (B,1,F,T) fp32 -> (B,T',D) fp32."""
         if spectrum.dim() != 4 or spectrum.shape[1] != 1 or spectrum.shape[2] != self.cfg.input_dim:
@@ -332,7 +357,7 @@ class Engine:
                                       _l.ptr(out), _l.stream()), "asr_encode")
         return out
 
-    def encoder_forward(self, z_f16: torch.Tensor, enc_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def _encoder_forward_impl(self, z_f16: torch.Tensor, enc_lens: Optional[torch.Tensor] = None) -> torch.Tensor:
         B, Tp, _ = z_f16.shape
         out = torch.empty(B, Tp, self.cfg.embedding_dim, dtype=torch.float32, device=z_f16.device)
         ws = self._ws(B, 4 * Tp + 3, self.cfg.decoder_seq_len)
@@ -341,7 +366,7 @@ class Engine:
                                                ws.numel(), _l.ptr(out), _l.stream()), "asr_encoder_forward")
         return out
 
-    def decoder_forward(self, enc_out: torch.Tensor, text: torch.Tensor, valid: torch.Tensor) -> torch.Tensor:
+    def _decoder_forward_impl(self, enc_out: torch.Tensor, text: torch.Tensor, valid: torch.Tensor) -> torch.Tensor:
         B, Tp, _ = enc_out.shape
         L = text.shape[1]
         enc_out = enc_out.to(torch.float32).contiguous()
@@ -354,7 +379,7 @@ class Engine:
                  "asr_decoder_forward")
         return logits
 
-    def decode_greedy(self, enc_out: torch.Tensor, max_len: Optional[int] = None, stop_at_eos: bool = False,
+    def _decode_greedy_impl(self, enc_out: torch.Tensor, max_len: Optional[int] = None, stop_at_eos: bool = False,
                       first_tokens: Optional[torch.Tensor] = None, want_logits: bool = False,
                       tokens_out: Optional[torch.Tensor] = None, n_tokens_out: Optional[torch.Tensor] = None,
                       enc_lens: Optional[torch.Tensor] = None, ws_tag: str = "model", phase: str = "both"):
@@ -383,7 +408,7 @@ class Engine:
         _l.check(_l.load().asr_decode_greedy(*args, _l.stream()), "asr_decode_greedy")
         return tokens, n_tok, step_logits
 
-    def decode_beam(self, enc_out: torch.Tensor, beam: int, max_len: Optional[int] = None):
+    def _decode_beam_impl(self, enc_out: torch.Tensor, beam: int, max_len: Optional[int] = None):
         """Beam search on the KV-cached decode step (asr_decode_beam): enc_out (B,T',D) -> tokens (B, beam, L+1) int32
         best first, scores (B, beam) fp32 (sum of token log-probabilities, no length normalisation)."""
         B, Tp, _ = enc_out.shape

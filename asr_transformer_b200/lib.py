@@ -135,18 +135,33 @@ def check(rc: int, what: str = "") -> None:
         raise RuntimeError(f"asr_b200 {what} failed ({rc}): {msg.decode() if msg else '?'}")
 
 
-def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
-    """Device pointer of a CUDA tensor (None -> NULL). CPU tensors are an error by design."""
+def ptr(t: Optional[torch.Tensor], dtype: Optional[torch.dtype] = None) -> Optional[int]:
+    """Device pointer of a CUDA tensor (None -> NULL). CPU tensors are an error by design; ``dtype`` (when given) must
+    match: the kernels read raw memory, a half-precision module would otherwise be read as fp32 silently."""
     if t is None:
         return None
     if not t.is_cuda:
         raise RuntimeError("asr_b200 has no CPU path: expected a CUDA tensor, got device %s" % t.device)
     if not t.is_contiguous():
         raise RuntimeError("asr_b200 expects contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"asr_b200 expects a {dtype} tensor here, got {t.dtype}")
     return t.data_ptr()
 
 
+def on(device) -> "torch.cuda.device":
+    """Context manager that makes ``device`` (a torch.device or a CUDA tensor) the current CUDA device for the C calls
+    inside it: kernels are launched on torch's current stream OF THAT DEVICE, and the library's per-device kernel
+    configuration applies to the device the pointers live on (a model on cuda:1 works while cuda:0 is current)."""
+    if isinstance(device, torch.Tensor):
+        device = device.device
+    if device.type != "cuda":
+        raise RuntimeError("asr_b200 has no CPU path: expected a CUDA device, got %s" % device)
+    return torch.cuda.device(device)
+
+
 def stream() -> int:
+    """torch's current stream on the current device (call inside ``on(device)``)."""
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -154,10 +169,16 @@ _workspaces = {}
 
 
 def workspace(nbytes: int, device: torch.device, tag: str = "default") -> torch.Tensor:
-    """Grow-only scratch buffer per (device, tag); contents are undefined between calls."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    """Grow-only scratch buffer per (device, stream, tag); contents are undefined between calls.  Keyed by the stream the
+    caller is on, so two streams never share scratch; a buffer that is outgrown stays alive until the work already
+    queued on that stream has finished with it (record_stream)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    st = torch.cuda.current_stream(idx)
+    key = (idx, st.cuda_stream, tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=device)
+        if buf is not None:
+            buf.record_stream(st)
+        buf = torch.empty(int(nbytes * 1.1) + 4096, dtype=torch.uint8, device=torch.device("cuda", idx))
         _workspaces[key] = buf
     return buf

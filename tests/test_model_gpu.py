@@ -231,6 +231,57 @@ def test_greedy_vs_oracle_baseline_sizes():
     assert same >= 0.99 * tot, (same, tot)
 
 
+def test_layer_dropins_match_oracle_T0(t0):
+    """EncoderLayer.forward / DecoderLayer.forward as stand-alone sub-module drop-ins (reference model.py:18-25, 65-75)
+    against the oracle's restatement of the same layers, incl. the (S, S) uint8 causal mask of Decoder.evaluate."""
+    cfg, fx, m, spec = t0
+    sd = cpu_state(m)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 37, cfg.embedding_dim, generator=g)
+    enc_ref = O.encoder_layer(sd, "encoder._layers.1", x)
+    assert_close(m.encoder._layers[1](x.to(DEV)), enc_ref, 2e-3, 2e-4, "EncoderLayer.forward")
+    y = torch.randn(2, 9, cfg.embedding_dim, generator=g)
+    mem = torch.randn(2, 37, cfg.embedding_dim, generator=g)
+    causal = torch.triu(torch.ones(9, 9, dtype=torch.uint8), diagonal=1)
+    dec_ref = O.decoder_layer(sd, "decoder._layers.0", y, causal, mem)
+    out = m.decoder._layers[0](y.to(DEV), causal.to(DEV), mem.to(DEV))
+    assert_close(out, dec_ref, 2e-3, 2e-4, "DecoderLayer.forward")
+
+
+def test_masks_on_C5():
+    """BASELINE config 5 (d_model 512, 8 heads, FFN 2048) with the key-padding masks ON: (a) the operator oracle, MHA
+    with attention_mask (layers.py:22-23), at C5's width; (b) truncation equivalence end to end: a zero-padded utterance
+    decoded with its length gives the encoder output and the tokens of the unpadded utterance decoded alone."""
+    cfg = O.CONFIGS["C5"]
+    m = build_model(cfg, DEV)
+    sd = cpu_state(m)
+    D = cfg.embedding_dim
+    g = torch.Generator().manual_seed(9)
+    x, src = torch.randn(3, 21, D, generator=g), torch.randn(3, 50, D, generator=g)
+    klen = torch.tensor([50, 17, 33])
+    mask = (torch.arange(50)[None, None, :] >= klen[:, None, None]).expand(3, 21, 50)
+    ref = O.mha(sd, "decoder._layers.2._cross_attention", x, src, mask)
+    out = m.decoder._layers[2]._cross_attention(x.to(DEV), src.to(DEV), mask.to(DEV))
+    assert_close(out, ref, 2e-3, 2e-4, "C5 MHA with key-padding mask")
+    lens = torch.tensor([cfg.frames, 611, 403, 877])
+    spec = O.structured_spectrum(4, cfg.frames, cfg.input_dim, seed=51, lengths=lens)
+    enc = m.encode(spec.to(DEV), lens.to(DEV))
+    tok, _, lg = m.greedy_decode(spec.to(DEV), lengths=lens.to(DEV), max_len=48, return_logits=True)
+    for b in (1, 2, 3):
+        n = int(lens[b])
+        alone = spec[b:b + 1, :, :, :n].contiguous().to(DEV)
+        enc1 = m.encode(alone)
+        assert_close(enc[b, :enc1.shape[1]], enc1[0], 1e-3, 1e-4, "C5 masked batch row == unpadded utterance")
+        t1, _, lg1 = m.greedy_decode(alone, max_len=48, return_logits=True)
+        r = O.compare_tokens(t1.cpu(), lg1.cpu(), tok[b:b + 1].cpu(), TAU)
+        assert not r["hard"], r
+        assert_close(lg[b, :8], lg1[0, :8], 2e-3, 2e-4, "C5 masked step logits == unpadded")
+    # the full-length row equals the unmasked reference-parity decode of that utterance
+    ref_tok, ref_lg = O.greedy_kv_cached(sd, O.encode(sd, spec[:1]), cfg, max_len=48)
+    r = O.compare_tokens(ref_tok, ref_lg, tok[:1].cpu(), TAU)
+    assert not r["hard"] and r["identical"] == 1, r
+
+
 def test_long_form_encoder_C4():
     """30 s utterances: encoder sequence 749 stresses the flash-attention tiling (6 KV tiles)."""
     cfg = O.CONFIGS["C4"]
