@@ -28,6 +28,9 @@
 namespace asr {
 namespace {
 
+#ifndef ASR_PEEK_MODE
+#define ASR_PEEK_MODE 0
+#endif
 constexpr int NCW = 8;                    // consumer warps (16 measured slower: per-warp fixed costs dominate, not divisible work)
 constexpr int NCT = NCW * 32;             // consumer threads
 constexpr int NTHREADS = NCT + 32;        // + producer warp (one working thread)
@@ -149,18 +152,19 @@ struct Mat {
 
 struct SmemMap {
   uint32_t ring, h, xn_hi, xn_lo, hid_hi, hid_lo, o_hi, o_lo, q, kvrow, scratch, prm, lg, recv, arg, part, stat, red, tok,
-      ctrl, bars, total;
+      ctrl, ph, bars, total;
 };
+// Every buffer but the ring sits at a COMPILE-TIME offset (the ring, whose depth is chosen at launch, comes last): the
+// kernel's shared-memory pointers are constants, not registers.
 template <class S>
-__host__ __device__ inline SmemMap smem_map(int nstages) {
-  SmemMap m;
+__host__ __device__ constexpr SmemMap smem_map(int nstages) {
+  SmemMap m{};
   uint32_t off = 0;
-  auto take = [&](uint32_t bytes) {
+  auto take = [&off](uint32_t bytes) {
     const uint32_t o = off;
     off += (bytes + 127u) & ~127u;
     return o;
   };
-  m.ring = take(uint32_t(nstages) * STAGE_BYTES);
   m.h = take(S::GUP * S::D * 4);
   m.xn_hi = take(S::GUP * S::LDX);
   m.xn_lo = take(S::GUP * S::LDX);
@@ -173,15 +177,18 @@ __host__ __device__ inline SmemMap smem_map(int nstages) {
   m.scratch = take(24 * 32 * 16);                      // [KG * MT <= 24 when KG > 1][32 lanes] float4 partial tiles
   m.prm = take(S::SMALL_BYTES);
   m.lg = take(S::GUP * S::VS * 4);
-  m.recv = take(2 * S::CS * S::D * S::GUP * 4);        // [parity][source rank][D][GUP] fp32 partial sums
+  m.recv = take(2 * S::CS * S::D * S::GUP * 4);        // [parity][source rank][GUP][D] fp32 partial sums (odd rows ^ 16)
   m.arg = take(2 * S::CS * S::GUP * 8);                // [parity][source rank][GUP] (value, index)
   m.part = take(NCW * 64 * 4);
   m.stat = take(2 * NCW * 4);
   m.red = take(NCW * 8 * 8);                           // LayerNorm partials [warp][utterance slot] (sum, sum of squares)
   m.tok = take(2 * 8 * 4);                             // [0..7] next tokens, [8..15] finished flags
   m.ctrl = take(16);                                   // [0] steps done, [1] stop, [2] cache rows written
+  m.ph = take(12 * 8);                                 // phase clocks (timed launches)
   m.bars = take((2 * MAX_STAGES + 4) * 8);
-  m.total = off;
+  off = (off + 1023u) & ~1023u;                        // swizzled TMA destinations: 1024-byte aligned stages
+  m.ring = off;
+  m.total = off + uint32_t(nstages) * STAGE_BYTES;
   return m;
 }
 
@@ -192,16 +199,23 @@ struct Ring {
   int nstages;
 };
 
+// The producer is a whole WARP walking the static access sequence in lock-step: lane 0 waits for the free slot and posts
+// the byte count, then the lanes issue the stage's copies IN PARALLEL (lane u = utterance slot u of a K/V stage).  One
+// thread issuing the eight copies of a K/V stage one after the other (address arithmetic + TMA issue, ~100 cycles each
+// at single-thread latency) took as long as the consumers need to eat the stage: the ring ran dry in every attention.
 struct Producer {
   Ring r;
   int slot = 0;
   uint32_t round = 0;
   long long waited = 0;
   __device__ __forceinline__ uint8_t* begin(uint32_t bytes) {
-    const long long w0 = clock64();
-    mbar_wait(&r.empty[slot], (round & 1u) ^ 1u);
-    waited += clock64() - w0;
-    mbar_expect_tx(&r.full[slot], bytes);
+    if ((threadIdx.x & 31) == 0) {
+      const long long w0 = clock64();
+      mbar_wait(&r.empty[slot], (round & 1u) ^ 1u);
+      waited += clock64() - w0;
+      mbar_expect_tx(&r.full[slot], bytes);
+    }
+    __syncwarp();                            // the slot is free and armed before any lane's copy can land in it
     return r.buf + size_t(slot) * STAGE_BYTES;
   }
   __device__ __forceinline__ uint64_t* bar() { return &r.full[slot]; }
@@ -216,7 +230,7 @@ struct Producer {
 #pragma unroll 1
     for (int s = 0; s < M::NST; ++s) {
       uint8_t* dst = begin(M::ST_BYTES);
-      bulk_load(dst, src, M::ST_BYTES, bar(), pol);
+      if ((threadIdx.x & 31) == 0) bulk_load(dst, src, M::ST_BYTES, bar(), pol);
       src += M::ST_BYTES;
       end();
     }
@@ -227,30 +241,59 @@ struct Consumer {
   Ring r;
   int slot = 0;
   uint32_t round = 0;
-  long long waited = 0;
-  bool timed = false;
-  __device__ __forceinline__ const uint8_t* acquire() {
-    if (!mbar_try_wait(&r.full[slot], round & 1u)) {   // stage not there yet: the (rare, out-of-line) slow path is timed
-      const long long w0 = timed ? clock64() : 0;
-      mbar_wait_slow(smem_u32(&r.full[slot]), round & 1u);
-      if (timed) waited += clock64() - w0;
-    }
-    return r.buf + size_t(slot) * STAGE_BYTES;
-  }
-  // wait for the stage i slots ahead of the current one (0 = current) without consuming it
-  __device__ __forceinline__ const uint8_t* acquire_ahead(int i) {
+  uint32_t okm = 0;        // bit i: the stage i slots ahead of the current one is known to be full
+#ifdef ASR_COUNT_LATE
+  long long late = 0;      // acquires that found the stage not yet full
+#endif
+  __device__ __forceinline__ uint64_t* bar_ahead(int i, uint32_t& parity) const {
     int sl = slot + i;
     uint32_t rd = round;
     if (sl >= r.nstages) {
       sl -= r.nstages;
       ++rd;
     }
-    mbar_wait(&r.full[sl], rd & 1u);
-    return r.buf + size_t(sl) * STAGE_BYTES;
+    parity = rd & 1u;
+    return &r.full[sl];
   }
+  // Non-blocking look at the stage i slots ahead (mbarrier.test_wait never suspends the warp).  A completed-phase query
+  // still takes ~100 cycles to come back, and with two warps per scheduler nothing hides it: every use site issues
+  // its peeks EARLY (before the math of the stage in hand) and tests the cached bit when it gets there.
+  __device__ __forceinline__ void peek(int i) {
+#if ASR_PEEK_MODE
+    if (i < r.nstages && !((okm >> i) & 1u)) {
+      uint32_t parity;
+      uint64_t* b = bar_ahead(i, parity);
+#if ASR_PEEK_MODE == 1
+      okm |= uint32_t(mbar_test_wait(b, parity)) << i;
+#else
+      okm |= uint32_t(mbar_try_wait(b, parity)) << i;
+#endif
+    }
+#endif
+  }
+  // wait for the stage i slots ahead of the current one (0 = current) without consuming it
+  __device__ __forceinline__ const uint8_t* acquire_ahead(int i) {
+    uint32_t parity;
+    uint64_t* b = bar_ahead(i, parity);
+    if (!((okm >> i) & 1u)) {
+#ifdef ASR_COUNT_LATE
+      if (!mbar_test_wait(b, parity)) {      // diagnostic build: how long do the consumers wait for DATA?
+        const long long w0 = clock64();
+        if (!mbar_try_wait(b, parity)) mbar_wait_slow(smem_u32(b), parity);
+        late += clock64() - w0;
+      }
+#else
+      if (!mbar_try_wait(b, parity)) mbar_wait_slow(smem_u32(b), parity);   // stage not there yet (rare): out of line
+#endif
+      okm |= 1u << i;
+    }
+    return r.buf + size_t(b - r.full) * STAGE_BYTES;
+  }
+  __device__ __forceinline__ const uint8_t* acquire() { return acquire_ahead(0); }
   __device__ __forceinline__ void release() {       // every consumer warp calls this once per stage
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbar_arrive(&r.empty[slot]);
+    okm >>= 1;
     if (++slot == r.nstages) {
       slot = 0;
       ++round;
@@ -262,12 +305,13 @@ struct Consumer {
 // out[n, u] = sum_k W[n, k] x[u, k] for the rows n of one packed matrix and the GUP utterance rows of x, W streamed
 // through the ring.  Image layout per k-block kb (32 columns) and m-tile mt (16 rows): 1 KB =
 // [k-tile s (2)][lane = g*4 + tg (32)][16 B] with the 16 bytes = the mma.m16n8k16 A fragment {a0,a1,a2,a3} of that
-// lane: {W[g][c..c+1], W[g+8][c..c+1], W[g][c+2..c+3], W[g+8][c+2..c+3]}, c = 32 kb + 8 tg + 4 s, i.e. the K
-// permutation k_mma {2tg, 2tg+1, 2tg+8, 2tg+9} <-> columns {c..c+3}.  The B fragment applies the same permutation:
+// lane: {W[2g][c..c+1], W[2g+1][c..c+1], W[2g][c+2..c+3], W[2g+1][c+2..c+3]} (rows within the m-tile), c = 32 kb + 8 tg
+// + 4 s, i.e. the K permutation k_mma {2tg, 2tg+1, 2tg+8, 2tg+9} <-> columns {c..c+3} and the row permutation MMA row
+// g -> 2g, g + 8 -> 2g + 1: a lane's result tile holds two ADJACENT output rows (paired stores in every epilogue).  The B fragment applies the same permutation:
 // lane (g, tg) reads the 16 bytes x[u = g][32 kb + 8 tg .. +7] (f16 hi and lo copies; row stride == 64 mod 128 B:
 // conflict free) and feeds halves s = 0 / 1 to the two MMAs.  Unit (m-tile mt, k-group kg) belongs to warp
-// (mt * KG + kg) % 8.  The finished tile {(n = 16mt+g, u = 2tg), (n, u+1), (n+8, u), (n+8, u+1)} goes to
-// epi(n, u0, v(u0), v(u0+1)); with KG > 1 the k-group partials are first combined through `scratch`.
+// (mt * KG + kg) % 8.  The finished tile v = {(n = 16mt+2g, u = 2tg), (n, u+1), (n+1, u), (n+1, u+1)} goes to
+// epi(n, u, v); with KG > 1 the k-group partials are first combined through `scratch`.
 template <class M, int GUP, class Epi>
 __device__ __forceinline__ void mm_stream(Consumer& c, const uint8_t* xhi, const uint8_t* xlo, int ldx, float4* scratch,
                                           Epi&& epi) {
@@ -308,10 +352,12 @@ __device__ __forceinline__ void mm_stream(Consumer& c, const uint8_t* xhi, const
     }
   };
   load_stage(0, 0, c.acquire());
+  c.peek(1);
 #pragma unroll
   for (int st_i = 0; st_i < M::NST; ++st_i) {
     const int cur = st_i & 1;
     if (st_i + 1 < M::NST) load_stage(cur ^ 1, st_i + 1, c.acquire_ahead(1));
+    c.peek(st_i + 1 < M::NST ? 2 : 1);   // the stage after next (or the next phase's first one), under this stage's MMAs
 #pragma unroll
     for (int q = 0; q < M::KPG; ++q)
 #pragma unroll
@@ -339,13 +385,8 @@ __device__ __forceinline__ void mm_stream(Consumer& c, const uint8_t* xhi, const
   }
   if (M::KG == 1) {
 #pragma unroll
-    for (int j = 0; j < M::UPW; ++j) {
-      const int n0 = 16 * (mt0 + j * M::MSTEP) + g;
-      if (2 * tg < GUP) {
-        epi(n0, 2 * tg, v[j].x, v[j].y);
-        epi(n0 + 8, 2 * tg, v[j].z, v[j].w);
-      }
-    }
+    for (int j = 0; j < M::UPW; ++j)
+      if (2 * tg < GUP) epi(16 * (mt0 + j * M::MSTEP) + 2 * g, 2 * tg, v[j]);
   } else {
 #pragma unroll
     for (int j = 0; j < M::UPW; ++j) scratch[(kg * M::MT + mt0 + j * M::MSTEP) * 32 + lane] = v[j];
@@ -359,13 +400,16 @@ __device__ __forceinline__ void mm_stream(Consumer& c, const uint8_t* xhi, const
           const float4 w = scratch[k * M::MT * 32 + it];
           s.x += w.x; s.y += w.y; s.z += w.z; s.w += w.w;
         }
-        const int n0 = 16 * (it >> 5) + g2;
-        epi(n0, 2 * tg2, s.x, s.y);
-        epi(n0 + 8, 2 * tg2, s.z, s.w);
+        epi(16 * (it >> 5) + 2 * g2, 2 * tg2, s);
       }
     }
   }
 }
+
+// Column skew of the [utterance][D] fp32 rows (residual stream, all-reduce receive slots): row u holds column n at
+// n ^ hswz(u).  Bit 4 separates the two utterances a warp of the all-reduce tail reads together; bits 3-4 spread the
+// four even (and the four odd) utterance rows the matmul epilogue writes together.  Multiples of 8 keep float4 groups.
+__device__ __forceinline__ int hswz(int u) { return ((u & 1) << 4) ^ (((u >> 1) & 3) << 3); }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm / split
 // rows u < GU of h (fp32, stride D) -> f16 hi + lo rows (stride ld elements); warp u handles row u.
@@ -377,7 +421,7 @@ __device__ __forceinline__ void rows_to_hilo(const float* h, int GU, const float
     const float* src = h + warp * D;
     float x[D / 32];
 #pragma unroll
-    for (int i = 0; i < D / 32; ++i) x[i] = src[lane + 32 * i];
+    for (int i = 0; i < D / 32; ++i) x[i] = src[(lane + 32 * i) ^ hswz(warp)];
     if (gam) {
       float sum = 0.f;
 #pragma unroll
@@ -412,12 +456,12 @@ __device__ __forceinline__ void ln_rows(const float* h, int GU, const float* gam
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int u = warp % S::GUP, part = warp / S::GUP;
   const float* src = h + u * D;
-  const int k0 = part * (D / WPU) + lane;
+  const int k0 = part * (D / WPU) + lane, hsw = hswz(u);
   const float c0 = src[0];
   float x[EPL], s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int i = 0; i < EPL; ++i) {
-    x[i] = src[k0 + 32 * i] - c0;
+    x[i] = src[(k0 + 32 * i) ^ hsw] - c0;
     s1 += x[i];
     s2 = fmaf(x[i], x[i], s2);
   }
@@ -483,11 +527,18 @@ __device__ __forceinline__ int q_frag_index(int d) {
   const int kt = d >> 4, r = d & 15;
   return (((r & 7) >> 1) * 4 + kt) * 4 + (r >> 3) * 2 + (r & 1);
 }
-__device__ __forceinline__ void q_store(f16* q_hi, f16* q_lo, int u, int d, float y) {
-  const f16 h = __float2half_rn(y);
+// f16 hi | lo split of a pair of values
+__device__ __forceinline__ void hilo2(float a, float b, __half2& hi, __half2& lo) {
+  hi = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(hi);
+  lo = __floats2half2_rn(a - f.x, b - f.y);
+}
+__device__ __forceinline__ void q_store2(f16* q_hi, f16* q_lo, int u, int d, float y0, float y1) {   // dims d (even), d+1
+  __half2 hi, lo;
+  hilo2(y0, y1, hi, lo);
   const int i = u * 64 + q_frag_index(d);
-  q_hi[i] = h;
-  q_lo[i] = __float2half_rn(y - __half2float(h));
+  *reinterpret_cast<__half2*>(q_hi + i) = hi;
+  *reinterpret_cast<__half2*>(q_lo + i) = lo;
 }
 __device__ __forceinline__ void attn_q_frags(const f16* q_hi, const f16* q_lo, int u, uint32_t (&qf)[8]) {
   const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
@@ -585,6 +636,8 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t
     float sa[SC][TPW], sb[SC][TPW];
     float mx = ca;
 #pragma unroll
+    for (int s = 1; s < SC; ++s) c.peek(s);                     // K stages of this super-chunk (stage 0: peeked earlier)
+#pragma unroll
     for (int s = 0; s < SC; ++s) {
 #pragma unroll
       for (int j = 0; j < TPW; ++j) sa[s][j] = sb[s][j] = -INFINITY;
@@ -600,6 +653,8 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t
         c.release();
       }
     }
+#pragma unroll
+    for (int s = 0; s < SC; ++s) c.peek(s);                     // the V stages, under the softmax
     // scores live in the lanes tg == 0 (-inf elsewhere): fold the 8 key rows, then broadcast
 #pragma unroll
     for (int o = 16; o >= 4; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -639,6 +694,7 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t
           if (n > 16 * j) pv_tile<false>(st, stg + j * 2048, pb0[s][j], pb1[s][j]);
         c.release();
       }
+    c.peek(0);                                                  // next super-chunk's / next phase's first stage
     if (cur) pv_tile<true>(st, cur_kb + 128, cb0, cb1, cur_swz);
     cur = false;
     ca = -INFINITY;
@@ -698,7 +754,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
   using MCls = Mat<VS / 16, D / 32>;
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  const SmemMap sm = smem_map<S>(p.nstages);
+  constexpr SmemMap sm = smem_map<S>(0);       // offsets do not depend on the ring depth
   Ring ring;
   ring.buf = smem + sm.ring;
   ring.nstages = p.nstages;
@@ -756,8 +812,9 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
   const uint8_t* my_image = p.image + size_t(rank) * p.rank_bytes;
 
   if (warp >= NCW) {
-    // =============================== producer: one thread walks the static access sequence
-    if (tid == NCT) {
+    // =============================== producer warp (see struct Producer)
+    {
+      const int plane = tid & 31;
       const uint64_t pol_w = policy_evict_last();
       const uint64_t pol_kv = p.kv_evict_first ? policy_evict_first() : policy_evict_last();
       Producer pr;
@@ -774,7 +831,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
           const uint8_t* img = my_image + size_t(l) * p.layer_bytes;
           {
             uint8_t* dst = pr.begin(S::SMALL_BYTES);
-            bulk_load(dst, img + p.off_small, S::SMALL_BYTES, pr.bar(), pol_w);
+            if (plane == 0) bulk_load(dst, img + p.off_small, S::SMALL_BYTES, pr.bar(), pol_w);
             pr.end();
           }
           pr.mat<MQkv>(img + p.off_qkv, pol_w);
@@ -783,33 +840,36 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
             while (ctrl[2] < need) {
             }
             asm volatile("fence.proxy.async;" ::: "memory");
+            // lane u: K rows | V rows of utterance slot u, head `rank`
+            const f16* cbase = p.cache + ((size_t(l) * p.B + ubase + (plane < GU ? plane : 0)) * H + rank) * cache_head;
             for (int c0 = 0; c0 < t; c0 += S::SCX * RPS) {
               const int nk = min(S::SCX * RPS, t - c0);
               for (int kv = 0; kv < 2; ++kv)               // K stages of the super-chunk, then its V stages
                 for (int r0 = 0; r0 < nk; r0 += RPS) {
                   const int n = (min(RPS, nk - r0) + 15) & ~15;   // whole 16-key tiles (rows past t are zero)
                   uint8_t* dst = pr.begin(uint32_t(GU) * n * 128u);
-                  for (int u = 0; u < GU; ++u) {
-                    const f16* src = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head +
-                                      size_t(kv) * Lc * 64 + size_t(c0 + r0) * 64;
-                    bulk_load(dst + u * RPS * 128, src, n * 128, pr.bar(), pol_kv);
-                  }
+                  if (plane < GU)
+                    bulk_load(dst + plane * RPS * 128, cbase + size_t(kv) * Lc * 64 + size_t(c0 + r0) * 64, n * 128,
+                              pr.bar(), pol_kv);
                   pr.end();
                 }
             }
           }
           pr.mat<MWo>(img + p.off_wo, pol_w);
           pr.mat<MWqc>(img + p.off_wqc, pol_w);
-          for (int c0 = 0; c0 < p.Tp; c0 += S::SCX * RPS) {   // encoder K/V of this head: 2-D boxes [RPS rows][64 columns]
-            const int nk = min(S::SCX * RPS, p.Tp - c0);
-            for (int kv = 0; kv < 2; ++kv)
-              for (int r0 = 0; r0 < nk; r0 += RPS) {
-                uint8_t* dst = pr.begin(uint32_t(GU) * RPS * 128u);
-                for (int u = 0; u < GU; ++u)
-                  tma_load_2d_hint(dst + u * RPS * 128, &ckv_map, pr.bar(), kv * D + rank * 64,
-                                   (l * p.B + ubase + u) * p.Tp + c0 + r0, pol_kv);
-                pr.end();
-              }
+          {
+            const int row0 = (l * p.B + ubase + plane) * p.Tp;   // lane u: encoder K/V rows of utterance slot u
+            for (int c0 = 0; c0 < p.Tp; c0 += S::SCX * RPS) {    // 2-D boxes [RPS rows][64 columns] of this head
+              const int nk = min(S::SCX * RPS, p.Tp - c0);
+              for (int kv = 0; kv < 2; ++kv)
+                for (int r0 = 0; r0 < nk; r0 += RPS) {
+                  uint8_t* dst = pr.begin(uint32_t(GU) * RPS * 128u);
+                  if (plane < GU)
+                    tma_load_2d_hint(dst + plane * RPS * 128, &ckv_map, pr.bar(), kv * D + rank * 64, row0 + c0 + r0,
+                                     pol_kv);
+                  pr.end();
+                }
+            }
           }
           pr.mat<MWo>(img + p.off_woc, pol_w);
           pr.mat<MW1>(img + p.off_w1, pol_w);
@@ -817,7 +877,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
         }
         pr.mat<MCls>(my_image + p.off_cls, pol_w);
       }
-      if (p.timing) {
+      if (p.timing && plane == 0) {
         p.timing[size_t(blockIdx.x) * 16 + 3] = pr.waited;
         p.timing[size_t(blockIdx.x) * 16 + 4] = (long long)pr.round * p.nstages + pr.slot;
       }
@@ -828,7 +888,6 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
     Consumer c;
     c.r = ring;
     const bool timed = p.timing != nullptr;
-    c.timed = timed;
     const long long t_begin = clock64();
     long long t_xchg = 0;
     uint32_t n_xchg = 0, n_arg = 0;
@@ -842,8 +901,9 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
     const uint8_t* xl = reinterpret_cast<const uint8_t*>(xn_lo);
 
     // embedding + PE of the first token (host-side init kernel)
-    for (int i = tid * 4; i < GU * D; i += NCT * 4)
-      *reinterpret_cast<float4*>(s_h + i) = *reinterpret_cast<const float4*>(p.h0 + size_t(ubase) * D + i);
+    for (int i = tid * 4; i < GU * D; i += NCT * 4)         // (row u holds column n at n ^ hswz(u))
+      *reinterpret_cast<float4*>(s_h + (i ^ hswz(i / D))) =
+          *reinterpret_cast<const float4*>(p.h0 + size_t(ubase) * D + i);
     consumer_sync();
 
     // partial sums over the full model dimension (this CTA's K-slice) -> all-reduce across the cluster:
@@ -857,23 +917,32 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
       peer_recv[k] = mapa_u32(smem_u32(recv), r);
       peer_bar[k] = mapa_u32(smem_u32(&xbar[0]), r);
     }
-    auto send_partial = [&](int n, int u0, float v0, float v1) {
+    // Residual stream s_h and the receive slots are [utterance][D] fp32 with skewed columns (hswz).
+    auto send_partial = [&](int n, int u0, const float4& v) {     // v = {(n,u0), (n,u0+1), (n+1,u0), (n+1,u0+1)}
       const uint32_t par = n_xchg & 1u;
-      const uint32_t off = uint32_t(((size_t(par) * CS + rank) * D + n) * GUP + u0) * 4u;
-      *reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(recv) + off) = make_float2(v0, v1);
+      const uint32_t off0 = uint32_t(((size_t(par) * CS + rank) * GUP + u0) * D + (n ^ hswz(u0))) * 4u;
+      const uint32_t off1 = uint32_t(((size_t(par) * CS + rank) * GUP + u0 + 1) * D + (n ^ hswz(u0 + 1))) * 4u;
+      *reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(recv) + off0) = make_float2(v.x, v.z);
+      *reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(recv) + off1) = make_float2(v.y, v.w);
 #pragma unroll
-      for (int k = 0; k < CS - 1; ++k) st_async_v2(peer_recv[k] + off, v0, v1, peer_bar[k] + par * 8u);
+      for (int k = 0; k < CS - 1; ++k) {
+        st_async_v2(peer_recv[k] + off0, v.x, v.z, peer_bar[k] + par * 8u);
+        st_async_v2(peer_recv[k] + off1, v.y, v.w, peer_bar[k] + par * 8u);
+      }
     };
     // ... and, fused into its tail, what follows every all-reduce: LayerNorm of the new rows (gam != nullptr) or the
-    // plain f16 hi | lo split (classifier input).  Thread tid owns elements idx = tid + NCT k: utterance u = tid % GUP,
-    // n = idx / GUP; the new values stay in registers between the sum and the normalisation.  Variance from one pass
-    // over (x - c), c = the row's previous first element (same for every thread: read before the first barrier).
+    // plain f16 hi | lo split (classifier input).  The GUP x D elements are dealt to the warps as blocks of 2 utterances
+    // x 16 column pairs: lane -> utterance 2 up + (lane & 1), columns n, n + 1 with n = 32 j + 2 (lane >> 1); a warp
+    // always serves the same utterance pair up = warp % (GUP / 2).  Every shared-memory access of the tail is then a
+    // conflict-free 8-byte (fp32 pair) or 4-byte (f16 pair) word per lane.  The new values stay in registers between the
+    // sum and the normalisation; variance from one pass over (x - c), c = an element of the row's previous value.
     auto all_reduce_finish = [&](const float* bias, const float* gam, const float* bet) {
-      constexpr int EP = D * GUP / NCT;
-      static_assert(D * GUP % NCT == 0 && NCT % GUP == 0, "all-reduce element split");
+      constexpr int UP = GUP / 2, NB = UP * (D / 32), BPW = (NB + NCW - 1) / NCW;
+      static_assert(NCW % UP == 0 && (NB % NCW == 0 || NB < NCW), "all-reduce block split");
       const uint32_t par = n_xchg & 1u, phase = (n_xchg >> 1) & 1u;
-      const int u = tid % GUP, nb = tid / GUP;
-      const float c0 = s_h[u * D];
+      const int up = warp % UP, u = 2 * up + (lane & 1), sw = hswz(u);
+      float* hrow = s_h + u * D;
+      const float c0 = hrow[0];
       if (tid == 0) mbar_expect_tx(&xbar[par], uint32_t(CS - 1) * D * GUP * 4u);
       consumer_sync();                                     // own slot written by every thread; c0 read by every thread
       if (timed) {
@@ -883,33 +952,44 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
       } else {
         mbar_wait_cluster(&xbar[par], phase);
       }
-      const float* rv = recv + size_t(par) * CS * D * GUP;
-      float hv[EP], s1 = 0.f, s2 = 0.f;
+      const float* rv = recv + (size_t(par) * CS * GUP + u) * D;
+      float2 hv[BPW];
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int k = 0; k < EP; ++k) {
-        const int idx = tid + NCT * k, n = nb + k * (NCT / GUP);
-        float s = 0.f;
+      for (int k = 0; k < BPW; ++k) {
+        const int blk = warp + NCW * k;
+        hv[k] = make_float2(c0, c0);
+        if (NB % NCW == 0 || blk < NB) {
+          const int n = (blk / UP) * 32 + (lane >> 1) * 2, pos = n ^ sw;
+          float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int r = 0; r < CS; ++r) s += rv[r * D * GUP + idx];
-        hv[k] = s_h[u * D + n] + (s + bias[n]);
-        if (u < GU) s_h[u * D + n] = hv[k];
-        const float d = hv[k] - c0;
-        s1 += d;
-        s2 = fmaf(d, d, s2);
+          for (int r = 0; r < CS; ++r) {
+            const float2 w = *reinterpret_cast<const float2*>(rv + size_t(r) * GUP * D + pos);
+            s.x += w.x;
+            s.y += w.y;
+          }
+          const float2 b = *reinterpret_cast<const float2*>(bias + n);
+          const float2 h = *reinterpret_cast<const float2*>(hrow + pos);
+          hv[k] = make_float2(h.x + (s.x + b.x), h.y + (s.y + b.y));
+          if (u < GU) *reinterpret_cast<float2*>(hrow + pos) = hv[k];
+          const float d0 = hv[k].x - c0, d1 = hv[k].y - c0;
+          s1 += d0 + d1;
+          s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+        }
       }
       float mean = 0.f, rstd = 1.f;
       if (gam) {
 #pragma unroll
-        for (int o = 16; o >= GUP; o >>= 1) {
+        for (int o = 16; o >= 2; o >>= 1) {
           s1 += __shfl_xor_sync(0xffffffffu, s1, o);
           s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         }
-        if (lane < GUP) red[warp * GUP + lane] = make_float2(s1, s2);
+        if (lane < 2) red[warp * 2 + lane] = make_float2(s1, s2);
         consumer_sync();
         float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-        for (int w = 0; w < NCW; ++w) {
-          const float2 r = red[w * GUP + u];
+        for (int w = 0; w < NCW / UP; ++w) {
+          const float2 r = red[(w * UP + up) * 2 + (lane & 1)];
           t1 += r.x;
           t2 += r.y;
         }
@@ -919,25 +999,39 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
       }
       if (u < GU) {
 #pragma unroll
-        for (int k = 0; k < EP; ++k) {
-          const int n = nb + k * (NCT / GUP);
-          const float y = gam ? (hv[k] - mean) * rstd * gam[n] + bet[n] : hv[k];
-          const f16 hh = __float2half_rn(y);
-          xn_hi[u * (D + 32) + n] = hh;
-          xn_lo[u * (D + 32) + n] = __float2half_rn(y - __half2float(hh));
+        for (int k = 0; k < BPW; ++k) {
+          const int blk = warp + NCW * k;
+          if (NB % NCW == 0 || blk < NB) {
+            const int n = (blk / UP) * 32 + (lane >> 1) * 2;
+            float y0 = hv[k].x, y1 = hv[k].y;
+            if (gam) {
+              const float2 gg = *reinterpret_cast<const float2*>(gam + n), bb = *reinterpret_cast<const float2*>(bet + n);
+              y0 = (y0 - mean) * rstd * gg.x + bb.x;
+              y1 = (y1 - mean) * rstd * gg.y + bb.y;
+            }
+            __half2 hi, lo;
+            hilo2(y0, y1, hi, lo);
+            *reinterpret_cast<__half2*>(xn_hi + u * (D + 32) + n) = hi;
+            *reinterpret_cast<__half2*>(xn_lo + u * (D + 32) + n) = lo;
+          }
         }
       }
       consumer_sync();
       ++n_xchg;
     };
 
-    long long ph[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // per-phase clock totals (thread 0; written if p.timing)
-    long long ph_t = clock64();
+    // per-phase clock totals (if p.timing): thread 0's, kept in SHARED memory - as registers the 12 counters cost 24 of
+    // the 168 registers per thread whether or not the launch is timed
+    long long* ph = reinterpret_cast<long long*>(smem + sm.ph);
+    if (tid == 0) {
+      for (int i = 0; i < 11; ++i) ph[i] = 0;
+      ph[11] = clock64();
+    }
     auto mark = [&](int i) {
-      if (timed) {
+      if (timed && tid == 0) {
         const long long now = clock64();
-        ph[i] += now - ph_t;
-        ph_t = now;
+        ph[i] += now - ph[11];
+        ph[11] = now;
       }
     };
     int t = 0;
@@ -981,15 +1075,15 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
             if (pass == 0) {
               // ---- masked self attention (model.py:67-68): q, k, v of this head, cache append, keys 0..t
               mark(1);
-              mm_stream<MQkv, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
-                const float y0 = v0 + b_qkv[n], y1 = v1 + b_qkv[n];
+              mm_stream<MQkv, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, const float4& v) {
+                const float2 b = *reinterpret_cast<const float2*>(b_qkv + n);
                 if (n < 64) {
-                  q_store(q_hi, q_lo, u0, n, y0 * qscale);
-                  q_store(q_hi, q_lo, u0 + 1, n, y1 * qscale);
+                  q_store2(q_hi, q_lo, u0, n, (v.x + b.x) * qscale, (v.z + b.y) * qscale);
+                  q_store2(q_hi, q_lo, u0 + 1, n, (v.y + b.x) * qscale, (v.w + b.y) * qscale);
                 } else {   // k_t | v_t rows in the cache's swizzled chunk order (chunk ^ (t & 7)): TMA-stored as they are
                   const int e = n - 64, pos = (e & 64) + ((((e & 63) >> 3) ^ (t & 7)) << 3) + (e & 7);
-                  kv_row[u0 * 128 + pos] = __float2half_rn(y0);
-                  kv_row[(u0 + 1) * 128 + pos] = __float2half_rn(y1);
+                  *reinterpret_cast<__half2*>(kv_row + u0 * 128 + pos) = __floats2half2_rn(v.x + b.x, v.z + b.y);
+                  *reinterpret_cast<__half2*>(kv_row + (u0 + 1) * 128 + pos) = __floats2half2_rn(v.y + b.x, v.w + b.y);
                 }
               });
               fence_proxy_async();                                   // kv_row: generic writes -> the TMA store below
@@ -1020,9 +1114,10 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
               ar_gam = ln + 2 * D;                              // out projection + residual (model.py:68) -> LN2 (:70)
             } else {
               // ---- cross-attention query -> attention over the encoder K/V (model.py:70-71)
-              mm_stream<MWqc, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
-                q_store(q_hi, q_lo, u0, n, (v0 + b_qc[n]) * qscale);
-                q_store(q_hi, q_lo, u0 + 1, n, (v1 + b_qc[n]) * qscale);
+              mm_stream<MWqc, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, const float4& v) {
+                const float2 b = *reinterpret_cast<const float2*>(b_qc + n);
+                q_store2(q_hi, q_lo, u0, n, (v.x + b.x) * qscale, (v.z + b.y) * qscale);
+                q_store2(q_hi, q_lo, u0 + 1, n, (v.y + b.x) * qscale, (v.w + b.y) * qscale);
               });
               consumer_sync();
               mark(7);
@@ -1053,13 +1148,15 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
             mark(5);
           } else {
             // ---- FFN: squeeze rows of this CTA + ReLU, then the matching K-slice of unsqueeze (model.py:73-74)
-            mm_stream<MW1, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
-              const float y0 = fmaxf(v0 + b_1[n], 0.f), y1 = fmaxf(v1 + b_1[n], 0.f);
-              const f16 h0 = __float2half_rn(y0), h1 = __float2half_rn(y1);
-              hid_hi[u0 * (FFS + 32) + n] = h0;
-              hid_lo[u0 * (FFS + 32) + n] = __float2half_rn(y0 - __half2float(h0));
-              hid_hi[(u0 + 1) * (FFS + 32) + n] = h1;
-              hid_lo[(u0 + 1) * (FFS + 32) + n] = __float2half_rn(y1 - __half2float(h1));
+            mm_stream<MW1, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, const float4& v) {
+              const float2 b = *reinterpret_cast<const float2*>(b_1 + n);
+              __half2 hi, lo;
+              hilo2(fmaxf(v.x + b.x, 0.f), fmaxf(v.z + b.y, 0.f), hi, lo);
+              *reinterpret_cast<__half2*>(hid_hi + u0 * (FFS + 32) + n) = hi;
+              *reinterpret_cast<__half2*>(hid_lo + u0 * (FFS + 32) + n) = lo;
+              hilo2(fmaxf(v.y + b.x, 0.f), fmaxf(v.w + b.y, 0.f), hi, lo);
+              *reinterpret_cast<__half2*>(hid_hi + (u0 + 1) * (FFS + 32) + n) = hi;
+              *reinterpret_cast<__half2*>(hid_lo + (u0 + 1) * (FFS + 32) + n) = lo;
             });
             consumer_sync();
             mark(9);
@@ -1080,9 +1177,9 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
         rows_to_hilo<D>(s_h, GU, nullptr, nullptr, xn_hi, xn_lo, D + 32);
         consumer_sync();
       }
-      mm_stream<MCls, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, float v0, float v1) {
-        s_lg[u0 * VS + n] = v0;
-        s_lg[(u0 + 1) * VS + n] = v1;
+      mm_stream<MCls, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, const float4& v) {
+        *reinterpret_cast<float2*>(s_lg + u0 * VS + n) = make_float2(v.x, v.z);
+        *reinterpret_cast<float2*>(s_lg + (u0 + 1) * VS + n) = make_float2(v.y, v.w);
       });
       consumer_sync();
       const int v_lo = rank * VS, v_n = max(0, min(VS, p.V - v_lo));   // this CTA's vocabulary range
@@ -1173,7 +1270,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
           const int u = i / D, d = i % D;
           const float4 e = __ldg(reinterpret_cast<const float4*>(p.emb + size_t(s_tok[u]) * D + d));
           const float4 q = __ldg(reinterpret_cast<const float4*>(p.pe + size_t(t + 1) * D + d));
-          *reinterpret_cast<float4*>(s_h + i) = make_float4(e.x + q.x, e.y + q.y, e.z + q.z, e.w + q.w);
+          *reinterpret_cast<float4*>(s_h + (i ^ hswz(u))) = make_float4(e.x + q.x, e.y + q.y, e.z + q.z, e.w + q.w);
         }
       }
       consumer_sync();
@@ -1186,7 +1283,11 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
       }
     if (p.timing && tid == 0) {
       p.timing[size_t(blockIdx.x) * 16 + 0] = clock64() - t_begin;
-      p.timing[size_t(blockIdx.x) * 16 + 1] = c.waited;
+#ifdef ASR_COUNT_LATE
+      p.timing[size_t(blockIdx.x) * 16 + 1] = c.late;   // stages this warp found not yet full (diagnostic build)
+#else
+      p.timing[size_t(blockIdx.x) * 16 + 1] = 0;
+#endif
       p.timing[size_t(blockIdx.x) * 16 + 2] = t_xchg;
       mark(0);
       for (int i = 0; i < 11; ++i) p.timing[size_t(blockIdx.x) * 16 + 5 + i] = ph[i];

@@ -47,6 +47,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking phase query (test_wait never suspends the thread; try_wait may park it until the phase completes)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.  The spin loop lives out of line:
 // the big persistent kernels inline ~100 waits, and their instruction footprint is what the SM's I-cache has to hold.
 static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {

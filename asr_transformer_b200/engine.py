@@ -113,12 +113,13 @@ def dec_image_layout(D: int, H: int, FF: int, V: int, nd: int) -> Optional[dict]
 def pack_mma_a(w: torch.Tensor) -> torch.Tensor:
     """fp16 [R, K] (R % 16 == 0, K % 32 == 0) -> flat fp16 in the cluster decoder's fragment-major order
     [k-block kb (32 cols)][m-tile mt (16 rows)][k-tile s (2)][g (8)][tg (4)][8], the 8 elements being the
-    mma.m16n8k16 A fragment {a0, a1, a2, a3} of lane (g, tg): with r = 16 mt + g and c = 32 kb + 8 tg + 4 s they are
-    w[r, c:c+2], w[r+8, c:c+2], w[r, c+2:c+4], w[r+8, c+2:c+4] - one LDS.128 per lane feeds one MMA directly."""
+    mma.m16n8k16 A fragment {a0, a1, a2, a3} of lane (g, tg): with r = 16 mt + 2 g and c = 32 kb + 8 tg + 4 s they are
+    w[r, c:c+2], w[r+1, c:c+2], w[r, c+2:c+4], w[r+1, c+2:c+4] - one LDS.128 per lane feeds one MMA directly.  MMA rows
+    g / g + 8 carry matrix rows 2g / 2g + 1 of the tile, so a lane's result fragment holds two ADJACENT output rows."""
     R, K = w.shape
     assert R % 16 == 0 and K % 32 == 0, (R, K)
-    t = w.reshape(R // 16, 2, 8, K // 32, 4, 2, 2, 2)    # mt, p, g, kb, tg, s, pair, e
-    return t.permute(3, 0, 5, 2, 4, 6, 1, 7).contiguous().reshape(-1)
+    t = w.reshape(R // 16, 8, 2, K // 32, 4, 2, 2, 2)    # mt, g, p, kb, tg, s, pair, e
+    return t.permute(3, 0, 5, 1, 4, 6, 2, 7).contiguous().reshape(-1)
 
 
 def pack_dec_image(decoder: nn.Module) -> Optional[torch.Tensor]:

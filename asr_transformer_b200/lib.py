@@ -12,7 +12,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libasr_b200.so")
+# ASR_B200_LIB: developer override (tools/variants.py builds experiment variants of the same library)
+LIB_PATH = os.environ.get("ASR_B200_LIB") or os.path.join(_HERE, "libasr_b200.so")
 
 c_void_p, c_int, c_float, c_size_t, c_longlong = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
 

@@ -96,8 +96,8 @@ typedef struct {
    *   Wqkv rows of head r (192 x D) | Wout[:, 64 r..] (D x 64) | cross Wq rows of head r (64 x D) |
    *   cross Wout[:, 64 r..] (D x 64) | W1[r FFS.., :] (FFS x D) | W2[:, r FFS..] (D x FFS)
    * then the classifier rows [r VS, (r+1) VS) (zero padded past vocab).  Every matrix [R x K] is stored f16 in
-   * mma.m16n8k16 A-fragment order [K/32 k-blocks][R/16 m-tiles][k-tile s 0..1][g 0..7][tg 0..3][8]: with r = 16 mt + g,
-   * c = 32 kb + 8 tg + 4 s the 8 elements are W[r][c..c+1], W[r+8][c..c+1], W[r][c+2..c+3], W[r+8][c+2..c+3].
+   * mma.m16n8k16 A-fragment order [K/32 k-blocks][R/16 m-tiles][k-tile s 0..1][g 0..7][tg 0..3][8]: with r = 16 mt + 2 g,
+   * c = 32 kb + 8 tg + 4 s the 8 elements are W[r][c..c+1], W[r+1][c..c+1], W[r][c+2..c+3], W[r+1][c+2..c+3].
    * asr_decoder_image_bytes() gives the total size (0 = shape not compiled into the cluster kernel). */
   const void* dec_image;
   size_t dec_image_bytes;

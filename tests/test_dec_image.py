@@ -56,10 +56,10 @@ def emulate_mm_stream(image, R, K, x):
             acc += mma_m16n8k16(a_regs[0], b_regs[0]) + mma_m16n8k16(a_regs[1], b_regs[1])
         for lane in range(32):                                             # epilogue interpretation of the float4 tile
             g, tg = lane >> 2, lane & 3
-            out[16 * mt + g, 2 * tg] = acc[lane, 0]
-            out[16 * mt + g, 2 * tg + 1] = acc[lane, 1]
-            out[16 * mt + g + 8, 2 * tg] = acc[lane, 2]
-            out[16 * mt + g + 8, 2 * tg + 1] = acc[lane, 3]
+            out[16 * mt + 2 * g, 2 * tg] = acc[lane, 0]                      # MMA row g     = matrix row 2g of the tile
+            out[16 * mt + 2 * g, 2 * tg + 1] = acc[lane, 1]
+            out[16 * mt + 2 * g + 1, 2 * tg] = acc[lane, 2]                  # MMA row g + 8 = matrix row 2g + 1
+            out[16 * mt + 2 * g + 1, 2 * tg + 1] = acc[lane, 3]
     return out
 
 
@@ -76,7 +76,7 @@ def test_fragment_order_matches_kernel_indexing(R, K):
 
 def unpack_mma_a(flat, R, K):
     t = flat.reshape(K // 32, R // 16, 2, 8, 4, 2, 2, 2)      # kb, mt, s, g, tg, pair, p, e
-    return t.permute(1, 6, 3, 0, 4, 2, 5, 7).reshape(R, K)    # mt, p, g, kb, tg, s, pair, e
+    return t.permute(1, 3, 6, 0, 4, 2, 5, 7).reshape(R, K)    # mt, g, p, kb, tg, s, pair, e
 
 
 @pytest.mark.parametrize("name", ["T0", "C2", "C5"])
