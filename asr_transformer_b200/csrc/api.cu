@@ -82,7 +82,7 @@ struct GreedyWs {
     const size_t vpad = (size_t(c.vocab_size) + 63) / 64 * 64;
     enc_f16 = b.take<f16>(M * D * 2);
     ckv = b.take<f16>(size_t(c.decoder_num_layers) * M * 2 * D);
-    cache = b.take<f16>(size_t(c.decoder_num_layers) * B * ((L + 15) / 16 * 16) * 2 * D);   // rows padded to 16-key tiles
+    cache = b.take<f16>(size_t(c.decoder_num_layers) * B * ((L + 31) / 32 * 32) * 2 * D);   // rows padded to 32-key blocks
     h = b.take<float>(size_t(B) * D);
     qkv = b.take<float>(size_t(B) * 3 * D);
     att = b.take<float>(size_t(B) * D);

@@ -151,7 +151,7 @@ struct Mat {
 };
 
 struct SmemMap {
-  uint32_t ring, h, xn_hi, xn_lo, hid_hi, hid_lo, o_hi, o_lo, q, kvrow, scratch, prm, lg, recv, arg, part, stat, red, tok,
+  uint32_t ring, h, xn_hi, xn_lo, hid_hi, hid_lo, o_hi, o_lo, q, qf, kvrow, scratch, prm, lg, recv, arg, part, stat, red, tok,
       ctrl, ph, bars, total;
 };
 // Every buffer but the ring sits at a COMPILE-TIME offset (the ring, whose depth is chosen at launch, comes last): the
@@ -173,11 +173,20 @@ __host__ __device__ constexpr SmemMap smem_map(int nstages) {
   m.o_hi = take(S::GUP * S::LDO);
   m.o_lo = take(S::GUP * S::LDO);
   m.q = take(S::GUP * 64 * 4);                         // f16 hi [GUP][64] | f16 lo [GUP][64], fragment order
+  m.qf = take(S::GUP * 64 * 4);                        // fp32 q of the self attention (score of the current key)
   m.kvrow = take(S::GUP * 128 * 2);
-  m.scratch = take(24 * 32 * 16);                      // [KG * MT <= 24 when KG > 1][32 lanes] float4 partial tiles
+  // [KG * MT <= 24 when KG > 1][32 lanes] float4 partial tiles of the split-K matmuls (QKV, cross q, classifier): they
+  // run while the FFN hidden rows and the attention output rows are dead, so the scratch shares their space when it fits
+  // (8 utterance slots: exactly 12 KB) - shared memory not spent here is ring depth.
+  constexpr uint32_t kScratch = 24 * 32 * 16;
+  if (m.q - m.hid_hi >= kScratch) {
+    m.scratch = m.hid_hi;
+  } else {
+    m.scratch = take(kScratch);
+  }
   m.prm = take(S::SMALL_BYTES);
   m.lg = take(S::GUP * S::VS * 4);
-  m.recv = take(2 * S::CS * S::D * S::GUP * 4);        // [parity][source rank][GUP][D] fp32 partial sums (odd rows ^ 16)
+  m.recv = take(S::CS * S::GUP * 64 * 4);              // [source rank][GUP][64] fp32 partial sums of this CTA's column slice
   m.arg = take(2 * S::CS * S::GUP * 8);                // [parity][source rank][GUP] (value, index)
   m.part = take(NCW * 64 * 4);
   m.stat = take(2 * NCW * 4);
@@ -494,38 +503,27 @@ __device__ __forceinline__ void ln_rows(const float* h, int GU, const float* gam
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-// Single-query attention of ONE head on the tensor cores, 16 keys per tile, flash style (log2 units).
-//   S = K q : mma.m16n8k16 with A = the K tile [16 keys x 16 dims] (ldmatrix from the 128-byte-swizzled rows TMA
-//             wrote), B = q with column 0 = f16 hi part, column 1 = lo part -> score(key) = c(col 0) + c(col 1), exact
-//             to fp32 products; the scores of keys g / g+8 live in lanes (g, tg = 0).
-//   o += V^T p: A = V^T [16 dims x 16 keys] (ldmatrix.trans of the same row-major rows), B = p with columns hi | lo.
-// Running max m is warp-uniform; the running sum l is kept per lane and reduced once at the end.
+// Single-query attention of ONE head on the tensor cores in blocks of 32 keys, flash style (log2 units), WITHOUT any
+// cross-lane data movement between the score and the value products:
+//   S = q K^T : A = q (MMA rows 0-7 = f16 hi part, rows 8-15 = lo part, each replicated), B = K^T: MMA group j takes the
+//               keys 8j .. 8j + 7 as its columns, B fragments by ldmatrix.x4 (non-transposed) from the 128-byte-swizzled
+//               K rows TMA wrote.  Lane (g, tg) ends up with the scores of keys 8j + 2tg, 8j + 2tg + 1 (j = 0..3; hi row
+//               + lo row added in the lane), replicated over g.
+//   o += V^T p: A = V^T [16 dims x 16 keys] by ldmatrix.x4.trans of the row-major V rows, B = p with even columns = f16
+//               hi parts, odd columns = lo parts: for k-tile kt lane (g, tg) must supply keys 16kt + 2tg (+1) and
+//               16kt + 8 + 2tg (+1) - exactly the scores it owns (groups 2kt and 2kt + 1).  o(dim) = c(even col) +
+//               c(odd col), replicated over tg.
+// Running max m is warp-uniform; the running sum l is a per-lane partial over the lane's own keys (replicated over g).
 struct AttnT {
   float m, l;
   float o[4][4];
 };
-__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint4& r) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint4& r) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-}
-__device__ __forceinline__ void attn_init(AttnT& st) {
-  st.m = -INFINITY;
-  st.l = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) st.o[i][j] = 0.f;
-}
-// q of one utterance is kept as f16 hi and lo parts in B-fragment order: element d (k-tile kt = d / 16, r = d % 16)
-// lives at index ((tg * 4 + kt) * 4 + slot), tg = (r % 8) / 2, slot = (r / 8) * 2 + (r % 2), so that lane (g, tg) reads
-// its four k-tile fragments {b0, b1} with two LDS.128 (g = 0: hi part = MMA column 0, g = 1: lo part = column 1).
-__device__ __forceinline__ int q_frag_index(int d) {
-  const int kt = d >> 4, r = d & 15;
-  return (((r & 7) >> 1) * 4 + kt) * 4 + (r >> 3) * 2 + (r & 1);
+// q of one utterance: 64 half2 words [tg 4][k-tile 4][a0 = hi pair 0, a1 = lo pair 0, a2 = hi pair 1, a3 = lo pair 1] with
+// pair 0 = dims 16 kt + 2 tg (+1), pair 1 = dims 16 kt + 8 + 2 tg (+1): lane (g, tg) loads its four A fragments with four
+// LDS.128 (all g read the same words: broadcast).
+__device__ __forceinline__ int q_word_index(int d) {
+  const int r = d & 15;
+  return ((((r & 7) >> 1) * 4 + (d >> 4)) * 4) + (r >> 3) * 2;
 }
 // f16 hi | lo split of a pair of values
 __device__ __forceinline__ void hilo2(float a, float b, __half2& hi, __half2& lo) {
@@ -533,42 +531,56 @@ __device__ __forceinline__ void hilo2(float a, float b, __half2& hi, __half2& lo
   const float2 f = __half22float2(hi);
   lo = __floats2half2_rn(a - f.x, b - f.y);
 }
-__device__ __forceinline__ void q_store2(f16* q_hi, f16* q_lo, int u, int d, float y0, float y1) {   // dims d (even), d+1
+__device__ __forceinline__ void q_store2(__half2* q, float* qf, int u, int d, float y0, float y1) {   // dims d (even), d+1
   __half2 hi, lo;
   hilo2(y0, y1, hi, lo);
-  const int i = u * 64 + q_frag_index(d);
-  *reinterpret_cast<__half2*>(q_hi + i) = hi;
-  *reinterpret_cast<__half2*>(q_lo + i) = lo;
+  const int i = u * 64 + q_word_index(d);
+  q[i] = hi;
+  q[i + 1] = lo;
+  if (qf) *reinterpret_cast<float2*>(qf + u * 64 + d) = make_float2(y0, y1);   // fp32 copy: score of the current key
 }
-__device__ __forceinline__ void attn_q_frags(const f16* q_hi, const f16* q_lo, int u, uint32_t (&qf)[8]) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
-  uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
-  if (g < 2) {
-    const f16* src = (g == 0 ? q_hi : q_lo) + u * 64 + tg * 16;
-    a = lds128(src);
-    b = lds128(src + 8);
+__device__ __forceinline__ void attn_q_frags(const __half2* q, int u, uint4 (&qa)[4]) {
+  const int tg = threadIdx.x & 3;
+  const uint4* src = reinterpret_cast<const uint4*>(q + u * 64 + tg * 16);
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt) qa[kt] = src[kt];
+}
+// ldmatrix with a "memory" clobber but NOT volatile: ordered against the ring's acquire / release (which clobber
+// memory) and among themselves, while the register-only MMAs are free to move between them.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint4& r) {
+  asm("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint4& r) {
+  asm("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+      : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+}
+// scores of the 32 keys of one K tile (32 rows of 128 B, chunk c of row r stored at chunk c ^ (r & 7)); s[2j + e] <-> key
+// 8j + 2tg + e; keys >= n_valid get -inf (select, not arithmetic: rows past the valid keys may hold anything)
+__device__ __forceinline__ void qk_block(uint32_t kbase, int n_valid, const uint4 (&qa)[4], float (&s)[8]) {
+  const int lane = threadIdx.x & 31, tg = lane & 3, mat = lane >> 3, r = lane & 7;
+  const uint32_t row = kbase + r * 128;
+  uint4 kf[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {                                  // all eight loads first, then the sixteen MMAs
+    ldsm_x4(row + j * 1024 + ((mat ^ r) << 4), kf[j][0]);        // dims 0..31  (chunks 0..3): k-tiles 0, 1
+    ldsm_x4(row + j * 1024 + (((mat + 4) ^ r) << 4), kf[j][1]);  // dims 32..63 (chunks 4..7): k-tiles 2, 3
   }
-  qf[0] = a.x; qf[1] = a.y; qf[2] = a.z; qf[3] = a.w;
-  qf[4] = b.x; qf[5] = b.y; qf[6] = b.z; qf[7] = b.w;
-}
-// Tiles of up to 16 keys.  kbase / vbase = shared address of the tile's first K / V row (rows of 128 B, 16-byte
-// chunk c of row r stored at chunk c ^ (r & 7): TMA SWIZZLE_128B; tiles start on multiples of 8 rows).
-// SINGLE: the tile is ONE row (the current step's k_t / v_t) replicated to all 16 key positions, keys >= 1 masked.
-template <bool SINGLE>
-__device__ __forceinline__ void qk_tile(uint32_t kbase, int n_valid, const uint32_t (&qf)[8], float& sa, float& sb,
-                                        int swz = 0) {
-  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3, mat = lane >> 3, r = lane & 7;
-  float sc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  const int key = SINGLE ? 0 : (mat & 1) * 8 + r;
-  const int xr = SINGLE ? swz : key;                 // swizzle key: the row's index within its 8-row group
-  const uint32_t row = kbase + key * 128;
-  uint4 a[4];
 #pragma unroll
-  for (int kt = 0; kt < 4; ++kt) ldsm_x4(row + ((((2 * kt + (mat >> 1)) ^ xr) & 7) << 4), a[kt]);
+  for (int j = 0; j < 4; ++j) {
+    float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
+    mma16816(ca, qa[0], kf[j][0].x, kf[j][0].y);
+    mma16816(cb, qa[1], kf[j][0].z, kf[j][0].w);
+    mma16816(ca, qa[2], kf[j][1].x, kf[j][1].y);
+    mma16816(cb, qa[3], kf[j][1].z, kf[j][1].w);
+    s[2 * j] = (ca[0] + cb[0]) + (ca[2] + cb[2]);                // key 8j + 2tg      (hi row + lo row)
+    s[2 * j + 1] = (ca[1] + cb[1]) + (ca[3] + cb[3]);            // key 8j + 2tg + 1
+  }
+  if (n_valid < 32) {
 #pragma unroll
-  for (int kt = 0; kt < 4; ++kt) mma16816(sc[kt & 1], a[kt], qf[2 * kt], qf[2 * kt + 1]);
-  sa = (tg == 0 && g < n_valid) ? (sc[0][0] + sc[1][0]) + (sc[0][1] + sc[1][1]) : -INFINITY;        // key g (lanes tg == 0)
-  sb = (tg == 0 && g + 8 < n_valid) ? (sc[0][2] + sc[1][2]) + (sc[0][3] + sc[1][3]) : -INFINITY;    // key g + 8
+    for (int i = 0; i < 8; ++i)
+      if (8 * (i >> 1) + 2 * tg + (i & 1) >= n_valid) s[i] = -INFINITY;
+  }
 }
 // exp2 on the SFU (ex2.approx.ftz: 2 ulp, -inf -> +0); the library exp2f costs three more instructions per value
 __device__ __forceinline__ float ex2(float x) {
@@ -576,108 +588,112 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// p -> (f16 hi part) | (f16 lo part) << 16 with hi + lo == p to 2^-17 relative
-__device__ __forceinline__ uint32_t hilo_pack(float p) {
-  const float r = p - __half2float(__float2half_rn(p));
-  uint32_t x;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(r), "f"(p));   // upper half = f16(r), lower half = f16(p)
-  return x;
-}
-// B fragment of the probabilities: lane (g, tg) holds keys 2tg, 2tg+1 (b0) and 2tg+8, 2tg+9 (b1) of column g.  Column
-// 0 carries the f16 hi parts, column 1 the lo parts; the other columns are never read (they repeat hi / lo by the
-// parity of g, so no lane needs a zero).  xa / xb: hilo_pack of the probabilities of keys g / g + 8 (lanes tg == 0).
-// Always called by the whole warp, outside data-dependent branches (plain SHFL, no divergence guards).
-__device__ __forceinline__ void p_frags(uint32_t xa, uint32_t xb, uint32_t& b0, uint32_t& b1) {
-  const int lane = threadIdx.x & 31, tg = lane & 3;
-  const uint32_t sel = (lane & 4) ? 0x7632u : 0x5410u;
-  const uint32_t a0 = __shfl_sync(0xffffffffu, xa, 8 * tg), a1 = __shfl_sync(0xffffffffu, xa, 8 * tg + 4);
-  const uint32_t c0 = __shfl_sync(0xffffffffu, xb, 8 * tg), c1 = __shfl_sync(0xffffffffu, xb, 8 * tg + 4);
-  b0 = __byte_perm(a0, a1, sel);
-  b1 = __byte_perm(c0, c1, sel);
-}
-template <bool SINGLE>
-__device__ __forceinline__ void pv_tile(AttnT& st, uint32_t vbase, uint32_t b0, uint32_t b1, int swz = 0) {
-  const int lane = threadIdx.x & 31, mat = lane >> 3, r = lane & 7;
-  const int key = SINGLE ? 0 : (mat >> 1) * 8 + r;
-  const int xr = SINGLE ? swz : key;
-  const uint32_t row = vbase + key * 128;
-  uint4 a[4];
+// B fragments of the probabilities p[2j + e] <-> key 8j + 2tg + e: k-tile kt needs {b0 = keys 16kt + 2tg (+1), b1 = keys
+// 16kt + 8 + 2tg (+1)} = pack(p[4kt], p[4kt+1]), pack(p[4kt+2], p[4kt+3]); even g supply the f16 hi parts (even MMA
+// columns), odd g the lo parts.
+__device__ __forceinline__ void p_pack(const float (&p)[8], uint32_t (&pb)[4]) {
+  const bool lo_lane = (threadIdx.x >> 2) & 1;
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) ldsm_x4_trans(row + ((((2 * mt + (mat & 1)) ^ xr) & 7) << 4), a[mt]);
-#pragma unroll
-  for (int mt = 0; mt < 4; ++mt) mma16816(st.o[mt], a[mt], b0, b1);
-}
-// Attention of this warp's utterance slot `au` over n_keys rows streamed through the ring as super-chunks of up to SC
-// K stages followed by the matching V stages ([utterance slot][RPS rows][128 B] each); warp partition `apart` owns
-// tiles TPW apart .. TPW apart + TPW - 1 of every stage.  All scores of a super-chunk are computed first (independent
-// MMAs), then ONE max / exp / sum, then all P V products: one softmax dependency chain per super-chunk instead of one
-// per tile.  Additionally the single current row of the self attention (k_t at cur_kb, v_t at cur_kb + 128; 0 for the
-// warps that do not own it and for the cross attention), merged into the first chunk.  n_keys rows are streamed (uniform over the CTA); only the
-// first n_mine of them are valid keys of THIS warp's utterance (key padding: cross attention with encoder lengths), the
-// rest are masked.  Control flow: stage presence (s < ns) is CTA-uniform; the shuffles of the softmax sit outside every
-// thread-dependent branch (masked tiles carry score -inf -> p = 0), only ldmatrix / MMA blocks are skipped per tile.
-template <class S, int SC>
-__device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t (&qf)[8], int n_keys, int n_mine,
-                                          bool active, int au, int apart, uint32_t cur_kb, int cur_swz) {
-  constexpr int RPS = S::RPS, TPW = S::TPW;
-  float ca = -INFINITY;
-  bool cur = cur_kb != 0;
-  {
-    float cb;
-    if (cur) qk_tile<true>(cur_kb, 1, qf, ca, cb, cur_swz);
+  for (int i = 0; i < 4; ++i) {
+    __half2 hi, lo;
+    hilo2(p[2 * i], p[2 * i + 1], hi, lo);
+    const __half2 v = lo_lane ? lo : hi;
+    pb[i] = *reinterpret_cast<const uint32_t*>(&v);
   }
-  const uint32_t slot_off = au * RPS * 128 + apart * (TPW * 2048);
+}
+// o += V^T p for one value tile (32 rows of 128 B, swizzled like K)
+__device__ __forceinline__ void pv_block(uint32_t vbase, AttnT& st, const uint32_t (&pb)[4]) {
+  const int lane = threadIdx.x & 31, mat = lane >> 3, r = lane & 7;
+  const uint32_t row = vbase + ((mat >> 1) * 8 + r) * 128;       // matrices 0, 1: keys 16kt + r; 2, 3: keys 16kt + 8 + r
+  uint4 vf[4][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {                               // all eight loads first, then the eight MMAs
+    const uint32_t ch = (((2 * mt + (mat & 1)) ^ r) & 7) << 4;   // matrices 0, 2: dims 16mt .. +7; 1, 3: dims 16mt + 8 ..
+    ldsm_x4_trans(row + ch, vf[mt][0]);
+    ldsm_x4_trans(row + 2048 + ch, vf[mt][1]);
+  }
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt) {
+    mma16816(st.o[mt], vf[mt][0], pb[0], pb[1]);
+    mma16816(st.o[mt], vf[mt][1], pb[2], pb[3]);
+  }
+}
+// State before the first streamed key: empty, or (self attention, the warp that owns it) the CURRENT key k_t / v_t taken
+// from shared memory: score = q . k_t in fp32 (q: fp32 copy; k_t | v_t: the f16 rows about to be appended, their 16-byte
+// chunks swizzled by t & 7), p = 1, o = v_t.
+__device__ __forceinline__ void attn_init(AttnT& st, const float* qf, const f16* kv_row_u, int swz) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  st.m = -INFINITY;
+  st.l = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st.o[i][j] = 0.f;
+  if (qf) {   // warp-uniform
+    const float2 q2 = *reinterpret_cast<const float2*>(qf + 2 * lane);
+    const int d = 2 * lane, pos = (((d >> 3) ^ swz) << 3) + (d & 7);
+    const float2 k2 = __half22float2(*reinterpret_cast<const __half2*>(kv_row_u + pos));
+    st.m = warp_sum(fmaf(q2.x, k2.x, q2.y * k2.y));
+    st.l = tg == 0 ? 1.f : 0.f;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {                             // dims 16mt + g, 16mt + g + 8: chunks 2mt, 2mt + 1
+      st.o[mt][0] = __half2float(kv_row_u[64 + (((2 * mt) ^ swz) << 3) + g]);
+      st.o[mt][2] = __half2float(kv_row_u[64 + (((2 * mt + 1) ^ swz) << 3) + g]);
+    }
+  }
+}
+// Attention of this warp's (utterance slot au, key partition apart) over n_keys rows streamed through the ring as
+// super-chunks of up to SC K stages followed by the matching V stages; a stage holds, per utterance slot, WPU blocks of
+// 32 keys ([slot][RPS rows][128 B]) and warp (au, apart) owns block apart of every stage.  All scores of a super-chunk are computed first, then ONE max / exp / sum, then all P V products.  n_keys rows
+// are streamed (uniform over the CTA); only the first n_mine are valid keys of THIS warp's utterance (key padding), the
+// rest are masked.  Stage presence (s < ns) is CTA-uniform; blocks without a valid key skip their math only.
+template <class S, int SC>
+__device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint4 (&qa)[4], int n_keys, int n_mine,
+                                          bool active, int au, int apart) {
+  constexpr int RPS = S::RPS;
+  const uint32_t blk_off = (au * S::WPU + apart) * 4096;
+  const int lane = threadIdx.x & 31, tg = lane & 3;
   int c0 = 0;
 #pragma unroll 1
-  do {
+  while (c0 < n_keys) {
     const int nk = min(SC * RPS, n_keys - c0);                  // CTA-uniform
     const int ns = (nk + RPS - 1) / RPS;
-    const int lim = active ? min(nk, n_mine - c0) - 16 * TPW * apart : 0;   // my valid rows from my first tile of stage 0
-    float sa[SC][TPW], sb[SC][TPW];
-    float mx = ca;
-#pragma unroll
-    for (int s = 1; s < SC; ++s) c.peek(s);                     // K stages of this super-chunk (stage 0: peeked earlier)
+    const int lim = active ? n_mine - c0 - 32 * apart : 0;      // my valid keys counted from my block of stage 0
+    float sc[SC][8];
+    float mx = -INFINITY;
 #pragma unroll
     for (int s = 0; s < SC; ++s) {
 #pragma unroll
-      for (int j = 0; j < TPW; ++j) sa[s][j] = sb[s][j] = -INFINITY;
+      for (int i = 0; i < 8; ++i) sc[s][i] = -INFINITY;
       if (s < ns) {
-        const uint32_t stg = smem_u32(c.acquire()) + slot_off;
+        const uint32_t stg = smem_u32(c.acquire()) + blk_off;
         const int n = lim - s * RPS;
+        if (n > 0) {
+          qk_block(stg, n, qa, sc[s]);
 #pragma unroll
-        for (int j = 0; j < TPW; ++j)
-          if (n > 16 * j) {
-            qk_tile<false>(stg + j * 2048, n - 16 * j, qf, sa[s][j], sb[s][j]);
-            mx = fmaxf(mx, fmaxf(sa[s][j], sb[s][j]));
-          }
+          for (int i = 0; i < 8; ++i) mx = fmaxf(mx, sc[s][i]);
+        }
         c.release();
       }
     }
-#pragma unroll
-    for (int s = 0; s < SC; ++s) c.peek(s);                     // the V stages, under the softmax
-    // scores live in the lanes tg == 0 (-inf elsewhere): fold the 8 key rows, then broadcast
-#pragma unroll
-    for (int o = 16; o >= 4; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const float m_new = fmaxf(st.m, __shfl_sync(0xffffffffu, mx, 0));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));        // the four tg lanes own different keys
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float m_new = fmaxf(st.m, mx);
     const float m_use = (m_new == -INFINITY) ? 0.f : m_new;     // a warp without any key: every p = ex2(-inf) = 0
     const float alpha = ex2(st.m - m_use);
     float lsum = 0.f;
-    uint32_t pb0[SC][TPW], pb1[SC][TPW], cb0 = 0, cb1 = 0;
+    uint32_t pb[SC][4];
 #pragma unroll
     for (int s = 0; s < SC; ++s)
       if (s < ns) {
+        float pr[8];
 #pragma unroll
-        for (int j = 0; j < TPW; ++j) {
-          const float pa = ex2(sa[s][j] - m_use), pb = ex2(sb[s][j] - m_use);
-          lsum += pa + pb;
-          p_frags(hilo_pack(pa), hilo_pack(pb), pb0[s][j], pb1[s][j]);
+        for (int i = 0; i < 8; ++i) {
+          pr[i] = ex2(sc[s][i] - m_use);
+          lsum += pr[i];
         }
+        p_pack(pr, pb[s]);
       }
-    {
-      const float pa = ex2(ca - m_use);                          // -inf -> 0 when this warp has no current row
-      lsum += pa;
-      p_frags(hilo_pack(pa), 0u, cb0, cb1);
-    }
     st.l = st.l * alpha + lsum;
     st.m = m_new;
 #pragma unroll
@@ -687,25 +703,21 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint32_t
 #pragma unroll
     for (int s = 0; s < SC; ++s)
       if (s < ns) {
-        const uint32_t stg = smem_u32(c.acquire()) + slot_off;
-        const int n = lim - s * RPS;
-#pragma unroll
-        for (int j = 0; j < TPW; ++j)
-          if (n > 16 * j) pv_tile<false>(st, stg + j * 2048, pb0[s][j], pb1[s][j]);
+        const uint32_t stg = smem_u32(c.acquire()) + blk_off;
+        if (lim - s * RPS > 0) pv_block(stg, st, pb[s]);
         c.release();
       }
-    c.peek(0);                                                  // next super-chunk's / next phase's first stage
-    if (cur) pv_tile<true>(st, cur_kb + 128, cb0, cb1, cur_swz);
-    cur = false;
-    ca = -INFINITY;
     c0 += SC * RPS;
-  } while (c0 < n_keys);
+  }
+  (void)tg;
 }
 // merge the key partitions of every utterance slot and emit o (f16 hi + lo rows, stride 96 elements)
 template <class S>
 __device__ __forceinline__ void attn_finish(AttnT& st, int GU, float* part_buf, float* stat, f16* o_hi, f16* o_lo) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
-  const float l = warp_sum(st.l);
+  float l = st.l;                                               // per-lane partial over the lane's keys, replicated over g
+  l += __shfl_xor_sync(0xffffffffu, l, 1);
+  l += __shfl_xor_sync(0xffffffffu, l, 2);
   if (tg == 0) {
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
@@ -722,14 +734,14 @@ __device__ __forceinline__ void attn_finish(AttnT& st, int GU, float* part_buf, 
     const int uu = d >> 6, dd = d & 63;
     float mm = -INFINITY;
 #pragma unroll
-    for (int pI = 0; pI < S::WPU; ++pI) mm = fmaxf(mm, stat[pI * S::GUP + uu]);
+    for (int pI = 0; pI < S::WPU; ++pI) mm = fmaxf(mm, stat[uu * S::WPU + pI]);
     float t = 0.f, ls = 0.f;
 #pragma unroll
     for (int pI = 0; pI < S::WPU; ++pI) {
-      const float mw = stat[pI * S::GUP + uu];
+      const float mw = stat[uu * S::WPU + pI];
       const float f = (mw == -INFINITY) ? 0.f : ex2(mw - mm);
-      t += part_buf[(pI * S::GUP + uu) * 64 + dd] * f;
-      ls += stat[NCW + pI * S::GUP + uu] * f;
+      t += part_buf[(uu * S::WPU + pI) * 64 + dd] * f;
+      ls += stat[NCW + uu * S::WPU + pI] * f;
     }
     const float y = ls > 0.f ? t / ls : 0.f;
     const f16 hh = __float2half_rn(y);
@@ -765,8 +777,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
   f16* hid_lo = reinterpret_cast<f16*>(smem + sm.hid_lo);
   f16* o_hi = reinterpret_cast<f16*>(smem + sm.o_hi);
   f16* o_lo = reinterpret_cast<f16*>(smem + sm.o_lo);
-  f16* q_hi = reinterpret_cast<f16*>(smem + sm.q);
-  f16* q_lo = q_hi + GUP * 64;
+  __half2* q_frag = reinterpret_cast<__half2*>(smem + sm.q);   // [GUP][64] hi | lo words in A-fragment order
   f16* kv_row = reinterpret_cast<f16*>(smem + sm.kvrow);
   float4* scratch = reinterpret_cast<float4*>(smem + sm.scratch);
   float* prm = reinterpret_cast<float*>(smem + sm.prm);
@@ -781,7 +792,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sm.bars);
   ring.full = bars;
   ring.empty = bars + MAX_STAGES;
-  uint64_t* xbar = bars + 2 * MAX_STAGES;       // [2] all-reduce parity barriers
+  uint64_t* xbar = bars + 2 * MAX_STAGES;       // all-reduce: [0] reduce-scatter, [1] all-gather
   uint64_t* abar = xbar + 2;                    // [2] argmax exchange parity barriers
 
   const int rank = int(cluster_ctarank());
@@ -802,12 +813,12 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
     fence_barrier_init();
   }
   // zero every activation buffer once: rows of absent utterances (u >= GU) stay zero for the whole decode
-  for (uint32_t i = sm.h / 4 + tid; i < sm.scratch / 4; i += NTHREADS) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
+  for (uint32_t i = sm.h / 4 + tid; i < sm.prm / 4; i += NTHREADS) reinterpret_cast<uint32_t*>(smem)[i] = 0u;
   if (tid < 16) s_tok[tid] = 0;
   __syncthreads();
   cluster_sync_all();   // peers' barriers are initialised before any remote store can arrive
 
-  const int Lc = (p.L + 15) & ~15;                                // cache rows per (layer, utterance, head, K|V)
+  const int Lc = (p.L + 31) & ~31;                                // cache rows per (layer, utterance, head, K|V): 32-key blocks
   const size_t cache_head = size_t(2) * Lc * 64;                  // elements per (layer, utterance, head): K rows | V rows
   const uint8_t* my_image = p.image + size_t(rank) * p.rank_bytes;
 
@@ -846,7 +857,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
               const int nk = min(S::SCX * RPS, t - c0);
               for (int kv = 0; kv < 2; ++kv)               // K stages of the super-chunk, then its V stages
                 for (int r0 = 0; r0 < nk; r0 += RPS) {
-                  const int n = (min(RPS, nk - r0) + 15) & ~15;   // whole 16-key tiles (rows past t are zero)
+                  const int n = (min(RPS, nk - r0) + 31) & ~31;   // whole 32-key blocks (rows past t are zero)
                   uint8_t* dst = pr.begin(uint32_t(GU) * n * 128u);
                   if (plane < GU)
                     bulk_load(dst + plane * RPS * 128, cbase + size_t(kv) * Lc * 64 + size_t(c0 + r0) * 64, n * 128,
@@ -892,7 +903,8 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
     long long t_xchg = 0;
     uint32_t n_xchg = 0, n_arg = 0;
     const int lane = tid & 31;
-    const int au = warp % GUP, apart = warp / GUP;                  // attention: utterance slot / 16-key tile of a stage
+    const int au = warp / S::WPU, apart = warp % S::WPU;            // attention: utterance slot / 32-key block of a stage
+    float* q_f32 = reinterpret_cast<float*>(smem + sm.qf);
     const bool a_active = au < GU;
     // key-padding mask of the cross attention: encoder frames >= enc_lens[utterance] are not attended (nullable)
     const int n_cross = (p.enc_lens && a_active) ? max(0, min(p.Tp, p.enc_lens[ubase + au])) : p.Tp;
@@ -906,53 +918,93 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
           *reinterpret_cast<const float4*>(p.h0 + size_t(ubase) * D + i);
     consumer_sync();
 
-    // partial sums over the full model dimension (this CTA's K-slice) -> all-reduce across the cluster:
-    // h[u][n] += sum over ranks + bias[n].  Called right after the mm_stream that sent the partial tiles.
-    // peer windows of the receive buffer / parity barriers, mapped once (mapa is linear inside a CTA's window);
-    // peer k = rank (rank + 1 + k) % CS
-    uint32_t peer_recv[CS - 1], peer_bar[CS - 1];
+    // Partial sums over the full model dimension (this CTA's K-slice) -> all-reduce across the cluster, as a REDUCE-SCATTER
+    // followed by an ALL-GATHER: h[u][n] += sum over ranks + bias[n].
+    //   1. (matmul epilogue, send_partial) every partial tile goes straight to the CTA that owns its 64 columns (rank
+    //      n / 64), into that CTA's receive slot of the sender: recv[src][u][64] fp32, 8-byte st.async + complete_tx on the
+    //      owner's barrier xbar[0];
+    //   2. the owner adds the CS slots in rank order (deterministic), the residual and the bias for its GUP x 64 slice and
+    //      writes the new residual values into EVERY CTA's copy of the residual stream s_h (st.async, barrier xbar[1]);
+    //   3. every CTA normalises the full rows locally (all_reduce_finish tail).
+    // Against all-gathering the partials (every CTA summing everything) this moves 2 x 6 KB instead of 24 KB into each
+    // CTA at 8 utterances, sums a quarter of the elements, and needs an 8 KB receive buffer instead of 64 KB - shared
+    // memory that is ring depth now (3 -> 5 stages at 8 utterances per cluster).  Neither buffer is double-buffered: a CTA
+    // can only send step n + 1 after it has completed step n, i.e. after it holds the step-n slice of every peer, and a
+    // peer sends its slice only after it has finished reading its receive slots (and every CTA's s_h readers of step n
+    // are done before that CTA sends its partials of step n + 1, without which nobody can produce a step n + 1 slice).
+    // Both barriers simply alternate phases.  Windows of every rank (own included: the data path is uniform):
+    uint32_t all_recv[CS], all_h[CS], all_bar[CS];
 #pragma unroll
-    for (int k = 0; k < CS - 1; ++k) {
-      const uint32_t r = uint32_t(rank + 1 + k) % CS;
-      peer_recv[k] = mapa_u32(smem_u32(recv), r);
-      peer_bar[k] = mapa_u32(smem_u32(&xbar[0]), r);
+    for (int r = 0; r < CS; ++r) {
+      all_recv[r] = mapa_u32(smem_u32(recv), uint32_t(r));
+      all_h[r] = mapa_u32(smem_u32(s_h), uint32_t(r));
+      all_bar[r] = mapa_u32(smem_u32(&xbar[0]), uint32_t(r));
     }
-    // Residual stream s_h and the receive slots are [utterance][D] fp32 with skewed columns (hswz).
+    // Residual stream s_h ([utterance][D]) and the receive slots ([source rank][utterance][64]) are fp32 rows with skewed
+    // columns (hswz).
     auto send_partial = [&](int n, int u0, const float4& v) {     // v = {(n,u0), (n,u0+1), (n+1,u0), (n+1,u0+1)}
-      const uint32_t par = n_xchg & 1u;
-      const uint32_t off0 = uint32_t(((size_t(par) * CS + rank) * GUP + u0) * D + (n ^ hswz(u0))) * 4u;
-      const uint32_t off1 = uint32_t(((size_t(par) * CS + rank) * GUP + u0 + 1) * D + (n ^ hswz(u0 + 1))) * 4u;
-      *reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(recv) + off0) = make_float2(v.x, v.z);
-      *reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(recv) + off1) = make_float2(v.y, v.w);
+      const int dst = n >> 6, nn = n & 63;
+      const uint32_t off0 = uint32_t((rank * GUP + u0) * 64 + (nn ^ hswz(u0))) * 4u;
+      const uint32_t off1 = uint32_t((rank * GUP + u0 + 1) * 64 + (nn ^ hswz(u0 + 1))) * 4u;
+      uint32_t base = all_recv[0], bar = all_bar[0];
 #pragma unroll
-      for (int k = 0; k < CS - 1; ++k) {
-        st_async_v2(peer_recv[k] + off0, v.x, v.z, peer_bar[k] + par * 8u);
-        st_async_v2(peer_recv[k] + off1, v.y, v.w, peer_bar[k] + par * 8u);
-      }
+      for (int r = 1; r < CS; ++r)
+        if (dst == r) {
+          base = all_recv[r];
+          bar = all_bar[r];
+        }
+      st_async_v2(base + off0, v.x, v.z, bar);
+      st_async_v2(base + off1, v.y, v.w, bar);
     };
-    // ... and, fused into its tail, what follows every all-reduce: LayerNorm of the new rows (gam != nullptr) or the
-    // plain f16 hi | lo split (classifier input).  The GUP x D elements are dealt to the warps as blocks of 2 utterances
-    // x 16 column pairs: lane -> utterance 2 up + (lane & 1), columns n, n + 1 with n = 32 j + 2 (lane >> 1); a warp
-    // always serves the same utterance pair up = warp % (GUP / 2).  Every shared-memory access of the tail is then a
-    // conflict-free 8-byte (fp32 pair) or 4-byte (f16 pair) word per lane.  The new values stay in registers between the
-    // sum and the normalisation; variance from one pass over (x - c), c = an element of the row's previous value.
+    // ... and what follows every all-reduce: LayerNorm of the new rows (gam != nullptr) or the plain f16 hi | lo split
+    // (classifier input).  Elements are dealt to the warps as blocks of 2 utterances x 16 column pairs: lane -> utterance
+    // 2 up + (lane & 1), columns n, n + 1 with n = 32 j + 2 (lane >> 1); a warp always serves the same utterance pair up =
+    // warp % (GUP / 2).  Every shared-memory access is then a conflict-free 8-byte (fp32 pair) or 4-byte (f16 pair) word
+    // per lane.  Variance from one pass over (x - c), c = an element of the row.
     auto all_reduce_finish = [&](const float* bias, const float* gam, const float* bet) {
       constexpr int UP = GUP / 2, NB = UP * (D / 32), BPW = (NB + NCW - 1) / NCW;
-      static_assert(NCW % UP == 0 && (NB % NCW == 0 || NB < NCW), "all-reduce block split");
-      const uint32_t par = n_xchg & 1u, phase = (n_xchg >> 1) & 1u;
+      constexpr int NBS = UP * 2;                               // blocks of this CTA's 64-column slice (<= NCW)
+      static_assert(NCW % UP == 0 && (NB % NCW == 0 || NB < NCW) && NBS <= NCW, "all-reduce block split");
+      const uint32_t phase = n_xchg & 1u;
       const int up = warp % UP, u = 2 * up + (lane & 1), sw = hswz(u);
       float* hrow = s_h + u * D;
-      const float c0 = hrow[0];
-      if (tid == 0) mbar_expect_tx(&xbar[par], uint32_t(CS - 1) * D * GUP * 4u);
-      consumer_sync();                                     // own slot written by every thread; c0 read by every thread
+      if (tid == 0) {
+        mbar_expect_tx(&xbar[0], uint32_t(CS) * 64 * GUP * 4u);
+        mbar_expect_tx(&xbar[1], uint32_t(CS) * 64 * GUP * 4u);
+      }
       if (timed) {
         const long long w0 = clock64();
-        mbar_wait_cluster(&xbar[par], phase);
+        mbar_wait_cluster(&xbar[0], phase);
         t_xchg += clock64() - w0;
       } else {
-        mbar_wait_cluster(&xbar[par], phase);
+        mbar_wait_cluster(&xbar[0], phase);
       }
-      const float* rv = recv + (size_t(par) * CS * GUP + u) * D;
+      // ---- reduce: this CTA's slice, one column pair per thread of the first NBS warps
+      if (warp < NBS) {
+        const int nn = (warp / UP) * 32 + (lane >> 1) * 2, pos = nn ^ sw, n = rank * 64 + nn;
+        float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < CS; ++r) {
+          const float2 w = *reinterpret_cast<const float2*>(recv + (r * GUP + u) * 64 + pos);
+          sum.x += w.x;
+          sum.y += w.y;
+        }
+        const float2 b = *reinterpret_cast<const float2*>(bias + n);
+        const float2 h = *reinterpret_cast<const float2*>(hrow + (n ^ sw));
+        const float hx = h.x + (sum.x + b.x), hy = h.y + (sum.y + b.y);
+        const uint32_t off = uint32_t(u * D + (n ^ sw)) * 4u;
+#pragma unroll
+        for (int r = 0; r < CS; ++r) st_async_v2(all_h[r] + off, hx, hy, all_bar[r] + 8u);
+      }
+      if (timed) {
+        const long long w0 = clock64();
+        mbar_wait_cluster(&xbar[1], phase);
+        t_xchg += clock64() - w0;
+      } else {
+        mbar_wait_cluster(&xbar[1], phase);
+      }
+      // ---- the new rows are complete in s_h: normalise
+      const float c0 = hrow[0];
       float2 hv[BPW];
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -960,18 +1012,8 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
         const int blk = warp + NCW * k;
         hv[k] = make_float2(c0, c0);
         if (NB % NCW == 0 || blk < NB) {
-          const int n = (blk / UP) * 32 + (lane >> 1) * 2, pos = n ^ sw;
-          float2 s = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int r = 0; r < CS; ++r) {
-            const float2 w = *reinterpret_cast<const float2*>(rv + size_t(r) * GUP * D + pos);
-            s.x += w.x;
-            s.y += w.y;
-          }
-          const float2 b = *reinterpret_cast<const float2*>(bias + n);
-          const float2 h = *reinterpret_cast<const float2*>(hrow + pos);
-          hv[k] = make_float2(h.x + (s.x + b.x), h.y + (s.y + b.y));
-          if (u < GU) *reinterpret_cast<float2*>(hrow + pos) = hv[k];
+          const int n = (blk / UP) * 32 + (lane >> 1) * 2;
+          hv[k] = *reinterpret_cast<const float2*>(hrow + (n ^ sw));
           const float d0 = hv[k].x - c0, d1 = hv[k].y - c0;
           s1 += d0 + d1;
           s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
@@ -1071,15 +1113,15 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
           const float* ar_gam;
           if (pass < 2) {
             int n_keys, n_mine;
-            uint32_t cur_kb = 0;
+            bool cur = false;
             if (pass == 0) {
               // ---- masked self attention (model.py:67-68): q, k, v of this head, cache append, keys 0..t
               mark(1);
               mm_stream<MQkv, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, const float4& v) {
                 const float2 b = *reinterpret_cast<const float2*>(b_qkv + n);
                 if (n < 64) {
-                  q_store2(q_hi, q_lo, u0, n, (v.x + b.x) * qscale, (v.z + b.y) * qscale);
-                  q_store2(q_hi, q_lo, u0 + 1, n, (v.y + b.x) * qscale, (v.w + b.y) * qscale);
+                  q_store2(q_frag, q_f32, u0, n, (v.x + b.x) * qscale, (v.z + b.y) * qscale);
+                  q_store2(q_frag, q_f32, u0 + 1, n, (v.y + b.x) * qscale, (v.w + b.y) * qscale);
                 } else {   // k_t | v_t rows in the cache's swizzled chunk order (chunk ^ (t & 7)): TMA-stored as they are
                   const int e = n - 64, pos = (e & 64) + ((((e & 63) >> 3) ^ (t & 7)) << 3) + (e & 7);
                   *reinterpret_cast<__half2*>(kv_row + u0 * 128 + pos) = __floats2half2_rn(v.x + b.x, v.z + b.y);
@@ -1091,33 +1133,33 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
               mark(2);
               // append k_t, v_t (f16) to the device-resident cache: [layer][utterance][head][K rows | V rows][Lc][64], the
               // 16-byte chunks of row t stored swizzled (chunk ^ (t & 7)) so that the bulk copy lands ldmatrix-ready.  The
-              // first row of every 16-row block also zeroes the block's other rows: whole 16-key tiles are always finite.
+              // first row of every 32-row block also zeroes the block's other rows: whole 32-key blocks are always finite.
               if (tid < GU * 2) {                                    // one 128-byte TMA store per (utterance, K | V)
                 const int u = tid >> 1, kv = tid & 1;
                 f16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * Lc * 64 +
                             size_t(t) * 64;
                 bulk_store(dst, kv_row + u * 128 + kv * 64, 128);
               }
-              if ((t & 15) == 0) {
-                for (int i = tid; i < GU * 2 * 15 * 8; i += NCT) {
-                  const int u = i / 240, rem = i - u * 240, kv = rem / 120, w = rem - kv * 120;   // w: 16-byte word in 15 rows
+              if ((t & 31) == 0) {
+                for (int i = tid; i < GU * 2 * 31 * 8; i += NCT) {
+                  const int u = i / 496, rem = i - u * 496, kv = rem / 248, w = rem - kv * 248;   // w: 16-byte word in 31 rows
                   f16* dst = p.cache + ((size_t(l) * p.B + ubase + u) * H + rank) * cache_head + size_t(kv) * Lc * 64 +
                               size_t(t + 1) * 64 + w * 8;
                   *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
                 }
-                asm volatile("fence.proxy.async;" ::: "memory");   // generic zero fill -> later TMA reads (1 step in 16)
+                asm volatile("fence.proxy.async;" ::: "memory");   // generic zero fill -> later TMA reads (1 step in 32)
               }
               n_keys = t;
               n_mine = t;
-              cur_kb = (a_active && apart == S::WPU - 1) ? smem_u32(kv_row) + au * 256 : 0u;   // current row: from smem
+              cur = a_active && apart == S::WPU - 1;                // the current key: from shared memory (attn_init)
               ar_bias = b_o;
               ar_gam = ln + 2 * D;                              // out projection + residual (model.py:68) -> LN2 (:70)
             } else {
               // ---- cross-attention query -> attention over the encoder K/V (model.py:70-71)
               mm_stream<MWqc, GUP>(c, xh, xl, S::LDX, scratch, [&](int n, int u0, const float4& v) {
                 const float2 b = *reinterpret_cast<const float2*>(b_qc + n);
-                q_store2(q_hi, q_lo, u0, n, (v.x + b.x) * qscale, (v.z + b.y) * qscale);
-                q_store2(q_hi, q_lo, u0 + 1, n, (v.y + b.x) * qscale, (v.w + b.y) * qscale);
+                q_store2(q_frag, nullptr, u0, n, (v.x + b.x) * qscale, (v.z + b.y) * qscale);
+                q_store2(q_frag, nullptr, u0 + 1, n, (v.y + b.x) * qscale, (v.w + b.y) * qscale);
               });
               consumer_sync();
               mark(7);
@@ -1127,10 +1169,10 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
               ar_gam = ln + 4 * D;                              // -> LN3 (model.py:73)
             }
             AttnT st;
-            uint32_t qf[8];
-            attn_init(st);
-            attn_q_frags(q_hi, q_lo, au, qf);
-            attention<S, S::SCX>(c, st, qf, n_keys, n_mine, a_active, au, apart, cur_kb, t & 7);
+            uint4 qa[4];
+            attn_init(st, cur ? q_f32 + au * 64 : nullptr, kv_row + au * 128, t & 7);
+            attn_q_frags(q_frag, au, qa);
+            attention<S, S::SCX>(c, st, qa, n_keys, n_mine, a_active, au, apart);
             if (pass == 0) {
               if (tid < GU * 2) bulk_store_wait();              // this step's cache rows are written (published below)
               mark(3);
