@@ -33,7 +33,7 @@ namespace {
 #endif
 constexpr int NCW = 8;                    // consumer warps (16 measured slower: per-warp fixed costs dominate, not divisible work)
 constexpr int NCT = NCW * 32;             // consumer threads
-constexpr int NTHREADS = NCT + 32;        // + producer warp (one working thread)
+constexpr int NTHREADS = NCT + 32;        // + producer warp
 constexpr int STAGE_BYTES = 32768;
 constexpr int MAX_STAGES = 6;
 constexpr float LOG2E = 1.4426950408889634f;
@@ -217,12 +217,23 @@ struct Producer {
   int slot = 0;
   uint32_t round = 0;
   long long waited = 0;
+#ifdef ASR_TRACE
+  long long* trace = nullptr;   // diagnostic build: per stage (wait begin, armed) clocks of one step of CTA 0
+  int ntrace = 0;
+#endif
   __device__ __forceinline__ uint8_t* begin(uint32_t bytes) {
     if ((threadIdx.x & 31) == 0) {
       const long long w0 = clock64();
       mbar_wait(&r.empty[slot], (round & 1u) ^ 1u);
       waited += clock64() - w0;
       mbar_expect_tx(&r.full[slot], bytes);
+#ifdef ASR_TRACE
+      if (trace && ntrace < 256) {
+        trace[2 * ntrace] = w0;
+        trace[2 * ntrace + 1] = clock64();
+        ++ntrace;
+      }
+#endif
     }
     __syncwarp();                            // the slot is free and armed before any lane's copy can land in it
     return r.buf + size_t(slot) * STAGE_BYTES;
@@ -251,6 +262,10 @@ struct Consumer {
   int slot = 0;
   uint32_t round = 0;
   uint32_t okm = 0;        // bit i: the stage i slots ahead of the current one is known to be full
+#ifdef ASR_TRACE
+  long long* trace = nullptr;   // diagnostic build: per acquire (begin, end) clocks of one step of CTA 0 / warp 0
+  int ntrace = 0;
+#endif
 #ifdef ASR_COUNT_LATE
   long long late = 0;      // acquires that found the stage not yet full
 #endif
@@ -285,7 +300,15 @@ struct Consumer {
     uint32_t parity;
     uint64_t* b = bar_ahead(i, parity);
     if (!((okm >> i) & 1u)) {
-#ifdef ASR_COUNT_LATE
+#ifdef ASR_TRACE
+      const long long tr0 = clock64();
+      if (!mbar_try_wait(b, parity)) mbar_wait_slow(smem_u32(b), parity);
+      if (trace && ntrace < 256 && threadIdx.x == 0) {
+        trace[2 * ntrace] = tr0;
+        trace[2 * ntrace + 1] = clock64();
+        ++ntrace;
+      }
+#elif defined(ASR_COUNT_LATE)
       if (!mbar_test_wait(b, parity)) {      // diagnostic build: how long do the consumers wait for DATA?
         const long long w0 = clock64();
         if (!mbar_try_wait(b, parity)) mbar_wait_slow(smem_u32(b), parity);
@@ -718,6 +741,27 @@ __device__ __forceinline__ void attn_finish(AttnT& st, int GU, float* part_buf, 
   float l = st.l;                                               // per-lane partial over the lane's keys, replicated over g
   l += __shfl_xor_sync(0xffffffffu, l, 1);
   l += __shfl_xor_sync(0xffffffffu, l, 2);
+  if (S::WPU == 1) {   // one warp holds the whole utterance: no merge; lane (g, tg) emits dims 16 tg + g, 16 tg + g + 8
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+      if (tg == mt) {
+        a = st.o[mt][0] + st.o[mt][1];
+        b = st.o[mt][2] + st.o[mt][3];
+      }
+    if (warp < GU) {
+      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      const float y0 = a * inv, y1 = b * inv;
+      const f16 h0 = __float2half_rn(y0), h1 = __float2half_rn(y1);
+      const int i = warp * 96 + 16 * tg + g;
+      o_hi[i] = h0;
+      o_lo[i] = __float2half_rn(y0 - __half2float(h0));
+      o_hi[i + 8] = h1;
+      o_lo[i + 8] = __float2half_rn(y1 - __half2float(h1));
+    }
+    consumer_sync();
+    return;
+  }
   if (tg == 0) {
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
@@ -830,8 +874,26 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
       const uint64_t pol_kv = p.kv_evict_first ? policy_evict_first() : policy_evict_last();
       Producer pr;
       pr.r = ring;
+      // Encoder K/V comes from HBM (392 MB per step over the GPU: it cannot stay in L2), and a stage requested when its
+      // ring slot frees needs ~3 k cycles to land - more than the 4 stages of lead the ring gives in the attention
+      // phases.  So every super-chunk is prefetched into L2 one super-chunk ahead; the ring's own copies then hit L2.  The
+      // rows of an utterance are contiguous over all heads ([Tp][K | V, 2D]), so the cluster's CTAs split the rows of the
+      // super-chunk and each lane u issues ONE bulk prefetch (rows x 4D bytes) for utterance slot u.
+      auto kv_prefetch = [&](int l, int c0) {
+        if (c0 >= p.Tp || plane >= GU) return;
+        const int nk = min(S::SCX * RPS, p.Tp - c0), per = (nk + CS - 1) / CS;
+        const int r0 = rank * per, n = min(per, nk - r0);
+        if (n > 0)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.ckv + (size_t(l * p.B + ubase + plane) * p.Tp +
+                                                                               c0 + r0) * 2 * D),
+                       "r"(uint32_t(n) * 4u * D)
+                       : "memory");
+      };
 #pragma unroll 1
       for (int t = 0; t < p.L; ++t) {
+#ifdef ASR_TRACE
+        pr.trace = (p.timing && blockIdx.x == 0 && t == 64) ? p.timing + 148 * 16 + 512 : nullptr;
+#endif
         if (p.stop_at_eos) {                       // strict gate: nothing of step t is requested before step t-1 ended
           while (ctrl[0] < t && !ctrl[1]) {
           }
@@ -845,6 +907,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
             if (plane == 0) bulk_load(dst, img + p.off_small, S::SMALL_BYTES, pr.bar(), pol_w);
             pr.end();
           }
+          if (p.kv_prefetch) kv_prefetch(l, 0);
           pr.mat<MQkv>(img + p.off_qkv, pol_w);
           if (t > 0) {   // self cache rows 0..t-1 of this layer (written by this CTA in earlier steps)
             const int need = (t - 1) * p.nd + l + 1;
@@ -872,6 +935,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
             const int row0 = (l * p.B + ubase + plane) * p.Tp;   // lane u: encoder K/V rows of utterance slot u
             for (int c0 = 0; c0 < p.Tp; c0 += S::SCX * RPS) {    // 2-D boxes [RPS rows][64 columns] of this head
               const int nk = min(S::SCX * RPS, p.Tp - c0);
+              if (p.kv_prefetch) kv_prefetch(l, c0 + S::SCX * RPS);   // the NEXT super-chunk: on its way to L2 meanwhile
               for (int kv = 0; kv < 2; ++kv)
                 for (int r0 = 0; r0 < nk; r0 += RPS) {
                   uint8_t* dst = pr.begin(uint32_t(GU) * RPS * 128u);
@@ -1079,6 +1143,9 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
     int t = 0;
 #pragma unroll 1
     for (; t < p.L; ++t) {
+#ifdef ASR_TRACE
+      c.trace = (p.timing && blockIdx.x == 0 && t == 64) ? p.timing + 148 * 16 : nullptr;
+#endif
 #pragma unroll 1
       for (int l = 0; l < p.nd; ++l) {
         // ---- this layer's biases and LayerNorm parameters (one ring stage)
@@ -1432,6 +1499,12 @@ int launch_dec_cluster(ClusterParams& p, cudaStream_t s) {
   p.GU = chosen_gu;
   p.GUP = chosen->GUP;
   p.nstages = chosen_stages;
+  {
+    // L2 prefetch of the encoder K/V one super-chunk ahead: pays at 8 utterances per cluster (16.85 -> 16.44 ms per
+    // 256-utterance decode), measured slightly negative at 4 (11.17 -> 11.50 ms); "0" / "1" force it off / on
+    const char* e = std::getenv("ASR_B200_KV_PREFETCH");
+    p.kv_prefetch = (e && e[0]) ? (e[0] != '0') : (p.GUP == 8);
+  }
   {
     const char* e = std::getenv("ASR_B200_KV_POLICY");   // "first" (default: stream K/V past the L2-resident weights) / "last"
     p.kv_evict_first = !(e && e[0] == 'l');

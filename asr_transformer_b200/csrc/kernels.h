@@ -191,7 +191,7 @@ struct ClusterLayout {                        // byte layout of the packed decod
 bool cluster_layout(int D, int H, int FF, int V, int nd, ClusterLayout* out);
 struct ClusterParams {
   int B, D, H, FF, V, L, Tp, nd;
-  int GU, GUP, FFS, VS, nstages, kv_evict_first;
+  int GU, GUP, FFS, VS, nstages, kv_evict_first, kv_prefetch;
   ClusterMat m_qkv, m_wo, m_wqc, m_w1, m_w2, m_cls;
   const uint8_t* image; size_t image_bytes, rank_bytes, layer_bytes;
   size_t off_small, off_qkv, off_wo, off_wqc, off_woc, off_w1, off_w2, off_cls;
