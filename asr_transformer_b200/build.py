@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libasr_b200.so")
-SOURCES = ["tmap.cu", "gemm_tc.cu", "attn_tc.cu", "simple_ops.cu", "decode.cu", "decode_cluster.cu", "frontend.cu", "api.cu"]
+SOURCES = ["tmap.cu", "gemm_tc.cu", "attn_tc.cu", "simple_ops.cu", "conv_tc.cu", "decode.cu", "decode_cluster.cu", "frontend.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

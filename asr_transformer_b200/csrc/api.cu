@@ -548,7 +548,13 @@ int asr_workspace_bytes(const AsrHandle* h, int B, int T, int L, size_t* bytes) 
 // path, kept as the fallback for very wide inputs and as the cross-check in the tests)
 static int conv_frontend(const float* spec, const float* w1, const float* b1, const f16* w2frag, const float* b2, int B,
                          int F, int T, f16* y1, f16* z, cudaStream_t s) {
+  // ASR_B200_CONV: "" (default) tcgen05 front-end where the shape allows, else the mma.sync fused kernel, else two kernels;
+  // "fused" / "split" force the legacy paths (cross-checks in tests/test_ops_gpu.py)
   const char* e = std::getenv("ASR_B200_CONV");
+  if (!(e && (e[0] == 's' || e[0] == 'f'))) {
+    const int rc = launch_conv_tc(spec, w1, b1, w2frag, b2, B, F, T, z, s, g_split);
+    if (rc <= 0) return rc;
+  }
   if (!(e && e[0] == 's')) {
     const int rc = launch_conv_fused(spec, w1, b1, w2frag, b2, B, F, T, z, s, g_split);
     if (rc <= 0) return rc;

@@ -123,6 +123,9 @@ int launch_conv1(const float* spec, const float* w1 /*[9][64]*/, const float* b1
 // conv2: y1 -> z f16 (B, T2, F2*64) with column order (f, c)
 // conv1 + conv2 in one kernel (the f16 intermediate stays in shared memory); returns 1 if it does not fit -> use the
 // two kernels below.  w2frag: pack_conv2_fragments order.
+// tcgen05 edition of the fused front-end (conv_tc.cu; input_dim 80 only, returns 1 = not launched otherwise)
+int launch_conv_tc(const float* spec, const float* w1, const float* b1, const f16* w2frag, const float* b2, int B, int F,
+                   int T, f16* z, cudaStream_t s, int split);
 int launch_conv_fused(const float* spec, const float* w1, const float* b1, const f16* w2frag, const float* b2, int B,
                       int F, int T, f16* z, cudaStream_t s, int split = 0);
 int launch_conv2(const f16* y1, const f16* w2 /*[64 co][9][64 ci]*/, const float* b2, int B, int F1, int T1,

@@ -276,19 +276,45 @@ class Transformer(nn.Module):
         staging = self.__dict__.setdefault("_pinned_staging", {})   # pinned D2H buffers live with the model:
         # cudaHostAlloc costs milliseconds, so they are allocated once per shape and reused by every call
 
+        # Both caches hold ONE grow-only flat buffer per slot, viewed per shape: a serving loop with varying batch sizes
+        # or frame counts (length-bucketed batches) keeps a bounded set of buffers instead of one per shape.  A buffer
+        # that is outgrown may still be in use by work already queued: the device one is handed back to the allocator
+        # only after every side stream has passed this point (record_stream), the pinned one is kept alive (growth is
+        # geometric, so only a handful are ever retired).
+        retired = self.__dict__.setdefault("_retired_staging", [])
+
+        def numel(shape):
+            n = 1
+            for d in shape:
+                n *= int(d)
+            return n
+
         def pinned(t, slot):
-            key = (slot, tuple(t.shape), t.dtype)
-            if key not in staging:
-                staging[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            return staging[key]
+            key = (slot, t.dtype)
+            n = t.numel()
+            flat = staging.get(key)
+            if flat is None or flat.numel() < n:
+                if flat is not None:
+                    retired.append(flat)
+                flat = torch.empty(max(n, int(1.5 * flat.numel()) if flat is not None else n), dtype=t.dtype,
+                                   pin_memory=True)
+                staging[key] = flat
+            return flat[:n].view(t.shape)
 
         bufs = self.__dict__.setdefault("_pipe_bufs", {})
 
         def stage_buf(kind, shape):
-            key = (str(dev),) + kind + tuple(shape)
-            if key not in bufs:
-                bufs[key] = torch.empty(shape, dtype=torch.float32, device=dev)
-            return bufs[key]
+            key = (str(dev),) + kind
+            n = numel(shape)
+            flat = bufs.get(key)
+            if flat is None or flat.numel() < n:
+                if flat is not None:
+                    for st in (up_s, down_s, enc_s, dec_s):
+                        flat.record_stream(st)
+                flat = torch.empty(max(n, int(1.5 * flat.numel()) if flat is not None else n), dtype=torch.float32,
+                                   device=dev)
+                bufs[key] = flat
+            return flat[:n].view(tuple(shape))
 
         def groups():
             """Consecutive batches of one shape / placement / masking, up to `coalesce` per group.  An item is a

@@ -330,10 +330,36 @@ def test_conv_fused_equals_split(B, Fdim, T, monkeypatch):
     spec = O.structured_spectrum(B, T, Fdim, seed=4).to(DEV)
     monkeypatch.setenv("ASR_B200_CONV", "split")
     ref = front(spec)
-    monkeypatch.setenv("ASR_B200_CONV", "")
+    monkeypatch.setenv("ASR_B200_CONV", "fused")
     out = front(spec)
     sync()
     assert out.shape == ref.shape and torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("B,T", [(2, 200), (3, 1000), (1, 15), (4, 301), (2, 7)])
+def test_conv_tc_matches_fused(B, T, monkeypatch):
+    """The tcgen05 front-end (conv_tc.cu: conv2 as an implicit GEMM over parity planes of the conv1 patch) against the
+    mma.sync fused kernel: same operands (fp32 conv1, f16 hi | lo split into conv2), another fp32 summation order, so
+    equal to fp32 rounding noise; both against the oracle at the front-end tolerance.  Ragged last tiles included."""
+    import asr_transformer_b200 as A
+    torch.manual_seed(3)
+    front = A.ConvFrontEnd(torch.nn.Conv2d(1, 64, 3, stride=2), torch.nn.ReLU(), torch.nn.Conv2d(64, 64, 3, stride=2),
+                           torch.nn.ReLU())
+    with torch.no_grad():
+        for p in front.parameters():
+            O.bf16_representable_(p)
+    spec = O.structured_spectrum(B, T, 80, seed=4)
+    sd = {"input_layer." + k: v for k, v in front.state_dict().items()}
+    ref = O.frontend(sd, spec)
+    front = front.to(DEV)
+    monkeypatch.setenv("ASR_B200_CONV", "fused")
+    legacy = front(spec.to(DEV))
+    monkeypatch.setenv("ASR_B200_CONV", "")
+    out = front(spec.to(DEV))
+    sync()
+    assert out.shape == legacy.shape == ref.shape
+    assert_close(out, legacy, 2e-3, 1e-4, "tcgen05 vs mma.sync front-end")
+    assert_close(out, ref, 6e-2, 4e-3, "tcgen05 front-end vs oracle")
 
 
 def test_embed_pe():
