@@ -161,7 +161,7 @@ def attention_tensor_pipe():
     if not files:
         return None
     p = files[-1]
-    rows = [l.split("|") for l in open(p) if "attn_tc_kernel" in l]
+    rows = [r for r in (l.split("|") for l in open(p) if "attn_tc_kernel" in l) if len(r) >= 12]   # per-launch rows only
     if not rows:
         return None
     try:
