@@ -31,11 +31,17 @@ namespace {
 #ifndef ASR_PEEK_MODE
 #define ASR_PEEK_MODE 0
 #endif
-constexpr int NCW = 8;                    // consumer warps (16 measured slower: per-warp fixed costs dominate, not divisible work)
+#ifndef ASR_NCW
+#define ASR_NCW 8
+#endif
+#ifndef ASR_STAGE_KB
+#define ASR_STAGE_KB 32
+#endif
+constexpr int NCW = ASR_NCW;              // consumer warps (16 measured slower: per-warp fixed costs dominate, not divisible work)
 constexpr int NCT = NCW * 32;             // consumer threads
 constexpr int NTHREADS = NCT + 32;        // + producer warp
-constexpr int STAGE_BYTES = 32768;
-constexpr int MAX_STAGES = 6;
+constexpr int STAGE_BYTES = ASR_STAGE_KB * 1024;
+constexpr int MAX_STAGES = 6 * 32 / ASR_STAGE_KB;
 constexpr float LOG2E = 1.4426950408889634f;
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -140,7 +146,7 @@ constexpr int pick_kg(int mt, int kbs) {
 template <int MT_, int KB_>
 struct Mat {
   static constexpr int MT = MT_, KB = KB_;
-  static constexpr int KBS = (32 / MT) < 1 ? 1 : ((32 / MT) > KB ? KB : (32 / MT));
+  static constexpr int KBS = (ASR_STAGE_KB / MT) < 1 ? 1 : ((ASR_STAGE_KB / MT) > KB ? KB : (ASR_STAGE_KB / MT));
   static constexpr int KG = pick_kg(MT, KBS);
   static constexpr int MSTEP = NCW / KG;                               // m-tile stride between a warp's units
   static constexpr int UPW = (MT + MSTEP - 1) / MSTEP, KPG = KBS / KG, NST = KB / KBS;
@@ -1414,9 +1420,13 @@ struct Instance {
 };
 #define ASR_INST(H, FFS, VS, G) {H, FFS, VS, G, dec_cluster_kernel<Shape<H, FFS, VS, G>>, smem_map<Shape<H, FFS, VS, G>>}
 const Instance kInstances[] = {
+#if ASR_NCW == 8
     ASR_INST(4, 256, 64, 2), ASR_INST(4, 256, 64, 4), ASR_INST(4, 256, 64, 8),     // C1-C4: d_model 256, FFN 1024
     ASR_INST(2, 128, 128, 2), ASR_INST(2, 128, 128, 4), ASR_INST(2, 128, 128, 8),  // T0: d_model 128, FFN 256
     ASR_INST(8, 256, 32, 2), ASR_INST(8, 256, 32, 4),                              // C5: d_model 512, FFN 2048
+#else
+    ASR_INST(4, 256, 64, 2), ASR_INST(4, 256, 64, 4),                              // (experiment: 4 consumer warps)
+#endif
 };
 const Instance* find_instance(int H, int FFS, int VS, int GUP) {
   for (const Instance& i : kInstances)

@@ -5,7 +5,7 @@
 
 One "step" = one pass of the hot path (conv front-end -> encoder -> cross-K/V -> 128 greedy decode steps) over one
 batch of synthetic utterances.  Workload = BASELINE.json configs[1] (C2): repo-default Speech-Transformer, batch 64
-per GPU, bf16 tensor-core operands with fp32 accumulation.  Weak scaling: every GPU decodes its own 64 utterances,
+per GPU, fp16 hi|lo split tensor-core operands with fp32 accumulation.  Weak scaling: every GPU decodes its own 64 utterances,
 no collective on the compute path, one final all_gather of the token matrices.
 
 Prints ONE JSON line (rank 0).  `value` is device-timed (CUDA events) with inputs resident in HBM; `e2e` goes through
@@ -183,7 +183,7 @@ def measured_peaks():
 
 
 def decode_class_bytes(cfg, B):
-    """Algorithmic HBM bytes per launch of each decode-step kernel class (bf16 weights and K/V caches, fp32
+    """Algorithmic HBM bytes per launch of each decode-step kernel class (fp16 weights and K/V caches, fp32
     activations), averaged over the L steps (self-attention reads t+1 cache rows at step t)."""
     D, FF, V, Tp, L = cfg.embedding_dim, cfg.ff_dim, cfg.vocab_size, cfg.encoder_seq_len, cfg.decoder_seq_len
     f = 4
