@@ -29,8 +29,10 @@ class LayerNorm(nn.LayerNorm):
         D = self.normalized_shape[0]
         x = x.to(torch.float32).contiguous()
         y = torch.empty_like(x)
-        _l.check(_l.load().asr_layernorm(_l.ptr(x), _l.ptr(self.weight.detach()), _l.ptr(self.bias.detach()),
-                                         x.numel() // D, D, _l.ptr(y), None, _l.stream()), "asr_layernorm")
+        with _l.on(x):   # (a half-precision module would otherwise be read as fp32: ptr() checks the dtype)
+            _l.check(_l.load().asr_layernorm(_l.ptr(x), _l.ptr(self.weight.detach(), torch.float32),
+                                             _l.ptr(self.bias.detach(), torch.float32), x.numel() // D, D, _l.ptr(y), None,
+                                             _l.stream()), "asr_layernorm")
         return y
 
 
