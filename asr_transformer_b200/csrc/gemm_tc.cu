@@ -398,9 +398,10 @@ int launch_one(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogu
 // 48 KB per pipeline stage (A 128 x 64 + B 256 x 64), accumulator double-buffered: all 512 TMEM columns.
 constexpr int LN_BN = 256;
 constexpr int LN_B_STAGE = LN_BN * BK * 2;
-template <int STAGES>
+template <int STAGES, bool TMAE = false>
 constexpr size_t gemm_ln_smem() {
-  return size_t(STAGES) * (A_STAGE_BYTES + LN_B_STAGE) + (2 * STAGES + 4) * 8 + 32 + 3 * LN_BN * 4 + 2 * BM * 2 * 8 + 1024;
+  return size_t(STAGES) * (A_STAGE_BYTES + LN_B_STAGE) + (TMAE ? EPI_WARPS * (3 * 4096 + 2 * 8) : 0) + (2 * STAGES + 4) * 8 +
+         32 + 3 * LN_BN * 4 + 2 * BM * 2 * 8 + 1024;
 }
 
 // Epilogue of one full-row (256-column) tile for the thread that owns `row` and the column half `half` (128 columns at
@@ -495,15 +496,175 @@ __device__ __forceinline__ void ln_epilogue_tile(const GemmEpilogue& ep, const L
       }
 }
 
-template <int STAGES>
+// The same epilogue with every row stream carried by TMA (gemm_ln_kernel<.., true>): one row per thread means a direct
+// global access sends 32 separate sectors through the LSU per instruction, and the three row streams of this epilogue
+// (residual in, fp32 residual out, f16 hi | lo out: 65 MB each at 256 utterances) then cost 20-30 us each against 10 us at
+// the HBM roofline (ablation in DESIGN.md section 8).  Here a warp owns three 4 KB staging tiles ([32 rows][128 B],
+// 128-byte swizzle: chunk j of row r at j ^ (r & 7), conflict free for the row-per-thread view): lane 0 requests the
+// residual box of chunk c + 1 (32 rows x 32 fp32) while chunk c is processed, the finished fp32 chunk and the f16 hi / lo
+// halves are written to a tile and leave as tensor stores.  Rows beyond M are clipped / zero-filled by the tensor maps.
+struct LnTma {
+  const CUtensorMap* res;     // fp32 [M][ld_res], box {32, 32}
+  const CUtensorMap* out32;   // fp32 [M][ld_f32], box {32, 32}
+  const CUtensorMap* out16;   // f16  [M][ldo],    box {64, 32}
+  uint8_t* tiles;             // this warp's 3 x 4 KB (1024-byte aligned)
+  uint64_t* bars;             // this warp's 2 mbarriers (residual double buffer)
+  uint32_t* n_loads;          // this warp's count of residual boxes requested so far (buffer = n & 1, parity = n >> 1 & 1)
+};
+__device__ __forceinline__ void ln_epilogue_tile_tma(const GemmEpilogue& ep, const LnEpilogue& ln, uint32_t tacc, int row0,
+                                                     int M, int half, const float* sbias, const float* sgamma,
+                                                     const float* sbeta, float2* st, const LnTma& t, uint32_t& n_loads) {
+      const int lane = threadIdx.x & 31, row = row0 + lane;
+      const bool live = row < M;
+      const float* pe_row = ep.rowvec ? ep.rowvec + size_t(row % ep.rowvec_period) * ep.ld_rowvec : nullptr;
+      auto tile = [&](int i) { return reinterpret_cast<uint4*>(t.tiles + i * 4096); };
+      auto sw = [&](int j) { return lane * 8 + (j ^ (lane & 7)); };
+      float shift = 0.f, s1 = 0.f, s2 = 0.f;
+      if (ep.residual && lane == 0) {
+        tma_store_wait_read<0>();                   // the previous tile's last stores have left tiles 0 / 1
+        const uint32_t b = n_loads & 1u;
+        mbar_expect_tx(&t.bars[b], 4096);
+        tma_load_2d(t.tiles + b * 4096, t.res, &t.bars[b], half * 128, row0);
+      }
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col = half * 128 + c * 32;
+        uint32_t r[32];
+        tmem_ld32(tacc + uint32_t(c * 32), r);
+        float4 res[8], pe[8];
+        if (ep.residual) {
+          const uint32_t k = n_loads + c, b = k & 1u;
+          __syncwarp();                             // every lane is done with the tile the next request overwrites
+          if (lane == 0 && c + 1 < 4) {
+            mbar_expect_tx(&t.bars[b ^ 1u], 4096);
+            tma_load_2d(t.tiles + (b ^ 1u) * 4096, t.res, &t.bars[b ^ 1u], col + 32, row0);
+          }
+          mbar_wait(&t.bars[b], (k >> 1) & 1u);
+          const uint4* rt = tile(b);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 v = rt[sw(j)];
+            res[j] = make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+          }
+        }
+        if (pe_row && live) {
+          const float4* pp = reinterpret_cast<const float4*>(pe_row + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pe[j] = __ldg(pp + j);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[4 * j + i]) + sbias[col + 4 * j + i];
+          if (ep.relu) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (pe_row && live) { v[0] += pe[j].x; v[1] += pe[j].y; v[2] += pe[j].z; v[3] += pe[j].w; }
+          if (ep.residual) { v[0] += res[j].x; v[1] += res[j].y; v[2] += res[j].z; v[3] += res[j].w; }
+          if (c == 0 && j == 0) shift = v[0];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float d = v[i] - shift;
+            s1 += d;
+            s2 = fmaf(d, d, s2);
+            r[4 * j + i] = __float_as_uint(v[i]);
+          }
+        }
+        if (ep.out_f32) {
+          if (lane == 0) tma_store_wait_read<0>();  // the previous chunk's store has read tile 2 (issued a chunk ago)
+          __syncwarp();
+          uint4* ot = tile(2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ot[sw(j)] = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(t.out32, ot, col, row0);
+            tma_store_commit();
+          }
+        }
+        tmem_st32(tacc + uint32_t(c * 32), r);      // the finished row values go back to TMEM for the second pass
+      }
+      if (ep.residual) n_loads += 4;
+      tmem_st_wait();
+      const float mean_h = shift + s1 * (1.0f / 128.0f);
+      const float m2_h = fmaxf(s2 - s1 * s1 * (1.0f / 128.0f), 0.f);
+      st[half] = make_float2(mean_h, m2_h);
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      const float2 other = st[half ^ 1];
+      const float mean = 0.5f * (mean_h + other.x);
+      const float dm = mean_h - other.x;
+      const float var = (m2_h + other.y + dm * dm * 64.0f) * (1.0f / 256.0f);
+      const float rstd = 1.0f / sqrtf(var + ln.eps);
+      int n_st = 0;                                  // stores of this pass: tile n_st % 3, at most 2 still reading
+#pragma unroll 1
+      for (int cp = 0; cp < 2; ++cp) {               // 64 columns per round: one 128-byte f16 row per tile
+        const int col = half * 128 + cp * 64;
+        uint4* th = tile(n_st % 3);
+        uint4* tl = tile((n_st + 1) % 3);
+        if (ln.out_f16) {
+          if (lane == 0) tma_store_wait_read<1>();   // both tiles of this round are free (their stores: >= 2 groups back)
+          __syncwarp();
+        }
+#pragma unroll 1
+        for (int h2 = 0; h2 < 2; ++h2) {
+          const int c = cp * 2 + h2;
+          uint32_t r[32];
+          tmem_ld32(tacc + uint32_t(c * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int cc = half * 128 + c * 32 + 8 * j;
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              y[i] = (__uint_as_float(r[8 * j + i]) - mean) * rstd * sgamma[cc + i] + sbeta[cc + i];
+            if (ln.out_f32 && live) {                                // (the model's last LayerNorm only: row per thread)
+              float* op = ln.out_f32 + size_t(row) * LN_BN + cc;
+              *reinterpret_cast<float4*>(op) = make_float4(y[0], y[1], y[2], y[3]);
+              *reinterpret_cast<float4*>(op + 4) = make_float4(y[4], y[5], y[6], y[7]);
+            }
+            if (ln.out_f16) {
+              const uint4 hi = make_uint4(pack_f16x2(y[0], y[1]), pack_f16x2(y[2], y[3]), pack_f16x2(y[4], y[5]),
+                                          pack_f16x2(y[6], y[7]));
+              th[sw(h2 * 4 + j)] = hi;
+              if (ln.split)
+                tl[sw(h2 * 4 + j)] = make_uint4(f16x2_residual(y[0], y[1], hi.x), f16x2_residual(y[2], y[3], hi.y),
+                                                f16x2_residual(y[4], y[5], hi.z), f16x2_residual(y[6], y[7], hi.w));
+            }
+          }
+        }
+        if (ln.out_f16) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(t.out16, th, col, row0);
+            tma_store_commit();
+            if (ln.split) {
+              tma_store_2d(t.out16, tl, LN_BN + col, row0);
+              tma_store_commit();
+            }
+          }
+          n_st += 2;
+        }
+      }
+}
+
+template <int STAGES, bool TMAE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
-               LnEpilogue ln, int M, int K, int nkw, int n_tiles) {
+gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmRes, const __grid_constant__ CUtensorMap tmO32,
+               const __grid_constant__ CUtensorMap tmO16, GemmEpilogue ep, LnEpilogue ln, int M, int K, int nkw, int n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * LN_B_STAGE);
+  uint8_t* stiles = sB + STAGES * LN_B_STAGE;                          // (TMAE) [EPI_WARPS][3][4 KB] epilogue staging tiles
+  uint64_t* tbars = reinterpret_cast<uint64_t*>(stiles + (TMAE ? EPI_WARPS * 3 * 4096 : 0));   // (TMAE) [EPI_WARPS][2]
+  uint64_t* full_bar = tbars + (TMAE ? EPI_WARPS * 2 : 0);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
@@ -526,12 +687,19 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], EPI_WARPS);
     }
+    if (TMAE)
+      for (int b = 0; b < EPI_WARPS * 2; ++b) mbar_init(&tbars[b], 1);
     fence_barrier_init();
   }
   if (warp == EPI_WARPS) {
     if (lane == 0) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
+      if (TMAE) {
+        tma_prefetch_desc(&tmRes);
+        tma_prefetch_desc(&tmO32);
+        tma_prefetch_desc(&tmO16);
+      }
     }
     __syncwarp();
     tmem_alloc(tmem_ptr, 2 * LN_BN);
@@ -588,7 +756,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---- epilogue: warp w -> TMEM lanes 32 (w % 4).., column half w / 4 (128 columns of the row)
     const int quad = warp & 3, half = warp >> 2;
     const int rl = quad * 32 + lane;
-    uint32_t lt = 0;
+    uint32_t lt = 0, n_loads = 0;
+    LnTma tm;
+    tm.res = &tmRes; tm.out32 = &tmO32; tm.out16 = &tmO16;
+    tm.tiles = stiles + warp * (3 * 4096); tm.bars = tbars + warp * 2; tm.n_loads = nullptr;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
       const uint32_t buf = lt & 1, use = lt >> 1;
       const int row = tile * BM + rl;
@@ -596,11 +767,16 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
       const uint32_t tacc = tmem_base + buf * LN_BN + (uint32_t(quad * 32) << 16) + uint32_t(half * 128);
-      ln_epilogue_tile(ep, ln, tacc, row, live, half, sbias, sgamma, sbeta, sstat + (size_t(buf) * BM + rl) * 2);
+      if (TMAE)
+        ln_epilogue_tile_tma(ep, ln, tacc, tile * BM + quad * 32, M, half, sbias, sgamma, sbeta,
+                             sstat + (size_t(buf) * BM + rl) * 2, tm, n_loads);
+      else
+        ln_epilogue_tile(ep, ln, tacc, row, live, half, sbias, sgamma, sbeta, sstat + (size_t(buf) * BM + rl) * 2);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
+    if (TMAE && lane == 0) tma_store_wait_all<0>();   // the last tensor stores have left shared memory and are complete
   }
   tc_fence_before();
   __syncthreads();
@@ -931,15 +1107,46 @@ int launch_gemm_ln(const f16* X, int ldx, const f16* W, int ldw, int M, int N, i
     uint32_t box[2] = {BK, (uint32_t)LN_BN};
     if (int rc = make_tmap_f16(&tmB, W, 2, dims, str, box, nullptr)) return rc;
   }
-  constexpr int STAGES = 4;
-  auto kern = gemm_ln_kernel<STAGES>;
-  constexpr size_t smem = gemm_ln_smem<STAGES>();
-  if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
   int n_sm = 0;
   if (int rc = device_props(&n_sm, nullptr)) return rc;
   const int n_tiles = (M + BM - 1) / BM;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-  kern<<<grid, GEMM_THREADS, smem, s>>>(tmA, tmB, ep, ln, M, KA, K / BK, n_tiles);
+  // Row streams of the epilogue by TMA (ASR_B200_LN_TMA=0: the row-per-thread epilogue): needs dense-enough strides
+  static const bool tma_off = [] {
+    const char* e = std::getenv("ASR_B200_LN_TMA");
+    return e && e[0] == '0';
+  }();
+  const int ldo = ln.split ? 2 * LN_BN : LN_BN;
+  CUtensorMap tmRes = tmA, tmO32 = tmA, tmO16 = tmA;
+  bool tmae = !tma_off;
+  if (tmae) {
+    const uint32_t box32[2] = {32, 32}, box16[2] = {64, 32};
+    if (ep.residual) {
+      uint64_t dims[2] = {(uint64_t)LN_BN, (uint64_t)M}, str[2] = {4, (uint64_t)ep.ld_res * 4};
+      tmae = tmae && make_tmap_f32(&tmRes, ep.residual, 2, dims, str, box32, nullptr) == 0;
+    }
+    if (ep.out_f32) {
+      uint64_t dims[2] = {(uint64_t)LN_BN, (uint64_t)M}, str[2] = {4, (uint64_t)ep.ld_f32 * 4};
+      tmae = tmae && make_tmap_f32(&tmO32, ep.out_f32, 2, dims, str, box32, nullptr) == 0;
+    }
+    if (ln.out_f16) {
+      uint64_t dims[2] = {(uint64_t)ldo, (uint64_t)M}, str[2] = {2, (uint64_t)ldo * 2};
+      tmae = tmae && make_tmap_f16(&tmO16, ln.out_f16, 2, dims, str, box16, nullptr) == 0;
+    }
+  }
+  if (tmae) {
+    constexpr int STAGES = 2;   // 2 x 48 KB ring + 96 KB of epilogue staging tiles
+    auto kern = gemm_ln_kernel<STAGES, true>;
+    constexpr size_t smem = gemm_ln_smem<STAGES, true>();
+    if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
+    kern<<<grid, GEMM_THREADS, smem, s>>>(tmA, tmB, tmRes, tmO32, tmO16, ep, ln, M, KA, K / BK, n_tiles);
+  } else {
+    constexpr int STAGES = 4;
+    auto kern = gemm_ln_kernel<STAGES, false>;
+    constexpr size_t smem = gemm_ln_smem<STAGES, false>();
+    if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
+    kern<<<grid, GEMM_THREADS, smem, s>>>(tmA, tmB, tmRes, tmO32, tmO16, ep, ln, M, KA, K / BK, n_tiles);
+  }
   ASR_CUDA_OK(cudaGetLastError());
   ASR_LAUNCHED(1);
   return 0;

@@ -36,6 +36,8 @@ int device_props(int* n_sm, int* max_smem_optin);
 // f16 tensor, innermost dim contiguous. dims/strides innermost first; strides in BYTES for dims >= 1.
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, const uint32_t* elem_strides /*nullable*/, int swizzle_bytes = 128 /* 0 = none */);
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const uint32_t* elem_strides /*nullable*/, int swizzle_bytes = 128 /* 0 = none */);
 
 // ---- GEMM  Y[M,N] = X[M,K] * W[N,K]^T (+bias)(relu)(+rowvec)(+residual)  (tcgen05 / TMEM / TMA)
 struct GemmEpilogue {

@@ -68,8 +68,18 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   return fn;
 }
 
+static int make_tmap_any(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes);
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes) {
+  return make_tmap_any(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, rank, dims, strides_bytes, box, elem_strides, swizzle_bytes);
+}
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes) {
+  return make_tmap_any(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, elem_strides, swizzle_bytes);
+}
+static int make_tmap_any(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides, int swizzle_bytes) {
   auto fn = encode_fn();
   if (!fn) return set_error(-101, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   cuuint64_t gdim[5];
@@ -86,7 +96,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
   for (int i = 1; i < rank; ++i)
     if (strides_bytes[i] % 16 != 0) return set_error(-102, "TMA stride %d (%llu B) not a multiple of 16", i,
                                                      (unsigned long long)strides_bytes[i]);
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(-103, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
