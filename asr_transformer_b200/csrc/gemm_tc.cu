@@ -507,7 +507,7 @@ struct LnTma {
   const CUtensorMap* res;     // fp32 [M][ld_res], box {32, 32}
   const CUtensorMap* out32;   // fp32 [M][ld_f32], box {32, 32}
   const CUtensorMap* out16;   // f16  [M][ldo],    box {64, 32}
-  uint8_t* tiles;             // this warp's 3 x 4 KB (1024-byte aligned)
+  uint8_t* tile[3];           // this warp's three 4 KB staging tiles (1024-byte aligned)
   uint64_t* bars;             // this warp's 2 mbarriers (residual double buffer)
   uint32_t* n_loads;          // this warp's count of residual boxes requested so far (buffer = n & 1, parity = n >> 1 & 1)
 };
@@ -517,14 +517,14 @@ __device__ __forceinline__ void ln_epilogue_tile_tma(const GemmEpilogue& ep, con
       const int lane = threadIdx.x & 31, row = row0 + lane;
       const bool live = row < M;
       const float* pe_row = ep.rowvec ? ep.rowvec + size_t(row % ep.rowvec_period) * ep.ld_rowvec : nullptr;
-      auto tile = [&](int i) { return reinterpret_cast<uint4*>(t.tiles + i * 4096); };
+      auto tile = [&](int i) { return reinterpret_cast<uint4*>(t.tile[i]); };
       auto sw = [&](int j) { return lane * 8 + (j ^ (lane & 7)); };
       float shift = 0.f, s1 = 0.f, s2 = 0.f;
       if (ep.residual && lane == 0) {
         tma_store_wait_read<0>();                   // the previous tile's last stores have left tiles 0 / 1
         const uint32_t b = n_loads & 1u;
         mbar_expect_tx(&t.bars[b], 4096);
-        tma_load_2d(t.tiles + b * 4096, t.res, &t.bars[b], half * 128, row0);
+        tma_load_2d(t.tile[b], t.res, &t.bars[b], half * 128, row0);
       }
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -537,7 +537,7 @@ __device__ __forceinline__ void ln_epilogue_tile_tma(const GemmEpilogue& ep, con
           __syncwarp();                             // every lane is done with the tile the next request overwrites
           if (lane == 0 && c + 1 < 4) {
             mbar_expect_tx(&t.bars[b ^ 1u], 4096);
-            tma_load_2d(t.tiles + (b ^ 1u) * 4096, t.res, &t.bars[b ^ 1u], col + 32, row0);
+            tma_load_2d(t.tile[b ^ 1u], t.res, &t.bars[b ^ 1u], col + 32, row0);
           }
           mbar_wait(&t.bars[b], (k >> 1) & 1u);
           const uint4* rt = tile(b);
@@ -759,7 +759,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t lt = 0, n_loads = 0;
     LnTma tm;
     tm.res = &tmRes; tm.out32 = &tmO32; tm.out16 = &tmO16;
-    tm.tiles = stiles + warp * (3 * 4096); tm.bars = tbars + warp * 2; tm.n_loads = nullptr;
+    for (int i = 0; i < 3; ++i) tm.tile[i] = stiles + (warp * 3 + i) * 4096;
+    tm.bars = tbars + warp * 2; tm.n_loads = nullptr;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
       const uint32_t buf = lt & 1, use = lt >> 1;
       const int row = tile * BM + rl;
@@ -796,22 +797,25 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // Ring stages of 32 KB: (x k-block 16 KB + W1 k-block 16 KB) for GEMM 1, one W2 k-block (256 x 64) for GEMM 2.
 constexpr int FFN_STAGE = 32768;
 constexpr int FFN_HID_BYTES = 4 * A_STAGE_BYTES;      // hi k-blocks 0, 1 | lo k-blocks 2, 3 of a 128-column chunk
-template <int STAGES>
+template <int STAGES, bool TMAE = false>
 constexpr size_t ffn_fused_smem(int FF) {
-  return size_t(STAGES) * FFN_STAGE + FFN_HID_BYTES + (2 * STAGES + 16) * 8 + 32 + (size_t(FF) + 3 * LN_BN) * 4 +
-         2 * BM * 2 * 8 + 1024;
+  return size_t(STAGES) * FFN_STAGE + FFN_HID_BYTES + (TMAE ? EPI_WARPS * (4096 + 2 * 8) : 0) + (2 * STAGES + 16) * 8 + 32 +
+         (size_t(FF) + 3 * LN_BN) * 4 + 2 * BM * 2 * 8 + 1024;
 }
 
-template <int STAGES>
+template <int STAGES, bool TMAE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW1,
-                 const __grid_constant__ CUtensorMap tmW2, GemmEpilogue ep, LnEpilogue ln, const float* __restrict__ b1,
-                 int M, int FF, int nk1, int nkw1, int split, int n_tiles) {
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmRes,
+                 const __grid_constant__ CUtensorMap tmO32, const __grid_constant__ CUtensorMap tmO16, GemmEpilogue ep,
+                 LnEpilogue ln, const float* __restrict__ b1, int M, int FF, int nk1, int nkw1, int split, int n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
   uint8_t* hid = smem + STAGES * FFN_STAGE;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(hid + FFN_HID_BYTES);
+  uint8_t* stiles = hid + FFN_HID_BYTES;                               // (TMAE) [EPI_WARPS][4 KB]: third staging tile per warp
+  uint64_t* tbars = reinterpret_cast<uint64_t*>(stiles + (TMAE ? EPI_WARPS * 4096 : 0));   // (TMAE) [EPI_WARPS][2]
+  uint64_t* full_bar = tbars + (TMAE ? EPI_WARPS * 2 : 0);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* acc1_full = empty_bar + STAGES;     // [2]
   uint64_t* acc1_empty = acc1_full + 2;         // [2]
@@ -844,6 +848,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     mbar_init(hid_empty, 1);
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, EPI_WARPS);
+    if (TMAE)
+      for (int b = 0; b < EPI_WARPS * 2; ++b) mbar_init(&tbars[b], 1);
     fence_barrier_init();
   }
   if (warp == EPI_WARPS) {
@@ -851,6 +857,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       tma_prefetch_desc(&tmX);
       tma_prefetch_desc(&tmW1);
       tma_prefetch_desc(&tmW2);
+      if (TMAE) {
+        tma_prefetch_desc(&tmRes);
+        tma_prefetch_desc(&tmO32);
+        tma_prefetch_desc(&tmO16);
+      }
     }
     __syncwarp();
     tmem_alloc(tmem_ptr, 512);
@@ -955,6 +966,16 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int quad = warp & 3, half = warp >> 2;
     const int rl = quad * 32 + lane;
     const uint32_t lane_addr = uint32_t(quad * 32) << 16;
+    // (TMAE) staging tiles of the output epilogue: the two 4 KB pieces of the hidden-chunk buffer that only THIS warp
+    // writes when it converts a chunk (k-blocks `half` and 2 + half, rows 32 quad .. + 31: free once the tile's last
+    // GEMM 2 has completed) and one private tile
+    uint32_t n_loads = 0;
+    LnTma tm;
+    tm.res = &tmRes; tm.out32 = &tmO32; tm.out16 = &tmO16;
+    tm.tile[0] = hid + half * A_STAGE_BYTES + quad * 4096;
+    tm.tile[1] = hid + (2 + half) * A_STAGE_BYTES + quad * 4096;
+    tm.tile[2] = stiles + warp * 4096;
+    tm.bars = tbars + warp * 2; tm.n_loads = nullptr;
     for (int g = 0; g < total_chunks; ++g) {
       const int lt = g / NC, c = g % NC;
       const uint32_t b = g & 1;
@@ -998,14 +1019,22 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int row = tile * BM + rl;
         mbar_wait(acc2_full, lt & 1);
         tc_fence_after();
-        ln_epilogue_tile(ep, ln, tm_acc2 + lane_addr + uint32_t(half * 128), row, row < M, half, sbias, sgamma, sbeta,
-                         sstat + (size_t(lt & 1) * BM + rl) * 2);
+        if (TMAE) {
+          ln_epilogue_tile_tma(ep, ln, tm_acc2 + lane_addr + uint32_t(half * 128), tile * BM + quad * 32, M, half, sbias,
+                               sgamma, sbeta, sstat + (size_t(lt & 1) * BM + rl) * 2, tm, n_loads);
+          if (lane == 0) tma_store_wait_read<0>();   // the stores have left tiles 0 / 1 before this warp converts into them
+          __syncwarp();
+        } else {
+          ln_epilogue_tile(ep, ln, tm_acc2 + lane_addr + uint32_t(half * 128), row, row < M, half, sbias, sgamma, sbeta,
+                           sstat + (size_t(lt & 1) * BM + rl) * 2);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acc2_empty);
       }
     }
   }
+  if (TMAE && warp < EPI_WARPS && lane == 0) tma_store_wait_all<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 512);
@@ -1185,15 +1214,46 @@ int launch_ffn_fused(const f16* X, int ldx, const f16* W1, const float* b1, cons
     uint32_t box[2] = {BK, 256};
     if (int rc = make_tmap_f16(&tmW2, W2, 2, dims, str, box, nullptr)) return rc;
   }
-  auto kern = ffn_fused_kernel<STAGES>;
-  const size_t smem = ffn_fused_smem<STAGES>(FF);
-  if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
   int n_sm = 0;
   if (int rc = device_props(&n_sm, nullptr)) return rc;
   LnEpilogue lnn = ln;
   const int n_tiles = (M + BM - 1) / BM;
   const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-  kern<<<grid, GEMM_THREADS, smem, s>>>(tmX, tmW1, tmW2, ep, lnn, b1, M, FF, K1 / BK, D / BK, split, n_tiles);
+  static const bool tma_off = [] {
+    const char* e = std::getenv("ASR_B200_LN_TMA");
+    return e && e[0] == '0';
+  }();
+  const int ldo = ln.split ? 2 * LN_BN : LN_BN;
+  CUtensorMap tmRes = tmX, tmO32 = tmX, tmO16 = tmX;
+  bool tmae = !tma_off && ffn_fused_smem<3, true>(FF) <= 227 * 1024;
+  if (tmae) {
+    const uint32_t box32[2] = {32, 32}, box16[2] = {64, 32};
+    if (ep.residual) {
+      uint64_t dims[2] = {(uint64_t)LN_BN, (uint64_t)M}, str[2] = {4, (uint64_t)ep.ld_res * 4};
+      tmae = tmae && make_tmap_f32(&tmRes, ep.residual, 2, dims, str, box32, nullptr) == 0;
+    }
+    if (ep.out_f32) {
+      uint64_t dims[2] = {(uint64_t)LN_BN, (uint64_t)M}, str[2] = {4, (uint64_t)ep.ld_f32 * 4};
+      tmae = tmae && make_tmap_f32(&tmO32, ep.out_f32, 2, dims, str, box32, nullptr) == 0;
+    }
+    if (ln.out_f16) {
+      uint64_t dims[2] = {(uint64_t)ldo, (uint64_t)M}, str[2] = {2, (uint64_t)ldo * 2};
+      tmae = tmae && make_tmap_f16(&tmO16, ln.out_f16, 2, dims, str, box16, nullptr) == 0;
+    }
+  }
+  if (tmae) {   // 3-stage ring (measured: as fast as 4 here) + one private staging tile per epilogue warp
+    auto kern = ffn_fused_kernel<3, true>;
+    const size_t smem = ffn_fused_smem<3, true>(FF);
+    if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
+    kern<<<grid, GEMM_THREADS, smem, s>>>(tmX, tmW1, tmW2, tmRes, tmO32, tmO16, ep, lnn, b1, M, FF, K1 / BK, D / BK, split,
+                                          n_tiles);
+  } else {
+    auto kern = ffn_fused_kernel<STAGES, false>;
+    const size_t smem = ffn_fused_smem<STAGES, false>(FF);
+    if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
+    kern<<<grid, GEMM_THREADS, smem, s>>>(tmX, tmW1, tmW2, tmRes, tmO32, tmO16, ep, lnn, b1, M, FF, K1 / BK, D / BK, split,
+                                          n_tiles);
+  }
   ASR_CUDA_OK(cudaGetLastError());
   ASR_LAUNCHED(1);
   return 0;
