@@ -220,16 +220,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpilogue& ep, const uin
 constexpr int EPI_WARPS = 8;
 constexpr int GEMM_THREADS = (EPI_WARPS + 2) * 32;
 
-template <int BN, int STAGES, int FLAGS>   // FLAGS >= 0: the specialised epilogue this launch uses; -1: generic
+// TMAS (bias + f16 output, BN = 128 only: the packed QKV and cross-K/V GEMMs): the 32 x 64 f16 block of every epilogue warp
+// leaves as ONE tensor store from a swizzled 4 KB staging tile instead of 8 row-per-thread 16-byte stores per thread
+// (32 sectors per instruction through the LSU).
+template <int BN, int STAGES, int FLAGS, bool TMAS = false>   // FLAGS >= 0: the specialised epilogue this launch uses; -1: generic
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep,
-               int M, int n_store, int K, int nkw, int tiles_n, int n_tiles) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, GemmEpilogue ep, int M, int n_store, int K, int nkw, int tiles_n,
+               int n_tiles) {
   constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static_assert(!TMAS || (BN == 128 && FLAGS == (EF_BIAS | EF_H16)), "tensor-store epilogue: bias + f16 output, BN 128");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE_BYTES);
+  uint8_t* stiles = sB + STAGES * B_STAGE_BYTES;                     // (TMAS) [EPI_WARPS][4 KB]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stiles + (TMAS ? EPI_WARPS * 4096 : 0));
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
@@ -318,6 +324,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
+      if (TMAS) {
+        uint4* tl = reinterpret_cast<uint4*>(stiles + warp * 4096);
+        if (lane == 0) tma_store_wait_read<0>();                        // the previous tile's store (issued a tile ago)
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int col = half * 64 + c * 32;
+          uint32_t r[32];
+          tmem_ld32(tmem_base + buf * BN + (uint32_t(quad * 32) << 16) + uint32_t(col), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]) + sb[col + 8 * j + i];
+            tl[lane * 8 + ((c * 4 + j) ^ (lane & 7))] =
+                make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmO, tl, n0 + half * 64, m0 + quad * 32);      // rows >= M / columns >= n_store: clipped by the map
+          tma_store_commit();
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {
         const int col = half * (BN / 2) + c * 32;
@@ -334,6 +366,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
     }
+    if (TMAS && lane == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -343,14 +376,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN, int STAGES, int FLAGS>
 int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmEpilogue& ep, int M, int n_store, int n_pad,
                 int K, int nkw, cudaStream_t s) {
-  auto kern = gemm_tc_kernel<BN, STAGES, FLAGS>;
-  constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
-  if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
   int n_slots = 0;   // persistent grid size: one CTA per SM (98 KB+ of shared memory each)
   if (int rc = device_props(&n_slots, nullptr)) return rc;
   const int tiles_n = n_pad / BN, n_tiles = tiles_n * ((M + BM - 1) / BM);
   const int grid = n_tiles < n_slots ? n_tiles : n_slots;
-  kern<<<grid, GEMM_THREADS, smem, s>>>(tmA, tmB, ep, M, n_store, K, nkw, tiles_n, n_tiles);
+  if constexpr (BN == 128 && FLAGS == (EF_BIAS | EF_H16)) {   // f16 output by tensor stores (ASR_B200_LN_TMA=0: off)
+    static const bool tma_off = [] {
+      const char* e = std::getenv("ASR_B200_LN_TMA");
+      return e && e[0] == '0';
+    }();
+    CUtensorMap tmO;
+    const uint64_t dims[2] = {(uint64_t)n_store, (uint64_t)M}, str[2] = {2, (uint64_t)ep.ld_f16 * 2};
+    const uint32_t box[2] = {64, 32};
+    if (!tma_off && n_store % 8 == 0 && make_tmap_f16(&tmO, ep.out_f16, 2, dims, str, box, nullptr) == 0) {
+      auto kern = gemm_tc_kernel<BN, STAGES, FLAGS, true>;
+      constexpr size_t smem = gemm_smem_bytes<BN, STAGES>() + EPI_WARPS * 4096;
+      if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
+      kern<<<grid, GEMM_THREADS, smem, s>>>(tmA, tmB, tmO, ep, M, n_store, K, nkw, tiles_n, n_tiles);
+      ASR_CUDA_OK(cudaGetLastError());
+      ASR_LAUNCHED(1);
+      return 0;
+    }
+  }
+  auto kern = gemm_tc_kernel<BN, STAGES, FLAGS, false>;
+  constexpr size_t smem = gemm_smem_bytes<BN, STAGES>();
+  if (int rc = ensure_dyn_smem((const void*)kern, smem)) return rc;
+  kern<<<grid, GEMM_THREADS, smem, s>>>(tmA, tmB, tmA, ep, M, n_store, K, nkw, tiles_n, n_tiles);
   ASR_CUDA_OK(cudaGetLastError());
   ASR_LAUNCHED(1);
   return 0;
