@@ -13,6 +13,7 @@
 //                                from TMEM and folded into fp32 register accumulators (no TMEM rescale needed).
 #include "kernels.h"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace asr {
 namespace {
@@ -41,11 +42,12 @@ struct AttnDev {
   const uint8_t* k_valid;
   const uint8_t* dense_mask;
   int mask_B;
+  int tma_out;    // the output goes by tensor stores (tmO valid)
 };
 
 __global__ void __launch_bounds__(160, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-               const __grid_constant__ CUtensorMap tmV, AttnDev p) {
+               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, AttnDev p) {
   extern __shared__ __align__(1024) uint8_t smem[];   // no static shared memory in this kernel: the base is 1 KB aligned
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();   // swizzled TMA / UMMA tiles need it
   uint8_t* sQ = smem;
@@ -281,7 +283,36 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(rr[i]);
       }
     }
-    if (qi < p.Sq) {
+    if (p.tma_out) {
+      // Output by tensor stores: a thread owns a query row, so direct stores would send 32 separate sectors through the
+      // LSU per instruction.  The P tile is free now (the last P V has completed): each warp stages its 32 rows x 64 dims
+      // there as f16 hi (and lo) rows of 128 B (128-byte swizzle) and one lane stores the box; rows >= Sq are clipped.
+      const float inv = l > 0.f ? 1.f / l : 0.f;   // fully masked row -> zeros (layers.py:25)
+      uint4* th = reinterpret_cast<uint4*>(sP + warp * 4096);
+      uint4* tl = reinterpret_cast<uint4*>(sP + 16384 + warp * 4096);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int d = 8 * j;
+        uint4 t;
+        t.x = pack_f16x2(o[d + 0] * inv, o[d + 1] * inv);
+        t.y = pack_f16x2(o[d + 2] * inv, o[d + 3] * inv);
+        t.z = pack_f16x2(o[d + 4] * inv, o[d + 5] * inv);
+        t.w = pack_f16x2(o[d + 6] * inv, o[d + 7] * inv);
+        th[lane * 8 + (j ^ (lane & 7))] = t;
+        if (p.out_lo_off)
+          tl[lane * 8 + (j ^ (lane & 7))] =
+              make_uint4(f16x2_residual(o[d + 0] * inv, o[d + 1] * inv, t.x), f16x2_residual(o[d + 2] * inv, o[d + 3] * inv, t.y),
+                         f16x2_residual(o[d + 4] * inv, o[d + 5] * inv, t.z), f16x2_residual(o[d + 6] * inv, o[d + 7] * inv, t.w));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0 && q0 + warp * 32 < p.Sq) {
+        tma_store_3d(&tmO, th, h * DH, q0 + warp * 32, b);
+        if (p.out_lo_off) tma_store_3d(&tmO, tl, p.out_lo_off + h * DH, q0 + warp * 32, b);
+        tma_store_commit();
+        tma_store_wait_read<0>();                  // the tiles are read before the CTA (and its shared memory) goes away
+      }
+    } else if (qi < p.Sq) {
       const float inv = l > 0.f ? 1.f / l : 0.f;   // fully masked row -> zeros (layers.py:25)
       f16* op = p.out + size_t(b) * p.o_batch_stride + size_t(qi) * p.ldo + h * DH;
 #pragma unroll
@@ -372,9 +403,24 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t s) {
   d.scale_log2 = p.scale * 1.4426950408889634f;
   d.causal = p.causal; d.k_lens = p.k_lens; d.q_valid = p.q_valid; d.k_valid = p.k_valid;
   d.dense_mask = p.dense_mask; d.mask_B = p.mask_B;
+  CUtensorMap tmO = tmQ;
+  d.tma_out = 0;
+  {
+    static const bool tma_off = [] {
+      const char* e = std::getenv("ASR_B200_LN_TMA");
+      return e && e[0] == '0';
+    }();
+    const uint64_t cols = uint64_t(p.H) * DH + uint64_t(p.out_lo_off);
+    if (!tma_off && cols <= uint64_t(p.ldo) && p.out_lo_off % 8 == 0) {
+      uint64_t dims[3] = {cols, (uint64_t)p.Sq, (uint64_t)p.B};
+      uint64_t str[3] = {2, (uint64_t)p.ldo * 2, (uint64_t)p.o_batch_stride * 2};
+      const uint32_t obox[3] = {DH, 32, 1};
+      d.tma_out = make_tmap_f16(&tmO, p.out, 3, dims, str, obox, nullptr) == 0;
+    }
+  }
   if (int rc = ensure_dyn_smem((const void*)attn_tc_kernel, ATTN_SMEM)) return rc;
   dim3 grid((p.Sq + BQ - 1) / BQ, p.H, p.B);
-  attn_tc_kernel<<<grid, 160, ATTN_SMEM, s>>>(tmQ, tmK, tmV, d);
+  attn_tc_kernel<<<grid, 160, ATTN_SMEM, s>>>(tmQ, tmK, tmV, tmO, d);
   ASR_CUDA_OK(cudaGetLastError());
   ASR_LAUNCHED(1);
   return 0;
