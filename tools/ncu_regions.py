@@ -4,6 +4,9 @@ nvdisasm -gi prints): per call site in the kernel, executed warp instructions, s
 
   python tools/ncu_regions.py rep.ncu-rep obj.o kernel_substring [top_n] [--inner]
 
+kernel_substring matches the MANGLED name in the object (e.g. "ShapeILi4ELi256ELi64ELi8E" picks one instantiation of
+dec_cluster_kernel); a substring that matches another instantiation silently mis-attributes the samples.
+
 --inner additionally splits every call site by the innermost line (helper level).
 """
 import csv
