@@ -595,15 +595,25 @@ __device__ __forceinline__ void qk_block(uint32_t kbase, int n_valid, const uint
     ldsm_x4(row + j * 1024 + ((mat ^ r) << 4), kf[j][0]);        // dims 0..31  (chunks 0..3): k-tiles 0, 1
     ldsm_x4(row + j * 1024 + (((mat + 4) ^ r) << 4), kf[j][1]);  // dims 32..63 (chunks 4..7): k-tiles 2, 3
   }
+  // one accumulator per 8-key group, the four k-tiles chained through it; the four groups interleave, so consecutive
+  // MMAs are independent (a dependent one waits ~20 cycles for its accumulator) and no add waits for a result before all
+  // sixteen are issued
+  float cc[4][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cc[j][i] = 0.f;
+#pragma unroll
+  for (int kt = 0; kt < 4; ++kt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4& k = kf[j][kt >> 1];
+      mma16816(cc[j], qa[kt], (kt & 1) ? k.z : k.x, (kt & 1) ? k.w : k.y);
+    }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    float ca[4] = {0.f, 0.f, 0.f, 0.f}, cb[4] = {0.f, 0.f, 0.f, 0.f};
-    mma16816(ca, qa[0], kf[j][0].x, kf[j][0].y);
-    mma16816(cb, qa[1], kf[j][0].z, kf[j][0].w);
-    mma16816(ca, qa[2], kf[j][1].x, kf[j][1].y);
-    mma16816(cb, qa[3], kf[j][1].z, kf[j][1].w);
-    s[2 * j] = (ca[0] + cb[0]) + (ca[2] + cb[2]);                // key 8j + 2tg      (hi row + lo row)
-    s[2 * j + 1] = (ca[1] + cb[1]) + (ca[3] + cb[3]);            // key 8j + 2tg + 1
+    s[2 * j] = cc[j][0] + cc[j][2];                              // key 8j + 2tg      (hi row + lo row)
+    s[2 * j + 1] = cc[j][1] + cc[j][3];                          // key 8j + 2tg + 1
   }
   if (n_valid < 32) {
 #pragma unroll
