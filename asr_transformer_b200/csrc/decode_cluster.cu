@@ -586,15 +586,17 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint4& r) {
 }
 // scores of the 32 keys of one K tile (32 rows of 128 B, chunk c of row r stored at chunk c ^ (r & 7)); s[2j + e] <-> key
 // 8j + 2tg + e; keys >= n_valid get -inf (select, not arithmetic: rows past the valid keys may hold anything)
-__device__ __forceinline__ void qk_block(uint32_t kbase, int n_valid, const uint4 (&qa)[4], float (&s)[8]) {
-  const int lane = threadIdx.x & 31, tg = lane & 3, mat = lane >> 3, r = lane & 7;
+__device__ __forceinline__ void qk_load(uint32_t kbase, uint4 (&kf)[4][2]) {
+  const int lane = threadIdx.x & 31, mat = lane >> 3, r = lane & 7;
   const uint32_t row = kbase + r * 128;
-  uint4 kf[4][2];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {                                  // all eight loads first, then the sixteen MMAs
+  for (int j = 0; j < 4; ++j) {
     ldsm_x4(row + j * 1024 + ((mat ^ r) << 4), kf[j][0]);        // dims 0..31  (chunks 0..3): k-tiles 0, 1
     ldsm_x4(row + j * 1024 + (((mat + 4) ^ r) << 4), kf[j][1]);  // dims 32..63 (chunks 4..7): k-tiles 2, 3
   }
+}
+__device__ __forceinline__ void qk_math(const uint4 (&kf)[4][2], int n_valid, const uint4 (&qa)[4], float (&s)[8]) {
+  const int tg = threadIdx.x & 3;
   // one accumulator per 8-key group, the four k-tiles chained through it; the four groups interleave, so consecutive
   // MMAs are independent (a dependent one waits ~20 cycles for its accumulator) and no add waits for a result before all
   // sixteen are issued
@@ -641,16 +643,17 @@ __device__ __forceinline__ void p_pack(const float (&p)[8], uint32_t (&pb)[4]) {
   }
 }
 // o += V^T p for one value tile (32 rows of 128 B, swizzled like K)
-__device__ __forceinline__ void pv_block(uint32_t vbase, AttnT& st, const uint32_t (&pb)[4]) {
+__device__ __forceinline__ void pv_load(uint32_t vbase, uint4 (&vf)[4][2]) {
   const int lane = threadIdx.x & 31, mat = lane >> 3, r = lane & 7;
   const uint32_t row = vbase + ((mat >> 1) * 8 + r) * 128;       // matrices 0, 1: keys 16kt + r; 2, 3: keys 16kt + 8 + r
-  uint4 vf[4][2];
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt) {                               // all eight loads first, then the eight MMAs
+  for (int mt = 0; mt < 4; ++mt) {
     const uint32_t ch = (((2 * mt + (mat & 1)) ^ r) & 7) << 4;   // matrices 0, 2: dims 16mt .. +7; 1, 3: dims 16mt + 8 ..
     ldsm_x4_trans(row + ch, vf[mt][0]);
     ldsm_x4_trans(row + 2048 + ch, vf[mt][1]);
   }
+}
+__device__ __forceinline__ void pv_math(const uint4 (&vf)[4][2], AttnT& st, const uint32_t (&pb)[4]) {
 #pragma unroll
   for (int mt = 0; mt < 4; ++mt) {
     mma16816(st.o[mt], vf[mt][0], pb[0], pb[1]);
@@ -708,11 +711,18 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint4 (&
         const uint32_t stg = smem_u32(c.acquire()) + blk_off;
         const int n = lim - s * RPS;
         if (n > 0) {
-          qk_block(stg, n, qa, sc[s]);
+          // The slot goes back to the producer as soon as its rows are requested: the arrive is a release, so the
+          // ldmatrix reads before it are ordered before the producer's next copy into the slot; the math then runs
+          // from registers while the refill is under way (64 / 128-utterance launches -1.8 %, 256 unchanged).
+          uint4 kf[4][2];
+          qk_load(stg, kf);
+          c.release();
+          qk_math(kf, n, qa, sc[s]);
 #pragma unroll
           for (int i = 0; i < 8; ++i) mx = fmaxf(mx, sc[s][i]);
+        } else {
+          c.release();
         }
-        c.release();
       }
     }
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));        // the four tg lanes own different keys
@@ -743,8 +753,14 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint4 (&
     for (int s = 0; s < SC; ++s)
       if (s < ns) {
         const uint32_t stg = smem_u32(c.acquire()) + blk_off;
-        if (lim - s * RPS > 0) pv_block(stg, st, pb[s]);
-        c.release();
+        if (lim - s * RPS > 0) {
+          uint4 vf[4][2];
+          pv_load(stg, vf);
+          c.release();
+          pv_math(vf, st, pb[s]);
+        } else {
+          c.release();
+        }
       }
     c0 += SC * RPS;
   }

@@ -382,7 +382,14 @@ def main():
     clocks = sampler.stop()
     launches = lib.asr_launch_count() - launches0
     total_ms = torch.tensor([t_s.elapsed_time(t_e)], dtype=torch.float64, device=dev)
+    per_rank = None
     if dist is not None:
+        # every rank's own timed region and SM clock: the headline divides by the MAX, this shows what the max is made of
+        mine = torch.tensor([float(total_ms.item()), float(clocks.get("sm_mhz") or 0.0)], dtype=torch.float64, device=dev)
+        allr = torch.empty(world * 2, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine)
+        allr = allr.view(world, 2).cpu()
+        per_rank = {"ms": [round(float(v), 3) for v in allr[:, 0]], "sm_mhz": [float(v) for v in allr[:, 1]]}
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     value = world * batch * args.steps / (total_ms / 1e3)
@@ -442,7 +449,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp16 tensor-core operands (hi|lo split activations into every linear layer), fp32 accumulate",
-        "data": "synthetic", "config": workload_desc(cfg, batch, world), "clocks": clocks,
+        "data": "synthetic", "config": workload_desc(cfg, batch, world), "clocks": clocks, "per_rank": per_rank,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "Transformer.greedy_decode_batches (pinned host batches in, CPU transcripts out; copies of "
                        "neighbouring steps overlap compute; multi-GPU: per-rank D2H, one all_gather of the token ids at "
