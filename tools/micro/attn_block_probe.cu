@@ -15,7 +15,7 @@ __device__ __forceinline__ void ldsmt(uint32_t addr, uint4& r) {
 }
 // MODE 0: QK block (8 ldsm + 16 mma chained + adds + max)   1: QK without the loads (constant fragments)
 // MODE 2: PV block (8 ldsm.trans + 8 mma)                   3: loads only (8 ldsm, consumed by an xor)
-template <int MODE>
+template <int MODE, int WAIT = 0, int SKEW = 0>
 __global__ void __launch_bounds__(256) probe(long long* out, float* sink, int iters) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, mat = lane >> 3, r = lane & 7;
@@ -26,9 +26,21 @@ __global__ void __launch_bounds__(256) probe(long long* out, float* sink, int it
   float o[4][4] = {}, mx = -1e30f;
   uint32_t acc = 0;
   const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem) + warp * 4096;
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&bar)));
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(&bar)) : "memory");   // phase 0 complete
+  }
   __syncthreads();
+  if (SKEW && warp >= 4) { long long t = clock64(); while (clock64() - t < SKEW) {} }
   long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
+    if (WAIT) {   // the ring's acquire: a try_wait on a phase that is already complete
+      uint32_t ok;
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                   : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(&bar)), "r"(0u) : "memory");
+      if (!ok) __trap();
+    }
     const uint32_t kbase = base + (it & 3) * 32768;
     uint4 kf[4][2];
     if (MODE == 0 || MODE == 3) {
@@ -75,12 +87,12 @@ __global__ void __launch_bounds__(256) probe(long long* out, float* sink, int it
   sink[blockIdx.x * 256 + threadIdx.x] = s;
   if (threadIdx.x == 0) out[blockIdx.x] = t1 - t0;
 }
-template <int MODE>
+template <int MODE, int WAIT = 0, int SKEW = 0>
 void run(int warps, const char* what) {
   long long* d; float* sink; cudaMalloc(&d, 8 * 148); cudaMalloc(&sink, 4 * 148 * 256);
-  cudaFuncSetAttribute(probe<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
+  cudaFuncSetAttribute(probe<MODE, WAIT, SKEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
   const int iters = 4000;
-  for (int rep = 0; rep < 2; ++rep) probe<MODE><<<1, warps * 32, 131072>>>(d, sink, iters);
+  for (int rep = 0; rep < 2; ++rep) probe<MODE, WAIT, SKEW><<<1, warps * 32, 131072>>>(d, sink, iters);
   long long h; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
   printf("%-44s warps %d: %.1f cycles per block\n", what, warps, double(h) / iters);
   cudaFree(d); cudaFree(sink);
@@ -93,6 +105,12 @@ int main() {
   run<2>(4, "PV block: 8 ldsm.trans + 8 mma");
   run<3>(8, "loads only (8 ldsm)");
   run<3>(4, "loads only (8 ldsm)");
+  run<0, 1, 0>(8, "QK block + try_wait, warps in step");
+  run<0, 1, 170>(8, "QK block + try_wait, warps 4-7 skewed 170");
+  run<0, 1, 250>(8, "QK block + try_wait, warps 4-7 skewed 250");
+  run<2, 1, 0>(8, "PV block + try_wait, warps in step");
+  run<2, 1, 130>(8, "PV block + try_wait, warps 4-7 skewed 130");
+  run<0, 1, 0>(4, "QK block + try_wait, 4 warps");
   printf("status %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
   return 0;
 }
