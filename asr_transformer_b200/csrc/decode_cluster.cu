@@ -226,6 +226,7 @@ struct Producer {
 #ifdef ASR_TRACE
   long long* trace = nullptr;   // diagnostic build: per stage (wait begin, armed) clocks of one step of CTA 0
   int ntrace = 0;
+  int tag = 0;                  // what the stage holds (low 4 bits of the recorded wait-begin clock)
 #endif
   __device__ __forceinline__ uint8_t* begin(uint32_t bytes) {
     if ((threadIdx.x & 31) == 0) {
@@ -235,7 +236,7 @@ struct Producer {
       mbar_expect_tx(&r.full[slot], bytes);
 #ifdef ASR_TRACE
       if (trace && ntrace < 256) {
-        trace[2 * ntrace] = w0;
+        trace[2 * ntrace] = (w0 & ~15LL) | tag;
         trace[2 * ntrace + 1] = clock64();
         ++ntrace;
       }
@@ -924,7 +925,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
 #pragma unroll 1
       for (int t = 0; t < p.L; ++t) {
 #ifdef ASR_TRACE
-        pr.trace = (p.timing && blockIdx.x == 0 && t == 64) ? p.timing + 148 * 16 + 512 : nullptr;
+        pr.trace = (p.timing && blockIdx.x == 0 && t == 70) ? p.timing + 148 * 16 + 512 : nullptr;
 #endif
         if (p.stop_at_eos) {                       // strict gate: nothing of step t is requested before step t-1 ended
           while (ctrl[0] < t && !ctrl[1]) {
@@ -934,12 +935,18 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
 #pragma unroll 1
         for (int l = 0; l < p.nd; ++l) {
           const uint8_t* img = my_image + size_t(l) * p.layer_bytes;
+#ifdef ASR_TRACE
+          pr.tag = 1;
+#endif
           {
             uint8_t* dst = pr.begin(S::SMALL_BYTES);
             if (plane == 0) bulk_load(dst, img + p.off_small, S::SMALL_BYTES, pr.bar(), pol_w);
             pr.end();
           }
           if (p.kv_prefetch) kv_prefetch(l, 0);
+#ifdef ASR_TRACE
+          pr.tag = 2;
+#endif
           pr.mat<MQkv>(img + p.off_qkv, pol_w);
           if (t > 0) {   // self cache rows 0..t-1 of this layer (written by this CTA in earlier steps)
             const int need = (t - 1) * p.nd + l + 1;
@@ -953,6 +960,9 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
               for (int kv = 0; kv < 2; ++kv)               // K stages of the super-chunk, then its V stages
                 for (int r0 = 0; r0 < nk; r0 += RPS) {
                   const int n = (min(RPS, nk - r0) + 31) & ~31;   // whole 32-key blocks (rows past t are zero)
+#ifdef ASR_TRACE
+                  pr.tag = 3 + kv;
+#endif
                   uint8_t* dst = pr.begin(uint32_t(GU) * n * 128u);
                   if (plane < GU)
                     bulk_load(dst + plane * RPS * 128, cbase + size_t(kv) * Lc * 64 + size_t(c0 + r0) * 64, n * 128,
@@ -961,7 +971,13 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
                 }
             }
           }
+#ifdef ASR_TRACE
+          pr.tag = 5;
+#endif
           pr.mat<MWo>(img + p.off_wo, pol_w);
+#ifdef ASR_TRACE
+          pr.tag = 6;
+#endif
           pr.mat<MWqc>(img + p.off_wqc, pol_w);
           {
             const int row0 = (l * p.B + ubase + plane) * p.Tp;   // lane u: encoder K/V rows of utterance slot u
@@ -970,6 +986,9 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
               if (p.kv_prefetch) kv_prefetch(l, c0 + S::SCX * RPS);   // the NEXT super-chunk: on its way to L2 meanwhile
               for (int kv = 0; kv < 2; ++kv)
                 for (int r0 = 0; r0 < nk; r0 += RPS) {
+#ifdef ASR_TRACE
+                  pr.tag = 7 + kv;
+#endif
                   uint8_t* dst = pr.begin(uint32_t(GU) * RPS * 128u);
                   if (plane < GU)
                     tma_load_2d_hint(dst + plane * RPS * 128, &ckv_map, pr.bar(), kv * D + rank * 64, row0 + c0 + r0,
@@ -978,10 +997,22 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
                 }
             }
           }
+#ifdef ASR_TRACE
+          pr.tag = 9;
+#endif
           pr.mat<MWo>(img + p.off_woc, pol_w);
+#ifdef ASR_TRACE
+          pr.tag = 10;
+#endif
           pr.mat<MW1>(img + p.off_w1, pol_w);
+#ifdef ASR_TRACE
+          pr.tag = 11;
+#endif
           pr.mat<MW2>(img + p.off_w2, pol_w);
         }
+#ifdef ASR_TRACE
+          pr.tag = 12;
+#endif
         pr.mat<MCls>(my_image + p.off_cls, pol_w);
       }
       if (p.timing && plane == 0) {
@@ -1176,7 +1207,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
 #pragma unroll 1
     for (; t < p.L; ++t) {
 #ifdef ASR_TRACE
-      c.trace = (p.timing && blockIdx.x == 0 && t == 64) ? p.timing + 148 * 16 : nullptr;
+      c.trace = (p.timing && blockIdx.x == 0 && t == 70) ? p.timing + 148 * 16 : nullptr;
 #endif
 #pragma unroll 1
       for (int l = 0; l < p.nd; ++l) {

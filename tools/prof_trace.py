@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Stage timeline of one decode step (diagnostic build -DASR_TRACE): consumer warp 0 acquire (begin, end) clocks and the
-producer's (wait begin, armed) clocks for step 64 of CTA 0.  python tools/prof_trace.py [batch]"""
+producer's (wait begin, armed) clocks for step 70 of CTA 0.  python tools/prof_trace.py [batch]"""
 import ctypes as C
 import os
 import sys
@@ -29,9 +29,12 @@ for _ in range(2):
 tr = phase[148 * 16:].cpu().view(2, 256, 2)
 cons, prod = tr[0], tr[1]
 t0 = int(min(cons[0, 0], prod[0, 0]))
-print("stage | producer: wait_begin armed | consumer: acq_begin acq_end (wait) | lead = acq_begin - armed")
+TAGS = ["?", "small", "Wqkv", "selfK", "selfV", "Wo", "Wqc", "crossK", "crossV", "Woc", "W1", "W2", "Wcls", "?", "?", "?"]
+print("stage kind | producer: wait_begin armed | consumer: acq_begin acq_end (wait) | lead = acq_begin - armed | to next acquire")
 for i in range(256):
     if cons[i, 0] == 0:
         break
     pb, pa, cb, ce = int(prod[i, 0]) - t0, int(prod[i, 1]) - t0, int(cons[i, 0]) - t0, int(cons[i, 1]) - t0
-    print(f"{i:3d} | {pb:7d} {pa:7d} | {cb:7d} {ce:7d} ({ce - cb:5d}) | {cb - pa:7d}")
+    kind = TAGS[int(prod[i, 0]) & 15]
+    nxt = (int(cons[i + 1, 0]) - t0 - cb) if i + 1 < 256 and cons[i + 1, 0] != 0 else 0
+    print(f"{i:3d} {kind:7s} | {pb:7d} {pa:7d} | {cb:7d} {ce:7d} ({ce - cb:5d}) | {cb - pa:7d} | {nxt:6d}")
