@@ -129,7 +129,8 @@ struct Shape {
   static constexpr int H = H_, CS = H_, D = 64 * H_, FFS = FFS_, VS = VS_, GUP = GUP_;
   static constexpr int RPS = (STAGE_BYTES / 128) / GUP;   // key rows per utterance slot per ring stage (K or V rows)
   static constexpr int WPU = NCW / GUP;                   // attention warps per utterance slot
-  static constexpr int SCX = GUP >= 4 ? 4 : 2;            // K stages per super-chunk (softmax granularity): 256 keys (128 at GUP 8)
+  static constexpr int SCX = GUP >= 4 ? 4 : 2;            // K stages per super-chunk (softmax granularity): 256 keys (128 at GUP 8;
+                                                          // 256 there: 15.4 -> 17.3 ms, the V stages fall too far behind their K stages)
   static constexpr int TPW = (RPS / 16) / WPU;            // 16-key tiles per warp per stage
   static constexpr int SMALL_FLOATS = 256 + FFS + 11 * D;   // ... | ln1 | ln2 | ln3 | ln1 of the NEXT layer
   static constexpr uint32_t SMALL_BYTES = (SMALL_FLOATS * 4 + 127) / 128 * 128;
@@ -533,24 +534,26 @@ __device__ __forceinline__ void ln_rows(const float* h, int GU, const float* gam
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-// Single-query attention of ONE head on the tensor cores in blocks of 32 keys, flash style (log2 units), WITHOUT any
-// cross-lane data movement between the score and the value products:
-//   S = q K^T : A = q (MMA rows 0-7 = f16 hi part, rows 8-15 = lo part, each replicated), B = K^T: MMA group j takes the
-//               keys 8j .. 8j + 7 as its columns, B fragments by ldmatrix.x4 (non-transposed) from the 128-byte-swizzled
-//               K rows TMA wrote.  Lane (g, tg) ends up with the scores of keys 8j + 2tg, 8j + 2tg + 1 (j = 0..3; hi row
-//               + lo row added in the lane), replicated over g.
+// Single-query attention of ONE head on the tensor cores in blocks of 32 keys, flash style (log2 units):
+//   S = K q   : A = K [16 keys x 16 dims] by ldmatrix.x4 (non-transposed) from the 128-byte-swizzled K rows TMA wrote,
+//               B = q with even MMA columns = f16 hi part, odd columns = lo part (replicated): 2 key tiles x 4 dim tiles
+//               = 8 MMAs per block.  Lane (g, tg) ends up with the scores of keys 16 mi + g and 16 mi + 8 + g (hi
+//               column + lo column added in the lane), replicated over tg: 4 scores per lane and block.  (Round 2 first
+//               ran the transposed form, A = q as two distinct rows of 16 and B = K^T: 16 MMAs and 8 scores per lane,
+//               no lane exchange before P V; the legacy MMA issue rate of ~10 cycles per scheduler made that the bound
+//               of the K stages - 15.7 -> 15.4 ms per 256-utterance launch for this form, same tokens.)
 //   o += V^T p: A = V^T [16 dims x 16 keys] by ldmatrix.x4.trans of the row-major V rows, B = p with even columns = f16
 //               hi parts, odd columns = lo parts: for k-tile kt lane (g, tg) must supply keys 16kt + 2tg (+1) and
-//               16kt + 8 + 2tg (+1) - exactly the scores it owns (groups 2kt and 2kt + 1).  o(dim) = c(even col) +
-//               c(odd col), replicated over tg.
-// Running max m is warp-uniform; the running sum l is a per-lane partial over the lane's own keys (replicated over g).
+//               16kt + 8 + 2tg (+1), which live in lanes (2tg, *) and (2tg + 1, *): 2 shuffles + 2 byte permutes per
+//               k-tile (p_pack_ka).  o(dim) = c(even col) + c(odd col), replicated over tg.
+// Running max m is warp-uniform; the running sum l is a per-lane partial over the lane's own keys (replicated over tg).
 struct AttnT {
   float m, l;
   float o[4][4];
 };
-// q of one utterance: 64 half2 words [tg 4][k-tile 4][a0 = hi pair 0, a1 = lo pair 0, a2 = hi pair 1, a3 = lo pair 1] with
-// pair 0 = dims 16 kt + 2 tg (+1), pair 1 = dims 16 kt + 8 + 2 tg (+1): lane (g, tg) loads its four A fragments with four
-// LDS.128 (all g read the same words: broadcast).
+// q of one utterance: 64 half2 words [tg 4][k-tile 4][hi pair 0, lo pair 0, hi pair 1, lo pair 1] with pair 0 = dims
+// 16 kt + 2 tg (+1), pair 1 = dims 16 kt + 8 + 2 tg (+1): lane (g, tg) reads the word group (tg, kt) with one LDS.128 (all g
+// read the same words: broadcast) and keeps the hi or the lo halves (attn_q_bfrags).
 __device__ __forceinline__ int q_word_index(int d) {
   const int r = d & 15;
   return ((((r & 7) >> 1) * 4 + (d >> 4)) * 4) + (r >> 3) * 2;
@@ -569,12 +572,6 @@ __device__ __forceinline__ void q_store2(__half2* q, float* qf, int u, int d, fl
   q[i + 1] = lo;
   if (qf) *reinterpret_cast<float2*>(qf + u * 64 + d) = make_float2(y0, y1);   // fp32 copy: score of the current key
 }
-__device__ __forceinline__ void attn_q_frags(const __half2* q, int u, uint4 (&qa)[4]) {
-  const int tg = threadIdx.x & 3;
-  const uint4* src = reinterpret_cast<const uint4*>(q + u * 64 + tg * 16);
-#pragma unroll
-  for (int kt = 0; kt < 4; ++kt) qa[kt] = src[kt];
-}
 // ldmatrix with a "memory" clobber but NOT volatile: ordered against the ring's acquire / release (which clobber
 // memory) and among themselves, while the register-only MMAs are free to move between them.
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint4& r) {
@@ -585,43 +582,69 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint4& r) {
   asm("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
       : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
 }
-// scores of the 32 keys of one K tile (32 rows of 128 B, chunk c of row r stored at chunk c ^ (r & 7)); s[2j + e] <-> key
-// 8j + 2tg + e; keys >= n_valid get -inf (select, not arithmetic: rows past the valid keys may hold anything)
-__device__ __forceinline__ void qk_load(uint32_t kbase, uint4 (&kf)[4][2]) {
-  const int lane = threadIdx.x & 31, mat = lane >> 3, r = lane & 7;
-  const uint32_t row = kbase + r * 128;
+// B fragments of q: lane (g, tg) holds, for every k-tile, dims 16 kt + 2 tg (+1) and 16 kt + 8 + 2 tg (+1) of column g =
+// the hi part (even g) or the lo part (odd g)
+__device__ __forceinline__ void attn_q_bfrags(const __half2* q, int u, uint2 (&qb)[4]) {
+  const int lane = threadIdx.x & 31, tg = lane & 3;
+  const bool odd = (lane >> 2) & 1;
+  const uint4* src = reinterpret_cast<const uint4*>(q + u * 64 + tg * 16);   // {hi pair 0, lo pair 0, hi pair 1, lo pair 1}
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    ldsm_x4(row + j * 1024 + ((mat ^ r) << 4), kf[j][0]);        // dims 0..31  (chunks 0..3): k-tiles 0, 1
-    ldsm_x4(row + j * 1024 + (((mat + 4) ^ r) << 4), kf[j][1]);  // dims 32..63 (chunks 4..7): k-tiles 2, 3
+  for (int kt = 0; kt < 4; ++kt) {
+    const uint4 v = src[kt];
+    qb[kt] = make_uint2(odd ? v.y : v.x, odd ? v.w : v.z);
   }
 }
-__device__ __forceinline__ void qk_math(const uint4 (&kf)[4][2], int n_valid, const uint4 (&qa)[4], float (&s)[8]) {
-  const int tg = threadIdx.x & 3;
-  // one accumulator per 8-key group, the four k-tiles chained through it; the four groups interleave, so consecutive
-  // MMAs are independent (a dependent one waits ~20 cycles for its accumulator) and no add waits for a result before all
-  // sixteen are issued
-  float cc[4][4];
+// A fragments of one K tile (32 rows of 128 B, chunk c of row r stored at chunk c ^ (r & 7)): matrices of an ldmatrix.x4 =
+// keys 0-7 | 8-15 of dims 0-7, then of dims 8-15 of the (key tile mi, dim tile kt)
+__device__ __forceinline__ void ka_load(uint32_t kbase, uint4 (&ka)[2][4]) {
+  const int lane = threadIdx.x & 31, mat = lane >> 3, r = lane & 7;
+  const uint32_t row = kbase + ((mat & 1) * 8 + r) * 128;
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
+  for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) cc[j][i] = 0.f;
+    for (int kt = 0; kt < 4; ++kt) ldsm_x4(row + mi * 2048 + (((2 * kt + (mat >> 1)) ^ r) << 4), ka[mi][kt]);
+}
+// s[2 mi + e] <-> key 16 mi + 8 e + g; keys >= n_valid get -inf (select, not arithmetic: rows past the valid keys may
+// hold anything).  One accumulator per key tile, the four dim tiles chained through it.
+__device__ __forceinline__ void ka_math(const uint4 (&ka)[2][4], int n_valid, const uint2 (&qb)[4], float (&s)[4]) {
+  const int g = (threadIdx.x & 31) >> 2;
+  float cc[2][4];
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cc[mi][i] = 0.f;
 #pragma unroll
   for (int kt = 0; kt < 4; ++kt)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint4& k = kf[j][kt >> 1];
-      mma16816(cc[j], qa[kt], (kt & 1) ? k.z : k.x, (kt & 1) ? k.w : k.y);
-    }
+    for (int mi = 0; mi < 2; ++mi) mma16816(cc[mi], ka[mi][kt], qb[kt].x, qb[kt].y);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    s[2 * j] = cc[j][0] + cc[j][2];                              // key 8j + 2tg      (hi row + lo row)
-    s[2 * j + 1] = cc[j][1] + cc[j][3];                          // key 8j + 2tg + 1
+  for (int mi = 0; mi < 2; ++mi) {
+    s[2 * mi] = cc[mi][0] + cc[mi][1];                           // key 16 mi + g      (hi column + lo column)
+    s[2 * mi + 1] = cc[mi][2] + cc[mi][3];                       // key 16 mi + 8 + g
   }
   if (n_valid < 32) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (8 * (i >> 1) + 2 * tg + (i & 1) >= n_valid) s[i] = -INFINITY;
+    for (int i = 0; i < 4; ++i)
+      if (16 * (i >> 1) + 8 * (i & 1) + g >= n_valid) s[i] = -INFINITY;
+  }
+}
+// B fragments of the probabilities for o += V^T p: k-tile kt needs, in lane (g, tg), {keys 16 kt + 2 tg (+1), keys
+// 16 kt + 8 + 2 tg (+1)} as f16 hi parts (even g) or lo parts (odd g); the lane owns keys 16 kt + g and 16 kt + 8 + g.
+// Every lane publishes ONE word per k-tile, (part of key g, part of key g + 8) with part = hi in the replicas tg even, lo
+// in the replicas tg odd, and the reader takes it from the replica of its own parity: 2 shuffles + 2 byte permutes per
+// k-tile.
+__device__ __forceinline__ void p_pack_ka(const float (&p)[4], uint32_t (&pb)[4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+  const int src = 8 * tg + (g & 1);                              // lane (2 tg, g & 1); + 4: lane (2 tg + 1, g & 1)
+#pragma unroll
+  for (int kt = 0; kt < 2; ++kt) {
+    __half2 hi, lo;
+    hilo2(p[2 * kt], p[2 * kt + 1], hi, lo);
+    const __half2 mine = (tg & 1) ? lo : hi;
+    const uint32_t r = *reinterpret_cast<const uint32_t*>(&mine);
+    const uint32_t x = __shfl_sync(0xffffffffu, r, src), y = __shfl_sync(0xffffffffu, r, src + 4);
+    pb[2 * kt] = __byte_perm(x, y, 0x5410);                      // keys 16 kt + 2 tg, + 1
+    pb[2 * kt + 1] = __byte_perm(x, y, 0x7632);                  // keys 16 kt + 8 + 2 tg, + 1
   }
 }
 // exp2 on the SFU (ex2.approx.ftz: 2 ulp, -inf -> +0); the library exp2f costs three more instructions per value
@@ -629,19 +652,6 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-// B fragments of the probabilities p[2j + e] <-> key 8j + 2tg + e: k-tile kt needs {b0 = keys 16kt + 2tg (+1), b1 = keys
-// 16kt + 8 + 2tg (+1)} = pack(p[4kt], p[4kt+1]), pack(p[4kt+2], p[4kt+3]); even g supply the f16 hi parts (even MMA
-// columns), odd g the lo parts.
-__device__ __forceinline__ void p_pack(const float (&p)[8], uint32_t (&pb)[4]) {
-  const bool lo_lane = (threadIdx.x >> 2) & 1;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __half2 hi, lo;
-    hilo2(p[2 * i], p[2 * i + 1], hi, lo);
-    const __half2 v = lo_lane ? lo : hi;
-    pb[i] = *reinterpret_cast<const uint32_t*>(&v);
-  }
 }
 // o += V^T p for one value tile (32 rows of 128 B, swizzled like K)
 __device__ __forceinline__ void pv_load(uint32_t vbase, uint4 (&vf)[4][2]) {
@@ -677,7 +687,7 @@ __device__ __forceinline__ void attn_init(AttnT& st, const float* qf, const f16*
     const int d = 2 * lane, pos = (((d >> 3) ^ swz) << 3) + (d & 7);
     const float2 k2 = __half22float2(*reinterpret_cast<const __half2*>(kv_row_u + pos));
     st.m = warp_sum(fmaf(q2.x, k2.x, q2.y * k2.y));
-    st.l = tg == 0 ? 1.f : 0.f;
+    st.l = g == 0 ? 1.f : 0.f;     // per-lane partial sums are replicated over tg, distinct over g
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {                             // dims 16mt + g, 16mt + g + 8: chunks 2mt, 2mt + 1
       st.o[mt][0] = __half2float(kv_row_u[64 + (((2 * mt) ^ swz) << 3) + g]);
@@ -685,13 +695,15 @@ __device__ __forceinline__ void attn_init(AttnT& st, const float* qf, const f16*
     }
   }
 }
+typedef uint2 QFrag;     // B fragment of q for one k-tile
+constexpr int SPB = 4;   // scores per lane and 32-key block
 // Attention of this warp's (utterance slot au, key partition apart) over n_keys rows streamed through the ring as
 // super-chunks of up to SC K stages followed by the matching V stages; a stage holds, per utterance slot, WPU blocks of
 // 32 keys ([slot][RPS rows][128 B]) and warp (au, apart) owns block apart of every stage.  All scores of a super-chunk are computed first, then ONE max / exp / sum, then all P V products.  n_keys rows
 // are streamed (uniform over the CTA); only the first n_mine are valid keys of THIS warp's utterance (key padding), the
 // rest are masked.  Stage presence (s < ns) is CTA-uniform; blocks without a valid key skip their math only.
 template <class S, int SC>
-__device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint4 (&qa)[4], int n_keys, int n_mine,
+__device__ __forceinline__ void attention(Consumer& c, AttnT& st, const QFrag (&qa)[4], int n_keys, int n_mine,
                                           bool active, int au, int apart) {
   constexpr int RPS = S::RPS;
   const uint32_t blk_off = (au * S::WPU + apart) * 4096;
@@ -702,12 +714,12 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint4 (&
     const int nk = min(SC * RPS, n_keys - c0);                  // CTA-uniform
     const int ns = (nk + RPS - 1) / RPS;
     const int lim = active ? n_mine - c0 - 32 * apart : 0;      // my valid keys counted from my block of stage 0
-    float sc[SC][8];
+    float sc[SC][SPB];
     float mx = -INFINITY;
 #pragma unroll
     for (int s = 0; s < SC; ++s) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) sc[s][i] = -INFINITY;
+      for (int i = 0; i < SPB; ++i) sc[s][i] = -INFINITY;
       if (s < ns) {
         const uint32_t stg = smem_u32(c.acquire()) + blk_off;
         const int n = lim - s * RPS;
@@ -715,19 +727,20 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint4 (&
           // The slot goes back to the producer as soon as its rows are requested: the arrive is a release, so the
           // ldmatrix reads before it are ordered before the producer's next copy into the slot; the math then runs
           // from registers while the refill is under way (64 / 128-utterance launches -1.8 %, 256 unchanged).
-          uint4 kf[4][2];
-          qk_load(stg, kf);
+          uint4 ka[2][4];
+          ka_load(stg, ka);
           c.release();
-          qk_math(kf, n, qa, sc[s]);
+          ka_math(ka, n, qa, sc[s]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) mx = fmaxf(mx, sc[s][i]);
+          for (int i = 0; i < SPB; ++i) mx = fmaxf(mx, sc[s][i]);
         } else {
           c.release();
         }
       }
     }
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));        // the four tg lanes own different keys
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));        // the eight g lanes own different keys
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
     const float m_new = fmaxf(st.m, mx);
     const float m_use = (m_new == -INFINITY) ? 0.f : m_new;     // a warp without any key: every p = ex2(-inf) = 0
     const float alpha = ex2(st.m - m_use);
@@ -736,13 +749,13 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint4 (&
 #pragma unroll
     for (int s = 0; s < SC; ++s)
       if (s < ns) {
-        float pr[8];
+        float pr[SPB];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < SPB; ++i) {
           pr[i] = ex2(sc[s][i] - m_use);
           lsum += pr[i];
         }
-        p_pack(pr, pb[s]);
+        p_pack_ka(pr, pb[s]);
       }
     st.l = st.l * alpha + lsum;
     st.m = m_new;
@@ -771,9 +784,10 @@ __device__ __forceinline__ void attention(Consumer& c, AttnT& st, const uint4 (&
 template <class S>
 __device__ __forceinline__ void attn_finish(AttnT& st, int GU, float* part_buf, float* stat, f16* o_hi, f16* o_lo) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
-  float l = st.l;                                               // per-lane partial over the lane's keys, replicated over g
-  l += __shfl_xor_sync(0xffffffffu, l, 1);
-  l += __shfl_xor_sync(0xffffffffu, l, 2);
+  float l = st.l;                                               // per-lane partial over the lane's keys
+  l += __shfl_xor_sync(0xffffffffu, l, 4);                      // (replicated over tg, summed over g)
+  l += __shfl_xor_sync(0xffffffffu, l, 8);
+  l += __shfl_xor_sync(0xffffffffu, l, 16);
   if (S::WPU == 1) {   // one warp holds the whole utterance: no merge; lane (g, tg) emits dims 16 tg + g, 16 tg + g + 8
     float a = 0.f, b = 0.f;
 #pragma unroll
@@ -1299,9 +1313,9 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
               ar_gam = ln + 4 * D;                              // -> LN3 (model.py:73)
             }
             AttnT st;
-            uint4 qa[4];
+            QFrag qa[4];
             attn_init(st, cur ? q_f32 + au * 64 : nullptr, kv_row + au * 128, t & 7);
-            attn_q_frags(q_frag, au, qa);
+            attn_q_bfrags(q_frag, au, qa);
             attention<S, S::SCX>(c, st, qa, n_keys, n_mine, a_active, au, apart);
             if (pass == 0) {
               if (tid < GU * 2) bulk_store_wait();              // this step's cache rows are written (published below)
