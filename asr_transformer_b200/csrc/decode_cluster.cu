@@ -108,6 +108,22 @@ __device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* m
       ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(pol)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_hint(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                 uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], "
+      "[%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_hint(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                                 int c3, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2], %7;"
+      ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(pol)
+      : "memory");
+}
 // TMA store of a small contiguous block shared -> global (async proxy), tracked by the thread's bulk group
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
@@ -847,7 +863,8 @@ __device__ __forceinline__ void attn_finish(AttnT& st, int GU, float* part_buf, 
 // (setmaxnreg with a donor warpgroup was tried: ptxas drops the pair unless the producer branch fits 40 registers.)
 template <class S>
 __global__ void __launch_bounds__(NTHREADS, 1)
-dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constant__ CUtensorMap ckv_map) {
+dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constant__ CUtensorMap ckv_map,
+                   const __grid_constant__ CUtensorMap cache_map) {
   constexpr int D = S::D, H = S::H, CS = S::CS, GUP = S::GUP, FFS = S::FFS, VS = S::VS, RPS = S::RPS;
   using MQkv = Mat<12, D / 32>;
   using MWo = Mat<D / 16, 2>;
@@ -977,11 +994,19 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
 #ifdef ASR_TRACE
                   pr.tag = 3 + kv;
 #endif
-                  uint8_t* dst = pr.begin(uint32_t(GU) * n * 128u);
-                  if (plane < GU)
-                    bulk_load(dst + plane * RPS * 128, cbase + size_t(kv) * Lc * 64 + size_t(c0 + r0) * 64, n * 128,
-                              pr.bar(), pol_kv);
-                  pr.end();
+                  if constexpr (RPS == 32) {   // 8 utterance slots of 32 rows: ONE 4-D box [slot][1][32 rows][64] per stage
+                    uint8_t* dst = pr.begin(uint32_t(GUP) * RPS * 128u);
+                    if (plane == 0)
+                      tma_load_4d_hint(dst, &cache_map, pr.bar(), 0, c0 + r0, rank * 2 + kv, l * p.B + ubase, pol_kv);
+                    pr.end();
+                    (void)n;
+                  } else {                     // (fewer, longer slots: a fixed box would copy rows nobody needs)
+                    uint8_t* dst = pr.begin(uint32_t(GU) * n * 128u);
+                    if (plane < GU)
+                      bulk_load(dst + plane * RPS * 128, cbase + size_t(kv) * Lc * 64 + size_t(c0 + r0) * 64, n * 128,
+                                pr.bar(), pol_kv);
+                    pr.end();
+                  }
                 }
             }
           }
@@ -994,8 +1019,11 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
 #endif
           pr.mat<MWqc>(img + p.off_wqc, pol_w);
           {
-            const int row0 = (l * p.B + ubase + plane) * p.Tp;   // lane u: encoder K/V rows of utterance slot u
-            for (int c0 = 0; c0 < p.Tp; c0 += S::SCX * RPS) {    // 2-D boxes [RPS rows][64 columns] of this head
+            // ONE 3-D box per stage: [GUP utterance slots][RPS rows][64 columns of this head] (eight per-utterance 2-D
+            // copies issued by eight lanes cost the producer ~700 cycles per stage - TMA issue is serial within a warp -
+            // against the ~500 the consumers need: the ring ran dry in the second half of every cross attention).  Rows
+            // past Tp and utterance slots past the batch are out of bounds: zero-filled, counted in the byte count.
+            for (int c0 = 0; c0 < p.Tp; c0 += S::SCX * RPS) {
               const int nk = min(S::SCX * RPS, p.Tp - c0);
               if (p.kv_prefetch) kv_prefetch(l, c0 + S::SCX * RPS);   // the NEXT super-chunk: on its way to L2 meanwhile
               for (int kv = 0; kv < 2; ++kv)
@@ -1003,10 +1031,9 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
 #ifdef ASR_TRACE
                   pr.tag = 7 + kv;
 #endif
-                  uint8_t* dst = pr.begin(uint32_t(GU) * RPS * 128u);
-                  if (plane < GU)
-                    tma_load_2d_hint(dst + plane * RPS * 128, &ckv_map, pr.bar(), kv * D + rank * 64, row0 + c0 + r0,
-                                     pol_kv);
+                  uint8_t* dst = pr.begin(uint32_t(GUP) * RPS * 128u);
+                  if (plane == 0)
+                    tma_load_3d_hint(dst, &ckv_map, pr.bar(), kv * D + rank * 64, c0 + r0, l * p.B + ubase, pol_kv);
                   pr.end();
                 }
             }
@@ -1483,7 +1510,7 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------ instances
-typedef void (*ClusterKernel)(const ClusterParams, const CUtensorMap);
+typedef void (*ClusterKernel)(const ClusterParams, const CUtensorMap, const CUtensorMap);
 struct Instance {
   int H, FFS, VS, GUP;
   ClusterKernel fn;
@@ -1591,13 +1618,24 @@ int launch_dec_cluster(ClusterParams& p, cudaStream_t s) {
     p.kv_evict_first = !(e && e[0] == 'l');
   }
 
-  // encoder K/V as a 2-D tensor: [nd * B * Tp rows][2D columns] f16; box = [RPS rows][64 columns] (one head)
+  // encoder K/V as a 3-D tensor: [nd * B utterances][Tp rows][2D columns] f16; box = [GUP utterances][RPS rows][64 columns
+  // (one head)] = one ring stage
   CUtensorMap map;
   const int rps = (STAGE_BYTES / 128) / p.GUP;
-  const uint64_t dims[2] = {uint64_t(2 * p.D), uint64_t(p.nd) * p.B * p.Tp};
-  const uint64_t strides[2] = {0, uint64_t(4 * p.D)};
-  const uint32_t box[2] = {64u, uint32_t(rps)};
-  if (int rc = make_tmap_f16(&map, p.ckv, 2, dims, strides, box, nullptr, /*swizzle=*/128)) return rc;
+  const uint64_t dims[3] = {uint64_t(2 * p.D), uint64_t(p.Tp), uint64_t(p.nd) * p.B};
+  const uint64_t strides[3] = {0, uint64_t(4 * p.D), uint64_t(p.Tp) * 4 * p.D};
+  const uint32_t box[3] = {64u, uint32_t(rps), uint32_t(p.GUP)};
+  if (int rc = make_tmap_f16(&map, p.ckv, 3, dims, strides, box, nullptr, /*swizzle=*/128)) return rc;
+  // self K/V cache as a 4-D tensor: [nd * B utterances][H heads x (K | V)][Lc rows][64] f16, rows stored pre-swizzled
+  // (no TMA swizzle); box = [GUP utterances][1][RPS rows][64]
+  CUtensorMap cmap;
+  {
+    const uint64_t Lc = uint64_t((p.L + 31) & ~31);
+    const uint64_t cdims[4] = {64, Lc, uint64_t(2 * p.H), uint64_t(p.nd) * p.B};
+    const uint64_t cstr[4] = {0, 128, Lc * 128, uint64_t(2 * p.H) * Lc * 128};
+    const uint32_t cbox[4] = {64u, uint32_t(rps), 1u, uint32_t(p.GUP)};
+    if (int rc = make_tmap_f16(&cmap, p.cache, 4, cdims, cstr, cbox, nullptr, /*swizzle=*/0)) return rc;
+  }
 
   const int n_clusters = (p.B + p.GU - 1) / p.GU;
   cudaLaunchConfig_t cfg{};
@@ -1609,7 +1647,7 @@ int launch_dec_cluster(ClusterParams& p, cudaStream_t s) {
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = p.H; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  ASR_CUDA_OK(cudaLaunchKernelEx(&cfg, chosen->fn, p, map));
+  ASR_CUDA_OK(cudaLaunchKernelEx(&cfg, chosen->fn, p, map, cmap));
   ASR_LAUNCHED(1);
   return 0;
 }
