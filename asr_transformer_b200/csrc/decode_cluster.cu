@@ -953,6 +953,17 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
                        "r"(uint32_t(n) * 4u * D)
                        : "memory");
       };
+      // The self K/V cache (201 MB at 256 utterances) does not stay in L2 either: the first self-attention stage of a layer
+      // used to arrive ~1.7 k cycles late.  Its rows are prefetched one layer ahead (lane = utterance slot x (K | V), one
+      // contiguous block of round32(t) rows each), issued where the producer is normally waiting for a free slot.
+      auto self_prefetch = [&](int l2, int t2) {
+        const int u = plane >> 1, n = (t2 + 31) & ~31;
+        if (t2 > 0 && plane < 2 * GU)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.cache + ((size_t(l2) * p.B + ubase + u) * H + rank) *
+                                                                                  cache_head + size_t(plane & 1) * Lc * 64),
+                       "r"(uint32_t(n) * 128u)
+                       : "memory");
+      };
 #pragma unroll 1
       for (int t = 0; t < p.L; ++t) {
 #ifdef ASR_TRACE
@@ -1041,6 +1052,10 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
 #ifdef ASR_TRACE
           pr.tag = 9;
 #endif
+          if (p.kv_prefetch) {
+            if (l + 1 < p.nd) self_prefetch(l + 1, t);
+            else if (t + 1 < p.L) self_prefetch(0, t + 1);
+          }
           pr.mat<MWo>(img + p.off_woc, pol_w);
 #ifdef ASR_TRACE
           pr.tag = 10;
