@@ -1116,26 +1116,15 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
     // peer sends its slice only after it has finished reading its receive slots (and every CTA's s_h readers of step n
     // are done before that CTA sends its partials of step n + 1, without which nobody can produce a step n + 1 slice).
     // Both barriers simply alternate phases.  Windows of every rank (own included: the data path is uniform):
-    uint32_t all_recv[CS], all_h[CS], all_bar[CS];
-#pragma unroll
-    for (int r = 0; r < CS; ++r) {
-      all_recv[r] = mapa_u32(smem_u32(recv), uint32_t(r));
-      all_h[r] = mapa_u32(smem_u32(s_h), uint32_t(r));
-      all_bar[r] = mapa_u32(smem_u32(&xbar[0]), uint32_t(r));
-    }
+    // (the peers' windows are mapped where they are used: `mapa` is one instruction, twelve mapped addresses held for the
+    // whole kernel are twelve registers of a kernel that sits at its register cap)
     // Residual stream s_h ([utterance][D]) and the receive slots ([source rank][utterance][64]) are fp32 rows with skewed
     // columns (hswz).
     auto send_partial = [&](int n, int u0, const float4& v) {     // v = {(n,u0), (n,u0+1), (n+1,u0), (n+1,u0+1)}
       const int dst = n >> 6, nn = n & 63;
       const uint32_t off0 = uint32_t((rank * GUP + u0) * 64 + (nn ^ hswz(u0))) * 4u;
       const uint32_t off1 = uint32_t((rank * GUP + u0 + 1) * 64 + (nn ^ hswz(u0 + 1))) * 4u;
-      uint32_t base = all_recv[0], bar = all_bar[0];
-#pragma unroll
-      for (int r = 1; r < CS; ++r)
-        if (dst == r) {
-          base = all_recv[r];
-          bar = all_bar[r];
-        }
+      const uint32_t base = mapa_u32(smem_u32(recv), uint32_t(dst)), bar = mapa_u32(smem_u32(&xbar[0]), uint32_t(dst));
       st_async_v2(base + off0, v.x, v.z, bar);
       st_async_v2(base + off1, v.y, v.w, bar);
     };
@@ -1177,7 +1166,8 @@ dec_cluster_kernel(const __grid_constant__ ClusterParams p, const __grid_constan
         const float hx = h.x + (sum.x + b.x), hy = h.y + (sum.y + b.y);
         const uint32_t off = uint32_t(u * D + (n ^ sw)) * 4u;
 #pragma unroll
-        for (int r = 0; r < CS; ++r) st_async_v2(all_h[r] + off, hx, hy, all_bar[r] + 8u);
+        for (int r = 0; r < CS; ++r)
+          st_async_v2(mapa_u32(smem_u32(s_h) + off, uint32_t(r)), hx, hy, mapa_u32(smem_u32(&xbar[1]), uint32_t(r)));
       }
       if (timed) {
         const long long w0 = clock64();
