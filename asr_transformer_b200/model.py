@@ -7,6 +7,8 @@ the additive, batched API (device KV cache, on-GPU argmax/EOS, no per-token host
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional, Tuple
 
 import torch
@@ -363,6 +365,8 @@ class Transformer(nn.Module):
                 for xb in group:
                     xb.record_stream(enc_s)
             with torch.cuda.stream(enc_s):
+                if ptrace is not None:
+                    ptrace.append({"enc0": tev(enc_s)})
                 if group[0].is_cuda and not single:
                     o = 0
                     for xb in group:
@@ -382,6 +386,8 @@ class Transformer(nn.Module):
                                  ws_tag="pipe_enc")
                 x_free[slot] = torch.cuda.Event()
                 x_free[slot].record(enc_s)
+                if ptrace is not None:
+                    ptrace[-1]["enc1"] = tev(enc_s)
                 # cross-attention K/V + decoder state of this group: also under the previous group's decode loop.  Two
                 # decode workspaces alternate; a slot is reused only after the decode that last ran on it has finished.
                 if ws_done[slot] is not None:
@@ -393,6 +399,9 @@ class Transformer(nn.Module):
                 n_in[0] += 1
                 ev = torch.cuda.Event()
                 ev.record(enc_s)
+                if ptrace is not None:
+                    ptrace[-1]["prep1"] = tev(enc_s)
+                    ctx["trace"] = ptrace[-1]
             return ctx, ev
 
         def emit(a, b, sizes):
@@ -405,6 +414,14 @@ class Transformer(nn.Module):
         n_in = [0]
         ws_done = [None, None]
         x_free = [None, None]
+        # ASR_B200_PIPE_TRACE=1 (diagnostic): timed events around every group's encoder + prepare and decode launch; the
+        # timeline is printed to stderr when the loop ends (tools/prof_pipeline.py)
+        ptrace = [] if os.environ.get("ASR_B200_PIPE_TRACE") else None
+
+        def tev(stream):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            return e
         it = groups()
         nxt = stage_in(next(it, None))
         pending = deque()
@@ -416,9 +433,13 @@ class Transformer(nn.Module):
             for t in (ctx["keep"][0], ctx["tokens"], ctx["n_tok"]):
                 t.record_stream(dec_s)
             with torch.cuda.stream(dec_s):
+                if ptrace is not None:
+                    ctx["trace"]["dec0"] = tev(dec_s)
                 tokens, n_tok, _ = eng.decode_greedy(None, phase=ctx)
                 done = torch.cuda.Event()
                 done.record(dec_s)
+                if ptrace is not None:
+                    ctx["trace"]["dec1"] = tev(dec_s)
             ws_done[ctx["slot"]] = done
             nxt = stage_in(next(it, None))            # next group: upload + encoder under this group's decode
             # transcript side (its own stream, so that neither the multi-GPU gather - a rendezvous of all ranks - nor
@@ -463,3 +484,12 @@ class Transformer(nn.Module):
             else:
                 caller.wait_event(e)
             yield from emit(a, b, sz)
+        if ptrace:
+            import sys
+            torch.cuda.synchronize(dev)
+            t0 = ptrace[0]["enc0"]
+            print("group | encoder start end | prepare end | decode start end   (ms since the first encoder start)", file=sys.stderr)
+            for i, r in enumerate(ptrace):
+                if "dec1" in r:
+                    print("%5d | %8.3f %8.3f | %8.3f | %8.3f %8.3f" % ((i,) + tuple(t0.elapsed_time(r[k]) for k in (
+                        "enc0", "enc1", "prep1", "dec0", "dec1"))), file=sys.stderr)
