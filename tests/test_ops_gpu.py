@@ -214,6 +214,25 @@ def test_attention_nomask(B, H, Sq, Sk, impl):
     assert_close(out, attn_reference(q, k, v, scale), 2e-2, 2e-3, f"attention impl={impl}")
 
 
+@pytest.mark.parametrize("B,H,Sq,Sk", [(40, 4, 250, 250), (37, 4, 128, 250), (9, 8, 300, 256), (150, 1, 77, 33)])
+def test_attention_persistent_many_items(B, H, Sq, Sk):
+    """Sk <= 256 without causal / byte masks runs the persistent ping-pong kernel (attn_pp_kernel): every CTA walks
+    several (utterance, head, q tile) items, K/V are reloaded when the head changes, ragged key lengths incl. 0
+    (reference layers.py:20-27 with the key-padding mask of dataset.py:53-55)."""
+    q, k, v = (rnd(B, S, H, 64, seed=40 + i, scale=1.5, dtype=torch.float16) for i, S in enumerate((Sq, Sk, Sk)))
+    scale = (64 * H) ** -0.5
+    out = run_attn(q, k, v, scale)
+    assert_close(out, attn_reference(q, k, v, scale), 2e-2, 2e-3, "persistent attention")
+    g = torch.Generator().manual_seed(B)
+    k_lens = torch.randint(0, Sk + 1, (B,), generator=g, dtype=torch.int32)
+    k_lens[0], k_lens[-1] = Sk, 0
+    k_lens = k_lens.to(DEV)
+    out = run_attn(q, k, v, scale, k_lens=k_lens)
+    assert_close(out, attn_reference(q, k, v, scale, k_lens=k_lens), 2e-2, 2e-3, "persistent attention, k_lens")
+    assert (out[-1] == 0).all()
+    assert torch.equal(out, run_attn(q, k, v, scale, k_lens=k_lens))          # run-to-run identical
+
+
 @pytest.mark.parametrize("impl", [0, 1])
 def test_attention_masks(impl):
     B, H, S = 3, 2, 200
