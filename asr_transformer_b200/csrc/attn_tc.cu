@@ -635,6 +635,300 @@ attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------ the same schedule with P in tensor memory
+// attn_ts_kernel: the probabilities never touch shared memory.  A softmax thread overwrites the first half of its own
+// score row in TMEM with the packed f16 probabilities (tcgen05.st; chunk c of P lands on columns the thread has already
+// consumed) and P V is issued in the TS form (A operand from TMEM, O into columns [128, 192) of the same buffer).  The
+// 128 KB of P tiles this frees buy double buffers for Q, K and V - the producer runs two items and one head ahead, so
+// no tensor-map load sits on the critical path - and private output staging tiles per warp (the TMA store of item i
+// drains under the softmax of item i+2).
+constexpr int TS_STAGE_BYTES = 2 * BQ * DH * 2;     // 32 KB per warpgroup: f16 hi rows | lo rows of one 128-query tile
+constexpr size_t TS_SMEM = 2 * PP_Q_BYTES + 4 * PP_KV_BYTES + 2 * TS_STAGE_BYTES + 256;   // 224.25 KB
+
+__global__ void __launch_bounds__(320, 1)
+attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, AttnDev p, int nq,
+               int n_items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
+  uint8_t* sQ = smem;                               // [2] x 16 KB
+  uint8_t* sK = sQ + 2 * PP_Q_BYTES;                // [2] x 32 KB
+  uint8_t* sV = sK + 2 * PP_KV_BYTES;               // [2] x 32 KB
+  uint8_t* sO = sV + 2 * PP_KV_BYTES;               // [2 warpgroups] x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * TS_STAGE_BYTES);
+  uint64_t* q_full = bars + 0;     // every barrier below: [2]
+  uint64_t* q_free = bars + 2;
+  uint64_t* k_full = bars + 4;
+  uint64_t* k_free = bars + 6;
+  uint64_t* v_full = bars + 8;
+  uint64_t* v_free = bars + 10;
+  uint64_t* s_full = bars + 12;
+  uint64_t* p_ready = bars + 14;
+  uint64_t* o_full = bars + 16;
+  uint64_t* o_read = bars + 18;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int f0 = int((long long)blockIdx.x * n_items / gridDim.x);
+  const int f1 = int((long long)(blockIdx.x + 1) * n_items / gridDim.x);
+  const int n = f1 - f0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_free[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_free[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_free[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_read[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // keys in use for utterance b, in 32-key chunks (>= 1: an empty row then sums to l = 0 and stores zeros)
+  auto key_chunks = [&](int b, int& k_lim) {
+    k_lim = p.Sk;
+    if (p.k_lens) k_lim = min(k_lim, max(0, p.k_lens[b]));
+    return max(1, (k_lim + 31) >> 5);
+  };
+
+  if (warp == 8) {
+    if (lane == 0 && n > 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      int prev_bh = -1, kc = -1;
+      for (int it = 0; it < n; ++it) {
+        const int f = f0 + it;
+        const int bh = f / nq, qt = f - bh * nq;
+        const int b = bh / p.H, h = bh - b * p.H;
+        const int qs = it & 1;
+        if (it >= 2) mbar_wait(&q_free[qs], ((it >> 1) - 1) & 1);
+        mbar_expect_tx(&q_full[qs], PP_Q_BYTES);
+        tma_load_3d(sQ + qs * PP_Q_BYTES, &tmQ, &q_full[qs], h * DH, qt * BQ, b);
+        if (bh != prev_bh) {
+          prev_bh = bh;
+          ++kc;
+          const int st = kc & 1;
+          if (kc >= 2) mbar_wait(&k_free[st], ((kc >> 1) - 1) & 1);
+          mbar_expect_tx(&k_full[st], PP_KV_BYTES);
+          tma_load_3d(sK + st * PP_KV_BYTES, &tmK, &k_full[st], h * DH, 0, b);
+          if (kc >= 2) mbar_wait(&v_free[st], ((kc >> 1) - 1) & 1);
+          mbar_expect_tx(&v_full[st], PP_KV_BYTES);
+          tma_load_3d(sV + st * PP_KV_BYTES, &tmV, &v_full[st], h * DH, 0, b);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0 && n > 0) {
+      constexpr uint32_t idesc_S = umma_idesc_f16(BQ, PP_KEYS, 0, 0);
+      constexpr uint32_t idesc_O = umma_idesc_f16(BQ, DH, 0, 1);   // B = V tile, MN-major
+      int s_bh = -1, s_kc = -1, pv_bh = -1, pv_kc = -1;
+      auto issue_pv = [&](int j) {
+        const int f = f0 + j, s = j & 1;
+        const int bh = f / nq, b = bh / p.H;
+        int k_lim;
+        const int nk = 2 * key_chunks(b, k_lim);             // 16-key MMA steps
+        if (bh != pv_bh) {
+          pv_bh = bh;
+          ++pv_kc;
+          mbar_wait(&v_full[pv_kc & 1], (pv_kc >> 1) & 1);
+        }
+        mbar_wait(&p_ready[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(sV + (pv_kc & 1) * PP_KV_BYTES), 1024, 1024);
+        const uint32_t tbuf = tmem_base + uint32_t(s * 256);
+        for (int k = 0; k < nk; ++k)
+          umma_f16_ts(tbuf + 128u, tbuf + uint32_t(k * 8), v_desc + uint64_t(k * (2048 >> 4)), idesc_O, k != 0);
+        umma_commit(&o_full[s]);
+        if (j + 1 == n || (f + 1) / nq != bh) umma_commit(&v_free[pv_kc & 1]);
+      };
+      for (int it = 0; it < n; ++it) {
+        const int f = f0 + it, s = it & 1;
+        const int bh = f / nq;
+        if (it >= 2) mbar_wait(&o_read[s], ((it >> 1) - 1) & 1);   // P and O of item it-2 have left this TMEM buffer
+        mbar_wait(&q_full[s], (it >> 1) & 1);
+        if (bh != s_bh) {
+          s_bh = bh;
+          ++s_kc;
+          mbar_wait(&k_full[s_kc & 1], (s_kc >> 1) & 1);
+        }
+        tc_fence_after();
+        const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(sQ + s * PP_Q_BYTES), 16, 1024);
+        const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(sK + (s_kc & 1) * PP_KV_BYTES), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          umma_f16_ss(tmem_base + s * 256, q_desc + uint64_t(k * 2), k_desc + uint64_t(k * 2), idesc_S, k != 0);
+        umma_commit(&s_full[s]);
+        umma_commit(&q_free[s]);
+        if (it + 1 == n || (f + 1) / nq != bh) umma_commit(&k_free[s_kc & 1]);
+        if (it >= 1) issue_pv(it - 1);
+      }
+      issue_pv(n - 1);
+    }
+  } else {
+    // ---------------- softmax warpgroups: thread <-> query row of every second item
+    const int wg = warp >> 2, w4 = warp & 3;
+    const uint32_t tS = tmem_base + uint32_t(wg * 256) + (uint32_t(w4 * 32) << 16);
+    uint4* th = reinterpret_cast<uint4*>(sO + wg * TS_STAGE_BYTES + w4 * 4096);
+    uint4* tl = reinterpret_cast<uint4*>(sO + wg * TS_STAGE_BYTES + 16384 + w4 * 4096);
+    for (int it = wg; it < n; it += 2) {
+      const int f = f0 + it;
+      const int bh = f / nq, qt = f - bh * nq;
+      const int b = bh / p.H, h = bh - b * p.H;
+      int k_lim;
+      const int nch = key_chunks(b, k_lim);
+      const uint32_t par = (it >> 1) & 1;
+      mbar_wait(&s_full[wg], par);
+      tc_fence_after();
+      // pass 1: row maximum (the loads of chunk c+1 are in flight while chunk c is reduced)
+      float mx = -INFINITY;
+      {
+        uint32_t ra[32], rb[32];
+        auto red = [&](const uint32_t (&rr)[32], int c) {
+          const int nv = k_lim - c * 32;
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          if (nv >= 32) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(rr[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], i < nv ? __uint_as_float(rr[i]) : -INFINITY);
+          }
+          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+        };
+        tmem_ld32(tS, ra);
+#pragma unroll 1
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < nch) tmem_ld32(tS + uint32_t((c + 1) * 32), rb);
+          red(ra, c);
+          if (c + 1 < nch) {
+            tmem_ld_wait();
+            if (c + 2 < nch) tmem_ld32(tS + uint32_t((c + 2) * 32), ra);
+            red(rb, c + 1);
+          }
+        }
+      }
+      const float m_s = mx * p.scale_log2;                  // scale > 0; -inf when no key is valid
+      // pass 2: probabilities -> packed f16 over the consumed half of the score row, row sum in fp32.
+      // The f32 -> f16x2 conversion instruction shares the MUFU pipe with the exponentials at 4 lanes per clock and
+      // scheduler (ncu: 256 EX2 + 128 F2FP per row = the whole XU pipe time of the kernel), so the exponentials are
+      // taken 2^-112 smaller: ex2.ftz then yields exactly the f16 normal range as f32 values whose exponent field is
+      // already the f16 one (anything below 2^-14 of the row maximum flushes to zero), and round-to-nearest packing is
+      // one integer multiply-add per value (bits * 8 + 0x8000: the f16 pattern lands in the upper half) plus one byte
+      // permute per pair.  The row sum is taken over the same scaled values and rescaled once.
+      const float m_use = ((m_s == -INFINITY) ? 0.f : m_s) + 112.f;
+      float lsum = 0.f;
+      {
+        uint32_t ra[32], rb[32];
+        auto emit = [&](const uint32_t (&rr)[32], int c) {
+          const int nv = k_lim - c * 32;
+          uint32_t packed[16];
+          float l4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (nv >= 32) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = fast_exp2(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_use));
+              const float p1 = fast_exp2(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -m_use));
+              l4[(i >> 1) & 3] += p0 + p1;
+              packed[i >> 1] = __byte_perm(__float_as_uint(p0) * 8u + 0x8000u, __float_as_uint(p1) * 8u + 0x8000u, 0x7632);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float p0 = i < nv ? fast_exp2(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_use)) : 0.f;
+              const float p1 = i + 1 < nv ? fast_exp2(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -m_use)) : 0.f;
+              l4[(i >> 1) & 3] += p0 + p1;
+              packed[i >> 1] = __byte_perm(__float_as_uint(p0) * 8u + 0x8000u, __float_as_uint(p1) * 8u + 0x8000u, 0x7632);
+            }
+          }
+          lsum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+          tmem_st16(tS + uint32_t(c * 16), packed);
+        };
+        tmem_ld32(tS, ra);
+#pragma unroll 1
+        for (int c = 0; c < nch; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < nch) tmem_ld32(tS + uint32_t((c + 1) * 32), rb);
+          emit(ra, c);
+          if (c + 1 < nch) {
+            tmem_ld_wait();
+            if (c + 2 < nch) tmem_ld32(tS + uint32_t((c + 2) * 32), ra);
+            emit(rb, c + 1);
+          }
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();     // our TMEM stores (P) and loads (S) are ordered before the MMAs that read P / write O
+      mbar_arrive(&p_ready[wg]);
+
+      mbar_wait(&o_full[wg], par);
+      tc_fence_after();
+      float o[DH];
+      {
+        uint32_t ra[32], rb[32];
+        tmem_ld32(tS + 128u, ra);
+        tmem_ld32(tS + 160u, rb);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          o[i] = __uint_as_float(ra[i]);
+          o[32 + i] = __uint_as_float(rb[i]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&o_read[wg]);   // the TMEM buffer may take S of item it+2
+      // stage the warp's 32 rows x 64 dims as f16 hi (and lo) rows of 128 B (128-byte swizzle) in its private tiles;
+      // one lane stores the boxes, rows >= Sq are clipped by the tensor map
+      if (lane == 0) tma_store_wait_read<0>();            // the boxes of item it-2 have been read
+      __syncwarp();
+      const float inv = lsum > 0.f ? 1.f / (lsum * 0x1p112f) : 0.f;   // fully masked row -> zeros (layers.py:25)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int d = 8 * j;
+        uint4 t;
+        t.x = pack_f16x2(o[d + 0] * inv, o[d + 1] * inv);
+        t.y = pack_f16x2(o[d + 2] * inv, o[d + 3] * inv);
+        t.z = pack_f16x2(o[d + 4] * inv, o[d + 5] * inv);
+        t.w = pack_f16x2(o[d + 6] * inv, o[d + 7] * inv);
+        th[lane * 8 + (j ^ (lane & 7))] = t;
+        if (p.out_lo_off)
+          tl[lane * 8 + (j ^ (lane & 7))] =
+              make_uint4(f16x2_residual(o[d + 0] * inv, o[d + 1] * inv, t.x), f16x2_residual(o[d + 2] * inv, o[d + 3] * inv, t.y),
+                         f16x2_residual(o[d + 4] * inv, o[d + 5] * inv, t.z), f16x2_residual(o[d + 6] * inv, o[d + 7] * inv, t.w));
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        const int row0 = qt * BQ + w4 * 32;
+        if (row0 < p.Sq) {
+          tma_store_3d(&tmO, th, h * DH, row0, b);
+          if (p.out_lo_off) tma_store_3d(&tmO, tl, p.out_lo_off + h * DH, row0, b);
+          tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_read<0>();   // the staging tiles are read before the CTA (and its shared memory) goes away
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------ naive cross-check (CUDA cores, one warp per row)
 __global__ void attn_naive_kernel(AttnParams p) {
   const int qi = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -735,10 +1029,19 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t s) {
     if (int rc = device_props(&n_sm, nullptr)) return rc;
     const int nq = (p.Sq + BQ - 1) / BQ;
     const long long items = (long long)p.B * p.H * nq;
+    static const bool ts_off = [] {
+      const char* e = std::getenv("ASR_B200_ATTN_PP");
+      return e && e[0] == '1';      // "1": probabilities through shared memory (attn_pp_kernel)
+    }();
     if (items < (1ll << 30)) {
-      if (int rc = ensure_dyn_smem((const void*)attn_pp_kernel, PP_SMEM)) return rc;
       const int grid = (int)std::min<long long>(n_sm, items);
-      attn_pp_kernel<<<grid, 320, PP_SMEM, s>>>(tmQ, tmK, tmV, tmO, d, nq, (int)items);
+      if (ts_off) {
+        if (int rc = ensure_dyn_smem((const void*)attn_pp_kernel, PP_SMEM)) return rc;
+        attn_pp_kernel<<<grid, 320, PP_SMEM, s>>>(tmQ, tmK, tmV, tmO, d, nq, (int)items);
+      } else {
+        if (int rc = ensure_dyn_smem((const void*)attn_ts_kernel, TS_SMEM)) return rc;
+        attn_ts_kernel<<<grid, 320, TS_SMEM, s>>>(tmQ, tmK, tmV, tmO, d, nq, (int)items);
+      }
       ASR_CUDA_OK(cudaGetLastError());
       ASR_LAUNCHED(1);
       return 0;
