@@ -4,7 +4,10 @@
 // Quirks reproduced: scale is a runtime float (= emb_dim**-0.5, layers.py:20), fully masked rows give zeros
 // (nan_to_num, layers.py:25).
 //
-// sm_100a design, one CTA per (q-tile of 128 rows, head, utterance), dh = 64:
+// Two sm_100a kernels, dh = 64.  attn_ts_kernel (below, persistent, probabilities in tensor memory) takes every launch
+// with at most 256 keys and index-only masks (k_lens): the encoder's self attention and the cross attention of the
+// teacher-forced decoder.  attn_tc_kernel takes the rest (causal, byte / dense masks, longer sequences):
+// one CTA per (q-tile of 128 rows, head, utterance):
 //   warp 4 (one elected thread): TMA loads of the Q tile and a 2-deep K/V tile ring (SWIZZLE_128B), and all
 //                                tcgen05.mma issue: S = Q K^T (M128 N128 K64) and O_j = P V (M128 N64 K128,
 //                                V consumed in place as an MN-major B operand, P from shared memory).
@@ -44,6 +47,7 @@ struct AttnDev {
   const uint8_t* dense_mask;
   int mask_B;
   int tma_out;    // the output goes by tensor stores (tmO valid)
+  uint32_t eight; // = 8, as a run-time value: keeps "bits * 8 + 0x8000" an integer multiply-add (see attn_ts_kernel)
 };
 
 __global__ void __launch_bounds__(160, 2)
@@ -338,310 +342,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
 // ------------------------------------------------------------------ persistent ping-pong kernel (Sk <= 256)
 // The encoder's self attention (T' = 250 keys at 10 s) and the teacher-forced decoder's cross attention see at most
-// 256 keys: a whole score row fits one TMEM accumulator (128 x 256 fp32), so there is no online rescaling, and the
-// kernel is bound by the exponentials (256 per row on the MUFU pipe) - provided the tensor pipe, TMA and the softmax of
-// ANOTHER tile keep running meanwhile.  One persistent CTA per SM walks a contiguous range of (utterance, head, q tile)
+// 256 keys: a whole score row fits one TMEM accumulator (128 x 256 fp32), so there is no online rescaling and K / V are
+// loaded once per (utterance, head).  One persistent CTA per SM walks a contiguous range of (utterance, head, q tile)
 // items:
-//   warp 8 (one thread): TMA producer.  Q tile per item; the K and V tiles (256 rows, zero-filled past Sk) only when
-//                        (utterance, head) changes.  Single buffers: Q / K are free again once S = Q K^T has completed,
-//                        long before the next item's MMAs can be issued; V once the last P V of its head has.
+//   warp 8 (one thread): TMA producer.  Q tile per item (2 stages); the K and V tiles (256 rows, zero-filled past Sk,
+//                        2 stages each) only when (utterance, head) changes: it runs two items / one head ahead.
 //   warp 9 (one thread): tcgen05.mma issue.  S_i = Q K^T (M128 N256 K64) into TMEM buffer i & 1, then O_{i-1} = P V
-//                        (M128 N64, K = the used keys) into the first 64 columns of buffer (i-1) & 1 (S is dead by then).
+//                        (M128 N64, K = the used keys, TS form: P from TMEM) into columns [128, 192) of buffer (i-1) & 1.
 //   warps 0-3 / 4-7:     two softmax warpgroups, even / odd items (ping-pong): thread <-> query row, pass 1 row maximum,
-//                        pass 2 exp2 -> f16 P tile in shared memory (K-major, 128-byte swizzle) + fp32 row sum; then
-//                        O from TMEM, 1/l, f16 hi | lo rows staged in the (free) P tile and stored by TMA.
-// While warpgroup A waits for P V / the next S, warpgroup B's exponentials own the MUFU pipe and vice versa.
+//                        pass 2 exp2 -> packed f16 probabilities written over the consumed half of the thread's own score
+//                        row (tcgen05.st: chunk c of P lands on columns the thread has already read) + fp32 row sum;
+//                        then O from TMEM, 1/l, f16 hi | lo rows staged in the warp's private tiles and stored by TMA
+//                        (the store of item i drains under the softmax of item i+2).
+// While warpgroup A waits for P V / the next S, warpgroup B's exponentials run and vice versa.  The probabilities never
+// touch shared memory (an earlier version kept a 64 KB f16 P tile per warpgroup there, which left room for single Q / K /
+// V buffers only and put every tensor-map load on the critical path: 57 us per layer at 256 utterances against 51 us).
 constexpr int PP_KEYS = 256;
 constexpr int PP_Q_BYTES = BQ * DH * 2;            // 16 KB
 constexpr int PP_KV_BYTES = PP_KEYS * DH * 2;      // 32 KB
-constexpr int PP_P_BYTES = BQ * PP_KEYS * 2;       // 64 KB
-constexpr size_t PP_SMEM = PP_Q_BYTES + 2 * PP_KV_BYTES + 2 * PP_P_BYTES + 256;   // 208.25 KB: one CTA per SM
-
-template <int ID>
-__device__ __forceinline__ void named_bar_sync_128() {
-  asm volatile("bar.sync %0, 128;" ::"n"(ID) : "memory");
-}
-
-__global__ void __launch_bounds__(320, 1)
-attn_pp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, AttnDev p, int nq,
-               int n_items) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + PP_Q_BYTES;
-  uint8_t* sV = sK + PP_KV_BYTES;
-  uint8_t* sP = sV + PP_KV_BYTES;                   // [2] x 64 KB: four 64-key K blocks of 16 KB each
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * PP_P_BYTES);
-  uint64_t* qk_full = bars + 0;
-  uint64_t* qk_free = bars + 1;
-  uint64_t* v_full = bars + 2;
-  uint64_t* v_free = bars + 3;
-  uint64_t* s_full = bars + 4;    // [2]
-  uint64_t* p_ready = bars + 6;   // [2]
-  uint64_t* o_full = bars + 8;    // [2]
-  uint64_t* o_read = bars + 10;   // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int f0 = int((long long)blockIdx.x * n_items / gridDim.x);
-  const int f1 = int((long long)(blockIdx.x + 1) * n_items / gridDim.x);
-  const int n = f1 - f0;
-
-  if (threadIdx.x == 0) {
-    mbar_init(qk_full, 1);
-    mbar_init(qk_free, 1);
-    mbar_init(v_full, 1);
-    mbar_init(v_free, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 128);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&o_read[i], 128);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 9) {
-    tmem_alloc(tmem_ptr, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  // keys in use for utterance b (>= 1 so that P V always runs: an empty row then sums to l = 0 and stores zeros)
-  auto key_chunks = [&](int b, int& k_lim) {
-    k_lim = p.Sk;
-    if (p.k_lens) k_lim = min(k_lim, max(0, p.k_lens[b]));
-    return max(1, (k_lim + 31) >> 5);
-  };
-
-  if (warp == 8) {
-    if (lane == 0 && n > 0) {
-      tma_prefetch_desc(&tmQ);
-      tma_prefetch_desc(&tmK);
-      tma_prefetch_desc(&tmV);
-      int prev_bh = -1, vcnt = 0;
-      for (int it = 0; it < n; ++it) {
-        const int f = f0 + it;
-        const int bh = f / nq, qt = f - bh * nq;
-        const int b = bh / p.H, h = bh - b * p.H;
-        const bool newkv = bh != prev_bh;
-        if (it > 0) mbar_wait(qk_free, (it - 1) & 1);
-        mbar_expect_tx(qk_full, newkv ? PP_Q_BYTES + PP_KV_BYTES : PP_Q_BYTES);
-        tma_load_3d(sQ, &tmQ, qk_full, h * DH, qt * BQ, b);
-        if (newkv) {
-          tma_load_3d(sK, &tmK, qk_full, h * DH, 0, b);
-          if (vcnt > 0) mbar_wait(v_free, (vcnt - 1) & 1);
-          mbar_expect_tx(v_full, PP_KV_BYTES);
-          tma_load_3d(sV, &tmV, v_full, h * DH, 0, b);
-          ++vcnt;
-        }
-        prev_bh = bh;
-      }
-    }
-  } else if (warp == 9) {
-    if (lane == 0 && n > 0) {
-      constexpr uint32_t idesc_S = umma_idesc_f16(BQ, PP_KEYS, 0, 0);
-      constexpr uint32_t idesc_O = umma_idesc_f16(BQ, DH, 0, 1);   // B = V tile, MN-major
-      const uint64_t q_desc = umma_smem_desc_sw128(smem_u32(sQ), 16, 1024);
-      const uint64_t k_desc = umma_smem_desc_sw128(smem_u32(sK), 16, 1024);
-      const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(sV), 1024, 1024);
-      int pv_bh = -1, vcnt = 0;
-      auto issue_pv = [&](int j) {
-        const int f = f0 + j, s = j & 1;
-        const int bh = f / nq, b = bh / p.H;
-        int k_lim;
-        const int nk = 2 * key_chunks(b, k_lim);             // 16-key MMA steps
-        if (bh != pv_bh) {
-          mbar_wait(v_full, vcnt & 1);
-          ++vcnt;
-          pv_bh = bh;
-        }
-        mbar_wait(&p_ready[s], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t sPs = smem_u32(sP + s * PP_P_BYTES);
-        for (int k = 0; k < nk; ++k) {
-          const uint64_t p_desc = umma_smem_desc_sw128(sPs + (k >> 2) * (BQ * 128), 16, 1024) + uint64_t((k & 3) * 2);
-          umma_f16_ss(tmem_base + s * 256, p_desc, v_desc + uint64_t(k * (2048 >> 4)), idesc_O, k != 0);
-        }
-        umma_commit(&o_full[s]);
-        if (j + 1 == n || (f + 1) / nq != bh) umma_commit(v_free);
-      };
-      for (int it = 0; it < n; ++it) {
-        const int s = it & 1;
-        if (it >= 2) mbar_wait(&o_read[s], ((it >> 1) - 1) & 1);   // O of item it-2 has left this TMEM buffer
-        mbar_wait(qk_full, it & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k)
-          umma_f16_ss(tmem_base + s * 256, q_desc + uint64_t(k * 2), k_desc + uint64_t(k * 2), idesc_S, k != 0);
-        umma_commit(&s_full[s]);
-        umma_commit(qk_free);
-        if (it >= 1) issue_pv(it - 1);
-      }
-      issue_pv(n - 1);
-    }
-  } else {
-    // ---------------- softmax warpgroups: thread <-> query row of every second item
-    const int wg = warp >> 2, w4 = warp & 3;
-    const int r = w4 * 32 + lane;
-    const uint32_t tS = tmem_base + uint32_t(wg * 256) + (uint32_t(w4 * 32) << 16);
-    uint8_t* sPw = sP + wg * PP_P_BYTES;
-    for (int it = wg; it < n; it += 2) {
-      const int f = f0 + it;
-      const int bh = f / nq, qt = f - bh * nq;
-      const int b = bh / p.H, h = bh - b * p.H;
-      int k_lim;
-      const int nch = key_chunks(b, k_lim);
-      const uint32_t par = (it >> 1) & 1;
-      mbar_wait(&s_full[wg], par);
-      tc_fence_after();
-      // pass 1: row maximum (the loads of chunk c+1 are in flight while chunk c is reduced)
-      float mx = -INFINITY;
-      {
-        uint32_t ra[32], rb[32];
-        auto red = [&](const uint32_t (&rr)[32], int c) {
-          const int nv = k_lim - c * 32;
-          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          if (nv >= 32) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(rr[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], i < nv ? __uint_as_float(rr[i]) : -INFINITY);
-          }
-          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
-        };
-        tmem_ld32(tS, ra);
-#pragma unroll 1
-        for (int c = 0; c < nch; c += 2) {
-          tmem_ld_wait();
-          if (c + 1 < nch) tmem_ld32(tS + uint32_t((c + 1) * 32), rb);
-          red(ra, c);
-          if (c + 1 < nch) {
-            tmem_ld_wait();
-            if (c + 2 < nch) tmem_ld32(tS + uint32_t((c + 2) * 32), ra);
-            red(rb, c + 1);
-          }
-        }
-      }
-      const float m_s = mx * p.scale_log2;                  // scale > 0; -inf when no key is valid
-      const float m_use = (m_s == -INFINITY) ? 0.f : m_s;
-      // pass 2: probabilities -> f16 P tile (swizzled K-major A operand), row sum in fp32
-      float lsum = 0.f;
-      {
-        uint32_t ra[32], rb[32];
-        auto emit = [&](const uint32_t (&rr)[32], int c) {
-          const int nv = k_lim - c * 32;
-          uint32_t packed[16];
-          float l4[4] = {0.f, 0.f, 0.f, 0.f};
-          if (nv >= 32) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = fast_exp2(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_use));
-              const float p1 = fast_exp2(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -m_use));
-              l4[(i >> 1) & 3] += p0 + p1;
-              packed[i >> 1] = pack_f16x2(p0, p1);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float p0 = i < nv ? fast_exp2(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_use)) : 0.f;
-              const float p1 = i + 1 < nv ? fast_exp2(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -m_use)) : 0.f;
-              l4[(i >> 1) & 3] += p0 + p1;
-              packed[i >> 1] = pack_f16x2(p0, p1);
-            }
-          }
-          lsum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-          uint8_t* blk = sPw + (c >> 1) * (BQ * 128) + r * 128;
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const int chunk = (c & 1) * 4 + q4;
-            *reinterpret_cast<uint4*>(blk + ((chunk ^ (r & 7)) << 4)) =
-                make_uint4(packed[q4 * 4 + 0], packed[q4 * 4 + 1], packed[q4 * 4 + 2], packed[q4 * 4 + 3]);
-          }
-        };
-        tmem_ld32(tS, ra);
-#pragma unroll 1
-        for (int c = 0; c < nch; c += 2) {
-          tmem_ld_wait();
-          if (c + 1 < nch) tmem_ld32(tS + uint32_t((c + 1) * 32), rb);
-          emit(ra, c);
-          if (c + 1 < nch) {
-            tmem_ld_wait();
-            if (c + 2 < nch) tmem_ld32(tS + uint32_t((c + 2) * 32), ra);
-            emit(rb, c + 1);
-          }
-        }
-      }
-      fence_proxy_async();   // P writes (generic proxy) -> UMMA operand reads (async proxy)
-      tc_fence_before();     // our TMEM loads are ordered before the MMAs that overwrite S with O
-      mbar_arrive(&p_ready[wg]);
-
-      mbar_wait(&o_full[wg], par);
-      tc_fence_after();
-      float o[DH];
-      {
-        uint32_t ra[32], rb[32];
-        tmem_ld32(tS, ra);
-        tmem_ld32(tS + 32u, rb);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          o[i] = __uint_as_float(ra[i]);
-          o[32 + i] = __uint_as_float(rb[i]);
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(&o_read[wg]);   // the TMEM buffer may take S of item it+2
-      // The P tile is free (P V has completed): stage the warp's 32 rows x 64 dims as f16 hi (and lo) rows of 128 B
-      // (128-byte swizzle); one lane stores the boxes, rows >= Sq are clipped by the tensor map.
-      const float inv = lsum > 0.f ? 1.f / lsum : 0.f;   // fully masked row -> zeros (layers.py:25)
-      uint4* th = reinterpret_cast<uint4*>(sPw + w4 * 4096);
-      uint4* tl = reinterpret_cast<uint4*>(sPw + 16384 + w4 * 4096);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int d = 8 * j;
-        uint4 t;
-        t.x = pack_f16x2(o[d + 0] * inv, o[d + 1] * inv);
-        t.y = pack_f16x2(o[d + 2] * inv, o[d + 3] * inv);
-        t.z = pack_f16x2(o[d + 4] * inv, o[d + 5] * inv);
-        t.w = pack_f16x2(o[d + 6] * inv, o[d + 7] * inv);
-        th[lane * 8 + (j ^ (lane & 7))] = t;
-        if (p.out_lo_off)
-          tl[lane * 8 + (j ^ (lane & 7))] =
-              make_uint4(f16x2_residual(o[d + 0] * inv, o[d + 1] * inv, t.x), f16x2_residual(o[d + 2] * inv, o[d + 3] * inv, t.y),
-                         f16x2_residual(o[d + 4] * inv, o[d + 5] * inv, t.z), f16x2_residual(o[d + 6] * inv, o[d + 7] * inv, t.w));
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        const int row0 = qt * BQ + w4 * 32;
-        if (row0 < p.Sq) {
-          tma_store_3d(&tmO, th, h * DH, row0, b);
-          if (p.out_lo_off) tma_store_3d(&tmO, tl, p.out_lo_off + h * DH, row0, b);
-          tma_store_commit();
-          tma_store_wait_read<0>();
-        }
-      }
-      if (wg == 0) named_bar_sync_128<1>(); else named_bar_sync_128<2>();   // every warp's staging tiles have been read before anyone writes P again
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
-}
-
-// ------------------------------------------------------------------ the same schedule with P in tensor memory
-// attn_ts_kernel: the probabilities never touch shared memory.  A softmax thread overwrites the first half of its own
-// score row in TMEM with the packed f16 probabilities (tcgen05.st; chunk c of P lands on columns the thread has already
-// consumed) and P V is issued in the TS form (A operand from TMEM, O into columns [128, 192) of the same buffer).  The
-// 128 KB of P tiles this frees buy double buffers for Q, K and V - the producer runs two items and one head ahead, so
-// no tensor-map load sits on the critical path - and private output staging tiles per warp (the TMA store of item i
-// drains under the softmax of item i+2).
 constexpr int TS_STAGE_BYTES = 2 * BQ * DH * 2;     // 32 KB per warpgroup: f16 hi rows | lo rows of one 128-query tile
 constexpr size_t TS_SMEM = 2 * PP_Q_BYTES + 4 * PP_KV_BYTES + 2 * TS_STAGE_BYTES + 256;   // 224.25 KB
 
@@ -829,9 +547,10 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // scheduler (ncu: 256 EX2 + 128 F2FP per row = the whole XU pipe time of the kernel), so the exponentials are
       // taken 2^-112 smaller: ex2.ftz then yields exactly the f16 normal range as f32 values whose exponent field is
       // already the f16 one (anything below 2^-14 of the row maximum flushes to zero), and round-to-nearest packing is
-      // one integer multiply-add per value (bits * 8 + 0x8000: the f16 pattern lands in the upper half) plus one byte
+      // one integer multiply-add (FMA pipe) per value (bits * 8 + 0x8000: the f16 pattern lands in the upper half) plus one byte
       // permute per pair.  The row sum is taken over the same scaled values and rescaled once.
       const float m_use = ((m_s == -INFINITY) ? 0.f : m_s) + 112.f;
+      const uint32_t k8 = p.eight;   // not a literal: ptxas turns "* 8" into LEA, which ncu shows on the XU pipe as well
       float lsum = 0.f;
       {
         uint32_t ra[32], rb[32];
@@ -845,7 +564,7 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               const float p0 = fast_exp2(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_use));
               const float p1 = fast_exp2(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -m_use));
               l4[(i >> 1) & 3] += p0 + p1;
-              packed[i >> 1] = __byte_perm(__float_as_uint(p0) * 8u + 0x8000u, __float_as_uint(p1) * 8u + 0x8000u, 0x7632);
+              packed[i >> 1] = __byte_perm(__float_as_uint(p0) * k8 + 0x8000u, __float_as_uint(p1) * k8 + 0x8000u, 0x7632);
             }
           } else {
 #pragma unroll
@@ -853,7 +572,7 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               const float p0 = i < nv ? fast_exp2(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_use)) : 0.f;
               const float p1 = i + 1 < nv ? fast_exp2(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -m_use)) : 0.f;
               l4[(i >> 1) & 3] += p0 + p1;
-              packed[i >> 1] = __byte_perm(__float_as_uint(p0) * 8u + 0x8000u, __float_as_uint(p1) * 8u + 0x8000u, 0x7632);
+              packed[i >> 1] = __byte_perm(__float_as_uint(p0) * k8 + 0x8000u, __float_as_uint(p1) * k8 + 0x8000u, 0x7632);
             }
           }
           lsum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
@@ -997,6 +716,7 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t s) {
   d.scale_log2 = p.scale * 1.4426950408889634f;
   d.causal = p.causal; d.k_lens = p.k_lens; d.q_valid = p.q_valid; d.k_valid = p.k_valid;
   d.dense_mask = p.dense_mask; d.mask_B = p.mask_B;
+  d.eight = 8;
   CUtensorMap tmO = tmQ;
   d.tma_out = 0;
   {
@@ -1029,19 +749,10 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t s) {
     if (int rc = device_props(&n_sm, nullptr)) return rc;
     const int nq = (p.Sq + BQ - 1) / BQ;
     const long long items = (long long)p.B * p.H * nq;
-    static const bool ts_off = [] {
-      const char* e = std::getenv("ASR_B200_ATTN_PP");
-      return e && e[0] == '1';      // "1": probabilities through shared memory (attn_pp_kernel)
-    }();
     if (items < (1ll << 30)) {
       const int grid = (int)std::min<long long>(n_sm, items);
-      if (ts_off) {
-        if (int rc = ensure_dyn_smem((const void*)attn_pp_kernel, PP_SMEM)) return rc;
-        attn_pp_kernel<<<grid, 320, PP_SMEM, s>>>(tmQ, tmK, tmV, tmO, d, nq, (int)items);
-      } else {
-        if (int rc = ensure_dyn_smem((const void*)attn_ts_kernel, TS_SMEM)) return rc;
-        attn_ts_kernel<<<grid, 320, TS_SMEM, s>>>(tmQ, tmK, tmV, tmO, d, nq, (int)items);
-      }
+      if (int rc = ensure_dyn_smem((const void*)attn_ts_kernel, TS_SMEM)) return rc;
+      attn_ts_kernel<<<grid, 320, TS_SMEM, s>>>(tmQ, tmK, tmV, tmO, d, nq, (int)items);
       ASR_CUDA_OK(cudaGetLastError());
       ASR_LAUNCHED(1);
       return 0;

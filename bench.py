@@ -161,7 +161,8 @@ def attention_tensor_pipe():
     if not files:
         return None
     p = files[-1]
-    rows = [r for r in (l.split("|") for l in open(p) if "attn_tc_kernel" in l) if len(r) >= 12]   # per-launch rows only
+    rows = [r for r in (l.split("|") for l in open(p) if "attn_ts_kernel" in l or "attn_tc_kernel" in l)
+            if len(r) >= 12]   # per-launch rows only
     if not rows:
         return None
     try:
@@ -169,7 +170,8 @@ def attention_tensor_pipe():
         us = [float(r[4]) for r in rows]
     except (ValueError, IndexError):
         return None
-    return {"kernel": "attn_tc_kernel (encoder self attention)",
+    return {"kernel": "attn_ts_kernel (encoder self attention)" if any("attn_ts" in r[1] for r in rows)
+            else "attn_tc_kernel (encoder self attention)",
             "tensor_pipe_active_pct": round(sum(pct) / len(pct), 1), "us_per_launch": round(sum(us) / len(us), 1),
             "source": os.path.relpath(p, ROOT) + " (ncu --set full, cold cache; quoted, not measured in this run)"}
 

@@ -216,7 +216,7 @@ def test_attention_nomask(B, H, Sq, Sk, impl):
 
 @pytest.mark.parametrize("B,H,Sq,Sk", [(40, 4, 250, 250), (37, 4, 128, 250), (9, 8, 300, 256), (150, 1, 77, 33)])
 def test_attention_persistent_many_items(B, H, Sq, Sk):
-    """Sk <= 256 without causal / byte masks runs the persistent ping-pong kernel (attn_pp_kernel): every CTA walks
+    """Sk <= 256 without causal / byte masks runs the persistent ping-pong kernel (attn_ts_kernel): every CTA walks
     several (utterance, head, q tile) items, K/V are reloaded when the head changes, ragged key lengths incl. 0
     (reference layers.py:20-27 with the key-padding mask of dataset.py:53-55)."""
     q, k, v = (rnd(B, S, H, 64, seed=40 + i, scale=1.5, dtype=torch.float16) for i, S in enumerate((Sq, Sk, Sk)))
