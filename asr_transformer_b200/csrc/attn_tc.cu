@@ -17,6 +17,7 @@
 #include "kernels.h"
 #include "ptx.cuh"
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 namespace asr {
@@ -341,38 +342,61 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------ persistent ping-pong kernel (Sk <= 256)
-// The encoder's self attention (T' = 250 keys at 10 s) and the teacher-forced decoder's cross attention see at most
-// 256 keys: a whole score row fits one TMEM accumulator (128 x 256 fp32), so there is no online rescaling and K / V are
-// loaded once per (utterance, head).  One persistent CTA per SM walks a contiguous range of (utterance, head, q tile)
-// items:
-//   warp 8 (one thread): TMA producer.  Q tile per item (2 stages); the K and V tiles (256 rows, zero-filled past Sk,
-//                        2 stages each) only when (utterance, head) changes: it runs two items / one head ahead.
-//   warp 9 (one thread): tcgen05.mma issue.  S_i = Q K^T (M128 N256 K64) into TMEM buffer i & 1, then O_{i-1} = P V
-//                        (M128 N64, K = the used keys, TS form: P from TMEM) into columns [128, 192) of buffer (i-1) & 1.
-//   warps 0-3 / 4-7:     two softmax warpgroups, even / odd items (ping-pong): thread <-> query row, pass 1 row maximum,
-//                        pass 2 exp2 -> packed f16 probabilities written over the consumed half of the thread's own score
-//                        row (tcgen05.st: chunk c of P lands on columns the thread has already read) + fp32 row sum;
-//                        then O from TMEM, 1/l, f16 hi | lo rows staged in the warp's private tiles and stored by TMA
-//                        (the store of item i drains under the softmax of item i+2).
-// While warpgroup A waits for P V / the next S, warpgroup B's exponentials run and vice versa.  The probabilities never
-// touch shared memory (an earlier version kept a 64 KB f16 P tile per warpgroup there, which left room for single Q / K /
-// V buffers only and put every tensor-map load on the critical path: 57 us per layer at 256 utterances against 51 us).
+// attn_ts_kernel.  The encoder's self attention (T' = 250 keys at 10 s) and the teacher-forced decoder's cross attention
+// see at most 256 keys: a whole score row fits one TMEM accumulator (128 x 256 fp32), so there is no online rescaling and
+// K / V are loaded once per (utterance, head).  One persistent CTA per SM (18 warps) walks a contiguous range of
+// (utterance, head, q tile) items:
+//   warp 16 (one thread): TMA producer.  Q tile per item (2 stages); the K and V tiles (256 rows, zero-filled past Sk,
+//                         2 stages each) only when (utterance, head) changes: it runs two items / one head ahead.
+//   warp 17 (one thread): tcgen05.mma issue.  S_i = Q K^T (M128 N256 K64) into TMEM buffer i & 1 (256 columns each), then
+//                         O_{i-1} = P V (M128 N64, K = the used keys, TS form: P from TMEM) into columns [64,128) of
+//                         buffer (i-1) & 1.
+//   warps 0-7 / 8-15:     two softmax groups, even / odd items (ping-pong).  Within a group warps [0,4) take score columns
+//                         [0,128) of the 128 rows and warps [4,8) columns [128,256) (TMEM lanes are tied to warp id % 4, so
+//                         both warps of a row see the same lanes): pass 1 row maximum, pass 2 exp2 -> packed f16
+//                         probabilities written by tcgen05.st over score columns the thread has consumed itself (half 0:
+//                         columns [0,64), half 1: [128,192)) + fp32 row sum; the halves exchange maxima and sums through
+//                         shared memory (256-thread named barriers); then each half reads 32 of the 64 O columns, scales
+//                         by 1/l and stages f16 hi | lo rows in the group's tiles, stored by TMA (the store of item i
+//                         drains under the softmax of item i+2).
+// While group A waits for P V / the next S, group B's exponentials run and vice versa.  The probabilities never touch
+// shared memory: earlier versions of this kernel measured, per layer at 256 utterances (legacy kernel: 70 us):
+//   57 us  one thread per row (8 softmax warps), 64 KB f16 P tile per group in shared memory, single Q / K / V buffers
+//          (every tensor-map load on the critical path);
+//   51 us  P in TMEM, double-buffered Q / K / V, private staging; f32 -> f16x2 by integer ops or F2FP, LEA or IMAD: same
+//          time - neither the XU pipe (50-63 %) nor issue slots (0.45 per cycle) bound it, the chain softmax -> P V ->
+//          epilogue -> next S of a group did (clock64 timeline, -DASR_ATTN_TIMELINE);
+//   47 us  16 softmax warps (this layout); 46 us with the item coordinates of the MMA thread tracked incrementally (its
+//          integer divisions sat between a barrier wait and the tcgen05.mma issue) and the P V issue loop unrolled.
+// Timeline of a group in steady state (cycles): pass 1 1.2 k, pass 2 3.2 k (XU floor 2.0 k), wait for P V 1.5 k (16 TS-form
+// MMAs of N = 64 take 1.1 k), epilogue 1.0 k, loop 0.4 k: 7.5 k per two items against 4.1 k of exponentials.
 constexpr int PP_KEYS = 256;
 constexpr int PP_Q_BYTES = BQ * DH * 2;            // 16 KB
 constexpr int PP_KV_BYTES = PP_KEYS * DH * 2;      // 32 KB
-constexpr int TS_STAGE_BYTES = 2 * BQ * DH * 2;     // 32 KB per warpgroup: f16 hi rows | lo rows of one 128-query tile
-constexpr size_t TS_SMEM = 2 * PP_Q_BYTES + 4 * PP_KV_BYTES + 2 * TS_STAGE_BYTES + 256;   // 224.25 KB
+constexpr int TS_STAGE_BYTES = 2 * BQ * DH * 2;    // 32 KB per group: f16 hi rows | lo rows of one 128-query tile
+constexpr size_t TS_SMEM = 2 * PP_Q_BYTES + 4 * PP_KV_BYTES + 2 * TS_STAGE_BYTES + 256 + 2048;   // 226.25 KB (barriers, exchange)
 
-__global__ void __launch_bounds__(320, 1)
+#ifdef ASR_ATTN_TIMELINE   // diagnostic build: clock64 stamps of CTA 0 (softmax warp 0 of group 0, MMA thread), printed by the launcher
+__device__ long long g_attn_tl[2 * 32 * 8];
+#define TL(role, it, k) do { if (blockIdx.x == 0 && (it) < 32) g_attn_tl[((role) * 32 + (it)) * 8 + (k)] = clock64(); } while (0)
+#else
+#define TL(role, it, k) do { } while (0)
+#endif
+__device__ __forceinline__ void group_sync(int g) {   // the 256 softmax threads of group g (named barriers 1 and 2)
+  if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else asm volatile("bar.sync 2, 256;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(576, 1)
 attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, AttnDev p, int nq,
-               int n_items) {
+                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, AttnDev p, int nq,
+                 int n_items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u)) __trap();
   uint8_t* sQ = smem;                               // [2] x 16 KB
   uint8_t* sK = sQ + 2 * PP_Q_BYTES;                // [2] x 32 KB
   uint8_t* sV = sK + 2 * PP_KV_BYTES;               // [2] x 32 KB
-  uint8_t* sO = sV + 2 * PP_KV_BYTES;               // [2 warpgroups] x 32 KB
+  uint8_t* sO = sV + 2 * PP_KV_BYTES;               // [2 groups] x 32 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * TS_STAGE_BYTES);
   uint64_t* q_full = bars + 0;     // every barrier below: [2]
   uint64_t* q_free = bars + 2;
@@ -385,6 +409,7 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* o_full = bars + 16;
   uint64_t* o_read = bars + 18;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+  float* xch = reinterpret_cast<float*>(bars + 22);   // [2 groups][2 halves][128 rows] row maxima, then row sums (2 KB)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -401,13 +426,13 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       mbar_init(&v_full[i], 1);
       mbar_init(&v_free[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 128);
+      mbar_init(&p_ready[i], 256);
       mbar_init(&o_full[i], 1);
-      mbar_init(&o_read[i], 128);
+      mbar_init(&o_read[i], 256);
     }
     fence_barrier_init();
   }
-  if (warp == 9) {
+  if (warp == 17) {
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
   }
@@ -416,14 +441,13 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // keys in use for utterance b, in 32-key chunks (>= 1: an empty row then sums to l = 0 and stores zeros)
   auto key_chunks = [&](int b, int& k_lim) {
     k_lim = p.Sk;
     if (p.k_lens) k_lim = min(k_lim, max(0, p.k_lens[b]));
     return max(1, (k_lim + 31) >> 5);
   };
 
-  if (warp == 8) {
+  if (warp == 16) {
     if (lane == 0 && n > 0) {
       tma_prefetch_desc(&tmQ);
       tma_prefetch_desc(&tmK);
@@ -450,37 +474,54 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     if (lane == 0 && n > 0) {
       constexpr uint32_t idesc_S = umma_idesc_f16(BQ, PP_KEYS, 0, 0);
       constexpr uint32_t idesc_O = umma_idesc_f16(BQ, DH, 0, 1);   // B = V tile, MN-major
-      int s_bh = -1, s_kc = -1, pv_bh = -1, pv_kc = -1;
+      // This thread shares its scheduler with four softmax warps, so every instruction it executes between a barrier
+      // wait and a tcgen05.mma costs tens of cycles of the chain softmax -> P V -> epilogue -> next S: the item
+      // coordinates are tracked incrementally (no divisions) and the P V issue loop is fully unrolled.
+      int s_kc = -1, pv_kc = -1;
+      const int bh0 = f0 / nq;
+      int s_qt = f0 - bh0 * nq, s_new = 1;                    // S side: q tile of item it, item starts a new (b, h)
+      int pv_qt = s_qt, pv_new = 1, pv_b = bh0 / p.H, pv_h = bh0 - pv_b * p.H;   // P V side, one item behind
       auto issue_pv = [&](int j) {
-        const int f = f0 + j, s = j & 1;
-        const int bh = f / nq, b = bh / p.H;
+        const int s = j & 1;
         int k_lim;
-        const int nk = 2 * key_chunks(b, k_lim);             // 16-key MMA steps
-        if (bh != pv_bh) {
-          pv_bh = bh;
+        const int nk = 2 * key_chunks(pv_b, k_lim);          // 16-key MMA steps
+        if (pv_new) {
           ++pv_kc;
           mbar_wait(&v_full[pv_kc & 1], (pv_kc >> 1) & 1);
         }
-        mbar_wait(&p_ready[s], (j >> 1) & 1);
-        tc_fence_after();
+        const bool last_of_head = j + 1 == n || pv_qt + 1 == nq;
         const uint64_t v_desc = umma_smem_desc_sw128(smem_u32(sV + (pv_kc & 1) * PP_KV_BYTES), 1024, 1024);
         const uint32_t tbuf = tmem_base + uint32_t(s * 256);
-        for (int k = 0; k < nk; ++k)
-          umma_f16_ts(tbuf + 128u, tbuf + uint32_t(k * 8), v_desc + uint64_t(k * (2048 >> 4)), idesc_O, k != 0);
+        TL(1, j, 3);
+        mbar_wait(&p_ready[s], (j >> 1) & 1);
+        TL(1, j, 4);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 16; ++k)   // P of keys [0,128) in columns [0,64), of keys [128,256) in columns [128,192)
+          if (k < nk)
+            umma_f16_ts(tbuf + 64u, tbuf + uint32_t(k < 8 ? k * 8 : 64 + k * 8), v_desc + uint64_t(k * (2048 >> 4)), idesc_O,
+                        k != 0);
         umma_commit(&o_full[s]);
-        if (j + 1 == n || (f + 1) / nq != bh) umma_commit(&v_free[pv_kc & 1]);
+        TL(1, j, 5);
+        if (last_of_head) umma_commit(&v_free[pv_kc & 1]);
+        pv_new = 0;
+        if (++pv_qt == nq) {
+          pv_qt = 0;
+          pv_new = 1;
+          if (++pv_h == p.H) { pv_h = 0; ++pv_b; }
+        }
       };
       for (int it = 0; it < n; ++it) {
-        const int f = f0 + it, s = it & 1;
-        const int bh = f / nq;
+        const int s = it & 1;
+        TL(1, it, 0);
         if (it >= 2) mbar_wait(&o_read[s], ((it >> 1) - 1) & 1);   // P and O of item it-2 have left this TMEM buffer
+        TL(1, it, 1);
         mbar_wait(&q_full[s], (it >> 1) & 1);
-        if (bh != s_bh) {
-          s_bh = bh;
+        if (s_new) {
           ++s_kc;
           mbar_wait(&k_full[s_kc & 1], (s_kc >> 1) & 1);
         }
@@ -492,32 +533,56 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           umma_f16_ss(tmem_base + s * 256, q_desc + uint64_t(k * 2), k_desc + uint64_t(k * 2), idesc_S, k != 0);
         umma_commit(&s_full[s]);
         umma_commit(&q_free[s]);
-        if (it + 1 == n || (f + 1) / nq != bh) umma_commit(&k_free[s_kc & 1]);
+        TL(1, it, 2);
+        if (it + 1 == n || s_qt + 1 == nq) umma_commit(&k_free[s_kc & 1]);
+        s_new = 0;
+        if (++s_qt == nq) { s_qt = 0; s_new = 1; }
         if (it >= 1) issue_pv(it - 1);
       }
       issue_pv(n - 1);
     }
   } else {
-    // ---------------- softmax warpgroups: thread <-> query row of every second item
-    const int wg = warp >> 2, w4 = warp & 3;
-    const uint32_t tS = tmem_base + uint32_t(wg * 256) + (uint32_t(w4 * 32) << 16);
-    uint4* th = reinterpret_cast<uint4*>(sO + wg * TS_STAGE_BYTES + w4 * 4096);
-    uint4* tl = reinterpret_cast<uint4*>(sO + wg * TS_STAGE_BYTES + 16384 + w4 * 4096);
-    for (int it = wg; it < n; it += 2) {
-      const int f = f0 + it;
-      const int bh = f / nq, qt = f - bh * nq;
-      const int b = bh / p.H, h = bh - b * p.H;
+    // ---------------- softmax: group g (items it = g mod 2), column half hf, rows 32 * w4 + lane
+    const int g = warp >> 3, hf = (warp >> 2) & 1, w4 = warp & 3;
+    const int r = w4 * 32 + lane;
+    const uint32_t tB = tmem_base + uint32_t(g * 256) + (uint32_t(w4 * 32) << 16);   // the group's TMEM buffer, own lanes
+    const uint32_t tS = tB + uint32_t(hf * 128);                                     // own score columns
+    float* xmine = xch + (g * 2 + hf) * 128 + r;
+    const float* xother = xch + (g * 2 + (hf ^ 1)) * 128 + r;
+    uint4* th = reinterpret_cast<uint4*>(sO + g * TS_STAGE_BYTES + w4 * 4096);
+    uint4* tl = reinterpret_cast<uint4*>(sO + g * TS_STAGE_BYTES + 16384 + w4 * 4096);
+    const uint32_t k8 = p.eight;
+    int qt, h, b;                                       // coordinates of item it, advanced by two items per iteration
+    {
+      const int f = f0 + g;
+      const int bh = f / nq;
+      qt = f - bh * nq;
+      b = bh / p.H;
+      h = bh - b * p.H;
+    }
+    auto advance = [&]() {
+      for (int u = 0; u < 2; ++u)
+        if (++qt == nq) {
+          qt = 0;
+          if (++h == p.H) { h = 0; ++b; }
+        }
+    };
+    for (int it = g; it < n; it += 2, advance()) {
       int k_lim;
-      const int nch = key_chunks(b, k_lim);
+      const int nch = min(4, key_chunks(b, k_lim) - 4 * hf);   // own 32-key chunks in use (<= 0: none)
+      const int k_off = hf * 128;
       const uint32_t par = (it >> 1) & 1;
-      mbar_wait(&s_full[wg], par);
+      const bool tl_on = warp == 0 && lane == 0;
+      if (tl_on) TL(0, it, 0);
+      mbar_wait(&s_full[g], par);
+      if (tl_on) TL(0, it, 1);
       tc_fence_after();
-      // pass 1: row maximum (the loads of chunk c+1 are in flight while chunk c is reduced)
+      // pass 1: row maximum over the own columns
       float mx = -INFINITY;
-      {
-        uint32_t ra[32], rb[32];
+      if (nch > 0) {
+        uint32_t ra[32];
         auto red = [&](const uint32_t (&rr)[32], int c) {
-          const int nv = k_lim - c * 32;
+          const int nv = k_lim - k_off - c * 32;
           float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
           if (nv >= 32) {
 #pragma unroll
@@ -528,34 +593,31 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
           mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
         };
-        tmem_ld32(tS, ra);
 #pragma unroll 1
-        for (int c = 0; c < nch; c += 2) {
+        for (int c = 0; c < nch; ++c) {   // four warps per scheduler hide the TMEM latency: no register double buffer
+          tmem_ld32(tS + uint32_t(c * 32), ra);
           tmem_ld_wait();
-          if (c + 1 < nch) tmem_ld32(tS + uint32_t((c + 1) * 32), rb);
           red(ra, c);
-          if (c + 1 < nch) {
-            tmem_ld_wait();
-            if (c + 2 < nch) tmem_ld32(tS + uint32_t((c + 2) * 32), ra);
-            red(rb, c + 1);
-          }
         }
       }
+      if (hf == 0 && lane == 0) tma_store_wait_read<0>();   // the boxes of item it-2 have left the staging tiles
+      *xmine = mx;
+      if (tl_on) TL(0, it, 2);
+      group_sync(g);
+      if (tl_on) TL(0, it, 3);
+      mx = fmaxf(mx, *xother);
       const float m_s = mx * p.scale_log2;                  // scale > 0; -inf when no key is valid
-      // pass 2: probabilities -> packed f16 over the consumed half of the score row, row sum in fp32.
-      // The f32 -> f16x2 conversion instruction shares the MUFU pipe with the exponentials at 4 lanes per clock and
-      // scheduler (ncu: 256 EX2 + 128 F2FP per row = the whole XU pipe time of the kernel), so the exponentials are
-      // taken 2^-112 smaller: ex2.ftz then yields exactly the f16 normal range as f32 values whose exponent field is
-      // already the f16 one (anything below 2^-14 of the row maximum flushes to zero), and round-to-nearest packing is
-      // one integer multiply-add (FMA pipe) per value (bits * 8 + 0x8000: the f16 pattern lands in the upper half) plus one byte
-      // permute per pair.  The row sum is taken over the same scaled values and rescaled once.
+      // The exponentials are taken 2^-112 smaller: ex2.ftz then yields exactly the f16 normal range as f32 values whose
+      // exponent field is already the f16 one (anything below 2^-14 of the row maximum flushes to zero), so round-to-
+      // nearest packing is one integer multiply-add per value (bits * 8 + 0x8000: the f16 pattern lands in the upper
+      // half) plus one byte permute per pair instead of an F2FP on the XU pipe the exponentials use; the row sum is
+      // taken over the same scaled values and rescaled once.
       const float m_use = ((m_s == -INFINITY) ? 0.f : m_s) + 112.f;
-      const uint32_t k8 = p.eight;   // not a literal: ptxas turns "* 8" into LEA, which ncu shows on the XU pipe as well
       float lsum = 0.f;
-      {
-        uint32_t ra[32], rb[32];
+      if (nch > 0) {
+        uint32_t ra[32];
         auto emit = [&](const uint32_t (&rr)[32], int c) {
-          const int nv = k_lim - c * 32;
+          const int nv = k_lim - k_off - c * 32;
           uint32_t packed[16];
           float l4[4] = {0.f, 0.f, 0.f, 0.f};
           if (nv >= 32) {
@@ -576,63 +638,55 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
           }
           lsum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-          tmem_st16(tS + uint32_t(c * 16), packed);
+          tmem_st16(tS + uint32_t(c * 16), packed);          // over own, consumed score columns
         };
-        tmem_ld32(tS, ra);
 #pragma unroll 1
-        for (int c = 0; c < nch; c += 2) {
+        for (int c = 0; c < nch; ++c) {
+          tmem_ld32(tS + uint32_t(c * 32), ra);
           tmem_ld_wait();
-          if (c + 1 < nch) tmem_ld32(tS + uint32_t((c + 1) * 32), rb);
           emit(ra, c);
-          if (c + 1 < nch) {
-            tmem_ld_wait();
-            if (c + 2 < nch) tmem_ld32(tS + uint32_t((c + 2) * 32), ra);
-            emit(rb, c + 1);
-          }
         }
       }
       tmem_st_wait();
-      tc_fence_before();     // our TMEM stores (P) and loads (S) are ordered before the MMAs that read P / write O
-      mbar_arrive(&p_ready[wg]);
-
-      mbar_wait(&o_full[wg], par);
-      tc_fence_after();
-      float o[DH];
-      {
-        uint32_t ra[32], rb[32];
-        tmem_ld32(tS + 128u, ra);
-        tmem_ld32(tS + 160u, rb);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          o[i] = __uint_as_float(ra[i]);
-          o[32 + i] = __uint_as_float(rb[i]);
-        }
-      }
       tc_fence_before();
-      mbar_arrive(&o_read[wg]);   // the TMEM buffer may take S of item it+2
-      // stage the warp's 32 rows x 64 dims as f16 hi (and lo) rows of 128 B (128-byte swizzle) in its private tiles;
-      // one lane stores the boxes, rows >= Sq are clipped by the tensor map
-      if (lane == 0) tma_store_wait_read<0>();            // the boxes of item it-2 have been read
-      __syncwarp();
+      mbar_arrive(&p_ready[g]);
+      if (tl_on) TL(0, it, 4);
+      group_sync(g);             // everyone has read the row maxima: the exchange slots take the row sums
+      *xmine = lsum;
+
+      mbar_wait(&o_full[g], par);
+      if (tl_on) TL(0, it, 5);
+      tc_fence_after();
+      uint32_t ro[32];
+      tmem_ld32(tB + 64u + uint32_t(hf * 32), ro);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&o_read[g]);   // the TMEM buffer may take S of item it+2
+      if (tl_on) TL(0, it, 6);
+      group_sync(g);             // row sums written
+      lsum += *xother;
       const float inv = lsum > 0.f ? 1.f / (lsum * 0x1p112f) : 0.f;   // fully masked row -> zeros (layers.py:25)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 4; ++j) {
         const int d = 8 * j;
+        const float o0 = __uint_as_float(ro[d + 0]) * inv, o1 = __uint_as_float(ro[d + 1]) * inv;
+        const float o2 = __uint_as_float(ro[d + 2]) * inv, o3 = __uint_as_float(ro[d + 3]) * inv;
+        const float o4 = __uint_as_float(ro[d + 4]) * inv, o5 = __uint_as_float(ro[d + 5]) * inv;
+        const float o6 = __uint_as_float(ro[d + 6]) * inv, o7 = __uint_as_float(ro[d + 7]) * inv;
         uint4 t;
-        t.x = pack_f16x2(o[d + 0] * inv, o[d + 1] * inv);
-        t.y = pack_f16x2(o[d + 2] * inv, o[d + 3] * inv);
-        t.z = pack_f16x2(o[d + 4] * inv, o[d + 5] * inv);
-        t.w = pack_f16x2(o[d + 6] * inv, o[d + 7] * inv);
-        th[lane * 8 + (j ^ (lane & 7))] = t;
+        t.x = pack_f16x2(o0, o1);
+        t.y = pack_f16x2(o2, o3);
+        t.z = pack_f16x2(o4, o5);
+        t.w = pack_f16x2(o6, o7);
+        const int ch = (hf * 4 + j) ^ (lane & 7);
+        th[lane * 8 + ch] = t;
         if (p.out_lo_off)
-          tl[lane * 8 + (j ^ (lane & 7))] =
-              make_uint4(f16x2_residual(o[d + 0] * inv, o[d + 1] * inv, t.x), f16x2_residual(o[d + 2] * inv, o[d + 3] * inv, t.y),
-                         f16x2_residual(o[d + 4] * inv, o[d + 5] * inv, t.z), f16x2_residual(o[d + 6] * inv, o[d + 7] * inv, t.w));
+          tl[lane * 8 + ch] = make_uint4(f16x2_residual(o0, o1, t.x), f16x2_residual(o2, o3, t.y),
+                                         f16x2_residual(o4, o5, t.z), f16x2_residual(o6, o7, t.w));
       }
       fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
+      group_sync(g);             // both halves of every row are staged
+      if (hf == 0 && lane == 0) {
         const int row0 = qt * BQ + w4 * 32;
         if (row0 < p.Sq) {
           tma_store_3d(&tmO, th, h * DH, row0, b);
@@ -640,12 +694,13 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           tma_store_commit();
         }
       }
+      if (tl_on) TL(0, it, 7);
     }
-    if (lane == 0) tma_store_wait_read<0>();   // the staging tiles are read before the CTA (and its shared memory) goes away
+    if (hf == 0 && lane == 0) tma_store_wait_read<0>();   // the staging tiles are read before the CTA goes away
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
+  if (warp == 17) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------ naive cross-check (CUDA cores, one warp per row)
@@ -752,7 +807,24 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t s) {
     if (items < (1ll << 30)) {
       const int grid = (int)std::min<long long>(n_sm, items);
       if (int rc = ensure_dyn_smem((const void*)attn_ts_kernel, TS_SMEM)) return rc;
-      attn_ts_kernel<<<grid, 320, TS_SMEM, s>>>(tmQ, tmK, tmV, tmO, d, nq, (int)items);
+      attn_ts_kernel<<<grid, 576, TS_SMEM, s>>>(tmQ, tmK, tmV, tmO, d, nq, (int)items);
+#ifdef ASR_ATTN_TIMELINE
+        {
+          static long long tl[2 * 32 * 8];
+          cudaStreamSynchronize(s);
+          cudaMemcpyFromSymbol(tl, g_attn_tl, sizeof(tl));
+          const long long t0 = tl[32 * 8];   // MMA thread, item 0, stamp 0
+          for (int it = 0; it < 16; ++it) {
+            fprintf(stderr, "it %2d  mma:", it);
+            for (int k = 0; k < 6; ++k) fprintf(stderr, " %7lld", tl[(32 + it) * 8 + k] - t0);
+            if (it % 2 == 0) {
+              fprintf(stderr, "   wg0:");
+              for (int k = 0; k < 8; ++k) fprintf(stderr, " %7lld", tl[it * 8 + k] - t0);
+            }
+            fprintf(stderr, "\n");
+          }
+        }
+#endif
       ASR_CUDA_OK(cudaGetLastError());
       ASR_LAUNCHED(1);
       return 0;
