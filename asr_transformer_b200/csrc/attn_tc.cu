@@ -48,7 +48,6 @@ struct AttnDev {
   const uint8_t* dense_mask;
   int mask_B;
   int tma_out;    // the output goes by tensor stores (tmO valid)
-  uint32_t eight; // = 8, as a run-time value: keeps "bits * 8 + 0x8000" an integer multiply-add (see attn_ts_kernel)
 };
 
 __global__ void __launch_bounds__(160, 2)
@@ -363,13 +362,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 // shared memory: earlier versions of this kernel measured, per layer at 256 utterances (legacy kernel: 70 us):
 //   57 us  one thread per row (8 softmax warps), 64 KB f16 P tile per group in shared memory, single Q / K / V buffers
 //          (every tensor-map load on the critical path);
-//   51 us  P in TMEM, double-buffered Q / K / V, private staging; f32 -> f16x2 by integer ops or F2FP, LEA or IMAD: same
-//          time - neither the XU pipe (50-63 %) nor issue slots (0.45 per cycle) bound it, the chain softmax -> P V ->
-//          epilogue -> next S of a group did (clock64 timeline, -DASR_ATTN_TIMELINE);
-//   47 us  16 softmax warps (this layout); 46 us with the item coordinates of the MMA thread tracked incrementally (its
-//          integer divisions sat between a barrier wait and the tcgen05.mma issue) and the P V issue loop unrolled.
-// Timeline of a group in steady state (cycles): pass 1 1.2 k, pass 2 3.2 k (XU floor 2.0 k), wait for P V 1.5 k (16 TS-form
-// MMAs of N = 64 take 1.1 k), epilogue 1.0 k, loop 0.4 k: 7.5 k per two items against 4.1 k of exponentials.
+//   51 us  P in TMEM, double-buffered Q / K / V, private staging;
+//   47 us  16 softmax warps (this layout); 45-46 us with the item coordinates of the MMA thread tracked incrementally
+//          (its integer divisions sat between a barrier wait and the tcgen05.mma issue) and the P V issue loop unrolled.
+// What bounds it is the instruction stream of the softmax warps, not a pipe: ncu shows the XU pipe 50-70 % busy and 0.5
+// issue slots per cycle used, but every variant that ADDS instructions to remove XU work is slower - exponentials scaled
+// by 2^-112 and packed to f16 by integer ops instead of F2FP (LEA / IMAD + PRMT: +0 ... +2 us), a degree-4 polynomial
+// exp2 on the FMA pipe for 4 / 5 / 7 / 8 / 10 of every 16 columns (+2 / +2 / +4 / +4 / +6 us).
+// Timeline of a group in steady state (clock64 stamps, -DASR_ATTN_TIMELINE), cycles: pass 1 1.2 k, pass 2 3.2 k, wait for
+// P V 1.5 k (the 16 TS-form MMAs of N = 64 take 1.1 k), epilogue 1.0 k, loop 0.4 k: 7.5 k per two items.
 constexpr int PP_KEYS = 256;
 constexpr int PP_Q_BYTES = BQ * DH * 2;            // 16 KB
 constexpr int PP_KV_BYTES = PP_KEYS * DH * 2;      // 32 KB
@@ -382,6 +383,26 @@ __device__ long long g_attn_tl[2 * 32 * 8];
 #else
 #define TL(role, it, k) do { } while (0)
 #endif
+// packed fp32 pairs (fma.rn.f32x2 / add.rn.f32x2, sm_100): the softmax warps are bound by their instruction count, and a
+// pair op is one issue slot for two score columns
+__device__ __forceinline__ uint64_t f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_split(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ void group_sync(int g) {   // the 256 softmax threads of group g (named barriers 1 and 2)
   if (g == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
   else asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -551,7 +572,6 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const float* xother = xch + (g * 2 + (hf ^ 1)) * 128 + r;
     uint4* th = reinterpret_cast<uint4*>(sO + g * TS_STAGE_BYTES + w4 * 4096);
     uint4* tl = reinterpret_cast<uint4*>(sO + g * TS_STAGE_BYTES + 16384 + w4 * 4096);
-    const uint32_t k8 = p.eight;
     int qt, h, b;                                       // coordinates of item it, advanced by two items per iteration
     {
       const int f = f0 + g;
@@ -607,13 +627,9 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (tl_on) TL(0, it, 3);
       mx = fmaxf(mx, *xother);
       const float m_s = mx * p.scale_log2;                  // scale > 0; -inf when no key is valid
-      // The exponentials are taken 2^-112 smaller: ex2.ftz then yields exactly the f16 normal range as f32 values whose
-      // exponent field is already the f16 one (anything below 2^-14 of the row maximum flushes to zero), so round-to-
-      // nearest packing is one integer multiply-add per value (bits * 8 + 0x8000: the f16 pattern lands in the upper
-      // half) plus one byte permute per pair instead of an F2FP on the XU pipe the exponentials use; the row sum is
-      // taken over the same scaled values and rescaled once.
-      const float m_use = ((m_s == -INFINITY) ? 0.f : m_s) + 112.f;
+      const float m_use = (m_s == -INFINITY) ? 0.f : m_s;
       float lsum = 0.f;
+      const uint64_t sc2 = f32x2(p.scale_log2, p.scale_log2), nm2 = f32x2(-m_use, -m_use);
       if (nch > 0) {
         uint32_t ra[32];
         auto emit = [&](const uint32_t (&rr)[32], int c) {
@@ -621,20 +637,23 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           uint32_t packed[16];
           float l4[4] = {0.f, 0.f, 0.f, 0.f};
           if (nv >= 32) {
+            uint64_t a2[2] = {0ull, 0ull};                   // two pairs of partial sums
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              const float p0 = fast_exp2(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_use));
-              const float p1 = fast_exp2(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -m_use));
-              l4[(i >> 1) & 3] += p0 + p1;
-              packed[i >> 1] = __byte_perm(__float_as_uint(p0) * k8 + 0x8000u, __float_as_uint(p1) * k8 + 0x8000u, 0x7632);
+              float x0, x1;
+              f32x2_split(fma_f32x2(f32x2(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1])), sc2, nm2), x0, x1);
+              const float p0 = fast_exp2(x0), p1 = fast_exp2(x1);
+              a2[(i >> 1) & 1] = add_f32x2(a2[(i >> 1) & 1], f32x2(p0, p1));
+              packed[i >> 1] = pack_f16x2(p0, p1);
             }
+            f32x2_split(add_f32x2(a2[0], a2[1]), l4[0], l4[1]);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
               const float p0 = i < nv ? fast_exp2(fmaf(__uint_as_float(rr[i]), p.scale_log2, -m_use)) : 0.f;
               const float p1 = i + 1 < nv ? fast_exp2(fmaf(__uint_as_float(rr[i + 1]), p.scale_log2, -m_use)) : 0.f;
               l4[(i >> 1) & 3] += p0 + p1;
-              packed[i >> 1] = __byte_perm(__float_as_uint(p0) * k8 + 0x8000u, __float_as_uint(p1) * k8 + 0x8000u, 0x7632);
+              packed[i >> 1] = pack_f16x2(p0, p1);
             }
           }
           lsum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
@@ -665,7 +684,7 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (tl_on) TL(0, it, 6);
       group_sync(g);             // row sums written
       lsum += *xother;
-      const float inv = lsum > 0.f ? 1.f / (lsum * 0x1p112f) : 0.f;   // fully masked row -> zeros (layers.py:25)
+      const float inv = lsum > 0.f ? 1.f / lsum : 0.f;   // fully masked row -> zeros (layers.py:25)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int d = 8 * j;
@@ -771,7 +790,6 @@ int launch_attention_tc(const AttnParams& p, cudaStream_t s) {
   d.scale_log2 = p.scale * 1.4426950408889634f;
   d.causal = p.causal; d.k_lens = p.k_lens; d.q_valid = p.q_valid; d.k_valid = p.k_valid;
   d.dense_mask = p.dense_mask; d.mask_B = p.mask_B;
-  d.eight = 8;
   CUtensorMap tmO = tmQ;
   d.tma_out = 0;
   {
