@@ -630,13 +630,18 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const float m_use = (m_s == -INFINITY) ? 0.f : m_s;
       float lsum = 0.f;
       const uint64_t sc2 = f32x2(p.scale_log2, p.scale_log2), nm2 = f32x2(-m_use, -m_use);
+      // The chunk that straddles Sk (250 keys: 26 of 32 columns) would take the predicated path below, ~2.6x the
+      // instructions of a full chunk, and the other half of the row waits for it at the exchange.  When nothing but the
+      // end of the sequence masks it, the K and V rows past Sk are the tensor map's zero fill: those scores are exactly
+      // 0, their probabilities meet zero V rows, and their known contribution 2^-m each is taken out of the row sum.
+      const bool tail_zero = k_lim == p.Sk && m_use > -64.f;
       if (nch > 0) {
         uint32_t ra[32];
         auto emit = [&](const uint32_t (&rr)[32], int c) {
           const int nv = k_lim - k_off - c * 32;
           uint32_t packed[16];
           float l4[4] = {0.f, 0.f, 0.f, 0.f};
-          if (nv >= 32) {
+          if (nv >= 32 || tail_zero) {
             uint64_t a2[2] = {0ull, 0ull};                   // two pairs of partial sums
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
@@ -647,6 +652,7 @@ attn_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               packed[i >> 1] = pack_f16x2(p0, p1);
             }
             f32x2_split(add_f32x2(a2[0], a2[1]), l4[0], l4[1]);
+            if (nv < 32) l4[2] = -float(32 - nv) * fast_exp2(-m_use);   // the columns past Sk: score 0, V row 0
           } else {
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
