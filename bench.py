@@ -14,10 +14,11 @@ the public API with pinned HOST buffers, H2D of the spectrogram and D2H of the t
 baseline/_ref/ that tools/install_ref.sh fills; kind "reference") on the host cores, one utterance per step; only when
 baseline/_ref is absent does it fall back to the oracle's literal restatement of model.py:125-151 (kind "port").
 
-Beside the headline (C2, weak scaling) the same run reports three short extra passes under their own keys: `c3_strong`
+Beside the headline (C2, weak scaling) the same run reports four short extra passes under their own keys: `c3_strong`
 (BASELINE config 3: paper-size model, global batch 256 split over the N GPUs), `c5_masks` (config 5: widened model,
-mixed-length batch with key-padding masks on, length-balanced over the ranks) and `cross_n_tokens` (every N decodes
-the same seed-1 global batch; SHA-256 of the gathered tokens against the N=1 value in tests/golden/).
+mixed-length batch with key-padding masks on, length-balanced over the ranks), `c4_longform` (config 4: 30 s
+utterances, 384 greedy steps, 64 utterances per GPU) and `cross_n_tokens` (every N decodes the same seed-1 global
+batch; SHA-256 of the gathered tokens against the N=1 value in tests/golden/).
 """
 from __future__ import annotations
 
@@ -54,7 +55,7 @@ def parse():
     ap.add_argument("--no-profile", action="store_true", help="skip the per-kernel / per-phase profiling pass")
     ap.add_argument("--decode-mode", default="", choices=["", "cluster", "graph", "eager"],
                     help="sets ASR_B200_DECODE (default: the library default, cluster)")
-    ap.add_argument("--no-extras", action="store_true", help="skip the c3_strong / c5_masks / cross_n_tokens passes")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c3_strong / c5_masks / c4_longform / cross_n_tokens passes")
     return ap.parse_args()
 
 
@@ -661,6 +662,22 @@ def run_extras(model, dev, rank, world, dist, barrier):
                        "frames_processed_frac": round(float(sum(int(x.shape[-1]) * x.shape[0] for x, _ in items)) /
                                                       (64 * 1000), 3)}
     del m5, items
+    torch.cuda.empty_cache()
+
+    # ---- C4: long-form (30 s utterances -> 749 encoder frames, 384 greedy steps), 64 utterances per GPU.  The encoder's
+    # self attention sees 749 keys here (attn_tc_kernel, online softmax), the cluster decoder 749 cross keys per utterance.
+    c4 = W.CONFIGS["C4"]
+    m4 = W.build_model(c4, dev)
+    x4 = W.structured_spectrum(c4.batch, c4.frames, c4.input_dim, seed=40 + rank).to(dev)
+
+    def step4():
+        m4.greedy_decode(x4)
+    ms4 = timed(step4, steps=1)
+    out["c4_longform"] = {"workload": "C4: 12 enc / 6 dec, d_model 256, %d utterances of 30 s per GPU (T' = %d), greedy "
+                                      "decode %d steps, inputs resident" % (c4.batch, c4.encoder_seq_len, c4.decoder_seq_len),
+                          "value": c4.batch * world / (ms4 / 1e3), "unit": UNIT, "ms_per_step": round(ms4, 3),
+                          "scaling": "weak"}
+    del m4, x4
     torch.cuda.empty_cache()
     return out
 
