@@ -1526,7 +1526,7 @@ const Instance kInstances[] = {
 #if ASR_NCW == 8
     ASR_INST(4, 256, 64, 2), ASR_INST(4, 256, 64, 4), ASR_INST(4, 256, 64, 8),     // C1-C4: d_model 256, FFN 1024
     ASR_INST(2, 128, 128, 2), ASR_INST(2, 128, 128, 4), ASR_INST(2, 128, 128, 8),  // T0: d_model 128, FFN 256
-    ASR_INST(8, 256, 32, 2), ASR_INST(8, 256, 32, 4),                              // C5: d_model 512, FFN 2048
+    ASR_INST(8, 256, 32, 2), ASR_INST(8, 256, 32, 4), ASR_INST(8, 256, 32, 8),     // C5: d_model 512, FFN 2048
 #else
     ASR_INST(4, 256, 64, 2), ASR_INST(4, 256, 64, 4),                              // (experiment: 4 consumer warps)
 #endif

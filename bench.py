@@ -632,11 +632,10 @@ def run_extras(model, dev, rank, world, dist, barrier):
     torch.cuda.empty_cache()
 
     # ---- C5: widened model, mixed-length batch (len ~ U{400..1000}) with key-padding masks ON, 64 utterances per GPU,
-    # length-balanced over the ranks, length-bucketed into batches of 32 (each padded to its own longest utterance).
-    # Bucket size = the trade between encoder padding and decode launches (tools/prof_c5.py, one B200, 64 utterances):
-    # buckets of 16 -> 4 launches, 53.3 ms; 32 -> 2 launches, 34.7 ms; 64 -> 1 launch, 34.3 ms (clusters of 8 CTAs hold 4
-    # utterances: 16 clusters no longer fit one wave).  A decode launch costs ~12-15 ms whatever it holds; the whole
-    # encode side is 5-6 ms.
+    # length-balanced over the ranks, ONE padded batch per GPU.  Bucket size = the trade between encoder padding and decode
+    # launches (tools/prof_c5.py, one B200, 64 utterances): a decode launch costs 12-15 ms whatever it holds, the whole
+    # encode side 5-6 ms.  Buckets of 16 -> 4 launches, 53.3 ms; 32 -> 2 launches, 34.7 ms; 64 -> 1 launch, 27.7 ms (8
+    # utterances per cluster of 8 CTAs; before that instance existed 64 utterances took two waves of clusters, 34.3 ms).
     c5 = W.CONFIGS["C5"]
     m5 = W.build_model(c5, dev)
     G = 64 * world
@@ -644,7 +643,7 @@ def run_extras(model, dev, rank, world, dist, barrier):
     lens = torch.randint(400, 1001, (G,), generator=g)
     mine = balanced_assignment(lens.tolist(), world)[rank]
     items = []
-    for b in bucket_by_length([int(lens[i]) for i in mine], 32):
+    for b in bucket_by_length([int(lens[i]) for i in mine], 64):
         idx = [mine[j] for j in b]
         ln = lens[idx]
         T = int(ln.max())
@@ -657,7 +656,7 @@ def run_extras(model, dev, rank, world, dist, barrier):
     ms5 = timed(step5)
     out["c5_masks"] = {"workload": "C5: 12 enc / 6 dec, d_model 512, 8 heads, FFN 2048; %d utterances per GPU, lengths "
                                    "U{400..1000} frames, key-padding masks on (encoder self attention + decoder cross "
-                                   "attention), balanced_assignment over %d rank(s), 2 length buckets of 32" % (64, world),
+                                   "attention), balanced_assignment over %d rank(s), one padded batch per GPU (one decode launch)" % (64, world),
                        "value": G / (ms5 / 1e3), "unit": UNIT, "ms_per_step": round(ms5, 3), "scaling": "weak",
                        "frames_processed_frac": round(float(sum(int(x.shape[-1]) * x.shape[0] for x, _ in items)) /
                                                       (64 * 1000), 3)}
